@@ -1,0 +1,200 @@
+/* neuralcodecs_cuda.h -- C ABI of libneuralcodecs_cuda.so
+ *
+ * Blackwell (sm_100a) backend for the codec encode/decode hot path of
+ * DillionLowry/NeuralCodecs.  A `NeuralCodecs.Cuda` C# project binds these entry
+ * points through P/Invoke ([LibraryImport]); see INTEGRATION.md.  Every function cites
+ * the reference interface it replaces (paths relative to
+ * /root/reference/NeuralCodecs.Torch/ unless stated otherwise).
+ *
+ * Conventions
+ *  - plain C, no exceptions cross the boundary: every call returns nc_status and sets
+ *    a thread-local message readable through nc_last_error().
+ *  - host arrays are row-major fp32 / int64 exactly as the reference's tensors:
+ *    audio [B,1,L], latents z [B,C,T], codes [B,nq,T] (int64).
+ *  - the CALLER allocates every output (sizes from the *_query_shapes calls); the
+ *    library owns device weights and workspaces per handle.
+ *  - a handle is bound to one CUDA device and is not re-entrant (one thread at a time,
+ *    matching the reference's de-facto contract: Models/DAC.cs:354,381 mutate global
+ *    state in LoadWeights; nothing is synchronised).  Different handles are independent.
+ *  - there is NO CPU fallback: without a usable CUDA device nc_create fails with
+ *    NC_CUDA_UNAVAILABLE (ref: Utils/TorchUtils.cs:97-99 "CUDA requested but not
+ *    available").
+ */
+#ifndef NEURALCODECS_CUDA_H_
+#define NEURALCODECS_CUDA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define NC_API __declspec(dllexport)
+#else
+#define NC_API __attribute__((visibility("default")))
+#endif
+
+typedef struct nc_handle_s* nc_handle;
+
+/* Status codes; the C# layer maps them onto the reference's exception conventions
+ * (NeuralCodecs.Core/Exceptions/*.cs; Models/DAC.cs:53,146,207,347-388):
+ *   INVALID_ARGUMENT -> ArgumentException        FILE_NOT_FOUND -> FileNotFoundException
+ *   BAD_WEIGHTS / SHAPE_MISMATCH -> InvalidOperationException("Failed to load ... weights")
+ *   CUDA_UNAVAILABLE -> InvalidOperationException("CUDA requested but not available")
+ *   CUDA_ERROR / OUT_OF_MEMORY / INTERNAL -> CodecException(codec, CodecOperation, msg) */
+typedef enum nc_status {
+  NC_OK = 0,
+  NC_INVALID_ARGUMENT = 1,
+  NC_FILE_NOT_FOUND = 2,
+  NC_BAD_WEIGHTS = 3,
+  NC_SHAPE_MISMATCH = 4,
+  NC_CUDA_UNAVAILABLE = 5,
+  NC_CUDA_ERROR = 6,
+  NC_OUT_OF_MEMORY = 7,
+  NC_INTERNAL = 8,
+  NC_UNSUPPORTED = 9
+} nc_status;
+
+typedef enum nc_codec_kind { NC_CODEC_DAC = 1, NC_CODEC_SNAC = 2, NC_CODEC_ENCODEC = 3 } nc_codec_kind;
+
+#define NC_MAX_RATES 8
+
+/* Flat mirror of Config/DAC/DACConfig.cs:8-100 (fields the model constructor reads,
+ * Models/DAC.cs:51-93).  latent_dim = 0 means "encoder_dim * 2^n_encoder_rates". */
+typedef struct nc_dac_config {
+  uint32_t struct_size; /* = sizeof(nc_dac_config) */
+  int32_t sample_rate;
+  int32_t encoder_dim;
+  int32_t n_encoder_rates;
+  int32_t encoder_rates[NC_MAX_RATES];
+  int32_t decoder_dim;
+  int32_t n_decoder_rates;
+  int32_t decoder_rates[NC_MAX_RATES];
+  int32_t n_codebooks;
+  int32_t codebook_size;
+  int32_t codebook_dim;
+  int32_t latent_dim;
+} nc_dac_config;
+
+/* Flat mirror of Config/SNAC/SNACConfig.cs:11-153 (Models/SNAC.cs:34-63). */
+typedef struct nc_snac_config {
+  uint32_t struct_size;
+  int32_t sample_rate;
+  int32_t encoder_dim;
+  int32_t n_encoder_rates;
+  int32_t encoder_rates[NC_MAX_RATES];
+  int32_t decoder_dim;
+  int32_t n_decoder_rates;
+  int32_t decoder_rates[NC_MAX_RATES];
+  int32_t latent_dim; /* 0 = encoder_dim * 2^n_encoder_rates */
+  int32_t attn_window_size; /* 0 = no LocalMHA (24 kHz preset) */
+  int32_t codebook_size;
+  int32_t codebook_dim;
+  int32_t n_vq_strides;
+  int32_t vq_strides[NC_MAX_RATES];
+  int32_t noise;     /* bool */
+  int32_t depthwise; /* bool */
+} nc_snac_config;
+
+/* Flat mirror of Config/Encodec/EncodecConfig.cs:6-153 for the 24 kHz mono causal
+ * weight-norm preset (Models/Encodec.cs:46-90). */
+typedef struct nc_encodec_config {
+  uint32_t struct_size;
+  int32_t sample_rate;
+  int32_t channels;
+  int32_t n_filters;
+  int32_t dimension;
+  int32_t n_ratios;
+  int32_t ratios[NC_MAX_RATES]; /* decoder order, e.g. 8,5,4,2 */
+  int32_t n_residual_layers;
+  int32_t lstm_layers;
+  int32_t codebook_size;
+  int32_t n_quantizers; /* layers constructed (32 for 24 kHz) */
+  int32_t causal;       /* bool */
+} nc_encodec_config;
+
+/* -- library ---------------------------------------------------------------------- */
+NC_API const char* nc_version(void);
+/* thread-local description of the last failure on this thread ("" if none) */
+NC_API const char* nc_last_error(void);
+/* number of usable sm_100 devices (0 when CUDA is unavailable) */
+NC_API int nc_device_count(void);
+
+/* -- lifecycle -------------------------------------------------------------------- */
+/* replaces: model constructors reached through ModelRegistry.CreateModel<TModel,TConfig>
+ * (NeuralCodecs.Core/Loading/ModelRegistry.cs:35-74): new DAC(cfg) Models/DAC.cs:51,
+ * new SNAC(cfg) Models/SNAC.cs:34, new Encodec(cfg) Models/Encodec.cs:46.
+ * cfg points at the nc_*_config matching `kind`; device_index = DeviceConfiguration.Index
+ * (NeuralCodecs.Core/Configuration/DeviceConfiguration.cs:7-17). */
+NC_API nc_status nc_create(nc_codec_kind kind, const void* cfg, size_t cfg_size, int device_index,
+                           nc_handle* out);
+/* replaces: IDisposable.Dispose on the model (Models/DAC.cs:328-337). */
+NC_API nc_status nc_destroy(nc_handle h);
+/* replaces: INeuralCodec.LoadWeights(path) (NeuralCodecs.Core/INeuralCodec.cs:8-20;
+ * Models/DAC.cs:345-389, Models/SNAC.cs:200-246, Models/Encodec.cs:348-402).  Reads a
+ * .safetensors file in the reference's key layout for the codec (DAC: HF DacModel layout
+ * translated by Config/DAC/StateDictNameConverter.cs:40-65,274-376) and folds
+ * weight-norm once, in fp32, with the reference's epsilon placement. */
+NC_API nc_status nc_load_weights(nc_handle h, const char* utf8_path);
+/* test hook: supply one named tensor from host memory instead of a file.  dtype: 0 = f32,
+ * 1 = i64.  Call nc_finalize_weights when all tensors are set. */
+NC_API nc_status nc_set_tensor(nc_handle h, const char* name, int dtype, int rank, const int64_t* shape,
+                               const void* data);
+NC_API nc_status nc_finalize_weights(nc_handle h);
+/* engine options (strings), e.g. "encoder_precision" / "decoder_precision" =
+ * "fp32" | "tf32" | "3xtf32"; "max_workspace_mb" = "<n>"; "profile" = "0|1". */
+NC_API nc_status nc_set_option(nc_handle h, const char* key, const char* value);
+
+/* -- DAC -------------------------------------------------------------------------- */
+/* DAC.Preprocess length algebra (Models/DAC.cs:141-154): padded length and frame count. */
+NC_API nc_status nc_dac_query_shapes(nc_handle h, int64_t length, int64_t* padded_length, int64_t* frames,
+                                     int32_t* latent_dim, int32_t* n_codebooks, int32_t* codebook_dim);
+/* replaces: DAC.Encode(Tensor audio, int? nQuantizers, int? sampleRate) Models/DAC.cs:163-181
+ * (and EncodeAudio :188-198, Encode(float[]) :205-224 which return z only).
+ * audio [B,1,L]; sample_rate 0 = model rate, otherwise must equal it (ArgumentException in
+ * the ref, Models/DAC.cs:144-149); n_quantizers 0 = all.  Outputs (each nullable):
+ * z [B,latent,T] fp32, codes [B,nq,T] int64, latents [B,nq*codebook_dim,T] fp32. */
+NC_API nc_status nc_dac_encode(nc_handle h, const float* audio, int32_t batch, int64_t length,
+                               int32_t sample_rate, int32_t n_quantizers, float* z, int64_t* codes,
+                               float* latents, int64_t* frames_out);
+/* replaces: DAC.Decode(Tensor z) Models/DAC.cs:231-234 and Decode(float[]) :241-253.
+ * z [B,latent,T] -> audio [B,1,T*hop] (NOT trimmed, as in the reference). */
+NC_API nc_status nc_dac_decode(nc_handle h, const float* z, int32_t batch, int64_t frames, float* audio);
+/* replaces: DAC.FromCodes(Tensor codes) Models/DAC.cs:101-106 ->
+ * ResidualVectorQuantizer.FromCodes Modules/DAC/ResidualVectorQuantizer.cs:211-238.
+ * codes [B,nq,T] int64 -> z [B,latent,T]. */
+NC_API nc_status nc_dac_from_codes(nc_handle h, const int64_t* codes, int32_t batch, int32_t n_quantizers,
+                                   int64_t frames, float* z);
+/* replaces: Dia.Decode(codes) Models/Dia.cs:973-981 = FromCodes + Decode, batched (the
+ * reference loops serially per item, Models/Dia.cs:1057-1060).  codes [B,nq,T] int64 ->
+ * audio [B,1,T*hop]. */
+NC_API nc_status nc_dac_decode_codes(nc_handle h, const int64_t* codes, int32_t batch, int32_t n_quantizers,
+                                     int64_t frames, float* audio);
+/* replaces: DAC.forward(Tensor) Models/DAC.cs:262-322 (Encode then Decode).  Outputs
+ * nullable: audio_out [B,1,padded L], codes [B,nq,T], z [B,latent,T]. */
+NC_API nc_status nc_dac_forward(nc_handle h, const float* audio, int32_t batch, int64_t length,
+                                int32_t n_quantizers, float* audio_out, int64_t* codes, float* z,
+                                int64_t* frames_out);
+/* Device-pointer variant of nc_dac_forward for zero-copy callers and device-only timing:
+ * all pointers are device memory on the handle's device; work is enqueued on the handle's
+ * stream and the call returns after that stream is synchronised. */
+NC_API nc_status nc_dac_forward_dev(nc_handle h, const float* audio_dev, int32_t batch, int64_t length,
+                                    int32_t n_quantizers, float* audio_out_dev, int64_t* codes_dev,
+                                    float* z_dev, int64_t* frames_out);
+NC_API nc_status nc_dac_decode_codes_dev(nc_handle h, const int64_t* codes_dev, int32_t batch,
+                                         int32_t n_quantizers, int64_t frames, float* audio_dev);
+
+/* -- instrumentation ---------------------------------------------------------------- */
+/* kernels launched by this handle since creation (bench.py's gpu_launches). */
+NC_API uint64_t nc_launch_count(nc_handle h);
+/* With option profile=1 every kernel launch is bracketed by CUDA events on the handle's
+ * stream; this writes a JSON object {kernel: {launches, ms, flops, bytes}} into buf and
+ * resets the counters.  Returns NC_INVALID_ARGUMENT when buf is too small. */
+NC_API nc_status nc_profile_report(nc_handle h, char* buf, size_t buf_size);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEURALCODECS_CUDA_H_ */

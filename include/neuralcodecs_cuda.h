@@ -39,7 +39,7 @@ extern "C" {
 typedef struct nc_handle_s* nc_handle;
 
 /* Status codes; the C# layer maps them onto the reference's exception conventions
- * (NeuralCodecs.Core/Exceptions/*.cs; Models/DAC.cs:53,146,207,347-388):
+ * (NeuralCodecs.Core/Exceptions/ directory; Models/DAC.cs:53,146,207,347-388):
  *   INVALID_ARGUMENT -> ArgumentException        FILE_NOT_FOUND -> FileNotFoundException
  *   BAD_WEIGHTS / SHAPE_MISMATCH -> InvalidOperationException("Failed to load ... weights")
  *   CUDA_UNAVAILABLE -> InvalidOperationException("CUDA requested but not available")

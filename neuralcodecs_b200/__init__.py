@@ -1,0 +1,11 @@
+"""neuralcodecs_b200 -- Blackwell (sm_100a) backend for the NeuralCodecs codec hot path.
+
+Host-side mirror (Python, over ctypes) of the reference's model classes; all arithmetic is
+in ``libneuralcodecs_cuda.so`` (hand-written CUDA, C ABI in include/neuralcodecs_cuda.h).
+There is no CPU fallback and nothing here imports ``oracle/``.
+"""
+from .config import DACConfig, DeviceConfiguration  # noqa: F401
+from .dac import DAC  # noqa: F401
+from ._lib import CodecException  # noqa: F401
+
+__all__ = ["DAC", "DACConfig", "DeviceConfiguration", "CodecException"]

@@ -1,0 +1,83 @@
+"""Config classes of the Cuda backend: same fields, defaults, presets and JSON property
+names as the reference's config classes (paths under /root/reference/NeuralCodecs.Torch/):
+  DACConfig      Config/DAC/DACConfig.cs:8-136
+  SNACConfig     Config/SNAC/SNACConfig.cs:11-153
+  EncodecConfig  Config/Encodec/EncodecConfig.cs:6-153
+"""
+from __future__ import annotations
+
+import json
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+
+@dataclass
+class DeviceConfiguration:
+    """NeuralCodecs.Core/Configuration/DeviceConfiguration.cs:6-28 (CUDA only here)."""
+    type: str = "CUDA"
+    index: int = 0
+
+    @staticmethod
+    def CUDA(index: int = 0) -> "DeviceConfiguration":
+        return DeviceConfiguration("CUDA", index)
+
+
+@dataclass
+class DACConfig:
+    device: DeviceConfiguration = field(default_factory=DeviceConfiguration)
+    architecture: str = "dac"
+    sample_rate: int = 44100                                   # "sampling_rate"
+    encoder_dim: int = 64                                      # "encoder_hidden_size"
+    encoder_rates: List[int] = field(default_factory=lambda: [2, 4, 8, 8])   # "downsampling_ratios"
+    decoder_dim: int = 1536                                    # "decoder_hidden_size"
+    decoder_rates: List[int] = field(default_factory=lambda: [8, 8, 4, 2])   # "upsampling_ratios"
+    num_codebooks: int = 9                                     # "n_codebooks"
+    codebook_size: int = 1024
+    codebook_dim: int = 8
+    latent_dim: Optional[int] = None
+    quantizer_dropout: float = 0.0
+    version: str = "0.0.1"
+
+    _JSON = {"sampling_rate": "sample_rate", "encoder_hidden_size": "encoder_dim",
+             "downsampling_ratios": "encoder_rates", "decoder_hidden_size": "decoder_dim",
+             "upsampling_ratios": "decoder_rates", "n_codebooks": "num_codebooks",
+             "codebook_size": "codebook_size", "codebook_dim": "codebook_dim",
+             "latent_dim": "latent_dim", "quantizer_dropout": "quantizer_dropout",
+             "model_type": "architecture"}
+
+    @property
+    def hop_length(self) -> int:
+        return int(math.prod(self.encoder_rates))
+
+    @property
+    def resolved_latent_dim(self) -> int:
+        # Models/DAC.cs:64
+        return self.latent_dim if self.latent_dim else self.encoder_dim * (1 << len(self.encoder_rates))
+
+    @classmethod
+    def from_json(cls, text: str) -> "DACConfig":
+        cfg = cls()
+        for k, v in json.loads(text).items():
+            if k in cls._JSON and v is not None:
+                setattr(cfg, cls._JSON[k], v)
+        return cfg
+
+    # presets: DACConfig.cs:102-136
+    @classmethod
+    def DAC44kHz(cls) -> "DACConfig":
+        return cls()
+
+    @classmethod
+    def DAC44kHz_16kbps(cls) -> "DACConfig":
+        return cls(num_codebooks=18, latent_dim=128, version="1.0.0")
+
+    @classmethod
+    def DAC24kHz(cls) -> "DACConfig":
+        return cls(sample_rate=24000, num_codebooks=32, encoder_rates=[2, 4, 5, 8],
+                   decoder_rates=[8, 5, 4, 2], version="0.0.4")
+
+    @classmethod
+    def DAC16kHz(cls) -> "DACConfig":
+        return cls(sample_rate=16000, num_codebooks=12, encoder_rates=[2, 4, 5, 8],
+                   decoder_rates=[8, 5, 4, 2], version="0.0.5")

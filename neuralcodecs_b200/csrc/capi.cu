@@ -1,0 +1,310 @@
+// C ABI of libneuralcodecs_cuda.so (include/neuralcodecs_cuda.h).  No exception crosses the
+// boundary; the last error message is kept per thread.
+#include <cstring>
+#include <new>
+
+#include "engine.h"
+
+using namespace nc;
+
+struct nc_handle_s {
+  Engine* engine = nullptr;
+  nc_codec_kind kind;
+};
+
+namespace {
+thread_local std::string g_last_error;
+
+nc_status fail(nc_status s, const std::string& msg) {
+  g_last_error = msg;
+  return s;
+}
+
+template <typename F>
+nc_status guarded(F&& f) {
+  try {
+    f();
+    g_last_error.clear();
+    return NC_OK;
+  } catch (const Error& e) {
+    return fail(e.status, e.what());
+  } catch (const std::bad_alloc&) {
+    return fail(NC_OUT_OF_MEMORY, "host allocation failed");
+  } catch (const std::exception& e) {
+    return fail(NC_INTERNAL, e.what());
+  } catch (...) {
+    return fail(NC_INTERNAL, "unknown error");
+  }
+}
+
+struct BusyGuard {
+  Engine* e;
+  explicit BusyGuard(Engine* eng) : e(eng) {
+    if (e->busy) throw Error(NC_INVALID_ARGUMENT, "handle is in use by another call (handles are not re-entrant)");
+    e->busy = true;
+  }
+  ~BusyGuard() { e->busy = false; }
+};
+
+DacEngine* dac_of(nc_handle h) {
+  if (!h || !h->engine) throw Error(NC_INVALID_ARGUMENT, "null handle");
+  if (h->kind != NC_CODEC_DAC) throw Error(NC_INVALID_ARGUMENT, "handle is not a DAC codec");
+  return static_cast<DacEngine*>(h->engine);
+}
+
+// scoped device allocation for the host-pointer entry points
+struct DevMem {
+  void* p = nullptr;
+  explicit DevMem(size_t bytes) {
+    if (bytes) NC_CUDA(cudaMalloc(&p, bytes));
+  }
+  ~DevMem() { cudaFree(p); }
+  template <typename T>
+  T* as() { return static_cast<T*>(p); }
+};
+}  // namespace
+
+extern "C" {
+
+const char* nc_version(void) { return "neuralcodecs_cuda 0.1.0 (sm_100a)"; }
+const char* nc_last_error(void) { return g_last_error.c_str(); }
+
+int nc_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    cudaDeviceProp p{};
+    if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
+  }
+  return ok;
+}
+
+nc_status nc_create(nc_codec_kind kind, const void* cfg, size_t cfg_size, int device_index, nc_handle* out) {
+  return guarded([&] {
+    if (!out) throw Error(NC_INVALID_ARGUMENT, "out handle is null");
+    *out = nullptr;
+    Engine* e = create_engine(kind, cfg, cfg_size, device_index);
+    nc_handle h = new nc_handle_s;
+    h->engine = e;
+    h->kind = kind;
+    *out = h;
+  });
+}
+
+nc_status nc_destroy(nc_handle h) {
+  return guarded([&] {
+    if (!h) return;
+    delete h->engine;
+    delete h;
+  });
+}
+
+nc_status nc_load_weights(nc_handle h, const char* path) {
+  return guarded([&] {
+    if (!h || !h->engine) throw Error(NC_INVALID_ARGUMENT, "null handle");
+    if (!path) throw Error(NC_INVALID_ARGUMENT, "path is null");
+    BusyGuard g(h->engine);
+    h->engine->bind();
+    h->engine->load_weights(path);
+  });
+}
+
+nc_status nc_set_tensor(nc_handle h, const char* name, int dtype, int rank, const int64_t* shape, const void* data) {
+  return guarded([&] {
+    if (!h || !h->engine) throw Error(NC_INVALID_ARGUMENT, "null handle");
+    if (!name || !data || rank < 0 || rank > 8 || (rank > 0 && !shape)) throw Error(NC_INVALID_ARGUMENT, "bad tensor arguments");
+    HostTensor t;
+    t.shape.assign(shape, shape + rank);
+    for (auto d : t.shape)
+      if (d < 0) throw Error(NC_INVALID_ARGUMENT, "negative dimension");
+    const size_t n = t.numel();
+    if (dtype == 0) {
+      t.f32.assign(static_cast<const float*>(data), static_cast<const float*>(data) + n);
+    } else if (dtype == 1) {
+      t.is_int = true;
+      t.i64.assign(static_cast<const int64_t*>(data), static_cast<const int64_t*>(data) + n);
+    } else {
+      throw Error(NC_INVALID_ARGUMENT, "dtype must be 0 (f32) or 1 (i64)");
+    }
+    h->engine->set_tensor(name, std::move(t));
+  });
+}
+
+nc_status nc_finalize_weights(nc_handle h) {
+  return guarded([&] {
+    if (!h || !h->engine) throw Error(NC_INVALID_ARGUMENT, "null handle");
+    BusyGuard g(h->engine);
+    h->engine->bind();
+    h->engine->finalize_weights();
+  });
+}
+
+nc_status nc_set_option(nc_handle h, const char* key, const char* value) {
+  return guarded([&] {
+    if (!h || !h->engine) throw Error(NC_INVALID_ARGUMENT, "null handle");
+    if (!key || !value) throw Error(NC_INVALID_ARGUMENT, "null option");
+    h->engine->set_option(key, value);
+  });
+}
+
+// ------------------------------------------------------------------------------------ DAC
+nc_status nc_dac_query_shapes(nc_handle h, int64_t length, int64_t* padded_length, int64_t* frames, int32_t* latent_dim,
+                              int32_t* n_codebooks, int32_t* codebook_dim) {
+  return guarded([&] {
+    DacEngine* e = dac_of(h);
+    if (length < 0) throw Error(NC_INVALID_ARGUMENT, "length must be non-negative");
+    if (padded_length) *padded_length = e->padded_length(length);
+    if (frames) *frames = e->frames(length);
+    if (latent_dim) *latent_dim = e->config().latent_dim;
+    if (n_codebooks) *n_codebooks = e->config().n_codebooks;
+    if (codebook_dim) *codebook_dim = e->config().codebook_dim;
+  });
+}
+
+static void check_rate(DacEngine* e, int32_t sample_rate) {
+  // Models/DAC.cs:143-149: ArgumentException on mismatch
+  if (sample_rate != 0 && sample_rate != e->config().sample_rate)
+    throw Error(NC_INVALID_ARGUMENT, "Input audio sample rate " + std::to_string(sample_rate) +
+                                         "Hz does not match model sample rate " +
+                                         std::to_string(e->config().sample_rate) + "Hz");
+}
+
+static int eff_nq(DacEngine* e, int nq) { return (nq <= 0 || nq > e->config().n_codebooks) ? e->config().n_codebooks : nq; }
+
+nc_status nc_dac_encode(nc_handle h, const float* audio, int32_t batch, int64_t length, int32_t sample_rate,
+                        int32_t n_quantizers, float* z, int64_t* codes, float* latents, int64_t* frames_out) {
+  return guarded([&] {
+    DacEngine* e = dac_of(h);
+    if (!audio) throw Error(NC_INVALID_ARGUMENT, "audio is null");
+    if (batch <= 0 || length <= 0) throw Error(NC_INVALID_ARGUMENT, "batch and length must be positive");
+    if (n_quantizers < 0) throw Error(NC_INVALID_ARGUMENT, "n_quantizers must be >= 0");
+    check_rate(e, sample_rate);
+    BusyGuard g(e);
+    e->bind();
+    const int nq = eff_nq(e, n_quantizers);
+    const int64_t T = e->frames(length);
+    const auto& c = e->config();
+    DevMem d_audio((size_t)batch * length * 4), d_z(z ? (size_t)batch * c.latent_dim * T * 4 : 0),
+        d_codes(codes ? (size_t)batch * nq * T * 8 : 0), d_lat(latents ? (size_t)batch * nq * c.codebook_dim * T * 4 : 0);
+    NC_CUDA(cudaMemcpy(d_audio.p, audio, (size_t)batch * length * 4, cudaMemcpyHostToDevice));
+    e->encode_dev(d_audio.as<float>(), batch, length, nq, d_z.as<float>(), d_codes.as<int64_t>(), d_lat.as<float>());
+    if (z) NC_CUDA(cudaMemcpy(z, d_z.p, (size_t)batch * c.latent_dim * T * 4, cudaMemcpyDeviceToHost));
+    if (codes) NC_CUDA(cudaMemcpy(codes, d_codes.p, (size_t)batch * nq * T * 8, cudaMemcpyDeviceToHost));
+    if (latents) NC_CUDA(cudaMemcpy(latents, d_lat.p, (size_t)batch * nq * c.codebook_dim * T * 4, cudaMemcpyDeviceToHost));
+    if (frames_out) *frames_out = T;
+  });
+}
+
+nc_status nc_dac_decode(nc_handle h, const float* z, int32_t batch, int64_t frames, float* audio) {
+  return guarded([&] {
+    DacEngine* e = dac_of(h);
+    if (!z || !audio) throw Error(NC_INVALID_ARGUMENT, "null buffer");
+    if (batch <= 0 || frames <= 0) throw Error(NC_INVALID_ARGUMENT, "batch and frames must be positive");
+    BusyGuard g(e);
+    e->bind();
+    const auto& c = e->config();
+    const int64_t L = e->decoded_length(frames);
+    DevMem d_z((size_t)batch * c.latent_dim * frames * 4), d_a((size_t)batch * L * 4);
+    NC_CUDA(cudaMemcpy(d_z.p, z, (size_t)batch * c.latent_dim * frames * 4, cudaMemcpyHostToDevice));
+    e->decode_dev(d_z.as<float>(), batch, frames, d_a.as<float>());
+    NC_CUDA(cudaMemcpy(audio, d_a.p, (size_t)batch * L * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
+nc_status nc_dac_from_codes(nc_handle h, const int64_t* codes, int32_t batch, int32_t n_quantizers, int64_t frames,
+                            float* z) {
+  return guarded([&] {
+    DacEngine* e = dac_of(h);
+    if (!codes || !z) throw Error(NC_INVALID_ARGUMENT, "null buffer");
+    if (batch <= 0 || frames <= 0) throw Error(NC_INVALID_ARGUMENT, "batch and frames must be positive");
+    BusyGuard g(e);
+    e->bind();
+    const auto& c = e->config();
+    DevMem d_c((size_t)batch * n_quantizers * frames * 8), d_z((size_t)batch * c.latent_dim * frames * 4);
+    NC_CUDA(cudaMemcpy(d_c.p, codes, (size_t)batch * n_quantizers * frames * 8, cudaMemcpyHostToDevice));
+    e->from_codes_dev(d_c.as<int64_t>(), batch, n_quantizers, frames, d_z.as<float>());
+    NC_CUDA(cudaMemcpy(z, d_z.p, (size_t)batch * c.latent_dim * frames * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
+nc_status nc_dac_decode_codes(nc_handle h, const int64_t* codes, int32_t batch, int32_t n_quantizers, int64_t frames,
+                              float* audio) {
+  return guarded([&] {
+    DacEngine* e = dac_of(h);
+    if (!codes || !audio) throw Error(NC_INVALID_ARGUMENT, "null buffer");
+    if (batch <= 0 || frames <= 0) throw Error(NC_INVALID_ARGUMENT, "batch and frames must be positive");
+    BusyGuard g(e);
+    e->bind();
+    const int64_t L = e->decoded_length(frames);
+    DevMem d_c((size_t)batch * n_quantizers * frames * 8), d_a((size_t)batch * L * 4);
+    NC_CUDA(cudaMemcpy(d_c.p, codes, (size_t)batch * n_quantizers * frames * 8, cudaMemcpyHostToDevice));
+    e->decode_codes_dev(d_c.as<int64_t>(), batch, n_quantizers, frames, d_a.as<float>());
+    NC_CUDA(cudaMemcpy(audio, d_a.p, (size_t)batch * L * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
+nc_status nc_dac_forward(nc_handle h, const float* audio, int32_t batch, int64_t length, int32_t n_quantizers,
+                         float* audio_out, int64_t* codes, float* z, int64_t* frames_out) {
+  return guarded([&] {
+    DacEngine* e = dac_of(h);
+    if (!audio) throw Error(NC_INVALID_ARGUMENT, "audio is null");
+    if (batch <= 0 || length <= 0) throw Error(NC_INVALID_ARGUMENT, "batch and length must be positive");
+    if (n_quantizers < 0) throw Error(NC_INVALID_ARGUMENT, "n_quantizers must be >= 0");
+    BusyGuard g(e);
+    e->bind();
+    const int nq = eff_nq(e, n_quantizers);
+    const int64_t T = e->frames(length);
+    const int64_t Lout = e->decoded_length(T);
+    const auto& c = e->config();
+    DevMem d_audio((size_t)batch * length * 4), d_out(audio_out ? (size_t)batch * Lout * 4 : 0),
+        d_z(z ? (size_t)batch * c.latent_dim * T * 4 : 0), d_codes(codes ? (size_t)batch * nq * T * 8 : 0);
+    NC_CUDA(cudaMemcpy(d_audio.p, audio, (size_t)batch * length * 4, cudaMemcpyHostToDevice));
+    e->forward_dev(d_audio.as<float>(), batch, length, nq, d_out.as<float>(), d_codes.as<int64_t>(), d_z.as<float>());
+    if (audio_out) NC_CUDA(cudaMemcpy(audio_out, d_out.p, (size_t)batch * Lout * 4, cudaMemcpyDeviceToHost));
+    if (z) NC_CUDA(cudaMemcpy(z, d_z.p, (size_t)batch * c.latent_dim * T * 4, cudaMemcpyDeviceToHost));
+    if (codes) NC_CUDA(cudaMemcpy(codes, d_codes.p, (size_t)batch * nq * T * 8, cudaMemcpyDeviceToHost));
+    if (frames_out) *frames_out = T;
+  });
+}
+
+nc_status nc_dac_forward_dev(nc_handle h, const float* audio_dev, int32_t batch, int64_t length, int32_t n_quantizers,
+                             float* audio_out_dev, int64_t* codes_dev, float* z_dev, int64_t* frames_out) {
+  return guarded([&] {
+    DacEngine* e = dac_of(h);
+    if (!audio_dev) throw Error(NC_INVALID_ARGUMENT, "audio is null");
+    if (batch <= 0 || length <= 0) throw Error(NC_INVALID_ARGUMENT, "batch and length must be positive");
+    BusyGuard g(e);
+    e->forward_dev(audio_dev, batch, length, eff_nq(e, n_quantizers), audio_out_dev, codes_dev, z_dev);
+    if (frames_out) *frames_out = e->frames(length);
+  });
+}
+
+nc_status nc_dac_decode_codes_dev(nc_handle h, const int64_t* codes_dev, int32_t batch, int32_t n_quantizers,
+                                  int64_t frames, float* audio_dev) {
+  return guarded([&] {
+    DacEngine* e = dac_of(h);
+    if (!codes_dev || !audio_dev) throw Error(NC_INVALID_ARGUMENT, "null buffer");
+    BusyGuard g(e);
+    e->decode_codes_dev(codes_dev, batch, n_quantizers, frames, audio_dev);
+  });
+}
+
+// ------------------------------------------------------------------------------------ instrumentation
+uint64_t nc_launch_count(nc_handle h) { return (h && h->engine) ? h->engine->launches() : 0; }
+
+nc_status nc_profile_report(nc_handle h, char* buf, size_t buf_size) {
+  return guarded([&] {
+    if (!h || !h->engine) throw Error(NC_INVALID_ARGUMENT, "null handle");
+    if (!buf || buf_size == 0) throw Error(NC_INVALID_ARGUMENT, "null buffer");
+    h->engine->bind();
+    const std::string s = h->engine->profiler().report_json(true);
+    if (s.size() + 1 > buf_size) throw Error(NC_INVALID_ARGUMENT, "profile buffer too small");
+    std::memcpy(buf, s.c_str(), s.size() + 1);
+  });
+}
+
+}  // extern "C"

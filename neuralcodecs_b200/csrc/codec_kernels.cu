@@ -1,0 +1,290 @@
+// HBM-bound kernels of the codec hot path.  See codec_kernels.h for the contracts.
+#include "codec_kernels.h"
+
+#include <cfloat>
+
+namespace nc {
+
+// ------------------------------------------------------------------------------ first conv (Cin = 1)
+__global__ void __launch_bounds__(256)
+conv_cin1_kernel(const float* __restrict__ in, long long in_stride, int in_len, float* __restrict__ out, int t_out,
+                 int cout, const float* __restrict__ w, const float* __restrict__ bias, int k, int dil, int pad,
+                 int batch) {
+  extern __shared__ float sw[];  // [cout][k] + [cout]
+  for (int i = threadIdx.x; i < cout * k; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) sw[cout * k + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int c4n = cout / 4;
+  const long long total = (long long)batch * t_out * c4n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % c4n);
+    const long long bt = i / c4n;
+    const int t = (int)(bt % t_out);
+    const int b = (int)(bt / t_out);
+    const float* x = in + (long long)b * in_stride;
+    float a0 = sw[cout * k + 4 * c4 + 0], a1 = sw[cout * k + 4 * c4 + 1], a2 = sw[cout * k + 4 * c4 + 2],
+          a3 = sw[cout * k + 4 * c4 + 3];
+    for (int j = 0; j < k; ++j) {
+      const int ti = t + j * dil - pad;
+      const float v = (ti >= 0 && ti < in_len) ? __ldg(x + ti) : 0.f;
+      a0 = fmaf(sw[(4 * c4 + 0) * k + j], v, a0);
+      a1 = fmaf(sw[(4 * c4 + 1) * k + j], v, a1);
+      a2 = fmaf(sw[(4 * c4 + 2) * k + j], v, a2);
+      a3 = fmaf(sw[(4 * c4 + 3) * k + j], v, a3);
+    }
+    reinterpret_cast<float4*>(out)[i] = make_float4(a0, a1, a2, a3);
+  }
+}
+
+void launch_conv_cin1(const float* in, long long in_stride, int in_len, float* out, int t_out, int cout,
+                      const float* w, const float* bias, int k, int dil, int pad, int batch, const LaunchCtx& ctx) {
+  if (cout % 4 != 0) throw Error(NC_UNSUPPORTED, "conv_cin1: Cout must be a multiple of 4");
+  const long long total = (long long)batch * t_out * (cout / 4);
+  if (total == 0) return;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)ctx.num_sms * 16;
+  if (blocks > cap) blocks = cap;
+  const int ev = ctx.begin();
+  conv_cin1_kernel<<<(unsigned)blocks, 256, (size_t)(cout * k + cout) * sizeof(float), ctx.stream>>>(
+      in, in_stride, in_len, out, t_out, cout, w, bias, k, dil, pad, batch);
+  check_launch((int)cudaGetLastError(), "conv_cin1");
+  ctx.end(ev, "conv_cin1", 2.0 * k * cout * (double)t_out * batch, 4.0 * batch * ((double)in_len + (double)t_out * cout));
+}
+
+// ------------------------------------------------------------------------------ transposes
+// in: [B][R][Cn] -> out: [B][Cn][R]
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int Cn) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const float* src = in + (long long)b * R * Cn;
+  float* dst = out + (long long)b * R * Cn;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < Cn) ? src[(long long)r * Cn + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < Cn) dst[(long long)c * R + r] = tile[threadIdx.x][i];
+  }
+}
+
+static void launch_transpose(const float* in, float* out, int batch, int R, int Cn, const LaunchCtx& ctx,
+                             const char* name) {
+  if (batch == 0 || R == 0 || Cn == 0) return;
+  dim3 grid((Cn + 31) / 32, (R + 31) / 32, batch), block(32, 8);
+  const int ev = ctx.begin();
+  transpose_kernel<<<grid, block, 0, ctx.stream>>>(in, out, R, Cn);
+  check_launch((int)cudaGetLastError(), name);
+  ctx.end(ev, name, 0, 8.0 * batch * (double)R * Cn);
+}
+void launch_transpose_ct_to_tc(const float* in, float* out, int batch, int C, int T, const LaunchCtx& ctx) {
+  launch_transpose(in, out, batch, C, T, ctx, "transpose");
+}
+void launch_transpose_tc_to_ct(const float* in, float* out, int batch, int C, int T, const LaunchCtx& ctx) {
+  launch_transpose(in, out, batch, T, C, ctx, "transpose");
+}
+
+// ------------------------------------------------------------------------------ fused RVQ encode
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+constexpr int kVqD = 8;
+
+template <int CPL>
+__global__ void __launch_bounds__(256)
+rvq_encode_kernel(const RvqWeights w, const float* __restrict__ z, float* __restrict__ zq, int64_t* __restrict__ codes,
+                  float* __restrict__ latents, int batch, int T, int n_q) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long frames = (long long)batch * T;
+  const int Dz = w.Dz, K = w.K;
+  for (long long f = warp0; f < frames; f += nwarps) {
+    const int b = (int)(f / T), t = (int)(f % T);
+    const float* zr = z + f * Dz;
+    float r[CPL], acc[CPL];
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+      r[i] = __ldg(zr + lane + 32 * i);
+      acc[i] = 0.f;
+    }
+    for (int s = 0; s < n_q; ++s) {
+      // ---- in_proj (WNConv1d Dz -> 8, k = 1): Modules/DAC/VectorQuantizer.cs:70
+      const float* Win = w.in_w + (size_t)s * kVqD * Dz;
+      float ze[kVqD];
+#pragma unroll
+      for (int d = 0; d < kVqD; ++d) {
+        float p = 0.f;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) p = fmaf(__ldg(Win + (size_t)d * Dz + lane + 32 * i), r[i], p);
+        ze[d] = warp_sum(p) + __ldg(w.in_b + s * kVqD + d);
+      }
+      // ---- nearest codebook entry, un-normalised expanded form (VectorQuantizer.cs:110-121)
+      float e2 = 0.f;
+#pragma unroll
+      for (int d = 0; d < kVqD; ++d) e2 = fmaf(ze[d], ze[d], e2);
+      const float* cb = w.cb + (size_t)s * K * kVqD;
+      const float* csq = w.cb_sq + (size_t)s * K;
+      float best = FLT_MAX;
+      int best_k = 0;
+      for (int k = lane; k < K; k += 32) {
+        const float4 c0 = __ldg(reinterpret_cast<const float4*>(cb + (size_t)k * kVqD));
+        const float4 c1 = __ldg(reinterpret_cast<const float4*>(cb + (size_t)k * kVqD) + 1);
+        float dot = ze[0] * c0.x;
+        dot = fmaf(ze[1], c0.y, dot); dot = fmaf(ze[2], c0.z, dot); dot = fmaf(ze[3], c0.w, dot);
+        dot = fmaf(ze[4], c1.x, dot); dot = fmaf(ze[5], c1.y, dot); dot = fmaf(ze[6], c1.z, dot);
+        dot = fmaf(ze[7], c1.w, dot);
+        const float dist = (e2 + __ldg(csq + k)) - 2.0f * dot;
+        if (dist < best) { best = dist; best_k = k; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(0xffffffffu, best, o);
+        const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
+        if (od < best || (od == best && ok < best_k)) { best = od; best_k = ok; }  // argmin: lowest index wins
+      }
+      // ---- lookup + straight-through arithmetic (VectorQuantizer.cs:81) + out_proj (:82)
+      const float4 q0 = __ldg(reinterpret_cast<const float4*>(cb + (size_t)best_k * kVqD));
+      const float4 q1 = __ldg(reinterpret_cast<const float4*>(cb + (size_t)best_k * kVqD) + 1);
+      float q[kVqD] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+      for (int d = 0; d < kVqD; ++d) q[d] = ze[d] + (q[d] - ze[d]);
+      const float* Wout = w.out_w + (size_t)s * Dz * kVqD;
+      const float* bout = w.out_b + (size_t)s * Dz;
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) {
+        const int c = lane + 32 * i;
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(Wout + (size_t)c * kVqD));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(Wout + (size_t)c * kVqD) + 1);
+        float v = w0.x * q[0];
+        v = fmaf(w0.y, q[1], v); v = fmaf(w0.z, q[2], v); v = fmaf(w0.w, q[3], v);
+        v = fmaf(w1.x, q[4], v); v = fmaf(w1.y, q[5], v); v = fmaf(w1.z, q[6], v); v = fmaf(w1.w, q[7], v);
+        v += __ldg(bout + c);
+        acc[i] += v;   // zQ.add_(zQi)        ResidualVectorQuantizer.cs:68
+        r[i] -= v;     // residual.sub_(zQi)  ResidualVectorQuantizer.cs:69
+      }
+      if (codes && lane == 0) codes[((long long)b * n_q + s) * T + t] = best_k;
+      if (latents && lane < kVqD) {
+        float mine = ze[0];
+#pragma unroll
+        for (int d = 1; d < kVqD; ++d) mine = lane == d ? ze[d] : mine;
+        latents[((long long)b * n_q * kVqD + s * kVqD + lane) * T + t] = mine;
+      }
+    }
+    if (zq) {
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) zq[f * Dz + lane + 32 * i] = acc[i];
+    }
+  }
+}
+
+template <int CPL>
+static void rvq_encode_launch(const RvqWeights& w, const float* z, float* zq, int64_t* codes, float* latents,
+                              int batch, int T, int n_q, const LaunchCtx& ctx) {
+  const long long frames = (long long)batch * T;
+  long long blocks = (frames + 7) / 8;
+  const long long cap = (long long)ctx.num_sms * 8;
+  if (blocks > cap) blocks = cap;
+  rvq_encode_kernel<CPL><<<(unsigned)blocks, 256, 0, ctx.stream>>>(w, z, zq, codes, latents, batch, T, n_q);
+}
+
+void launch_rvq_encode(const RvqWeights& w, const float* z, float* zq, int64_t* codes, float* latents, int batch,
+                       int T, int n_q, const LaunchCtx& ctx) {
+  if (w.D != kVqD) throw Error(NC_UNSUPPORTED, "rvq: codebook_dim must be 8");
+  if (w.Dz % 32 != 0 || w.K % 32 != 0) throw Error(NC_UNSUPPORTED, "rvq: latent dim / codebook size must be multiples of 32");
+  if ((long long)batch * T == 0) return;
+  const int ev = ctx.begin();
+  switch (w.Dz / 32) {
+    case 1: rvq_encode_launch<1>(w, z, zq, codes, latents, batch, T, n_q, ctx); break;
+    case 2: rvq_encode_launch<2>(w, z, zq, codes, latents, batch, T, n_q, ctx); break;
+    case 4: rvq_encode_launch<4>(w, z, zq, codes, latents, batch, T, n_q, ctx); break;
+    case 8: rvq_encode_launch<8>(w, z, zq, codes, latents, batch, T, n_q, ctx); break;
+    case 16: rvq_encode_launch<16>(w, z, zq, codes, latents, batch, T, n_q, ctx); break;
+    case 24: rvq_encode_launch<24>(w, z, zq, codes, latents, batch, T, n_q, ctx); break;
+    case 32: rvq_encode_launch<32>(w, z, zq, codes, latents, batch, T, n_q, ctx); break;
+    default: throw Error(NC_UNSUPPORTED, "rvq: unsupported latent dim " + std::to_string(w.Dz));
+  }
+  check_launch((int)cudaGetLastError(), "rvq_encode");
+  const double fr = (double)batch * T;
+  ctx.end(ev, "rvq_encode", fr * n_q * 2.0 * (2.0 * w.D * w.Dz + (double)w.D * w.K),
+          fr * (2.0 * w.Dz * 4 + (codes ? n_q * 8.0 : 0) + (latents ? n_q * w.D * 4.0 : 0)));
+}
+
+// ------------------------------------------------------------------------------ codes -> latent
+template <int CPL>
+__global__ void __launch_bounds__(256)
+rvq_from_codes_kernel(const RvqWeights w, const int64_t* __restrict__ codes, float* __restrict__ zq, int batch, int T,
+                      int n_q) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long frames = (long long)batch * T;
+  const int Dz = w.Dz, K = w.K;
+  for (long long f = warp0; f < frames; f += nwarps) {
+    const int b = (int)(f / T), t = (int)(f % T);
+    float acc[CPL];
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) acc[i] = 0.f;
+    for (int s = 0; s < n_q; ++s) {
+      long long code = codes[((long long)b * n_q + s) * T + t];
+      code = code < 0 ? 0 : (code >= K ? K - 1 : code);
+      const float* cb = w.cb + ((size_t)s * K + (size_t)code) * kVqD;
+      const float4 q0 = __ldg(reinterpret_cast<const float4*>(cb));
+      const float4 q1 = __ldg(reinterpret_cast<const float4*>(cb) + 1);
+      const float* Wout = w.out_w + (size_t)s * Dz * kVqD;
+      const float* bout = w.out_b + (size_t)s * Dz;
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) {
+        const int c = lane + 32 * i;
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(Wout + (size_t)c * kVqD));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(Wout + (size_t)c * kVqD) + 1);
+        float v = w0.x * q0.x;
+        v = fmaf(w0.y, q0.y, v); v = fmaf(w0.z, q0.z, v); v = fmaf(w0.w, q0.w, v);
+        v = fmaf(w1.x, q1.x, v); v = fmaf(w1.y, q1.y, v); v = fmaf(w1.z, q1.z, v); v = fmaf(w1.w, q1.w, v);
+        v += __ldg(bout + c);
+        acc[i] += v;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) zq[f * Dz + lane + 32 * i] = acc[i];
+  }
+}
+
+template <int CPL>
+static void rvq_from_codes_launch(const RvqWeights& w, const int64_t* codes, float* zq, int batch, int T, int n_q,
+                                  const LaunchCtx& ctx) {
+  const long long frames = (long long)batch * T;
+  long long blocks = (frames + 7) / 8;
+  const long long cap = (long long)ctx.num_sms * 8;
+  if (blocks > cap) blocks = cap;
+  rvq_from_codes_kernel<CPL><<<(unsigned)blocks, 256, 0, ctx.stream>>>(w, codes, zq, batch, T, n_q);
+}
+
+void launch_rvq_from_codes(const RvqWeights& w, const int64_t* codes, float* zq, int batch, int T, int n_q,
+                           const LaunchCtx& ctx) {
+  if (w.D != kVqD) throw Error(NC_UNSUPPORTED, "rvq: codebook_dim must be 8");
+  if (w.Dz % 32 != 0) throw Error(NC_UNSUPPORTED, "rvq: latent dim must be a multiple of 32");
+  if ((long long)batch * T == 0) return;
+  const int ev = ctx.begin();
+  switch (w.Dz / 32) {
+    case 1: rvq_from_codes_launch<1>(w, codes, zq, batch, T, n_q, ctx); break;
+    case 2: rvq_from_codes_launch<2>(w, codes, zq, batch, T, n_q, ctx); break;
+    case 4: rvq_from_codes_launch<4>(w, codes, zq, batch, T, n_q, ctx); break;
+    case 8: rvq_from_codes_launch<8>(w, codes, zq, batch, T, n_q, ctx); break;
+    case 16: rvq_from_codes_launch<16>(w, codes, zq, batch, T, n_q, ctx); break;
+    case 24: rvq_from_codes_launch<24>(w, codes, zq, batch, T, n_q, ctx); break;
+    case 32: rvq_from_codes_launch<32>(w, codes, zq, batch, T, n_q, ctx); break;
+    default: throw Error(NC_UNSUPPORTED, "rvq: unsupported latent dim " + std::to_string(w.Dz));
+  }
+  check_launch((int)cudaGetLastError(), "rvq_from_codes");
+  const double fr = (double)batch * T;
+  ctx.end(ev, "rvq_from_codes", fr * n_q * 2.0 * w.D * w.Dz, fr * (w.Dz * 4.0 + n_q * 8.0));
+}
+
+}  // namespace nc

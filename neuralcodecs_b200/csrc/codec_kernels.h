@@ -1,0 +1,47 @@
+// Non-GEMM kernels of the codec hot path (HBM-bound): first conv (Cin = 1), layout
+// transposes at the API boundary, fused residual vector quantisation, code lookup.
+#pragma once
+#include <cstdint>
+
+#include "runtime.h"
+
+namespace nc {
+
+// out[b, t, co] = bias[co] + sum_j w[co, j] * f(in[b, t + j*dil - pad])   (Cin = 1, stride 1)
+// in: [B][in_stride] with `in_len` valid samples per clip (reads beyond in_len give 0: this is
+// DAC.Preprocess' right zero padding, Models/DAC.cs:151-153); out: [B][t_out][cout] channels-last.
+void launch_conv_cin1(const float* in, long long in_stride, int in_len, float* out, int t_out, int cout,
+                      const float* w /*[cout][k]*/, const float* bias, int k, int dil, int pad, int batch,
+                      const LaunchCtx& ctx);
+
+// [B][C][T] <-> [B][T][C]
+void launch_transpose_ct_to_tc(const float* in, float* out, int batch, int C, int T, const LaunchCtx& ctx);
+void launch_transpose_tc_to_ct(const float* in, float* out, int batch, int C, int T, const LaunchCtx& ctx);
+
+// Device-resident parameters of a DAC/SNAC-style factorised RVQ
+// (Modules/DAC/VectorQuantizer.cs, ResidualVectorQuantizer.cs): per stage in_proj [D][Dz] + bias [D],
+// codebook [K][D] + squared norms [K], out_proj [Dz][D] + bias [Dz].
+struct RvqWeights {
+  int n_stages = 0, Dz = 0, D = 0, K = 0;
+  const float* in_w = nullptr;   // [stage][D][Dz]
+  const float* in_b = nullptr;   // [stage][D]
+  const float* cb = nullptr;     // [stage][K][D]
+  const float* cb_sq = nullptr;  // [stage][K]   fp32 sum of squares (d ascending)
+  const float* out_w = nullptr;  // [stage][Dz][D]
+  const float* out_b = nullptr;  // [stage][Dz]
+};
+
+// Fused DAC RVQ encode over frames z[b, t, :] (channels-last rows of Dz floats):
+//   per stage: zE = in_proj(res); idx = argmin_k (|zE|^2 + |c_k|^2) - 2 zE.c_k (lowest index wins);
+//   zQ = out_proj(zE + (c_idx - zE)); zq_sum += zQ; res -= zQ
+// Outputs: zq [B][T][Dz] (nullable), codes [B][n_q][T] int64 (nullable), latents [B][n_q*D][T] (nullable).
+void launch_rvq_encode(const RvqWeights& w, const float* z, float* zq, int64_t* codes, float* latents,
+                       int batch, int T, int n_q, const LaunchCtx& ctx);
+
+// ResidualVectorQuantizer.FromCodes (Modules/DAC/ResidualVectorQuantizer.cs:211-238):
+// zq[b, t, :] = sum_i out_proj_i(codebook_i[codes[b, i, t]]).  codes: [B][n_q][T] int64.
+// Returns false through *bad (device flag, nullable) if a code is out of range (clamped to 0..K-1).
+void launch_rvq_from_codes(const RvqWeights& w, const int64_t* codes, float* zq, int batch, int T, int n_q,
+                           const LaunchCtx& ctx);
+
+}  // namespace nc

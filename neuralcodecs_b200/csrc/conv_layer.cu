@@ -1,0 +1,283 @@
+// Lowering of the reference's conv layers to multi-tap row-shifted GEMM plans + weight packing.
+//   Conv1d          : Modules/DAC/WNConv1d.cs:152 (functional.conv1d), SNAC/WNConv1d.cs:137,
+//                     Encodec/WNConv1d.cs:124
+//   ConvTranspose1d : Modules/DAC/WNConvTranspose1d.cs:152-160 (functional.conv_transpose1d),
+//                     SNAC/WNConvTranspose1d.cs:134-142, Encodec/WNConvTranspose1d.cs:140-148
+#include "conv_layer.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+
+#include "umma.cuh"
+
+namespace nc {
+
+Precision parse_precision(const std::string& s) {
+  if (s == "fp32") return PREC_FP32;
+  if (s == "tf32") return PREC_TF32;
+  if (s == "3xtf32") return PREC_3XTF32;
+  throw Error(NC_INVALID_ARGUMENT, "unknown precision '" + s + "' (fp32|tf32|3xtf32)");
+}
+
+static int g_fast_sin = -1;  // -1 auto (tf32 -> fast), 0 never, 1 always
+void set_fast_sin_policy(int v) { g_fast_sin = v; }
+
+static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+// cvt.rna.tf32.f32 on the host: round the magnitude to 10 mantissa bits, ties away from zero
+static inline float host_rna_tf32(float x) {
+  uint32_t u;
+  std::memcpy(&u, &x, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return x;
+  u += 0x1000u;
+  u &= 0xFFFFE000u;
+  float r;
+  std::memcpy(&r, &u, 4);
+  return r;
+}
+
+ConvLayer::~ConvLayer() {
+  cudaFree(d_bias_);
+  cudaFree(d_w_plain_);
+  cudaFree(d_w_hi_);
+  cudaFree(d_w_lo_);
+}
+
+int ConvLayer::out_len(int t_in) const {
+  const ConvSpec& s = spec_;
+  if (s.transposed) return (t_in - 1) * s.stride - 2 * s.padding + s.dilation * (s.k - 1) + s.output_padding + 1;
+  const int num = t_in + 2 * s.padding - s.dilation * (s.k - 1) - 1;
+  return num < 0 ? 0 : num / s.stride + 1;
+}
+
+double ConvLayer::flops(int batch, int t_in) const {
+  const ConvSpec& s = spec_;
+  if (s.transposed) return 2.0 * s.cin * s.cout * s.k * (double)t_in * batch;
+  return 2.0 * s.cin * s.cout * s.k * (double)out_len(t_in) * batch;
+}
+
+void ConvLayer::build(const std::string& name, const ConvSpec& spec, const std::vector<float>& w,
+                      const std::vector<float>& bias, Precision requested) {
+  name_ = name;
+  spec_ = spec;
+  const ConvSpec& s = spec_;
+  if ((size_t)s.cin * s.cout * s.k != w.size())
+    throw Error(NC_SHAPE_MISMATCH, name + ": weight has " + std::to_string(w.size()) + " elements, expected " +
+                                       std::to_string((size_t)s.cin * s.cout * s.k));
+  if (!bias.empty() && (int)bias.size() != s.cout) throw Error(NC_SHAPE_MISMATCH, name + ": bias size");
+  if (s.transposed && s.dilation != 1) throw Error(NC_UNSUPPORTED, name + ": dilated transposed conv");
+
+  // ---------------------------------------------------------------- logical taps
+  std::map<int, std::map<int, int>> groups;  // conv: q -> (r -> kernel index j)
+  taps_.clear();
+  if (!s.transposed) {
+    n_logical_ = s.cout;
+    k_view_ = s.stride * s.cin;
+    for (int j = 0; j < s.k; ++j) {
+      const int u = j * s.dilation - s.padding;
+      const int q = floordiv(u, s.stride);
+      groups[q][u - q * s.stride] = j;
+    }
+    for (auto& g : groups) {
+      const int rmin = g.second.begin()->first, rmax = g.second.rbegin()->first;
+      Tap t;
+      t.shift = g.first;
+      t.koff = rmin * s.cin;
+      t.klen = (rmax - rmin + 1) * s.cin;
+      t.w.assign((size_t)n_logical_ * t.klen, 0.f);
+      for (auto& rj : g.second) {
+        const int r = rj.first, j = rj.second;
+        for (int n = 0; n < s.cout; ++n)
+          for (int ci = 0; ci < s.cin; ++ci)
+            t.w[(size_t)n * t.klen + (size_t)(r - rmin) * s.cin + ci] = w[((size_t)n * s.cin + ci) * s.k + j];
+      }
+      taps_.push_back(std::move(t));
+    }
+  } else {
+    // out[t*s + phi] += x[t - q] * W[ci][co][phi + p + q*s]  (valid kernel indices only)
+    n_logical_ = s.stride * s.cout;
+    k_view_ = s.cin;
+    for (int q = -8; q <= 8; ++q) {
+      bool any = false;
+      for (int phi = 0; phi < s.stride; ++phi) {
+        const int j = phi + s.padding + q * s.stride;
+        if (j >= 0 && j < s.k) any = true;
+      }
+      if (!any) continue;
+      Tap t;
+      t.shift = -q;
+      t.koff = 0;
+      t.klen = s.cin;
+      t.w.assign((size_t)n_logical_ * t.klen, 0.f);
+      for (int phi = 0; phi < s.stride; ++phi) {
+        const int j = phi + s.padding + q * s.stride;
+        if (j < 0 || j >= s.k) continue;
+        for (int co = 0; co < s.cout; ++co)
+          for (int ci = 0; ci < s.cin; ++ci)
+            t.w[(size_t)(phi * s.cout + co) * t.klen + ci] = w[((size_t)ci * s.cout + co) * s.k + j];
+      }
+      taps_.push_back(std::move(t));
+    }
+    std::sort(taps_.begin(), taps_.end(), [](const Tap& a, const Tap& b) { return a.shift < b.shift; });
+  }
+  if ((int)taps_.size() > kMaxTaps) throw Error(NC_UNSUPPORTED, name + ": more than 8 GEMM taps");
+  n_pad_ = (n_logical_ + 15) / 16 * 16;
+  smin_ = taps_.front().shift;
+  int smax = smin_;
+  for (auto& t : taps_) {
+    smin_ = std::min(smin_, t.shift);
+    smax = std::max(smax, t.shift);
+  }
+  span_ = smax - smin_;
+
+  if (!bias.empty()) d_bias_ = upload(bias);
+
+  // ---------------------------------------------------------------- tcgen05 eligibility + tiling
+  umma_ok_ = requested != PREC_FP32 && span_ <= 64 && (k_view_ % 4) == 0;
+  for (auto& t : taps_) umma_ok_ = umma_ok_ && (t.koff % 32 == 0) && (t.klen % 32 == 0);
+  if (umma_ok_) {
+    ConvGemmParams probe{};
+    probe.span = span_;
+    probe.passes = requested == PREC_3XTF32 ? 3 : 1;
+    int bn = 0;
+    if (n_pad_ <= 256) {
+      bn = n_pad_;
+    } else {
+      for (int c = 256; c >= 16; c -= 16)
+        if (n_pad_ % c == 0) { bn = c; break; }
+    }
+    // shrink until at least 2 weight stages fit
+    UmmaLaunch L;
+    while (bn >= 16) {
+      probe.BN = bn;
+      if (n_pad_ % bn == 0 && umma_smem_bytes(probe, &L) != 0 && L.w_stages >= 3) break;
+      bn -= 16;
+    }
+    if (bn < 16 || n_pad_ / bn > kMaxNTiles) {
+      umma_ok_ = false;
+    } else {
+      bn_ = bn;
+      n_tiles_ = n_pad_ / bn;
+    }
+  }
+  mode_ = umma_ok_ ? requested : PREC_FP32;
+
+  std::memset(tap_mask_, 0, sizeof tap_mask_);
+  if (umma_ok_) {
+    kc_begin_ = 1 << 30;
+    int kc_end = 0, tile_base = 0;
+    for (size_t j = 0; j < taps_.size(); ++j) {
+      utaps_[j].shift = taps_[j].shift;
+      utaps_[j].kc_lo = taps_[j].koff / 32;
+      utaps_[j].kc_hi = (taps_[j].koff + taps_[j].klen) / 32;
+      utaps_[j].tile_base = tile_base;
+      tile_base += utaps_[j].kc_hi - utaps_[j].kc_lo;
+      kc_begin_ = std::min(kc_begin_, utaps_[j].kc_lo);
+      kc_end = std::max(kc_end, utaps_[j].kc_hi);
+    }
+    tiles_per_ntile_ = tile_base;
+    n_kc_ = kc_end - kc_begin_;
+    const size_t tile_elems = (size_t)bn_ * 32;
+    std::vector<float> hi((size_t)n_tiles_ * tiles_per_ntile_ * tile_elems, 0.f), lo;
+    if (mode_ == PREC_3XTF32) lo.assign(hi.size(), 0.f);
+    for (int nt = 0; nt < n_tiles_; ++nt) {
+      for (size_t j = 0; j < taps_.size(); ++j) {
+        const Tap& t = taps_[j];
+        bool any = false;
+        for (int kcl = 0; kcl < utaps_[j].kc_hi - utaps_[j].kc_lo; ++kcl) {
+          float* th = hi.data() + ((size_t)nt * tiles_per_ntile_ + utaps_[j].tile_base + kcl) * tile_elems;
+          float* tl = lo.empty() ? nullptr : lo.data() + ((size_t)nt * tiles_per_ntile_ + utaps_[j].tile_base + kcl) * tile_elems;
+          for (int nl = 0; nl < bn_; ++nl) {
+            const int n = nt * bn_ + nl;
+            if (n >= n_logical_) continue;
+            for (int kk = 0; kk < 32; ++kk) {
+              const float v = t.w[(size_t)n * t.klen + (size_t)kcl * 32 + kk];
+              if (v != 0.f) any = true;
+              const size_t off = ptx::sw128_offset((uint32_t)nl, (uint32_t)(kk / 4)) / 4 + (kk % 4);
+              const float h = host_rna_tf32(v);
+              th[off] = h;
+              if (tl) tl[off] = host_rna_tf32(v - h);
+            }
+          }
+        }
+        if (any) tap_mask_[nt] |= (unsigned char)(1u << j);
+      }
+    }
+    d_w_hi_ = upload(hi);
+    if (!lo.empty()) d_w_lo_ = upload(lo);
+  } else {
+    // plain [tap][n_pad][klen] for the CUDA-core executor; masks at 16-column granularity
+    size_t total = 0;
+    for (size_t j = 0; j < taps_.size(); ++j) {
+      simt_w_off_[j] = (long long)total;
+      total += (size_t)n_pad_ * taps_[j].klen;
+    }
+    std::vector<float> plain(total, 0.f);
+    for (size_t j = 0; j < taps_.size(); ++j)
+      std::memcpy(plain.data() + simt_w_off_[j], taps_[j].w.data(), taps_[j].w.size() * sizeof(float));
+    d_w_plain_ = upload(plain);
+  }
+  for (auto& t : taps_) std::vector<float>().swap(t.w);
+}
+
+void ConvLayer::run(const ConvRunArgs& a, const LaunchCtx& ctx) const {
+  const ConvSpec& s = spec_;
+  const int t_out = out_len(a.t_in);
+  if (a.batch <= 0 || t_out <= 0) return;
+  int a_rows, m_rows, n_total;
+  long long a_valid = (long long)a.t_in * s.cin, d_valid;
+  if (!s.transposed) {
+    a_rows = (a.t_in + s.stride - 1) / s.stride;
+    m_rows = t_out;
+    n_total = s.cout;
+    d_valid = (long long)t_out * s.cout;
+  } else {
+    a_rows = a.t_in;
+    m_rows = (t_out + s.stride - 1) / s.stride;
+    n_total = s.stride * s.cout;
+    d_valid = (long long)t_out * s.cout;
+  }
+  const int m_tiles = (m_rows + 127) / 128;
+  const double fl = flops(a.batch, a.t_in);
+  const double bytes = 4.0 * a.batch * ((double)a_valid + (double)d_valid * (a.residual ? 2 : 1));
+  const int ev = ctx.begin();
+  if (mode_ != PREC_FP32) {
+    ConvGemmParams p{};
+    p.A = a.in; p.a_clip_stride = a_valid; p.a_rows = a_rows; p.a_pitch = k_view_; p.a_valid = a_valid;
+    p.D = a.out; p.R = a.residual; p.d_clip_stride = d_valid; p.m_rows = m_rows; p.n_total = n_total;
+    p.n_valid = n_logical_; p.d_valid = d_valid;
+    p.bias = d_bias_; p.bias_period = s.cout; p.noise = a.noise;
+    p.alpha = a.alpha; p.inv_alpha = a.inv_alpha; p.alpha_period = s.cin; p.prologue = a.prologue; p.act = a.act;
+    p.W_hi = d_w_hi_; p.W_lo = d_w_lo_; p.BN = bn_; p.n_tiles = n_tiles_; p.tiles_per_ntile = tiles_per_ntile_;
+    p.passes = mode_ == PREC_3XTF32 ? 3 : 1;
+    p.n_taps = (int)taps_.size();
+    for (int j = 0; j < p.n_taps; ++j) p.taps[j] = utaps_[j];
+    std::memcpy(p.tap_mask, tap_mask_, sizeof tap_mask_);
+    p.n_kc = n_kc_; p.kc_begin = kc_begin_; p.smin = smin_; p.span = span_;
+    p.batch = a.batch; p.m_tiles_per_clip = m_tiles;
+    p.fast_sin = g_fast_sin >= 0 ? g_fast_sin : (mode_ == PREC_TF32 ? 1 : 0);
+    check_launch(launch_conv_umma(p, ctx.num_sms, ctx.stream), name_.c_str());
+    ctx.end(ev, mode_ == PREC_3XTF32 ? "conv_umma_3xtf32" : "conv_umma_tf32", fl, bytes);
+  } else {
+    ConvSimtParams p{};
+    p.A = a.in; p.a_clip_stride = a_valid; p.a_rows = a_rows; p.a_pitch = k_view_; p.a_valid = a_valid;
+    p.D = a.out; p.R = a.residual; p.d_clip_stride = d_valid; p.m_rows = m_rows; p.n_total = n_total;
+    p.n_valid = n_logical_; p.d_valid = d_valid;
+    p.bias = d_bias_; p.bias_period = s.cout; p.noise = a.noise;
+    p.alpha = a.alpha; p.alpha_period = s.cin; p.prologue = a.prologue; p.act = a.act;
+    p.W = d_w_plain_; p.n_pad = n_pad_;
+    p.n_taps = (int)taps_.size();
+    for (int j = 0; j < p.n_taps; ++j) {
+      p.taps[j].shift = taps_[j].shift; p.taps[j].koff = taps_[j].koff; p.taps[j].klen = taps_[j].klen;
+      p.taps[j].w_off = simt_w_off_[j];
+    }
+    p.mask_bn = 0;
+    p.batch = a.batch; p.m_tiles_per_clip = m_tiles;
+    check_launch(launch_conv_simt(p, ctx.stream), name_.c_str());
+    ctx.end(ev, "conv_simt_fp32", fl, bytes);
+  }
+}
+
+}  // namespace nc

@@ -1,0 +1,82 @@
+// A weight-normalised Conv1d / ConvTranspose1d of the reference, lowered once at load time to a
+// multi-tap row-shifted GEMM plan (conv_plan.h) with packed device weights.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "conv_plan.h"
+#include "runtime.h"
+
+namespace nc {
+
+enum Precision : int { PREC_FP32 = 0, PREC_TF32 = 1, PREC_3XTF32 = 3 };
+
+Precision parse_precision(const std::string& s);
+// Snake prologue sin(): -1 = MUFU sin on tf32 layers only (default), 0 = always sinf, 1 = always MUFU
+void set_fast_sin_policy(int v);
+
+struct ConvSpec {
+  bool transposed = false;
+  int cin = 0, cout = 0, k = 1, stride = 1, dilation = 1, padding = 0, output_padding = 0;
+};
+
+struct ConvRunArgs {
+  const float* in = nullptr;        // [B][T_in][Cin] channels-last
+  float* out = nullptr;             // [B][T_out][Cout]
+  const float* residual = nullptr;  // same shape as out
+  const float* noise = nullptr;     // [B][T_out] (SNAC NoiseBlock: out = residual + noise * conv)
+  int batch = 0;
+  int t_in = 0;
+  int prologue = PRO_NONE;
+  const float* alpha = nullptr;      // device [Cin]
+  const float* inv_alpha = nullptr;  // device [Cin]
+  int act = ACT_NONE;
+  // row pitch override for the output (floats per output time step); 0 = Cout
+  int out_valid_cols = 0;            // logical Cout written (0 = all)
+};
+
+class ConvLayer {
+ public:
+  ConvLayer() = default;
+  ConvLayer(const ConvLayer&) = delete;
+  ConvLayer& operator=(const ConvLayer&) = delete;
+  ~ConvLayer();
+
+  // w: folded weights, conv [Cout][Cin][k] / transposed [Cin][Cout][k]; bias [Cout] or empty.
+  void build(const std::string& name, const ConvSpec& spec, const std::vector<float>& w,
+             const std::vector<float>& bias, Precision requested);
+  int out_len(int t_in) const;
+  void run(const ConvRunArgs& a, const LaunchCtx& ctx) const;
+
+  const ConvSpec& spec() const { return spec_; }
+  Precision precision() const { return mode_; }
+  const std::string& name() const { return name_; }
+  double flops(int batch, int t_in) const;
+
+ private:
+  struct Tap {
+    int shift, koff, klen;
+    std::vector<float> w;  // [n_logical][klen]
+  };
+  std::string name_;
+  ConvSpec spec_;
+  Precision mode_ = PREC_FP32;
+  int n_logical_ = 0;  // GEMM N: Cout, or stride*Cout for transposed
+  int n_pad_ = 0;      // rounded up to 16
+  int k_view_ = 0;     // floats per A-view row
+  std::vector<Tap> taps_;
+  // device
+  float* d_bias_ = nullptr;
+  float* d_w_plain_ = nullptr;
+  float* d_w_hi_ = nullptr;
+  float* d_w_lo_ = nullptr;
+  // UMMA tiling
+  int bn_ = 0, n_tiles_ = 0, tiles_per_ntile_ = 0;
+  ConvTap utaps_[kMaxTaps];
+  unsigned char tap_mask_[kMaxNTiles];
+  int kc_begin_ = 0, n_kc_ = 0, smin_ = 0, span_ = 0;
+  long long simt_w_off_[kMaxTaps];
+  bool umma_ok_ = false;
+};
+
+}  // namespace nc

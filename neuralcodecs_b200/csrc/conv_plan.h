@@ -1,0 +1,114 @@
+// Multi-tap row-shifted GEMM: the one formulation every conv on the codec hot path is
+// lowered to.  Activations live in HBM channels-last, [clip][time][channel] fp32.
+//
+//   D[b, m, n] = act( bias[n % bias_period]
+//                     + sum_taps sum_{k in [kc_lo*32, kc_hi*32)} f(A[b, m + shift_tap, k]) * W_tap[n, k]
+//                     (+ R[b, m, n]) )
+//
+// where the "A view" re-reads the channels-last input as rows of `a_pitch` floats:
+//   stride-1 conv (k taps, dilation d, padding p) : row = time step,  shift_j = j*d - p, K = Cin
+//   stride-s conv (kernel 2s)                      : row = s time steps (s*Cin floats); the kernel
+//                                                    taps fold into <=3 super-taps with partial K
+//   transposed conv (kernel 2s, stride s)          : row = input time step, N = s*Cout (phase-major),
+//                                                    <=3 super-taps, some masked per N tile
+// f = Snake / ELU prologue of the consumer (alpha indexed k % alpha_period), applied once per
+// staged input element.  Out-of-range rows read as zero (f(0) = 0 for both prologues).
+#pragma once
+#include <cstdint>
+
+namespace nc {
+
+constexpr int kMaxTaps = 8;
+constexpr int kMaxNTiles = 64;
+
+enum Prologue : int { PRO_NONE = 0, PRO_SNAKE = 1, PRO_ELU = 2 };
+enum Activation : int { ACT_NONE = 0, ACT_TANH = 1 };
+
+struct ConvTap {
+  int shift;      // row shift in the A view
+  int kc_lo;      // first 32-float K chunk of the A view this tap reads
+  int kc_hi;      // one past the last chunk
+  int tile_base;  // index of this tap's first weight tile inside an N tile's tile list
+};
+
+struct ConvGemmParams {
+  // ---- A view (input)
+  const float* A;
+  long long a_clip_stride;  // floats between clips
+  int a_rows;               // rows per clip
+  int a_pitch;              // floats per row
+  long long a_valid;        // valid floats per clip (guards a partial last row)
+  // ---- output / residual (same layout)
+  float* D;
+  const float* R;           // nullable
+  long long d_clip_stride;
+  int m_rows;               // output rows per clip
+  int n_total;              // floats per output row
+  int n_valid;              // logical N (<= n_tiles*BN)
+  long long d_valid;        // valid floats per clip
+  const float* bias;        // nullable
+  int bias_period;
+  const float* noise;       // nullable; [clip][m_rows]: D = R + noise*acc (SNAC NoiseBlock)
+  // ---- prologue / activation
+  const float* alpha;       // [alpha_period]
+  const float* inv_alpha;   // [alpha_period] (1/alpha, 0 where alpha == 0)
+  int alpha_period;
+  int prologue;
+  int act;
+  // ---- weights
+  const float* W_hi;        // UMMA: pre-swizzled tiles [n_tile][tiles_per_ntile][BN*32]; SIMT: plain [tap][N_pad][K_tap]
+  const float* W_lo;        // 3xTF32 residual tiles (same tiling) or null
+  int BN;                   // N tile (multiple of 16, <= 256)
+  int n_tiles;
+  int tiles_per_ntile;
+  int passes;               // 1 = tf32, 3 = 3xtf32
+  int n_taps;
+  ConvTap taps[kMaxTaps];
+  unsigned char tap_mask[kMaxNTiles];  // bit j set => tap j contributes to this N tile
+  int n_kc;                 // K chunks of the A view touched by any tap: [kc_begin, kc_begin + n_kc)
+  int kc_begin;
+  int smin;                 // min shift over taps
+  int span;                 // max shift - min shift
+  // ---- grid
+  int batch;
+  int m_tiles_per_clip;
+  int fast_sin;             // 1: MUFU-based sin in the Snake prologue (tf32 paths)
+};
+
+// ---- fp32 CUDA-core executor (conv_simt.cu): general tap extents, plain weights
+struct SimtTap {
+  int shift;
+  int koff;         // floats into the A-view row
+  int klen;         // floats
+  long long w_off;  // floats into W: this tap's [N_pad][klen] block
+};
+
+struct ConvSimtParams {
+  const float* A; long long a_clip_stride; int a_rows; int a_pitch; long long a_valid;
+  float* D; const float* R; long long d_clip_stride; int m_rows; int n_total; int n_valid; long long d_valid;
+  const float* bias; int bias_period;
+  const float* noise;
+  const float* alpha; int alpha_period; int prologue; int act;
+  const float* W; int n_pad;
+  int n_taps; SimtTap taps[kMaxTaps];
+  unsigned char tap_mask[kMaxNTiles]; int mask_bn;  // mask granularity in columns (0 = no masks)
+  int batch; int m_tiles_per_clip;
+};
+
+struct UmmaLaunch {
+  int w_stages;
+  int a_rows_alloc;  // multiple of 8
+};
+
+}  // namespace nc
+
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+namespace nc {
+// return 0 on success, a cudaError_t (>0) on launch failure, -1 when the shape does not fit
+int launch_conv_simt(const ConvSimtParams& p, cudaStream_t stream);
+int launch_conv_umma(const ConvGemmParams& p, int num_sms, cudaStream_t stream);
+// dynamic smem the tcgen05 kernel needs for this plan (0 = does not fit); fills L
+size_t umma_smem_bytes(const ConvGemmParams& p, UmmaLaunch* L);
+}  // namespace nc
+#endif

@@ -1,0 +1,516 @@
+// Engine base + DAC engine.  The DAC graph follows (paths under /root/reference/NeuralCodecs.Torch/):
+//   Models/DAC.cs:141-154 (Preprocess), :163-181 (Encode), :231-234 (Decode), :101-106 (FromCodes)
+//   Modules/DAC/Encoder.cs:21-58, EncoderBlock.cs:20-43, ResidualUnit.cs:24-59, Decoder.cs:22-58,
+//   DecoderBlock.cs:20-44, ResidualVectorQuantizer.cs:54-103,211-238
+// with activations channels-last in HBM and every Snake fused into the consuming conv's prologue.
+#include "engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace nc {
+
+// ------------------------------------------------------------------------------------ Engine
+Engine::Engine(int device_index) : device_(device_index) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    throw Error(NC_CUDA_UNAVAILABLE, "CUDA requested but not available");
+  }
+  if (device_index < 0 || device_index >= count)
+    throw Error(NC_INVALID_ARGUMENT, "device index " + std::to_string(device_index) + " out of range (" +
+                                         std::to_string(count) + " devices)");
+  cudaDeviceProp prop{};
+  NC_CUDA(cudaGetDeviceProperties(&prop, device_index));
+  if (prop.major != 10)
+    throw Error(NC_CUDA_UNAVAILABLE, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                                         std::to_string(prop.minor) + "; this library is built for sm_100a only");
+  num_sms_ = prop.multiProcessorCount;
+  NC_CUDA(cudaSetDevice(device_index));
+  NC_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+}
+
+Engine::~Engine() {
+  cudaSetDevice(device_);
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+void Engine::bind() const { NC_CUDA(cudaSetDevice(device_)); }
+
+LaunchCtx Engine::ctx() {
+  LaunchCtx c;
+  c.stream = stream_;
+  c.num_sms = num_sms_;
+  c.prof = prof_.enabled ? &prof_ : nullptr;
+  c.launches = &launches_;
+  return c;
+}
+
+void Engine::sync() { NC_CUDA(cudaStreamSynchronize(stream_)); }
+
+void Engine::set_option(const std::string& key, const std::string& value) {
+  if (key == "profile") {
+    prof_.enabled = value == "1" || value == "true";
+  } else if (key == "fast_sin") {
+    set_fast_sin_policy(std::atoi(value.c_str()));
+  } else if (key == "max_workspace_mb") {
+    const long long mb = std::atoll(value.c_str());
+    if (mb < 64) throw Error(NC_INVALID_ARGUMENT, "max_workspace_mb must be >= 64");
+    max_workspace_bytes_ = (size_t)mb << 20;
+  } else {
+    throw Error(NC_INVALID_ARGUMENT, "unknown option '" + key + "'");
+  }
+}
+
+void Engine::load_weights(const std::string& path) {
+  tensors_.clear();
+  load_safetensors(path, &tensors_);
+  finalize_weights();
+}
+
+const HostTensor& Engine::tensor(const std::string& name) const {
+  auto it = tensors_.find(name);
+  if (it == tensors_.end()) throw Error(NC_BAD_WEIGHTS, std::string("Failed to load ") + codec_name() +
+                                                            " weights: missing tensor '" + name + "'");
+  return it->second;
+}
+
+SnakeParams::~SnakeParams() {
+  cudaFree(alpha);
+  cudaFree(inv_alpha);
+}
+void SnakeParams::build(const std::vector<float>& a) {
+  std::vector<float> inv(a.size());
+  for (size_t i = 0; i < a.size(); ++i) inv[i] = a[i] == 0.f ? 0.f : 1.0f / a[i];
+  cudaFree(alpha);
+  cudaFree(inv_alpha);
+  alpha = upload(a);
+  inv_alpha = upload(inv);
+}
+
+// ------------------------------------------------------------------------------------ DAC
+DacEngine::DacEngine(const nc_dac_config& c, int device_index) : Engine(device_index) {
+  if (c.struct_size != sizeof(nc_dac_config)) throw Error(NC_INVALID_ARGUMENT, "nc_dac_config.struct_size mismatch");
+  if (c.n_encoder_rates < 1 || c.n_encoder_rates > NC_MAX_RATES || c.n_decoder_rates < 1 ||
+      c.n_decoder_rates > NC_MAX_RATES)
+    throw Error(NC_INVALID_ARGUMENT, "DAC config: rate count out of range");
+  cfg_.sample_rate = c.sample_rate;
+  cfg_.encoder_dim = c.encoder_dim;
+  cfg_.encoder_rates.assign(c.encoder_rates, c.encoder_rates + c.n_encoder_rates);
+  cfg_.decoder_dim = c.decoder_dim;
+  cfg_.decoder_rates.assign(c.decoder_rates, c.decoder_rates + c.n_decoder_rates);
+  cfg_.n_codebooks = c.n_codebooks;
+  cfg_.codebook_size = c.codebook_size;
+  cfg_.codebook_dim = c.codebook_dim;
+  // Models/DAC.cs:64 : LatentDim ?? encoderDim * 2^len(rates)
+  cfg_.latent_dim = c.latent_dim > 0 ? c.latent_dim : c.encoder_dim * (1 << c.n_encoder_rates);
+  if (cfg_.sample_rate <= 0 || cfg_.encoder_dim <= 0 || cfg_.decoder_dim <= 0 || cfg_.n_codebooks <= 0 ||
+      cfg_.codebook_size <= 0 || cfg_.codebook_dim <= 0)
+    throw Error(NC_INVALID_ARGUMENT, "DAC config: non-positive field");
+  for (int r : cfg_.encoder_rates)
+    if (r < 1) throw Error(NC_INVALID_ARGUMENT, "DAC config: bad encoder rate");
+  for (int r : cfg_.decoder_rates)
+    if (r < 1) throw Error(NC_INVALID_ARGUMENT, "DAC config: bad decoder rate");
+  if (cfg_.decoder_dim % (1 << cfg_.decoder_rates.size()) != 0)
+    throw Error(NC_INVALID_ARGUMENT, "DAC config: decoder_dim not divisible by 2^n_rates");
+}
+
+DacEngine::~DacEngine() {
+  cudaSetDevice(device_);
+  cudaFree(d_conv_in_w_);
+  cudaFree(d_conv_in_b_);
+  for (float* p : rvq_alloc_) cudaFree(p);
+}
+
+void DacEngine::set_option(const std::string& key, const std::string& value) {
+  if (key == "encoder_precision") {
+    enc_prec_ = parse_precision(value);
+    if (ready_) throw Error(NC_INVALID_ARGUMENT, "precision options must be set before weights are loaded");
+  } else if (key == "decoder_boost") {
+    dec_boost_ = value == "1" || value == "true";
+    if (ready_) throw Error(NC_INVALID_ARGUMENT, "precision options must be set before weights are loaded");
+  } else if (key == "decoder_precision") {
+    dec_prec_ = parse_precision(value);
+    if (ready_) throw Error(NC_INVALID_ARGUMENT, "precision options must be set before weights are loaded");
+  } else {
+    Engine::set_option(key, value);
+  }
+}
+
+void DacEngine::require_ready() const {
+  if (!ready_) throw Error(NC_INVALID_ARGUMENT, "DAC weights have not been loaded");
+}
+
+// Fold weight normalisation once, in fp32, as the reference does on every forward
+// (Modules/DAC/WNConv1d.cs:145-150, WNConvTranspose1d.cs:146-150): w = v / (||v||_(1,2) + 1e-7) * g.
+// HF-layout files carry only the folded `weight`; the reference then sets weight_v = weight and
+// weight_g = ||weight||_(1,2) (Config/DAC/StateDictNameConverter.cs:48-58).
+std::vector<float> DacEngine::folded_conv(const std::string& prefix, int d0, int d1, int k, std::vector<float>* bias,
+                                          int bias_n) {
+  const bool hf = has_tensor(prefix + ".weight");
+  const HostTensor& v = tensor(hf ? prefix + ".weight" : prefix + ".weight_v");
+  if (v.is_int || v.shape.size() != 3 || v.shape[0] != d0 || v.shape[1] != d1 || v.shape[2] != k)
+    throw Error(NC_SHAPE_MISMATCH, "Failed to load DAC weights: '" + prefix + "' has the wrong shape");
+  const HostTensor* g = hf ? nullptr : &tensor(prefix + ".weight_g");
+  if (g && (g->is_int || (int64_t)g->numel() != d0))
+    throw Error(NC_SHAPE_MISMATCH, "Failed to load DAC weights: '" + prefix + ".weight_g' has the wrong shape");
+  std::vector<float> w(v.f32.size());
+  const size_t inner = (size_t)d1 * k;
+  for (int i = 0; i < d0; ++i) {
+    double ss = 0;
+    for (size_t j = 0; j < inner; ++j) ss += (double)v.f32[i * inner + j] * v.f32[i * inner + j];
+    const float norm = std::sqrt((float)ss);
+    const float gi = g ? g->f32[i] : norm;
+    const float denom = norm + 1e-7f;
+    for (size_t j = 0; j < inner; ++j) w[i * inner + j] = (v.f32[i * inner + j] / denom) * gi;
+  }
+  if (bias) {
+    bias->clear();
+    if (has_tensor(prefix + ".bias")) {
+      const HostTensor& b = tensor(prefix + ".bias");
+      if (b.is_int || (int)b.numel() != bias_n)
+        throw Error(NC_SHAPE_MISMATCH, "Failed to load DAC weights: '" + prefix + ".bias' has the wrong shape");
+      *bias = b.f32;
+    }
+  }
+  return w;
+}
+
+static std::vector<float> alpha_of(const HostTensor& t, int c, const std::string& name) {
+  if (t.is_int || (int)t.numel() != c)
+    throw Error(NC_SHAPE_MISMATCH, "Failed to load DAC weights: '" + name + "' has the wrong shape");
+  return t.f32;
+}
+
+// Precision policy of the decoder's "tf32" mode (measured with a CPU emulation of tf32 operand
+// rounding, DESIGN.md "Precision"): the final 96->1 conv and the 1x1 convs of the two narrow
+// blocks contribute most of the output error and are HBM-bound anyway, so they run 3xTF32.
+Precision DacEngine::boosted(Precision p, bool narrow) const {
+  return (p == PREC_TF32 && dec_boost_ && narrow) ? PREC_3XTF32 : p;
+}
+
+void DacEngine::build_ru(ResUnit& ru, const std::string& p, int dim, int dil, Precision prec) {
+  std::vector<float> b;
+  ru.s1.build(alpha_of(tensor(p + ".snake1.alpha"), dim, p + ".snake1.alpha"));
+  ru.s2.build(alpha_of(tensor(p + ".snake2.alpha"), dim, p + ".snake2.alpha"));
+  ConvSpec s1;
+  s1.cin = s1.cout = dim; s1.k = 7; s1.dilation = dil; s1.padding = (7 - 1) * dil / 2;  // ResidualUnit.cs:27
+  auto w1 = folded_conv(p + ".conv1", dim, dim, 7, &b, dim);
+  ru.c1.build(p + ".conv1", s1, w1, b, prec);
+  ConvSpec s2;
+  s2.cin = s2.cout = dim; s2.k = 1;
+  auto w2 = folded_conv(p + ".conv2", dim, dim, 1, &b, dim);
+  const bool is_dec = p.compare(0, 8, "decoder.") == 0;
+  ru.c2.build(p + ".conv2", s2, w2, b, is_dec ? boosted(prec, dim <= 192) : prec);
+}
+
+void DacEngine::finalize_weights() {
+  bind();
+  ready_ = false;
+  std::vector<float> b;
+  // ---- encoder (Modules/DAC/Encoder.cs:21-58)
+  int d = cfg_.encoder_dim;
+  {
+    auto w = folded_conv("encoder.conv1", d, 1, 7, &b, d);
+    if (b.empty()) b.assign(d, 0.f);
+    cudaFree(d_conv_in_w_); cudaFree(d_conv_in_b_);
+    d_conv_in_w_ = upload(w);
+    d_conv_in_b_ = upload(b);
+  }
+  enc_blocks_.clear();
+  for (size_t i = 0; i < cfg_.encoder_rates.size(); ++i) {
+    const int s = cfg_.encoder_rates[i];
+    auto blk = std::make_unique<EncBlock>();
+    const std::string p = "encoder.block." + std::to_string(i);
+    const int dils[3] = {1, 3, 9};
+    for (int u = 0; u < 3; ++u) build_ru(blk->ru[u], p + ".res_unit" + std::to_string(u + 1), d, dils[u], enc_prec_);
+    blk->s.build(alpha_of(tensor(p + ".snake1.alpha"), d, p + ".snake1.alpha"));
+    ConvSpec cs;
+    cs.cin = d; cs.cout = 2 * d; cs.k = 2 * s; cs.stride = s; cs.padding = (s + 1) / 2;  // EncoderBlock.cs:27-33
+    auto w = folded_conv(p + ".conv1", 2 * d, d, 2 * s, &b, 2 * d);
+    blk->down.build(p + ".conv1", cs, w, b, enc_prec_);
+    enc_blocks_.push_back(std::move(blk));
+    d *= 2;
+  }
+  enc_snake_.build(alpha_of(tensor("encoder.snake1.alpha"), d, "encoder.snake1.alpha"));
+  {
+    ConvSpec cs;
+    cs.cin = d; cs.cout = cfg_.latent_dim; cs.k = 3; cs.padding = 1;
+    auto w = folded_conv("encoder.conv2", cfg_.latent_dim, d, 3, &b, cfg_.latent_dim);
+    enc_out_.build("encoder.conv2", cs, w, b, enc_prec_);
+  }
+  // ---- quantiser (Modules/DAC/VectorQuantizer.cs:36-43)
+  {
+    for (float* p : rvq_alloc_) cudaFree(p);
+    rvq_alloc_.clear();
+    const int nq = cfg_.n_codebooks, D = cfg_.codebook_dim, K = cfg_.codebook_size, Dz = cfg_.latent_dim;
+    std::vector<float> in_w((size_t)nq * D * Dz), in_b((size_t)nq * D), cb((size_t)nq * K * D), cb_sq((size_t)nq * K),
+        out_w((size_t)nq * Dz * D), out_b((size_t)nq * Dz);
+    for (int q = 0; q < nq; ++q) {
+      const std::string p = "quantizer.quantizers." + std::to_string(q);
+      auto wi = folded_conv(p + ".in_proj", D, Dz, 1, &b, D);
+      if (b.empty()) b.assign(D, 0.f);
+      std::copy(wi.begin(), wi.end(), in_w.begin() + (size_t)q * D * Dz);
+      std::copy(b.begin(), b.end(), in_b.begin() + (size_t)q * D);
+      auto wo = folded_conv(p + ".out_proj", Dz, D, 1, &b, Dz);
+      if (b.empty()) b.assign(Dz, 0.f);
+      std::copy(wo.begin(), wo.end(), out_w.begin() + (size_t)q * Dz * D);
+      std::copy(b.begin(), b.end(), out_b.begin() + (size_t)q * Dz);
+      const HostTensor& c = tensor(p + ".codebook.weight");
+      if (c.is_int || c.shape.size() != 2 || c.shape[0] != K || c.shape[1] != D)
+        throw Error(NC_SHAPE_MISMATCH, "Failed to load DAC weights: '" + p + ".codebook.weight' has the wrong shape");
+      std::copy(c.f32.begin(), c.f32.end(), cb.begin() + (size_t)q * K * D);
+      for (int k = 0; k < K; ++k) {
+        float s = 0.f;
+        for (int dd = 0; dd < D; ++dd) {
+          const float x = c.f32[(size_t)k * D + dd];
+          const float x2 = x * x;
+          s += x2;
+        }
+        cb_sq[(size_t)q * K + k] = s;
+      }
+    }
+    rvq_.n_stages = nq; rvq_.Dz = Dz; rvq_.D = D; rvq_.K = K;
+    float* p;
+    rvq_alloc_.push_back(p = upload(in_w)); rvq_.in_w = p;
+    rvq_alloc_.push_back(p = upload(in_b)); rvq_.in_b = p;
+    rvq_alloc_.push_back(p = upload(cb)); rvq_.cb = p;
+    rvq_alloc_.push_back(p = upload(cb_sq)); rvq_.cb_sq = p;
+    rvq_alloc_.push_back(p = upload(out_w)); rvq_.out_w = p;
+    rvq_alloc_.push_back(p = upload(out_b)); rvq_.out_b = p;
+  }
+  // ---- decoder (Modules/DAC/Decoder.cs:22-58)
+  const int C = cfg_.decoder_dim;
+  {
+    ConvSpec cs;
+    cs.cin = cfg_.latent_dim; cs.cout = C; cs.k = 7; cs.padding = 3;
+    auto w = folded_conv("decoder.conv1", C, cfg_.latent_dim, 7, &b, C);
+    dec_in_.build("decoder.conv1", cs, w, b, dec_prec_);
+  }
+  dec_blocks_.clear();
+  int cout = C;
+  for (size_t i = 0; i < cfg_.decoder_rates.size(); ++i) {
+    const int s = cfg_.decoder_rates[i];
+    const int cin = C / (1 << i);
+    cout = C / (1 << (i + 1));
+    auto blk = std::make_unique<DecBlock>();
+    const std::string p = "decoder.block." + std::to_string(i);
+    blk->s.build(alpha_of(tensor(p + ".snake1.alpha"), cin, p + ".snake1.alpha"));
+    ConvSpec cs;
+    cs.transposed = true; cs.cin = cin; cs.cout = cout; cs.k = 2 * s; cs.stride = s; cs.padding = (s + 1) / 2;
+    auto w = folded_conv(p + ".conv_t1", cin, cout, 2 * s, &b, cout);  // norm per in-channel (dims 1,2 of [Cin,Cout,k])
+    blk->up.build(p + ".conv_t1", cs, w, b, dec_prec_);
+    const int dils[3] = {1, 3, 9};
+    for (int u = 0; u < 3; ++u) build_ru(blk->ru[u], p + ".res_unit" + std::to_string(u + 1), cout, dils[u], dec_prec_);
+    dec_blocks_.push_back(std::move(blk));
+  }
+  dec_snake_.build(alpha_of(tensor("decoder.snake1.alpha"), cout, "decoder.snake1.alpha"));
+  {
+    ConvSpec cs;
+    cs.cin = cout; cs.cout = 1; cs.k = 7; cs.padding = 3;
+    auto w = folded_conv("decoder.conv2", 1, cout, 7, &b, 1);
+    dec_out_.build("decoder.conv2", cs, w, b, boosted(dec_prec_, true));
+  }
+  drop_tensors();
+  ready_ = true;
+}
+
+int64_t DacEngine::padded_length(int64_t L) const {
+  const int64_t hop = cfg_.hop();
+  return (L + hop - 1) / hop * hop;  // Models/DAC.cs:151-153
+}
+
+int64_t DacEngine::decoded_length(int64_t T) const {
+  int64_t t = dec_in_.out_len((int)T);
+  for (auto& b : dec_blocks_) t = b->up.out_len((int)t);
+  return dec_out_.out_len((int)t);
+}
+
+int DacEngine::micro_batch(int B, int64_t Lp) const {
+  // per clip: 3 rotating buffers of max(Lp*enc_dim, decoder peak) floats
+  const int64_t T = Lp / cfg_.hop();
+  int64_t peak = Lp * cfg_.encoder_dim;
+  int64_t t = dec_in_.out_len((int)T);
+  peak = std::max<int64_t>(peak, t * cfg_.decoder_dim);
+  int c = cfg_.decoder_dim;
+  for (auto& b : dec_blocks_) {
+    t = b->up.out_len((int)t);
+    c /= 2;
+    peak = std::max<int64_t>(peak, t * c);
+  }
+  const double per_clip = 3.0 * (double)peak * 4 + 2.0 * (double)T * cfg_.latent_dim * 4;
+  int mb = (int)std::max(1.0, std::floor((double)max_workspace_bytes_ / per_clip));
+  const_cast<DacEngine*>(this)->per_clip_elems_ = peak;
+  return std::min(mb, B);
+}
+
+void DacEngine::ensure_workspace(int mb, int64_t Lp) {
+  micro_batch(mb, Lp);
+  const int64_t T = Lp / cfg_.hop();
+  for (auto& w : ws_) w.reserve((size_t)mb * per_clip_elems_ * sizeof(float));
+  z_in_.reserve((size_t)mb * T * cfg_.latent_dim * sizeof(float));
+  z_q_.reserve((size_t)mb * T * cfg_.latent_dim * sizeof(float));
+}
+
+int DacEngine::run_ru(const ResUnit& ru, int cur, int B, int T) {
+  const LaunchCtx c = ctx();
+  const int h = (cur + 1) % 3, y = (cur + 2) % 3;
+  ConvRunArgs a;
+  a.in = buf(cur); a.out = buf(h); a.batch = B; a.t_in = T;
+  a.prologue = PRO_SNAKE; a.alpha = ru.s1.alpha; a.inv_alpha = ru.s1.inv_alpha;
+  ru.c1.run(a, c);
+  ConvRunArgs b;
+  b.in = buf(h); b.out = buf(y); b.residual = buf(cur); b.batch = B; b.t_in = T;
+  b.prologue = PRO_SNAKE; b.alpha = ru.s2.alpha; b.inv_alpha = ru.s2.inv_alpha;
+  ru.c2.run(b, c);
+  return y;
+}
+
+int DacEngine::run_encoder(const float* audio, long long audio_stride, int in_len, int B, int Lp, int* T_out) {
+  const LaunchCtx c = ctx();
+  launch_conv_cin1(audio, audio_stride, in_len, buf(0), Lp, cfg_.encoder_dim, d_conv_in_w_, d_conv_in_b_, 7, 1, 3, B, c);
+  int cur = 0, T = Lp;
+  for (auto& blk : enc_blocks_) {
+    for (int u = 0; u < 3; ++u) cur = run_ru(blk->ru[u], cur, B, T);
+    ConvRunArgs a;
+    a.in = buf(cur); a.out = buf((cur + 1) % 3); a.batch = B; a.t_in = T;
+    a.prologue = PRO_SNAKE; a.alpha = blk->s.alpha; a.inv_alpha = blk->s.inv_alpha;
+    blk->down.run(a, c);
+    T = blk->down.out_len(T);
+    cur = (cur + 1) % 3;
+  }
+  ConvRunArgs a;
+  a.in = buf(cur); a.out = z_in_.as<float>(); a.batch = B; a.t_in = T;
+  a.prologue = PRO_SNAKE; a.alpha = enc_snake_.alpha; a.inv_alpha = enc_snake_.inv_alpha;
+  enc_out_.run(a, c);
+  *T_out = enc_out_.out_len(T);
+  return cur;
+}
+
+// input latent: z_q_ [B][T][latent] channels-last
+int DacEngine::run_decoder(int, int B, int T, float* audio_out, long long) {
+  const LaunchCtx c = ctx();
+  ConvRunArgs a;
+  a.in = z_q_.as<float>(); a.out = buf(0); a.batch = B; a.t_in = T;
+  dec_in_.run(a, c);
+  int cur = 0;
+  T = dec_in_.out_len(T);
+  for (auto& blk : dec_blocks_) {
+    ConvRunArgs u;
+    u.in = buf(cur); u.out = buf((cur + 1) % 3); u.batch = B; u.t_in = T;
+    u.prologue = PRO_SNAKE; u.alpha = blk->s.alpha; u.inv_alpha = blk->s.inv_alpha;
+    blk->up.run(u, c);
+    T = blk->up.out_len(T);
+    cur = (cur + 1) % 3;
+    for (int r = 0; r < 3; ++r) cur = run_ru(blk->ru[r], cur, B, T);
+  }
+  ConvRunArgs o;
+  o.in = buf(cur); o.out = audio_out; o.batch = B; o.t_in = T;
+  o.prologue = PRO_SNAKE; o.alpha = dec_snake_.alpha; o.inv_alpha = dec_snake_.inv_alpha;
+  o.act = ACT_TANH;
+  dec_out_.run(o, c);
+  return cur;
+}
+
+static int clamp_nq(int nq, int n_codebooks) { return (nq <= 0 || nq > n_codebooks) ? n_codebooks : nq; }
+
+void DacEngine::encode_dev(const float* audio, int B, int64_t L, int nq_in, float* z, int64_t* codes, float* latents) {
+  forward_impl(audio, B, L, nq_in, nullptr, codes, z, latents);
+}
+
+void DacEngine::forward_dev(const float* audio, int B, int64_t L, int nq_in, float* audio_out, int64_t* codes, float* z) {
+  forward_impl(audio, B, L, nq_in, audio_out, codes, z, nullptr);
+}
+
+void DacEngine::forward_impl(const float* audio, int B, int64_t L, int nq_in, float* audio_out, int64_t* codes, float* z,
+                             float* latents) {
+  require_ready();
+  bind();
+  if (B <= 0 || L <= 0) throw Error(NC_INVALID_ARGUMENT, "batch and length must be positive");
+  const int nq = clamp_nq(nq_in, cfg_.n_codebooks);
+  const int64_t Lp = padded_length(L);
+  if (Lp > (int64_t)1 << 30) throw Error(NC_INVALID_ARGUMENT, "clip too long");
+  const int mb = micro_batch(B, Lp);
+  ensure_workspace(mb, Lp);
+  const int64_t T = Lp / cfg_.hop();
+  const int64_t out_len = decoded_length(T);
+  const LaunchCtx c = ctx();
+  for (int b0 = 0; b0 < B; b0 += mb) {
+    const int nb = std::min(mb, B - b0);
+    int Tm = 0;
+    run_encoder(audio + (int64_t)b0 * L, L, (int)L, nb, (int)Lp, &Tm);
+    launch_rvq_encode(rvq_, z_in_.as<float>(), z_q_.as<float>(), codes ? codes + (int64_t)b0 * nq * T : nullptr,
+                      latents ? latents + (int64_t)b0 * nq * cfg_.codebook_dim * T : nullptr, nb, Tm, nq, c);
+    if (z) launch_transpose_tc_to_ct(z_q_.as<float>(), z + (int64_t)b0 * cfg_.latent_dim * T, nb, cfg_.latent_dim, Tm, c);
+    if (audio_out) run_decoder(0, nb, Tm, audio_out + (int64_t)b0 * out_len, out_len);
+  }
+  sync();
+}
+
+void DacEngine::decode_dev(const float* z, int B, int64_t T, float* audio_out) {
+  require_ready();
+  bind();
+  if (B <= 0 || T <= 0) throw Error(NC_INVALID_ARGUMENT, "batch and frames must be positive");
+  const int64_t Lp = T * cfg_.hop();
+  const int mb = micro_batch(B, Lp);
+  ensure_workspace(mb, Lp);
+  const int64_t out_len = decoded_length(T);
+  const LaunchCtx c = ctx();
+  for (int b0 = 0; b0 < B; b0 += mb) {
+    const int nb = std::min(mb, B - b0);
+    launch_transpose_ct_to_tc(z + (int64_t)b0 * cfg_.latent_dim * T, z_q_.as<float>(), nb, cfg_.latent_dim, (int)T, c);
+    run_decoder(0, nb, (int)T, audio_out + (int64_t)b0 * out_len, out_len);
+  }
+  sync();
+}
+
+void DacEngine::from_codes_dev(const int64_t* codes, int B, int nq, int64_t T, float* z) {
+  require_ready();
+  bind();
+  if (B <= 0 || T <= 0 || nq <= 0 || nq > cfg_.n_codebooks)
+    throw Error(NC_INVALID_ARGUMENT, "from_codes: bad batch / frames / n_quantizers");
+  const int64_t Lp = T * cfg_.hop();
+  const int mb = micro_batch(B, Lp);
+  ensure_workspace(mb, Lp);
+  const LaunchCtx c = ctx();
+  for (int b0 = 0; b0 < B; b0 += mb) {
+    const int nb = std::min(mb, B - b0);
+    launch_rvq_from_codes(rvq_, codes + (int64_t)b0 * nq * T, z_q_.as<float>(), nb, (int)T, nq, c);
+    launch_transpose_tc_to_ct(z_q_.as<float>(), z + (int64_t)b0 * cfg_.latent_dim * T, nb, cfg_.latent_dim, (int)T, c);
+  }
+  sync();
+}
+
+void DacEngine::decode_codes_dev(const int64_t* codes, int B, int nq, int64_t T, float* audio_out) {
+  require_ready();
+  bind();
+  if (B <= 0 || T <= 0 || nq <= 0 || nq > cfg_.n_codebooks)
+    throw Error(NC_INVALID_ARGUMENT, "decode_codes: bad batch / frames / n_quantizers");
+  const int64_t Lp = T * cfg_.hop();
+  const int mb = micro_batch(B, Lp);
+  ensure_workspace(mb, Lp);
+  const int64_t out_len = decoded_length(T);
+  const LaunchCtx c = ctx();
+  for (int b0 = 0; b0 < B; b0 += mb) {
+    const int nb = std::min(mb, B - b0);
+    launch_rvq_from_codes(rvq_, codes + (int64_t)b0 * nq * T, z_q_.as<float>(), nb, (int)T, nq, c);
+    run_decoder(0, nb, (int)T, audio_out + (int64_t)b0 * out_len, out_len);
+  }
+  sync();
+}
+
+Engine* create_engine(nc_codec_kind kind, const void* cfg, size_t cfg_size, int device_index) {
+  if (!cfg) throw Error(NC_INVALID_ARGUMENT, "config is null");
+  switch (kind) {
+    case NC_CODEC_DAC: {
+      if (cfg_size != sizeof(nc_dac_config)) throw Error(NC_INVALID_ARGUMENT, "cfg_size != sizeof(nc_dac_config)");
+      return new DacEngine(*static_cast<const nc_dac_config*>(cfg), device_index);
+    }
+    default:
+      throw Error(NC_UNSUPPORTED, "codec kind not built into this library yet");
+  }
+}
+
+}  // namespace nc

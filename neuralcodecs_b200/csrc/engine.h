@@ -1,0 +1,147 @@
+// Engine objects behind an nc_handle.
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "codec_kernels.h"
+#include "conv_layer.h"
+#include "runtime.h"
+#include "safetensors.h"
+
+namespace nc {
+
+// Base of every codec engine: device binding, stream, profiler, named host tensors.
+class Engine {
+ public:
+  Engine(int device_index);
+  virtual ~Engine();
+  virtual const char* codec_name() const = 0;
+  virtual void finalize_weights() = 0;
+  virtual void set_option(const std::string& key, const std::string& value);
+
+  void load_weights(const std::string& path);
+  void set_tensor(const std::string& name, HostTensor&& t) { tensors_[name] = std::move(t); }
+  void bind() const;  // cudaSetDevice
+  LaunchCtx ctx();
+  uint64_t launches() const { return launches_; }
+  Profiler& profiler() { return prof_; }
+  void sync();
+
+  // re-entrancy guard (a handle is one-thread-at-a-time)
+  bool busy = false;
+
+ protected:
+  const HostTensor& tensor(const std::string& name) const;
+  bool has_tensor(const std::string& name) const { return tensors_.count(name) != 0; }
+  void drop_tensors() { tensors_.clear(); }
+
+  int device_ = 0;
+  int num_sms_ = 148;
+  cudaStream_t stream_ = nullptr;
+  Profiler prof_;
+  uint64_t launches_ = 0;
+  size_t max_workspace_bytes_ = (size_t)32 << 30;
+  TensorMap tensors_;
+  bool ready_ = false;
+};
+
+struct SnakeParams {
+  float* alpha = nullptr;      // device [C]
+  float* inv_alpha = nullptr;  // device [C]
+  ~SnakeParams();
+  void build(const std::vector<float>& a);
+};
+
+// ------------------------------------------------------------------------------------ DAC
+struct DacConfig {
+  int sample_rate = 44100;
+  int encoder_dim = 64;
+  std::vector<int> encoder_rates{2, 4, 8, 8};
+  int decoder_dim = 1536;
+  std::vector<int> decoder_rates{8, 8, 4, 2};
+  int n_codebooks = 9, codebook_size = 1024, codebook_dim = 8;
+  int latent_dim = 1024;
+  int hop() const {
+    int h = 1;
+    for (int r : encoder_rates) h *= r;
+    return h;
+  }
+};
+
+class DacEngine : public Engine {
+ public:
+  DacEngine(const nc_dac_config& cfg, int device_index);
+  ~DacEngine() override;
+  const char* codec_name() const override { return "DAC"; }
+  void finalize_weights() override;
+  void set_option(const std::string& key, const std::string& value) override;
+  const DacConfig& config() const { return cfg_; }
+
+  int64_t padded_length(int64_t L) const;
+  int64_t frames(int64_t L) const { return padded_length(L) / cfg_.hop(); }
+  int64_t decoded_length(int64_t T) const;  // samples produced by Decode for T frames
+
+  // All pointers are device memory on this engine's device; nullable outputs may be null.
+  // audio [B][L]; audio_out [B][decoded_length(T)]; codes [B][nq][T]; z [B][latent][T]; latents [B][nq*D][T]
+  void encode_dev(const float* audio, int B, int64_t L, int nq, float* z, int64_t* codes, float* latents);
+  void decode_dev(const float* z, int B, int64_t T, float* audio_out);
+  void from_codes_dev(const int64_t* codes, int B, int nq, int64_t T, float* z);
+  void decode_codes_dev(const int64_t* codes, int B, int nq, int64_t T, float* audio_out);
+  void forward_dev(const float* audio, int B, int64_t L, int nq, float* audio_out, int64_t* codes, float* z);
+
+ private:
+  struct ResUnit {
+    SnakeParams s1, s2;
+    ConvLayer c1, c2;
+  };
+  struct EncBlock {
+    ResUnit ru[3];
+    SnakeParams s;
+    ConvLayer down;
+  };
+  struct DecBlock {
+    SnakeParams s;
+    ConvLayer up;
+    ResUnit ru[3];
+  };
+  void require_ready() const;
+  void forward_impl(const float* audio, int B, int64_t L, int nq, float* audio_out, int64_t* codes, float* z,
+                    float* latents);
+  std::vector<float> folded_conv(const std::string& prefix, int d0, int d1, int k, std::vector<float>* bias,
+                                 int bias_n);
+  Precision boosted(Precision p, bool narrow) const;
+  void build_ru(ResUnit& ru, const std::string& prefix, int dim, int dil, Precision prec);
+  // returns the buffer index holding the result; T_io: in = input length, out = output length
+  int run_ru(const ResUnit& ru, int cur, int B, int T);
+  int run_encoder(const float* audio, long long audio_stride, int in_len, int B, int Lp, int* T_out);
+  int run_decoder(int cur, int B, int T, float* audio_out, long long out_stride);
+  int micro_batch(int B, int64_t Lp) const;
+  void ensure_workspace(int mb, int64_t Lp);
+  float* buf(int i) { return ws_[i].as<float>(); }
+
+  DacConfig cfg_;
+  Precision enc_prec_ = PREC_3XTF32, dec_prec_ = PREC_TF32;
+  bool dec_boost_ = true;
+  // encoder
+  float* d_conv_in_w_ = nullptr;
+  float* d_conv_in_b_ = nullptr;
+  std::vector<std::unique_ptr<EncBlock>> enc_blocks_;
+  SnakeParams enc_snake_;
+  ConvLayer enc_out_;
+  // quantiser
+  RvqWeights rvq_{};
+  std::vector<float*> rvq_alloc_;
+  // decoder
+  ConvLayer dec_in_;
+  std::vector<std::unique_ptr<DecBlock>> dec_blocks_;
+  SnakeParams dec_snake_;
+  ConvLayer dec_out_;
+  // workspaces: 3 rotating activation buffers + latent buffers
+  DeviceBuffer ws_[3], z_in_, z_q_;
+  int64_t per_clip_elems_ = 0;  // per padded sample, see ensure_workspace
+};
+
+Engine* create_engine(nc_codec_kind kind, const void* cfg, size_t cfg_size, int device_index);
+
+}  // namespace nc

@@ -1,0 +1,58 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CACHE = os.path.join(ROOT, "tests", ".cache")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with `-m gpu` on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def cache_dir():
+    os.makedirs(CACHE, exist_ok=True)
+    return CACHE
+
+
+def _write_weights(cfg, path, codebooks, seconds):
+    from oracle import synth
+    if not os.path.exists(path):
+        sd = synth.make_dac_weights_hf(cfg, codebooks=codebooks, codebook_seconds=seconds)
+        synth.save_safetensors(sd, path + ".tmp")
+        os.replace(path + ".tmp", path)
+    return path
+
+
+@pytest.fixture(scope="session")
+def dac_tiny(cache_dir):
+    """(oracle cfg, engine cfg, weights path): 16 kHz, channels not multiples of 32 -> fp32 CUDA-core path."""
+    from oracle import dac as odac
+    import neuralcodecs_b200 as nc
+    co = odac.DACConfig(sample_rate=16000, encoder_dim=16, decoder_dim=128, n_codebooks=4, codebook_size=64)
+    ce = nc.DACConfig(sample_rate=16000, encoder_dim=16, decoder_dim=128, num_codebooks=4, codebook_size=64)
+    return co, ce, _write_weights(co, os.path.join(cache_dir, "dac_tiny.safetensors"), "data", 2.0)
+
+
+@pytest.fixture(scope="session")
+def dac_mid(cache_dir):
+    """Small config whose channel counts are multiples of 32 -> tcgen05 path."""
+    from oracle import dac as odac
+    import neuralcodecs_b200 as nc
+    co = odac.DACConfig(sample_rate=16000, encoder_dim=32, decoder_dim=512, n_codebooks=4, codebook_size=256)
+    ce = nc.DACConfig(sample_rate=16000, encoder_dim=32, decoder_dim=512, num_codebooks=4, codebook_size=256)
+    return co, ce, _write_weights(co, os.path.join(cache_dir, "dac_mid.safetensors"), "data", 2.0)
+
+
+@pytest.fixture(scope="session")
+def dac_full(cache_dir):
+    """DAC 44.1 kHz preset (BASELINE configs #1/#4/#5) with seeded weights + data-fitted codebooks."""
+    from oracle import dac as odac
+    import neuralcodecs_b200 as nc
+    co, ce = odac.DACConfig.dac_44khz(), nc.DACConfig.DAC44kHz()
+    return co, ce, _write_weights(co, os.path.join(cache_dir, "dac44_seed4321.safetensors"), "data", 10.0)

@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""bench.py -- audio-seconds per second of the DAC 44.1 kHz encode+decode hot path.
+
+Workload (BASELINE.json configs[3], the configuration the metric is quoted on):
+DAC 44.1 kHz, 9 codebooks, 512 clips x 30 s of synthetic mono audio, sharded by batch across
+the ranks (one process per GPU, no collective on the data path; strong scaling: the global
+batch is fixed).  One step = one encode -> RVQ -> decode pass over the rank's shard through
+the C ABI of libneuralcodecs_cuda.so.
+
+  value : whole-job audio-s/s, inputs and outputs resident in HBM (nc_dac_forward_dev)
+  e2e   : the same pass through the host-buffer entry point (nc_dac_forward) with pinned
+          host audio in and codes + audio out, copies inside the timed region
+  roofline     : the tcgen05 implicit-GEMM conv kernel (tensor bound), timed live with CUDA
+                 events on the engine's stream over one extra profiled pass
+  cpu_baseline : the CPU oracle (PyTorch restatement of the reference's op stream) on a
+                 bounded sample, rank 0, N=1 only
+
+`--impl reference` times that CPU oracle alone (the reference is C#/TorchSharp and cannot run
+here).  Nothing in the timed GPU path imports oracle/.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "audio_seconds_per_second_encode_decode"
+UNIT = "audio-s/s"
+SAMPLE_RATE = 44100
+GFLOP_PER_AUDIO_S = 199.98        # conv/GEMM work of DAC-44.1k encode+decode
+WORKLOADS = {
+    # name: (global batch, seconds per clip, decode_only)
+    "dac44k_b512x30s": (512, 30.0, False),       # BASELINE configs[3]
+    "dac44k_b1x10s": (1, 10.0, False),           # BASELINE configs[0]
+    "dia_dac_decode_b256x20s": (256, 20.004, True),  # BASELINE configs[4]
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="dac44k_b512x30s", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override the global batch (debug)")
+    ap.add_argument("--seconds", type=float, default=0.0, help="override seconds per clip (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--encoder-precision", default=None)
+    ap.add_argument("--decoder-precision", default=None)
+    ap.add_argument("--workspace-mb", type=int, default=0)
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); smax.append(float(p[1])); power.append(float(p[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_oracle_rate(budget_s: float, weights_path: str, threads: int):
+    """audio-s/s of the CPU oracle (encode -> RVQ -> decode) on a bounded sample.  The ONLY place
+    bench.py executes oracle/ (the checker, used here as the reported CPU baseline)."""
+    import numpy as np
+    import torch
+    from oracle import dac as odac
+    from neuralcodecs_b200 import synthetic
+
+    torch.set_num_threads(threads)
+    cfg = odac.DACConfig.dac_44khz()
+    model = odac.load_hf_safetensors(weights_path, cfg)
+
+    def run(seconds):
+        x = torch.from_numpy(synthetic.synth_audio(1, int(round(seconds * SAMPLE_RATE)), SAMPLE_RATE)).unsqueeze(1)
+        t0 = time.perf_counter()
+        model.forward(x)
+        return time.perf_counter() - t0
+
+    run(0.5)                                   # warm-up (thread pool, oneDNN primitives)
+    t1 = run(1.0)
+    seconds = max(1.0, min(30.0, budget_s / max(t1, 1e-3)))
+    seconds = float(int(seconds))
+    dt = run(seconds)
+    return seconds / dt, seconds, dt
+
+
+def reference_arm(args, rank: int):
+    """`--impl reference`: the reference's CPU implementation of the path.  The reference itself
+    (C# + TorchSharp/libtorch) cannot run here; the oracle issues the same ATen op stream."""
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    wpath = ensure_weights()
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    budget = 150.0 / (steps + warm)
+    torch.set_num_threads(threads)
+    import numpy as np
+    from oracle import dac as odac
+    from neuralcodecs_b200 import synthetic
+    model = odac.load_hf_safetensors(wpath, odac.DACConfig.dac_44khz())
+
+    def run(seconds):
+        x = torch.from_numpy(synthetic.synth_audio(1, int(round(seconds * SAMPLE_RATE)), SAMPLE_RATE)).unsqueeze(1)
+        t0 = time.perf_counter()
+        model.forward(x)
+        return time.perf_counter() - t0
+
+    run(0.5)
+    t1 = run(1.0)
+    seconds = float(int(max(1.0, min(30.0, budget / max(t1, 1e-3)))))
+    for _ in range(warm):
+        run(seconds)
+    times = [run(seconds) for _ in range(steps)]
+    total = sum(times)
+    value = seconds * steps / total
+    B, S, dec_only = WORKLOADS[args.workload]
+    sample = f"1 clip x {seconds:.0f} s per step (of {B} x {S:g} s), fp32 PyTorch-CPU restatement of the reference op stream"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": 1e3 * total / steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ weights
+def ensure_weights() -> str:
+    """Seeded random-init DAC-44.1k weights in the reference's HF safetensors layout."""
+    from neuralcodecs_b200 import DACConfig, synthetic
+    path = os.path.join(tempfile.gettempdir(), f"nc_bench_dac44_seed{synthetic.WEIGHT_SEED}.safetensors")
+    if not os.path.exists(path):
+        sd = synthetic.make_dac_weights_hf(DACConfig.DAC44kHz())
+        # nn.Embedding-default N(0,1) rows are far from the latents of random-init encoders; scale them
+        # into the latents' range so more than one code per stage is used (timing is data independent)
+        for k in sd:
+            if k.endswith("codebook.weight"):
+                sd[k] = (0.05 * sd[k]).astype("float32")
+        tmp = f"{path}.{os.getpid()}.tmp"
+        synthetic.save_safetensors(sd, tmp)
+        os.replace(tmp, path)
+    return path
+
+
+def synth_audio_cuda(torch, batch, length, first_clip, device):
+    """Same recipe as neuralcodecs_b200.synthetic.synth_audio, generated on the device."""
+    t = torch.arange(length, device=device, dtype=torch.float64) / SAMPLE_RATE
+    out = torch.empty(batch, length, device=device, dtype=torch.float32)
+    g = torch.Generator(device=device)
+    for i in range(batch):
+        b = first_clip + i
+        f = 110.0 * 2.0 ** ((b % 48) / 12.0)
+        g.manual_seed(1234 * 100003 + b)
+        x = 0.30 * torch.sin(2 * torch.pi * f * t + 0.37 * b) + 0.15 * torch.sin(2 * torch.pi * 3.1 * f * t)
+        x = x.float() + 0.05 * torch.randn(length, device=device, generator=g)
+        out[i] = x.clamp_(-1.0, 1.0)
+    return out
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import neuralcodecs_b200 as nc
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, S, dec_only = WORKLOADS[args.workload]
+    if args.batch:
+        B = args.batch
+    if args.seconds:
+        S = args.seconds
+    L = int(round(S * SAMPLE_RATE))
+    # contiguous shard of the global batch
+    lo, hi = rank * B // world, (rank + 1) * B // world
+    nb = hi - lo
+
+    wpath = ensure_weights() if rank == 0 else None
+    if dist is not None:
+        dist.barrier()
+        wpath = ensure_weights()
+    cfg = nc.DACConfig.DAC44kHz()
+    cfg.device = nc.DeviceConfiguration.CUDA(local_rank)
+    opts = {}
+    if args.encoder_precision:
+        opts["encoder_precision"] = args.encoder_precision
+    if args.decoder_precision:
+        opts["decoder_precision"] = args.decoder_precision
+    if args.workspace_mb:
+        opts["max_workspace_mb"] = str(args.workspace_mb)
+    model = nc.DAC(cfg, options=opts)
+    model.LoadWeights(wpath)
+    Lp, T = model.query_shapes(L)
+    nq = cfg.num_codebooks
+
+    # ---- inputs resident in HBM
+    codes_in = None
+    if dec_only:
+        gen = torch.Generator(device=dev); gen.manual_seed(99 + lo)
+        codes_in = torch.randint(0, cfg.codebook_size, (nb, nq, T), device=dev, dtype=torch.int64, generator=gen)
+        audio = None
+    else:
+        audio = synth_audio_cuda(torch, nb, L, lo, dev) if nb else torch.empty(0, L, device=dev)
+    audio_out = torch.empty(nb, 1, Lp, device=dev, dtype=torch.float32)
+    codes_out = torch.empty(nb, nq, T, device=dev, dtype=torch.int64)
+    stream = torch.cuda.ExternalStream(model.stream_ptr(), device=dev)
+
+    def step_dev():
+        if nb == 0:
+            return
+        if dec_only:
+            model.decode_codes_dev(codes_in.data_ptr(), nb, nq, T, audio_out.data_ptr())
+        else:
+            model.forward_dev(audio.data_ptr(), nb, L, audio_out.data_ptr(), codes_out.data_ptr())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        dev_ms = e0.elapsed_time(e1)
+        barrier()
+        t = torch.tensor([dev_ms, wall * 1e3], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1])
+
+    for _ in range(args.warmup):
+        step_dev()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = model.launch_count()
+    dev_ms, wall_ms = timed(step_dev, args.steps)
+    launches = model.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    audio_seconds_per_step = B * L / SAMPLE_RATE          # unpadded input length
+    value = audio_seconds_per_step * args.steps / (dev_ms / 1e3)
+
+    # ---- e2e: host buffers through the public host-pointer entry point
+    e2e = None
+    if not args.no_e2e:
+        if dec_only:
+            h_in = torch.empty(nb, nq, T, dtype=torch.int64).pin_memory()
+            h_in.copy_(codes_in)
+        else:
+            h_in = torch.empty(nb, L, dtype=torch.float32).pin_memory()
+            h_in.copy_(audio)
+        h_audio = torch.empty(nb, 1, Lp, dtype=torch.float32).pin_memory()
+        h_codes = torch.empty(nb, nq, T, dtype=torch.int64).pin_memory()
+
+        def step_host():
+            if nb == 0:
+                return
+            if dec_only:
+                model.decode_codes_host(h_in.data_ptr(), nb, nq, T, h_audio.data_ptr())
+            else:
+                model.forward_host(h_in.data_ptr(), nb, L, h_audio.data_ptr(), h_codes.data_ptr())
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            step_host()
+        _, e2e_wall_ms = timed(step_host, args.steps)
+        h2d = h_in.numel() * h_in.element_size()
+        d2h = h_audio.numel() * 4 + (0 if dec_only else h_codes.numel() * 8)
+        if dist is not None:
+            t = torch.tensor([h2d, d2h], device=dev, dtype=torch.float64)
+            dist.all_reduce(t)
+            h2d, d2h = int(t[0]), int(t[1])
+        e2e = {"value": audio_seconds_per_step * args.steps / (e2e_wall_ms / 1e3), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "timer": "wall clock, max over ranks"}
+
+    # ---- roofline of the dominant kernel: one extra pass with per-launch CUDA events
+    roofline = None
+    kernels = None
+    if rank == 0 and nb:
+        peaks, peak_src = measured_peaks()
+        model.set_option("profile", "1")
+        model.profile_report()
+        step_dev()
+        rep = model.profile_report()
+        model.set_option("profile", "0")
+        total_ms = sum(v["ms"] for v in rep.values())
+        kernels = {k: {"launches": v["launches"], "ms": round(v["ms"], 3), "share": round(v["ms"] / total_ms, 4),
+                       "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 2),
+                       "gbs": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1)} for k, v in rep.items()}
+        mma = {k: v for k, v in rep.items() if k.startswith("conv_umma")}
+        if mma:
+            fl = sum(v["flops"] for v in mma.values())
+            ms = sum(v["ms"] for v in mma.values())
+            n = sum(v["launches"] for v in mma.values())
+            mma_fl = sum(v["flops"] * (3 if "3x" in k else 1) for k, v in mma.items())
+            peak = peaks["bf16_tflops_sustained"] / 2.0
+            ach = fl / ms / 1e9
+            roofline = {"bound": "tensor", "kernel": "conv_umma_kernel (tcgen05.mma kind::tf32, all conv layers)",
+                        "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                        "traffic": None, "launches": n, "avg_launch_ms": ms / n,
+                        "share_of_step": ms / total_ms,
+                        "issued_mma_tflops": mma_fl / ms / 1e9, "issued_frac": mma_fl / ms / 1e9 / peak,
+                        "peak_note": f"{peak_src} bf16_tflops_sustained / 2 (kind::tf32 runs at half the bf16 rate); "
+                                     "achieved = algorithmic conv FLOPs (2*MAC), issued = x3 for 3xTF32 layers"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not dec_only:
+        threads = os.cpu_count() or 1
+        rate, sec, dt = cpu_oracle_rate(20.0, wpath, threads)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"1 clip x {sec:.0f} s (of {B} x {S:g} s) in {dt:.1f} s, fp32 PyTorch-CPU restatement of the "
+                         "reference op stream (reference is C#/TorchSharp: not runnable here)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "tf32/3xtf32 operands, f32 accumulate",
+                "data": "synthetic",
+                "config": {"workload": args.workload, "codec": "DAC 44.1 kHz 9 codebooks",
+                           "global_batch": B, "clip_seconds": S, "clips_per_gpu": nb, "frames_per_clip": T,
+                           "decode_only": dec_only, "precision": model.precision_summary(),
+                           "l2": "inputs (%.1f MB/rank) larger than L2; no flush" % (nb * L * 4 / 1e6),
+                           "weights": "random-init (seeded), HF DacModel safetensors layout"},
+                "wall_ms_per_step": wall_ms / args.steps,
+                "gflop_per_audio_s": GFLOP_PER_AUDIO_S if not dec_only else 138.6,
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+                "cpu_baseline": cpu, "kernels": kernels}
+        print(json.dumps(line), flush=True)
+    model.Dispose()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -186,6 +186,14 @@ NC_API nc_status nc_dac_forward_dev(nc_handle h, const float* audio_dev, int32_t
 NC_API nc_status nc_dac_decode_codes_dev(nc_handle h, const int64_t* codes_dev, int32_t batch,
                                          int32_t n_quantizers, int64_t frames, float* audio_dev);
 
+/* The CUDA stream (cudaStream_t) every *_dev call of this handle enqueues on, so a caller
+ * can bracket calls with its own events or order its own work against them. */
+NC_API nc_status nc_get_stream(nc_handle h, void** stream_out);
+
+/* JSON description of the loaded engine (codec, precision policy, per-layer executor) into
+ * buf; NC_INVALID_ARGUMENT when buf is too small. */
+NC_API nc_status nc_describe(nc_handle h, char* buf, size_t buf_size);
+
 /* -- instrumentation ---------------------------------------------------------------- */
 /* kernels launched by this handle since creation (bench.py's gpu_launches). */
 NC_API uint64_t nc_launch_count(nc_handle h);

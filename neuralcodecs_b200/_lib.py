@@ -90,6 +90,8 @@ SIGNATURES = {
     "nc_dac_forward": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int32, _P, _P, _P, _I64]),
     "nc_dac_forward_dev": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int32, _P, _P, _P, _I64]),
     "nc_dac_decode_codes_dev": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int64, _P]),
+    "nc_get_stream": (C.c_int, [_P, C.POINTER(_P)]),
+    "nc_describe": (C.c_int, [_P, C.c_char_p, C.c_size_t]),
     "nc_launch_count": (C.c_uint64, [_P]),
     "nc_profile_report": (C.c_int, [_P, C.c_char_p, C.c_size_t]),
 }

@@ -293,6 +293,24 @@ nc_status nc_dac_decode_codes_dev(nc_handle h, const int64_t* codes_dev, int32_t
   });
 }
 
+nc_status nc_get_stream(nc_handle h, void** stream_out) {
+  return guarded([&] {
+    if (!h || !h->engine) throw Error(NC_INVALID_ARGUMENT, "null handle");
+    if (!stream_out) throw Error(NC_INVALID_ARGUMENT, "stream_out is null");
+    *stream_out = (void*)h->engine->stream();
+  });
+}
+
+nc_status nc_describe(nc_handle h, char* buf, size_t buf_size) {
+  return guarded([&] {
+    if (!h || !h->engine) throw Error(NC_INVALID_ARGUMENT, "null handle");
+    if (!buf || buf_size == 0) throw Error(NC_INVALID_ARGUMENT, "null buffer");
+    const std::string s = h->engine->describe();
+    if (s.size() + 1 > buf_size) throw Error(NC_INVALID_ARGUMENT, "describe buffer too small");
+    std::memcpy(buf, s.c_str(), s.size() + 1);
+  });
+}
+
 // ------------------------------------------------------------------------------------ instrumentation
 uint64_t nc_launch_count(nc_handle h) { return (h && h->engine) ? h->engine->launches() : 0; }
 

@@ -52,6 +52,11 @@ class ConvLayer {
   Precision precision() const { return mode_; }
   const std::string& name() const { return name_; }
   double flops(int batch, int t_in) const;
+  // "tcgen05 tf32 BN=256" / "tcgen05 3xtf32 BN=128" / "simt fp32"
+  std::string executor() const {
+    if (mode_ == PREC_FP32) return "simt fp32";
+    return std::string("tcgen05 ") + (mode_ == PREC_TF32 ? "tf32" : "3xtf32") + " BN=" + std::to_string(bn_);
+  }
 
  private:
   struct Tap {

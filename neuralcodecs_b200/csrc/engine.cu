@@ -317,6 +317,38 @@ void DacEngine::finalize_weights() {
   ready_ = true;
 }
 
+static const char* prec_name(Precision p) {
+  return p == PREC_FP32 ? "fp32" : p == PREC_TF32 ? "tf32" : "3xtf32";
+}
+
+std::string DacEngine::describe() const {
+  std::string s = "{\"codec\": \"DAC\", \"encoder_precision\": \"";
+  s += prec_name(enc_prec_);
+  s += "\", \"decoder_precision\": \"";
+  s += prec_name(dec_prec_);
+  s += dec_boost_ ? "\", \"decoder_boost\": true, \"layers\": {" : "\", \"decoder_boost\": false, \"layers\": {";
+  bool first = true;
+  auto add = [&](const ConvLayer& l) {
+    if (l.name().empty()) return;
+    s += first ? "\"" : ", \"";
+    first = false;
+    s += l.name() + "\": \"" + l.executor() + "\"";
+  };
+  for (auto& b : enc_blocks_) {
+    for (auto& r : b->ru) { add(r.c1); add(r.c2); }
+    add(b->down);
+  }
+  add(enc_out_);
+  add(dec_in_);
+  for (auto& b : dec_blocks_) {
+    add(b->up);
+    for (auto& r : b->ru) { add(r.c1); add(r.c2); }
+  }
+  add(dec_out_);
+  s += "}}";
+  return s;
+}
+
 int64_t DacEngine::padded_length(int64_t L) const {
   const int64_t hop = cfg_.hop();
   return (L + hop - 1) / hop * hop;  // Models/DAC.cs:151-153

@@ -19,6 +19,7 @@ class Engine {
   virtual const char* codec_name() const = 0;
   virtual void finalize_weights() = 0;
   virtual void set_option(const std::string& key, const std::string& value);
+  virtual std::string describe() const = 0;
 
   void load_weights(const std::string& path);
   void set_tensor(const std::string& name, HostTensor&& t) { tensors_[name] = std::move(t); }
@@ -27,6 +28,7 @@ class Engine {
   uint64_t launches() const { return launches_; }
   Profiler& profiler() { return prof_; }
   void sync();
+  cudaStream_t stream() const { return stream_; }
 
   // re-entrancy guard (a handle is one-thread-at-a-time)
   bool busy = false;
@@ -77,6 +79,7 @@ class DacEngine : public Engine {
   void finalize_weights() override;
   void set_option(const std::string& key, const std::string& value) override;
   const DacConfig& config() const { return cfg_; }
+  std::string describe() const override;
 
   int64_t padded_length(int64_t L) const;
   int64_t frames(int64_t L) const { return padded_length(L) / cfg_.hop(); }

@@ -108,6 +108,22 @@ class DAC:
         _lib.check(_lib.lib().nc_profile_report(self._handle(), buf, len(buf)), "DAC", "Profile")
         return json.loads(buf.value.decode())
 
+    def describe(self) -> dict:
+        buf = C.create_string_buffer(1 << 16)
+        _lib.check(_lib.lib().nc_describe(self._handle(), buf, len(buf)), "DAC", "Describe")
+        return json.loads(buf.value.decode())
+
+    def precision_summary(self) -> str:
+        d = self.describe()
+        return (f"encoder {d['encoder_precision']}, decoder {d['decoder_precision']}"
+                + (" (+3xtf32 on narrow 1x1 / final conv)" if d.get("decoder_boost") and d["decoder_precision"] == "tf32" else ""))
+
+    def stream_ptr(self) -> int:
+        """cudaStream_t the *_dev calls enqueue on (wrap with torch.cuda.ExternalStream to time them)."""
+        s = C.c_void_p()
+        _lib.check(_lib.lib().nc_get_stream(self._handle(), C.byref(s)), "DAC", "GetStream")
+        return s.value or 0
+
     def query_shapes(self, length: int) -> Tuple[int, int]:
         """(padded length, frames) for an input of `length` samples (DAC.Preprocess, DAC.cs:141-154)."""
         pl, fr = C.c_int64(), C.c_int64()
@@ -217,6 +233,21 @@ class DAC:
     def decode_codes_dev(self, codes_ptr: int, batch: int, n_quantizers: int, frames: int, audio_ptr: int) -> None:
         _lib.check(_lib.lib().nc_dac_decode_codes_dev(self._handle(), codes_ptr, batch, n_quantizers, frames,
                                                       audio_ptr), "DAC", "Decoding")
+
+    # ------------------------------------------------------------------ raw host-pointer variants
+    def forward_host(self, audio_ptr: int, batch: int, length: int, audio_out_ptr: int, codes_ptr: int,
+                     z_ptr: int = 0, n_quantizers: int = 0) -> int:
+        """nc_dac_forward on caller-owned HOST buffers given as raw addresses (e.g. pinned torch
+        tensors' data_ptr()); H2D / D2H copies happen inside the call."""
+        frames = C.c_int64()
+        _lib.check(_lib.lib().nc_dac_forward(self._handle(), audio_ptr, batch, length, n_quantizers,
+                                             audio_out_ptr or None, codes_ptr or None, z_ptr or None,
+                                             C.byref(frames)), "DAC", "Encoding")
+        return frames.value
+
+    def decode_codes_host(self, codes_ptr: int, batch: int, n_quantizers: int, frames: int, audio_ptr: int) -> None:
+        _lib.check(_lib.lib().nc_dac_decode_codes(self._handle(), codes_ptr, batch, n_quantizers, frames,
+                                                  audio_ptr), "DAC", "Decoding")
 
     # ------------------------------------------------------------------ helpers
     def _handle(self):

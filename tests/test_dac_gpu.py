@@ -1,0 +1,237 @@
+"""Parity of the CUDA engine (through the C ABI, via the ctypes host mirror) against the CPU oracle.
+
+Gates (BASELINE.json north_star): RVQ codes bit-exact except near-ties whose scale-normalised
+distance margin is below 1e-6; decoded audio max-abs <= 1e-3 and SNR >= 60 dB vs the fp32 oracle.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+MAX_ABS = 1e-3      # north_star tolerance
+MIN_SNR_DB = 60.0   # north_star tolerance
+NEAR_TIE = 1e-6     # north_star: relative (scale-normalised) distance margin of an allowed code flip
+
+
+def snr_db(ref, test):
+    ref = np.asarray(ref, np.float64)
+    test = np.asarray(test, np.float64)
+    return 10 * np.log10((ref ** 2).sum() / max(((ref - test) ** 2).sum(), 1e-300))
+
+
+def _models(fix, options=None):
+    import neuralcodecs_b200 as nc
+    from oracle import dac as odac
+    co, ce, path = fix
+    o = odac.load_hf_safetensors(path, co)
+    m = nc.DAC(ce, options=options)
+    m.LoadWeights(path)
+    return o, m
+
+
+def _audio(cfg, batch, length, first=3):
+    from oracle import synth
+    return synth.synth_audio(batch, length, cfg.sample_rate, first_clip=first)
+
+
+def _check_codes(o, ref, codes, allow_near_ties=True):
+    """bit-exact, or every un-cascaded flip is a near-tie under the scale normalisation"""
+    from oracle import dac as odac
+    rc = ref["codes"].numpy()
+    if np.array_equal(rc, codes):
+        return 0
+    assert allow_near_ties, f"{(rc != codes).sum()} code mismatches on an exact path"
+    rep = odac.near_tie_report(o, ref["z_e"], ref["codes"], torch.from_numpy(codes))
+    bad = [r for r in rep["uncascaded_flips"] if abs(r["margin_scale"]) >= NEAR_TIE]
+    assert not bad, f"code flips that are not near-ties: {bad[:5]} (of {len(rep['uncascaded_flips'])})"
+    return len(rep["uncascaded_flips"])
+
+
+def _oracle_forward(o, x):
+    xt = torch.from_numpy(x).unsqueeze(1)
+    ref = o.forward(xt)
+    ref["z_e"] = o.encode_latent(xt)
+    return ref
+
+
+# ------------------------------------------------------------------------------------------------ fp32 path
+def test_tiny_fp32_cuda_core_path_is_tight(dac_tiny):
+    o, m = _models(dac_tiny, {"encoder_precision": "fp32", "decoder_precision": "fp32"})
+    x = _audio(dac_tiny[0], 3, 8000 + 37)
+    ref = _oracle_forward(o, x)
+    out = m.forward(x[:, None, :])
+    assert out["codes"].dtype == np.int64 and out["codes"].shape == tuple(ref["codes"].shape)
+    _check_codes(o, ref, out["codes"])
+    np.testing.assert_allclose(out["z"], ref["z"].numpy(), atol=5e-6)
+    assert out["audio"].shape == tuple(ref["audio"].shape)          # padded length, never trimmed
+    np.testing.assert_allclose(out["audio"], ref["audio"].numpy(), atol=5e-6)
+    m.Dispose()
+
+
+def test_golden_hf_fixture_decoder_and_from_codes(dac_tiny):
+    """Committed transformers.DacModel outputs (tests/golden) through the engine."""
+    import neuralcodecs_b200 as nc
+    from oracle import synth
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "dac_hf_small.npz"))
+    co, ce, _ = dac_tiny
+    sd = synth.make_dac_weights_hf(co, codebooks="normal")
+    m = nc.DAC(ce, options={"encoder_precision": "fp32", "decoder_precision": "fp32"})
+    for k, v in sd.items():
+        m.set_tensor(k, v)
+    m.finalize_weights()
+    np.testing.assert_allclose(m.Decode(g["encoder_out"]), g["decoder_out"], atol=1e-5)
+    np.testing.assert_allclose(m.FromCodes(g["codes"]), g["from_codes"], atol=1e-5)
+    z = m.EncodeAudio(g["audio_in"])
+    assert z.shape == g["encoder_out"].shape
+    m.Dispose()
+
+
+# ------------------------------------------------------------------------------------------------ tcgen05 path
+@pytest.mark.parametrize("prec", ["tf32", "3xtf32"])
+def test_mid_tcgen05_path(dac_mid, prec):
+    o, m = _models(dac_mid, {"encoder_precision": "3xtf32", "decoder_precision": prec})
+    assert any(v.startswith("tcgen05") for v in m.describe()["layers"].values())
+    x = _audio(dac_mid[0], 2, 16000 + 123)
+    ref = _oracle_forward(o, x)
+    out = m.forward(x[:, None, :])
+    _check_codes(o, ref, out["codes"])
+    a_dec = m.Decode(ref["z"].numpy())                             # decoder numerics on the oracle's latent
+    a_ref = ref["audio"].numpy()
+    if prec == "3xtf32":
+        assert np.abs(a_dec - a_ref).max() <= MAX_ABS and snr_db(a_ref, a_dec) >= MIN_SNR_DB
+        assert np.abs(out["audio"] - a_ref).max() <= MAX_ABS and snr_db(a_ref, out["audio"]) >= MIN_SNR_DB
+    else:   # single-pass tf32 is an opt-in speed mode: report, loose bound only
+        assert snr_db(a_ref, a_dec) >= 50.0
+    m.Dispose()
+
+
+def test_full_config_default_policy_meets_the_gates(dac_full):
+    """DAC 44.1 kHz preset, default precision policy (the one bench.py measures)."""
+    o, m = _models(dac_full)
+    x = _audio(dac_full[0], 2, 2 * 44100 + 37)
+    ref = _oracle_forward(o, x)
+    out = m.forward(x[:, None, :])
+    flips = _check_codes(o, ref, out["codes"])
+    a_ref = ref["audio"].numpy()
+    a_dec = m.Decode(ref["z"].numpy())
+    print(f"full: flips {flips}; dec-only max-abs {np.abs(a_dec - a_ref).max():.2e} snr {snr_db(a_ref, a_dec):.1f} dB; "
+          f"e2e max-abs {np.abs(out['audio'] - a_ref).max():.2e} snr {snr_db(a_ref, out['audio']):.1f} dB")
+    assert np.abs(a_dec - a_ref).max() <= MAX_ABS and snr_db(a_ref, a_dec) >= MIN_SNR_DB
+    if flips == 0:
+        assert np.abs(out["audio"] - a_ref).max() <= MAX_ABS and snr_db(a_ref, out["audio"]) >= MIN_SNR_DB
+    # Dia stage (config #5): codes -> audio, fused FromCodes + Decode
+    zc = m.FromCodes(ref["codes"].numpy())
+    zo = o.from_codes(ref["codes"])
+    np.testing.assert_allclose(zc, zo.numpy(), atol=2e-6)
+    ac = m.DecodeCodes(ref["codes"].numpy())
+    ao = o.decode(zo).numpy()
+    assert np.abs(ac - ao).max() <= MAX_ABS and snr_db(ao, ac) >= MIN_SNR_DB
+    m.Dispose()
+
+
+# ------------------------------------------------------------------------------------------------ edge cases
+@pytest.mark.parametrize("length", [1, 511, 512, 513, 5000])
+def test_ragged_lengths_pad_like_preprocess(dac_tiny, length):
+    """DAC.Preprocess right-zero-pads to a hop multiple (hop = 2*4*8*8 = 512 here); output is padded length."""
+    o, m = _models(dac_tiny, {"encoder_precision": "fp32", "decoder_precision": "fp32"})
+    x = _audio(dac_tiny[0], 2, length)
+    ref = _oracle_forward(o, x)
+    out = m.forward(x[:, None, :])
+    hop = dac_tiny[0].hop_length
+    assert out["audio"].shape[-1] == -(-length // hop) * hop == ref["audio"].shape[-1]
+    _check_codes(o, ref, out["codes"])
+    np.testing.assert_allclose(out["audio"], ref["audio"].numpy(), atol=5e-6)
+    m.Dispose()
+
+
+def test_n_quantizers_subset_and_latents(dac_tiny):
+    o, m = _models(dac_tiny, {"encoder_precision": "fp32", "decoder_precision": "fp32"})
+    x = _audio(dac_tiny[0], 2, 4000)
+    xt = torch.from_numpy(x).unsqueeze(1)
+    z_ref, c_ref, l_ref = o.encode(xt, 2)
+    z, codes, latents = m.Encode(x[:, None, :], 2)
+    assert codes.shape == (2, 2, c_ref.shape[-1]) and latents.shape == tuple(l_ref.shape)
+    np.testing.assert_array_equal(codes, c_ref.numpy())
+    np.testing.assert_allclose(latents, l_ref.numpy(), atol=2e-6)
+    np.testing.assert_allclose(z, z_ref.numpy(), atol=5e-6)
+    m.Dispose()
+
+
+def test_batch_sharding_and_micro_batching_do_not_change_results(dac_mid):
+    """Per-clip results are bit-identical for any batch split (SURVEY 8e determinism requirement)."""
+    _, m = _models(dac_mid)
+    x = _audio(dac_mid[0], 5, 9000)
+    full = m.forward(x[:, None, :])
+    m.set_option("max_workspace_mb", "64")                          # forces micro-batches
+    small = m.forward(x[:, None, :])
+    np.testing.assert_array_equal(full["codes"], small["codes"])
+    np.testing.assert_array_equal(full["audio"], small["audio"])
+    for lo, hi in ((0, 2), (2, 5)):                                 # what two ranks would compute
+        part = m.forward(x[lo:hi, None, :])
+        np.testing.assert_array_equal(full["codes"][lo:hi], part["codes"])
+        np.testing.assert_array_equal(full["audio"][lo:hi], part["audio"])
+    m.Dispose()
+
+
+def test_error_conventions(dac_tiny, tmp_path):
+    import neuralcodecs_b200 as nc
+    co, ce, path = dac_tiny
+    m = nc.DAC(ce)
+    with pytest.raises(RuntimeError):                               # weights not loaded
+        m.forward(np.zeros((1, 1, 100), np.float32))
+    with pytest.raises(FileNotFoundError):                          # DAC.cs:347-351
+        m.LoadWeights(str(tmp_path / "missing.safetensors"))
+    bad = tmp_path / "bad.safetensors"
+    bad.write_bytes(b"\x08\x00\x00\x00\x00\x00\x00\x00{\"a\":1}")
+    with pytest.raises(RuntimeError):                               # InvalidOperationException("Failed to load ...")
+        m.LoadWeights(str(bad))
+    m.LoadWeights(path)
+    with pytest.raises(ValueError, match="does not match model sample rate"):   # DAC.cs:143-149
+        m.Encode(np.zeros((1, 1, 1000), np.float32), sampleRate=8000)
+    with pytest.raises(TypeError):
+        m.Encode(None)
+    m.Dispose()
+    with pytest.raises(RuntimeError):
+        m.Encode(np.zeros((1, 1, 1000), np.float32))
+
+
+# ------------------------------------------------------------------------------------------------ full size
+def test_full_size_properties_config4_clip(dac_full):
+    """One 30 s clip of BASELINE config #4 (T = 2584): properties that need no oracle at this size --
+    encode -> FromCodes -> Decode reproduces forward's audio; codes in range; a second identical call
+    is bit-identical; clip results do not depend on their batch neighbours."""
+    _, m = _models(dac_full)
+    L = 30 * 44100
+    x = _audio(dac_full[0], 2, L)
+    out = m.forward(x[:, None, :])
+    assert out["codes"].shape == (2, 9, 2584) and out["audio"].shape == (2, 1, 1323008)
+    assert out["codes"].min() >= 0 and out["codes"].max() < 1024
+    assert len(np.unique(out["codes"][:, 0])) > 64                  # non-degenerate code usage
+    again = m.forward(x[:, None, :])
+    np.testing.assert_array_equal(out["codes"], again["codes"])
+    np.testing.assert_array_equal(out["audio"], again["audio"])
+    solo = m.forward(x[1:2, None, :])
+    np.testing.assert_array_equal(out["codes"][1:2], solo["codes"])
+    np.testing.assert_array_equal(out["audio"][1:2], solo["audio"])
+    a2 = m.DecodeCodes(out["codes"])                                # FromCodes lacks the STE roundings: ~1e-7 on z
+    assert np.abs(a2 - out["audio"]).max() <= MAX_ABS and snr_db(out["audio"], a2) >= MIN_SNR_DB
+    assert np.isfinite(out["audio"]).all() and np.abs(out["audio"]).max() <= 1.0
+    m.Dispose()
+
+
+def test_config1_ten_second_clip_against_oracle(dac_full):
+    """BASELINE config #1: one 10 s clip, batch 1, full oracle comparison with near-tie accounting."""
+    o, m = _models(dac_full)
+    x = _audio(dac_full[0], 1, 441000, first=0)
+    ref = _oracle_forward(o, x)
+    out = m.forward(x[:, None, :])
+    assert out["codes"].shape == (1, 9, 862)
+    flips = _check_codes(o, ref, out["codes"])
+    a_ref = ref["audio"].numpy()
+    a_dec = m.Decode(ref["z"].numpy())
+    print(f"config1: flips {flips}; dec-only max-abs {np.abs(a_dec - a_ref).max():.2e} snr {snr_db(a_ref, a_dec):.1f} dB")
+    assert np.abs(a_dec - a_ref).max() <= MAX_ABS and snr_db(a_ref, a_dec) >= MIN_SNR_DB
+    m.Dispose()

@@ -1,0 +1,69 @@
+// P/Invoke surface of libneuralcodecs_cuda.so (include/neuralcodecs_cuda.h).
+// Written against .NET 8 [LibraryImport]; NOT compiled in this repository (no dotnet toolchain in
+// the build image) -- the executable twin of this file is neuralcodecs_b200/_lib.py (ctypes).
+using System;
+using System.Runtime.InteropServices;
+
+namespace NeuralCodecs.Cuda;
+
+internal enum NcStatus
+{
+    Ok = 0, InvalidArgument = 1, FileNotFound = 2, BadWeights = 3, ShapeMismatch = 4,
+    CudaUnavailable = 5, CudaError = 6, OutOfMemory = 7, Internal = 8, Unsupported = 9,
+}
+
+internal enum NcCodecKind { Dac = 1, Snac = 2, Encodec = 3 }
+
+[StructLayout(LayoutKind.Sequential)]
+internal unsafe struct NcDacConfig
+{
+    public uint StructSize;
+    public int SampleRate, EncoderDim, NEncoderRates;
+    public fixed int EncoderRates[8];
+    public int DecoderDim, NDecoderRates;
+    public fixed int DecoderRates[8];
+    public int NCodebooks, CodebookSize, CodebookDim, LatentDim;
+}
+
+internal sealed class NcHandle : SafeHandle
+{
+    public NcHandle() : base(IntPtr.Zero, true) { }
+    public override bool IsInvalid => handle == IntPtr.Zero;
+    protected override bool ReleaseHandle() => Native.nc_destroy(handle) == NcStatus.Ok;
+}
+
+internal static unsafe partial class Native
+{
+    private const string Lib = "neuralcodecs_cuda";
+
+    [LibraryImport(Lib)] internal static partial IntPtr nc_version();
+    [LibraryImport(Lib)] internal static partial IntPtr nc_last_error();
+    [LibraryImport(Lib)] internal static partial int nc_device_count();
+    [LibraryImport(Lib)] internal static partial NcStatus nc_create(NcCodecKind kind, void* cfg, nuint cfgSize, int deviceIndex, out NcHandle handle);
+    [LibraryImport(Lib)] internal static partial NcStatus nc_destroy(IntPtr handle);
+    [LibraryImport(Lib, StringMarshalling = StringMarshalling.Utf8)] internal static partial NcStatus nc_load_weights(NcHandle h, string path);
+    [LibraryImport(Lib, StringMarshalling = StringMarshalling.Utf8)] internal static partial NcStatus nc_set_option(NcHandle h, string key, string value);
+    [LibraryImport(Lib)] internal static partial NcStatus nc_dac_query_shapes(NcHandle h, long length, out long paddedLength, out long frames, out int latentDim, out int nCodebooks, out int codebookDim);
+    [LibraryImport(Lib)] internal static partial NcStatus nc_dac_encode(NcHandle h, float* audio, int batch, long length, int sampleRate, int nQuantizers, float* z, long* codes, float* latents, out long frames);
+    [LibraryImport(Lib)] internal static partial NcStatus nc_dac_decode(NcHandle h, float* z, int batch, long frames, float* audio);
+    [LibraryImport(Lib)] internal static partial NcStatus nc_dac_from_codes(NcHandle h, long* codes, int batch, int nQuantizers, long frames, float* z);
+    [LibraryImport(Lib)] internal static partial NcStatus nc_dac_decode_codes(NcHandle h, long* codes, int batch, int nQuantizers, long frames, float* audio);
+    [LibraryImport(Lib)] internal static partial NcStatus nc_dac_forward(NcHandle h, float* audio, int batch, long length, int nQuantizers, float* audioOut, long* codes, float* z, out long frames);
+
+    /// Status -> the reference's exception conventions (SURVEY 8b "Error conventions").
+    internal static void Check(NcStatus s, string codec, Core.Exceptions.CodecOperation op)
+    {
+        if (s == NcStatus.Ok) return;
+        string msg = Marshal.PtrToStringUTF8(nc_last_error()) ?? s.ToString();
+        throw s switch
+        {
+            NcStatus.InvalidArgument => new ArgumentException(msg),                       // Models/DAC.cs:146,207
+            NcStatus.FileNotFound => new System.IO.FileNotFoundException(msg),            // Models/DAC.cs:347-351
+            NcStatus.BadWeights or NcStatus.ShapeMismatch or NcStatus.Unsupported
+                => new InvalidOperationException(msg),                                    // Models/DAC.cs:386-388
+            NcStatus.CudaUnavailable => new InvalidOperationException("CUDA requested but not available"), // Utils/TorchUtils.cs:97-99
+            NcStatus.OutOfMemory => new OutOfMemoryException(msg),
+            _ => new Core.Exceptions.CodecException(codec, op, msg),                      // Core/Exceptions/CodecException.cs:8-40
+        };
+    }
+}

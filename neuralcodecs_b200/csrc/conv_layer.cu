@@ -259,7 +259,7 @@ void ConvLayer::run(const ConvRunArgs& a, const LaunchCtx& ctx) const {
     p.batch = a.batch; p.m_tiles_per_clip = m_tiles;
     p.fast_sin = g_fast_sin >= 0 ? g_fast_sin : (mode_ == PREC_TF32 ? 1 : 0);
     check_launch(launch_conv_umma(p, ctx.num_sms, ctx.stream), name_.c_str());
-    ctx.end(ev, mode_ == PREC_3XTF32 ? "conv_umma_3xtf32" : "conv_umma_tf32", fl, bytes);
+    ctx.end(ev, mode_ == PREC_3XTF32 ? "conv_umma_3xtf32" : "conv_umma_tf32", fl, bytes, name_);
   } else {
     ConvSimtParams p{};
     p.A = a.in; p.a_clip_stride = a_valid; p.a_rows = a_rows; p.a_pitch = k_view_; p.a_valid = a_valid;
@@ -276,7 +276,7 @@ void ConvLayer::run(const ConvRunArgs& a, const LaunchCtx& ctx) const {
     p.mask_bn = 0;
     p.batch = a.batch; p.m_tiles_per_clip = m_tiles;
     check_launch(launch_conv_simt(p, ctx.stream), name_.c_str());
-    ctx.end(ev, "conv_simt_fp32", fl, bytes);
+    ctx.end(ev, "conv_simt_fp32", fl, bytes, name_);
   }
 }
 

@@ -52,7 +52,8 @@ void Engine::sync() { NC_CUDA(cudaStreamSynchronize(stream_)); }
 
 void Engine::set_option(const std::string& key, const std::string& value) {
   if (key == "profile") {
-    prof_.enabled = value == "1" || value == "true";
+    prof_.enabled = value == "1" || value == "true" || value == "2";
+    prof_.by_layer = value == "2";
   } else if (key == "fast_sin") {
     set_fast_sin_policy(std::atoi(value.c_str()));
   } else if (key == "max_workspace_mb") {
@@ -140,7 +141,7 @@ void DacEngine::set_option(const std::string& key, const std::string& value) {
 }
 
 void DacEngine::require_ready() const {
-  if (!ready_) throw Error(NC_INVALID_ARGUMENT, "DAC weights have not been loaded");
+  if (!ready_) throw Error(NC_BAD_WEIGHTS, "DAC weights have not been loaded");
 }
 
 // Fold weight normalisation once, in fp32, as the reference does on every forward

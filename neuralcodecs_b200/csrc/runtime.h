@@ -83,6 +83,7 @@ struct KernelStat {
 class Profiler {
  public:
   bool enabled = false;
+  bool by_layer = false;  // key the report by layer name instead of kernel name
   ~Profiler() {
     for (auto e : pool_) cudaEventDestroy(e);
   }
@@ -162,9 +163,9 @@ struct LaunchCtx {
   uint64_t* launches = nullptr;
 
   int begin() const { return prof ? prof->begin(stream) : -1; }
-  void end(int id, const std::string& name, double flops, double bytes) const {
+  void end(int id, const std::string& name, double flops, double bytes, const std::string& layer = "") const {
     if (launches) ++*launches;
-    if (prof) prof->end(id, stream, name, flops, bytes);
+    if (prof) prof->end(id, stream, (prof->by_layer && !layer.empty()) ? layer + " [" + name + "]" : name, flops, bytes);
   }
 };
 

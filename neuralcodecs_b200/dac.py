@@ -104,12 +104,12 @@ class DAC:
         return int(_lib.lib().nc_launch_count(self._handle()))
 
     def profile_report(self) -> dict:
-        buf = C.create_string_buffer(1 << 16)
+        buf = C.create_string_buffer(1 << 18)
         _lib.check(_lib.lib().nc_profile_report(self._handle(), buf, len(buf)), "DAC", "Profile")
         return json.loads(buf.value.decode())
 
     def describe(self) -> dict:
-        buf = C.create_string_buffer(1 << 16)
+        buf = C.create_string_buffer(1 << 18)
         _lib.check(_lib.lib().nc_describe(self._handle(), buf, len(buf)), "DAC", "Describe")
         return json.loads(buf.value.decode())
 

@@ -18,7 +18,80 @@ Precision parse_precision(const std::string& s) {
   if (s == "fp32") return PREC_FP32;
   if (s == "tf32") return PREC_TF32;
   if (s == "3xtf32") return PREC_3XTF32;
-  throw Error(NC_INVALID_ARGUMENT, "unknown precision '" + s + "' (fp32|tf32|3xtf32)");
+  if (s == "bf16x3") return PREC_BF16X3;
+  if (s == "f16x3") return PREC_F16X3;
+  throw Error(NC_INVALID_ARGUMENT, "unknown precision '" + s + "' (fp32|tf32|3xtf32|bf16x3|f16x3)");
+}
+
+const char* precision_name(Precision p) {
+  switch (p) {
+    case PREC_FP32: return "fp32";
+    case PREC_TF32: return "tf32";
+    case PREC_3XTF32: return "3xtf32";
+    case PREC_BF16X3: return "bf16x3";
+    default: return "f16x3";
+  }
+}
+
+static int mma_mode(Precision p) {
+  switch (p) {
+    case PREC_TF32: return MODE_TF32;
+    case PREC_3XTF32: return MODE_TF32X3;
+    case PREC_BF16X3: return MODE_BF16X3;
+    default: return MODE_F16X3;
+  }
+}
+
+// round-to-nearest-even fp32 -> bf16 / fp16 bit patterns on the host (finite inputs)
+static inline uint16_t host_bf16(float x) {
+  uint32_t u;
+  std::memcpy(&u, &x, 4);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+static inline float host_bf16_to_f(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+static inline uint16_t host_f16(float x) {
+  uint32_t u;
+  std::memcpy(&u, &x, 4);
+  const uint32_t sign = (u >> 16) & 0x8000u;
+  const int32_t e = (int32_t)((u >> 23) & 0xFF) - 127 + 15;
+  uint32_t m = u & 0x7FFFFFu;
+  if (e >= 31) return (uint16_t)(sign | 0x7C00u);           // overflow -> inf
+  if (e <= 0) {                                             // subnormal / zero
+    if (e < -10) return (uint16_t)sign;
+    m |= 0x800000u;
+    const int shift = 14 - e;                               // 14..24
+    uint32_t r = m >> shift;
+    const uint32_t rem = m & ((1u << shift) - 1), halfway = 1u << (shift - 1);
+    if (rem > halfway || (rem == halfway && (r & 1u))) ++r;
+    return (uint16_t)(sign | r);
+  }
+  uint32_t r = ((uint32_t)e << 10) | (m >> 13);
+  const uint32_t rem = m & 0x1FFFu;
+  if (rem > 0x1000u || (rem == 0x1000u && (r & 1u))) ++r;   // may carry into the exponent: still correct
+  return (uint16_t)(sign | r);
+}
+static inline float host_f16_to_f(uint16_t h) {
+  const uint32_t sign = ((uint32_t)h & 0x8000u) << 16;
+  const uint32_t e = (h >> 10) & 0x1Fu, m = h & 0x3FFu;
+  float f;
+  if (e == 0) {
+    f = std::ldexp((float)m, -24);
+  } else if (e == 31) {
+    f = m ? NAN : INFINITY;
+  } else {
+    f = std::ldexp((float)(m | 0x400u), (int)e - 25);
+  }
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  u |= sign;
+  std::memcpy(&f, &u, 4);
+  return f;
 }
 
 static int g_fast_sin = -1;  // -1 auto (tf32 -> fast), 0 never, 1 always
@@ -41,8 +114,7 @@ static inline float host_rna_tf32(float x) {
 ConvLayer::~ConvLayer() {
   cudaFree(d_bias_);
   cudaFree(d_w_plain_);
-  cudaFree(d_w_hi_);
-  cudaFree(d_w_lo_);
+  cudaFree(d_w_tiles_);
 }
 
 int ConvLayer::out_len(int t_in) const {
@@ -140,7 +212,7 @@ void ConvLayer::build(const std::string& name, const ConvSpec& spec, const std::
   if (umma_ok_) {
     ConvGemmParams probe{};
     probe.span = span_;
-    probe.passes = requested == PREC_3XTF32 ? 3 : 1;
+    probe.mode = mma_mode(requested);
     int bn = 0;
     if (n_pad_ <= 256) {
       bn = n_pad_;
@@ -179,36 +251,53 @@ void ConvLayer::build(const std::string& name, const ConvSpec& spec, const std::
     }
     tiles_per_ntile_ = tile_base;
     n_kc_ = kc_end - kc_begin_;
-    const size_t tile_elems = (size_t)bn_ * 32;
-    std::vector<float> hi((size_t)n_tiles_ * tiles_per_ntile_ * tile_elems, 0.f), lo;
-    if (mode_ == PREC_3XTF32) lo.assign(hi.size(), 0.f);
+    // one smem image per (N tile, tap, K chunk): [BN rows][128 B], 16-byte chunks XOR-swizzled by row & 7.
+    //   TF32   : 32 tf32-rounded floats per row
+    //   TF32X3 : hi image followed by lo image (fetched with one bulk copy)
+    //   H16X3  : 32 hi halves (64 B) then 32 lo halves (64 B) per row
+    const size_t img = (size_t)bn_ * 32;
+    w_tile_floats_ = (int)(img * (mode_ == PREC_3XTF32 ? 2 : 1));
+    std::vector<float> tiles((size_t)n_tiles_ * tiles_per_ntile_ * w_tile_floats_, 0.f);
     for (int nt = 0; nt < n_tiles_; ++nt) {
       for (size_t j = 0; j < taps_.size(); ++j) {
         const Tap& t = taps_[j];
         bool any = false;
         for (int kcl = 0; kcl < utaps_[j].kc_hi - utaps_[j].kc_lo; ++kcl) {
-          float* th = hi.data() + ((size_t)nt * tiles_per_ntile_ + utaps_[j].tile_base + kcl) * tile_elems;
-          float* tl = lo.empty() ? nullptr : lo.data() + ((size_t)nt * tiles_per_ntile_ + utaps_[j].tile_base + kcl) * tile_elems;
+          float* th = tiles.data() + ((size_t)nt * tiles_per_ntile_ + utaps_[j].tile_base + kcl) * w_tile_floats_;
+          uint16_t* t16 = reinterpret_cast<uint16_t*>(th);
           for (int nl = 0; nl < bn_; ++nl) {
             const int n = nt * bn_ + nl;
             if (n >= n_logical_) continue;
             for (int kk = 0; kk < 32; ++kk) {
               const float v = t.w[(size_t)n * t.klen + (size_t)kcl * 32 + kk];
               if (v != 0.f) any = true;
-              const size_t off = ptx::sw128_offset((uint32_t)nl, (uint32_t)(kk / 4)) / 4 + (kk % 4);
-              const float h = host_rna_tf32(v);
-              th[off] = h;
-              if (tl) tl[off] = host_rna_tf32(v - h);
+              if (mode_ == PREC_BF16X3 || mode_ == PREC_F16X3) {
+                const bool bf = mode_ == PREC_BF16X3;
+                const uint16_t h = bf ? host_bf16(v) : host_f16(v);
+                const float hf = bf ? host_bf16_to_f(h) : host_f16_to_f(h);
+                const uint16_t l = bf ? host_bf16(v - hf) : host_f16(v - hf);
+                const size_t hi_off = ptx::sw128_offset((uint32_t)nl, (uint32_t)(kk / 8)) / 2 + (kk % 8);
+                const size_t lo_off = ptx::sw128_offset((uint32_t)nl, 4u + (uint32_t)(kk / 8)) / 2 + (kk % 8);
+                t16[hi_off] = h;
+                t16[lo_off] = l;
+              } else {
+                const size_t off = ptx::sw128_offset((uint32_t)nl, (uint32_t)(kk / 4)) / 4 + (kk % 4);
+                const float h = host_rna_tf32(v);
+                th[off] = h;
+                if (mode_ == PREC_3XTF32) th[img + off] = host_rna_tf32(v - h);
+              }
             }
           }
         }
         if (any) tap_mask_[nt] |= (unsigned char)(1u << j);
       }
     }
-    d_w_hi_ = upload(hi);
-    if (!lo.empty()) d_w_lo_ = upload(lo);
-  } else {
-    // plain [tap][n_pad][klen] for the CUDA-core executor; masks at 16-column granularity
+    d_w_tiles_ = upload(tiles);
+  }
+  // plain weights for the CUDA-core executor: fp32 layers, and strided convs whose input length may
+  // not be a whole number of rows (the TMA-fed tensor-core kernel needs whole rows per clip)
+  if (!umma_ok_ || (!s.transposed && s.stride > 1)) {
+    // plain [tap][n_pad][klen]
     size_t total = 0;
     for (size_t j = 0; j < taps_.size(); ++j) {
       simt_w_off_[j] = (long long)total;
@@ -243,23 +332,27 @@ void ConvLayer::run(const ConvRunArgs& a, const LaunchCtx& ctx) const {
   const double fl = flops(a.batch, a.t_in);
   const double bytes = 4.0 * a.batch * ((double)a_valid + (double)d_valid * (a.residual ? 2 : 1));
   const int ev = ctx.begin();
-  if (mode_ != PREC_FP32) {
+  const bool whole_rows = a_valid == (long long)a_rows * k_view_ && (a_valid % 4) == 0 &&
+                          (reinterpret_cast<uintptr_t>(a.in) & 15) == 0;
+  if (mode_ != PREC_FP32 && (whole_rows || !d_w_plain_)) {
     ConvGemmParams p{};
     p.A = a.in; p.a_clip_stride = a_valid; p.a_rows = a_rows; p.a_pitch = k_view_; p.a_valid = a_valid;
     p.D = a.out; p.R = a.residual; p.d_clip_stride = d_valid; p.m_rows = m_rows; p.n_total = n_total;
     p.n_valid = n_logical_; p.d_valid = d_valid;
     p.bias = d_bias_; p.bias_period = s.cout; p.noise = a.noise;
     p.alpha = a.alpha; p.inv_alpha = a.inv_alpha; p.alpha_period = s.cin; p.prologue = a.prologue; p.act = a.act;
-    p.W_hi = d_w_hi_; p.W_lo = d_w_lo_; p.BN = bn_; p.n_tiles = n_tiles_; p.tiles_per_ntile = tiles_per_ntile_;
-    p.passes = mode_ == PREC_3XTF32 ? 3 : 1;
+    p.post = a.post; p.post_alpha = a.post_alpha; p.post_inv_alpha = a.post_inv_alpha; p.post_period = s.cout;
+    p.W = d_w_tiles_; p.w_tile_floats = w_tile_floats_; p.BN = bn_; p.n_tiles = n_tiles_; p.tiles_per_ntile = tiles_per_ntile_;
+    p.mode = mma_mode(mode_);
     p.n_taps = (int)taps_.size();
     for (int j = 0; j < p.n_taps; ++j) p.taps[j] = utaps_[j];
     std::memcpy(p.tap_mask, tap_mask_, sizeof tap_mask_);
     p.n_kc = n_kc_; p.kc_begin = kc_begin_; p.smin = smin_; p.span = span_;
     p.batch = a.batch; p.m_tiles_per_clip = m_tiles;
-    p.fast_sin = g_fast_sin >= 0 ? g_fast_sin : (mode_ == PREC_TF32 ? 1 : 0);
+    const int fast = g_fast_sin >= 0 ? g_fast_sin : ((mode_ == PREC_TF32 || mode_ == PREC_BF16X3) ? 1 : 0);
+    p.precise_sin = fast ? 0 : 1;
     check_launch(launch_conv_umma(p, ctx.num_sms, ctx.stream), name_.c_str());
-    ctx.end(ev, mode_ == PREC_3XTF32 ? "conv_umma_3xtf32" : "conv_umma_tf32", fl, bytes, name_);
+    ctx.end(ev, std::string("conv_umma_") + precision_name(mode_), fl, bytes, name_);
   } else {
     ConvSimtParams p{};
     p.A = a.in; p.a_clip_stride = a_valid; p.a_rows = a_rows; p.a_pitch = k_view_; p.a_valid = a_valid;
@@ -267,6 +360,7 @@ void ConvLayer::run(const ConvRunArgs& a, const LaunchCtx& ctx) const {
     p.n_valid = n_logical_; p.d_valid = d_valid;
     p.bias = d_bias_; p.bias_period = s.cout; p.noise = a.noise;
     p.alpha = a.alpha; p.alpha_period = s.cin; p.prologue = a.prologue; p.act = a.act;
+    p.post = a.post; p.post_alpha = a.post_alpha; p.post_period = s.cout;
     p.W = d_w_plain_; p.n_pad = n_pad_;
     p.n_taps = (int)taps_.size();
     for (int j = 0; j < p.n_taps; ++j) {

@@ -9,10 +9,12 @@
 
 namespace nc {
 
-enum Precision : int { PREC_FP32 = 0, PREC_TF32 = 1, PREC_3XTF32 = 3 };
+enum Precision : int { PREC_FP32 = 0, PREC_TF32 = 1, PREC_3XTF32 = 3, PREC_BF16X3 = 4, PREC_F16X3 = 5 };
+const char* precision_name(Precision p);
 
 Precision parse_precision(const std::string& s);
-// Snake prologue sin(): -1 = MUFU sin on tf32 layers only (default), 0 = always sinf, 1 = always MUFU
+// Snake sin(): -1 = MUFU sin on tf32 / bf16x3 layers, precise elsewhere (default); 0 = always precise;
+// 1 = always MUFU
 void set_fast_sin_policy(int v);
 
 struct ConvSpec {
@@ -31,6 +33,10 @@ struct ConvRunArgs {
   const float* alpha = nullptr;      // device [Cin]
   const float* inv_alpha = nullptr;  // device [Cin]
   int act = ACT_NONE;
+  // activation of the NEXT layer applied in this layer's epilogue (after bias + residual)
+  int post = PRO_NONE;
+  const float* post_alpha = nullptr;      // device [Cout]
+  const float* post_inv_alpha = nullptr;  // device [Cout]
   // row pitch override for the output (floats per output time step); 0 = Cout
   int out_valid_cols = 0;            // logical Cout written (0 = all)
 };
@@ -55,7 +61,7 @@ class ConvLayer {
   // "tcgen05 tf32 BN=256" / "tcgen05 3xtf32 BN=128" / "simt fp32"
   std::string executor() const {
     if (mode_ == PREC_FP32) return "simt fp32";
-    return std::string("tcgen05 ") + (mode_ == PREC_TF32 ? "tf32" : "3xtf32") + " BN=" + std::to_string(bn_);
+    return std::string("tcgen05 ") + precision_name(mode_) + " BN=" + std::to_string(bn_);
   }
 
  private:
@@ -73,8 +79,8 @@ class ConvLayer {
   // device
   float* d_bias_ = nullptr;
   float* d_w_plain_ = nullptr;
-  float* d_w_hi_ = nullptr;
-  float* d_w_lo_ = nullptr;
+  float* d_w_tiles_ = nullptr;
+  int w_tile_floats_ = 0;
   // UMMA tiling
   int bn_ = 0, n_tiles_ = 0, tiles_per_ntile_ = 0;
   ConvTap utaps_[kMaxTaps];

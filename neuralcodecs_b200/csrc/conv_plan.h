@@ -1,9 +1,9 @@
 // Multi-tap row-shifted GEMM: the one formulation every conv on the codec hot path is
 // lowered to.  Activations live in HBM channels-last, [clip][time][channel] fp32.
 //
-//   D[b, m, n] = act( bias[n % bias_period]
-//                     + sum_taps sum_{k in [kc_lo*32, kc_hi*32)} f(A[b, m + shift_tap, k]) * W_tap[n, k]
-//                     (+ R[b, m, n]) )
+//   D[b, m, n] = act( post( bias[n % bias_period]
+//                           + sum_taps sum_{k in [kc_lo*32, kc_hi*32)} f(A[b, m + shift_tap, k]) * W_tap[n, k]
+//                           (+ R[b, m, n]) ) )
 //
 // where the "A view" re-reads the channels-last input as rows of `a_pitch` floats:
 //   stride-1 conv (k taps, dilation d, padding p) : row = time step,  shift_j = j*d - p, K = Cin
@@ -11,8 +11,10 @@
 //                                                    taps fold into <=3 super-taps with partial K
 //   transposed conv (kernel 2s, stride s)          : row = input time step, N = s*Cout (phase-major),
 //                                                    <=3 super-taps, some masked per N tile
-// f = Snake / ELU prologue of the consumer (alpha indexed k % alpha_period), applied once per
-// staged input element.  Out-of-range rows read as zero (f(0) = 0 for both prologues).
+// f    = Snake / ELU prologue of THIS conv (alpha indexed k % alpha_period), applied once per
+//        staged input element.  Out-of-range rows read as zero (f(0) = 0 for both prologues).
+// post = Snake / ELU of the NEXT layer (alpha indexed n % post_period) applied in the epilogue, so
+//        the consumer needs no prologue: used whenever the raw value has no other reader.
 #pragma once
 #include <cstdint>
 
@@ -23,6 +25,13 @@ constexpr int kMaxNTiles = 64;
 
 enum Prologue : int { PRO_NONE = 0, PRO_SNAKE = 1, PRO_ELU = 2 };
 enum Activation : int { ACT_NONE = 0, ACT_TANH = 1 };
+// tensor-core operand modes of the tcgen05 executor
+//   TF32   : one kind::tf32 MMA per K step                                  (10-bit mantissa operands)
+//   TF32X3 : hi/lo TF32 split of both operands, 3 MMAs (lo*hi, hi*lo, hi*hi)  (~21 bits)
+//   BF16X3 : hi/lo BF16 split packed in one 128-byte row (32 hi | 32 lo), 3 kind::f16 MMAs of K=16
+//            per 16 channels -> 1.5x the MMA time of TF32, ~16-bit operands
+//   F16X3  : same with FP16 halves (~22 bits while values stay in fp16's normal range)
+enum MmaMode : int { MODE_TF32 = 0, MODE_TF32X3 = 1, MODE_BF16X3 = 2, MODE_F16X3 = 3 };
 
 struct ConvTap {
   int shift;      // row shift in the A view
@@ -49,19 +58,23 @@ struct ConvGemmParams {
   const float* bias;        // nullable
   int bias_period;
   const float* noise;       // nullable; [clip][m_rows]: D = R + noise*acc (SNAC NoiseBlock)
-  // ---- prologue / activation
+  // ---- prologue / post-activation / activation
   const float* alpha;       // [alpha_period]
   const float* inv_alpha;   // [alpha_period] (1/alpha, 0 where alpha == 0)
   int alpha_period;
   int prologue;
+  const float* post_alpha;      // [post_period] or null
+  const float* post_inv_alpha;
+  int post_period;
+  int post;                 // Prologue enum applied after bias (+ residual)
   int act;
-  // ---- weights
-  const float* W_hi;        // UMMA: pre-swizzled tiles [n_tile][tiles_per_ntile][BN*32]; SIMT: plain [tap][N_pad][K_tap]
-  const float* W_lo;        // 3xTF32 residual tiles (same tiling) or null
+  // ---- weights: pre-swizzled smem images, [n_tile][tiles_per_ntile][w_tile_floats]
+  const float* W;
+  int w_tile_floats;        // BN*32 (TF32, BF16X3, F16X3) or 2*BN*32 (TF32X3: hi image then lo image)
   int BN;                   // N tile (multiple of 16, <= 256)
   int n_tiles;
   int tiles_per_ntile;
-  int passes;               // 1 = tf32, 3 = 3xtf32
+  int mode;                 // MmaMode
   int n_taps;
   ConvTap taps[kMaxTaps];
   unsigned char tap_mask[kMaxNTiles];  // bit j set => tap j contributes to this N tile
@@ -72,7 +85,7 @@ struct ConvGemmParams {
   // ---- grid
   int batch;
   int m_tiles_per_clip;
-  int fast_sin;             // 1: MUFU-based sin in the Snake prologue (tf32 paths)
+  int precise_sin;          // 1: Cody-Waite + polynomial sin in Snake; 0: MUFU sin (abs err ~4e-7)
 };
 
 // ---- fp32 CUDA-core executor (conv_simt.cu): general tap extents, plain weights
@@ -88,7 +101,9 @@ struct ConvSimtParams {
   float* D; const float* R; long long d_clip_stride; int m_rows; int n_total; int n_valid; long long d_valid;
   const float* bias; int bias_period;
   const float* noise;
-  const float* alpha; int alpha_period; int prologue; int act;
+  const float* alpha; int alpha_period; int prologue;
+  const float* post_alpha; int post_period; int post;
+  int act;
   const float* W; int n_pad;
   int n_taps; SimtTap taps[kMaxTaps];
   unsigned char tap_mask[kMaxNTiles]; int mask_bn;  // mask granularity in columns (0 = no masks)
@@ -96,8 +111,10 @@ struct ConvSimtParams {
 };
 
 struct UmmaLaunch {
+  int a_stages;
   int w_stages;
   int a_rows_alloc;  // multiple of 8
+  int tma_epilogue;  // 1: output / residual tiles move by TMA through a swizzled smem ring
 };
 
 }  // namespace nc
@@ -110,5 +127,7 @@ int launch_conv_simt(const ConvSimtParams& p, cudaStream_t stream);
 int launch_conv_umma(const ConvGemmParams& p, int num_sms, cudaStream_t stream);
 // dynamic smem the tcgen05 kernel needs for this plan (0 = does not fit); fills L
 size_t umma_smem_bytes(const ConvGemmParams& p, UmmaLaunch* L);
+// whether the A view of p can be fetched by TMA (whole rows per clip, 16-byte aligned strides)
+bool umma_view_ok(const ConvGemmParams& p);
 }  // namespace nc
 #endif

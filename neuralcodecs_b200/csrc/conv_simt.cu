@@ -104,6 +104,8 @@ conv_simt_kernel(const __grid_constant__ ConvSimtParams p) {
       float x = acc[i][j];
       if (p.bias) x += __ldg(p.bias + n % p.bias_period);
       if (Rrow) x = p.noise ? fmaf(nz, x, Rrow[n]) : x + Rrow[n];
+      if (p.post != PRO_NONE)
+        x = simt_prologue(x, p.post == PRO_SNAKE ? __ldg(p.post_alpha + n % p.post_period) : 0.f, p.post);
       if (p.act == ACT_TANH) x = tanhf(x);
       Drow[n] = x;
     }

@@ -1,18 +1,30 @@
 // tcgen05 / TMEM implicit-GEMM executor of the multi-tap row-shifted GEMM (conv_plan.h).
 //
-// One persistent CTA per SM, 448 threads, warp-specialised:
-//   warp 0      weight producer : one thread streams pre-swizzled [BN x 32] fp32 weight tiles
-//                                 HBM/L2 -> smem with 1-D bulk async copies (UBLKCP) on an mbarrier ring
-//   warp 1      MMA issuer      : one thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8); a conv
-//                                 tap is a ROW SHIFT of the A-tile smem descriptor (the 128B swizzle is a
-//                                 function of absolute smem address bits, so start addresses that are not
-//                                 multiples of the 8-row period are legal; verified by tools/probe_umma.cu)
-//   warps 2-5   epilogue        : TMEM -> registers (tcgen05.ld 32x32b), + bias, + residual, tanh, store
-//   warps 6-13  A producers     : coalesced 128-bit loads of the channels-last input tile (+halo), the
-//                                 consumer's Snake/ELU applied ONCE per staged element, tf32 rounding
-//                                 (or hi/lo split for 3xTF32), swizzled st.shared, fence.proxy.async
+// One persistent CTA per SM, 576 threads, warp-specialised:
+//   warp 0       weight producer : one thread streams pre-swizzled [BN x 128 B] weight tiles
+//                                  HBM/L2 -> smem with 1-D bulk async copies (UBLKCP) on an mbarrier ring
+//   warp 1       MMA issuer      : one thread issues tcgen05.mma (M=128, N=BN); a conv tap is a ROW SHIFT
+//                                  of the A-tile smem descriptor (the 128B swizzle is a function of absolute
+//                                  smem address bits, so start addresses that are not multiples of the 8-row
+//                                  period are legal; verified by tools/probe_umma.cu)
+//   warps 2-9    epilogue        : TMEM -> registers (tcgen05.ld 32x32b), + bias, + residual, the NEXT layer's
+//                                  Snake/ELU ("post"), tanh, store; two warps per TMEM lane quarter
+//   warps 10-17  A transformers  : the raw fp32 input tile (+halo rows) of one 32-channel K chunk arrives by
+//                                  TMA (warp 18); these warps apply this conv's Snake/ELU ONCE per staged
+//                                  element and the operand rounding / hi-lo split IN PLACE in smem, then
+//                                  fence.proxy.async and hand the stage to the MMA issuer
+//   warp 18      A loader        : one thread issues cp.async.bulk.tensor (3-D map [clip][row][channel],
+//                                  128B swizzle, out-of-range rows zero-filled = the conv's zero padding) into
+//                                  a ring of up to 6 stages, so tens of KB are in flight per SM
 // Accumulators are double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the
-// main loop of tile i+1.
+// main loop of tile i+1.  Operand modes: see MmaMode in conv_plan.h.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <cstring>
+#include <mutex>
+
 #include "conv_plan.h"
 #include "umma.cuh"
 
@@ -21,16 +33,24 @@ namespace nc {
 using namespace ptx;
 
 constexpr int kBM = 128;
+constexpr int kEpilogueWarps = 8;
 constexpr int kProducerWarps = 8;
-constexpr int kProducerThreads = kProducerWarps * 32;
 constexpr int kFirstEpilogueWarp = 2;
-constexpr int kFirstProducerWarp = 6;
-constexpr int kUmmaThreads = 32 * (kFirstProducerWarp + kProducerWarps);  // 448
-constexpr int kAStages = 2;
+constexpr int kFirstProducerWarp = kFirstEpilogueWarp + kEpilogueWarps;           // 10
+constexpr int kLoaderWarp = kFirstProducerWarp + kProducerWarps;                  // 18
+constexpr int kResidualWarp = kLoaderWarp + 1;                                    // 19
+constexpr int kUmmaThreads = 32 * (kResidualWarp + 1);                            // 640
+constexpr int kEpiStages = 3;
+constexpr uint32_t kEpiStageBytes = kBM * 128;                                    // [128 rows][32 fp32]
+constexpr int kMaxAStages = 6;
 constexpr int kMaxWStages = 8;
-constexpr int kMaxARowIters = 6;  // (128 + span) <= 192 rows
 // 227 KB opt-in limit minus the kernel's static shared memory (barriers), rounded up to 1 KB
 constexpr size_t kUmmaMaxDynSmem = 227 * 1024 - 1024;
+
+// producer template codes
+constexpr int P_NONE = 0, P_SNAKE_FAST = 1, P_SNAKE_PRECISE = 2, P_ELU = 3;
+// operand template codes (BF16X3 and F16X3 share one instantiation)
+constexpr int O_TF32 = 0, O_TF32X3 = 1, O_H16X3 = 2;
 
 __device__ __forceinline__ float rna_tf32(float x) {
   uint32_t r;
@@ -38,27 +58,147 @@ __device__ __forceinline__ float rna_tf32(float x) {
   return __uint_as_float(r);
 }
 
-template <bool kFast>
+// |sin(x)| to ~1.2 ulp for |x| < 1e5 (3-term Cody-Waite reduction by pi/2 + degree-7/8 minimax
+// polynomials; the sign is dropped because Snake only uses sin^2).  Branch-free.
+__device__ __forceinline__ float sin_abs_precise(float x) {
+  const int q = __float2int_rn(x * 0.636619772f);
+  const float j = __int2float_rn(q);
+  float r = fmaf(j, -1.57079601e+00f, x);
+  r = fmaf(j, -3.13916473e-07f, r);
+  r = fmaf(j, -5.39030253e-15f, r);
+  const float s = r * r;
+  const bool odd = (q & 1) != 0;
+  float p = odd ? 2.44331571e-5f : -1.95152959e-4f;
+  p = fmaf(p, s, odd ? -1.38873163e-3f : 8.33216087e-3f);
+  p = fmaf(p, s, odd ? 4.16666457e-2f : -1.66666546e-1f);
+  const float a = odd ? fmaf(p, s, -0.5f) : p;
+  const float m = odd ? s : r * s;
+  const float b = odd ? 1.0f : r;
+  return fmaf(a, m, b);
+}
+
+template <bool kPrecise>
 __device__ __forceinline__ float snake_f(float x, float a, float ia) {
-  float s = kFast ? __sinf(a * x) : sinf(a * x);
-  return fmaf(s * s, ia, x);  // a == 0 -> ia == 0 -> x
+  const float t = a * x;
+  float s;
+  if (kPrecise) {
+    s = sin_abs_precise(t);
+    if (fabsf(t) > 9.0e4f) s = sinf(t);  // Payne-Hanek territory: never reached by real activations
+  } else {
+    s = __sinf(t);
+  }
+  return fmaf(s * s, ia, x);  // a == 0 -> ia == 0 -> x   (where(alpha == 0, x, x + sin^2(alpha x)/alpha))
 }
 __device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : expm1f(x); }
 
+template <int PRO>
+__device__ __forceinline__ float4 prologue4(float4 x, const float4& al, const float4& ia) {
+  if (PRO == P_SNAKE_FAST) {
+    x.x = snake_f<false>(x.x, al.x, ia.x); x.y = snake_f<false>(x.y, al.y, ia.y);
+    x.z = snake_f<false>(x.z, al.z, ia.z); x.w = snake_f<false>(x.w, al.w, ia.w);
+  } else if (PRO == P_SNAKE_PRECISE) {
+    x.x = snake_f<true>(x.x, al.x, ia.x); x.y = snake_f<true>(x.y, al.y, ia.y);
+    x.z = snake_f<true>(x.z, al.z, ia.z); x.w = snake_f<true>(x.w, al.w, ia.w);
+  } else if (PRO == P_ELU) {
+    x.x = elu_f(x.x); x.y = elu_f(x.y); x.z = elu_f(x.z); x.w = elu_f(x.w);
+  }
+  return x;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// 3-D tiled TMA load: box [1][rows][32 floats] at (channel c0, row r0, clip b) -> smem, completion on bar
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int r0, int b, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(r0), "r"(b), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int r0, int b) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(r0), "r"(b)
+               : "memory");
+}
+
+// v[16] += bias[n0 .. n0+16)  (index modulo bias_period: transposed convs repeat the bias per phase)
+__device__ __forceinline__ void epi_bias(const ConvGemmParams& p, float (&v)[16], int n0) {
+  if (!p.bias) return;
+  const int bi = n0 % p.bias_period;
+  if ((p.bias_period & 3) == 0 && bi + 16 <= p.bias_period) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + bi) + i);
+      v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + (n0 + i) % p.bias_period);
+  }
+}
+
+// the consumer's activation (applied once per element, here) followed by this layer's own activation
+__device__ __forceinline__ void epi_post(const ConvGemmParams& p, float (&v)[16], int n0) {
+  if (p.post == PRO_SNAKE) {
+    const int pi = n0 % p.post_period;
+    if ((p.post_period & 3) == 0 && pi + 16 <= p.post_period) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 al = __ldg(reinterpret_cast<const float4*>(p.post_alpha + pi) + i);
+        const float4 ia = __ldg(reinterpret_cast<const float4*>(p.post_inv_alpha + pi) + i);
+        if (p.precise_sin) {
+          v[4 * i + 0] = snake_f<true>(v[4 * i + 0], al.x, ia.x); v[4 * i + 1] = snake_f<true>(v[4 * i + 1], al.y, ia.y);
+          v[4 * i + 2] = snake_f<true>(v[4 * i + 2], al.z, ia.z); v[4 * i + 3] = snake_f<true>(v[4 * i + 3], al.w, ia.w);
+        } else {
+          v[4 * i + 0] = snake_f<false>(v[4 * i + 0], al.x, ia.x); v[4 * i + 1] = snake_f<false>(v[4 * i + 1], al.y, ia.y);
+          v[4 * i + 2] = snake_f<false>(v[4 * i + 2], al.z, ia.z); v[4 * i + 3] = snake_f<false>(v[4 * i + 3], al.w, ia.w);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int ai = (n0 + i) % p.post_period;
+        const float al = __ldg(p.post_alpha + ai), ia = __ldg(p.post_inv_alpha + ai);
+        v[i] = p.precise_sin ? snake_f<true>(v[i], al, ia) : snake_f<false>(v[i], al, ia);
+      }
+    }
+  } else if (p.post == PRO_ELU) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = elu_f(v[i]);
+  }
+  if (p.act == ACT_TANH) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i]);
+  }
+}
+
+template <int OPS, int PRO, int RIT>
 __global__ void __launch_bounds__(kUmmaThreads, 1)
-conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L) {
+conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, const __grid_constant__ CUtensorMap tmapA,
+                 const __grid_constant__ CUtensorMap tmapD, const __grid_constant__ CUtensorMap tmapR) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t a_tile_bytes = (uint32_t)L.a_rows_alloc * 128u;
-  const uint32_t a_stage_bytes = a_tile_bytes * (p.passes == 3 ? 2u : 1u);
+  const uint32_t a_stage_bytes = a_tile_bytes * (OPS == O_TF32X3 ? 2u : 1u);
   const uint32_t w_tile_bytes = (uint32_t)p.BN * 128u;
-  const uint32_t w_stage_bytes = w_tile_bytes * (p.passes == 3 ? 2u : 1u);
+  const uint32_t w_stage_bytes = w_tile_bytes * (OPS == O_TF32X3 ? 2u : 1u);
   uint8_t* sA = smem;
-  uint8_t* sW = smem + kAStages * a_stage_bytes;
+  uint8_t* sW = smem + (uint32_t)L.a_stages * a_stage_bytes;
+  uint8_t* sE = sW + (uint32_t)L.w_stages * w_stage_bytes;   // epilogue ring (TMA epilogue only)
 
-  __shared__ uint64_t a_full[kAStages], a_empty[kAStages];
+  __shared__ uint64_t raw_full[kMaxAStages], a_full[kMaxAStages], a_empty[kMaxAStages];
   __shared__ uint64_t w_full[kMaxWStages], w_empty[kMaxWStages];
   __shared__ uint64_t acc_full[2], acc_empty[2];
+  __shared__ uint64_t r_full[kEpiStages], e_free[kEpiStages];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x;
@@ -66,7 +206,8 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L) {
   const int lane = tid & 31;
 
   if (tid == 0) {
-    for (int i = 0; i < kAStages; ++i) {
+    for (int i = 0; i < kMaxAStages; ++i) {
+      mbar_init(&raw_full[i], 1);
       mbar_init(&a_full[i], kProducerWarps);
       mbar_init(&a_empty[i], 1);
     }
@@ -76,7 +217,11 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 4);
+      mbar_init(&acc_empty[i], kEpilogueWarps);
+    }
+    for (int i = 0; i < kEpiStages; ++i) {
+      mbar_init(&r_full[i], 1);
+      mbar_init(&e_free[i], 1);
     }
     fence_barrier_init();
   }
@@ -100,18 +245,15 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L) {
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile / tiles_per_n;
         const unsigned mask = p.tap_mask[nt];
-        const float* whi = p.W_hi + (size_t)nt * p.tiles_per_ntile * (size_t)(p.BN * 32);
-        const float* wlo = p.passes == 3 ? p.W_lo + (size_t)nt * p.tiles_per_ntile * (size_t)(p.BN * 32) : nullptr;
+        const float* wbase = p.W + (size_t)nt * p.tiles_per_ntile * (size_t)p.w_tile_floats;
         for (int kci = 0; kci < p.n_kc; ++kci) {
           const int kc = p.kc_begin + kci;
           for (int j = 0; j < p.n_taps; ++j) {
             if (!((mask >> j) & 1u) || kc < p.taps[j].kc_lo || kc >= p.taps[j].kc_hi) continue;
             mbar_wait(&w_empty[ws], wph ^ 1u);
-            const size_t toff = (size_t)(p.taps[j].tile_base + (kc - p.taps[j].kc_lo)) * (size_t)(p.BN * 32);
+            const size_t toff = (size_t)(p.taps[j].tile_base + (kc - p.taps[j].kc_lo)) * (size_t)p.w_tile_floats;
             mbar_arrive_expect_tx(&w_full[ws], w_stage_bytes);
-            bulk_g2s(sW + (size_t)ws * w_stage_bytes, whi + toff, w_tile_bytes, &w_full[ws]);
-            if (p.passes == 3)
-              bulk_g2s(sW + (size_t)ws * w_stage_bytes + w_tile_bytes, wlo + toff, w_tile_bytes, &w_full[ws]);
+            bulk_g2s(sW + (size_t)ws * w_stage_bytes, wbase + toff, w_stage_bytes, &w_full[ws]);
             if (++ws == L.w_stages) { ws = 0; wph ^= 1u; }
           }
         }
@@ -120,7 +262,8 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L) {
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = idesc_tf32(kBM, p.BN);
+      const uint32_t idesc = OPS == O_H16X3 ? idesc_f16(kBM, p.BN, p.mode == MODE_BF16X3 ? 1 : 0) : idesc_tf32(kBM, p.BN);
+      const uint32_t sA_u = smem_u32(sA), sW_u = smem_u32(sW);
       int ws = 0, as = 0, it = 0;
       uint32_t wph = 0, aph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -136,81 +279,129 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L) {
           const int kc = p.kc_begin + kci;
           mbar_wait(&a_full[as], aph);
           tc_fence_after();
-          const uint32_t a_stage = smem_u32(sA) + (uint32_t)as * a_stage_bytes;
+          const uint32_t a_stage = sA_u + (uint32_t)as * a_stage_bytes;
           for (int j = 0; j < p.n_taps; ++j) {
             if (!((mask >> j) & 1u) || kc < p.taps[j].kc_lo || kc >= p.taps[j].kc_hi) continue;
             mbar_wait(&w_full[ws], wph);
             tc_fence_after();
-            const uint32_t a_hi = a_stage + (uint32_t)(p.taps[j].shift - p.smin) * 128u;
-            const uint32_t b_hi = smem_u32(sW) + (uint32_t)ws * w_stage_bytes;
-            if (p.passes == 1) {
+            const uint64_t a0 = desc_at(a_stage + (uint32_t)(p.taps[j].shift - p.smin) * 128u);
+            const uint64_t b0 = desc_at(sW_u + (uint32_t)ws * w_stage_bytes);
+            if (OPS == O_TF32) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                umma_tf32(d_tmem, smem_desc_sw128(a_hi + k * 32, 1024), smem_desc_sw128(b_hi + k * 32, 1024),
-                          idesc, acc);
+              for (int k = 0; k < 4; ++k) {  // K step = 8 tf32 = 32 B = +2 in descriptor units
+                umma_tf32(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, acc);
                 acc = 1;
               }
-            } else {
-              const uint32_t a_lo = a_hi + a_tile_bytes;
-              const uint32_t b_lo = b_hi + w_tile_bytes;
+            } else if (OPS == O_TF32X3) {
+              const uint64_t a1 = a0 + (a_tile_bytes >> 4), b1 = b0 + (w_tile_bytes >> 4);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                umma_tf32(d_tmem, smem_desc_sw128(a_lo + k * 32, 1024), smem_desc_sw128(b_hi + k * 32, 1024),
-                          idesc, acc);
+                umma_tf32(d_tmem, a1 + 2 * k, b0 + 2 * k, idesc, acc);  // lo * hi
                 acc = 1;
-                umma_tf32(d_tmem, smem_desc_sw128(a_hi + k * 32, 1024), smem_desc_sw128(b_lo + k * 32, 1024),
-                          idesc, 1);
-                umma_tf32(d_tmem, smem_desc_sw128(a_hi + k * 32, 1024), smem_desc_sw128(b_hi + k * 32, 1024),
-                          idesc, 1);
+                umma_tf32(d_tmem, a0 + 2 * k, b1 + 2 * k, idesc, 1);    // hi * lo
+                umma_tf32(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, 1);    // hi * hi
+              }
+            } else {
+              // row = [32 hi halves (64 B) | 32 lo halves (64 B)]; K step = 16 halves = 32 B
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                umma_f16(d_tmem, a0 + 4 + 2 * k, b0 + 2 * k, idesc, acc);      // lo * hi
+                acc = 1;
+                umma_f16(d_tmem, a0 + 2 * k, b0 + 4 + 2 * k, idesc, 1);        // hi * lo
+                umma_f16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, 1);            // hi * hi
               }
             }
             tc_commit(&w_empty[ws]);
             if (++ws == L.w_stages) { ws = 0; wph ^= 1u; }
           }
           tc_commit(&a_empty[as]);
-          if (++as == kAStages) { as = 0; aph ^= 1u; }
+          if (++as == L.a_stages) { as = 0; aph ^= 1u; }
         }
         tc_commit(&acc_full[buf]);
       }
     }
+  } else if (warp == kLoaderWarp) {
+    // ===================================================================== A loader (TMA)
+    if (lane == 0) {
+      int as = 0;
+      uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile / tiles_per_n;
+        const int rem = tile - nt * tiles_per_n;
+        const int b = rem / p.m_tiles_per_clip;
+        const int mt = rem - b * p.m_tiles_per_clip;
+        const int r_base = mt * kBM + p.smin;
+        for (int kci = 0; kci < p.n_kc; ++kci) {
+          mbar_wait(&a_empty[as], aph ^ 1u);
+          mbar_arrive_expect_tx(&raw_full[as], a_tile_bytes);
+          tma_load_3d(sA + (size_t)as * a_stage_bytes, &tmapA, (p.kc_begin + kci) * 32, r_base, b, &raw_full[as]);
+          if (++as == L.a_stages) { as = 0; aph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == kResidualWarp) {
+    // ===================================================================== residual loader (TMA)
+    if (lane == 0 && L.tma_epilogue && p.R) {
+      const int groups = p.BN / 32;
+      int es = 0;
+      uint32_t eph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile / tiles_per_n;
+        const int rem = tile - nt * tiles_per_n;
+        const int b = rem / p.m_tiles_per_clip;
+        const int mt = rem - b * p.m_tiles_per_clip;
+        for (int g = 0; g < groups; ++g) {
+          mbar_wait(&e_free[es], eph ^ 1u);
+          mbar_arrive_expect_tx(&r_full[es], kEpiStageBytes);
+          tma_load_3d(sE + (size_t)es * kEpiStageBytes, &tmapR, nt * p.BN + g * 32, mt * kBM, b, &r_full[es]);
+          if (++es == kEpiStages) { es = 0; eph ^= 1u; }
+        }
+      }
+    }
   } else if (warp < kFirstProducerWarp) {
     // ===================================================================== epilogue
-    const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    const int q = warp & 3;                                  // TMEM lane quarter this warp may touch
+    const int half = (warp - kFirstEpilogueWarp) >> 2;       // which 16-column half of a 32-column group
     int it = 0;
-    const bool vec_ok = (p.n_total & 3) == 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int nt = tile / tiles_per_n;
-      const int rem = tile - nt * tiles_per_n;
-      const int b = rem / p.m_tiles_per_clip;
-      const int mt = rem - b * p.m_tiles_per_clip;
-      const int buf = it & 1;
-      const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
-      const int row = mt * kBM + q * 32 + lane;
-      const bool row_ok = row < p.m_rows;
-      const long long row_off = (long long)row * p.n_total;
-      float* Drow = p.D + (long long)b * p.d_clip_stride + row_off;
-      const float* Rrow = p.R ? p.R + (long long)b * p.d_clip_stride + row_off : nullptr;
-      const float nz = (p.noise && row_ok) ? __ldg(p.noise + (long long)b * p.m_rows + row) : 0.f;
-      mbar_wait(&acc_full[buf], acc_ph);
-      tc_fence_after();
-      const uint32_t t_addr = tmem_base + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16);
-      for (int cc = 0; cc < p.BN / 16; ++cc) {
-        float v[16];
-        __syncwarp();
-        tmem_ld16(t_addr + cc * 16, v);
-        tmem_ld_wait();
-        const int n0 = nt * p.BN + cc * 16;
-        if (!row_ok || n0 >= p.n_valid) continue;
-        if (p.bias) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + (n0 + i) % p.bias_period);
-        }
-        const bool full = (n0 + 16 <= p.n_valid) && (row_off + n0 + 16 <= p.d_valid);
-        if (full && vec_ok) {
-          if (Rrow) {
+    if (L.tma_epilogue) {
+      // Output (and residual) tiles move as [128 rows x 32 cols] fp32 boxes through a 128B-swizzled smem
+      // ring: residual arrives by TMA load, the result leaves by TMA store; every thread touches only its own
+      // row with conflict-free 128-bit smem accesses, so no uncoalesced global traffic is issued.
+      const int groups = p.BN / 32;
+      const bool leader = warp == kFirstEpilogueWarp && lane == 0;
+      int es = 0, prev = -1;
+      uint32_t eph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int nt = tile / tiles_per_n;
+        const int rem = tile - nt * tiles_per_n;
+        const int b = rem / p.m_tiles_per_clip;
+        const int mt = rem - b * p.m_tiles_per_clip;
+        const int buf = it & 1;
+        const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+        const int rloc = q * 32 + lane;
+        const int row = mt * kBM + rloc;
+        const float nz = (p.noise && row < p.m_rows) ? __ldg(p.noise + (long long)b * p.m_rows + row) : 0.f;
+        mbar_wait(&acc_full[buf], acc_ph);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16);
+        for (int g = 0; g < groups; ++g) {
+          float v[16];
+          __syncwarp();
+          tmem_ld16(t_addr + g * 32 + half * 16, v);
+          tmem_ld_wait();
+          if (g == groups - 1) {   // accumulator fully read by this warp: hand the TMEM buffer back early
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          }
+          const int n0 = nt * p.BN + g * 32 + half * 16;
+          epi_bias(p, v, n0);
+          uint8_t* stage = sE + (size_t)es * kEpiStageBytes;
+          if (p.R) mbar_wait(&r_full[es], eph); else mbar_wait(&e_free[es], eph ^ 1u);
+          if (p.R) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              float4 r = __ldg(reinterpret_cast<const float4*>(Rrow + n0) + i);
+              const float4 r = *reinterpret_cast<const float4*>(stage + sw128_offset((uint32_t)rloc, (uint32_t)(half * 4 + i)));
               if (p.noise) {
                 v[4 * i + 0] = fmaf(nz, v[4 * i + 0], r.x); v[4 * i + 1] = fmaf(nz, v[4 * i + 1], r.y);
                 v[4 * i + 2] = fmaf(nz, v[4 * i + 2], r.z); v[4 * i + 3] = fmaf(nz, v[4 * i + 3], r.w);
@@ -219,94 +410,154 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L) {
               }
             }
           }
-          if (p.act == ACT_TANH) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i]);
-          }
+          epi_post(p, v, n0);
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            reinterpret_cast<float4*>(Drow + n0)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        } else {
+            *reinterpret_cast<float4*>(stage + sw128_offset((uint32_t)rloc, (uint32_t)(half * 4 + i))) =
+                make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueWarps * 32) : "memory");
+          if (leader) {
+            tma_store_3d(&tmapD, stage, nt * p.BN + g * 32, mt * kBM, b);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the previous store has left smem
+            if (prev >= 0) mbar_arrive(&e_free[prev]);
+            prev = es;
+          }
+          if (++es == kEpiStages) { es = 0; eph ^= 1u; }
+        }
+      }
+      if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    } else {
+      // direct path (ragged outputs, Cout not a multiple of 32): each thread stores its own row
+      const bool vec_ok = (p.n_total & 3) == 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int nt = tile / tiles_per_n;
+        const int rem = tile - nt * tiles_per_n;
+        const int b = rem / p.m_tiles_per_clip;
+        const int mt = rem - b * p.m_tiles_per_clip;
+        const int buf = it & 1;
+        const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+        const int row = mt * kBM + q * 32 + lane;
+        const bool row_ok = row < p.m_rows;
+        const long long row_off = (long long)row * p.n_total;
+        float* Drow = p.D + (long long)b * p.d_clip_stride + row_off;
+        const float* Rrow = p.R ? p.R + (long long)b * p.d_clip_stride + row_off : nullptr;
+        const float nz = (p.noise && row_ok) ? __ldg(p.noise + (long long)b * p.m_rows + row) : 0.f;
+        mbar_wait(&acc_full[buf], acc_ph);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16);
+        for (int cc = half; cc < p.BN / 16; cc += 2) {
+          float v[16];
+          __syncwarp();
+          tmem_ld16(t_addr + cc * 16, v);
+          tmem_ld_wait();
+          const int n0 = nt * p.BN + cc * 16;
+          if (!row_ok || n0 >= p.n_valid) continue;
+          const bool full = (n0 + 16 <= p.n_valid) && (row_off + n0 + 16 <= p.d_valid);
+          epi_bias(p, v, n0);
+          if (Rrow) {
+            if (full && vec_ok) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int n = n0 + i;
-            if (n < p.n_valid && row_off + n < p.d_valid) {
-              float x = v[i];
-              if (Rrow) x = p.noise ? fmaf(nz, x, Rrow[n]) : x + Rrow[n];
-              if (p.act == ACT_TANH) x = tanhf(x);
-              Drow[n] = x;
+              for (int i = 0; i < 4; ++i) {
+                const float4 r = __ldg(reinterpret_cast<const float4*>(Rrow + n0) + i);
+                if (p.noise) {
+                  v[4 * i + 0] = fmaf(nz, v[4 * i + 0], r.x); v[4 * i + 1] = fmaf(nz, v[4 * i + 1], r.y);
+                  v[4 * i + 2] = fmaf(nz, v[4 * i + 2], r.z); v[4 * i + 3] = fmaf(nz, v[4 * i + 3], r.w);
+                } else {
+                  v[4 * i + 0] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int n = n0 + i;
+                if (n < p.n_valid && row_off + n < p.d_valid) v[i] = p.noise ? fmaf(nz, v[i], Rrow[n]) : v[i] + Rrow[n];
+              }
+            }
+          }
+          epi_post(p, v, n0);
+          if (full && vec_ok) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              reinterpret_cast<float4*>(Drow + n0)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int n = n0 + i;
+              if (n < p.n_valid && row_off + n < p.d_valid) Drow[n] = v[i];
             }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
   } else {
-    // ===================================================================== A producers
+    // ===================================================================== A transformers
     const int ptid = tid - kFirstProducerWarp * 32;
-    const int c = ptid & 7;      // 16-byte chunk of the 128-byte row
+    const int c = ptid & 7;      // 16-byte (4-float) chunk of the 128-byte input row
     const int rho0 = ptid >> 3;  // 0..31
     const int rows_needed = kBM + p.span;
     int as = 0;
     uint32_t aph = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int nt = tile / tiles_per_n;
-      const int rem = tile - nt * tiles_per_n;
-      const int b = rem / p.m_tiles_per_clip;
-      const int mt = rem - b * p.m_tiles_per_clip;
-      const float* Ab = p.A + (long long)b * p.a_clip_stride;
-      const int r_base = mt * kBM + p.smin;
       for (int kci = 0; kci < p.n_kc; ++kci) {
-        const int kcol = (p.kc_begin + kci) * 32 + c * 4;
-        float4 al = make_float4(0, 0, 0, 0), ia = al;
-        if (p.prologue == PRO_SNAKE) {
-          const int ai = kcol % p.alpha_period;
+        float4 al = make_float4(0.f, 0.f, 0.f, 0.f), ia = al;
+        if (PRO == P_SNAKE_FAST || PRO == P_SNAKE_PRECISE) {
+          const int ai = ((p.kc_begin + kci) * 32 + c * 4) % p.alpha_period;
           al = __ldg(reinterpret_cast<const float4*>(p.alpha + ai));
           ia = __ldg(reinterpret_cast<const float4*>(p.inv_alpha + ai));
         }
-        float4 v[kMaxARowIters];
-#pragma unroll
-        for (int i = 0; i < kMaxARowIters; ++i) {
-          const int rho = rho0 + 32 * i;
-          const int r = r_base + rho;
-          const long long e = (long long)r * p.a_pitch + kcol;
-          v[i] = make_float4(0, 0, 0, 0);
-          if (rho < rows_needed && r >= 0 && r < p.a_rows && e < p.a_valid)
-            v[i] = __ldg(reinterpret_cast<const float4*>(Ab + e));
-        }
-        mbar_wait(&a_empty[as], aph ^ 1u);
         uint8_t* stage = sA + (size_t)as * a_stage_bytes;
+        mbar_wait(&raw_full[as], aph);
+        float4 cur[RIT];
 #pragma unroll
-        for (int i = 0; i < kMaxARowIters; ++i) {
+        for (int i = 0; i < RIT; ++i) {
           const int rho = rho0 + 32 * i;
-          if (rho >= rows_needed) continue;
-          float4 x = v[i];
-          if (p.prologue == PRO_SNAKE) {
-            if (p.fast_sin) {
-              x.x = snake_f<true>(x.x, al.x, ia.x); x.y = snake_f<true>(x.y, al.y, ia.y);
-              x.z = snake_f<true>(x.z, al.z, ia.z); x.w = snake_f<true>(x.w, al.w, ia.w);
+          cur[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rho < rows_needed) cur[i] = *reinterpret_cast<const float4*>(stage + sw128_offset((uint32_t)rho, (uint32_t)c));
+        }
+        if (OPS == O_H16X3) __syncwarp();  // the 8 lanes of a row exchange 16-byte chunks in place
+#pragma unroll
+        for (int i = 0; i < RIT; ++i) {
+          const int rho = rho0 + 32 * i;
+          const float4 x = prologue4<PRO>(cur[i], al, ia);
+          if (rho < rows_needed) {
+            if (OPS == O_H16X3) {
+              // hi halves of channels 4c..4c+3 -> bytes [8c, 8c+8) of the row; lo halves -> 64 + [8c, 8c+8)
+              uint2 hi, lo;
+              if (p.mode == MODE_BF16X3) {
+                hi.x = pack_bf16(x.x, x.y); hi.y = pack_bf16(x.z, x.w);
+                const __nv_bfloat162 h0 = *reinterpret_cast<__nv_bfloat162*>(&hi.x), h1 = *reinterpret_cast<__nv_bfloat162*>(&hi.y);
+                lo.x = pack_bf16(x.x - __low2float(h0), x.y - __high2float(h0));
+                lo.y = pack_bf16(x.z - __low2float(h1), x.w - __high2float(h1));
+              } else {
+                hi.x = pack_f16(x.x, x.y); hi.y = pack_f16(x.z, x.w);
+                const __half2 h0 = *reinterpret_cast<__half2*>(&hi.x), h1 = *reinterpret_cast<__half2*>(&hi.y);
+                lo.x = pack_f16(x.x - __low2float(h0), x.y - __high2float(h0));
+                lo.y = pack_f16(x.z - __low2float(h1), x.w - __high2float(h1));
+              }
+              const uint32_t sub = (uint32_t)(c & 1) * 8u;
+              *reinterpret_cast<uint2*>(stage + sw128_offset((uint32_t)rho, (uint32_t)(c >> 1)) + sub) = hi;
+              *reinterpret_cast<uint2*>(stage + sw128_offset((uint32_t)rho, 4u + (uint32_t)(c >> 1)) + sub) = lo;
             } else {
-              x.x = snake_f<false>(x.x, al.x, ia.x); x.y = snake_f<false>(x.y, al.y, ia.y);
-              x.z = snake_f<false>(x.z, al.z, ia.z); x.w = snake_f<false>(x.w, al.w, ia.w);
+              const float4 hi = make_float4(rna_tf32(x.x), rna_tf32(x.y), rna_tf32(x.z), rna_tf32(x.w));
+              const uint32_t off = sw128_offset((uint32_t)rho, (uint32_t)c);
+              *reinterpret_cast<float4*>(stage + off) = hi;
+              if (OPS == O_TF32X3) {
+                const float4 lo = make_float4(rna_tf32(x.x - hi.x), rna_tf32(x.y - hi.y), rna_tf32(x.z - hi.z),
+                                              rna_tf32(x.w - hi.w));
+                *reinterpret_cast<float4*>(stage + a_tile_bytes + off) = lo;
+              }
             }
-          } else if (p.prologue == PRO_ELU) {
-            x.x = elu_f(x.x); x.y = elu_f(x.y); x.z = elu_f(x.z); x.w = elu_f(x.w);
-          }
-          float4 hi = make_float4(rna_tf32(x.x), rna_tf32(x.y), rna_tf32(x.z), rna_tf32(x.w));
-          const uint32_t off = sw128_offset((uint32_t)rho, (uint32_t)c);
-          *reinterpret_cast<float4*>(stage + off) = hi;
-          if (p.passes == 3) {
-            float4 lo = make_float4(rna_tf32(x.x - hi.x), rna_tf32(x.y - hi.y), rna_tf32(x.z - hi.z),
-                                    rna_tf32(x.w - hi.w));
-            *reinterpret_cast<float4*>(stage + a_tile_bytes + off) = lo;
           }
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_full[as]);
-        if (++as == kAStages) { as = 0; aph ^= 1u; }
+        if (++as == L.a_stages) { as = 0; aph ^= 1u; }
       }
     }
   }
@@ -317,38 +568,131 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L) {
 }
 
 // ------------------------------------------------------------------------------- host launcher
-static bool g_umma_attr_set[64] = {};
-
 size_t umma_smem_bytes(const ConvGemmParams& p, UmmaLaunch* L) {
   const int rows = ((kBM + p.span) + 7) / 8 * 8;
-  const size_t a_stage = (size_t)rows * 128 * (p.passes == 3 ? 2 : 1);
-  const size_t w_stage = (size_t)p.BN * 128 * (p.passes == 3 ? 2 : 1);
-  const size_t budget = kUmmaMaxDynSmem - 1024 /*alignment slack*/;
-  long avail = (long)budget - (long)(kAStages * a_stage);
-  int ws = (int)(avail / (long)w_stage);
-  if (ws > kMaxWStages) ws = kMaxWStages;
-  L->w_stages = ws;
+  const int mul = p.mode == MODE_TF32X3 ? 2 : 1;
+  const long a_stage = (long)rows * 128 * mul;
+  const long w_stage = (long)p.BN * 128 * mul;
+  // TMA epilogue: whole [rows x n_total] output per clip, 16-byte strides, N tile a multiple of 32 columns
+  L->tma_epilogue = (p.BN % 32 == 0 && p.n_total % 4 == 0 && p.d_valid == (long long)p.m_rows * p.n_total &&
+                     p.d_clip_stride % 4 == 0 && p.n_valid == p.n_total &&
+                     (reinterpret_cast<uintptr_t>(p.D) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.R) & 15) == 0)
+                        ? 1 : 0;
+  const long budget = (long)kUmmaMaxDynSmem - 1024 /*alignment slack*/ - (L->tma_epilogue ? (long)kEpiStages * kEpiStageBytes : 0);
   L->a_rows_alloc = rows;
-  if (ws < 2 || p.span > 64) return 0;
-  return 1024 + kAStages * a_stage + (size_t)ws * w_stage;
+  L->a_stages = L->w_stages = 0;
+  if (p.span > 64) return 0;
+  // at least 2 A stages and 2 W stages; then alternate while both fit (A up to 6, W up to 8):
+  // A stages buy bytes in flight from HBM, W stages hide L2 latency of the weight stream
+  int as = 2, ws = 2;
+  if (as * a_stage + ws * w_stage > budget) return 0;
+  for (;;) {
+    bool grew = false;
+    if (ws < 4 && as * a_stage + (ws + 1) * w_stage <= budget) { ++ws; grew = true; }
+    if (as < kMaxAStages && (as + 1) * a_stage + ws * w_stage <= budget) { ++as; grew = true; }
+    if (!grew) break;
+  }
+  while (ws < kMaxWStages && as * a_stage + (ws + 1) * w_stage <= budget) ++ws;
+  L->a_stages = as;
+  L->w_stages = ws;
+  return 1024 + (size_t)as * a_stage + (size_t)ws * w_stage + (L->tma_epilogue ? kEpiStages * kEpiStageBytes : 0);
+}
+
+typedef void (*UmmaKernel)(const ConvGemmParams, const UmmaLaunch, const CUtensorMap, const CUtensorMap, const CUtensorMap);
+
+template <int OPS, int PRO>
+static UmmaKernel pick_rit(int rit) {
+  switch (rit) {
+    case 4: return conv_umma_kernel<OPS, PRO, 4>;
+    case 5: return conv_umma_kernel<OPS, PRO, 5>;
+    default: return conv_umma_kernel<OPS, PRO, 6>;
+  }
+}
+template <int OPS>
+static UmmaKernel pick_pro(int pro, int rit) {
+  switch (pro) {
+    case P_NONE: return pick_rit<OPS, P_NONE>(rit);
+    case P_SNAKE_FAST: return pick_rit<OPS, P_SNAKE_FAST>(rit);
+    case P_SNAKE_PRECISE: return pick_rit<OPS, P_SNAKE_PRECISE>(rit);
+    default: return pick_rit<OPS, P_ELU>(rit);
+  }
+}
+static UmmaKernel pick_kernel(int mode, int pro, int rit) {
+  switch (mode) {
+    case MODE_TF32: return pick_pro<O_TF32>(pro, rit);
+    case MODE_TF32X3: return pick_pro<O_TF32X3>(pro, rit);
+    default: return pick_pro<O_H16X3>(pro, rit);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+// The A view can be fetched by TMA when every clip is a whole number of rows and strides are 16-byte multiples.
+bool umma_view_ok(const ConvGemmParams& p) {
+  return p.a_pitch % 4 == 0 && p.a_valid == (long long)p.a_rows * p.a_pitch && p.a_clip_stride % 4 == 0 &&
+         (reinterpret_cast<uintptr_t>(p.A) & 15) == 0 && p.batch >= 1;
 }
 
 // returns cudaError_t as int; 0 on success; -1 if the shape does not fit this kernel
 int launch_conv_umma(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
   UmmaLaunch L;
   const size_t smem = umma_smem_bytes(p, &L);
-  if (smem == 0) return -1;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !g_umma_attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaMaxDynSmem);
-    if (e != cudaSuccess) return (int)e;
-    if (dev >= 0 && dev < 64) g_umma_attr_set[dev] = true;
+  if (smem == 0 || !umma_view_ok(p)) return -1;
+  const int rows_needed = kBM + p.span;
+  const int rit = (rows_needed + 31) / 32;
+  if (rit > 6) return -1;
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return (int)cudaErrorNotSupported;
+  alignas(64) CUtensorMap tmap, tmapD, tmapR;
+  std::memset(&tmapD, 0, sizeof tmapD);
+  std::memset(&tmapR, 0, sizeof tmapR);
+  if (L.tma_epilogue) {
+    const cuuint64_t dd[3] = {(cuuint64_t)p.n_total, (cuuint64_t)p.m_rows, (cuuint64_t)p.batch};
+    const cuuint64_t ds[2] = {(cuuint64_t)p.n_total * 4, (cuuint64_t)p.d_clip_stride * 4};
+    const cuuint32_t db[3] = {32, (cuuint32_t)kBM, 1};
+    const cuuint32_t de[3] = {1, 1, 1};
+    if (enc(&tmapD, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p.D, dd, ds, db, de, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return (int)cudaErrorInvalidValue;
+    if (p.R && enc(&tmapR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.R), dd, ds, db, de,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return (int)cudaErrorInvalidValue;
   }
+  const cuuint64_t gdim[3] = {(cuuint64_t)p.a_pitch, (cuuint64_t)p.a_rows, (cuuint64_t)p.batch};
+  const cuuint64_t gstr[2] = {(cuuint64_t)p.a_pitch * 4, (cuuint64_t)p.a_clip_stride * 4};
+  const cuuint32_t box[3] = {32, (cuuint32_t)L.a_rows_alloc, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.A), gdim, gstr, box, estr,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return (int)cudaErrorInvalidValue;
+  int pro = P_NONE;
+  if (p.prologue == PRO_SNAKE) pro = p.precise_sin ? P_SNAKE_PRECISE : P_SNAKE_FAST;
+  else if (p.prologue == PRO_ELU) pro = P_ELU;
+  UmmaKernel k = pick_kernel(p.mode, pro, rit < 4 ? 4 : rit);
+  // opt-in shared memory: idempotent, set on every launch (handles may live on any device)
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaMaxDynSmem);
+  if (e != cudaSuccess) return (int)e;
   const int total_tiles = p.n_tiles * p.batch * p.m_tiles_per_clip;
   const int grid = total_tiles < num_sms ? total_tiles : num_sms;
   if (grid <= 0) return 0;
-  conv_umma_kernel<<<grid, kUmmaThreads, smem, stream>>>(p, L);
+  k<<<grid, kUmmaThreads, smem, stream>>>(p, L, tmap, tmapD, tmapR);
   return (int)cudaGetLastError();
 }
 

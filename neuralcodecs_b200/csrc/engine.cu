@@ -318,9 +318,7 @@ void DacEngine::finalize_weights() {
   ready_ = true;
 }
 
-static const char* prec_name(Precision p) {
-  return p == PREC_FP32 ? "fp32" : p == PREC_TF32 ? "tf32" : "3xtf32";
-}
+static const char* prec_name(Precision p) { return precision_name(p); }
 
 std::string DacEngine::describe() const {
   std::string s = "{\"codec\": \"DAC\", \"encoder_precision\": \"";
@@ -387,16 +385,22 @@ void DacEngine::ensure_workspace(int mb, int64_t Lp) {
   z_q_.reserve((size_t)mb * T * cfg_.latent_dim * sizeof(float));
 }
 
-int DacEngine::run_ru(const ResUnit& ru, int cur, int B, int T) {
+// One ResidualUnit (Modules/DAC/ResidualUnit.cs:24-59): y = conv_k1(Snake2(conv_k7(Snake1(x)))) + x.
+// Snake1 is the k7 conv's prologue (x stays raw for the residual); Snake2 is applied in the k7 conv's
+// epilogue (its output has no other reader), so the 1x1 conv streams its input untouched; `post`, when
+// given, is the Snake that follows this unit in the graph (block Snake before the strided / transposed
+// conv, or the codec's final Snake) and is applied in the 1x1 conv's epilogue after the residual add.
+int DacEngine::run_ru(const ResUnit& ru, int cur, int B, int T, const SnakeParams* post) {
   const LaunchCtx c = ctx();
   const int h = (cur + 1) % 3, y = (cur + 2) % 3;
   ConvRunArgs a;
   a.in = buf(cur); a.out = buf(h); a.batch = B; a.t_in = T;
   a.prologue = PRO_SNAKE; a.alpha = ru.s1.alpha; a.inv_alpha = ru.s1.inv_alpha;
+  a.post = PRO_SNAKE; a.post_alpha = ru.s2.alpha; a.post_inv_alpha = ru.s2.inv_alpha;
   ru.c1.run(a, c);
   ConvRunArgs b;
   b.in = buf(h); b.out = buf(y); b.residual = buf(cur); b.batch = B; b.t_in = T;
-  b.prologue = PRO_SNAKE; b.alpha = ru.s2.alpha; b.inv_alpha = ru.s2.inv_alpha;
+  if (post) { b.post = PRO_SNAKE; b.post_alpha = post->alpha; b.post_inv_alpha = post->inv_alpha; }
   ru.c2.run(b, c);
   return y;
 }
@@ -405,18 +409,20 @@ int DacEngine::run_encoder(const float* audio, long long audio_stride, int in_le
   const LaunchCtx c = ctx();
   launch_conv_cin1(audio, audio_stride, in_len, buf(0), Lp, cfg_.encoder_dim, d_conv_in_w_, d_conv_in_b_, 7, 1, 3, B, c);
   int cur = 0, T = Lp;
-  for (auto& blk : enc_blocks_) {
-    for (int u = 0; u < 3; ++u) cur = run_ru(blk->ru[u], cur, B, T);
-    ConvRunArgs a;
+  for (size_t i = 0; i < enc_blocks_.size(); ++i) {
+    auto& blk = enc_blocks_[i];
+    for (int u = 0; u < 3; ++u) cur = run_ru(blk->ru[u], cur, B, T, u == 2 ? &blk->s : nullptr);
+    ConvRunArgs a;   // input already carries the block's Snake (EncoderBlock.cs:26-33)
     a.in = buf(cur); a.out = buf((cur + 1) % 3); a.batch = B; a.t_in = T;
-    a.prologue = PRO_SNAKE; a.alpha = blk->s.alpha; a.inv_alpha = blk->s.inv_alpha;
+    if (i + 1 == enc_blocks_.size()) {   // Encoder.cs:44: Snake1d before the output conv
+      a.post = PRO_SNAKE; a.post_alpha = enc_snake_.alpha; a.post_inv_alpha = enc_snake_.inv_alpha;
+    }
     blk->down.run(a, c);
     T = blk->down.out_len(T);
     cur = (cur + 1) % 3;
   }
   ConvRunArgs a;
   a.in = buf(cur); a.out = z_in_.as<float>(); a.batch = B; a.t_in = T;
-  a.prologue = PRO_SNAKE; a.alpha = enc_snake_.alpha; a.inv_alpha = enc_snake_.inv_alpha;
   enc_out_.run(a, c);
   *T_out = enc_out_.out_len(T);
   return cur;
@@ -427,21 +433,24 @@ int DacEngine::run_decoder(int, int B, int T, float* audio_out, long long) {
   const LaunchCtx c = ctx();
   ConvRunArgs a;
   a.in = z_q_.as<float>(); a.out = buf(0); a.batch = B; a.t_in = T;
+  if (!dec_blocks_.empty()) {   // DecoderBlock.cs:26: Snake1d before the transposed conv
+    a.post = PRO_SNAKE; a.post_alpha = dec_blocks_[0]->s.alpha; a.post_inv_alpha = dec_blocks_[0]->s.inv_alpha;
+  }
   dec_in_.run(a, c);
   int cur = 0;
   T = dec_in_.out_len(T);
-  for (auto& blk : dec_blocks_) {
+  for (size_t i = 0; i < dec_blocks_.size(); ++i) {
+    auto& blk = dec_blocks_[i];
     ConvRunArgs u;
     u.in = buf(cur); u.out = buf((cur + 1) % 3); u.batch = B; u.t_in = T;
-    u.prologue = PRO_SNAKE; u.alpha = blk->s.alpha; u.inv_alpha = blk->s.inv_alpha;
     blk->up.run(u, c);
     T = blk->up.out_len(T);
     cur = (cur + 1) % 3;
-    for (int r = 0; r < 3; ++r) cur = run_ru(blk->ru[r], cur, B, T);
+    const SnakeParams* next = i + 1 < dec_blocks_.size() ? &dec_blocks_[i + 1]->s : &dec_snake_;
+    for (int r = 0; r < 3; ++r) cur = run_ru(blk->ru[r], cur, B, T, r == 2 ? next : nullptr);
   }
-  ConvRunArgs o;
+  ConvRunArgs o;   // Decoder.cs:44-46: (Snake already applied) -> conv -> tanh
   o.in = buf(cur); o.out = audio_out; o.batch = B; o.t_in = T;
-  o.prologue = PRO_SNAKE; o.alpha = dec_snake_.alpha; o.inv_alpha = dec_snake_.inv_alpha;
   o.act = ACT_TANH;
   dec_out_.run(o, c);
   return cur;

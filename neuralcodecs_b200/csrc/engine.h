@@ -116,7 +116,7 @@ class DacEngine : public Engine {
   Precision boosted(Precision p, bool narrow) const;
   void build_ru(ResUnit& ru, const std::string& prefix, int dim, int dil, Precision prec);
   // returns the buffer index holding the result; T_io: in = input length, out = output length
-  int run_ru(const ResUnit& ru, int cur, int B, int T);
+  int run_ru(const ResUnit& ru, int cur, int B, int T, const SnakeParams* post);
   int run_encoder(const float* audio, long long audio_stride, int in_len, int B, int Lp, int* T_out);
   int run_decoder(int cur, int B, int T, float* audio_out, long long out_stride);
   int micro_batch(int B, int64_t Lp) const;

@@ -139,6 +139,30 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
          | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// kind::f16 with BF16 (fmt = 1) or FP16 (fmt = 0) operands, fp32 accumulate, K-major, dense.
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int fmt) {
+  return (1u << 4) | (static_cast<uint32_t>(fmt) << 7) | (static_cast<uint32_t>(fmt) << 10) |
+         (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// constant part of a K-major SWIZZLE_128B descriptor with SBO = 1024 (8-row groups contiguous);
+// OR in ((smem byte address & 0x3FFFF) >> 4) to get the descriptor of a tile / K step / row shift.
+constexpr uint64_t kDescSw128Base = (static_cast<uint64_t>(1) << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) |
+                                    (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61);
+__device__ __forceinline__ uint64_t desc_at(uint32_t saddr) {
+  return kDescSw128Base | static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                           uint32_t idesc, uint32_t accumulate) {

@@ -293,6 +293,15 @@ void ConvLayer::build(const std::string& name, const ConvSpec& spec, const std::
       }
     }
     d_w_tiles_ = upload(tiles);
+    // dense plan: every tap reads every K chunk, contributes to every N tile, and shifts are equally spaced
+    dense_step_ = taps_.size() == 1 ? 0 : taps_[1].shift - taps_[0].shift;
+    for (size_t j = 0; j < taps_.size(); ++j) {
+      if (utaps_[j].kc_lo != kc_begin_ || utaps_[j].kc_hi != kc_begin_ + n_kc_ ||
+          taps_[j].shift != smin_ + (int)j * dense_step_)
+        dense_step_ = -1;
+    }
+    for (int nt = 0; nt < n_tiles_ && dense_step_ >= 0; ++nt)
+      if (tap_mask_[nt] != (unsigned char)((1u << taps_.size()) - 1)) dense_step_ = -1;
   }
   // plain weights for the CUDA-core executor: fp32 layers, and strided convs whose input length may
   // not be a whole number of rows (the TMA-fed tensor-core kernel needs whole rows per clip)
@@ -348,6 +357,7 @@ void ConvLayer::run(const ConvRunArgs& a, const LaunchCtx& ctx) const {
     for (int j = 0; j < p.n_taps; ++j) p.taps[j] = utaps_[j];
     std::memcpy(p.tap_mask, tap_mask_, sizeof tap_mask_);
     p.n_kc = n_kc_; p.kc_begin = kc_begin_; p.smin = smin_; p.span = span_;
+    p.dense_step = dense_step_;
     p.batch = a.batch; p.m_tiles_per_clip = m_tiles;
     const int fast = g_fast_sin >= 0 ? g_fast_sin : ((mode_ == PREC_TF32 || mode_ == PREC_BF16X3) ? 1 : 0);
     p.precise_sin = fast ? 0 : 1;

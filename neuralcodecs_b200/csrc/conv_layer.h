@@ -85,7 +85,7 @@ class ConvLayer {
   int bn_ = 0, n_tiles_ = 0, tiles_per_ntile_ = 0;
   ConvTap utaps_[kMaxTaps];
   unsigned char tap_mask_[kMaxNTiles];
-  int kc_begin_ = 0, n_kc_ = 0, smin_ = 0, span_ = 0;
+  int kc_begin_ = 0, n_kc_ = 0, smin_ = 0, span_ = 0, dense_step_ = -1;
   long long simt_w_off_[kMaxTaps];
   bool umma_ok_ = false;
 };

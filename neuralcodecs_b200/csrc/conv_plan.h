@@ -80,6 +80,8 @@ struct ConvGemmParams {
   unsigned char tap_mask[kMaxNTiles];  // bit j set => tap j contributes to this N tile
   int n_kc;                 // K chunks of the A view touched by any tap: [kc_begin, kc_begin + n_kc)
   int kc_begin;
+  int dense_step;           // >= 0: every tap covers every K chunk of every N tile and shift_j = smin + j*dense_step
+                            // (stride-1 convs: dense_step = dilation); -1: general plan (use taps[] / tap_mask[])
   int smin;                 // min shift over taps
   int span;                 // max shift - min shift
   // ---- grid

@@ -22,6 +22,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -239,7 +240,7 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
 
   if (warp == 0) {
     // ===================================================================== weight producer
-    if (lane == 0) {
+    if (elect_one()) {
       int ws = 0;
       uint32_t wph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -261,68 +262,77 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
+    // ONE elected lane runs the whole persistent loop (elect.sync tells ptxas the region is single-threaded,
+    // so descriptors go straight to uniform registers and each tcgen05.mma is a single UTCHMMA).
+    if (elect_one()) {
       const uint32_t idesc = OPS == O_H16X3 ? idesc_f16(kBM, p.BN, p.mode == MODE_BF16X3 ? 1 : 0) : idesc_tf32(kBM, p.BN);
-      const uint32_t sA_u = smem_u32(sA), sW_u = smem_u32(sW);
+      const uint64_t a_desc0 = desc_at(smem_u32(sA)), w_desc0 = desc_at(smem_u32(sW));
+      const uint32_t a_stage_u = a_stage_bytes >> 4, w_stage_u = w_stage_bytes >> 4;   // descriptor units (16 B)
+      const uint32_t a_lo_u = a_tile_bytes >> 4, w_lo_u = w_tile_bytes >> 4;
+      const uint32_t tap_u = (uint32_t)p.dense_step * 8u;                             // rows * 128 B / 16
       int ws = 0, as = 0, it = 0;
       uint32_t wph = 0, aph = 0;
+      uint64_t a_desc = a_desc0, w_desc = w_desc0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int nt = tile / tiles_per_n;
-        const unsigned mask = p.tap_mask[nt];
         const int buf = it & 1;
         const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
         mbar_wait(&acc_empty[buf], acc_ph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u;
         uint32_t acc = 0;
+        const unsigned mask = p.dense_step >= 0 ? 0u : (unsigned)p.tap_mask[tile / tiles_per_n];
         for (int kci = 0; kci < p.n_kc; ++kci) {
-          const int kc = p.kc_begin + kci;
           mbar_wait(&a_full[as], aph);
           tc_fence_after();
-          const uint32_t a_stage = sA_u + (uint32_t)as * a_stage_bytes;
+          uint64_t a_tap = a_desc;
           for (int j = 0; j < p.n_taps; ++j) {
-            if (!((mask >> j) & 1u) || kc < p.taps[j].kc_lo || kc >= p.taps[j].kc_hi) continue;
+            if (p.dense_step >= 0) {
+              // stride-1 conv: every tap reads every chunk; tap j is the A tile shifted down by j*dilation rows
+              if (j) a_tap += tap_u;
+            } else {
+              const int kc = p.kc_begin + kci;
+              if (!((mask >> j) & 1u) || kc < p.taps[j].kc_lo || kc >= p.taps[j].kc_hi) continue;
+              a_tap = a_desc + (uint32_t)(p.taps[j].shift - p.smin) * 8u;
+            }
             mbar_wait(&w_full[ws], wph);
             tc_fence_after();
-            const uint64_t a0 = desc_at(a_stage + (uint32_t)(p.taps[j].shift - p.smin) * 128u);
-            const uint64_t b0 = desc_at(sW_u + (uint32_t)ws * w_stage_bytes);
+            const uint64_t a0 = a_tap, b0 = w_desc;
             if (OPS == O_TF32) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {  // K step = 8 tf32 = 32 B = +2 in descriptor units
-                umma_tf32(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, acc);
-                acc = 1;
-              }
+              for (int k = 0; k < 4; ++k)   // K step = 8 tf32 = 32 B = +2 descriptor units
+                umma_tf32(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, acc | (uint32_t)k);
             } else if (OPS == O_TF32X3) {
-              const uint64_t a1 = a0 + (a_tile_bytes >> 4), b1 = b0 + (w_tile_bytes >> 4);
+              const uint64_t a1 = a0 + a_lo_u, b1 = b0 + w_lo_u;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                umma_tf32(d_tmem, a1 + 2 * k, b0 + 2 * k, idesc, acc);  // lo * hi
-                acc = 1;
-                umma_tf32(d_tmem, a0 + 2 * k, b1 + 2 * k, idesc, 1);    // hi * lo
-                umma_tf32(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, 1);    // hi * hi
+                umma_tf32(d_tmem, a1 + 2 * k, b0 + 2 * k, idesc, acc | (uint32_t)k);  // lo * hi
+                umma_tf32(d_tmem, a0 + 2 * k, b1 + 2 * k, idesc, 1);                  // hi * lo
+                umma_tf32(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, 1);                  // hi * hi
               }
             } else {
               // row = [32 hi halves (64 B) | 32 lo halves (64 B)]; K step = 16 halves = 32 B
 #pragma unroll
               for (int k = 0; k < 2; ++k) {
-                umma_f16(d_tmem, a0 + 4 + 2 * k, b0 + 2 * k, idesc, acc);      // lo * hi
-                acc = 1;
-                umma_f16(d_tmem, a0 + 2 * k, b0 + 4 + 2 * k, idesc, 1);        // hi * lo
-                umma_f16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, 1);            // hi * hi
+                umma_f16(d_tmem, a0 + 4 + 2 * k, b0 + 2 * k, idesc, acc | (uint32_t)k);  // lo * hi
+                umma_f16(d_tmem, a0 + 2 * k, b0 + 4 + 2 * k, idesc, 1);                  // hi * lo
+                umma_f16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, 1);                      // hi * hi
               }
             }
             tc_commit(&w_empty[ws]);
-            if (++ws == L.w_stages) { ws = 0; wph ^= 1u; }
+            acc = 1;
+            w_desc += w_stage_u;
+            if (++ws == L.w_stages) { ws = 0; wph ^= 1u; w_desc = w_desc0; }
           }
           tc_commit(&a_empty[as]);
-          if (++as == L.a_stages) { as = 0; aph ^= 1u; }
+          a_desc += a_stage_u;
+          if (++as == L.a_stages) { as = 0; aph ^= 1u; a_desc = a_desc0; }
         }
         tc_commit(&acc_full[buf]);
       }
     }
   } else if (warp == kLoaderWarp) {
     // ===================================================================== A loader (TMA)
-    if (lane == 0) {
+    if (elect_one()) {
       int as = 0;
       uint32_t aph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -341,7 +351,7 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
     }
   } else if (warp == kResidualWarp) {
     // ===================================================================== residual loader (TMA)
-    if (lane == 0 && L.tma_epilogue && p.R) {
+    if (L.tma_epilogue && p.R && elect_one()) {
       const int groups = p.BN / 32;
       int es = 0;
       uint32_t eph = 0;
@@ -586,10 +596,11 @@ size_t umma_smem_bytes(const ConvGemmParams& p, UmmaLaunch* L) {
   // A stages buy bytes in flight from HBM, W stages hide L2 latency of the weight stream
   int as = 2, ws = 2;
   if (as * a_stage + ws * w_stage > budget) return 0;
+  static const int w_first = getenv("NC_W_FIRST") ? atoi(getenv("NC_W_FIRST")) : 4;
   for (;;) {
     bool grew = false;
-    if (ws < 4 && as * a_stage + (ws + 1) * w_stage <= budget) { ++ws; grew = true; }
-    if (as < kMaxAStages && (as + 1) * a_stage + ws * w_stage <= budget) { ++as; grew = true; }
+    if (ws < w_first && as * a_stage + (ws + 1) * w_stage <= budget) { ++ws; grew = true; }
+    if (as < kMaxAStages && (as + 1) * a_stage + ws * w_stage <= budget && (ws >= w_first || as < 3)) { ++as; grew = true; }
     if (!grew) break;
   }
   while (ws < kMaxWStages && as * a_stage + (ws + 1) * w_stage <= budget) ++ws;

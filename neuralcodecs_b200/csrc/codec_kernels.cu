@@ -6,50 +6,129 @@
 namespace nc {
 
 // ------------------------------------------------------------------------------ first conv (Cin = 1)
+// Each thread owns 4 output channels for the whole launch (weights + bias in registers) and walks time;
+// a warp writes 2 consecutive time steps x 64 channels = 512 contiguous bytes per store instruction.
+template <int K>
 __global__ void __launch_bounds__(256)
 conv_cin1_kernel(const float* __restrict__ in, long long in_stride, int in_len, float* __restrict__ out, int t_out,
-                 int cout, const float* __restrict__ w, const float* __restrict__ bias, int k, int dil, int pad,
-                 int batch) {
-  extern __shared__ float sw[];  // [cout][k] + [cout]
-  for (int i = threadIdx.x; i < cout * k; i += blockDim.x) sw[i] = w[i];
-  for (int i = threadIdx.x; i < cout; i += blockDim.x) sw[cout * k + i] = bias ? bias[i] : 0.f;
-  __syncthreads();
+                 int cout, const float* __restrict__ w, const float* __restrict__ bias, int dil, int pad, int batch) {
   const int c4n = cout / 4;
-  const long long total = (long long)batch * t_out * c4n;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % c4n);
-    const long long bt = i / c4n;
+  const int lanes_t = blockDim.x / c4n;              // time steps covered by one block iteration
+  const int c4 = threadIdx.x % c4n, tl = threadIdx.x / c4n;
+  float wr[4][K], br[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    br[i] = bias ? __ldg(bias + 4 * c4 + i) : 0.f;
+#pragma unroll
+    for (int j = 0; j < K; ++j) wr[i][j] = __ldg(w + (4 * c4 + i) * K + j);
+  }
+  const long long total_t = (long long)batch * t_out;
+  for (long long bt = (long long)blockIdx.x * lanes_t + tl; bt < total_t; bt += (long long)gridDim.x * lanes_t) {
     const int t = (int)(bt % t_out);
     const int b = (int)(bt / t_out);
     const float* x = in + (long long)b * in_stride;
-    float a0 = sw[cout * k + 4 * c4 + 0], a1 = sw[cout * k + 4 * c4 + 1], a2 = sw[cout * k + 4 * c4 + 2],
-          a3 = sw[cout * k + 4 * c4 + 3];
-    for (int j = 0; j < k; ++j) {
+    float a0 = br[0], a1 = br[1], a2 = br[2], a3 = br[3];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
       const int ti = t + j * dil - pad;
       const float v = (ti >= 0 && ti < in_len) ? __ldg(x + ti) : 0.f;
-      a0 = fmaf(sw[(4 * c4 + 0) * k + j], v, a0);
-      a1 = fmaf(sw[(4 * c4 + 1) * k + j], v, a1);
-      a2 = fmaf(sw[(4 * c4 + 2) * k + j], v, a2);
-      a3 = fmaf(sw[(4 * c4 + 3) * k + j], v, a3);
+      a0 = fmaf(wr[0][j], v, a0); a1 = fmaf(wr[1][j], v, a1); a2 = fmaf(wr[2][j], v, a2); a3 = fmaf(wr[3][j], v, a3);
     }
-    reinterpret_cast<float4*>(out)[i] = make_float4(a0, a1, a2, a3);
+    reinterpret_cast<float4*>(out)[bt * c4n + c4] = make_float4(a0, a1, a2, a3);
   }
 }
 
 void launch_conv_cin1(const float* in, long long in_stride, int in_len, float* out, int t_out, int cout,
                       const float* w, const float* bias, int k, int dil, int pad, int batch, const LaunchCtx& ctx) {
-  if (cout % 4 != 0) throw Error(NC_UNSUPPORTED, "conv_cin1: Cout must be a multiple of 4");
-  const long long total = (long long)batch * t_out * (cout / 4);
-  if (total == 0) return;
-  long long blocks = (total + 255) / 256;
-  const long long cap = (long long)ctx.num_sms * 16;
+  if (cout % 4 != 0 || 256 % (cout / 4) != 0) throw Error(NC_UNSUPPORTED, "conv_cin1: Cout/4 must divide 256");
+  if (k != 7 && k != 3) throw Error(NC_UNSUPPORTED, "conv_cin1: kernel size must be 3 or 7");
+  const long long total_t = (long long)batch * t_out;
+  if (total_t == 0) return;
+  const int lanes_t = 256 / (cout / 4);
+  long long blocks = (total_t + lanes_t - 1) / lanes_t;
+  const long long cap = (long long)ctx.num_sms * 8;
   if (blocks > cap) blocks = cap;
   const int ev = ctx.begin();
-  conv_cin1_kernel<<<(unsigned)blocks, 256, (size_t)(cout * k + cout) * sizeof(float), ctx.stream>>>(
-      in, in_stride, in_len, out, t_out, cout, w, bias, k, dil, pad, batch);
+  if (k == 7)
+    conv_cin1_kernel<7><<<(unsigned)blocks, 256, 0, ctx.stream>>>(in, in_stride, in_len, out, t_out, cout, w, bias, dil, pad, batch);
+  else
+    conv_cin1_kernel<3><<<(unsigned)blocks, 256, 0, ctx.stream>>>(in, in_stride, in_len, out, t_out, cout, w, bias, dil, pad, batch);
   check_launch((int)cudaGetLastError(), "conv_cin1");
   ctx.end(ev, "conv_cin1", 2.0 * k * cout * (double)t_out * batch, 4.0 * batch * ((double)in_len + (double)t_out * cout));
+}
+
+// ------------------------------------------------------------------------------ last conv (Cout = 1)
+// out[b, t] = act(bias + sum_j sum_c w[j, c] * x[b, t + j - pad, c]); x channels-last, already carrying the
+// preceding Snake.  One block produces kCoutTile consecutive samples: every input row is read ONCE (8 lanes
+// per row, 384 contiguous bytes for C = 96), its K partial dot products go to shared memory, then thread t
+// gathers its K diagonal entries.  HBM-bound: C*4 bytes in, 4 bytes out per sample.
+constexpr int kCoutTile = 256;
+template <int K>
+__global__ void __launch_bounds__(256)
+conv_cout1_kernel(const float* __restrict__ in, float* __restrict__ out, int T, int C, const float* __restrict__ w /*[K][C]*/,
+                  const float* __restrict__ bias, int pad, int act, int tiles_per_clip) {
+  extern __shared__ float sm[];
+  float* sw = sm;                    // [K][C]
+  float* sp = sm + K * C;            // [kCoutTile + K - 1][K]
+  for (int i = threadIdx.x; i < K * C; i += blockDim.x) sw[i] = w[i];
+  const int b = blockIdx.x / tiles_per_clip;
+  const int t0 = (blockIdx.x - b * tiles_per_clip) * kCoutTile;
+  const float* x = in + (long long)b * T * C;
+  __syncthreads();
+  const int grp = threadIdx.x >> 3, l8 = threadIdx.x & 7;   // 32 row groups of 8 lanes
+  const int rows = kCoutTile + K - 1;
+  const int c4_per_lane = C / 32;                            // float4 per lane
+  for (int r0 = 0; r0 < rows; r0 += 32) {   // uniform trip count: the shuffles below need the whole warp
+    const int r = r0 + grp;
+    const int tr = t0 + r - pad;
+    float acc[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) acc[j] = 0.f;
+    if (r < rows && tr >= 0 && tr < T) {
+      const float4* xr = reinterpret_cast<const float4*>(x + (long long)tr * C);
+      for (int i = 0; i < c4_per_lane; ++i) {
+        const int c4 = i * 8 + l8;
+        const float4 v = __ldg(xr + c4);
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          const float4 ww = *reinterpret_cast<const float4*>(sw + j * C + 4 * c4);
+          acc[j] = fmaf(v.x, ww.x, acc[j]); acc[j] = fmaf(v.y, ww.y, acc[j]);
+          acc[j] = fmaf(v.z, ww.z, acc[j]); acc[j] = fmaf(v.w, ww.w, acc[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 1);
+      acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 2);
+      acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 4);
+    }
+    if (l8 == 0 && r < rows) {
+#pragma unroll
+      for (int j = 0; j < K; ++j) sp[r * K + j] = acc[j];
+    }
+  }
+  __syncthreads();
+  const int t = t0 + threadIdx.x;
+  if (t < T) {
+    float v = bias ? __ldg(bias) : 0.f;
+#pragma unroll
+    for (int j = 0; j < K; ++j) v += sp[(threadIdx.x + j) * K + j];
+    if (act == 1) v = tanhf(v);
+    out[(long long)b * T + t] = v;
+  }
+}
+
+void launch_conv_cout1(const float* in, float* out, int T, int C, const float* w_kc, const float* bias, int k, int pad,
+                       int act, int batch, const LaunchCtx& ctx) {
+  if (C % 32 != 0 || k != 7) throw Error(NC_UNSUPPORTED, "conv_cout1: needs C % 32 == 0 and kernel size 7");
+  if ((long long)batch * T == 0) return;
+  const int tiles = (T + kCoutTile - 1) / kCoutTile;
+  const size_t smem = (size_t)(7 * C + (kCoutTile + 6) * 7) * sizeof(float);
+  const int ev = ctx.begin();
+  conv_cout1_kernel<7><<<(unsigned)(batch * tiles), 256, smem, ctx.stream>>>(in, out, T, C, w_kc, bias, pad, act, tiles);
+  check_launch((int)cudaGetLastError(), "conv_cout1");
+  ctx.end(ev, "conv_cout1", 2.0 * k * C * (double)T * batch, 4.0 * batch * ((double)T * C + T));
 }
 
 // ------------------------------------------------------------------------------ transposes

@@ -14,6 +14,11 @@ void launch_conv_cin1(const float* in, long long in_stride, int in_len, float* o
                       const float* w /*[cout][k]*/, const float* bias, int k, int dil, int pad, int batch,
                       const LaunchCtx& ctx);
 
+// out[b, t] = act(bias + sum_j sum_c w[j][c] * in[b, t + j - pad, c])   (Cout = 1, stride 1, dilation 1; act 1 = tanh)
+// in: [B][T][C] channels-last (already activated); out: [B][T]; w_kc: [k][C].
+void launch_conv_cout1(const float* in, float* out, int T, int C, const float* w_kc, const float* bias, int k, int pad,
+                       int act, int batch, const LaunchCtx& ctx);
+
 // [B][C][T] <-> [B][T][C]
 void launch_transpose_ct_to_tc(const float* in, float* out, int batch, int C, int T, const LaunchCtx& ctx);
 void launch_transpose_tc_to_ct(const float* in, float* out, int batch, int C, int T, const LaunchCtx& ctx);

@@ -122,6 +122,8 @@ DacEngine::~DacEngine() {
   cudaSetDevice(device_);
   cudaFree(d_conv_in_w_);
   cudaFree(d_conv_in_b_);
+  cudaFree(d_conv_out_w_);
+  cudaFree(d_conv_out_b_);
   for (float* p : rvq_alloc_) cudaFree(p);
 }
 
@@ -313,6 +315,18 @@ void DacEngine::finalize_weights() {
     cs.cin = cout; cs.cout = 1; cs.k = 7; cs.padding = 3;
     auto w = folded_conv("decoder.conv2", 1, cout, 7, &b, 1);
     dec_out_.build("decoder.conv2", cs, w, b, boosted(dec_prec_, true));
+    // Cout = 1: a GEMV, not a GEMM -- dedicated HBM-bound fp32 kernel when the channel count allows
+    cudaFree(d_conv_out_w_); cudaFree(d_conv_out_b_);
+    d_conv_out_w_ = d_conv_out_b_ = nullptr;
+    conv_out_c_ = 0;
+    if (cout % 32 == 0) {
+      std::vector<float> wkc((size_t)7 * cout);
+      for (int ci = 0; ci < cout; ++ci)
+        for (int j = 0; j < 7; ++j) wkc[(size_t)j * cout + ci] = w[(size_t)ci * 7 + j];
+      d_conv_out_w_ = upload(wkc);
+      if (!b.empty()) d_conv_out_b_ = upload(b);
+      conv_out_c_ = cout;
+    }
   }
   drop_tensors();
   ready_ = true;
@@ -452,7 +466,10 @@ int DacEngine::run_decoder(int, int B, int T, float* audio_out, long long) {
   ConvRunArgs o;   // Decoder.cs:44-46: (Snake already applied) -> conv -> tanh
   o.in = buf(cur); o.out = audio_out; o.batch = B; o.t_in = T;
   o.act = ACT_TANH;
-  dec_out_.run(o, c);
+  if (conv_out_c_)
+    launch_conv_cout1(buf(cur), audio_out, T, conv_out_c_, d_conv_out_w_, d_conv_out_b_, 7, 3, 1, B, c);
+  else
+    dec_out_.run(o, c);
   return cur;
 }
 

@@ -124,7 +124,7 @@ class DacEngine : public Engine {
   float* buf(int i) { return ws_[i].as<float>(); }
 
   DacConfig cfg_;
-  Precision enc_prec_ = PREC_3XTF32, dec_prec_ = PREC_TF32;
+  Precision enc_prec_ = PREC_BF16X3, dec_prec_ = PREC_BF16X3;
   bool dec_boost_ = true;
   // encoder
   float* d_conv_in_w_ = nullptr;
@@ -140,6 +140,9 @@ class DacEngine : public Engine {
   std::vector<std::unique_ptr<DecBlock>> dec_blocks_;
   SnakeParams dec_snake_;
   ConvLayer dec_out_;
+  float* d_conv_out_w_ = nullptr;  // [7][C] for the Cout = 1 kernel (null: use dec_out_)
+  float* d_conv_out_b_ = nullptr;
+  int conv_out_c_ = 0;
   // workspaces: 3 rotating activation buffers + latent buffers
   DeviceBuffer ws_[3], z_in_, z_q_;
   int64_t per_clip_elems_ = 0;  // per padded sample, see ensure_workspace

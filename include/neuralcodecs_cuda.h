@@ -186,6 +186,34 @@ NC_API nc_status nc_dac_forward_dev(nc_handle h, const float* audio_dev, int32_t
 NC_API nc_status nc_dac_decode_codes_dev(nc_handle h, const int64_t* codes_dev, int32_t batch,
                                          int32_t n_quantizers, int64_t frames, float* audio_dev);
 
+/* -- SNAC ------------------------------------------------------------------------- */
+/* SNAC.Preprocess length algebra (Models/SNAC.cs:70-80): audio is right-padded to a multiple of
+ * hop * lcm(vq_strides[0], attn_window or 1).  frames = padded_length / hop (finest code rate);
+ * code_lengths[i] = frames / vq_strides[i]; noise_lengths[i] = time steps after decoder block i
+ * (NoiseBlock.cs:38-45 draws randn[B,1,T_i]).  Arrays must hold NC_MAX_RATES entries. */
+NC_API nc_status nc_snac_query_shapes(nc_handle h, int64_t length, int64_t* padded_length, int64_t* frames,
+                                      int32_t* n_stages, int64_t* code_lengths, int32_t* n_noise,
+                                      int64_t* noise_lengths);
+/* replaces: SNAC.Encode(float[]) Models/SNAC.cs:129-150 (codes of the PADDED audio; the Tensor overload's
+ * unpadded-input bug, SNAC.cs:117-118, is not reproduced).  codes[i]: [B, frames / vq_strides[i]] int64
+ * (the reference's List<float[]> API casts them to float32, SNAC.cs:147). */
+NC_API nc_status nc_snac_encode(nc_handle h, const float* audio, int32_t batch, int64_t length,
+                                int64_t* const* codes);
+/* replaces: SNAC.Decode(List<...>) Models/SNAC.cs:157-192 = RVQ.FromCodes + Decoder; audio [B,1,frames*hop]
+ * (not trimmed).  noise[i]: [B, noise_lengths[i]] explicit N(0,1) tensors, or noise == NULL / noise[i] ==
+ * NULL to draw them on the device from `seed` (the reference draws randn per call and is not reproducible). */
+NC_API nc_status nc_snac_decode(nc_handle h, const int64_t* const* codes, int32_t batch, int64_t frames,
+                                const float* const* noise, uint64_t seed, float* audio);
+/* replaces: SNAC.forward Models/SNAC.cs:91-106 and ProcessAudio :255-282 (without the CPU resampler):
+ * audio_out [B,1,length] trimmed to the input length; codes nullable (array of n_stages pointers). */
+NC_API nc_status nc_snac_forward(nc_handle h, const float* audio, int32_t batch, int64_t length,
+                                 const float* const* noise, uint64_t seed, float* audio_out,
+                                 int64_t* const* codes);
+/* device-pointer variant (arrays of pointers live on the host, the buffers they point to on the device) */
+NC_API nc_status nc_snac_forward_dev(nc_handle h, const float* audio_dev, int32_t batch, int64_t length,
+                                     const float* const* noise_dev, uint64_t seed, float* audio_out_dev,
+                                     int64_t* const* codes_dev);
+
 /* The CUDA stream (cudaStream_t) every *_dev call of this handle enqueues on, so a caller
  * can bracket calls with its own events or order its own work against them. */
 NC_API nc_status nc_get_stream(nc_handle h, void** stream_out);

@@ -90,6 +90,11 @@ SIGNATURES = {
     "nc_dac_forward": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int32, _P, _P, _P, _I64]),
     "nc_dac_forward_dev": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int32, _P, _P, _P, _I64]),
     "nc_dac_decode_codes_dev": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int64, _P]),
+    "nc_snac_query_shapes": (C.c_int, [_P, C.c_int64, _I64, _I64, C.POINTER(C.c_int32), _I64, C.POINTER(C.c_int32), _I64]),
+    "nc_snac_encode": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _P]),
+    "nc_snac_decode": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _P, C.c_uint64, _P]),
+    "nc_snac_forward": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _P, C.c_uint64, _P, _P]),
+    "nc_snac_forward_dev": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _P, C.c_uint64, _P, _P]),
     "nc_get_stream": (C.c_int, [_P, C.POINTER(_P)]),
     "nc_describe": (C.c_int, [_P, C.c_char_p, C.c_size_t]),
     "nc_launch_count": (C.c_uint64, [_P]),

@@ -81,3 +81,55 @@ class DACConfig:
     def DAC16kHz(cls) -> "DACConfig":
         return cls(sample_rate=16000, num_codebooks=12, encoder_rates=[2, 4, 5, 8],
                    decoder_rates=[8, 5, 4, 2], version="0.0.5")
+
+
+@dataclass
+class SNACConfig:
+    """Config/SNAC/SNACConfig.cs:11-153 (same defaults = the 44 kHz preset; JSON names in comments)."""
+    device: DeviceConfiguration = field(default_factory=DeviceConfiguration)
+    sample_rate: int = 44100                                                 # "sampling_rate"
+    encoder_dim: int = 64
+    encoder_rates: List[int] = field(default_factory=lambda: [2, 3, 8, 8])
+    latent_dim: Optional[int] = None
+    decoder_dim: int = 1536
+    decoder_rates: List[int] = field(default_factory=lambda: [8, 8, 3, 2])
+    attn_window_size: Optional[int] = 32
+    codebook_size: int = 4096
+    codebook_dim: int = 8
+    vq_strides: List[int] = field(default_factory=lambda: [8, 4, 2, 1])
+    noise: bool = True
+    depthwise: bool = True
+
+    _JSON = {"sampling_rate": "sample_rate", "encoder_dim": "encoder_dim", "encoder_rates": "encoder_rates",
+             "latent_dim": "latent_dim", "decoder_dim": "decoder_dim", "decoder_rates": "decoder_rates",
+             "attn_window_size": "attn_window_size", "codebook_size": "codebook_size", "codebook_dim": "codebook_dim",
+             "vq_strides": "vq_strides", "noise": "noise", "depthwise": "depthwise"}
+
+    @property
+    def hop_length(self) -> int:
+        return int(math.prod(self.encoder_rates))
+
+    @property
+    def resolved_latent_dim(self) -> int:      # Models/SNAC.cs:37
+        return self.latent_dim if self.latent_dim else self.encoder_dim * (1 << len(self.encoder_rates))
+
+    @classmethod
+    def from_json(cls, text: str) -> "SNACConfig":
+        cfg = cls()
+        for k, v in json.loads(text).items():
+            if k in cls._JSON:
+                setattr(cfg, cls._JSON[k], v)
+        return cfg
+
+    @classmethod
+    def SNAC44kHz(cls) -> "SNACConfig":        # SNACConfig.cs:113
+        return cls()
+
+    @classmethod
+    def SNAC32kHz(cls) -> "SNACConfig":        # SNACConfig.cs:119-133
+        return cls(sample_rate=32000)
+
+    @classmethod
+    def SNAC24kHz(cls) -> "SNACConfig":        # SNACConfig.cs:139-153
+        return cls(sample_rate=24000, encoder_dim=48, encoder_rates=[2, 4, 8, 8], decoder_dim=1024,
+                   decoder_rates=[8, 8, 4, 2], attn_window_size=None, vq_strides=[4, 2, 1])

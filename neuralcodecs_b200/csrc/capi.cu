@@ -293,6 +293,136 @@ nc_status nc_dac_decode_codes_dev(nc_handle h, const int64_t* codes_dev, int32_t
   });
 }
 
+// ------------------------------------------------------------------------------------ SNAC
+static SnacEngine* snac_of(nc_handle h) {
+  if (!h || !h->engine) throw Error(NC_INVALID_ARGUMENT, "null handle");
+  if (h->kind != NC_CODEC_SNAC) throw Error(NC_INVALID_ARGUMENT, "handle is not a SNAC codec");
+  return static_cast<SnacEngine*>(h->engine);
+}
+
+nc_status nc_snac_query_shapes(nc_handle h, int64_t length, int64_t* padded_length, int64_t* frames, int32_t* n_stages,
+                               int64_t* code_lengths, int32_t* n_noise, int64_t* noise_lengths) {
+  return guarded([&] {
+    SnacEngine* e = snac_of(h);
+    if (length < 0) throw Error(NC_INVALID_ARGUMENT, "length must be non-negative");
+    const int64_t T = e->frames(length);
+    if (padded_length) *padded_length = e->padded_length(length);
+    if (frames) *frames = T;
+    if (n_stages) *n_stages = e->n_stages();
+    if (code_lengths)
+      for (int i = 0; i < e->n_stages(); ++i) code_lengths[i] = T / e->config().vq_strides[i];
+    const auto nl = e->noise_lengths(T);
+    if (n_noise) *n_noise = e->config().noise ? (int32_t)nl.size() : 0;
+    if (noise_lengths)
+      for (size_t i = 0; i < nl.size(); ++i) noise_lengths[i] = nl[i];
+  });
+}
+
+namespace {
+// host arrays of host pointers -> device staging, with copy-back for outputs
+struct SnacStaging {
+  std::vector<DevMem*> mem;
+  std::vector<int64_t*> codes_dev;
+  std::vector<const float*> noise_dev;
+  ~SnacStaging() {
+    for (auto* m : mem) delete m;
+  }
+};
+}  // namespace
+
+static void snac_forward_host(SnacEngine* e, const float* audio, int32_t batch, int64_t length, const float* const* noise,
+                              uint64_t seed, float* audio_out, int64_t* const* codes) {
+  if (!audio) throw Error(NC_INVALID_ARGUMENT, "audio is null");
+  if (batch <= 0 || length <= 0) throw Error(NC_INVALID_ARGUMENT, "batch and length must be positive");
+  BusyGuard g(e);
+  e->bind();
+  const int64_t T = e->frames(length);
+  const int ns = e->n_stages();
+  SnacStaging st;
+  DevMem d_audio((size_t)batch * length * 4), d_out(audio_out ? (size_t)batch * length * 4 : 0);
+  NC_CUDA(cudaMemcpy(d_audio.p, audio, (size_t)batch * length * 4, cudaMemcpyHostToDevice));
+  st.codes_dev.assign(ns, nullptr);
+  if (codes)
+    for (int i = 0; i < ns; ++i)
+      if (codes[i]) {
+        st.mem.push_back(new DevMem((size_t)batch * (T / e->config().vq_strides[i]) * 8));
+        st.codes_dev[i] = st.mem.back()->as<int64_t>();
+      }
+  const auto nl = e->noise_lengths(T);
+  st.noise_dev.assign(nl.size(), nullptr);
+  if (noise && audio_out)
+    for (size_t i = 0; i < nl.size(); ++i)
+      if (noise[i]) {
+        st.mem.push_back(new DevMem((size_t)batch * nl[i] * 4));
+        NC_CUDA(cudaMemcpy(st.mem.back()->p, noise[i], (size_t)batch * nl[i] * 4, cudaMemcpyHostToDevice));
+        st.noise_dev[i] = st.mem.back()->as<float>();
+      }
+  e->forward_dev(d_audio.as<float>(), batch, length, st.noise_dev.data(), seed, d_out.as<float>(),
+                 codes ? st.codes_dev.data() : nullptr);
+  if (audio_out) NC_CUDA(cudaMemcpy(audio_out, d_out.p, (size_t)batch * length * 4, cudaMemcpyDeviceToHost));
+  if (codes)
+    for (int i = 0; i < ns; ++i)
+      if (codes[i])
+        NC_CUDA(cudaMemcpy(codes[i], st.codes_dev[i], (size_t)batch * (T / e->config().vq_strides[i]) * 8, cudaMemcpyDeviceToHost));
+}
+
+nc_status nc_snac_encode(nc_handle h, const float* audio, int32_t batch, int64_t length, int64_t* const* codes) {
+  return guarded([&] {
+    SnacEngine* e = snac_of(h);
+    if (!codes) throw Error(NC_INVALID_ARGUMENT, "codes is null");
+    snac_forward_host(e, audio, batch, length, nullptr, 0, nullptr, codes);
+  });
+}
+
+nc_status nc_snac_forward(nc_handle h, const float* audio, int32_t batch, int64_t length, const float* const* noise,
+                          uint64_t seed, float* audio_out, int64_t* const* codes) {
+  return guarded([&] { snac_forward_host(snac_of(h), audio, batch, length, noise, seed, audio_out, codes); });
+}
+
+nc_status nc_snac_decode(nc_handle h, const int64_t* const* codes, int32_t batch, int64_t frames, const float* const* noise,
+                         uint64_t seed, float* audio) {
+  return guarded([&] {
+    SnacEngine* e = snac_of(h);
+    if (!codes || !audio) throw Error(NC_INVALID_ARGUMENT, "Codes list cannot be empty or contain null arrays");   // SNAC.cs:177-180
+    if (batch <= 0 || frames <= 0) throw Error(NC_INVALID_ARGUMENT, "batch and frames must be positive");
+    BusyGuard g(e);
+    e->bind();
+    const int ns = e->n_stages();
+    SnacStaging st;
+    std::vector<const int64_t*> cdev(ns, nullptr);
+    for (int i = 0; i < ns; ++i) {
+      if (!codes[i]) throw Error(NC_INVALID_ARGUMENT, "Codes list cannot be empty or contain null arrays");
+      const size_t bytes = (size_t)batch * (frames / e->config().vq_strides[i]) * 8;
+      st.mem.push_back(new DevMem(bytes));
+      NC_CUDA(cudaMemcpy(st.mem.back()->p, codes[i], bytes, cudaMemcpyHostToDevice));
+      cdev[i] = st.mem.back()->as<int64_t>();
+    }
+    const auto nl = e->noise_lengths(frames);
+    st.noise_dev.assign(nl.size(), nullptr);
+    if (noise)
+      for (size_t i = 0; i < nl.size(); ++i)
+        if (noise[i]) {
+          st.mem.push_back(new DevMem((size_t)batch * nl[i] * 4));
+          NC_CUDA(cudaMemcpy(st.mem.back()->p, noise[i], (size_t)batch * nl[i] * 4, cudaMemcpyHostToDevice));
+          st.noise_dev[i] = st.mem.back()->as<float>();
+        }
+    const int64_t L = e->decoded_length(frames);
+    DevMem d_a((size_t)batch * L * 4);
+    e->decode_dev(cdev.data(), batch, frames, st.noise_dev.data(), seed, d_a.as<float>());
+    NC_CUDA(cudaMemcpy(audio, d_a.p, (size_t)batch * L * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
+nc_status nc_snac_forward_dev(nc_handle h, const float* audio_dev, int32_t batch, int64_t length, const float* const* noise_dev,
+                              uint64_t seed, float* audio_out_dev, int64_t* const* codes_dev) {
+  return guarded([&] {
+    SnacEngine* e = snac_of(h);
+    if (!audio_dev) throw Error(NC_INVALID_ARGUMENT, "audio is null");
+    BusyGuard g(e);
+    e->forward_dev(audio_dev, batch, length, noise_dev, seed, audio_out_dev, codes_dev);
+  });
+}
+
 nc_status nc_get_stream(nc_handle h, void** stream_out) {
   return guarded([&] {
     if (!h || !h->engine) throw Error(NC_INVALID_ARGUMENT, "null handle");

@@ -15,6 +15,7 @@ conv_cin1_kernel(const float* __restrict__ in, long long in_stride, int in_len, 
   const int c4n = cout / 4;
   const int lanes_t = blockDim.x / c4n;              // time steps covered by one block iteration
   const int c4 = threadIdx.x % c4n, tl = threadIdx.x / c4n;
+  if (tl >= lanes_t) return;
   float wr[4][K], br[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -40,7 +41,7 @@ conv_cin1_kernel(const float* __restrict__ in, long long in_stride, int in_len, 
 
 void launch_conv_cin1(const float* in, long long in_stride, int in_len, float* out, int t_out, int cout,
                       const float* w, const float* bias, int k, int dil, int pad, int batch, const LaunchCtx& ctx) {
-  if (cout % 4 != 0 || 256 % (cout / 4) != 0) throw Error(NC_UNSUPPORTED, "conv_cin1: Cout/4 must divide 256");
+  if (cout % 4 != 0 || cout > 1024) throw Error(NC_UNSUPPORTED, "conv_cin1: Cout must be a multiple of 4, at most 1024");
   if (k != 7 && k != 3) throw Error(NC_UNSUPPORTED, "conv_cin1: kernel size must be 3 or 7");
   const long long total_t = (long long)batch * t_out;
   if (total_t == 0) return;

@@ -567,6 +567,10 @@ Engine* create_engine(nc_codec_kind kind, const void* cfg, size_t cfg_size, int 
       if (cfg_size != sizeof(nc_dac_config)) throw Error(NC_INVALID_ARGUMENT, "cfg_size != sizeof(nc_dac_config)");
       return new DacEngine(*static_cast<const nc_dac_config*>(cfg), device_index);
     }
+    case NC_CODEC_SNAC: {
+      if (cfg_size != sizeof(nc_snac_config)) throw Error(NC_INVALID_ARGUMENT, "cfg_size != sizeof(nc_snac_config)");
+      return new SnacEngine(*static_cast<const nc_snac_config*>(cfg), device_index);
+    }
     default:
       throw Error(NC_UNSUPPORTED, "codec kind not built into this library yet");
   }

@@ -151,3 +151,96 @@ class DacEngine : public Engine {
 Engine* create_engine(nc_codec_kind kind, const void* cfg, size_t cfg_size, int device_index);
 
 }  // namespace nc
+
+// ------------------------------------------------------------------------------------ SNAC
+#include "snac_kernels.h"
+namespace nc {
+
+struct SnacConfig {
+  int sample_rate = 24000, encoder_dim = 48, decoder_dim = 1024, latent_dim = 768;
+  std::vector<int> encoder_rates{2, 4, 8, 8}, decoder_rates{8, 8, 4, 2}, vq_strides{4, 2, 1};
+  int attn_window = 0, codebook_size = 4096, codebook_dim = 8;
+  bool noise = true, depthwise = true;
+  int hop() const {
+    int h = 1;
+    for (int r : encoder_rates) h *= r;
+    return h;
+  }
+};
+
+// Depthwise k=7 conv weights on the device ([7][C] + bias [C]).
+struct DwConv {
+  std::string name;
+  int C = 0, dil = 1;
+  float* w = nullptr;
+  float* b = nullptr;
+  ~DwConv();
+};
+
+class SnacEngine : public Engine {
+ public:
+  SnacEngine(const nc_snac_config& cfg, int device_index);
+  ~SnacEngine() override;
+  const char* codec_name() const override { return "SNAC"; }
+  void finalize_weights() override;
+  void set_option(const std::string& key, const std::string& value) override;
+  std::string describe() const override;
+  const SnacConfig& config() const { return cfg_; }
+
+  int64_t padded_length(int64_t L) const;             // Models/SNAC.cs:70-80
+  int64_t frames(int64_t L) const { return padded_length(L) / cfg_.hop(); }
+  int64_t decoded_length(int64_t T) const;
+  std::vector<int64_t> noise_lengths(int64_t T) const;  // per decoder block
+  int n_stages() const { return (int)cfg_.vq_strides.size(); }
+
+  // device pointers; codes[i]: [B][T / vq_strides[i]] int64; noise[i]: [B][noise_lengths(T)[i]] or null (seeded RNG)
+  void encode_dev(const float* audio, int B, int64_t L, int64_t* const* codes);
+  void decode_dev(const int64_t* const* codes, int B, int64_t T, const float* const* noise, uint64_t seed, float* audio_out);
+  // audio_out [B][L] (trimmed to the input length, Models/SNAC.cs:103); codes nullable
+  void forward_dev(const float* audio, int B, int64_t L, const float* const* noise, uint64_t seed, float* audio_out,
+                   int64_t* const* codes);
+
+ private:
+  struct ResUnit {
+    SnakeParams s1, s2;
+    DwConv dw;        // depthwise variant
+    ConvLayer c1;     // dense variant (depthwise = false)
+    ConvLayer c2;     // 1x1
+  };
+  struct EncBlock { ResUnit ru[3]; SnakeParams s; ConvLayer down; };
+  struct DecBlock { SnakeParams s; ConvLayer up; ConvLayer noise; ResUnit ru[3]; };
+  void require_ready() const;
+  std::vector<float> folded(const std::string& name, int d0, int d1, int k, std::vector<float>* bias, int bias_n);
+  void build_ru(ResUnit& ru, const std::string& p, int dim, int dil);
+  void build_dw(DwConv& d, const std::string& name, int C, int dil);
+  int run_ru(const ResUnit& ru, int cur, int B, int T, const SnakeParams* post);
+  void run_encoder(const float* audio, int in_len, int B, int Lp);   // -> z_in_
+  void run_rvq(int B, int T, int64_t* const* codes, int b0);         // z_in_ -> z_q_
+  void run_decoder(int B, int T, const float* const* noise, uint64_t seed, int b0, float* audio_out);  // z_q_ -> audio [B][T*hop]
+  int micro_batch(int B, int64_t Lp);
+  float* buf(int i) { return ws_[i].as<float>(); }
+  static int pad32(int c) { return (c + 31) / 32 * 32; }
+
+  SnacConfig cfg_;
+  Precision prec_ = PREC_BF16X3;
+  int dzp_ = 0;  // padded latent dim
+  float* d_conv_in_w_ = nullptr;
+  float* d_conv_in_b_ = nullptr;
+  int c0p_ = 0;
+  std::vector<std::unique_ptr<EncBlock>> enc_blocks_;
+  DwConv enc_out_dw_;
+  ConvLayer enc_out_dense_;
+  std::vector<SnacVqStage> stages_;
+  std::vector<float*> vq_alloc_;
+  DwConv dec_in_dw_;
+  ConvLayer dec_in_;
+  std::vector<std::unique_ptr<DecBlock>> dec_blocks_;
+  SnakeParams dec_snake_;
+  float* d_conv_out_w_ = nullptr;
+  float* d_conv_out_b_ = nullptr;
+  int conv_out_c_ = 0;
+  DeviceBuffer ws_[3], z_in_, z_q_, noise_buf_, audio_tmp_;
+  int64_t per_clip_elems_ = 0;
+};
+
+}  // namespace nc

@@ -160,3 +160,123 @@ def dia_codes(batch: int, frames: int, n_codebooks: int = 9, codebook_size: int 
     Models/Dia.cs:1039-1044)."""
     rng = np.random.default_rng(seed)
     return rng.integers(0, codebook_size, size=(batch, frames, n_codebooks), dtype=np.int64)
+
+
+# --------------------------------------------------------------------------- SNAC
+def _snac_cfg(cfg):
+    c = _Cfg()
+    for f in ("sample_rate", "encoder_dim", "encoder_rates", "decoder_dim", "decoder_rates", "attn_window_size",
+              "codebook_size", "codebook_dim", "vq_strides", "noise", "depthwise"):
+        setattr(c, f, getattr(cfg, f))
+    c.latent_dim = getattr(cfg, "resolved_latent_dim", None) or getattr(cfg, "latent_dim")
+    return c
+
+
+def snac_layer_specs(cfg) -> Dict[str, tuple]:
+    """Reference module-tree names (Modules/SNAC/*.cs registration order) -> layer kind and shape:
+    ("conv", cout, cin_per_group, k, has_bias) | ("convt", cin, cout, k) | ("alpha", c) | ("mha", dim)."""
+    c = _snac_cfg(cfg)
+    specs: Dict[str, tuple] = {}
+
+    def ru(p, dim, groups):
+        specs[p + ".block.0"] = ("alpha", dim)
+        specs[p + ".block.1"] = ("conv", dim, dim // groups, 7, True)
+        specs[p + ".block.2"] = ("alpha", dim)
+        specs[p + ".block.3"] = ("conv", dim, dim, 1, True)
+
+    d = c.encoder_dim
+    specs["encoder.block.0"] = ("conv", d, 1, 7, True)
+    idx = 1
+    for s in c.encoder_rates:
+        d *= 2
+        groups = d // 2 if c.depthwise else 1
+        p = f"encoder.block.{idx}"
+        for u in range(3):
+            ru(f"{p}.block.{u}", d // 2, groups)
+        specs[f"{p}.block.3"] = ("alpha", d // 2)
+        specs[f"{p}.block.4"] = ("conv", d, d // 2, 2 * s, True)
+        idx += 1
+    if c.attn_window_size:
+        specs[f"encoder.block.{idx}"] = ("mha", d)
+        idx += 1
+    specs[f"encoder.block.{idx}"] = ("conv", d, 1 if c.depthwise else d, 7, True)
+    for q in range(len(c.vq_strides)):
+        specs[f"quantizer.quantizers.{q}.in_proj"] = ("conv", c.codebook_dim, c.latent_dim, 1, True)
+        specs[f"quantizer.quantizers.{q}.out_proj"] = ("conv", c.latent_dim, c.codebook_dim, 1, True)
+    idx = 0
+    if c.depthwise:
+        specs["decoder.model.0"] = ("conv", c.latent_dim, 1, 7, True)
+        specs["decoder.model.1"] = ("conv", c.decoder_dim, c.latent_dim, 1, True)
+        idx = 2
+    else:
+        specs["decoder.model.0"] = ("conv", c.decoder_dim, c.latent_dim, 7, True)
+        idx = 1
+    if c.attn_window_size:
+        specs[f"decoder.model.{idx}"] = ("mha", c.decoder_dim)
+        idx += 1
+    out_dim = 1
+    for i, s in enumerate(c.decoder_rates):
+        in_dim, out_dim = c.decoder_dim // (1 << i), c.decoder_dim // (1 << (i + 1))
+        groups = out_dim if c.depthwise else 1
+        p = f"decoder.model.{idx}"
+        specs[f"{p}.block.0"] = ("alpha", in_dim)
+        specs[f"{p}.block.1"] = ("convt", in_dim, out_dim, 2 * s)
+        b = 2
+        if c.noise:
+            specs[f"{p}.block.2.linear"] = ("conv", out_dim, out_dim, 1, False)
+            b = 3
+        for u in range(3):
+            ru(f"{p}.block.{b + u}", out_dim, groups)
+        idx += 1
+    specs[f"decoder.model.{idx}"] = ("alpha", out_dim)
+    specs[f"decoder.model.{idx + 1}"] = ("conv", 1, out_dim, 7, True)
+    return specs
+
+
+def make_snac_weights(cfg) -> Dict[str, np.ndarray]:
+    """Seeded SNAC weights in the reference's key layout (weight-norm stored as original0 = g = ||W||,
+    original1 = v = W); codebooks N(0,1) (oracle/synth.py replaces them by data-fitted ones)."""
+    c = _snac_cfg(cfg)
+    sd: Dict[str, np.ndarray] = {}
+    for name, spec in snac_layer_specs(cfg).items():
+        kind = spec[0]
+        if kind == "alpha":
+            sd[name + ".alpha"] = snake_alpha(name + ".alpha", spec[1])
+        elif kind in ("conv", "convt"):
+            if kind == "conv":
+                _, cout, cin_g, k, has_bias = spec
+                w = conv_weight(name + ".weight", cout, cin_g, k)
+                fan_in, nb = cin_g * k, cout
+            else:
+                _, cin, cout, k = spec
+                w = convt_weight(name + ".weight", cin, cout, k)
+                fan_in, nb, has_bias = cout * k, cout, True
+            g = np.sqrt((w.astype(np.float64) ** 2).sum(axis=(1, 2), keepdims=True)).astype(np.float32)
+            sd[name + ".parametrizations.weight.original0"] = g
+            sd[name + ".parametrizations.weight.original1"] = w
+            if has_bias:
+                sd[name + ".bias"] = bias(name + ".bias", nb, fan_in)
+        elif kind == "mha":
+            dim = spec[1]
+            sd[name + ".norm.weight"] = (1.0 + 0.1 * _rng(name + ".norm.weight").standard_normal(dim)).astype(np.float32)
+            sd[name + ".norm.bias"] = (0.1 * _rng(name + ".norm.bias").standard_normal(dim)).astype(np.float32)
+            sd[name + ".to_qkv.weight"] = _uniform(name + ".to_qkv.weight", (3 * dim, dim), 1.0 / np.sqrt(dim))
+            sd[name + ".to_out.weight"] = _uniform(name + ".to_out.weight", (dim, dim), 1.0 / np.sqrt(dim))
+            # SinusoidalEmbedding.cs:46: inv_freq = 1 / 10000^(arange(0, dim_head, 2) / dim_head), dim_head = 64
+            sd[name + ".rel_pos.inv_freq"] = (1.0 / (10000.0 ** (np.arange(0, 64, 2, dtype=np.float32) / 64.0))).astype(np.float32)
+    K, D = c.codebook_size, c.codebook_dim
+    for q in range(len(c.vq_strides)):
+        nm = f"quantizer.quantizers.{q}.codebook.weight"
+        sd[nm] = _rng(nm).standard_normal((K, D)).astype(np.float32)
+    return sd
+
+
+def snac_noise(batch: int, lengths, first_clip: int = 0, seed: int = 777):
+    """Explicit decoder noise tensors N(0,1), one [batch, 1, T_i] per decoder block."""
+    out = []
+    for i, t in enumerate(lengths):
+        a = np.empty((batch, 1, t), np.float32)
+        for b in range(batch):
+            a[b, 0] = np.random.default_rng([seed, first_clip + b, i]).standard_normal(t).astype(np.float32)
+        out.append(a)
+    return out

@@ -57,3 +57,44 @@ def _fit_dac_codebooks(cfg, sd, clips: int, seconds: float) -> None:
             residual = residual - zq_i
 
 
+
+
+# --------------------------------------------------------------------------- SNAC
+from neuralcodecs_b200.synthetic import snac_layer_specs, snac_noise  # noqa: E402,F401
+
+
+def make_snac_weights(cfg, codebook_clips: int = 4, codebook_seconds: float = 4.0,
+                      codebooks: str = "data") -> Dict[str, np.ndarray]:
+    """Seeded SNAC weights in the reference's module-tree key layout; codebooks fitted on the oracle's
+    projected residuals (rows re-used with jitter when fewer than K frames are available)."""
+    sd = _generic.make_snac_weights(cfg)
+    if codebooks == "data":
+        _fit_snac_codebooks(cfg, sd, codebook_clips, codebook_seconds)
+    return sd
+
+
+def _fit_snac_codebooks(cfg, sd, clips: int, seconds: float) -> None:
+    import torch
+    from . import snac as snac_oracle
+
+    K = cfg.codebook_size
+    audio = torch.from_numpy(synth_audio(clips, int(round(seconds * cfg.sample_rate)), cfg.sample_rate)).unsqueeze(1)
+    model = snac_oracle.SNACOracle(cfg, {k: torch.from_numpy(v) for k, v in sd.items()})
+    with torch.inference_mode():
+        z = model.encoder(model.preprocess(audio))
+        residual = z.clone()
+        for q in range(len(cfg.vq_strides)):
+            ze = model.vq_in(q, residual)
+            rows = ze.transpose(1, 2).reshape(-1, cfg.codebook_dim)
+            nm = f"quantizer.quantizers.{q}.codebook.weight"
+            rng = _rng(nm + "/pick")
+            n = rows.shape[0]
+            pick = np.sort(rng.choice(n, size=K, replace=n < K))
+            cb = rows[torch.from_numpy(pick)].contiguous().clone()
+            if n < K:   # re-used rows: jitter so entries stay distinct
+                jit = rng.standard_normal(cb.shape).astype(np.float32) * 0.1 * float(rows.std())
+                cb = cb + torch.from_numpy(jit)
+            sd[nm] = cb.numpy().copy()
+            model.sd[nm] = cb
+            zqi, _, _ = model.vq_forward(q, residual)
+            residual = residual - zqi

@@ -56,3 +56,32 @@ def dac_full(cache_dir):
     import neuralcodecs_b200 as nc
     co, ce = odac.DACConfig.dac_44khz(), nc.DACConfig.DAC44kHz()
     return co, ce, _write_weights(co, os.path.join(cache_dir, "dac44_seed4321.safetensors"), "data", 10.0)
+
+
+def _write_snac(cfg, path, clips, seconds):
+    from oracle import synth
+    if not os.path.exists(path):
+        sd = synth.make_snac_weights(cfg, codebook_clips=clips, codebook_seconds=seconds)
+        synth.save_safetensors(sd, path + ".tmp")
+        os.replace(path + ".tmp", path)
+    return path
+
+
+@pytest.fixture(scope="session")
+def snac_tiny(cache_dir):
+    """Small depthwise SNAC (no attention), odd channel counts -> exercises channel padding."""
+    from oracle import snac as osnac
+    import neuralcodecs_b200 as nc
+    kw = dict(sample_rate=16000, encoder_dim=12, encoder_rates=[2, 4, 4], decoder_dim=96, decoder_rates=[4, 4, 2],
+              attn_window_size=None, codebook_size=128, vq_strides=[4, 2, 1])
+    co, ce = osnac.SNACConfig(**kw), nc.SNACConfig(**kw)
+    return co, ce, _write_snac(co, os.path.join(cache_dir, "snac_tiny.safetensors"), 2, 2.0)
+
+
+@pytest.fixture(scope="session")
+def snac_24k(cache_dir):
+    """SNAC 24 kHz preset (BASELINE config #2)."""
+    from oracle import snac as osnac
+    import neuralcodecs_b200 as nc
+    co, ce = osnac.SNACConfig.snac_24khz(), nc.SNACConfig.SNAC24kHz()
+    return co, ce, _write_snac(co, os.path.join(cache_dir, "snac24_seed4321.safetensors"), 4, 4.0)

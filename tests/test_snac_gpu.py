@@ -1,0 +1,137 @@
+"""SNAC engine (through the C ABI) against the CPU oracle.  Decoder noise is an explicit input on both sides."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+MAX_ABS, MIN_SNR_DB, NEAR_TIE = 1e-3, 60.0, 1e-6     # north_star tolerances
+
+
+def snr_db(ref, test):
+    ref, test = np.asarray(ref, np.float64), np.asarray(test, np.float64)
+    return 10 * np.log10((ref ** 2).sum() / max(((ref - test) ** 2).sum(), 1e-300))
+
+
+def _models(fix, options=None):
+    import neuralcodecs_b200 as nc
+    from oracle import snac as osnac
+    co, ce, path = fix
+    o = osnac.load_safetensors(path, co)
+    m = nc.SNAC(ce, options=options)
+    m.LoadWeights(path)
+    return o, m
+
+
+def _inputs(o, cfg, batch, length, first=5):
+    from oracle import synth
+    x = synth.synth_audio(batch, length, cfg.sample_rate, first_clip=first)
+    T = o.preprocess(torch.zeros(1, 1, length)).shape[-1] // cfg.hop_length
+    noise = synth.snac_noise(batch, o.noise_lengths(T), first_clip=first)
+    return x, noise
+
+
+def _flips_ok(o, ref, codes):
+    """Number of code flips that are NOT near-ties.  A flip is judged at the first stage where a frame group
+    differs (teacher-forced from the oracle's residual); groups already containing a flipped coarser stage are
+    cascades and skipped."""
+    bad = 0
+    residual = ref["z"].clone()
+    finest = ref["codes"][-1].shape[1] * o.cfg.vq_strides[-1]
+    tainted = torch.zeros(residual.shape[0], finest, dtype=torch.bool)       # per finest frame
+    with torch.inference_mode():
+        for q, (cr, ct) in enumerate(zip(ref["codes"], codes)):
+            ct = torch.from_numpy(ct)
+            s = o.cfg.vq_strides[q]
+            ze = o.vq_in(q, residual)
+            dist = o.vq_distances(q, ze).reshape(cr.shape[0], cr.shape[1], -1)
+            prev = tainted.reshape(cr.shape[0], -1, s).any(-1)
+            cb = o.sd[f"quantizer.quantizers.{q}.codebook.weight"]
+            for b, t in ((cr != ct) & ~prev).nonzero().tolist():
+                scale = float(ze[b, :, t].pow(2).sum() + cb[ct[b, t]].pow(2).sum())
+                margin = float(dist[b, t, ct[b, t]] - dist[b, t, cr[b, t]]) / max(scale, 1e-30)
+                bad += abs(margin) >= NEAR_TIE
+            tainted |= (cr != ct).repeat_interleave(s, dim=-1)
+            zqi, _, _ = o.vq_forward(q, residual)
+            residual = residual - zqi
+    return bad
+
+
+def test_tiny_fp32_exact_path(snac_tiny):
+    o, m = _models(snac_tiny, {"precision": "fp32"})
+    cfg = snac_tiny[0]
+    x, noise = _inputs(o, cfg, 2, 5000)
+    ref = o.forward(torch.from_numpy(x).unsqueeze(1), [torch.from_numpy(n) for n in noise])
+    audio, codes = m.forward(x[:, None, :], noise)
+    assert audio.shape == (2, 1, 5000)                                     # trimmed to the input length (SNAC.cs:103)
+    assert [c.shape for c in codes] == [tuple(c.shape) for c in ref["codes"]]
+    assert _flips_ok(o, ref, codes) == 0
+    if all(np.array_equal(cr.numpy(), ct) for cr, ct in zip(ref["codes"], codes)):
+        np.testing.assert_allclose(audio, ref["audio"].numpy(), atol=2e-5)
+    # Encode alone and Decode alone (untrimmed length = frames * hop)
+    enc = m.Encode(x[:, None, :])
+    for ca, cb in zip(codes, enc):
+        np.testing.assert_array_equal(ca, cb)
+    dec = m.Decode([c.numpy() for c in ref["codes"]], noise)
+    dref = o.decode(ref["codes"], [torch.from_numpy(n) for n in noise]).numpy()
+    assert dec.shape == dref.shape
+    np.testing.assert_allclose(dec, dref, atol=2e-5)
+    m.Dispose()
+
+
+def test_tiny_tensor_core_path(snac_tiny):
+    o, m = _models(snac_tiny)                                              # default bf16x3 on padded channels
+    assert any(v.startswith("tcgen05") for v in m.describe()["layers"].values())
+    cfg = snac_tiny[0]
+    x, noise = _inputs(o, cfg, 3, 7001)
+    ref = o.forward(torch.from_numpy(x).unsqueeze(1), [torch.from_numpy(n) for n in noise])
+    audio, codes = m.forward(x[:, None, :], noise)
+    assert _flips_ok(o, ref, codes) == 0
+    dec = m.Decode([c.numpy() for c in ref["codes"]], noise)
+    dref = o.decode(ref["codes"], [torch.from_numpy(n) for n in noise]).numpy()
+    assert np.abs(dec - dref).max() <= MAX_ABS and snr_db(dref, dec) >= MIN_SNR_DB
+    m.Dispose()
+
+
+def test_snac24k_preset_config2_clip(snac_24k):
+    """BASELINE config #2 shape: 24 kHz preset, 10 s clips -> codes 118/236/472 per clip."""
+    o, m = _models(snac_24k)
+    cfg = snac_24k[0]
+    x, noise = _inputs(o, cfg, 2, 240000)
+    ref = o.forward(torch.from_numpy(x).unsqueeze(1), [torch.from_numpy(n) for n in noise])
+    audio, codes = m.forward(x[:, None, :], noise)
+    assert [c.shape for c in codes] == [(2, 118), (2, 236), (2, 472)] and audio.shape == (2, 1, 240000)
+    assert _flips_ok(o, ref, codes) == 0
+    match = [float((cr.numpy() == ct).mean()) for cr, ct in zip(ref["codes"], codes)]
+    dec = m.Decode([c.numpy() for c in ref["codes"]], noise)
+    dref = o.decode(ref["codes"], [torch.from_numpy(n) for n in noise]).numpy()
+    print(f"snac24k: code match per stage {match}; decoder max-abs {np.abs(dec - dref).max():.2e} snr {snr_db(dref, dec):.1f} dB")
+    assert dec.shape == (2, 1, 241664)
+    assert np.abs(dec - dref).max() <= MAX_ABS and snr_db(dref, dec) >= MIN_SNR_DB
+    if all(v == 1.0 for v in match):
+        assert np.abs(audio - ref["audio"].numpy()).max() <= MAX_ABS
+    # seeded on-device noise: deterministic per seed, different across seeds, independent of batch neighbours
+    a1 = m.Decode([c.numpy() for c in ref["codes"]], None, seed=7)
+    a2 = m.Decode([c.numpy() for c in ref["codes"]], None, seed=7)
+    a3 = m.Decode([c.numpy() for c in ref["codes"]], None, seed=8)
+    np.testing.assert_array_equal(a1, a2)
+    assert np.abs(a1 - a3).max() > 0
+    m.Dispose()
+
+
+def test_errors_and_resampler(snac_tiny):
+    import neuralcodecs_b200 as nc
+    _, m = _models(snac_tiny, {"precision": "fp32"})
+    with pytest.raises(ValueError, match="Codes list cannot be empty"):
+        m.Decode([])
+    with pytest.raises(ValueError, match="Expected 3 codebooks"):
+        m.Decode([np.zeros((1, 4), np.int64)])
+    with pytest.raises(ValueError, match="Audio data cannot be empty"):
+        m.ProcessAudio(np.zeros(0, np.float32), 16000)
+    y = m.ProcessAudio(np.sin(np.arange(8000) / 20).astype(np.float32), 8000, seed=1)   # 8 kHz -> 16 kHz on the host
+    assert y.shape == (16000,)
+    r = nc.SNAC.ResampleAudio(np.array([0.0, 1.0, 2.0], np.float32), 1, 2)
+    np.testing.assert_allclose(r, [0.0, 0.5, 1.0, 1.5, 2.0, 2.0])
+    with pytest.raises(RuntimeError):
+        nc.SNAC(nc.SNACConfig.SNAC44kHz())                                # LocalMHA presets not built yet
+    m.Dispose()

@@ -214,6 +214,27 @@ NC_API nc_status nc_snac_forward_dev(nc_handle h, const float* audio_dev, int32_
                                      const float* const* noise_dev, uint64_t seed, float* audio_out_dev,
                                      int64_t* const* codes_dev);
 
+/* -- Encodec ---------------------------------------------------------------------- */
+/* 24 kHz mono causal preset.  frames = ceil-chain of the strided SConv1d layers (SConv1d.cs:245-250);
+ * n_q = max(1, floor(bandwidth*1000 / (log2(bins) * frame_rate))) (ResidualVectorQuantizer.cs:133-144);
+ * decoded_length = frames * hop.  bandwidth_kbps <= 0 selects every codebook in the file. */
+NC_API nc_status nc_encodec_query_shapes(nc_handle h, int64_t length, float bandwidth_kbps, int64_t* frames,
+                                         int32_t* n_q, int64_t* decoded_length);
+/* replaces: Encodec.Encode(float[]) / Encode(Tensor) Models/Encodec.cs:243-285 -> EncodeFrame :457-489 (one frame =
+ * the whole clip for the 24 kHz preset, Normalize = false -> scale = null).  codes [B, n_q, frames] int64. */
+NC_API nc_status nc_encodec_encode(nc_handle h, const float* audio, int32_t batch, int64_t length,
+                                   float bandwidth_kbps, int64_t* codes);
+/* replaces: Encodec.Decode(List<EncodedFrame>) Models/Encodec.cs:213-235 -> DecodeFrame :436-455.
+ * codes [B, n_q, frames] -> audio [B, 1, frames*hop] (not trimmed). */
+NC_API nc_status nc_encodec_decode(nc_handle h, const int64_t* codes, int32_t batch, int32_t n_q, int64_t frames,
+                                   float* audio);
+/* replaces: Encodec.forward Models/Encodec.cs:292-296: decode(encode(x)) sliced to the input length.
+ * audio_out [B,1,length]; codes nullable. */
+NC_API nc_status nc_encodec_forward(nc_handle h, const float* audio, int32_t batch, int64_t length,
+                                    float bandwidth_kbps, float* audio_out, int64_t* codes);
+NC_API nc_status nc_encodec_forward_dev(nc_handle h, const float* audio_dev, int32_t batch, int64_t length,
+                                        float bandwidth_kbps, float* audio_out_dev, int64_t* codes_dev);
+
 /* The CUDA stream (cudaStream_t) every *_dev call of this handle enqueues on, so a caller
  * can bracket calls with its own events or order its own work against them. */
 NC_API nc_status nc_get_stream(nc_handle h, void** stream_out);

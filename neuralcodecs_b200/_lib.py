@@ -95,6 +95,11 @@ SIGNATURES = {
     "nc_snac_decode": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _P, C.c_uint64, _P]),
     "nc_snac_forward": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _P, C.c_uint64, _P, _P]),
     "nc_snac_forward_dev": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _P, C.c_uint64, _P, _P]),
+    "nc_encodec_query_shapes": (C.c_int, [_P, C.c_int64, C.c_float, _I64, C.POINTER(C.c_int32), _I64]),
+    "nc_encodec_encode": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_float, _P]),
+    "nc_encodec_decode": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int64, _P]),
+    "nc_encodec_forward": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_float, _P, _P]),
+    "nc_encodec_forward_dev": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_float, _P, _P]),
     "nc_get_stream": (C.c_int, [_P, C.POINTER(_P)]),
     "nc_describe": (C.c_int, [_P, C.c_char_p, C.c_size_t]),
     "nc_launch_count": (C.c_uint64, [_P]),

@@ -133,3 +133,51 @@ class SNACConfig:
     def SNAC24kHz(cls) -> "SNACConfig":        # SNACConfig.cs:139-153
         return cls(sample_rate=24000, encoder_dim=48, encoder_rates=[2, 4, 8, 8], decoder_dim=1024,
                    decoder_rates=[8, 8, 4, 2], attn_window_size=None, vq_strides=[4, 2, 1])
+
+
+@dataclass
+class EncodecConfig:
+    """Config/Encodec/EncodecConfig.cs:6-153 (defaults = Encodec24Khz; JSON names follow the HF config)."""
+    device: DeviceConfiguration = field(default_factory=DeviceConfiguration)
+    sample_rate: int = 24000                    # "sampling_rate"
+    channels: int = 1                           # "audio_channels"
+    num_filters: int = 32
+    hidden_size: int = 128
+    upsampling_ratios: List[int] = field(default_factory=lambda: [8, 5, 4, 2])
+    num_residual_layers: int = 1
+    num_lstm_layers: int = 2
+    codebook_size: int = 1024
+    codebook_dim: int = 128
+    target_bandwidths: List[float] = field(default_factory=lambda: [1.5, 3.0, 6.0, 12.0, 24.0])
+    bandwidth: Optional[float] = 6.0
+    use_causal_conv: bool = True
+    normalize: bool = False
+    chunk_length_s: Optional[float] = None
+    norm_type: str = "weight_norm"
+
+    _JSON = {"sampling_rate": "sample_rate", "audio_channels": "channels", "num_filters": "num_filters",
+             "hidden_size": "hidden_size", "upsampling_ratios": "upsampling_ratios",
+             "num_residual_layers": "num_residual_layers", "num_lstm_layers": "num_lstm_layers",
+             "codebook_size": "codebook_size", "codebook_dim": "codebook_dim", "target_bandwidths": "target_bandwidths",
+             "use_causal_conv": "use_causal_conv", "normalize": "normalize", "chunk_length_s": "chunk_length_s",
+             "norm_type": "norm_type"}
+
+    @property
+    def hop_length(self) -> int:
+        return int(math.prod(self.upsampling_ratios))
+
+    @property
+    def num_quantizers(self) -> int:            # Models/Encodec.cs:70-71
+        return int(1000 * max(self.target_bandwidths) / (math.ceil(self.sample_rate / float(self.hop_length)) * 10))
+
+    @classmethod
+    def from_json(cls, text: str) -> "EncodecConfig":
+        cfg = cls()
+        for k, v in json.loads(text).items():
+            if k in cls._JSON:
+                setattr(cfg, cls._JSON[k], v)
+        return cfg
+
+    @classmethod
+    def Encodec24Khz(cls) -> "EncodecConfig":   # EncodecConfig.cs:9-34
+        return cls()

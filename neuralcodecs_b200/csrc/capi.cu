@@ -423,6 +423,81 @@ nc_status nc_snac_forward_dev(nc_handle h, const float* audio_dev, int32_t batch
   });
 }
 
+// ------------------------------------------------------------------------------------ Encodec
+static EncodecEngine* encodec_of(nc_handle h) {
+  if (!h || !h->engine) throw Error(NC_INVALID_ARGUMENT, "null handle");
+  if (h->kind != NC_CODEC_ENCODEC) throw Error(NC_INVALID_ARGUMENT, "handle is not an Encodec codec");
+  return static_cast<EncodecEngine*>(h->engine);
+}
+
+nc_status nc_encodec_query_shapes(nc_handle h, int64_t length, float bandwidth_kbps, int64_t* frames, int32_t* n_q,
+                                  int64_t* decoded_length) {
+  return guarded([&] {
+    EncodecEngine* e = encodec_of(h);
+    if (length < 0) throw Error(NC_INVALID_ARGUMENT, "length must be non-negative");
+    const int64_t T = e->frames(length);
+    if (frames) *frames = T;
+    if (n_q) *n_q = e->n_q_for_bandwidth(bandwidth_kbps);
+    if (decoded_length) *decoded_length = e->decoded_length(T);
+  });
+}
+
+static void encodec_forward_host(EncodecEngine* e, const float* audio, int32_t batch, int64_t length, float bw, float* audio_out,
+                                 int64_t* codes) {
+  if (!audio) throw Error(NC_INVALID_ARGUMENT, "audio is null");
+  if (batch <= 0 || length <= 0) throw Error(NC_INVALID_ARGUMENT, "batch and length must be positive");
+  BusyGuard g(e);
+  e->bind();
+  const int nq = e->n_q_for_bandwidth(bw);
+  const int64_t T = e->frames(length);
+  DevMem d_audio((size_t)batch * length * 4), d_out(audio_out ? (size_t)batch * length * 4 : 0),
+      d_codes(codes ? (size_t)batch * nq * T * 8 : 0);
+  NC_CUDA(cudaMemcpy(d_audio.p, audio, (size_t)batch * length * 4, cudaMemcpyHostToDevice));
+  e->forward_dev(d_audio.as<float>(), batch, length, nq, d_out.as<float>(), d_codes.as<int64_t>());
+  if (audio_out) NC_CUDA(cudaMemcpy(audio_out, d_out.p, (size_t)batch * length * 4, cudaMemcpyDeviceToHost));
+  if (codes) NC_CUDA(cudaMemcpy(codes, d_codes.p, (size_t)batch * nq * T * 8, cudaMemcpyDeviceToHost));
+}
+
+nc_status nc_encodec_encode(nc_handle h, const float* audio, int32_t batch, int64_t length, float bandwidth_kbps, int64_t* codes) {
+  return guarded([&] {
+    if (!codes) throw Error(NC_INVALID_ARGUMENT, "codes is null");
+    encodec_forward_host(encodec_of(h), audio, batch, length, bandwidth_kbps, nullptr, codes);
+  });
+}
+
+nc_status nc_encodec_forward(nc_handle h, const float* audio, int32_t batch, int64_t length, float bandwidth_kbps,
+                             float* audio_out, int64_t* codes) {
+  return guarded([&] {
+    if (!audio_out) throw Error(NC_INVALID_ARGUMENT, "audio_out is null");
+    encodec_forward_host(encodec_of(h), audio, batch, length, bandwidth_kbps, audio_out, codes);
+  });
+}
+
+nc_status nc_encodec_decode(nc_handle h, const int64_t* codes, int32_t batch, int32_t n_q, int64_t frames, float* audio) {
+  return guarded([&] {
+    EncodecEngine* e = encodec_of(h);
+    if (!codes || !audio) throw Error(NC_INVALID_ARGUMENT, "Invalid frame codes in Encodec Decode");   // Encodec.cs:438-442
+    if (batch <= 0 || frames <= 0 || n_q <= 0) throw Error(NC_INVALID_ARGUMENT, "No frames provided to decode");
+    BusyGuard g(e);
+    e->bind();
+    const int64_t L = e->decoded_length(frames);
+    DevMem d_c((size_t)batch * n_q * frames * 8), d_a((size_t)batch * L * 4);
+    NC_CUDA(cudaMemcpy(d_c.p, codes, (size_t)batch * n_q * frames * 8, cudaMemcpyHostToDevice));
+    e->decode_dev(d_c.as<int64_t>(), batch, n_q, frames, d_a.as<float>());
+    NC_CUDA(cudaMemcpy(audio, d_a.p, (size_t)batch * L * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
+nc_status nc_encodec_forward_dev(nc_handle h, const float* audio_dev, int32_t batch, int64_t length, float bandwidth_kbps,
+                                 float* audio_out_dev, int64_t* codes_dev) {
+  return guarded([&] {
+    EncodecEngine* e = encodec_of(h);
+    if (!audio_dev) throw Error(NC_INVALID_ARGUMENT, "audio is null");
+    BusyGuard g(e);
+    e->forward_dev(audio_dev, batch, length, e->n_q_for_bandwidth(bandwidth_kbps), audio_out_dev, codes_dev);
+  });
+}
+
 nc_status nc_get_stream(nc_handle h, void** stream_out) {
   return guarded([&] {
     if (!h || !h->engine) throw Error(NC_INVALID_ARGUMENT, "null handle");

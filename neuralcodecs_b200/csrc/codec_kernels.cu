@@ -11,7 +11,8 @@ namespace nc {
 template <int K>
 __global__ void __launch_bounds__(256)
 conv_cin1_kernel(const float* __restrict__ in, long long in_stride, int in_len, float* __restrict__ out, int t_out,
-                 int cout, const float* __restrict__ w, const float* __restrict__ bias, int dil, int pad, int batch) {
+                 int cout, const float* __restrict__ w, const float* __restrict__ bias, int dil, int pad, int batch,
+                 int reflect, long long out_clip_stride) {
   const int c4n = cout / 4;
   const int lanes_t = blockDim.x / c4n;              // time steps covered by one block iteration
   const int c4 = threadIdx.x % c4n, tl = threadIdx.x / c4n;
@@ -31,16 +32,22 @@ conv_cin1_kernel(const float* __restrict__ in, long long in_stride, int in_len, 
     float a0 = br[0], a1 = br[1], a2 = br[2], a3 = br[3];
 #pragma unroll
     for (int j = 0; j < K; ++j) {
-      const int ti = t + j * dil - pad;
+      int ti = t + j * dil - pad;
+      if (reflect) {   // F.pad(mode="reflect"): x[-i] = x[i], x[n-1+i] = x[n-1-i]
+        if (ti < 0) ti = -ti;
+        if (ti >= in_len) ti = 2 * (in_len - 1) - ti;
+      }
       const float v = (ti >= 0 && ti < in_len) ? __ldg(x + ti) : 0.f;
       a0 = fmaf(wr[0][j], v, a0); a1 = fmaf(wr[1][j], v, a1); a2 = fmaf(wr[2][j], v, a2); a3 = fmaf(wr[3][j], v, a3);
     }
-    reinterpret_cast<float4*>(out)[bt * c4n + c4] = make_float4(a0, a1, a2, a3);
+    reinterpret_cast<float4*>(out + (long long)b * out_clip_stride)[(long long)t * c4n + c4] = make_float4(a0, a1, a2, a3);
   }
 }
 
 void launch_conv_cin1(const float* in, long long in_stride, int in_len, float* out, int t_out, int cout,
-                      const float* w, const float* bias, int k, int dil, int pad, int batch, const LaunchCtx& ctx) {
+                      const float* w, const float* bias, int k, int dil, int pad, int batch, const LaunchCtx& ctx,
+                      int reflect, long long out_clip_stride) {
+  if (out_clip_stride == 0) out_clip_stride = (long long)t_out * cout;
   if (cout % 4 != 0 || cout > 1024) throw Error(NC_UNSUPPORTED, "conv_cin1: Cout must be a multiple of 4, at most 1024");
   if (k != 7 && k != 3) throw Error(NC_UNSUPPORTED, "conv_cin1: kernel size must be 3 or 7");
   const long long total_t = (long long)batch * t_out;
@@ -51,9 +58,9 @@ void launch_conv_cin1(const float* in, long long in_stride, int in_len, float* o
   if (blocks > cap) blocks = cap;
   const int ev = ctx.begin();
   if (k == 7)
-    conv_cin1_kernel<7><<<(unsigned)blocks, 256, 0, ctx.stream>>>(in, in_stride, in_len, out, t_out, cout, w, bias, dil, pad, batch);
+    conv_cin1_kernel<7><<<(unsigned)blocks, 256, 0, ctx.stream>>>(in, in_stride, in_len, out, t_out, cout, w, bias, dil, pad, batch, reflect, out_clip_stride);
   else
-    conv_cin1_kernel<3><<<(unsigned)blocks, 256, 0, ctx.stream>>>(in, in_stride, in_len, out, t_out, cout, w, bias, dil, pad, batch);
+    conv_cin1_kernel<3><<<(unsigned)blocks, 256, 0, ctx.stream>>>(in, in_stride, in_len, out, t_out, cout, w, bias, dil, pad, batch, reflect, out_clip_stride);
   check_launch((int)cudaGetLastError(), "conv_cin1");
   ctx.end(ev, "conv_cin1", 2.0 * k * cout * (double)t_out * batch, 4.0 * batch * ((double)in_len + (double)t_out * cout));
 }
@@ -67,21 +74,25 @@ constexpr int kCoutTile = 256;
 template <int K>
 __global__ void __launch_bounds__(256)
 conv_cout1_kernel(const float* __restrict__ in, float* __restrict__ out, int T, int C, const float* __restrict__ w /*[K][C]*/,
-                  const float* __restrict__ bias, int pad, int act, int tiles_per_clip) {
+                  const float* __restrict__ bias, int pad, int act, int tiles_per_clip, int reflect, long long in_clip_stride) {
   extern __shared__ float sm[];
   float* sw = sm;                    // [K][C]
   float* sp = sm + K * C;            // [kCoutTile + K - 1][K]
   for (int i = threadIdx.x; i < K * C; i += blockDim.x) sw[i] = w[i];
   const int b = blockIdx.x / tiles_per_clip;
   const int t0 = (blockIdx.x - b * tiles_per_clip) * kCoutTile;
-  const float* x = in + (long long)b * T * C;
+  const float* x = in + (long long)b * in_clip_stride;
   __syncthreads();
   const int grp = threadIdx.x >> 3, l8 = threadIdx.x & 7;   // 32 row groups of 8 lanes
   const int rows = kCoutTile + K - 1;
   const int c4_per_lane = C / 32;                            // float4 per lane
   for (int r0 = 0; r0 < rows; r0 += 32) {   // uniform trip count: the shuffles below need the whole warp
     const int r = r0 + grp;
-    const int tr = t0 + r - pad;
+    int tr = t0 + r - pad;
+    if (reflect) {
+      if (tr < 0) tr = -tr;
+      if (tr >= T) tr = 2 * (T - 1) - tr;
+    }
     float acc[K];
 #pragma unroll
     for (int j = 0; j < K; ++j) acc[j] = 0.f;
@@ -121,13 +132,14 @@ conv_cout1_kernel(const float* __restrict__ in, float* __restrict__ out, int T, 
 }
 
 void launch_conv_cout1(const float* in, float* out, int T, int C, const float* w_kc, const float* bias, int k, int pad,
-                       int act, int batch, const LaunchCtx& ctx) {
+                       int act, int batch, const LaunchCtx& ctx, int reflect, long long in_clip_stride) {
+  if (in_clip_stride == 0) in_clip_stride = (long long)T * C;
   if (C % 32 != 0 || k != 7) throw Error(NC_UNSUPPORTED, "conv_cout1: needs C % 32 == 0 and kernel size 7");
   if ((long long)batch * T == 0) return;
   const int tiles = (T + kCoutTile - 1) / kCoutTile;
   const size_t smem = (size_t)(7 * C + (kCoutTile + 6) * 7) * sizeof(float);
   const int ev = ctx.begin();
-  conv_cout1_kernel<7><<<(unsigned)(batch * tiles), 256, smem, ctx.stream>>>(in, out, T, C, w_kc, bias, pad, act, tiles);
+  conv_cout1_kernel<7><<<(unsigned)(batch * tiles), 256, smem, ctx.stream>>>(in, out, T, C, w_kc, bias, pad, act, tiles, reflect, in_clip_stride);
   check_launch((int)cudaGetLastError(), "conv_cout1");
   ctx.end(ev, "conv_cout1", 2.0 * k * C * (double)T * batch, 4.0 * batch * ((double)T * C + T));
 }

@@ -12,12 +12,13 @@ namespace nc {
 // DAC.Preprocess' right zero padding, Models/DAC.cs:151-153); out: [B][t_out][cout] channels-last.
 void launch_conv_cin1(const float* in, long long in_stride, int in_len, float* out, int t_out, int cout,
                       const float* w /*[cout][k]*/, const float* bias, int k, int dil, int pad, int batch,
-                      const LaunchCtx& ctx);
+                      const LaunchCtx& ctx, int reflect = 0 /*1: reflect padding instead of zeros*/,
+                      long long out_clip_stride = 0 /*floats between output clips; 0 = t_out*cout*/);
 
 // out[b, t] = act(bias + sum_j sum_c w[j][c] * in[b, t + j - pad, c])   (Cout = 1, stride 1, dilation 1; act 1 = tanh)
 // in: [B][T][C] channels-last (already activated); out: [B][T]; w_kc: [k][C].
 void launch_conv_cout1(const float* in, float* out, int T, int C, const float* w_kc, const float* bias, int k, int pad,
-                       int act, int batch, const LaunchCtx& ctx);
+                       int act, int batch, const LaunchCtx& ctx, int reflect = 0, long long in_clip_stride = 0);
 
 // [B][C][T] <-> [B][T][C]
 void launch_transpose_ct_to_tc(const float* in, float* out, int batch, int C, int T, const LaunchCtx& ctx);

@@ -341,12 +341,14 @@ void ConvLayer::run(const ConvRunArgs& a, const LaunchCtx& ctx) const {
   const double fl = flops(a.batch, a.t_in);
   const double bytes = 4.0 * a.batch * ((double)a_valid + (double)d_valid * (a.residual ? 2 : 1));
   const int ev = ctx.begin();
-  const bool whole_rows = a_valid == (long long)a_rows * k_view_ && (a_valid % 4) == 0 &&
+  const long long a_stride = a.in_clip_stride ? a.in_clip_stride : a_valid;
+  const long long d_stride = a.out_clip_stride ? a.out_clip_stride : d_valid;
+  const bool whole_rows = a_valid == (long long)a_rows * k_view_ && (a_stride % 4) == 0 &&
                           (reinterpret_cast<uintptr_t>(a.in) & 15) == 0;
   if (mode_ != PREC_FP32 && (whole_rows || !d_w_plain_)) {
     ConvGemmParams p{};
-    p.A = a.in; p.a_clip_stride = a_valid; p.a_rows = a_rows; p.a_pitch = k_view_; p.a_valid = a_valid;
-    p.D = a.out; p.R = a.residual; p.d_clip_stride = d_valid; p.m_rows = m_rows; p.n_total = n_total;
+    p.A = a.in; p.a_clip_stride = a_stride; p.a_rows = a_rows; p.a_pitch = k_view_; p.a_valid = a_valid;
+    p.D = a.out; p.R = a.residual; p.d_clip_stride = d_stride; p.m_rows = m_rows; p.n_total = n_total;
     p.n_valid = n_logical_; p.d_valid = d_valid;
     p.bias = d_bias_; p.bias_period = s.cout; p.noise = a.noise;
     p.alpha = a.alpha; p.inv_alpha = a.inv_alpha; p.alpha_period = s.cin; p.prologue = a.prologue; p.act = a.act;
@@ -365,8 +367,8 @@ void ConvLayer::run(const ConvRunArgs& a, const LaunchCtx& ctx) const {
     ctx.end(ev, std::string("conv_umma_") + precision_name(mode_), fl, bytes, name_);
   } else {
     ConvSimtParams p{};
-    p.A = a.in; p.a_clip_stride = a_valid; p.a_rows = a_rows; p.a_pitch = k_view_; p.a_valid = a_valid;
-    p.D = a.out; p.R = a.residual; p.d_clip_stride = d_valid; p.m_rows = m_rows; p.n_total = n_total;
+    p.A = a.in; p.a_clip_stride = a_stride; p.a_rows = a_rows; p.a_pitch = k_view_; p.a_valid = a_valid;
+    p.D = a.out; p.R = a.residual; p.d_clip_stride = d_stride; p.m_rows = m_rows; p.n_total = n_total;
     p.n_valid = n_logical_; p.d_valid = d_valid;
     p.bias = d_bias_; p.bias_period = s.cout; p.noise = a.noise;
     p.alpha = a.alpha; p.alpha_period = s.cin; p.prologue = a.prologue; p.act = a.act;

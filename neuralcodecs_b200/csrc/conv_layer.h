@@ -37,8 +37,10 @@ struct ConvRunArgs {
   int post = PRO_NONE;
   const float* post_alpha = nullptr;      // device [Cout]
   const float* post_inv_alpha = nullptr;  // device [Cout]
-  // row pitch override for the output (floats per output time step); 0 = Cout
-  int out_valid_cols = 0;            // logical Cout written (0 = all)
+  // floats between consecutive clips of the input / output (+ residual) tensors; 0 = dense (T*C).
+  // Lets callers keep margin rows around each clip (Encodec's reflect padding is materialised there).
+  long long in_clip_stride = 0;
+  long long out_clip_stride = 0;
 };
 
 class ConvLayer {

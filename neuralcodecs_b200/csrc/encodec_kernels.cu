@@ -1,0 +1,329 @@
+// Encodec-specific kernels: reflect-padding fix-up of margin rows, residual VQ with 128-d Euclidean
+// codebooks (fp32 register-tiled distance GEMM + running argmin), codes -> embedding sum, and the SEANet
+// LSTM as a persistent cooperative kernel.
+// Reference: Modules/Encodec/SConv1d.cs:144-173,252-274 (Pad1d), EuclideanCodebook.cs:155-182 (Quantize),
+// ResidualVectorQuantizer.cs:107-157, SLSTM.cs:40-57.
+#include "encodec_kernels.h"
+
+#include <cfloat>
+#include <cooperative_groups.h>
+
+namespace nc {
+
+// ------------------------------------------------------------------------------ reflect padding into margins
+// x points at row 0 of clip 0; rows -left..-1 and T..T+right-1 of every clip receive x[-j] = x[j],
+// x[T-1+j] = x[T-1-j] (F.pad mode="reflect").
+__global__ void reflect_pad_kernel(float* __restrict__ x, int T, int C, long long clip_stride, int left, int right, int batch) {
+  const int c4n = C / 4;
+  const int per_clip = (left + right) * c4n;
+  const long long total = (long long)batch * per_clip;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per_clip);
+    const int rem = (int)(i - (long long)b * per_clip);
+    const int j = rem / c4n, c4 = rem - j * c4n;
+    int dst, src;
+    if (j < left) { dst = -(j + 1); src = j + 1; } else { const int k = j - left + 1; dst = T - 1 + k; src = T - 1 - k; }
+    float4* base = reinterpret_cast<float4*>(x + (long long)b * clip_stride);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (src >= 0 && src < T) v = base[(long long)src * c4n + c4];
+    base[(long long)dst * c4n + c4] = v;
+  }
+}
+
+void launch_reflect_pad(float* x, int T, int C, long long clip_stride, int left, int right, int batch, const LaunchCtx& ctx) {
+  if (left + right == 0 || batch == 0) return;
+  if (C % 4 != 0) throw Error(NC_UNSUPPORTED, "reflect_pad: channel count must be a multiple of 4");
+  if (T <= left || T <= right) throw Error(NC_UNSUPPORTED, "reflect_pad: clip shorter than its padding");
+  const long long total = (long long)batch * (left + right) * (C / 4);
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 1024);
+  const int ev = ctx.begin();
+  reflect_pad_kernel<<<blocks, 256, 0, ctx.stream>>>(x, T, C, clip_stride, left, right, batch);
+  check_launch((int)cudaGetLastError(), "reflect_pad");
+  ctx.end(ev, "reflect_pad", 0, 32.0 * total);
+}
+
+// ------------------------------------------------------------------------------ VQ stage (D = 128)
+// One block = 64 frames.  dist[f][k] = (|x_f|^2 + |e_k|^2) + (-2 * x_f.e_k), dot accumulated sequentially over d
+// in fp32 (4x4 register tile per thread, x and e tiles staged in shared memory); running argmin with lowest-index
+// tie-break; then residual[f] -= embed[argmin].
+constexpr int kVqFrames = 64, kVqEntries = 64, kVqD = 128;
+
+__global__ void __launch_bounds__(256)
+encodec_vq_stage_kernel(float* __restrict__ residual, long long frames, const float* __restrict__ embed,
+                        const float* __restrict__ embed_sq, int K, int64_t* __restrict__ codes, int T, int nq, int stage) {
+  extern __shared__ __align__(16) float vq_smem[];
+  float (*xs)[kVqFrames + 4] = reinterpret_cast<float (*)[kVqFrames + 4]>(vq_smem);                               // [d][frame]
+  float (*es)[kVqEntries + 4] = reinterpret_cast<float (*)[kVqEntries + 4]>(vq_smem + kVqD * (kVqFrames + 4));    // [d][entry]
+  __shared__ float best_d[kVqFrames][16];
+  __shared__ int best_k[kVqFrames][16];
+  __shared__ int win[kVqFrames];
+  const long long f0 = (long long)blockIdx.x * kVqFrames;
+  const int tid = threadIdx.x;
+  const int tf = tid & 15, te = tid >> 4;      // thread tile: frames 4*tf..+3, entries 4*te..+3
+  for (int i = tid; i < kVqFrames * (kVqD / 4); i += 256) {
+    const int fr = i / (kVqD / 4), d4 = i % (kVqD / 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (f0 + fr < frames) v = *reinterpret_cast<const float4*>(residual + (f0 + fr) * kVqD + 4 * d4);
+    xs[4 * d4 + 0][fr] = v.x; xs[4 * d4 + 1][fr] = v.y; xs[4 * d4 + 2][fr] = v.z; xs[4 * d4 + 3][fr] = v.w;
+  }
+  __syncthreads();
+  // |x|^2 per frame: pow(2).sum(1) -- sequential over d
+  float x2[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float s = 0.f;
+    for (int d = 0; d < kVqD; ++d) { const float v = xs[d][4 * tf + i]; s += v * v; }
+    x2[i] = s;
+  }
+  float bd[4];
+  int bk[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { bd[i] = FLT_MAX; bk[i] = 0; }
+  for (int k0 = 0; k0 < K; k0 += kVqEntries) {
+    __syncthreads();
+    for (int i = tid; i < kVqEntries * (kVqD / 4); i += 256) {
+      const int en = i / (kVqD / 4), d4 = i % (kVqD / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + en < K) v = __ldg(reinterpret_cast<const float4*>(embed + (size_t)(k0 + en) * kVqD) + d4);
+      es[4 * d4 + 0][en] = v.x; es[4 * d4 + 1][en] = v.y; es[4 * d4 + 2][en] = v.z; es[4 * d4 + 3][en] = v.w;
+    }
+    __syncthreads();
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < kVqD; ++d) {
+      const float4 xv = *reinterpret_cast<const float4*>(&xs[d][4 * tf]);
+      const float4 ev = *reinterpret_cast<const float4*>(&es[d][4 * te]);
+      const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, ea[4] = {ev.x, ev.y, ev.z, ev.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xa[i], ea[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + 4 * te + j;
+      if (k >= K) continue;
+      const float e2 = __ldg(embed_sq + k);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float dist = (x2[i] + e2) + (-2.0f * acc[i][j]);
+        if (dist < bd[i]) { bd[i] = dist; bk[i] = k; }   // k ascending within a thread: first minimum wins
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { best_d[4 * tf + i][te] = bd[i]; best_k[4 * tf + i][te] = bk[i]; }
+  __syncthreads();
+  if (tid < kVqFrames) {
+    float d = best_d[tid][0];
+    int k = best_k[tid][0];
+    for (int j = 1; j < 16; ++j) {
+      const float dj = best_d[tid][j];
+      const int kj = best_k[tid][j];
+      if (dj < d || (dj == d && kj < k)) { d = dj; k = kj; }
+    }
+    win[tid] = k;
+    const long long f = f0 + tid;
+    if (f < frames && codes) codes[((f / T) * nq + stage) * T + (f % T)] = k;
+  }
+  __syncthreads();
+  // residual -= quantized
+  for (int i = tid; i < kVqFrames * (kVqD / 4); i += 256) {
+    const int fr = i / (kVqD / 4), d4 = i % (kVqD / 4);
+    if (f0 + fr >= frames) continue;
+    const float4 q = __ldg(reinterpret_cast<const float4*>(embed + (size_t)win[fr] * kVqD) + d4);
+    float4* r = reinterpret_cast<float4*>(residual + (f0 + fr) * kVqD) + d4;
+    float4 v = *r;
+    v.x -= q.x; v.y -= q.y; v.z -= q.z; v.w -= q.w;
+    *r = v;
+  }
+}
+
+void launch_encodec_vq_stage(float* residual, long long frames, const float* embed, const float* embed_sq, int K, int D,
+                             int64_t* codes, int T, int nq, int stage, const LaunchCtx& ctx) {
+  if (D != kVqD) throw Error(NC_UNSUPPORTED, "encodec vq: codebook dimension must be 128");
+  if (frames == 0) return;
+  const unsigned blocks = (unsigned)((frames + kVqFrames - 1) / kVqFrames);
+  const size_t smem = (size_t)kVqD * (kVqFrames + 4 + kVqEntries + 4) * sizeof(float);
+  cudaFuncSetAttribute(encodec_vq_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int ev = ctx.begin();
+  encodec_vq_stage_kernel<<<blocks, 256, smem, ctx.stream>>>(residual, frames, embed, embed_sq, K, codes, T, nq, stage);
+  check_launch((int)cudaGetLastError(), "encodec_vq_stage");
+  ctx.end(ev, "encodec_vq_stage", 2.0 * frames * K * D, (double)frames * D * 8.0);
+}
+
+// out[b, t, :] = sum_i embed_i[codes[b, i, t]]   (ResidualVectorQuantizer.Decode); out rows may be strided per clip
+__global__ void encodec_decode_codes_kernel(const int64_t* __restrict__ codes, const float* const* __restrict__ embeds,
+                                            float* __restrict__ out, long long out_clip_stride, int batch, int T, int nq,
+                                            int K) {
+  const long long total = (long long)batch * T * (kVqD / 4);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int d4 = (int)(i % (kVqD / 4));
+    const long long f = i / (kVqD / 4);
+    const int b = (int)(f / T), t = (int)(f % T);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < nq; ++s) {
+      long long c = codes[((long long)b * nq + s) * T + t];
+      c = c < 0 ? 0 : (c >= K ? K - 1 : c);
+      const float4 e = __ldg(reinterpret_cast<const float4*>(embeds[s] + (size_t)c * kVqD) + d4);
+      a.x += e.x; a.y += e.y; a.z += e.z; a.w += e.w;
+    }
+    reinterpret_cast<float4*>(out + (long long)b * out_clip_stride + (long long)t * kVqD)[d4] = a;
+  }
+}
+
+void launch_encodec_decode_codes(const int64_t* codes, const float* const* embeds_dev, float* out, long long out_clip_stride,
+                                 int batch, int T, int nq, int K, int D, const LaunchCtx& ctx) {
+  if (D != kVqD) throw Error(NC_UNSUPPORTED, "encodec vq: codebook dimension must be 128");
+  const long long total = (long long)batch * T * (kVqD / 4);
+  if (total == 0) return;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)ctx.num_sms * 16);
+  const int ev = ctx.begin();
+  encodec_decode_codes_kernel<<<blocks, 256, 0, ctx.stream>>>(codes, embeds_dev, out, out_clip_stride, batch, T, nq, K);
+  check_launch((int)cudaGetLastError(), "encodec_decode_codes");
+  ctx.end(ev, "encodec_decode_codes", 0, (double)batch * T * (D * 4.0 + nq * 8.0));
+}
+
+// ------------------------------------------------------------------------------ LSTM layer (persistent)
+// One launch = one layer over all T steps.  Grid: (H/16 unit slices) x (batch slices of 16); all CTAs are
+// co-resident (cooperative launch).  A CTA owns the 64 gate rows (i,f,g,o x 16 units) of W_hh for its units, held
+// in REGISTERS (thread = 4 gate rows x 32-wide K slice), and the cell state of its 16 units x 16 clips.
+// Per step: stage h_{t-1} of the 16 clips in shared memory, partial dots per K slice, shuffle-reduce over the 16
+// K slices, add the hoisted input projection (W_ih x_t + b_ih + b_hh, computed by one tensor-core GEMM),
+// gate math in fp32, write h_t; CTAs of the same batch slice meet at a global-memory barrier.
+constexpr int kLU = 16;   // units per CTA
+constexpr int kLB = 16;   // clips per CTA
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__global__ void __launch_bounds__(256, 1)
+lstm_layer_kernel(const float* __restrict__ xproj, long long xproj_clip_stride,   // [B][T][4H] (+clip stride)
+                  const float* __restrict__ w_hh,                                  // [4H][H]
+                  float* __restrict__ hbuf,                                        // [2][Bpad][H] ping-pong, zero-initialised
+                  float* __restrict__ out, long long out_clip_stride,              // [B][T][H]
+                  const float* __restrict__ skip, long long skip_clip_stride,      // nullable: out = h + skip (SLSTM skip)
+                  int post_elu, unsigned int* __restrict__ barriers,               // [batch slices], zero-initialised
+                  int batch, int T, int H) {
+  __shared__ __align__(16) float hs[kLB][16 * 36];   // [clip][K slice][32 + 4 pad]: conflict-free 128-bit reads
+  __shared__ float gates[4 * kLU][kLB + 1];
+  const int tid = threadIdx.x;
+  const int ks = tid & 15;          // K slice: columns 32*ks .. +31
+  const int rg = tid >> 4;          // row group: gate rows 4*rg .. +3 of this CTA's 64
+  const int u0 = blockIdx.x * kLU, b0 = blockIdx.y * kLB;
+  const int n_unit_ctas = gridDim.x;
+  const int bpad = gridDim.y * kLB;
+  // local gate row r (0..63): gate = r / 16, unit = r % 16  -> global row gate*H + u0 + unit
+  float w[4][32];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = 4 * rg + i;
+    const float* wr = w_hh + ((size_t)(r / kLU) * H + u0 + (r % kLU)) * H + 32 * ks;
+#pragma unroll
+    for (int k4 = 0; k4 < 8; ++k4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(wr) + k4);
+      w[i][4 * k4] = v.x; w[i][4 * k4 + 1] = v.y; w[i][4 * k4 + 2] = v.z; w[i][4 * k4 + 3] = v.w;
+    }
+  }
+  // cell state: thread tid owns (unit = tid / 16, clip = tid % 16)
+  const int my_u = tid >> 4, my_b = tid & 15;
+  float c_state = 0.f;
+  const bool clip_ok = b0 + my_b < batch;
+  for (int t = 0; t < T; ++t) {
+    const float* hprev = hbuf + (size_t)((t + 1) & 1) * bpad * H;   // written at step t-1 (zeros at t = 0)
+    float* hnext = hbuf + (size_t)(t & 1) * bpad * H;
+    for (int i = tid; i < kLB * (H / 4); i += 256) {
+      const int bb = i / (H / 4), k4 = i % (H / 4);
+      // written by other CTAs during this launch: bypass L1 (ld.global.cg)
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(hprev + (size_t)(b0 + bb) * H) + k4);
+      *reinterpret_cast<float4*>(&hs[bb][(k4 >> 3) * 36 + 4 * (k4 & 7)]) = v;
+    }
+    __syncthreads();
+    for (int bg = 0; bg < 4; ++bg) {
+      float acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll
+      for (int k4 = 0; k4 < 8; ++k4) {
+        float4 hv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hv[j] = *reinterpret_cast<const float4*>(&hs[4 * bg + j][36 * ks + 4 * k4]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc[i][j] = fmaf(w[i][4 * k4 + 0], hv[j].x, acc[i][j]);
+            acc[i][j] = fmaf(w[i][4 * k4 + 1], hv[j].y, acc[i][j]);
+            acc[i][j] = fmaf(w[i][4 * k4 + 2], hv[j].z, acc[i][j]);
+            acc[i][j] = fmaf(w[i][4 * k4 + 3], hv[j].w, acc[i][j]);
+          }
+      }
+      // reduce over the 16 K slices (lanes ks = tid & 15 of each half warp)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float v = acc[i][j];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          if (ks == 0) gates[4 * rg + i][4 * bg + j] = v;
+        }
+    }
+    __syncthreads();
+    if (clip_ok) {
+      const int b = b0 + my_b, u = u0 + my_u;
+      const float* xp = xproj + (long long)b * xproj_clip_stride + (long long)t * 4 * H;
+      const float gi = gates[0 * kLU + my_u][my_b] + xp[0 * H + u];
+      const float gf = gates[1 * kLU + my_u][my_b] + xp[1 * H + u];
+      const float gg = gates[2 * kLU + my_u][my_b] + xp[2 * H + u];
+      const float go = gates[3 * kLU + my_u][my_b] + xp[3 * H + u];
+      c_state = sigmoid_f(gf) * c_state + sigmoid_f(gi) * tanhf(gg);
+      const float h = sigmoid_f(go) * tanhf(c_state);
+      __stcg(hnext + (size_t)b * H + u, h);
+      float y = h;
+      if (skip) y += skip[(long long)b * skip_clip_stride + (long long)t * H + u];
+      if (post_elu) y = y > 0.f ? y : expm1f(y);
+      out[(long long)b * out_clip_stride + (long long)t * H + u] = y;
+    }
+    // barrier among the CTAs of this batch slice
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      atomicAdd(&barriers[blockIdx.y], 1u);
+      const unsigned int target = (unsigned int)n_unit_ctas * (unsigned int)(t + 1);
+      while (*reinterpret_cast<volatile unsigned int*>(&barriers[blockIdx.y]) < target) {
+      }
+      __threadfence();
+    }
+    __syncthreads();
+  }
+}
+
+void launch_lstm_layer(const float* xproj, long long xproj_clip_stride, const float* w_hh, float* hbuf, float* out,
+                       long long out_clip_stride, const float* skip, long long skip_clip_stride, int post_elu,
+                       unsigned int* barriers, int batch, int T, int H, const LaunchCtx& ctx) {
+  if (H != 512) throw Error(NC_UNSUPPORTED, "lstm: hidden size must be 512");
+  if (batch == 0 || T == 0) return;
+  const int by = (batch + kLB - 1) / kLB;
+  dim3 grid(H / kLU, by);
+  if ((int)(grid.x * grid.y) > ctx.num_sms) throw Error(NC_INTERNAL, "lstm: batch slice too large for a co-resident grid");
+  NC_CUDA(cudaMemsetAsync(hbuf, 0, (size_t)2 * by * kLB * H * sizeof(float), ctx.stream));
+  NC_CUDA(cudaMemsetAsync(barriers, 0, (size_t)by * sizeof(unsigned int), ctx.stream));
+  const int ev = ctx.begin();
+  void* args[] = {(void*)&xproj, (void*)&xproj_clip_stride, (void*)&w_hh, (void*)&hbuf, (void*)&out, (void*)&out_clip_stride,
+                  (void*)&skip, (void*)&skip_clip_stride, (void*)&post_elu, (void*)&barriers, (void*)&batch, (void*)&T, (void*)&H};
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)lstm_layer_kernel, grid, dim3(256), args, 0, ctx.stream);
+  check_launch((int)e, "lstm_layer");
+  ctx.end(ev, "lstm_layer", 2.0 * 4 * H * (double)H * T * batch, (double)batch * T * H * 4.0 * 6);
+}
+
+int lstm_max_batch(int num_sms, int H) { return (num_sms / (H / kLU)) * kLB; }
+
+}  // namespace nc

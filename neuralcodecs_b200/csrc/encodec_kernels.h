@@ -1,0 +1,31 @@
+// Encodec-specific kernels (encodec_kernels.cu).
+#pragma once
+#include <cstdint>
+
+#include "runtime.h"
+
+namespace nc {
+
+// Materialise F.pad(mode="reflect") in the margin rows around each clip: x -> row 0 of clip 0, clips
+// `clip_stride` floats apart; rows [-left, 0) and [T, T+right) are written.  (SConv1d.cs:252-274)
+void launch_reflect_pad(float* x, int T, int C, long long clip_stride, int left, int right, int batch, const LaunchCtx& ctx);
+
+// One residual-VQ stage with a 128-d Euclidean codebook (EuclideanCodebook.cs:155-182,
+// ResidualVectorQuantizer.cs:146-154): codes[b, stage, t] = argmin_k (|x|^2 + |e_k|^2) + (-2 x.e_k); residual -= e.
+// residual: [frames][128] dense rows (frames = B*T); codes: [B][nq][T] int64.
+void launch_encodec_vq_stage(float* residual, long long frames, const float* embed, const float* embed_sq, int K, int D,
+                             int64_t* codes, int T, int nq, int stage, const LaunchCtx& ctx);
+// out[b, t, :] = sum_i embed_i[codes[b, i, t]]  (ResidualVectorQuantizer.cs:107-124); embeds_dev: device array of nq pointers
+void launch_encodec_decode_codes(const int64_t* codes, const float* const* embeds_dev, float* out, long long out_clip_stride,
+                                 int batch, int T, int nq, int K, int D, const LaunchCtx& ctx);
+
+// One nn.LSTM layer over T steps as a persistent cooperative kernel (zero initial state, SLSTM.cs:47-48).
+// xproj: hoisted input projection W_ih x_t + b_ih + b_hh, [B][T][4H] (gate order i,f,g,o); out: [B][T][H] = h_t
+// (+ skip[b,t,:] if given; ELU applied when post_elu).  hbuf: 2*ceil(B/16)*16*H floats; barriers: ceil(B/16) uints.
+void launch_lstm_layer(const float* xproj, long long xproj_clip_stride, const float* w_hh, float* hbuf, float* out,
+                       long long out_clip_stride, const float* skip, long long skip_clip_stride, int post_elu,
+                       unsigned int* barriers, int batch, int T, int H, const LaunchCtx& ctx);
+// largest batch one launch can take (all CTAs must be co-resident)
+int lstm_max_batch(int num_sms, int H);
+
+}  // namespace nc

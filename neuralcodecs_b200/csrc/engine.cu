@@ -571,8 +571,12 @@ Engine* create_engine(nc_codec_kind kind, const void* cfg, size_t cfg_size, int 
       if (cfg_size != sizeof(nc_snac_config)) throw Error(NC_INVALID_ARGUMENT, "cfg_size != sizeof(nc_snac_config)");
       return new SnacEngine(*static_cast<const nc_snac_config*>(cfg), device_index);
     }
+    case NC_CODEC_ENCODEC: {
+      if (cfg_size != sizeof(nc_encodec_config)) throw Error(NC_INVALID_ARGUMENT, "cfg_size != sizeof(nc_encodec_config)");
+      return new EncodecEngine(*static_cast<const nc_encodec_config*>(cfg), device_index);
+    }
     default:
-      throw Error(NC_UNSUPPORTED, "codec kind not built into this library yet");
+      throw Error(NC_UNSUPPORTED, "unknown codec kind");
   }
 }
 

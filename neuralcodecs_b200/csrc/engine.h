@@ -244,3 +244,79 @@ class SnacEngine : public Engine {
 };
 
 }  // namespace nc
+
+// ------------------------------------------------------------------------------------ Encodec
+#include "encodec_kernels.h"
+namespace nc {
+
+struct EncodecConfig {
+  int sample_rate = 24000, channels = 1, n_filters = 32, dimension = 128;
+  std::vector<int> ratios{8, 5, 4, 2};   // decoder order
+  int n_residual_layers = 1, lstm_layers = 2, codebook_size = 1024, n_quantizers = 32;
+  bool causal = true;
+  int hop() const {
+    int h = 1;
+    for (int r : ratios) h *= r;
+    return h;
+  }
+};
+
+class EncodecEngine : public Engine {
+ public:
+  EncodecEngine(const nc_encodec_config& cfg, int device_index);
+  ~EncodecEngine() override;
+  const char* codec_name() const override { return "Encodec"; }
+  void finalize_weights() override;
+  void set_option(const std::string& key, const std::string& value) override;
+  std::string describe() const override;
+  const EncodecConfig& config() const { return cfg_; }
+
+  int64_t frames(int64_t L) const;                     // encoder frames for L samples (causal ceil chain)
+  int64_t decoded_length(int64_t T) const { return T * cfg_.hop(); }
+  int n_q_for_bandwidth(float kbps) const;             // ResidualVectorQuantizer.cs:133-144
+
+  // device pointers.  codes [B][nq][T] int64; audio_out [B][T*hop] for decode, [B][L] (trimmed) for forward.
+  void encode_dev(const float* audio, int B, int64_t L, int nq, int64_t* codes);
+  void decode_dev(const int64_t* codes, int B, int nq, int64_t T, float* audio_out);
+  void forward_dev(const float* audio, int B, int64_t L, int nq, float* audio_out, int64_t* codes);
+
+ private:
+  struct Act {            // channels-last activation with 8 margin rows on each side of every clip
+    float* base = nullptr;  // row 0 of clip 0
+    int T = 0, C = 0;
+    long long stride = 0;   // floats between clips
+  };
+  struct Res { ConvLayer shortcut, c3, c1; int hidden_p = 0; };
+  struct Lstm { ConvLayer ih[2]; float* whh[2] = {nullptr, nullptr}; int layers = 0; };
+  static constexpr int kMargin = 8;
+  void require_ready() const;
+  std::vector<float> folded(const std::string& p, int d0, int d1, int k, std::vector<float>* bias, int bias_n);
+  void build_res(Res& r, const std::string& p, int dim);
+  void build_lstm(Lstm& l, const std::string& p, int dim);
+  Act act(int buf, int B, int T, int C);
+  void conv(const ConvLayer& L, const Act& in, int left_pad, int t_in_extra, const Act& out, int B, int prologue, int post,
+            const Act* residual);
+  Act run_res(const Res& r, const Act& x, int B, int& free_a, int& free_b, int& free_c, bool post_elu);
+  Act run_lstm(const Lstm& l, const Act& x, int B, int out_buf);
+  void run_encoder(const float* audio, int B, int64_t L, int64_t* T_out);   // -> z_ (dense [B][T][128])
+  void run_decoder(int B, int T, float* audio_out, long long out_stride);   // zq_ act -> audio
+  int micro_batch(int B, int64_t L);
+  int pick_free(int a, int b, int c = -1, int d = -1) const;
+
+  EncodecConfig cfg_;
+  Precision prec_ = PREC_BF16X3;
+  float* d_conv_in_w_ = nullptr;
+  float* d_conv_in_b_ = nullptr;
+  std::vector<std::unique_ptr<Res>> enc_res_, dec_res_;
+  std::vector<std::unique_ptr<ConvLayer>> enc_down_, dec_up_;
+  Lstm enc_lstm_, dec_lstm_;
+  ConvLayer enc_out_, dec_in_;
+  float* d_conv_out_w_ = nullptr;
+  float* d_conv_out_b_ = nullptr;
+  int conv_out_c_ = 0;
+  std::vector<float*> embed_, embed_sq_;
+  const float** d_embed_ptrs_ = nullptr;
+  DeviceBuffer ws_[5], xproj_, z_, hbuf_, barriers_, audio_tmp_, codes_tmp_;
+};
+
+}  // namespace nc

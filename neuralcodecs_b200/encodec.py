@@ -1,0 +1,175 @@
+"""Host-side mirror of the reference's Encodec model class over the C ABI (24 kHz mono causal preset).
+
+Same public method names and argument meaning as /root/reference/NeuralCodecs.Torch/Models/Encodec.cs
+(Encode :243/:259, Decode :213, forward :292, LoadWeights :348), numpy arrays in place of TorchSharp tensors;
+an EncodedFrame is the pair (codes [B,nq,T] int64, scale or None) as in Modules/Encodec/EncodedFrame.cs:8.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from .config import EncodecConfig
+
+EncodedFrame = Tuple[np.ndarray, Optional[np.ndarray]]
+
+
+class Encodec:
+    def __init__(self, config: EncodecConfig, *, options: Optional[Dict[str, str]] = None):
+        if config is None:
+            raise TypeError("config is null")
+        if config.bandwidth is None or float(config.bandwidth) not in [float(b) for b in config.target_bandwidths]:
+            raise ValueError(f"Invalid bandwidth {config.bandwidth}. Select one of {config.target_bandwidths}")   # Encodec.cs:47-53
+        self._config = config
+        c = _lib.nc_encodec_config()
+        c.struct_size = C.sizeof(_lib.nc_encodec_config)
+        c.sample_rate, c.channels, c.n_filters, c.dimension = config.sample_rate, config.channels, config.num_filters, config.hidden_size
+        c.n_ratios = len(config.upsampling_ratios)
+        for i, r in enumerate(config.upsampling_ratios):
+            c.ratios[i] = r
+        c.n_residual_layers, c.lstm_layers = config.num_residual_layers, config.num_lstm_layers
+        c.codebook_size, c.n_quantizers, c.causal = config.codebook_size, config.num_quantizers, int(config.use_causal_conv)
+        self._h = C.c_void_p()
+        _lib.check(_lib.lib().nc_create(_lib.NC_CODEC_ENCODEC, C.byref(c), C.sizeof(c), config.device.index, C.byref(self._h)),
+                   "Encodec", "Create")
+        for k, v in (options or {}).items():
+            self.set_option(k, v)
+
+    # ------------------------------------------------------------------ INeuralCodec
+    @property
+    def Config(self) -> EncodecConfig:
+        return self._config
+
+    @property
+    def Bandwidth(self) -> float:
+        return float(self._config.bandwidth)
+
+    def SetTargetBandwidth(self, bandwidth: float) -> None:
+        """Encodec.SetTargetBandwidth (Encodec.cs:409-420)."""
+        if float(bandwidth) not in [float(b) for b in self._config.target_bandwidths]:
+            raise ValueError(f"This model doesn't support the bandwidth {bandwidth}. Select one of {self._config.target_bandwidths}")
+        self._config.bandwidth = float(bandwidth)
+
+    def LoadWeights(self, path: str) -> None:
+        _lib.check(_lib.lib().nc_load_weights(self._handle(), str(path).encode()), "Encodec", "LoadWeights")
+
+    def Dispose(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.lib().nc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    close = Dispose
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.Dispose()
+
+    def __del__(self):
+        try:
+            self.Dispose()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ engine controls
+    def set_option(self, key: str, value) -> None:
+        _lib.check(_lib.lib().nc_set_option(self._handle(), key.encode(), str(value).encode()), "Encodec", "SetOption")
+
+    def set_tensor(self, name: str, array: np.ndarray) -> None:
+        a = np.ascontiguousarray(array)
+        a, dt = (a, 1) if a.dtype == np.int64 else (np.ascontiguousarray(a, dtype=np.float32), 0)
+        shape = (C.c_int64 * a.ndim)(*a.shape)
+        _lib.check(_lib.lib().nc_set_tensor(self._handle(), name.encode(), dt, a.ndim, shape, a.ctypes.data_as(C.c_void_p)),
+                   "Encodec", "SetTensor")
+
+    def finalize_weights(self) -> None:
+        _lib.check(_lib.lib().nc_finalize_weights(self._handle()), "Encodec", "LoadWeights")
+
+    def launch_count(self) -> int:
+        return int(_lib.lib().nc_launch_count(self._handle()))
+
+    def profile_report(self) -> dict:
+        buf = C.create_string_buffer(1 << 18)
+        _lib.check(_lib.lib().nc_profile_report(self._handle(), buf, len(buf)), "Encodec", "Profile")
+        return json.loads(buf.value.decode())
+
+    def describe(self) -> dict:
+        buf = C.create_string_buffer(1 << 18)
+        _lib.check(_lib.lib().nc_describe(self._handle(), buf, len(buf)), "Encodec", "Describe")
+        return json.loads(buf.value.decode())
+
+    def stream_ptr(self) -> int:
+        s = C.c_void_p()
+        _lib.check(_lib.lib().nc_get_stream(self._handle(), C.byref(s)), "Encodec", "GetStream")
+        return s.value or 0
+
+    def query_shapes(self, length: int) -> Tuple[int, int, int]:
+        """(frames, n_q at the configured bandwidth, decoded length)."""
+        fr, nq, dl = C.c_int64(), C.c_int32(), C.c_int64()
+        _lib.check(_lib.lib().nc_encodec_query_shapes(self._handle(), length, float(self._config.bandwidth), C.byref(fr),
+                                                      C.byref(nq), C.byref(dl)))
+        return fr.value, nq.value, dl.value
+
+    # ------------------------------------------------------------------ model surface
+    def _audio3d(self, x) -> np.ndarray:
+        if x is None:
+            raise TypeError("audioData is null")
+        a = np.ascontiguousarray(x, dtype=np.float32)
+        if a.ndim == 1:
+            a = a.reshape(1, self._config.channels, -1)                    # Encode(float[]) (Encodec.cs:247-250)
+        if a.ndim != 3:
+            raise ValueError(f"Expected 3D input tensor [B,C,T], got shape {list(a.shape)}")   # Encodec.cs:493-497
+        if a.shape[1] != self._config.channels:
+            raise ValueError(f"Expected {self._config.channels} channels, got {a.shape[1]}")   # Encodec.cs:499-503
+        return a
+
+    def Encode(self, audioData) -> List[EncodedFrame]:
+        """Encodec.Encode (Encodec.cs:243-285): the 24 kHz preset has no segmenting -> one frame for the whole clip."""
+        a = self._audio3d(audioData)
+        B, _, L = a.shape
+        T, nq, _ = self.query_shapes(L)
+        codes = np.empty((B, nq, T), np.int64)
+        _lib.check(_lib.lib().nc_encodec_encode(self._handle(), a.ctypes.data_as(C.c_void_p), B, L, float(self._config.bandwidth),
+                                                codes.ctypes.data_as(C.c_void_p)), "Encodec", "Encoding")
+        return [(codes, None)]
+
+    def Decode(self, encodedFrames: List[EncodedFrame]) -> np.ndarray:
+        """Encodec.Decode (Encodec.cs:213-235): audio [B,1,frames*hop], not trimmed."""
+        if encodedFrames is None or len(encodedFrames) == 0:
+            raise ValueError("No frames provided to decode")
+        if len(encodedFrames) != 1:
+            raise ValueError("Expected single frame when no segmentation is used")
+        codes, scale = encodedFrames[0]
+        if codes is None:
+            raise ValueError("Invalid frame codes in Encodec Decode")
+        c = np.ascontiguousarray(codes, dtype=np.int64)
+        B, nq, T = c.shape
+        audio = np.empty((B, 1, T * self._config.hop_length), np.float32)
+        _lib.check(_lib.lib().nc_encodec_decode(self._handle(), c.ctypes.data_as(C.c_void_p), B, nq, T,
+                                                audio.ctypes.data_as(C.c_void_p)), "Encodec", "Decoding")
+        if scale is not None:
+            audio *= np.asarray(scale, np.float32).reshape(-1, 1, 1)       # Encodec.cs:449-452
+        return audio
+
+    def forward(self, x) -> np.ndarray:
+        """Encodec.forward (Encodec.cs:292-296): decode(encode(x)) sliced to the input length."""
+        a = self._audio3d(x)
+        B, _, L = a.shape
+        out = np.empty((B, 1, L), np.float32)
+        _lib.check(_lib.lib().nc_encodec_forward(self._handle(), a.ctypes.data_as(C.c_void_p), B, L, float(self._config.bandwidth),
+                                                 out.ctypes.data_as(C.c_void_p), None), "Encodec", "Encoding")
+        return out
+
+    def forward_dev(self, audio_ptr: int, batch: int, length: int, audio_out_ptr: int, codes_ptr: int = 0) -> None:
+        _lib.check(_lib.lib().nc_encodec_forward_dev(self._handle(), audio_ptr, batch, length, float(self._config.bandwidth),
+                                                     audio_out_ptr or None, codes_ptr or None), "Encodec", "Encoding")
+
+    def _handle(self):
+        if not self._h.value:
+            raise RuntimeError("Encodec has been disposed")
+        return self._h

@@ -280,3 +280,97 @@ def snac_noise(batch: int, lengths, first_clip: int = 0, seed: int = 777):
             a[b, 0] = np.random.default_rng([seed, first_clip + b, i]).standard_normal(t).astype(np.float32)
         out.append(a)
     return out
+
+
+# --------------------------------------------------------------------------- Encodec
+def _enc_cfg(cfg):
+    c = _Cfg()
+    for f in ("sample_rate", "channels", "num_filters", "hidden_size", "upsampling_ratios", "num_residual_layers",
+              "num_lstm_layers", "codebook_size"):
+        setattr(c, f, getattr(cfg, f))
+    c.num_quantizers = cfg.num_quantizers
+    return c
+
+
+def encodec_layer_specs(cfg) -> Dict[str, tuple]:
+    """Reference Sequential indices (SEANetEncoder.cs:60-125, SEANetDecoder.cs:75-145) -> ("conv", cout, cin, k) |
+    ("convt", cin, cout, k) | ("lstm", dim, layers)."""
+    c = _enc_cfg(cfg)
+    specs: Dict[str, tuple] = {}
+    nf = c.num_filters
+
+    def resnet(p, dim):
+        specs[p + ".block.1"] = ("conv", dim // 2, dim, 3)
+        specs[p + ".block.3"] = ("conv", dim, dim // 2, 1)
+        specs[p + ".shortcut"] = ("conv", dim, dim, 1)
+
+    mult, idx = 1, 1
+    specs["encoder.layers.0"] = ("conv", nf, c.channels, 7)
+    for r in reversed(c.upsampling_ratios):
+        for _ in range(c.num_residual_layers):
+            resnet(f"encoder.layers.{idx}", mult * nf)
+            idx += 1
+        idx += 1                                   # ELU
+        specs[f"encoder.layers.{idx}"] = ("conv", mult * nf * 2, mult * nf, 2 * r)
+        idx += 1
+        mult *= 2
+    if c.num_lstm_layers > 0:
+        specs[f"encoder.layers.{idx}"] = ("lstm", mult * nf, c.num_lstm_layers)
+        idx += 1
+    idx += 1
+    specs[f"encoder.layers.{idx}"] = ("conv", c.hidden_size, mult * nf, 7)
+
+    mult = 2 ** len(c.upsampling_ratios)
+    specs["decoder.layers.0"] = ("conv", mult * nf, c.hidden_size, 7)
+    idx = 1
+    if c.num_lstm_layers > 0:
+        specs[f"decoder.layers.{idx}"] = ("lstm", mult * nf, c.num_lstm_layers)
+        idx += 1
+    for r in c.upsampling_ratios:
+        idx += 1                                   # ELU
+        specs[f"decoder.layers.{idx}"] = ("convt", mult * nf, mult * nf // 2, 2 * r)
+        idx += 1
+        for _ in range(c.num_residual_layers):
+            resnet(f"decoder.layers.{idx}", mult * nf // 2)
+            idx += 1
+        mult //= 2
+    idx += 1
+    specs[f"decoder.layers.{idx}"] = ("conv", c.channels, nf, 7)
+    return specs
+
+
+def make_encodec_weights(cfg) -> Dict[str, np.ndarray]:
+    """Seeded Encodec weights in the reference's key layout (weight_g = ||W||, weight_v = W; LSTM U(+-1/sqrt(H));
+    codebooks N(0,1), inited = 1, cluster_size = 1, embed_avg = embed)."""
+    c = _enc_cfg(cfg)
+    sd: Dict[str, np.ndarray] = {}
+    for name, spec in encodec_layer_specs(cfg).items():
+        kind = spec[0]
+        if kind == "lstm":
+            _, dim, layers = spec
+            bnd = 1.0 / np.sqrt(dim)
+            for l in range(layers):
+                sd[f"{name}.lstm.weight_ih_l{l}"] = _uniform(f"{name}.lstm.weight_ih_l{l}", (4 * dim, dim), bnd)
+                sd[f"{name}.lstm.weight_hh_l{l}"] = _uniform(f"{name}.lstm.weight_hh_l{l}", (4 * dim, dim), bnd)
+                sd[f"{name}.lstm.bias_ih_l{l}"] = _uniform(f"{name}.lstm.bias_ih_l{l}", (4 * dim,), bnd)
+                sd[f"{name}.lstm.bias_hh_l{l}"] = _uniform(f"{name}.lstm.bias_hh_l{l}", (4 * dim,), bnd)
+            continue
+        if kind == "conv":
+            _, cout, cin, k = spec
+            w = conv_weight(name + ".conv.weight", cout, cin, k)
+            fan_in, nb = cin * k, cout
+        else:
+            _, cin, cout, k = spec
+            w = convt_weight(name + ".conv.weight", cin, cout, k)
+            fan_in, nb = cout * k, cout
+        sd[name + ".conv.weight_g"] = np.sqrt((w.astype(np.float64) ** 2).sum(axis=(1, 2), keepdims=True)).astype(np.float32)
+        sd[name + ".conv.weight_v"] = w
+        sd[name + ".conv.bias"] = bias(name + ".conv.bias", nb, fan_in)
+    for q in range(c.num_quantizers):
+        p = f"quantizer.layers.{q}.codebook"
+        e = _rng(p + ".embed").standard_normal((c.codebook_size, c.hidden_size)).astype(np.float32)
+        sd[p + ".embed"] = e
+        sd[p + ".embed_avg"] = e.copy()
+        sd[p + ".cluster_size"] = np.ones(c.codebook_size, np.float32)
+        sd[p + ".inited"] = np.ones(1, np.float32)
+    return sd

@@ -1,0 +1,241 @@
+"""CPU oracle for the reference's Encodec model (24 kHz mono causal weight-norm preset).  TEST INFRASTRUCTURE ONLY.
+
+PARITY UNPINNED by the reference (it has no tests); see oracle/__init__.py.
+
+Op-for-op restatement of
+  Models/Encodec.cs:213-296,436-489            (Encode / Decode / forward / EncodeFrame / DecodeFrame)
+  Modules/Encodec/SEANetEncoder.cs:37-148, SEANetDecoder.cs:40-153, SEANetResnetBlock.cs:30-86
+  Modules/Encodec/SConv1d.cs:144-173,245-274, SConvTranspose1d.cs:116-139
+  Modules/Encodec/WNConv1d.cs:113-127, WNConvTranspose1d.cs:124-156      (w = (v/||v||) * (g - 1e-7))
+  Modules/Encodec/SLSTM.cs:24-57
+  Modules/Encodec/ResidualVectorQuantizer.cs:107-157, VectorQuantizer.cs:58-115, EuclideanCodebook.cs:74-182
+(paths relative to /root/reference/NeuralCodecs.Torch/).  Weight keys are the reference's:
+``encoder.layers.{n}.conv.{weight_g,weight_v,bias}``, ``...block.{1,3}.conv.*``, ``...shortcut.conv.*``,
+``encoder.layers.13.lstm.{weight_ih,weight_hh,bias_ih,bias_hh}_l{0,1}``, ``quantizer.layers.{i}.codebook.embed``.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+@dataclass
+class EncodecConfig:
+    """Config/Encodec/EncodecConfig.cs:6-153 (24 kHz preset = defaults)."""
+    sample_rate: int = 24000
+    channels: int = 1
+    num_filters: int = 32
+    hidden_size: int = 128                      # SEANet `dimension` and codebook dim
+    upsampling_ratios: List[int] = field(default_factory=lambda: [8, 5, 4, 2])
+    num_residual_layers: int = 1
+    num_lstm_layers: int = 2
+    codebook_size: int = 1024
+    target_bandwidths: List[float] = field(default_factory=lambda: [1.5, 3.0, 6.0, 12.0, 24.0])
+    bandwidth: float = 6.0
+    causal: bool = True
+    normalize: bool = False
+
+    @property
+    def hop_length(self) -> int:
+        return int(math.prod(self.upsampling_ratios))
+
+    @property
+    def frame_rate(self) -> int:                # Models/Encodec.cs:86
+        return int(math.ceil(np.float32(self.sample_rate) / np.float32(self.hop_length)))
+
+    @property
+    def num_quantizers(self) -> int:            # Models/Encodec.cs:70-71
+        return int(1000 * max(self.target_bandwidths) / (math.ceil(self.sample_rate / float(self.hop_length)) * 10))
+
+    def n_q_for_bandwidth(self, bandwidth: Optional[float] = None) -> int:
+        """ResidualVectorQuantizer.Encode (ResidualVectorQuantizer.cs:133-144)."""
+        bw = self.bandwidth if bandwidth is None else bandwidth
+        bw_per_q = math.log2(self.codebook_size) * self.frame_rate
+        n_q = self.num_quantizers
+        if bw is not None and bw > 0:
+            n_q = int(max(1, math.floor(np.float32(bw) * 1000 / bw_per_q)))
+        return n_q
+
+
+class EncodecOracle:
+    def __init__(self, cfg: EncodecConfig, sd: Dict[str, torch.Tensor], dtype=torch.float32):
+        self.cfg, self.dtype = cfg, dtype
+        self.sd = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
+
+    # ---------------------------------------------------------------- conv wrappers
+    def _w(self, p):
+        v, g = self.sd[p + ".conv.weight_v"], self.sd[p + ".conv.weight_g"]
+        v_norm = v.contiguous().pow(2).sum([1, 2], keepdim=True, dtype=self.dtype).sqrt()
+        return torch.mul(v.div(v_norm), g.sub(1e-7)).contiguous()
+
+    @staticmethod
+    def _extra_padding(length, kernel, stride, padding_total):
+        """SConv1d.GetExtraPaddingForConv1d (SConv1d.cs:245-250): note the float32 division."""
+        n_frames = np.float32(length - kernel + padding_total) / np.float32(stride) + np.float32(1)
+        ideal = (int(math.ceil(n_frames)) - 1) * stride + (kernel - padding_total)
+        return ideal - length
+
+    @staticmethod
+    def _pad1d(x, left, right):
+        """SConv1d.Pad1d (SConv1d.cs:252-267): always reflect; small inputs are zero-extended first."""
+        if x.shape[-1] <= max(left, right):
+            extra = max(left, right) - x.shape[-1] + 1
+            x = F.pad(x, [0, extra])
+            return F.pad(x, [left, right], mode="reflect")
+        return F.pad(x, [left, right], mode="reflect")
+
+    def sconv1d(self, p, x, k, stride=1, dilation=1):
+        """SConv1d.forward (SConv1d.cs:144-173)."""
+        length = x.shape[2]
+        k_eff = (k - 1) * dilation + 1
+        padding_total = k_eff - stride
+        extra = self._extra_padding(length, k_eff, stride, padding_total)
+        if self.cfg.causal:
+            padded = self._pad1d(x, padding_total, extra)
+        else:
+            right = padding_total // 2
+            padded = self._pad1d(x, padding_total - right, right + extra)
+        return F.conv1d(padded, self._w(p), self.sd.get(p + ".conv.bias"), stride, 0, dilation, 1)
+
+    def sconvtr1d(self, p, x, k, stride):
+        """SConvTranspose1d.forward (SConvTranspose1d.cs:116-139), trim_right_ratio = 1."""
+        y = F.conv_transpose1d(x, self._w(p), self.sd.get(p + ".conv.bias"), stride=stride)
+        padding_total = k - stride
+        if self.cfg.causal:
+            right = int(math.ceil(padding_total * 1.0))
+            left = padding_total - right
+        else:
+            right = padding_total // 2
+            left = padding_total - right
+        return y[..., left:y.shape[-1] - right]
+
+    def resnet(self, p, x):
+        """SEANetResnetBlock.forward (SEANetResnetBlock.cs:70-86): shortcut conv + [ELU,k3,ELU,k1]."""
+        s = self.sconv1d(p + ".shortcut", x, 1)
+        y = F.elu(x)
+        y = self.sconv1d(p + ".block.1", y, 3)
+        y = F.elu(y)
+        y = self.sconv1d(p + ".block.3", y, 1)
+        return torch.add(s, y)
+
+    def slstm(self, p, x):
+        """SLSTM.forward (SLSTM.cs:40-57): [B,C,T] -> [T,B,C]; nn.LSTM (zero state); + skip; back."""
+        perm = x.permute(2, 0, 1).contiguous()
+        h = perm
+        for layer in range(self.cfg.num_lstm_layers):
+            w_ih, w_hh = self.sd[f"{p}.lstm.weight_ih_l{layer}"], self.sd[f"{p}.lstm.weight_hh_l{layer}"]
+            b_ih, b_hh = self.sd[f"{p}.lstm.bias_ih_l{layer}"], self.sd[f"{p}.lstm.bias_hh_l{layer}"]
+            h = torch._VF.lstm(h, (torch.zeros(1, h.shape[1], w_hh.shape[1], dtype=self.dtype),
+                                   torch.zeros(1, h.shape[1], w_hh.shape[1], dtype=self.dtype)),
+                               [w_ih, w_hh, b_ih, b_hh], True, 1, 0.0, False, False, False)[0]
+        return h.add(perm).permute(1, 2, 0)
+
+    # ---------------------------------------------------------------- encoder / decoder
+    def encoder(self, x):
+        c = self.cfg
+        x = self.sconv1d("encoder.layers.0", x, 7)
+        idx = 1
+        for r in reversed(c.upsampling_ratios):
+            for _ in range(c.num_residual_layers):
+                x = self.resnet(f"encoder.layers.{idx}", x)
+                idx += 1
+            x = F.elu(x)
+            idx += 1
+            x = self.sconv1d(f"encoder.layers.{idx}", x, 2 * r, stride=r)
+            idx += 1
+        if c.num_lstm_layers > 0:
+            x = self.slstm(f"encoder.layers.{idx}", x)
+            idx += 1
+        x = F.elu(x)
+        idx += 1
+        return self.sconv1d(f"encoder.layers.{idx}", x, 7)
+
+    def decoder(self, x):
+        c = self.cfg
+        x = self.sconv1d("decoder.layers.0", x, 7)
+        idx = 1
+        if c.num_lstm_layers > 0:
+            x = self.slstm(f"decoder.layers.{idx}", x)
+            idx += 1
+        for r in c.upsampling_ratios:
+            x = F.elu(x)
+            idx += 1
+            x = self.sconvtr1d(f"decoder.layers.{idx}", x, 2 * r, r)
+            idx += 1
+            for _ in range(c.num_residual_layers):
+                x = self.resnet(f"decoder.layers.{idx}", x)
+                idx += 1
+        x = F.elu(x)
+        idx += 1
+        return self.sconv1d(f"decoder.layers.{idx}", x, 7)
+
+    # ---------------------------------------------------------------- quantizer
+    def vq_distances(self, q, flat):
+        """EuclideanCodebook.Quantize (EuclideanCodebook.cs:155-182): (x^2 + e^2^T) + (-2 x e^T)."""
+        embed = self.sd[f"quantizer.layers.{q}.codebook.embed"]
+        x2 = flat.pow(2).sum(1, keepdim=True)
+        e2 = embed.pow(2).sum(1, keepdim=True).t()
+        neg = -2 * flat.matmul(embed.t())
+        return x2.add(e2).add(neg)
+
+    def vq_forward(self, q, x):
+        """VectorQuantizer.forward (VectorQuantizer.cs:76-115), eval mode -> (quantized [B,D,T], codes [B,T])."""
+        xt = x.transpose(1, 2)
+        flat = xt.reshape(-1, xt.shape[-1])
+        idx = self.vq_distances(q, flat).argmin(dim=-1).view(xt.shape[:-1])
+        quant = F.embedding(idx, self.sd[f"quantizer.layers.{q}.codebook.embed"])
+        return quant.transpose(1, 2), idx
+
+    def rvq_encode(self, x, bandwidth: Optional[float] = None):
+        """ResidualVectorQuantizer.Encode (ResidualVectorQuantizer.cs:133-157) -> codes [B,nq,T] int64."""
+        n_q = self.cfg.n_q_for_bandwidth(bandwidth)
+        residual = x.clone()
+        codes = []
+        for i in range(n_q):
+            quant, idx = self.vq_forward(i, residual)
+            residual = residual - quant
+            codes.append(idx)
+        return torch.stack(codes, dim=1)
+
+    def rvq_decode(self, codes):
+        """ResidualVectorQuantizer.Decode (ResidualVectorQuantizer.cs:107-124)."""
+        out = torch.zeros(1, dtype=self.dtype)
+        for i in range(codes.shape[1]):
+            quant = F.embedding(codes[:, i], self.sd[f"quantizer.layers.{i}.codebook.embed"]).transpose(1, 2)
+            out = out + quant
+        return out
+
+    # ---------------------------------------------------------------- model surface (24 kHz: one frame = whole clip)
+    def encode(self, audio, bandwidth: Optional[float] = None):
+        """Encodec.Encode -> EncodeFrame (Encodec.cs:259-285,457-489), Normalize = false -> codes [B,nq,T]."""
+        with torch.inference_mode():
+            if audio.dim() != 3:
+                raise ValueError(f"Expected 3D input tensor [B,C,T], got shape {list(audio.shape)}")
+            if audio.shape[1] != self.cfg.channels:
+                raise ValueError(f"Expected {self.cfg.channels} channels, got {audio.shape[1]}")
+            emb = self.encoder(audio.to(self.dtype))
+            return self.rvq_encode(emb, bandwidth)
+
+    def encode_latent(self, audio):
+        with torch.inference_mode():
+            return self.encoder(audio.to(self.dtype))
+
+    def decode(self, codes):
+        """Encodec.Decode -> DecodeFrame (Encodec.cs:213-235,436-455): not trimmed."""
+        with torch.inference_mode():
+            return self.decoder(self.rvq_decode(codes))
+
+    def forward(self, audio, bandwidth: Optional[float] = None):
+        """Encodec.forward (Encodec.cs:292-296): decode(encode(x)) sliced to the input length."""
+        codes = self.encode(audio, bandwidth)
+        return {"audio": self.decode(codes)[..., :audio.shape[-1]], "codes": codes}
+
+
+def load_safetensors(path: str, cfg: EncodecConfig, dtype=torch.float32) -> EncodecOracle:
+    from safetensors.torch import load_file
+    return EncodecOracle(cfg, load_file(path), dtype)

@@ -98,3 +98,41 @@ def _fit_snac_codebooks(cfg, sd, clips: int, seconds: float) -> None:
             model.sd[nm] = cb
             zqi, _, _ = model.vq_forward(q, residual)
             residual = residual - zqi
+
+
+# --------------------------------------------------------------------------- Encodec
+from neuralcodecs_b200.synthetic import encodec_layer_specs  # noqa: E402,F401
+
+
+def make_encodec_weights(cfg, codebook_clips: int = 2, codebook_seconds: float = 10.0,
+                         codebooks: str = "data", fit_stages: int = 8) -> Dict[str, np.ndarray]:
+    """Seeded Encodec weights; the first `fit_stages` codebooks are fitted on the oracle's residuals."""
+    sd = _generic.make_encodec_weights(cfg)
+    if codebooks == "data":
+        _fit_encodec_codebooks(cfg, sd, codebook_clips, codebook_seconds, fit_stages)
+    return sd
+
+
+def _fit_encodec_codebooks(cfg, sd, clips, seconds, stages) -> None:
+    import torch
+    from . import encodec as enc_oracle
+
+    K = cfg.codebook_size
+    audio = torch.from_numpy(synth_audio(clips, int(round(seconds * cfg.sample_rate)), cfg.sample_rate)).unsqueeze(1)
+    model = enc_oracle.EncodecOracle(cfg, {k: torch.from_numpy(v) for k, v in sd.items()})
+    with torch.inference_mode():
+        residual = model.encoder(audio).clone()
+        for q in range(min(stages, cfg.num_quantizers)):
+            rows = residual.transpose(1, 2).reshape(-1, residual.shape[1])
+            nm = f"quantizer.layers.{q}.codebook.embed"
+            rng = _rng(nm + "/pick")
+            n = rows.shape[0]
+            pick = np.sort(rng.choice(n, size=K, replace=n < K))
+            cb = rows[torch.from_numpy(pick)].contiguous().clone()
+            if n < K:
+                cb = cb + torch.from_numpy(rng.standard_normal(cb.shape).astype(np.float32) * 0.1 * float(rows.std()))
+            sd[nm] = cb.numpy().copy()
+            sd[f"quantizer.layers.{q}.codebook.embed_avg"] = sd[nm].copy()
+            model.sd[nm] = cb
+            quant, _ = model.vq_forward(q, residual)
+            residual = residual - quant

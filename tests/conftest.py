@@ -85,3 +85,30 @@ def snac_24k(cache_dir):
     import neuralcodecs_b200 as nc
     co, ce = osnac.SNACConfig.snac_24khz(), nc.SNACConfig.SNAC24kHz()
     return co, ce, _write_snac(co, os.path.join(cache_dir, "snac24_seed4321.safetensors"), 4, 4.0)
+
+
+def _write_encodec(cfg, path, clips, seconds):
+    from oracle import synth
+    if not os.path.exists(path):
+        sd = synth.make_encodec_weights(cfg, codebook_clips=clips, codebook_seconds=seconds)
+        synth.save_safetensors(sd, path + ".tmp")
+        os.replace(path + ".tmp", path)
+    return path
+
+
+@pytest.fixture(scope="session")
+def encodec_nolstm(cache_dir):
+    """24 kHz architecture without the LSTM (isolates the conv stacks + VQ)."""
+    from oracle import encodec as oenc
+    import neuralcodecs_b200 as nc
+    co, ce = oenc.EncodecConfig(num_lstm_layers=0), nc.EncodecConfig(num_lstm_layers=0)
+    return co, ce, _write_encodec(co, os.path.join(cache_dir, "encodec_nolstm.safetensors"), 2, 4.0)
+
+
+@pytest.fixture(scope="session")
+def encodec_24k(cache_dir):
+    """Encodec 24 kHz preset at 6 kbps (BASELINE config #3)."""
+    from oracle import encodec as oenc
+    import neuralcodecs_b200 as nc
+    co, ce = oenc.EncodecConfig(), nc.EncodecConfig.Encodec24Khz()
+    return co, ce, _write_encodec(co, os.path.join(cache_dir, "encodec24_seed4321.safetensors"), 2, 6.0)

@@ -1,0 +1,106 @@
+"""Encodec engine (through the C ABI) against the CPU oracle (24 kHz mono causal preset, 6 kbps)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+MAX_ABS, MIN_SNR_DB, NEAR_TIE = 1e-3, 60.0, 1e-6     # north_star tolerances
+
+
+def snr_db(ref, test):
+    ref, test = np.asarray(ref, np.float64), np.asarray(test, np.float64)
+    return 10 * np.log10((ref ** 2).sum() / max(((ref - test) ** 2).sum(), 1e-300))
+
+
+def _models(fix, options=None):
+    import neuralcodecs_b200 as nc
+    from oracle import encodec as oenc
+    co, ce, path = fix
+    o = oenc.load_safetensors(path, co)
+    m = nc.Encodec(ce, options=options)
+    m.LoadWeights(path)
+    return o, m
+
+
+def _bad_flips(o, emb, codes_ref, codes):
+    """un-cascaded code flips whose scale-normalised margin is not a near-tie"""
+    bad = 0
+    ct = torch.from_numpy(codes)
+    with torch.inference_mode():
+        residual = emb.clone()
+        tainted = torch.zeros(codes_ref.shape[0], codes_ref.shape[2], dtype=torch.bool)
+        for q in range(codes_ref.shape[1]):
+            flat = residual.transpose(1, 2).reshape(-1, residual.shape[1])
+            dist = o.vq_distances(q, flat).reshape(codes_ref.shape[0], codes_ref.shape[2], -1)
+            embed = o.sd[f"quantizer.layers.{q}.codebook.embed"]
+            new = (codes_ref[:, q] != ct[:, q]) & ~tainted
+            for b, t in new.nonzero().tolist():
+                scale = float(residual[b, :, t].pow(2).sum() + embed[ct[b, q, t]].pow(2).sum())
+                margin = float(dist[b, t, ct[b, q, t]] - dist[b, t, codes_ref[b, q, t]]) / max(scale, 1e-30)
+                bad += abs(margin) >= NEAR_TIE
+            tainted |= codes_ref[:, q] != ct[:, q]
+            quant, _ = o.vq_forward(q, residual)
+            residual = residual - quant
+    return bad
+
+
+def _run(fix, options, batch, length, first=9):
+    from oracle import synth
+    o, m = _models(fix, options)
+    x = synth.synth_audio(batch, length, fix[0].sample_rate, first_clip=first)[:, None, :]
+    xt = torch.from_numpy(x)
+    ref = o.forward(xt)
+    emb = o.encode_latent(xt)
+    (codes, scale), = m.Encode(x)
+    assert scale is None and codes.dtype == np.int64 and codes.shape == tuple(ref["codes"].shape)
+    dec = m.Decode([(ref["codes"].numpy(), None)])
+    dref = o.decode(ref["codes"]).numpy()
+    assert dec.shape == dref.shape
+    return o, m, x, ref, emb, codes, dec, dref
+
+
+@pytest.mark.parametrize("length", [24000, 12345])
+def test_conv_stacks_and_vq_without_lstm_fp32(encodec_nolstm, length):
+    o, m, x, ref, emb, codes, dec, dref = _run(encodec_nolstm, {"precision": "fp32"}, 2, length)
+    assert _bad_flips(o, emb, ref["codes"], codes) == 0
+    np.testing.assert_allclose(dec, dref, atol=5e-6)
+    m.Dispose()
+
+
+def test_conv_stacks_without_lstm_tensor_core(encodec_nolstm):
+    o, m, x, ref, emb, codes, dec, dref = _run(encodec_nolstm, None, 3, 30001)
+    assert any(v.startswith("tcgen05") for v in m.describe()["layers"].values())
+    assert _bad_flips(o, emb, ref["codes"], codes) == 0
+    assert np.abs(dec - dref).max() <= MAX_ABS and snr_db(dref, dec) >= MIN_SNR_DB
+    m.Dispose()
+
+
+def test_encodec24k_preset_with_lstm(encodec_24k):
+    """BASELINE config #3 shape: 10 s clip -> codes [B, 8, 750]."""
+    o, m, x, ref, emb, codes, dec, dref = _run(encodec_24k, None, 2, 240000)
+    assert codes.shape == (2, 8, 750) and dec.shape == (2, 1, 240000)
+    match = float((codes == ref["codes"].numpy()).mean())
+    print(f"encodec24k: code match {match:.5f}; decoder max-abs {np.abs(dec - dref).max():.2e} snr {snr_db(dref, dec):.1f} dB")
+    assert _bad_flips(o, emb, ref["codes"], codes) == 0
+    assert np.abs(dec - dref).max() <= MAX_ABS and snr_db(dref, dec) >= MIN_SNR_DB
+    y = m.forward(x)
+    assert y.shape == x.shape
+    if match == 1.0:
+        assert np.abs(y - ref["audio"].numpy()).max() <= MAX_ABS
+    m.Dispose()
+
+
+def test_errors(encodec_nolstm):
+    import neuralcodecs_b200 as nc
+    _, m = _models(encodec_nolstm, {"precision": "fp32"})
+    with pytest.raises(ValueError, match="Expected 1 channels"):
+        m.Encode(np.zeros((1, 2, 1000), np.float32))
+    with pytest.raises(ValueError, match="No frames provided"):
+        m.Decode([])
+    with pytest.raises(ValueError, match="Invalid bandwidth"):
+        nc.Encodec(nc.EncodecConfig(bandwidth=7.0))
+    m.SetTargetBandwidth(3.0)
+    (codes, _), = m.Encode(np.zeros((1, 1, 3200), np.float32))
+    assert codes.shape == (1, 4, 10)                                     # 3 kbps -> 4 codebooks, ceil(3200/320) frames
+    m.Dispose()

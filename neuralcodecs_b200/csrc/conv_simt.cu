@@ -21,8 +21,8 @@ __device__ __forceinline__ float simt_prologue(float x, float a, int kind) {
 
 __global__ void __launch_bounds__(kSimtThreads)
 conv_simt_kernel(const __grid_constant__ ConvSimtParams p) {
-  __shared__ float As[SBK][SBM + 4];
-  __shared__ float Ws[SBK][SBN + 4];
+  __shared__ __align__(16) float As[SBK][SBM + 4];
+  __shared__ __align__(16) float Ws[SBK][SBN + 4];
   const int tid = threadIdx.x;
   const int tile_m = blockIdx.x;
   const int b = tile_m / p.m_tiles_per_clip;
@@ -75,11 +75,11 @@ conv_simt_kernel(const __grid_constant__ ConvSimtParams p) {
       __syncthreads();
 #pragma unroll
       for (int kk = 0; kk < SBK; ++kk) {
-        float a[STM], w[STN];
-#pragma unroll
-        for (int i = 0; i < STM; ++i) a[i] = As[kk][ty * STM + i];
-#pragma unroll
-        for (int j = 0; j < STN; ++j) w[j] = Ws[kk][tx * STN + j];
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * STM]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * STM + 4]);
+        const float4 w0 = *reinterpret_cast<const float4*>(&Ws[kk][tx * STN]);
+        const float a[STM] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float w[STN] = {w0.x, w0.y, w0.z, w0.w};
 #pragma unroll
         for (int i = 0; i < STM; ++i)
 #pragma unroll

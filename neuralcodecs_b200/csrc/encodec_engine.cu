@@ -50,7 +50,8 @@ EncodecEngine::~EncodecEngine() {
 
 void EncodecEngine::set_option(const std::string& key, const std::string& value) {
   if (key == "precision" || key == "encoder_precision" || key == "decoder_precision") {
-    prec_ = parse_precision(value);
+    if (key != "decoder_precision") enc_prec_ = parse_precision(value);
+    if (key != "encoder_precision") dec_prec_ = parse_precision(value);
     if (ready_) throw Error(NC_INVALID_ARGUMENT, "precision options must be set before weights are loaded");
   } else {
     Engine::set_option(key, value);
@@ -62,8 +63,10 @@ void EncodecEngine::require_ready() const {
 }
 
 std::string EncodecEngine::describe() const {
-  std::string s = "{\"codec\": \"Encodec\", \"precision\": \"";
-  s += precision_name(prec_);
+  std::string s = "{\"codec\": \"Encodec\", \"encoder_precision\": \"";
+  s += precision_name(enc_prec_);
+  s += "\", \"decoder_precision\": \"";
+  s += precision_name(dec_prec_);
   s += "\", \"layers\": {";
   bool first = true;
   auto add = [&](const ConvLayer& l) {
@@ -123,6 +126,7 @@ static int pad32e(int c) { return (c + 31) / 32 * 32; }
 
 void EncodecEngine::build_res(Res& r, const std::string& p, int dim) {
   std::vector<float> b;
+  const Precision prec_ = p.compare(0, 8, "encoder.") == 0 ? enc_prec_ : dec_prec_;
   const int hid = dim / 2, hp = pad32e(hid);
   r.hidden_p = hp;
   ConvSpec s1;  // shortcut: SConv1d(dim, dim, 1)
@@ -140,6 +144,7 @@ void EncodecEngine::build_res(Res& r, const std::string& p, int dim) {
 }
 
 void EncodecEngine::build_lstm(Lstm& l, const std::string& p, int dim) {
+  const Precision prec_ = p.compare(0, 8, "encoder.") == 0 ? enc_prec_ : dec_prec_;
   l.layers = cfg_.lstm_layers;
   for (int i = 0; i < l.layers; ++i) {
     const std::string sfx = "_l" + std::to_string(i);
@@ -185,7 +190,7 @@ void EncodecEngine::finalize_weights() {
     cs.cin = dim; cs.cout = 2 * dim; cs.k = 2 * r; cs.stride = r;   // valid conv over the padded input
     const std::string p = "encoder.layers." + std::to_string(idx);
     auto w = folded(p, 2 * dim, dim, 2 * r, &b, 2 * dim);
-    down->build(p, cs, w, b, prec_);
+    down->build(p, cs, w, b, enc_prec_);
     enc_down_.push_back(std::move(down));
     ++idx;
     mult *= 2;
@@ -198,7 +203,7 @@ void EncodecEngine::finalize_weights() {
     cs.cin = dim_top; cs.cout = cfg_.dimension; cs.k = 7;
     const std::string p = "encoder.layers." + std::to_string(idx);
     auto w = folded(p, cfg_.dimension, dim_top, 7, &b, cfg_.dimension);
-    enc_out_.build(p, cs, w, b, prec_);
+    enc_out_.build(p, cs, w, b, enc_prec_);
   }
   // ---- quantiser codebooks (EuclideanCodebook.cs:22-25)
   {
@@ -233,7 +238,7 @@ void EncodecEngine::finalize_weights() {
     ConvSpec cs;
     cs.cin = cfg_.dimension; cs.cout = mult * nf; cs.k = 7;
     auto w = folded("decoder.layers.0", mult * nf, cfg_.dimension, 7, &b, mult * nf);
-    dec_in_.build("decoder.layers.0", cs, w, b, prec_);
+    dec_in_.build("decoder.layers.0", cs, w, b, dec_prec_);
   }
   idx = 1;
   if (cfg_.lstm_layers > 0) { build_lstm(dec_lstm_, "decoder.layers." + std::to_string(idx), mult * nf); ++idx; }
@@ -246,7 +251,7 @@ void EncodecEngine::finalize_weights() {
     cs.transposed = true; cs.cin = cin; cs.cout = cout; cs.k = 2 * r; cs.stride = r;   // padding 0; the tail is trimmed
     const std::string p = "decoder.layers." + std::to_string(idx);
     auto w = folded(p, cin, cout, 2 * r, &b, cout);
-    up->build(p, cs, w, b, prec_);
+    up->build(p, cs, w, b, dec_prec_);
     dec_up_.push_back(std::move(up));
     ++idx;
     auto res = std::make_unique<Res>();

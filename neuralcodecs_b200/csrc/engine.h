@@ -304,7 +304,9 @@ class EncodecEngine : public Engine {
   int pick_free(int a, int b, int c = -1, int d = -1) const;
 
   EncodecConfig cfg_;
-  Precision prec_ = PREC_BF16X3;
+  // The encoder feeds the argmin: tensor-core accumulation noise (~1e-5 of the embedding) flips codes whose
+  // margin is far above the 1e-6 near-tie gate at the later RVQ stages, so it runs in true fp32 by default.
+  Precision enc_prec_ = PREC_FP32, dec_prec_ = PREC_BF16X3;
   float* d_conv_in_w_ = nullptr;
   float* d_conv_in_b_ = nullptr;
   std::vector<std::unique_ptr<Res>> enc_res_, dec_res_;

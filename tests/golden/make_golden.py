@@ -45,3 +45,28 @@ def dac_small():
 
 if __name__ == "__main__":
     dac_small()
+
+
+def encodec_small():
+    """transformers.EncodecModel (24 kHz-style causal weight-norm config, shrunk) -> encoder / decoder / codes fixtures.
+    HF's Encodec and the reference agree on everything on this path (conv stacks, causal reflect padding, LSTM skip,
+    un-normalised Euclidean VQ), so -- unlike DAC -- the code decisions are pinned too."""
+    from transformers import EncodecConfig as HFC, EncodecModel
+    from oracle import encodec as oenc
+    torch.manual_seed(7)
+    hf = EncodecModel(HFC(num_filters=8, hidden_size=32, codebook_size=64, codebook_dim=32, upsampling_ratios=[4, 3, 2],
+                          target_bandwidths=[1.5, 3.0, 6.0])).eval()
+    sd = {k.replace(".parametrizations.weight.original0", ".weight_g").replace(".parametrizations.weight.original1", ".weight_v"):
+          v.detach().clone().numpy() for k, v in hf.state_dict().items()}
+    x = torch.from_numpy(synth.synth_audio(2, 2503, 24000)).unsqueeze(1)
+    with torch.inference_mode():
+        emb = hf.encoder(x)
+        codes = hf.quantizer.encode(emb, 3.0).transpose(0, 1).contiguous()     # [B, nq, T]
+        audio = hf.decoder(hf.quantizer.decode(codes.transpose(0, 1)))
+    np.savez_compressed(os.path.join(OUT, "encodec_hf_small.npz"), audio_in=x.numpy(), encoder_out=emb.numpy(),
+                        codes=codes.numpy(), decoder_out=audio.numpy(), **{"w/" + k: v for k, v in sd.items()})
+    print("encodec_hf_small.npz", emb.shape, codes.shape, audio.shape)
+
+
+if __name__ == "__main__" and "--encodec" in sys.argv:
+    encodec_small()

@@ -1,0 +1,150 @@
+"""CPU checks of the SNAC and Encodec oracles: length algebra, naive restatements of the ops that differ from DAC,
+and (Encodec) committed transformers.EncodecModel fixtures."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import encodec as oenc
+from oracle import snac as osnac
+from oracle import synth
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "encodec_hf_small.npz")
+
+
+# ------------------------------------------------------------------------------------------------ SNAC
+@pytest.fixture(scope="module")
+def snac_small():
+    cfg = osnac.SNACConfig(sample_rate=16000, encoder_dim=12, encoder_rates=[2, 4, 4], decoder_dim=96, decoder_rates=[4, 4, 2],
+                           attn_window_size=None, codebook_size=64, vq_strides=[4, 2, 1])
+    sd = synth.make_snac_weights(cfg, codebooks="normal")
+    return cfg, osnac.SNACOracle(cfg, {k: torch.from_numpy(v) for k, v in sd.items()})
+
+
+def test_snac_24k_length_algebra():
+    cfg = osnac.SNACConfig.snac_24khz()
+    assert cfg.hop_length == 512 and cfg.pad_multiple == 2048 and cfg.latent_dim == 768   # 240000 -> 241664
+    m = osnac.SNACOracle(cfg, {})
+    assert m.preprocess(torch.zeros(1, 1, 240000)).shape[-1] == 241664
+    assert m.noise_lengths(472) == [3776, 30208, 120832, 241664]
+    c44 = osnac.SNACConfig.snac_44khz()
+    assert c44.pad_multiple == 384 * math.lcm(8, 32)                                      # SNAC.cs:74-77
+
+
+def test_snac_forward_shapes_trim_and_noise(snac_small):
+    cfg, m = snac_small
+    x = torch.from_numpy(synth.synth_audio(2, 3001, cfg.sample_rate)).unsqueeze(1)
+    Lp = m.preprocess(x).shape[-1]
+    assert Lp % (cfg.hop_length * 4) == 0
+    T = Lp // cfg.hop_length
+    noise = [torch.from_numpy(n) for n in synth.snac_noise(2, m.noise_lengths(T))]
+    out = m.forward(x, noise)
+    assert out["audio"].shape == x.shape                                   # trimmed (SNAC.cs:103)
+    assert [c.shape[1] for c in out["codes"]] == [T // 4, T // 2, T]
+    dec = m.decode(out["codes"], noise)
+    assert dec.shape[-1] == Lp                                             # Decode does not trim (SNAC.cs:157-165)
+    # FromCodes reproduces the quantised latent up to the straight-through roundings
+    np.testing.assert_allclose(m.rvq_from_codes(out["codes"]).numpy(), out["zq"].numpy(), atol=1e-5)
+    # noise enters as x + n * linear(x): zero noise and non-zero noise differ
+    assert float((m.decode(out["codes"], None) - dec).abs().max()) > 0
+
+
+def test_snac_depthwise_unit_against_naive(snac_small):
+    cfg, m = snac_small
+    p = "encoder.block.1.block.1"                                          # ResidualUnit, dilation 3, groups = 12
+    x = torch.randn(1, 12, 50)
+    y = m.residual_unit(p, x, 3, 12).numpy()
+    xs = m.snake(p + ".block.0", x).numpy()[0]
+    w = m._weight(p + ".block.1").numpy()[:, 0, :]
+    b = m.sd[p + ".block.1.bias"].numpy()
+    h = np.zeros((12, 50))
+    for t in range(50):
+        for j in range(7):
+            ti = t + (j - 3) * 3
+            if 0 <= ti < 50:
+                h[:, t] += w[:, j] * xs[:, ti]
+    h += b[:, None]
+    hs = m.snake(p + ".block.2", torch.from_numpy(h[None].astype(np.float32)))
+    y2 = m.wnconv1d(p + ".block.3", hs).numpy() + x.numpy()
+    np.testing.assert_allclose(y, y2, atol=2e-5)
+
+
+def test_snac_vq_stride_pools_then_repeats(snac_small):
+    cfg, m = snac_small
+    z = torch.randn(1, cfg.latent_dim, 8)
+    zq, idx, ze = m.vq_forward(0, z)                                       # stride 4
+    assert idx.shape == (1, 2) and zq.shape == z.shape
+    np.testing.assert_array_equal(zq[..., 0].numpy(), zq[..., 3].numpy())  # repeat_interleave(4)
+    pooled = z.reshape(1, cfg.latent_dim, 2, 4).mean(-1)
+    np.testing.assert_allclose(m.wnconv1d("quantizer.quantizers.0.in_proj", pooled).numpy(), ze.numpy(), atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ Encodec
+def test_encodec_config_algebra():
+    cfg = oenc.EncodecConfig()
+    assert (cfg.hop_length, cfg.frame_rate, cfg.num_quantizers, cfg.n_q_for_bandwidth()) == (320, 75, 32, 8)
+    assert [cfg.n_q_for_bandwidth(b) for b in (1.5, 3.0, 12.0, 24.0)] == [2, 4, 16, 32]
+
+
+@pytest.fixture(scope="module")
+def encodec_gold():
+    g = np.load(GOLD)
+    cfg = oenc.EncodecConfig(num_filters=8, hidden_size=32, codebook_size=64, upsampling_ratios=[4, 3, 2],
+                             target_bandwidths=[1.5, 3.0, 6.0], bandwidth=3.0)
+    sd = {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w/")}
+    return g, cfg, oenc.EncodecOracle(cfg, sd)
+
+
+def test_encodec_matches_hf_fixture(encodec_gold):
+    g, cfg, m = encodec_gold
+    x = torch.from_numpy(g["audio_in"])
+    np.testing.assert_array_equal(synth.synth_audio(2, 2503, 24000), g["audio_in"][:, 0])
+    with torch.inference_mode():
+        emb = m.encoder(x)
+    assert emb.shape == g["encoder_out"].shape
+    np.testing.assert_allclose(emb.numpy(), g["encoder_out"], atol=2e-6)
+    codes = m.rvq_encode(torch.from_numpy(g["encoder_out"]), 3.0)
+    np.testing.assert_array_equal(codes.numpy(), g["codes"])               # un-normalised Euclidean argmin: pinned by HF too
+    audio = m.decode(torch.from_numpy(g["codes"]))
+    np.testing.assert_allclose(audio.numpy(), g["decoder_out"], atol=2e-6)
+    assert m.forward(x, 3.0)["audio"].shape == x.shape                     # sliced to the input length (Encodec.cs:292-296)
+
+
+def test_encodec_causal_reflect_padding_rules():
+    # SConv1d.cs:144-173: causal -> all of padding_total on the left (reflect), "extra" on the right so that frames = ceil(L/stride)
+    for length, k, s in ((2503, 8, 4), (17, 4, 2), (24000, 16, 8), (7, 7, 1)):
+        pt = k - s
+        extra = oenc.EncodecOracle._extra_padding(length, k, s, pt)
+        assert (length + pt + extra - k) % s == 0 and 0 <= extra < s
+        assert (length + pt + extra - k) // s + 1 == math.ceil(length / s)
+    x = torch.arange(5.0).reshape(1, 1, 5)
+    np.testing.assert_array_equal(oenc.EncodecOracle._pad1d(x, 2, 1).numpy().ravel(), [2, 1, 0, 1, 2, 3, 4, 3])
+    small = oenc.EncodecOracle._pad1d(torch.ones(1, 1, 2), 3, 0)           # small-input branch: zero-extend, then reflect
+    assert small.shape[-1] == 2 + 2 + 3
+
+
+def test_encodec_lstm_matches_manual_recurrence():
+    cfg = oenc.EncodecConfig(num_filters=8, hidden_size=32, upsampling_ratios=[2], codebook_size=16, num_lstm_layers=2)
+    H = 16
+    torch.manual_seed(0)
+    sd = {}
+    for l in range(2):
+        for n, shape in (("weight_ih", (4 * H, H)), ("weight_hh", (4 * H, H)), ("bias_ih", (4 * H,)), ("bias_hh", (4 * H,))):
+            sd[f"p.lstm.{n}_l{l}"] = torch.randn(*shape) * 0.3
+    m = oenc.EncodecOracle(cfg, sd)
+    x = torch.randn(2, H, 9)
+    y = m.slstm("p", x)
+    seq = x.permute(2, 0, 1)
+    inp = seq
+    for l in range(2):
+        h = torch.zeros(2, H); c = torch.zeros(2, H); outs = []
+        for t in range(9):
+            gates = inp[t] @ sd[f"p.lstm.weight_ih_l{l}"].t() + sd[f"p.lstm.bias_ih_l{l}"] + h @ sd[f"p.lstm.weight_hh_l{l}"].t() + sd[f"p.lstm.bias_hh_l{l}"]
+            i, f, g, o = gates.chunk(4, dim=1)
+            c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+            h = torch.sigmoid(o) * torch.tanh(c)
+            outs.append(h)
+        inp = torch.stack(outs)
+    np.testing.assert_allclose(y.numpy(), (inp + seq).permute(1, 2, 0).numpy(), atol=2e-6)   # + skip (SLSTM.cs:52-55)

@@ -40,10 +40,21 @@ SAMPLE_RATE = 44100
 GFLOP_PER_AUDIO_S = 199.98        # conv/GEMM work of DAC-44.1k encode+decode
 WORKLOADS = {
     # name: (global batch, seconds per clip, decode_only)
-    "dac44k_b512x30s": (512, 30.0, False),       # BASELINE configs[3]
+    "dac44k_b512x30s": (512, 30.0, False),       # BASELINE configs[3] (default: the config the metric is quoted on)
     "dac44k_b1x10s": (1, 10.0, False),           # BASELINE configs[0]
     "dia_dac_decode_b256x20s": (256, 20.004, True),  # BASELINE configs[4]
+    "snac24k_b32x10s": (32, 10.0, False),        # BASELINE configs[1]
+    "encodec24k_b64x10s": (64, 10.0, False),     # BASELINE configs[2]
 }
+
+
+def shard_range(rank: int, world: int, batch: int):
+    """Contiguous shard [lo, hi) of the global batch owned by `rank` (static split, no collective)."""
+    return rank * batch // world, (rank + 1) * batch // world
+
+
+def codec_of(workload: str) -> str:
+    return "snac" if workload.startswith("snac") else "encodec" if workload.startswith("encodec") else "dac"
 
 
 def parse_args():
@@ -220,6 +231,163 @@ def synth_audio_cuda(torch, batch, length, first_clip, device):
     return out
 
 
+# ------------------------------------------------------------------------------------------ SNAC / Encodec arms
+def run_other_codec(args, codec: str, rank: int, local_rank: int, world: int):
+    """BASELINE configs[1] (SNAC 24 kHz) and configs[2] (Encodec 24 kHz, 6 kbps): same JSON contract as the DAC arm."""
+    import numpy as np
+    import torch
+    import neuralcodecs_b200 as nc
+    from neuralcodecs_b200 import synthetic
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B, S, _ = WORKLOADS[args.workload]
+    B = args.batch or B
+    S = args.seconds or S
+    sr = 24000
+    L = int(round(S * sr))
+    lo, hi = shard_range(rank, world, B)
+    nb = hi - lo
+    wpath = os.path.join(tempfile.gettempdir(), f"nc_bench_{codec}24_seed{synthetic.WEIGHT_SEED}.safetensors")
+    if rank == 0 and not os.path.exists(wpath):
+        if codec == "snac":
+            sd = synthetic.make_snac_weights(nc.SNACConfig.SNAC24kHz())
+        else:
+            sd = synthetic.make_encodec_weights(nc.EncodecConfig.Encodec24Khz())
+        for k in sd:   # N(0,1) codebooks scaled into the latents' range (timing is data independent)
+            if k.endswith("codebook.weight") or k.endswith("codebook.embed"):
+                sd[k] = (0.05 * sd[k]).astype("float32")
+        synthetic.save_safetensors(sd, wpath + ".tmp")
+        os.replace(wpath + ".tmp", wpath)
+    if dist is not None:
+        dist.barrier()
+    if codec == "snac":
+        cfg = nc.SNACConfig.SNAC24kHz()
+        cfg.device = nc.DeviceConfiguration.CUDA(local_rank)
+        model = nc.SNAC(cfg)
+    else:
+        cfg = nc.EncodecConfig.Encodec24Khz()
+        cfg.device = nc.DeviceConfiguration.CUDA(local_rank)
+        model = nc.Encodec(cfg)
+    model.LoadWeights(wpath)
+    base = torch.from_numpy(synthetic.synth_audio(min(max(nb, 1), 16), L, sr, first_clip=lo)).to(dev)
+    audio = base.repeat((max(nb, 1) + base.shape[0] - 1) // base.shape[0], 1)[:nb].contiguous()
+    out = torch.empty(nb, L, device=dev)
+    if codec == "snac":
+        _, T, clens, _ = model.query_shapes(L)
+        codes = [torch.empty(nb, n, dtype=torch.int64, device=dev) for n in clens]
+        step_dev = lambda: nb and model.forward_dev(audio.data_ptr(), nb, L, out.data_ptr(), [c.data_ptr() for c in codes], None, 5)
+        code_bytes = sum(c.numel() for c in codes) * 8
+    else:
+        T, nq, _ = model.query_shapes(L)
+        codes = torch.empty(nb, nq, T, dtype=torch.int64, device=dev)
+        step_dev = lambda: nb and model.forward_dev(audio.data_ptr(), nb, L, out.data_ptr(), codes.data_ptr())
+        code_bytes = codes.numel() * 8
+    stream = torch.cuda.ExternalStream(model.stream_ptr(), device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        t = torch.tensor([e0.elapsed_time(e1), wall * 1e3], device=dev, dtype=torch.float64)
+        barrier()
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1])
+
+    for _ in range(args.warmup):
+        step_dev()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = model.launch_count()
+    dev_ms, wall_ms = timed(step_dev, args.steps)
+    launches = model.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    audio_s = B * L / sr
+    value = audio_s * args.steps / (dev_ms / 1e3)
+    # e2e through the host-buffer entry point
+    h_audio = audio.cpu().numpy()
+    if codec == "snac":
+        step_host = lambda: nb and model.forward(h_audio[:, None, :], None, 5)
+    else:
+        step_host = lambda: nb and model.forward(h_audio[:, None, :])
+    step_host()
+    _, e2e_ms = timed(step_host, args.steps)
+    e2e = {"value": audio_s * args.steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(B * L * 4),
+           "d2h_bytes_per_step": int(B * L * 4 + (code_bytes * B // max(nb, 1) if codec == "snac" else 0)),
+           "timer": "wall clock, max over ranks"}
+    roofline = kernels = cpu = None
+    if rank == 0 and nb:
+        peaks, src = measured_peaks()
+        model.set_option("profile", "1"); model.profile_report(); step_dev(); rep = model.profile_report()
+        model.set_option("profile", "0")
+        total_ms = sum(v["ms"] for v in rep.values())
+        kernels = {k: {"launches": v["launches"], "ms": round(v["ms"], 3), "share": round(v["ms"] / total_ms, 4),
+                       "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 2),
+                       "gbs": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1)} for k, v in rep.items()}
+        top = max(rep.items(), key=lambda kv: kv[1]["ms"])
+        k, v = top
+        if k.startswith("conv_umma") or k.startswith("conv_simt") or k == "lstm_layer":
+            peak = peaks["bf16_tflops_sustained"] if k.startswith("conv_umma") else 70.0
+            ach = v["flops"] / v["ms"] / 1e9
+            roofline = {"bound": "tensor", "kernel": k, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                        "traffic": None, "launches": v["launches"], "avg_launch_ms": v["ms"] / v["launches"],
+                        "share_of_step": v["ms"] / total_ms,
+                        "peak_note": f"{src} bf16_tflops_sustained" if k.startswith("conv_umma") else "fp32 FFMA nominal ~70 TFLOP/s (CUDA-core kernel)"}
+        else:
+            ach = v["bytes"] / v["ms"] / 1e6
+            roofline = {"bound": "hbm", "kernel": k, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": ach / peaks["hbm_gbs"], "traffic": None, "launches": v["launches"],
+                        "avg_launch_ms": v["ms"] / v["launches"], "share_of_step": v["ms"] / total_ms,
+                        "peak_note": f"{src} hbm_gbs (copy bandwidth)"}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        if codec == "snac":
+            from oracle import snac as om
+            o = om.load_safetensors(wpath, om.SNACConfig.snac_24khz())
+        else:
+            from oracle import encodec as om
+            o = om.load_safetensors(wpath, om.EncodecConfig())
+        xs = torch.from_numpy(synthetic.synth_audio(2, L, sr)).unsqueeze(1)
+        o.forward(xs[:1, :, : sr])
+        t0 = time.perf_counter(); o.forward(xs); dt = time.perf_counter() - t0
+        cpu = {"value": 2 * S / dt, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"2 clips x {S:g} s (of {B}) in {dt:.1f} s, fp32 PyTorch-CPU restatement of the reference op stream"}
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32 in/out; see config.precision", "data": "synthetic",
+                "config": {"workload": args.workload, "codec": "SNAC 24 kHz" if codec == "snac" else "Encodec 24 kHz 6 kbps",
+                           "global_batch": B, "clip_seconds": S, "clips_per_gpu": nb, "precision": model.describe().get("precision")
+                           or f"encoder {model.describe().get('encoder_precision')}, decoder {model.describe().get('decoder_precision')}",
+                           "l2": "inputs + activations far larger than L2; no flush", "weights": "random-init (seeded)"},
+                "wall_ms_per_step": wall_ms / args.steps, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels}
+        print(json.dumps(line), flush=True)
+    model.Dispose()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
 def main():
     args = parse_args()
@@ -228,6 +396,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         reference_arm(args, rank)
+        return
+    if codec_of(args.workload) != "dac":
+        import torch
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback (use --impl reference)")
+        run_other_codec(args, codec_of(args.workload), rank, local_rank, world)
         return
 
     import numpy as np
@@ -251,7 +425,7 @@ def main():
         S = args.seconds
     L = int(round(S * SAMPLE_RATE))
     # contiguous shard of the global batch
-    lo, hi = rank * B // world, (rank + 1) * B // world
+    lo, hi = shard_range(rank, world, B)
     nb = hi - lo
 
     wpath = ensure_weights() if rank == 0 else None

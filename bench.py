@@ -391,6 +391,9 @@ def run_other_codec(args, codec: str, rank: int, local_rank: int, world: int):
 # ------------------------------------------------------------------------------------------ GPU arm
 def main():
     args = parse_args()
+    # NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION; the contract is ONE JSON line on stdout
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

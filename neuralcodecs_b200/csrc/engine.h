@@ -209,6 +209,18 @@ class SnacEngine : public Engine {
   };
   struct EncBlock { ResUnit ru[3]; SnakeParams s; ConvLayer down; };
   struct DecBlock { SnakeParams s; ConvLayer up; ConvLayer noise; ResUnit ru[3]; };
+  struct LocalMha {          // Modules/SNAC/LocalMHA.cs:46-115
+    bool present = false;
+    int dim = 0, heads = 0;
+    float* ln_w = nullptr;
+    float* ln_b = nullptr;
+    float* inv_freq = nullptr;
+    ConvLayer qkv, out;
+    ~LocalMha();
+  };
+  void build_mha(LocalMha& m, const std::string& p, int dim);
+  // x (buffer cur) -> x + to_out(attn(to_qkv(LN(x)))) with `post` applied on the way out; returns the buffer index
+  int run_mha(const LocalMha& m, int cur, int B, int T, const SnakeParams* post);
   void require_ready() const;
   std::vector<float> folded(const std::string& name, int d0, int d1, int k, std::vector<float>* bias, int bias_n);
   void build_ru(ResUnit& ru, const std::string& p, int dim, int dil);
@@ -228,6 +240,7 @@ class SnacEngine : public Engine {
   float* d_conv_in_b_ = nullptr;
   int c0p_ = 0;
   std::vector<std::unique_ptr<EncBlock>> enc_blocks_;
+  LocalMha enc_mha_, dec_mha_;
   DwConv enc_out_dw_;
   ConvLayer enc_out_dense_;
   std::vector<SnacVqStage> stages_;
@@ -239,7 +252,7 @@ class SnacEngine : public Engine {
   float* d_conv_out_w_ = nullptr;
   float* d_conv_out_b_ = nullptr;
   int conv_out_c_ = 0;
-  DeviceBuffer ws_[3], z_in_, z_q_, noise_buf_, audio_tmp_;
+  DeviceBuffer ws_[3], z_in_, z_q_, noise_buf_, audio_tmp_, qkv_buf_;
   int64_t per_clip_elems_ = 0;
 };
 

@@ -5,7 +5,8 @@
 // Channels-last activations; every channel count is padded to a multiple of 32 with zero weights so the
 // dense layers run on the tcgen05 kernel (48 -> 64 for the 24 kHz preset's first block).  A ResidualUnit is
 // two launches: depthwise k7 kernel (Snake1 prologue, Snake2 post) and the 1x1 GEMM (+ residual, + the
-// Snake that follows the unit).  LocalMHA (32/44 kHz presets) is not built yet: attn_window must be 0.
+// Snake that follows the unit).  LocalMHA (32/44 kHz presets): LayerNorm kernel -> qkv GEMM -> rotary + windowed
+// attention kernel (one warp per clip x window x head) -> out-projection GEMM with the residual in its epilogue.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -17,6 +18,58 @@ namespace nc {
 DwConv::~DwConv() {
   cudaFree(w);
   cudaFree(b);
+}
+
+SnacEngine::LocalMha::~LocalMha() {
+  cudaFree(ln_w);
+  cudaFree(ln_b);
+  cudaFree(inv_freq);
+}
+
+// LocalMHA weights: norm.{weight,bias}, to_qkv.weight [3C, C], to_out.weight [C, C] (no biases), rel_pos.inv_freq
+void SnacEngine::build_mha(LocalMha& m, const std::string& p, int dim) {
+  m.present = true;
+  m.dim = dim;
+  m.heads = dim / 64;
+  const HostTensor& g = tensor(p + ".norm.weight");
+  const HostTensor& b = tensor(p + ".norm.bias");
+  const HostTensor& wq = tensor(p + ".to_qkv.weight");
+  const HostTensor& wo = tensor(p + ".to_out.weight");
+  if ((int)g.numel() != dim || (int)b.numel() != dim || (int64_t)wq.numel() != (int64_t)3 * dim * dim ||
+      (int64_t)wo.numel() != (int64_t)dim * dim)
+    throw Error(NC_SHAPE_MISMATCH, "Failed to load SNAC weights: '" + p + "' has the wrong shape");
+  cudaFree(m.ln_w); cudaFree(m.ln_b); cudaFree(m.inv_freq);
+  m.ln_w = upload(g.f32);
+  m.ln_b = upload(b.f32);
+  std::vector<float> inv(32);
+  if (has_tensor(p + ".rel_pos.inv_freq") && tensor(p + ".rel_pos.inv_freq").numel() == 32) {
+    inv = tensor(p + ".rel_pos.inv_freq").f32;
+  } else {
+    for (int i = 0; i < 32; ++i) inv[i] = 1.0f / std::pow(10000.0f, (float)(2 * i) / 64.0f);   // SinusoidalEmbedding.cs:37-40
+  }
+  m.inv_freq = upload(inv);
+  ConvSpec sq;
+  sq.cin = dim; sq.cout = 3 * dim; sq.k = 1;
+  m.qkv.build(p + ".to_qkv", sq, wq.f32, std::vector<float>(), prec_);
+  ConvSpec so;
+  so.cin = so.cout = dim; so.k = 1;
+  m.out.build(p + ".to_out", so, wo.f32, std::vector<float>(), prec_);
+}
+
+int SnacEngine::run_mha(const LocalMha& m, int cur, int B, int T, const SnakeParams* post) {
+  const LaunchCtx c = ctx();
+  const int a = (cur + 1) % 3, y = (cur + 2) % 3;
+  launch_layernorm_rows(buf(cur), buf(a), m.ln_w, m.ln_b, (long long)B * T, m.dim, c);
+  float* qkv = static_cast<float*>(qkv_buf_.reserve((size_t)B * T * 3 * m.dim * sizeof(float)));
+  ConvRunArgs q;
+  q.in = buf(a); q.out = qkv; q.batch = B; q.t_in = T;
+  m.qkv.run(q, c);
+  launch_local_attn(qkv, buf(a), m.inv_freq, B, T, m.dim, m.heads, cfg_.attn_window, c);
+  ConvRunArgs o;
+  o.in = buf(a); o.out = buf(y); o.residual = buf(cur); o.batch = B; o.t_in = T;
+  if (post) { o.post = PRO_SNAKE; o.post_alpha = post->alpha; o.post_inv_alpha = post->inv_alpha; }
+  m.out.run(o, c);
+  return y;
 }
 
 SnacEngine::SnacEngine(const nc_snac_config& c, int device_index) : Engine(device_index) {
@@ -39,7 +92,10 @@ SnacEngine::SnacEngine(const nc_snac_config& c, int device_index) : Engine(devic
   if (cfg_.sample_rate <= 0 || cfg_.encoder_dim <= 0 || cfg_.decoder_dim <= 0 || cfg_.codebook_size <= 0)
     throw Error(NC_INVALID_ARGUMENT, "SNAC config: non-positive field");
   if (cfg_.codebook_dim != 8) throw Error(NC_UNSUPPORTED, "SNAC: codebook_dim must be 8");
-  if (cfg_.attn_window != 0) throw Error(NC_UNSUPPORTED, "SNAC: LocalMHA presets (attn_window_size != 0) are not built yet");
+  if (cfg_.attn_window != 0 && cfg_.attn_window != 32)
+    throw Error(NC_UNSUPPORTED, "SNAC: LocalMHA is built for attn_window_size 32 (the reference presets) only");
+  if (cfg_.attn_window != 0 && (cfg_.latent_dim % 64 != 0 || cfg_.decoder_dim % 64 != 0))
+    throw Error(NC_UNSUPPORTED, "SNAC: LocalMHA needs latent_dim and decoder_dim to be multiples of the 64-wide heads");
   for (size_t i = 0; i < cfg_.vq_strides.size(); ++i)
     if (cfg_.vq_strides[i] < 1 || cfg_.vq_strides[0] % cfg_.vq_strides[i] != 0)
       throw Error(NC_INVALID_ARGUMENT, "SNAC config: every vq stride must divide the first");
@@ -216,6 +272,11 @@ void SnacEngine::finalize_weights() {
   }
   if (d != cfg_.latent_dim) throw Error(NC_INVALID_ARGUMENT, "SNAC: latent_dim must equal encoder_dim * 2^n_rates");
   dzp_ = pad32(d);
+  enc_mha_.present = dec_mha_.present = false;
+  if (cfg_.attn_window) {   // Encoder.cs:50-53
+    build_mha(enc_mha_, "encoder.block." + std::to_string(idx), d);
+    ++idx;
+  }
   {
     const std::string p = "encoder.block." + std::to_string(idx);   // final conv (no Snake before it, Encoder.cs:55-62)
     if (cfg_.depthwise) {
@@ -280,6 +341,10 @@ void SnacEngine::finalize_weights() {
     auto w = folded("decoder.model.0", C, cfg_.latent_dim, 7, &b, C);
     dec_in_.build("decoder.model.0", cs, pad3(w, C, cfg_.latent_dim, 7, cs.cout, cs.cin), pad1(b, C, cs.cout, 0.f), prec_);
     idx = 1;
+  }
+  if (cfg_.attn_window) {   // Decoder.cs:54-57
+    build_mha(dec_mha_, "decoder.model." + std::to_string(idx), C);
+    ++idx;
   }
   dec_blocks_.clear();
   int cout = C;
@@ -405,6 +470,7 @@ void SnacEngine::run_encoder(const float* audio, int in_len, int B, int Lp) {
     T = blk->down.out_len(T);
     cur = (cur + 1) % 3;
   }
+  if (enc_mha_.present) cur = run_mha(enc_mha_, cur, B, T, nullptr);
   if (cfg_.depthwise) {
     launch_dwconv7(buf(cur), z_in_.as<float>(), T, dzp_, enc_out_dw_.w, enc_out_dw_.b, 1, nullptr, nullptr, B, c,
                    enc_out_dw_.name.c_str());
@@ -432,7 +498,7 @@ void SnacEngine::run_decoder(int B, int T, const float* const* noise, uint64_t s
   const SnakeParams* first = dec_blocks_.empty() ? &dec_snake_ : &dec_blocks_[0]->s;
   ConvRunArgs a;
   a.batch = B; a.t_in = T; a.out = buf(0);
-  a.post = PRO_SNAKE; a.post_alpha = first->alpha; a.post_inv_alpha = first->inv_alpha;
+  if (!dec_mha_.present) { a.post = PRO_SNAKE; a.post_alpha = first->alpha; a.post_inv_alpha = first->inv_alpha; }
   if (cfg_.depthwise) {
     launch_dwconv7(z_q_.as<float>(), buf(1), T, dzp_, dec_in_dw_.w, dec_in_dw_.b, 1, nullptr, nullptr, B, c, dec_in_dw_.name.c_str());
     a.in = buf(1);
@@ -441,6 +507,7 @@ void SnacEngine::run_decoder(int B, int T, const float* const* noise, uint64_t s
   }
   dec_in_.run(a, c);
   int cur = 0;
+  if (dec_mha_.present) cur = run_mha(dec_mha_, cur, B, T, first);
   const auto nlen = noise_lengths(T);
   for (size_t i = 0; i < dec_blocks_.size(); ++i) {
     auto& blk = dec_blocks_[i];

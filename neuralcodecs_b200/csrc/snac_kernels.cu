@@ -256,6 +256,123 @@ void launch_snac_from_codes(const SnacFromCodes& a, float* zq, int batch, int T,
   ctx.end(ev, "snac_from_codes", (double)frames * a.n_stages * 2.0 * 8 * Dz, (double)frames * Dz * 4.0);
 }
 
+// ------------------------------------------------------------------------------ LocalMHA pieces
+// LayerNorm over channels of a channels-last row (Modules/SNAC/LocalMHA.cs:88: nn.LayerNorm(dim), eps 1e-5).
+__global__ void __launch_bounds__(256)
+layernorm_rows_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, long long rows, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    const float* xr = x + r * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += xr[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)C;
+    float v = 0.f;
+    for (int c = lane; c < C; c += 32) { const float d = xr[c] - mean; v = fmaf(d, d, v); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const float rstd = rsqrtf(v / (float)C + eps);
+    for (int c = lane; c < C; c += 32) y[r * C + c] = (xr[c] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+  }
+}
+
+void launch_layernorm_rows(const float* x, float* y, const float* gamma, const float* beta, long long rows, int C,
+                           const LaunchCtx& ctx) {
+  if (rows == 0) return;
+  const int blocks = (int)std::min<long long>((rows + 7) / 8, (long long)ctx.num_sms * 8);
+  const int ev = ctx.begin();
+  layernorm_rows_kernel<<<blocks, 256, 0, ctx.stream>>>(x, y, gamma, beta, rows, C, 1e-5f);
+  check_launch((int)cudaGetLastError(), "layernorm_rows");
+  ctx.end(ev, "layernorm_rows", 0, 8.0 * rows * C);
+}
+
+// Windowed multi-head attention with rotary position embedding, window = 32, head dim = 64
+// (LocalMHA.cs:93-110, SinusoidalEmbedding.cs:60-72, RotaryEmbedding.cs:33-52; xpos scale = 1).
+// qkv: [B][T][3C] (q | k | v); out: [B][T][C].  One warp per (clip, window, head); lane = query position.
+constexpr int kAttnW = 32, kAttnD = 64;
+__global__ void __launch_bounds__(64)
+local_attn_kernel(const float* __restrict__ qkv, float* __restrict__ out, const float* __restrict__ inv_freq, int batch,
+                  int T, int C, int heads) {
+  __shared__ float ks[2][kAttnW][kAttnD];
+  __shared__ float vs[2][kAttnW][kAttnD];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int windows = T / kAttnW;
+  const long long item = (long long)blockIdx.x * 2 + wib;
+  const long long total = (long long)batch * windows * heads;
+  if (item >= total) return;
+  const int h = (int)(item % heads);
+  const int w = (int)((item / heads) % windows);
+  const int b = (int)(item / ((long long)heads * windows));
+  const float* row = qkv + ((long long)b * T + (long long)w * kAttnW + lane) * 3 * C + h * kAttnD;
+  float q[kAttnD], kk[kAttnD];
+#pragma unroll
+  for (int d4 = 0; d4 < kAttnD / 4; ++d4) {
+    const float4 a = *reinterpret_cast<const float4*>(row + 4 * d4);
+    const float4 c = *reinterpret_cast<const float4*>(row + C + 4 * d4);
+    const float4 v = *reinterpret_cast<const float4*>(row + 2 * C + 4 * d4);
+    q[4 * d4] = a.x; q[4 * d4 + 1] = a.y; q[4 * d4 + 2] = a.z; q[4 * d4 + 3] = a.w;
+    kk[4 * d4] = c.x; kk[4 * d4 + 1] = c.y; kk[4 * d4 + 2] = c.z; kk[4 * d4 + 3] = c.w;
+    *reinterpret_cast<float4*>(&vs[wib][lane][4 * d4]) = v;
+  }
+  // rotary: x * cos(f) + rotate_half(x) * sin(f), f[d] = pos * inv_freq[d % 32], rotate_half = cat(-x2, x1)
+#pragma unroll
+  for (int d = 0; d < kAttnD / 2; ++d) {
+    const float f = (float)lane * __ldg(inv_freq + d);
+    const float cs = cosf(f), sn = sinf(f);
+    const float q1 = q[d], q2 = q[d + 32], k1 = kk[d], k2 = kk[d + 32];
+    q[d] = q1 * cs + (-q2) * sn;
+    q[d + 32] = q2 * cs + q1 * sn;
+    kk[d] = k1 * cs + (-k2) * sn;
+    kk[d + 32] = k2 * cs + k1 * sn;
+  }
+#pragma unroll
+  for (int d = 0; d < kAttnD; ++d) ks[wib][lane][d] = kk[d];
+  __syncwarp();
+  float sc[kAttnW];
+  float mx = -3.4e38f;
+#pragma unroll
+  for (int j = 0; j < kAttnW; ++j) {
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < kAttnD; ++d) s = fmaf(q[d], ks[wib][j][d], s);
+    s *= 0.125f;   // 1 / sqrt(64)
+    sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < kAttnW; ++j) { sc[j] = expf(sc[j] - mx); sum += sc[j]; }
+  const float inv = 1.0f / sum;
+  float* orow = out + ((long long)b * T + (long long)w * kAttnW + lane) * C + h * kAttnD;
+#pragma unroll
+  for (int d4 = 0; d4 < kAttnD / 4; ++d4) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < kAttnW; ++j) {
+      const float4 v = *reinterpret_cast<const float4*>(&vs[wib][j][4 * d4]);
+      const float p = sc[j] * inv;
+      a.x = fmaf(p, v.x, a.x); a.y = fmaf(p, v.y, a.y); a.z = fmaf(p, v.z, a.z); a.w = fmaf(p, v.w, a.w);
+    }
+    *reinterpret_cast<float4*>(orow + 4 * d4) = a;
+  }
+}
+
+void launch_local_attn(const float* qkv, float* out, const float* inv_freq, int batch, int T, int C, int heads, int window,
+                       const LaunchCtx& ctx) {
+  if (window != kAttnW || C != heads * kAttnD) throw Error(NC_UNSUPPORTED, "local attention: window must be 32 and head dim 64");
+  if (T % window != 0) throw Error(NC_INVALID_ARGUMENT, "local attention: frames not a multiple of the window");
+  const long long total = (long long)batch * (T / window) * heads;
+  if (total == 0) return;
+  const int ev = ctx.begin();
+  local_attn_kernel<<<(unsigned)((total + 1) / 2), 64, 0, ctx.stream>>>(qkv, out, inv_freq, batch, T, C, heads);
+  check_launch((int)cudaGetLastError(), "local_attn");
+  ctx.end(ev, "local_attn", (double)total * 2.0 * 2 * kAttnW * kAttnW * kAttnD, 16.0 * batch * (double)T * C);
+}
+
 // ------------------------------------------------------------------------------ misc
 __global__ void trim_rows_kernel(const float* __restrict__ in, float* __restrict__ out, long long in_stride, long long out_len,
                                  long long total) {

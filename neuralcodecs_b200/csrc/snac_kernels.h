@@ -38,6 +38,14 @@ struct SnacFromCodes {
 // zq[b,t,:] = sum_i out_proj_i(codebook_i[codes_i[b, t / stride_i]])   (ResidualVectorQuantizer.cs:91-131)
 void launch_snac_from_codes(const SnacFromCodes& a, float* zq, int batch, int T, int Dz, int K, const LaunchCtx& ctx);
 
+// y[r, :] = LayerNorm(x[r, :]) * gamma + beta over C channels (eps 1e-5), rows of a channels-last tensor
+void launch_layernorm_rows(const float* x, float* y, const float* gamma, const float* beta, long long rows, int C,
+                           const LaunchCtx& ctx);
+// Non-causal attention inside windows of 32 frames with rotary embeddings (Modules/SNAC/LocalMHA.cs:93-110):
+// qkv [B][T][3C] -> out [B][T][C]; heads = C / 64.
+void launch_local_attn(const float* qkv, float* out, const float* inv_freq, int batch, int T, int C, int heads, int window,
+                       const LaunchCtx& ctx);
+
 // out[b, 0:out_len] = in[b*in_stride + 0:out_len]
 void launch_trim_rows(const float* in, float* out, int batch, long long in_stride, long long out_len, const LaunchCtx& ctx);
 // N(0,1) samples from a counter-based generator keyed by (seed, stream_id, index)

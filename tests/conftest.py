@@ -112,3 +112,23 @@ def encodec_24k(cache_dir):
     import neuralcodecs_b200 as nc
     co, ce = oenc.EncodecConfig(), nc.EncodecConfig.Encodec24Khz()
     return co, ce, _write_encodec(co, os.path.join(cache_dir, "encodec24_seed4321.safetensors"), 2, 6.0)
+
+
+@pytest.fixture(scope="session")
+def snac_attn(cache_dir):
+    """Small SNAC with LocalMHA (window 32), an odd stride (3: conv_transpose output_padding = 1) and 4 VQ strides."""
+    from oracle import snac as osnac
+    import neuralcodecs_b200 as nc
+    kw = dict(sample_rate=32000, encoder_dim=16, encoder_rates=[2, 3, 2], decoder_dim=256, decoder_rates=[2, 3, 2],
+              attn_window_size=32, codebook_size=128, vq_strides=[4, 2, 1])
+    co, ce = osnac.SNACConfig(**kw), nc.SNACConfig(**kw)
+    return co, ce, _write_snac(co, os.path.join(cache_dir, "snac_attn.safetensors"), 4, 1.0)
+
+
+@pytest.fixture(scope="session")
+def snac_44k(cache_dir):
+    """SNAC 44 kHz preset (LocalMHA, vq strides 8/4/2/1, stride-3 blocks): SURVEY 8(d) extra coverage run."""
+    from oracle import snac as osnac
+    import neuralcodecs_b200 as nc
+    co, ce = osnac.SNACConfig.snac_44khz(), nc.SNACConfig.SNAC44kHz()
+    return co, ce, _write_snac(co, os.path.join(cache_dir, "snac44_seed4321.safetensors"), 2, 2.0)

@@ -119,6 +119,42 @@ def test_snac24k_preset_config2_clip(snac_24k):
     m.Dispose()
 
 
+@pytest.mark.parametrize("prec", ["fp32", None])
+def test_local_attention_odd_stride_config(snac_attn, prec):
+    """LocalMHA (LayerNorm -> qkv -> rotary -> windowed SDPA -> out proj + residual) in encoder and decoder,
+    stride-3 blocks (output_padding 1), latent 128 = 2 heads, decoder 256 = 4 heads."""
+    o, m = _models(snac_attn, {"precision": prec} if prec else None)
+    cfg = snac_attn[0]
+    assert cfg.pad_multiple == 12 * 32
+    x, noise = _inputs(o, cfg, 2, 3000)
+    ref = o.forward(torch.from_numpy(x).unsqueeze(1), [torch.from_numpy(n) for n in noise])
+    audio, codes = m.forward(x[:, None, :], noise)
+    assert [c.shape for c in codes] == [tuple(c.shape) for c in ref["codes"]] and audio.shape == (2, 1, 3000)
+    assert _flips_ok(o, ref, codes) == 0
+    dec = m.Decode([c.numpy() for c in ref["codes"]], noise)
+    dref = o.decode(ref["codes"], [torch.from_numpy(n) for n in noise]).numpy()
+    assert dec.shape == dref.shape
+    print(f"snac attn {prec}: decoder max-abs {np.abs(dec - dref).max():.2e} snr {snr_db(dref, dec):.1f} dB")
+    assert np.abs(dec - dref).max() <= MAX_ABS and snr_db(dref, dec) >= MIN_SNR_DB
+    m.Dispose()
+
+
+def test_snac44k_preset_with_attention(snac_44k):
+    o, m = _models(snac_44k)
+    cfg = snac_44k[0]
+    x, noise = _inputs(o, cfg, 1, 44100)
+    ref = o.forward(torch.from_numpy(x).unsqueeze(1), [torch.from_numpy(n) for n in noise])
+    audio, codes = m.forward(x[:, None, :], noise)
+    assert [c.shape for c in codes] == [(1, 16), (1, 32), (1, 64), (1, 128)]          # 44100 -> 49152 samples, 128 frames
+    assert _flips_ok(o, ref, codes) == 0
+    dec = m.Decode([c.numpy() for c in ref["codes"]], noise)
+    dref = o.decode(ref["codes"], [torch.from_numpy(n) for n in noise]).numpy()
+    print(f"snac44k: decoder max-abs {np.abs(dec - dref).max():.2e} snr {snr_db(dref, dec):.1f} dB")
+    assert dec.shape == (1, 1, 49152)
+    assert np.abs(dec - dref).max() <= MAX_ABS and snr_db(dref, dec) >= MIN_SNR_DB
+    m.Dispose()
+
+
 def test_errors_and_resampler(snac_tiny):
     import neuralcodecs_b200 as nc
     _, m = _models(snac_tiny, {"precision": "fp32"})
@@ -133,5 +169,5 @@ def test_errors_and_resampler(snac_tiny):
     r = nc.SNAC.ResampleAudio(np.array([0.0, 1.0, 2.0], np.float32), 1, 2)
     np.testing.assert_allclose(r, [0.0, 0.5, 1.0, 1.5, 2.0, 2.0])
     with pytest.raises(RuntimeError):
-        nc.SNAC(nc.SNACConfig.SNAC44kHz())                                # LocalMHA presets not built yet
+        nc.SNAC(nc.SNACConfig(attn_window_size=16))                       # LocalMHA is built for the presets' window 32 only
     m.Dispose()

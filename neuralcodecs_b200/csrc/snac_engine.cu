@@ -443,7 +443,8 @@ int SnacEngine::run_ru(const ResUnit& ru, int cur, int B, int T, const SnakePara
   const LaunchCtx c = ctx();
   const int h = (cur + 1) % 3, y = (cur + 2) % 3;
   if (cfg_.depthwise) {
-    launch_dwconv7(buf(cur), buf(h), T, ru.dw.C, ru.dw.w, ru.dw.b, ru.dw.dil, ru.s1.alpha, ru.s2.alpha, B, c, ru.dw.name.c_str());
+    launch_dwconv7(buf(cur), buf(h), T, ru.dw.C, ru.dw.w, ru.dw.b, ru.dw.dil, ru.s1.alpha, ru.s2.alpha, B, c, ru.dw.name.c_str(),
+                   prec_ != PREC_FP32 && prec_ != PREC_3XTF32);
   } else {
     ConvRunArgs a;
     a.in = buf(cur); a.out = buf(h); a.batch = B; a.t_in = T;

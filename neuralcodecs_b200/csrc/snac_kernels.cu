@@ -8,16 +8,47 @@
 
 namespace nc {
 
-__device__ __forceinline__ float snake_precise_dev(float x, float a) {
-  if (a == 0.f) return x;
-  const float s = sinf(a * x);
-  return x + (s * s) / a;   // addcdiv(x, sin(ax)^2, a)
+// |sin(t)| to ~1.2 ulp for |t| < 1e5: 3-term Cody-Waite reduction by pi/2 + minimax polynomials (branch-free;
+// the sign is dropped because Snake only uses sin^2).  Same routine as the conv kernel's prologue.
+__device__ __forceinline__ float sin_abs_cw(float x) {
+  const int q = __float2int_rn(x * 0.636619772f);
+  const float j = __int2float_rn(q);
+  float r = fmaf(j, -1.57079601e+00f, x);
+  r = fmaf(j, -3.13916473e-07f, r);
+  r = fmaf(j, -5.39030253e-15f, r);
+  const float s = r * r;
+  const bool odd = (q & 1) != 0;
+  float p = odd ? 2.44331571e-5f : -1.95152959e-4f;
+  p = fmaf(p, s, odd ? -1.38873163e-3f : 8.33216087e-3f);
+  p = fmaf(p, s, odd ? 4.16666457e-2f : -1.66666546e-1f);
+  const float a = odd ? fmaf(p, s, -0.5f) : p;
+  const float m = odd ? s : r * s;
+  const float b = odd ? 1.0f : r;
+  return fmaf(a, m, b);
+}
+// x + sin^2(a x) / a with ia = 1/a (0 where a == 0 -> identity): where(alpha == 0, x, addcdiv(x, sin(ax)^2, alpha))
+template <bool kFast>
+__device__ __forceinline__ float snake_dev(float x, float a, float ia) {
+  const float t = a * x;
+  float s;
+  if (kFast) {
+    s = __sinf(t);           // MUFU: abs error ~4e-7, below the tensor-core layers' own noise
+  } else {
+    s = sin_abs_cw(t);
+    if (fabsf(t) > 9.0e4f) s = sinf(t);
+  }
+  return fmaf(s * s, ia, x);
+}
+__device__ __forceinline__ float4 inv4(float4 a) {
+  return make_float4(a.x == 0.f ? 0.f : 1.0f / a.x, a.y == 0.f ? 0.f : 1.0f / a.y, a.z == 0.f ? 0.f : 1.0f / a.z,
+                     a.w == 0.f ? 0.f : 1.0f / a.w);
 }
 
 // ------------------------------------------------------------------------------ depthwise conv, k = 7
 constexpr int kDwTT = 128;  // output time steps per block
 constexpr int kDwCC = 64;   // channels per block
 
+template <bool kFast>
 __global__ void __launch_bounds__(256)
 dwconv7_kernel(const float* __restrict__ in, float* __restrict__ out, int T, int C, const float* __restrict__ w_kc,
                const float* __restrict__ bias, int dil, const float* __restrict__ pro_alpha,
@@ -34,14 +65,15 @@ dwconv7_kernel(const float* __restrict__ in, float* __restrict__ out, int T, int
   const int rows = kDwTT + 6 * dil;
   float4 pa = make_float4(0.f, 0.f, 0.f, 0.f);
   if (pro_alpha && c_ok) pa = __ldg(reinterpret_cast<const float4*>(pro_alpha + c));
+  const float4 pia = inv4(pa);
   for (int r = rl; r < rows; r += 16) {
     const int t = t0 - 3 * dil + r;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c_ok && t >= 0 && t < T) {
       v = __ldg(reinterpret_cast<const float4*>(x + (long long)t * C + c));
       if (pro_alpha) {
-        v.x = snake_precise_dev(v.x, pa.x); v.y = snake_precise_dev(v.y, pa.y);
-        v.z = snake_precise_dev(v.z, pa.z); v.w = snake_precise_dev(v.w, pa.w);
+        v.x = snake_dev<kFast>(v.x, pa.x, pia.x); v.y = snake_dev<kFast>(v.y, pa.y, pia.y);
+        v.z = snake_dev<kFast>(v.z, pa.z, pia.z); v.w = snake_dev<kFast>(v.w, pa.w, pia.w);
       }
     }
     *reinterpret_cast<float4*>(tile + r * kDwCC + 4 * c4) = v;
@@ -54,6 +86,7 @@ dwconv7_kernel(const float* __restrict__ in, float* __restrict__ out, int T, int
   const float4 bb = bias ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
   float4 qa = make_float4(0.f, 0.f, 0.f, 0.f);
   if (post_alpha) qa = __ldg(reinterpret_cast<const float4*>(post_alpha + c));
+  const float4 qia = inv4(qa);
   for (int r = rl; r < kDwTT; r += 16) {
     const int t = t0 + r;
     if (t >= T) break;
@@ -67,27 +100,25 @@ dwconv7_kernel(const float* __restrict__ in, float* __restrict__ out, int T, int
     }
     a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
     if (post_alpha) {
-      a.x = snake_precise_dev(a.x, qa.x); a.y = snake_precise_dev(a.y, qa.y);
-      a.z = snake_precise_dev(a.z, qa.z); a.w = snake_precise_dev(a.w, qa.w);
+      a.x = snake_dev<kFast>(a.x, qa.x, qia.x); a.y = snake_dev<kFast>(a.y, qa.y, qia.y);
+      a.z = snake_dev<kFast>(a.z, qa.z, qia.z); a.w = snake_dev<kFast>(a.w, qa.w, qia.w);
     }
     *reinterpret_cast<float4*>(y + (long long)t * C + c) = a;
   }
 }
 
 void launch_dwconv7(const float* in, float* out, int T, int C, const float* w_kc, const float* bias, int dil,
-                    const float* pro_alpha, const float* post_alpha, int batch, const LaunchCtx& ctx, const char* layer) {
+                    const float* pro_alpha, const float* post_alpha, int batch, const LaunchCtx& ctx, const char* layer,
+                    bool fast_sin) {
   if (C % 4 != 0) throw Error(NC_UNSUPPORTED, "dwconv7: channel count must be a multiple of 4");
   if ((long long)batch * T == 0) return;
   const int tiles = (T + kDwTT - 1) / kDwTT;
   const size_t smem = (size_t)(kDwTT + 6 * dil) * kDwCC * sizeof(float);
-  if (smem > 48 * 1024) {
-    static bool set = false;
-    (void)set;
-    cudaFuncSetAttribute(dwconv7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  }
+  auto kern = fast_sin ? dwconv7_kernel<true> : dwconv7_kernel<false>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   dim3 grid((unsigned)(batch * tiles), (unsigned)((C + kDwCC - 1) / kDwCC));
   const int ev = ctx.begin();
-  dwconv7_kernel<<<grid, 256, smem, ctx.stream>>>(in, out, T, C, w_kc, bias, dil, pro_alpha, post_alpha, tiles);
+  kern<<<grid, 256, smem, ctx.stream>>>(in, out, T, C, w_kc, bias, dil, pro_alpha, post_alpha, tiles);
   check_launch((int)cudaGetLastError(), "dwconv7");
   ctx.end(ev, "dwconv7", 2.0 * 7 * C * (double)T * batch, 8.0 * batch * (double)T * C, layer ? layer : "");
 }

@@ -10,7 +10,8 @@ namespace nc {
 //   out[b,t,c] = post(bias[c] + sum_j w[j][c] * pro(in[b, t + (j-3)*dil, c]))
 // pro / post = Snake with the given alpha vectors (null = none).  w_kc: [7][C].
 void launch_dwconv7(const float* in, float* out, int T, int C, const float* w_kc, const float* bias, int dil,
-                    const float* pro_alpha, const float* post_alpha, int batch, const LaunchCtx& ctx, const char* layer);
+                    const float* pro_alpha, const float* post_alpha, int batch, const LaunchCtx& ctx, const char* layer,
+                    bool fast_sin = false /*MUFU sin in the Snakes (as the tensor-core layers do)*/);
 
 // One stage of SNAC's residual VQ (Modules/SNAC/VectorQuantizer.cs:82-103) on channels-last rows.
 struct SnacVqStage {

@@ -550,7 +550,7 @@ def main():
         kernels = {k: {"launches": v["launches"], "ms": round(v["ms"], 3), "share": round(v["ms"] / total_ms, 4),
                        "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 2),
                        "gbs": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1)} for k, v in rep.items()}
-        mma = {k: v for k, v in rep.items() if k.startswith("conv_umma")}
+        mma = {k: v for k, v in rep.items() if k.startswith("conv_umma") or k.startswith("ru_fused")}
         if mma:
             # tensor-core passes per algorithmic FLOP and the peak of the operand kind actually issued
             def passes(k): return 1 if k.endswith("_tf32") else 3
@@ -562,7 +562,7 @@ def main():
             busy = sum(v["flops"] * passes(k) / kind_peak(k) for k, v in mma.items())   # seconds*1e12 at peak
             peak = peaks["bf16_tflops_sustained"]
             ach = fl / ms / 1e9
-            roofline = {"bound": "tensor", "kernel": "conv_umma_kernel (tcgen05.mma, TMA-fed implicit-GEMM conv; all conv layers)",
+            roofline = {"bound": "tensor", "kernel": "conv_umma_kernel + conv_ru_fused_kernel (tcgen05.mma, TMA-fed implicit-GEMM conv; all conv layers)",
                         "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                         "traffic": None, "launches": n, "avg_launch_ms": ms / n, "share_of_step": ms / total_ms,
                         "issued_tflops": issued / ms / 1e9, "issued_frac": busy / ms / 1e9,

@@ -320,6 +320,65 @@ void ConvLayer::build(const std::string& name, const ConvSpec& spec, const std::
   for (auto& t : taps_) std::vector<float>().swap(t.w);
 }
 
+// Fill the tcgen05 plan for one call; returns false when this layer / call cannot use the tensor-core kernel.
+bool ConvLayer::fill_umma(const ConvRunArgs& a, ConvGemmParams* pp) const {
+  const ConvSpec& s = spec_;
+  const int t_out = out_len(a.t_in);
+  if (mode_ == PREC_FP32 || a.batch <= 0 || t_out <= 0) return false;
+  int a_rows, m_rows, n_total;
+  const long long a_valid = (long long)a.t_in * s.cin;
+  long long d_valid;
+  if (!s.transposed) {
+    a_rows = (a.t_in + s.stride - 1) / s.stride; m_rows = t_out; n_total = s.cout; d_valid = (long long)t_out * s.cout;
+  } else {
+    a_rows = a.t_in; m_rows = (t_out + s.stride - 1) / s.stride; n_total = s.stride * s.cout; d_valid = (long long)t_out * s.cout;
+  }
+  const long long a_stride = a.in_clip_stride ? a.in_clip_stride : a_valid;
+  const long long d_stride = a.out_clip_stride ? a.out_clip_stride : d_valid;
+  const bool whole_rows = a_valid == (long long)a_rows * k_view_ && (a_stride % 4) == 0 &&
+                          (reinterpret_cast<uintptr_t>(a.in) & 15) == 0;
+  if (!whole_rows && d_w_plain_) return false;
+  ConvGemmParams& p = *pp;
+  p = ConvGemmParams{};
+  p.A = a.in; p.a_clip_stride = a_stride; p.a_rows = a_rows; p.a_pitch = k_view_; p.a_valid = a_valid;
+  p.D = a.out; p.R = a.residual; p.d_clip_stride = d_stride; p.m_rows = m_rows; p.n_total = n_total;
+  p.n_valid = n_logical_; p.d_valid = d_valid;
+  p.bias = d_bias_; p.bias_period = s.cout; p.noise = a.noise;
+  p.alpha = a.alpha; p.inv_alpha = a.inv_alpha; p.alpha_period = s.cin; p.prologue = a.prologue; p.act = a.act;
+  p.post = a.post; p.post_alpha = a.post_alpha; p.post_inv_alpha = a.post_inv_alpha; p.post_period = s.cout;
+  p.W = d_w_tiles_; p.w_tile_floats = w_tile_floats_; p.BN = bn_; p.n_tiles = n_tiles_; p.tiles_per_ntile = tiles_per_ntile_;
+  p.mode = mma_mode(mode_);
+  p.n_taps = (int)taps_.size();
+  for (int j = 0; j < p.n_taps; ++j) p.taps[j] = utaps_[j];
+  std::memcpy(p.tap_mask, tap_mask_, sizeof tap_mask_);
+  p.n_kc = n_kc_; p.kc_begin = kc_begin_; p.smin = smin_; p.span = span_;
+  p.dense_step = dense_step_;
+  p.batch = a.batch; p.m_tiles_per_clip = (m_rows + 127) / 128;
+  const int fast = g_fast_sin >= 0 ? g_fast_sin : ((mode_ == PREC_TF32 || mode_ == PREC_BF16X3) ? 1 : 0);
+  p.precise_sin = fast ? 0 : 1;
+  return true;
+}
+
+static int g_fuse_ru = 1;
+void set_ru_fusion(int v) { g_fuse_ru = v; }
+
+// y = c2(post1(c1(pro(x)))) + x [-> post2] in one launch when the shapes allow it (C <= 256, bf16x3 / f16x3).
+bool try_run_ru_fused(const ConvLayer& c1, const ConvLayer& c2, const ConvRunArgs& a1, const ConvRunArgs& a2,
+                      const LaunchCtx& ctx) {
+  if (!g_fuse_ru) return false;
+  ConvGemmParams p, p2;
+  if (!c1.fill_umma(a1, &p) || !c2.fill_umma(a2, &p2)) return false;
+  if (!ru_fused_supported(p, p2)) return false;
+  const int ev = ctx.begin();
+  const int rc = launch_ru_fused(p, p2, ctx.num_sms, ctx.stream);
+  if (rc < 0) return false;
+  check_launch(rc, c1.name().c_str());
+  const double fl = c1.flops(a1.batch, a1.t_in) + c2.flops(a1.batch, a1.t_in);
+  const double bytes = 4.0 * a1.batch * (double)a1.t_in * c1.spec().cin * 3;   // read x (operand + residual), write y
+  ctx.end(ev, std::string("ru_fused_") + precision_name(c1.precision()), fl, bytes, c1.name());
+  return true;
+}
+
 void ConvLayer::run(const ConvRunArgs& a, const LaunchCtx& ctx) const {
   const ConvSpec& s = spec_;
   const int t_out = out_len(a.t_in);
@@ -343,27 +402,9 @@ void ConvLayer::run(const ConvRunArgs& a, const LaunchCtx& ctx) const {
   const int ev = ctx.begin();
   const long long a_stride = a.in_clip_stride ? a.in_clip_stride : a_valid;
   const long long d_stride = a.out_clip_stride ? a.out_clip_stride : d_valid;
-  const bool whole_rows = a_valid == (long long)a_rows * k_view_ && (a_stride % 4) == 0 &&
-                          (reinterpret_cast<uintptr_t>(a.in) & 15) == 0;
-  if (mode_ != PREC_FP32 && (whole_rows || !d_w_plain_)) {
-    ConvGemmParams p{};
-    p.A = a.in; p.a_clip_stride = a_stride; p.a_rows = a_rows; p.a_pitch = k_view_; p.a_valid = a_valid;
-    p.D = a.out; p.R = a.residual; p.d_clip_stride = d_stride; p.m_rows = m_rows; p.n_total = n_total;
-    p.n_valid = n_logical_; p.d_valid = d_valid;
-    p.bias = d_bias_; p.bias_period = s.cout; p.noise = a.noise;
-    p.alpha = a.alpha; p.inv_alpha = a.inv_alpha; p.alpha_period = s.cin; p.prologue = a.prologue; p.act = a.act;
-    p.post = a.post; p.post_alpha = a.post_alpha; p.post_inv_alpha = a.post_inv_alpha; p.post_period = s.cout;
-    p.W = d_w_tiles_; p.w_tile_floats = w_tile_floats_; p.BN = bn_; p.n_tiles = n_tiles_; p.tiles_per_ntile = tiles_per_ntile_;
-    p.mode = mma_mode(mode_);
-    p.n_taps = (int)taps_.size();
-    for (int j = 0; j < p.n_taps; ++j) p.taps[j] = utaps_[j];
-    std::memcpy(p.tap_mask, tap_mask_, sizeof tap_mask_);
-    p.n_kc = n_kc_; p.kc_begin = kc_begin_; p.smin = smin_; p.span = span_;
-    p.dense_step = dense_step_;
-    p.batch = a.batch; p.m_tiles_per_clip = m_tiles;
-    const int fast = g_fast_sin >= 0 ? g_fast_sin : ((mode_ == PREC_TF32 || mode_ == PREC_BF16X3) ? 1 : 0);
-    p.precise_sin = fast ? 0 : 1;
-    check_launch(launch_conv_umma(p, ctx.num_sms, ctx.stream), name_.c_str());
+  ConvGemmParams up;
+  if (fill_umma(a, &up)) {
+    check_launch(launch_conv_umma(up, ctx.num_sms, ctx.stream), name_.c_str());
     ctx.end(ev, std::string("conv_umma_") + precision_name(mode_), fl, bytes, name_);
   } else {
     ConvSimtParams p{};

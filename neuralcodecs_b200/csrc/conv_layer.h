@@ -55,6 +55,7 @@ class ConvLayer {
              const std::vector<float>& bias, Precision requested);
   int out_len(int t_in) const;
   void run(const ConvRunArgs& a, const LaunchCtx& ctx) const;
+  bool fill_umma(const ConvRunArgs& a, ConvGemmParams* p) const;
 
   const ConvSpec& spec() const { return spec_; }
   Precision precision() const { return mode_; }
@@ -91,5 +92,11 @@ class ConvLayer {
   long long simt_w_off_[kMaxTaps];
   bool umma_ok_ = false;
 };
+
+// Whole ResidualUnit (k7 conv -> Snake -> 1x1 conv -> + x [-> following Snake]) in one launch when supported;
+// a1: args of the k7 conv with out = the UNIT's output and residual = the unit's input; a2: the 1x1 conv's post.
+bool try_run_ru_fused(const ConvLayer& c1, const ConvLayer& c2, const ConvRunArgs& a1, const ConvRunArgs& a2,
+                      const LaunchCtx& ctx);
+void set_ru_fusion(int v);   // 0 disables (option "fuse_ru")
 
 }  // namespace nc

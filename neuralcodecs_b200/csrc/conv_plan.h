@@ -131,5 +131,9 @@ int launch_conv_umma(const ConvGemmParams& p, int num_sms, cudaStream_t stream);
 size_t umma_smem_bytes(const ConvGemmParams& p, UmmaLaunch* L);
 // whether the A view of p can be fetched by TMA (whole rows per clip, 16-byte aligned strides)
 bool umma_view_ok(const ConvGemmParams& p);
+// Whole DAC-style ResidualUnit in one launch: p = the k7 conv's plan (p.D = unit output, p.R = unit input,
+// p.post = Snake2), p2 = the 1x1 conv's plan (weights, bias, post = the Snake that follows the unit).
+bool ru_fused_supported(const ConvGemmParams& p, const ConvGemmParams& p2);
+int launch_ru_fused(const ConvGemmParams& p, const ConvGemmParams& p2, int num_sms, cudaStream_t stream);
 }  // namespace nc
 #endif

@@ -577,6 +577,362 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------- fused ResidualUnit
+// y = conv_k1(post1(conv_k7(f(x)) + b1)) + b2 + x  [-> post2]   in ONE kernel (DAC ResidualUnit.cs:24-59):
+// the k7 accumulator (TMEM acc1) is drained by the epilogue warps 32 channels at a time, activated, split into
+// bf16 hi|lo and written as K-chunk operand tiles ("H stages") in shared memory; the MMA thread multiplies them
+// with the 1x1 weights into a second accumulator (acc2); the usual TMA epilogue adds bias, the residual tile (TMA
+// load of x) and the following Snake and stores y.  The intermediate never touches HBM.
+// C <= 128: both accumulators double-buffered (4 x C <= 512 TMEM columns) and the k7 MMAs of tile i+1 are issued
+// BEFORE the 1x1 MMAs of tile i, so draining acc1 overlaps tensor-core work.  128 < C <= 256: single-buffered,
+// issue order k7(i), 1x1(i).  Operand mode: bf16x3 / f16x3 only.
+constexpr int kHStages = 3;
+
+template <int PRO, int RIT>
+__global__ void __launch_bounds__(kUmmaThreads, 1)
+conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_constant__ ConvGemmParams p2, const UmmaLaunch L,
+                     const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapD,
+                     const __grid_constant__ CUtensorMap tmapR) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t a_stage_bytes = (uint32_t)L.a_rows_alloc * 128u;
+  const uint32_t w_stage_bytes = (uint32_t)p.BN * 128u;
+  uint8_t* sA = smem;
+  uint8_t* sW = sA + (uint32_t)L.a_stages * a_stage_bytes;
+  uint8_t* sH = sW + (uint32_t)L.w_stages * w_stage_bytes;
+  uint8_t* sE = sH + kHStages * kEpiStageBytes;
+
+  __shared__ uint64_t raw_full[kMaxAStages], a_full[kMaxAStages], a_empty[kMaxAStages];
+  __shared__ uint64_t w_full[kMaxWStages], w_empty[kMaxWStages];
+  __shared__ uint64_t acc1_full[2], acc1_empty[2], acc2_full[2], acc2_empty[2];
+  __shared__ uint64_t h_full[kHStages], h_free[kHStages];
+  __shared__ uint64_t r_full[kEpiStages], e_free[kEpiStages];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < kMaxAStages; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&a_full[i], kProducerWarps); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < kMaxWStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], kEpilogueWarps);
+      mbar_init(&acc2_full[i], 1); mbar_init(&acc2_empty[i], kEpilogueWarps);
+    }
+    for (int i = 0; i < kHStages; ++i) { mbar_init(&h_full[i], kEpilogueWarps); mbar_init(&h_free[i], 1); }
+    for (int i = 0; i < kEpiStages; ++i) { mbar_init(&r_full[i], 1); mbar_init(&e_free[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc<512>(&tmem_base_s); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int total_tiles = p.batch * p.m_tiles_per_clip;      // one N tile (C <= 256)
+  const int my_tiles = total_tiles > (int)blockIdx.x ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const bool dbl = p.BN <= 128;
+  const int n_kc = p.n_kc;                                   // K chunks of the k7 conv == K chunks of the 1x1 conv
+  auto acc1_col = [&](int it) { return (uint32_t)(dbl ? (it & 1) * 128 : 0); };
+  auto acc2_col = [&](int it) { return (uint32_t)(256 + (dbl ? (it & 1) * 128 : 0)); };
+  auto buf_of = [&](int it) { return dbl ? (it & 1) : 0; };
+  auto use_of = [&](int it) { return (uint32_t)(dbl ? (it >> 1) : it); };   // how often that buffer was used before
+
+  if (warp == 0) {
+    // ===================================================================== weight producer (W1 and W2 tiles, MMA order)
+    if (elect_one()) {
+      int ws = 0;
+      uint32_t wph = 0;
+      auto push = [&](const float* src) {
+        mbar_wait(&w_empty[ws], wph ^ 1u);
+        mbar_arrive_expect_tx(&w_full[ws], w_stage_bytes);
+        bulk_g2s(sW + (size_t)ws * w_stage_bytes, src, w_stage_bytes, &w_full[ws]);
+        if (++ws == L.w_stages) { ws = 0; wph ^= 1u; }
+      };
+      auto w1 = [&]() {
+        for (int kci = 0; kci < n_kc; ++kci)
+          for (int j = 0; j < p.n_taps; ++j)
+            push(p.W + (size_t)(p.taps[j].tile_base + kci) * (size_t)p.w_tile_floats);
+      };
+      auto w2 = [&]() {
+        for (int g = 0; g < n_kc; ++g) push(p2.W + (size_t)g * (size_t)p2.w_tile_floats);
+      };
+      if (dbl) {
+        if (my_tiles > 0) w1();
+        for (int it = 0; it < my_tiles; ++it) { if (it + 1 < my_tiles) w1(); w2(); }
+      } else {
+        for (int it = 0; it < my_tiles; ++it) { w1(); w2(); }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (elect_one()) {
+      const uint32_t idesc = idesc_f16(kBM, p.BN, p.mode == MODE_BF16X3 ? 1 : 0);
+      const uint64_t a_desc0 = desc_at(smem_u32(sA)), w_desc0 = desc_at(smem_u32(sW)), h_desc0 = desc_at(smem_u32(sH));
+      const uint32_t a_stage_u = a_stage_bytes >> 4, w_stage_u = w_stage_bytes >> 4, h_stage_u = kEpiStageBytes >> 4;
+      const uint32_t tap_u = (uint32_t)p.dense_step * 8u;
+      int ws = 0, as = 0, hs = 0;
+      uint32_t wph = 0, aph = 0, hph = 0;
+      uint64_t a_desc = a_desc0, w_desc = w_desc0, h_desc = h_desc0;
+      auto mma6 = [&](uint32_t d_tmem, uint64_t a0, uint64_t b0, uint32_t acc) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          umma_f16(d_tmem, a0 + 4 + 2 * k, b0 + 2 * k, idesc, acc | (uint32_t)k);  // lo * hi
+          umma_f16(d_tmem, a0 + 2 * k, b0 + 4 + 2 * k, idesc, 1);                  // hi * lo
+          umma_f16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, 1);                      // hi * hi
+        }
+      };
+      auto next_w = [&]() {
+        tc_commit(&w_empty[ws]);
+        w_desc += w_stage_u;
+        if (++ws == L.w_stages) { ws = 0; wph ^= 1u; w_desc = w_desc0; }
+      };
+      auto m1 = [&](int it) {
+        const int b = buf_of(it);
+        mbar_wait(&acc1_empty[b], (use_of(it) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc1_col(it);
+        uint32_t acc = 0;
+        for (int kci = 0; kci < n_kc; ++kci) {
+          mbar_wait(&a_full[as], aph);
+          tc_fence_after();
+          uint64_t a_tap = a_desc;
+          for (int j = 0; j < p.n_taps; ++j) {
+            if (j) a_tap += tap_u;
+            mbar_wait(&w_full[ws], wph);
+            tc_fence_after();
+            mma6(d_tmem, a_tap, w_desc, acc);
+            acc = 1;
+            next_w();
+          }
+          tc_commit(&a_empty[as]);
+          a_desc += a_stage_u;
+          if (++as == L.a_stages) { as = 0; aph ^= 1u; a_desc = a_desc0; }
+        }
+        tc_commit(&acc1_full[b]);
+      };
+      auto m2 = [&](int it) {
+        const int b = buf_of(it);
+        mbar_wait(&acc2_empty[b], (use_of(it) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc2_col(it);
+        for (int g = 0; g < n_kc; ++g) {
+          mbar_wait(&h_full[hs], hph);
+          mbar_wait(&w_full[ws], wph);
+          tc_fence_after();
+          mma6(d_tmem, h_desc, w_desc, g ? 1u : 0u);
+          next_w();
+          tc_commit(&h_free[hs]);
+          h_desc += h_stage_u;
+          if (++hs == kHStages) { hs = 0; hph ^= 1u; h_desc = h_desc0; }
+        }
+        tc_commit(&acc2_full[b]);
+      };
+      if (dbl) {
+        if (my_tiles > 0) m1(0);
+        for (int it = 0; it < my_tiles; ++it) { if (it + 1 < my_tiles) m1(it + 1); m2(it); }
+      } else {
+        for (int it = 0; it < my_tiles; ++it) { m1(it); m2(it); }
+      }
+    }
+  } else if (warp == kLoaderWarp) {
+    // ===================================================================== A loader (TMA)
+    if (elect_one()) {
+      int as = 0;
+      uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int b = tile / p.m_tiles_per_clip;
+        const int mt = tile - b * p.m_tiles_per_clip;
+        const int r_base = mt * kBM + p.smin;
+        for (int kci = 0; kci < n_kc; ++kci) {
+          mbar_wait(&a_empty[as], aph ^ 1u);
+          mbar_arrive_expect_tx(&raw_full[as], a_stage_bytes);
+          tma_load_3d(sA + (size_t)as * a_stage_bytes, &tmapA, (p.kc_begin + kci) * 32, r_base, b, &raw_full[as]);
+          if (++as == L.a_stages) { as = 0; aph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == kResidualWarp) {
+    // ===================================================================== residual loader (TMA): tiles of x for E2
+    if (elect_one()) {
+      const int groups = p.BN / 32;
+      int es = 0;
+      uint32_t eph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int b = tile / p.m_tiles_per_clip;
+        const int mt = tile - b * p.m_tiles_per_clip;
+        for (int g = 0; g < groups; ++g) {
+          mbar_wait(&e_free[es], eph ^ 1u);
+          mbar_arrive_expect_tx(&r_full[es], kEpiStageBytes);
+          tma_load_3d(sE + (size_t)es * kEpiStageBytes, &tmapR, g * 32, mt * kBM, b, &r_full[es]);
+          if (++es == kEpiStages) { es = 0; eph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp < kFirstProducerWarp) {
+    // ===================================================================== epilogue warps: E1 (acc1 -> H stages), E2 (acc2 -> y)
+    const int q = warp & 3;
+    const int half = (warp - kFirstEpilogueWarp) >> 2;
+    const int rloc = q * 32 + lane;
+    const int groups = p.BN / 32;
+    const bool leader = warp == kFirstEpilogueWarp && lane == 0;
+    int hs = 0, es = 0, prev = -1;
+    uint32_t hph = 0, eph = 0;
+    auto e1 = [&](int it) {
+      const int b = buf_of(it);
+      mbar_wait(&acc1_full[b], use_of(it) & 1u);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + acc1_col(it) + ((uint32_t)(q * 32) << 16);
+      for (int g = 0; g < groups; ++g) {
+        float v[16];
+        __syncwarp();
+        tmem_ld16(t_addr + g * 32 + half * 16, v);
+        tmem_ld_wait();
+        if (g == groups - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc1_empty[b]);
+        }
+        const int n0 = g * 32 + half * 16;
+        epi_bias(p, v, n0);
+        epi_post(p, v, n0);
+        // 16 channels -> bf16/f16 hi (32 B) and lo (32 B) halves of this row of the K-chunk operand tile
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float x0 = v[2 * i], x1 = v[2 * i + 1];
+          if (p.mode == MODE_BF16X3) {
+            hi[i] = pack_bf16(x0, x1);
+            const __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&hi[i]);
+            lo[i] = pack_bf16(x0 - __low2float(h), x1 - __high2float(h));
+          } else {
+            hi[i] = pack_f16(x0, x1);
+            const __half2 h = *reinterpret_cast<__half2*>(&hi[i]);
+            lo[i] = pack_f16(x0 - __low2float(h), x1 - __high2float(h));
+          }
+        }
+        mbar_wait(&h_free[hs], hph ^ 1u);
+        uint8_t* stage = sH + (size_t)hs * kEpiStageBytes;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          *reinterpret_cast<uint4*>(stage + sw128_offset((uint32_t)rloc, (uint32_t)(half * 2 + c))) =
+              make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+          *reinterpret_cast<uint4*>(stage + sw128_offset((uint32_t)rloc, (uint32_t)(4 + half * 2 + c))) =
+              make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&h_full[hs]);
+        if (++hs == kHStages) { hs = 0; hph ^= 1u; }
+      }
+    };
+    auto e2 = [&](int it) {
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const int bb = tile / p.m_tiles_per_clip;
+      const int mt = tile - bb * p.m_tiles_per_clip;
+      const int b = buf_of(it);
+      mbar_wait(&acc2_full[b], use_of(it) & 1u);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + acc2_col(it) + ((uint32_t)(q * 32) << 16);
+      for (int g = 0; g < groups; ++g) {
+        float v[16];
+        __syncwarp();
+        tmem_ld16(t_addr + g * 32 + half * 16, v);
+        tmem_ld_wait();
+        if (g == groups - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc2_empty[b]);
+        }
+        const int n0 = g * 32 + half * 16;
+        epi_bias(p2, v, n0);
+        uint8_t* stage = sE + (size_t)es * kEpiStageBytes;
+        mbar_wait(&r_full[es], eph);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 r = *reinterpret_cast<const float4*>(stage + sw128_offset((uint32_t)rloc, (uint32_t)(half * 4 + i)));
+          v[4 * i + 0] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
+        }
+        epi_post(p2, v, n0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<float4*>(stage + sw128_offset((uint32_t)rloc, (uint32_t)(half * 4 + i))) =
+              make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueWarps * 32) : "memory");
+        if (leader) {
+          tma_store_3d(&tmapD, stage, g * 32, mt * kBM, bb);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          if (prev >= 0) mbar_arrive(&e_free[prev]);
+          prev = es;
+        }
+        if (++es == kEpiStages) { es = 0; eph ^= 1u; }
+      }
+    };
+    if (dbl) {
+      if (my_tiles > 0) e1(0);
+      for (int it = 0; it < my_tiles; ++it) { if (it + 1 < my_tiles) e1(it + 1); e2(it); }
+    } else {
+      for (int it = 0; it < my_tiles; ++it) { e1(it); e2(it); }
+    }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  } else {
+    // ===================================================================== A transformers (as conv_umma_kernel, H16X3)
+    const int ptid = tid - kFirstProducerWarp * 32;
+    const int c = ptid & 7;
+    const int rho0 = ptid >> 3;
+    const int rows_needed = kBM + p.span;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      for (int kci = 0; kci < n_kc; ++kci) {
+        const int ai = ((p.kc_begin + kci) * 32 + c * 4) % p.alpha_period;
+        const float4 al = __ldg(reinterpret_cast<const float4*>(p.alpha + ai));
+        const float4 ia = __ldg(reinterpret_cast<const float4*>(p.inv_alpha + ai));
+        uint8_t* stage = sA + (size_t)as * a_stage_bytes;
+        mbar_wait(&raw_full[as], aph);
+        float4 cur[RIT];
+#pragma unroll
+        for (int i = 0; i < RIT; ++i) {
+          const int rho = rho0 + 32 * i;
+          cur[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rho < rows_needed) cur[i] = *reinterpret_cast<const float4*>(stage + sw128_offset((uint32_t)rho, (uint32_t)c));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < RIT; ++i) {
+          const int rho = rho0 + 32 * i;
+          const float4 x = prologue4<PRO>(cur[i], al, ia);
+          if (rho < rows_needed) {
+            uint2 hi, lo;
+            if (p.mode == MODE_BF16X3) {
+              hi.x = pack_bf16(x.x, x.y); hi.y = pack_bf16(x.z, x.w);
+              const __nv_bfloat162 h0 = *reinterpret_cast<__nv_bfloat162*>(&hi.x), h1 = *reinterpret_cast<__nv_bfloat162*>(&hi.y);
+              lo.x = pack_bf16(x.x - __low2float(h0), x.y - __high2float(h0));
+              lo.y = pack_bf16(x.z - __low2float(h1), x.w - __high2float(h1));
+            } else {
+              hi.x = pack_f16(x.x, x.y); hi.y = pack_f16(x.z, x.w);
+              const __half2 h0 = *reinterpret_cast<__half2*>(&hi.x), h1 = *reinterpret_cast<__half2*>(&hi.y);
+              lo.x = pack_f16(x.x - __low2float(h0), x.y - __high2float(h0));
+              lo.y = pack_f16(x.z - __low2float(h1), x.w - __high2float(h1));
+            }
+            const uint32_t sub = (uint32_t)(c & 1) * 8u;
+            *reinterpret_cast<uint2*>(stage + sw128_offset((uint32_t)rho, (uint32_t)(c >> 1)) + sub) = hi;
+            *reinterpret_cast<uint2*>(stage + sw128_offset((uint32_t)rho, 4u + (uint32_t)(c >> 1)) + sub) = lo;
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[as]);
+        if (++as == L.a_stages) { as = 0; aph ^= 1u; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
 // ------------------------------------------------------------------------------- host launcher
 size_t umma_smem_bytes(const ConvGemmParams& p, UmmaLaunch* L) {
   const int rows = ((kBM + p.span) + 7) / 8 * 8;
@@ -704,6 +1060,81 @@ int launch_conv_umma(const ConvGemmParams& p, int num_sms, cudaStream_t stream) 
   const int grid = total_tiles < num_sms ? total_tiles : num_sms;
   if (grid <= 0) return 0;
   k<<<grid, kUmmaThreads, smem, stream>>>(p, L, tmap, tmapD, tmapR);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------- fused RU launcher
+typedef void (*RuKernel)(const ConvGemmParams, const ConvGemmParams, const UmmaLaunch, const CUtensorMap, const CUtensorMap,
+                         const CUtensorMap);
+
+// Measured (profiles/r01_layers_dac_b16x30s_fusedru.txt): fusion wins while both accumulators can be double-buffered in
+// TMEM (C <= 128); the single-buffered variant (128 < C <= 256) loses to two launches, so it is off by default.
+static int ru_fuse_max_c() {
+  static const int v = getenv("NC_RU_FUSE_MAX_C") ? atoi(getenv("NC_RU_FUSE_MAX_C")) : 128;
+  return v;
+}
+
+bool ru_fused_supported(const ConvGemmParams& p, const ConvGemmParams& p2) {
+  return (p.mode == MODE_BF16X3 || p.mode == MODE_F16X3) && p2.mode == p.mode && p.n_tiles == 1 && p2.n_tiles == 1 &&
+         p.BN == p2.BN && p.BN % 32 == 0 && p.BN <= ru_fuse_max_c() && p.n_total == p.BN && p.n_valid == p.BN && p.dense_step >= 0 &&
+         p.prologue == PRO_SNAKE && p2.n_taps == 1 && p2.n_kc == p.n_kc && p.kc_begin == 0 && p.span <= 64 &&
+         p.a_pitch == p.BN && umma_view_ok(p) && p.d_valid == (long long)p.m_rows * p.n_total && p.d_clip_stride % 4 == 0 &&
+         !p.noise && (reinterpret_cast<uintptr_t>(p.D) & 15) == 0;
+}
+
+// p: the k7 conv's plan with p.D = final output y, p.R = x (the unit's input), p.post = Snake2;
+// p2: the 1x1 conv's plan (weights, bias, post = the Snake that follows the unit or none).
+int launch_ru_fused(const ConvGemmParams& p, const ConvGemmParams& p2, int num_sms, cudaStream_t stream) {
+  if (!ru_fused_supported(p, p2)) return -1;
+  UmmaLaunch L;
+  const int rows = ((kBM + p.span) + 7) / 8 * 8;
+  const long a_stage = (long)rows * 128, w_stage = (long)p.BN * 128;
+  const long budget = (long)kUmmaMaxDynSmem - 1024 - (long)(kHStages + kEpiStages) * kEpiStageBytes;
+  int as = 2, ws = 2;
+  if (as * a_stage + ws * w_stage > budget) return -1;
+  for (;;) {
+    bool grew = false;
+    if (ws < 4 && as * a_stage + (ws + 1) * w_stage <= budget) { ++ws; grew = true; }
+    if (as < 4 && (as + 1) * a_stage + ws * w_stage <= budget) { ++as; grew = true; }
+    if (!grew) break;
+  }
+  while (ws < kMaxWStages && as * a_stage + (ws + 1) * w_stage <= budget) ++ws;
+  L.a_stages = as; L.w_stages = ws; L.a_rows_alloc = rows; L.tma_epilogue = 1;
+  const size_t smem = 1024 + (size_t)as * a_stage + (size_t)ws * w_stage + (size_t)(kHStages + kEpiStages) * kEpiStageBytes;
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return (int)cudaErrorNotSupported;
+  alignas(64) CUtensorMap tA, tD, tR;
+  const cuuint32_t estr[3] = {1, 1, 1};
+  {
+    const cuuint64_t gdim[3] = {(cuuint64_t)p.a_pitch, (cuuint64_t)p.a_rows, (cuuint64_t)p.batch};
+    const cuuint64_t gstr[2] = {(cuuint64_t)p.a_pitch * 4, (cuuint64_t)p.a_clip_stride * 4};
+    const cuuint32_t box[3] = {32, (cuuint32_t)rows, 1};
+    if (enc(&tA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.A), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return (int)cudaErrorInvalidValue;
+  }
+  {
+    const cuuint64_t dd[3] = {(cuuint64_t)p.n_total, (cuuint64_t)p.m_rows, (cuuint64_t)p.batch};
+    const cuuint64_t ds[2] = {(cuuint64_t)p.n_total * 4, (cuuint64_t)p.d_clip_stride * 4};
+    const cuuint32_t db[3] = {32, (cuuint32_t)kBM, 1};
+    if (enc(&tD, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p.D, dd, ds, db, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return (int)cudaErrorInvalidValue;
+    const cuuint64_t rs[2] = {(cuuint64_t)p.a_pitch * 4, (cuuint64_t)p.a_clip_stride * 4};
+    if (enc(&tR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.A), dd, rs, db, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return (int)cudaErrorInvalidValue;
+  }
+  const int rit = (kBM + p.span + 31) / 32;
+  RuKernel k;
+  if (p.precise_sin) k = rit <= 5 ? conv_ru_fused_kernel<P_SNAKE_PRECISE, 5> : conv_ru_fused_kernel<P_SNAKE_PRECISE, 6>;
+  else k = rit <= 5 ? conv_ru_fused_kernel<P_SNAKE_FAST, 5> : conv_ru_fused_kernel<P_SNAKE_FAST, 6>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaMaxDynSmem);
+  if (e != cudaSuccess) return (int)e;
+  const int total_tiles = p.batch * p.m_tiles_per_clip;
+  const int grid = total_tiles < num_sms ? total_tiles : num_sms;
+  if (grid <= 0) return 0;
+  k<<<grid, kUmmaThreads, smem, stream>>>(p, p2, L, tA, tD, tR);
   return (int)cudaGetLastError();
 }
 

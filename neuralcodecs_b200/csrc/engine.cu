@@ -56,6 +56,8 @@ void Engine::set_option(const std::string& key, const std::string& value) {
     prof_.by_layer = value == "2";
   } else if (key == "fast_sin") {
     set_fast_sin_policy(std::atoi(value.c_str()));
+  } else if (key == "fuse_ru") {
+    set_ru_fusion(std::atoi(value.c_str()));
   } else if (key == "max_workspace_mb") {
     const long long mb = std::atoll(value.c_str());
     if (mb < 64) throw Error(NC_INVALID_ARGUMENT, "max_workspace_mb must be >= 64");
@@ -411,10 +413,15 @@ int DacEngine::run_ru(const ResUnit& ru, int cur, int B, int T, const SnakeParam
   a.in = buf(cur); a.out = buf(h); a.batch = B; a.t_in = T;
   a.prologue = PRO_SNAKE; a.alpha = ru.s1.alpha; a.inv_alpha = ru.s1.inv_alpha;
   a.post = PRO_SNAKE; a.post_alpha = ru.s2.alpha; a.post_inv_alpha = ru.s2.inv_alpha;
-  ru.c1.run(a, c);
   ConvRunArgs b;
   b.in = buf(h); b.out = buf(y); b.residual = buf(cur); b.batch = B; b.t_in = T;
   if (post) { b.post = PRO_SNAKE; b.post_alpha = post->alpha; b.post_inv_alpha = post->inv_alpha; }
+  {   // whole unit in one launch (intermediate stays in TMEM / shared memory) when the shapes allow it
+    ConvRunArgs fa = a;
+    fa.out = buf(y); fa.residual = buf(cur);
+    if (try_run_ru_fused(ru.c1, ru.c2, fa, b, c)) return y;
+  }
+  ru.c1.run(a, c);
   ru.c2.run(b, c);
   return y;
 }

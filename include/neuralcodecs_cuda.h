@@ -172,6 +172,14 @@ NC_API nc_status nc_dac_from_codes(nc_handle h, const int64_t* codes, int32_t ba
  * audio [B,1,T*hop]. */
 NC_API nc_status nc_dac_decode_codes(nc_handle h, const int64_t* codes, int32_t batch, int32_t n_quantizers,
                                      int64_t frames, float* audio);
+/* replaces: Dia.GenerateOutput's codec stage Models/Dia.cs:1010-1060: generated [B,T,C] int64 are
+ * the delayed codes as Dia emits them; the delay pattern is reverted (Modules/Dia/AudioUtils.cs:108-176), the last
+ * max(delay) steps dropped, values outside [0, codebook_size) set to 0, and item b's first lengths[b] frames decoded.
+ * audio [B, audio_stride]: item b holds lengths[b]*hop samples (the rest of its row is left untouched).  Items are
+ * decoded in batches of equal length instead of the reference's serial loop. */
+NC_API nc_status nc_dac_decode_dia(nc_handle h, const int64_t* generated, int32_t batch, int32_t steps,
+                                   int32_t channels, const int32_t* delay_pattern, const int64_t* lengths,
+                                   float* audio, int64_t audio_stride);
 /* replaces: DAC.forward(Tensor) Models/DAC.cs:262-322 (Encode then Decode).  Outputs
  * nullable: audio_out [B,1,padded L], codes [B,nq,T], z [B,latent,T]. */
 NC_API nc_status nc_dac_forward(nc_handle h, const float* audio, int32_t batch, int64_t length,

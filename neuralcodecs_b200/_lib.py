@@ -87,6 +87,7 @@ SIGNATURES = {
     "nc_dac_decode": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _P]),
     "nc_dac_from_codes": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int64, _P]),
     "nc_dac_decode_codes": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int64, _P]),
+    "nc_dac_decode_dia": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), _I64, _P, C.c_int64]),
     "nc_dac_forward": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int32, _P, _P, _P, _I64]),
     "nc_dac_forward_dev": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int32, _P, _P, _P, _I64]),
     "nc_dac_decode_codes_dev": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int64, _P]),

@@ -247,6 +247,23 @@ nc_status nc_dac_decode_codes(nc_handle h, const int64_t* codes, int32_t batch, 
   });
 }
 
+nc_status nc_dac_decode_dia(nc_handle h, const int64_t* generated, int32_t batch, int32_t steps, int32_t channels,
+                            const int32_t* delay_pattern, const int64_t* lengths, float* audio, int64_t audio_stride) {
+  return guarded([&] {
+    DacEngine* e = dac_of(h);
+    if (!generated || !delay_pattern || !lengths || !audio) throw Error(NC_INVALID_ARGUMENT, "null buffer");
+    if (batch <= 0 || steps <= 0 || channels <= 0 || audio_stride <= 0) throw Error(NC_INVALID_ARGUMENT, "bad sizes");
+    BusyGuard g(e);
+    e->bind();
+    const size_t n = (size_t)batch * steps * channels;
+    DevMem d_g(n * 8), d_a((size_t)batch * audio_stride * 4);
+    NC_CUDA(cudaMemcpy(d_g.p, generated, n * 8, cudaMemcpyHostToDevice));
+    NC_CUDA(cudaMemset(d_a.p, 0, (size_t)batch * audio_stride * 4));
+    e->decode_dia_dev(d_g.as<int64_t>(), batch, steps, channels, delay_pattern, lengths, d_a.as<float>(), audio_stride);
+    NC_CUDA(cudaMemcpy(audio, d_a.p, (size_t)batch * audio_stride * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
 nc_status nc_dac_forward(nc_handle h, const float* audio, int32_t batch, int64_t length, int32_t n_quantizers,
                          float* audio_out, int64_t* codes, float* z, int64_t* frames_out) {
   return guarded([&] {

@@ -379,4 +379,34 @@ void launch_rvq_from_codes(const RvqWeights& w, const int64_t* codes, float* zq,
   ctx.end(ev, "rvq_from_codes", fr * n_q * 2.0 * w.D * w.Dz, fr * (w.Dz * 4.0 + n_q * 8.0));
 }
 
+// ------------------------------------------------------------------------------ Dia hand-off
+// Dia.GenerateOutput (Models/Dia.cs:1010-1044) + Decode's layout change (:973-981): undo the per-channel delay
+// (gather at min(t + delay[c], T-1); the reference's pad mask can never fire because the index is clamped first),
+// replace values outside [0, K) by 0, and write the DAC layout [n][C][len] for the selected items.
+__global__ void dia_revert_kernel(const int64_t* __restrict__ gen, const int* __restrict__ items, const int* __restrict__ delay,
+                                  int64_t* __restrict__ codes, int n_items, int T, int C, int len, int K) {
+  const long long total = (long long)n_items * C * len;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % len);
+    const int c = (int)((i / len) % C);
+    const int n = (int)(i / ((long long)len * C));
+    int ts = t + delay[c];
+    if (ts > T - 1) ts = T - 1;
+    long long v = gen[((long long)items[n] * T + ts) * C + c];
+    if (v < 0 || v >= K) v = 0;
+    codes[i] = v;
+  }
+}
+
+void launch_dia_revert(const int64_t* gen, const int* items_dev, const int* delay_dev, int64_t* codes, int n_items, int T, int C,
+                       int len, int K, const LaunchCtx& ctx) {
+  const long long total = (long long)n_items * C * len;
+  if (total == 0) return;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)ctx.num_sms * 16);
+  const int ev = ctx.begin();
+  dia_revert_kernel<<<blocks, 256, 0, ctx.stream>>>(gen, items_dev, delay_dev, codes, n_items, T, C, len, K);
+  check_launch((int)cudaGetLastError(), "dia_revert");
+  ctx.end(ev, "dia_revert", 0, 16.0 * total);
+}
+
 }  // namespace nc

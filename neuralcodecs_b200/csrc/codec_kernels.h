@@ -50,4 +50,8 @@ void launch_rvq_encode(const RvqWeights& w, const float* z, float* zq, int64_t* 
 void launch_rvq_from_codes(const RvqWeights& w, const int64_t* codes, float* zq, int batch, int T, int n_q,
                            const LaunchCtx& ctx);
 
+// Dia's delayed codes [B][T][C] -> DAC codes [n_items][C][len] for the listed items (revert delay, clamp to 0).
+void launch_dia_revert(const int64_t* gen, const int* items_dev, const int* delay_dev, int64_t* codes, int n_items, int T, int C,
+                       int len, int K, const LaunchCtx& ctx);
+
 }  // namespace nc

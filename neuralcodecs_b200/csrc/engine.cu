@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <map>
 
 namespace nc {
 
@@ -563,6 +564,53 @@ void DacEngine::decode_codes_dev(const int64_t* codes, int B, int nq, int64_t T,
     const int nb = std::min(mb, B - b0);
     launch_rvq_from_codes(rvq_, codes + (int64_t)b0 * nq * T, z_q_.as<float>(), nb, (int)T, nq, c);
     run_decoder(0, nb, (int)T, audio_out + (int64_t)b0 * out_len, out_len);
+  }
+  sync();
+}
+
+void DacEngine::decode_dia_dev(const int64_t* generated, int B, int T, int C, const int* delay, const int64_t* lengths,
+                               float* audio_out, int64_t audio_stride) {
+  require_ready();
+  bind();
+  if (B <= 0 || T <= 0 || !generated || !delay || !lengths || !audio_out) throw Error(NC_INVALID_ARGUMENT, "decode_dia: bad arguments");
+  if (C != cfg_.n_codebooks) throw Error(NC_INVALID_ARGUMENT, "decode_dia: channel count must equal the number of codebooks");
+  int max_delay = 0;
+  for (int c = 0; c < C; ++c) {
+    if (delay[c] < 0) throw Error(NC_INVALID_ARGUMENT, "decode_dia: negative delay");
+    max_delay = std::max(max_delay, delay[c]);
+  }
+  const int t_valid = T - max_delay;   // codebook[:, :-maxDelay, :]  (Dia.cs:1039)
+  std::map<int64_t, std::vector<int>> groups;
+  for (int b = 0; b < B; ++b) {
+    if (lengths[b] < 0 || lengths[b] > t_valid) throw Error(NC_INVALID_ARGUMENT, "decode_dia: length exceeds T - max(delay)");
+    if (lengths[b] > 0) groups[lengths[b]].push_back(b);
+    if (lengths[b] * cfg_.hop() > audio_stride) throw Error(NC_INVALID_ARGUMENT, "decode_dia: audio_stride too small");
+  }
+  int* d_delay = static_cast<int*>(dia_idx_.reserve((size_t)(C + B) * sizeof(int)));
+  int* d_items = d_delay + C;
+  NC_CUDA(cudaMemcpyAsync(d_delay, delay, (size_t)C * sizeof(int), cudaMemcpyHostToDevice, stream_));
+  const LaunchCtx c = ctx();
+  for (auto& g : groups) {
+    const int64_t len = g.first;
+    const std::vector<int>& items = g.second;
+    const int n = (int)items.size();
+    NC_CUDA(cudaMemcpyAsync(d_items, items.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    int64_t* codes = static_cast<int64_t*>(dia_codes_.reserve((size_t)n * C * len * sizeof(int64_t)));
+    launch_dia_revert(generated, d_items, d_delay, codes, n, T, C, (int)len, cfg_.codebook_size, c);
+    const int64_t Lp = len * cfg_.hop();
+    const int mb = micro_batch(n, Lp);
+    ensure_workspace(mb, Lp);
+    const int64_t out_len = decoded_length(len);
+    float* tmp = static_cast<float*>(dia_audio_.reserve((size_t)mb * out_len * sizeof(float)));
+    for (int b0 = 0; b0 < n; b0 += mb) {
+      const int nb = std::min(mb, n - b0);
+      launch_rvq_from_codes(rvq_, codes + (int64_t)b0 * C * len, z_q_.as<float>(), nb, (int)len, C, c);
+      run_decoder(0, nb, (int)len, tmp, out_len);
+      for (int i = 0; i < nb; ++i)   // scatter to each item's row of the caller's buffer
+        NC_CUDA(cudaMemcpyAsync(audio_out + (int64_t)items[b0 + i] * audio_stride, tmp + (int64_t)i * out_len,
+                                (size_t)std::min<int64_t>(out_len, audio_stride) * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
+    }
+    sync();   // d_items / codes are reused by the next group
   }
   sync();
 }

@@ -92,6 +92,11 @@ class DacEngine : public Engine {
   void from_codes_dev(const int64_t* codes, int B, int nq, int64_t T, float* z);
   void decode_codes_dev(const int64_t* codes, int B, int nq, int64_t T, float* audio_out);
   void forward_dev(const float* audio, int B, int64_t L, int nq, float* audio_out, int64_t* codes, float* z);
+  // Batched Dia hand-off (Models/Dia.cs:1010-1060): generated [B][T][C] delayed codes (device), lengths [B] (host),
+  // delay [C] (host) -> audio_out [B][audio_stride] (device), item b holding lengths[b]*hop samples.  Items of equal
+  // length are decoded together (the reference decodes them one by one).
+  void decode_dia_dev(const int64_t* generated, int B, int T, int C, const int* delay, const int64_t* lengths,
+                      float* audio_out, int64_t audio_stride);
 
  private:
   struct ResUnit {
@@ -144,7 +149,7 @@ class DacEngine : public Engine {
   float* d_conv_out_b_ = nullptr;
   int conv_out_c_ = 0;
   // workspaces: 3 rotating activation buffers + latent buffers
-  DeviceBuffer ws_[3], z_in_, z_q_;
+  DeviceBuffer ws_[3], z_in_, z_q_, dia_codes_, dia_idx_, dia_audio_;
   int64_t per_clip_elems_ = 0;  // per padded sample, see ensure_workspace
 };
 

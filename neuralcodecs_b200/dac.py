@@ -201,6 +201,28 @@ class DAC:
                                                   audio.ctypes.data_as(C.c_void_p)), "DAC", "Decoding")
         return audio
 
+    DIA_DELAY_PATTERN = (0, 8, 9, 10, 11, 12, 13, 14, 15)      # Config/Dia/DataConfig.cs:56
+
+    def DecodeDia(self, generatedCodes, lengths, delayPattern=DIA_DELAY_PATTERN):
+        """Batched Dia.GenerateOutput codec stage (Models/Dia.cs:1010-1060): generatedCodes [B,T,C] int64 (delayed, as
+        Dia emits them), lengths [B] -> list of per-item audio arrays of lengths[b]*hop samples."""
+        if generatedCodes is None or lengths is None:
+            raise TypeError("generatedCodes / lengths is null")
+        g = np.ascontiguousarray(generatedCodes, dtype=np.int64)
+        if g.ndim != 3:
+            raise ValueError("expected generatedCodes of shape [B,T,C]")
+        B, T, Cc = g.shape
+        ln = np.ascontiguousarray(lengths, dtype=np.int64).reshape(-1)
+        if ln.shape[0] != B or len(delayPattern) != Cc:
+            raise ValueError("lengths / delayPattern do not match generatedCodes")
+        dl = (C.c_int32 * Cc)(*[int(d) for d in delayPattern])
+        stride = max(int(ln.max()) * self._config.hop_length, 1)
+        audio = np.zeros((B, stride), np.float32)
+        _lib.check(_lib.lib().nc_dac_decode_dia(self._handle(), g.ctypes.data_as(C.c_void_p), B, T, Cc, dl,
+                                                ln.ctypes.data_as(C.POINTER(C.c_int64)), audio.ctypes.data_as(C.c_void_p),
+                                                stride), "DAC", "Decoding")
+        return [audio[b, : int(ln[b]) * self._config.hop_length].copy() for b in range(B)]
+
     def forward(self, audioData, sampleRate: Optional[int] = None, nQuantizers: Optional[int] = None) -> dict:
         """DAC.forward (DAC.cs:262-322): {"audio","z","codes"} (losses are constant zeros in the ref)."""
         a = _f32(audioData, "audioData")

@@ -252,6 +252,23 @@ class DACOracle:
         return self.decode(z).squeeze()
 
 
+def dia_generate_output(model: "DACOracle", generated: torch.Tensor, lengths, delay_pattern=(0, 8, 9, 10, 11, 12, 13, 14, 15),
+                        min_valid: int = 0, max_valid: int = 1023):
+    """Dia.GenerateOutput's codec stage (Models/Dia.cs:1010-1060 with Modules/Dia/AudioUtils.cs:108-176):
+    BuildRevertIndices (t + delay clamped to T-1) -> gather -> where(t_idx >= T, pad, x) (never true after the clamp)
+    -> drop the last max(delay) steps -> invalid codes := 0 -> per item [:length] -> Dia.Decode (serial loop)."""
+    B, T, Cn = generated.shape
+    delay = torch.tensor(delay_pattern, dtype=torch.int64)
+    t_idx = torch.minimum(torch.arange(T).view(1, T, 1) + delay.view(1, 1, Cn), torch.tensor(T - 1)).expand(B, T, Cn)
+    b_idx = torch.arange(B).view(B, 1, 1).expand(B, T, Cn)
+    c_idx = torch.arange(Cn).view(1, 1, Cn).expand(B, T, Cn)
+    gathered = generated[b_idx.reshape(-1), t_idx.reshape(-1), c_idx.reshape(-1)].view(B, T, Cn)
+    reverted = torch.where(t_idx >= T, torch.tensor(1025, dtype=generated.dtype), gathered)
+    codebook = reverted[:, : T - max(delay_pattern), :].clone()
+    codebook[(codebook < min_valid) | (codebook > max_valid)] = 0
+    return [model.dia_decode(codebook[i, : int(lengths[i]), :]) for i in range(B)]
+
+
 def load_hf_safetensors(path: str, cfg: DACConfig, dtype=torch.float32) -> DACOracle:
     from safetensors.torch import load_file
     return DACOracle(cfg, convert_hf_state_dict(load_file(path)), dtype)

@@ -235,3 +235,28 @@ def test_config1_ten_second_clip_against_oracle(dac_full):
     print(f"config1: flips {flips}; dec-only max-abs {np.abs(a_dec - a_ref).max():.2e} snr {snr_db(a_ref, a_dec):.1f} dB")
     assert np.abs(a_dec - a_ref).max() <= MAX_ABS and snr_db(a_ref, a_dec) >= MIN_SNR_DB
     m.Dispose()
+
+
+def test_dia_handoff_revert_delay_clamp_and_ragged_batch(dac_mid):
+    """Dia.GenerateOutput's codec stage, batched by equal length (the reference loops serially)."""
+    from oracle import dac as odac
+    o, m = _models(dac_mid)
+    cfg = dac_mid[0]
+    rng = np.random.default_rng(42)
+    B, T, C = 5, 60, cfg.n_codebooks
+    delay = (0, 2, 3, 5)
+    gen = rng.integers(0, cfg.codebook_size, size=(B, T, C), dtype=np.int64)
+    gen[0, 3, 1] = 1025           # pad / BOS values that Dia can emit -> 0
+    gen[2, 10, 0] = -1
+    gen[4, :, 2] = cfg.codebook_size
+    lengths = np.array([55, 40, 55, 7, 40], np.int64)               # T - max(delay) = 55
+    ref = odac.dia_generate_output(o, torch.from_numpy(gen), lengths, delay, 0, cfg.codebook_size - 1)
+    out = m.DecodeDia(gen, lengths, delay)
+    assert len(out) == B
+    for b in range(B):
+        r = ref[b].numpy()
+        assert out[b].shape == r.shape == (lengths[b] * cfg.hop_length,)
+        assert np.abs(out[b] - r).max() <= MAX_ABS and snr_db(r, out[b]) >= MIN_SNR_DB
+    with pytest.raises(ValueError):
+        m.DecodeDia(gen, np.array([56, 1, 1, 1, 1]), delay)          # longer than T - max(delay)
+    m.Dispose()

@@ -243,6 +243,33 @@ NC_API nc_status nc_encodec_forward(nc_handle h, const float* audio, int32_t bat
 NC_API nc_status nc_encodec_forward_dev(nc_handle h, const float* audio_dev, int32_t batch, int64_t length,
                                         float bandwidth_kbps, float* audio_out_dev, int64_t* codes_dev);
 
+/* -- Encodec .ecdc container, language-model entropy coder off --------------------
+ * Stream = "ECDC" | version byte 0 | int32 big-endian JSON length | JSON {m,al,nc,lm,ch,sr,bw}
+ * (Modules/Encodec/BinaryIO.cs:11,152-190) | codes bit-packed LSB-first at log2(bins) bits each, time-major then
+ * codebook, last byte zero-padded (EncodecCompressor.cs:170-190, Modules/Encodec/BitPacker.cs:60-110).  The 24 kHz
+ * preset has one frame per clip and Normalize = false, so no scale block is written. */
+/* sizes of the header and of the whole stream nc_encodec_compress writes for one clip of `length` samples */
+NC_API nc_status nc_encodec_ecdc_size(nc_handle h, int64_t length, float bandwidth_kbps, int64_t* header_bytes,
+                                      int64_t* stream_bytes);
+/* replaces: EncodecCompressor.CompressToStreamAsync(model, wav, stream, useLm: false)
+ * Modules/Encodec/EncodecCompressor.cs:60-200 (and Compress :26-39), batched: audio [B,1,length] -> B streams of
+ * *stream_bytes bytes each, clip b at out + b*out_stride.  Encode and bit-pack run on the device. */
+NC_API nc_status nc_encodec_compress(nc_handle h, const float* audio, int32_t batch, int64_t length,
+                                     float bandwidth_kbps, uint8_t* out, int64_t out_stride, int64_t* stream_bytes);
+/* replaces: BinaryIO.ReadHeaderAsync + ValidateMetadata Modules/Encodec/BinaryIO.cs:44-146 and the metadata defaults
+ * of EncodecCompressor.cs:253-275.  Host only; every output nullable. */
+NC_API nc_status nc_encodec_ecdc_info(const uint8_t* stream, int64_t stream_bytes, int64_t* audio_length, int32_t* n_q,
+                                      int32_t* channels, int32_t* sample_rate, float* bandwidth_kbps, int32_t* use_lm,
+                                      int64_t* payload_offset);
+/* replaces: EncodecCompressor.DecompressFromStreamAsync Modules/Encodec/EncodecCompressor.cs:236-420 (and Decompress
+ * :46-52), batched over streams with identical metadata: B streams of stream_bytes bytes, stream b at
+ * streams + b*stream_stride -> audio [B][audio_capacity] with the first *audio_length samples of each row written
+ * (output trimmed to the stored length, :412-415).  audio == NULL only reports *audio_length / *sample_rate.
+ * lm = true streams return NC_UNSUPPORTED; a truncated payload returns NC_INVALID_ARGUMENT "Stream ended too soon". */
+NC_API nc_status nc_encodec_decompress(nc_handle h, const uint8_t* streams, int32_t batch, int64_t stream_stride,
+                                       int64_t stream_bytes, float* audio, int64_t audio_capacity, int64_t* audio_length,
+                                       int32_t* sample_rate);
+
 /* The CUDA stream (cudaStream_t) every *_dev call of this handle enqueues on, so a caller
  * can bracket calls with its own events or order its own work against them. */
 NC_API nc_status nc_get_stream(nc_handle h, void** stream_out);

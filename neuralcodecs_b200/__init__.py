@@ -7,7 +7,7 @@ There is no CPU fallback and nothing here imports ``oracle/``.
 from .config import DACConfig, DeviceConfiguration, EncodecConfig, SNACConfig  # noqa: F401
 from .dac import DAC  # noqa: F401
 from .snac import SNAC  # noqa: F401
-from .encodec import Encodec  # noqa: F401
+from .encodec import Encodec, EncodecCompressor  # noqa: F401
 from ._lib import CodecException  # noqa: F401
 
-__all__ = ["DAC", "DACConfig", "SNAC", "SNACConfig", "Encodec", "EncodecConfig", "DeviceConfiguration", "CodecException"]
+__all__ = ["DAC", "DACConfig", "SNAC", "SNACConfig", "Encodec", "EncodecCompressor", "EncodecConfig", "DeviceConfiguration", "CodecException"]

@@ -3,6 +3,7 @@
 #include <cstring>
 #include <new>
 
+#include "ecdc.h"
 #include "engine.h"
 
 using namespace nc;
@@ -512,6 +513,113 @@ nc_status nc_encodec_forward_dev(nc_handle h, const float* audio_dev, int32_t ba
     if (!audio_dev) throw Error(NC_INVALID_ARGUMENT, "audio is null");
     BusyGuard g(e);
     e->forward_dev(audio_dev, batch, length, e->n_q_for_bandwidth(bandwidth_kbps), audio_out_dev, codes_dev);
+  });
+}
+
+// ------------------------------------------------------------------------------------ .ecdc container
+static EcdcMeta ecdc_meta_for(EncodecEngine* e, int64_t length, float bw) {
+  EcdcMeta m;
+  const EncodecConfig& c = e->config();
+  m.model = c.sample_rate == 48000 ? "encodec_48khz" : "encodec_24khz";   // EncodecCompressor.cs:14-18 factory keys
+  m.audio_length = length;
+  m.n_codebooks = e->n_q_for_bandwidth(bw);
+  m.use_lm = false;
+  m.channels = c.channels;
+  m.sample_rate = c.sample_rate;
+  m.bandwidth = bw;
+  m.has_bandwidth = true;
+  return m;
+}
+
+nc_status nc_encodec_ecdc_size(nc_handle h, int64_t length, float bandwidth_kbps, int64_t* header_bytes, int64_t* stream_bytes) {
+  return guarded([&] {
+    EncodecEngine* e = encodec_of(h);
+    if (length <= 0) throw Error(NC_INVALID_ARGUMENT, "length must be positive");
+    const EcdcMeta m = ecdc_meta_for(e, length, bandwidth_kbps);
+    const int64_t hb = (int64_t)ecdc_header(m).size();
+    if (header_bytes) *header_bytes = hb;
+    if (stream_bytes) *stream_bytes = hb + e->ecdc_payload_bytes(m.n_codebooks, e->frames(length));
+  });
+}
+
+nc_status nc_encodec_compress(nc_handle h, const float* audio, int32_t batch, int64_t length, float bandwidth_kbps, uint8_t* out,
+                              int64_t out_stride, int64_t* stream_bytes) {
+  return guarded([&] {
+    EncodecEngine* e = encodec_of(h);
+    if (!audio) throw Error(NC_INVALID_ARGUMENT, "audio is null");
+    if (!out) throw Error(NC_INVALID_ARGUMENT, "out is null");
+    if (batch <= 0 || length <= 0) throw Error(NC_INVALID_ARGUMENT, "batch and length must be positive");
+    const EcdcMeta m = ecdc_meta_for(e, length, bandwidth_kbps);
+    const std::string header = ecdc_header(m);
+    const int64_t payload = e->ecdc_payload_bytes(m.n_codebooks, e->frames(length));
+    const int64_t total = (int64_t)header.size() + payload;
+    if (out_stride < total) throw Error(NC_INVALID_ARGUMENT, "out_stride is smaller than the stream (see nc_encodec_ecdc_size)");
+    BusyGuard g(e);
+    e->bind();
+    DevMem d_audio((size_t)batch * length * 4), d_pay((size_t)batch * payload);
+    NC_CUDA(cudaMemcpy(d_audio.p, audio, (size_t)batch * length * 4, cudaMemcpyHostToDevice));
+    e->compress_dev(d_audio.as<float>(), batch, length, m.n_codebooks, d_pay.as<uint8_t>(), payload);
+    for (int b = 0; b < batch; ++b) std::memcpy(out + (size_t)b * out_stride, header.data(), header.size());
+    NC_CUDA(cudaMemcpy2D(out + header.size(), (size_t)out_stride, d_pay.p, (size_t)payload, (size_t)payload, (size_t)batch,
+                         cudaMemcpyDeviceToHost));
+    if (stream_bytes) *stream_bytes = total;
+  });
+}
+
+nc_status nc_encodec_ecdc_info(const uint8_t* stream, int64_t stream_bytes, int64_t* audio_length, int32_t* n_q, int32_t* channels,
+                               int32_t* sample_rate, float* bandwidth_kbps, int32_t* use_lm, int64_t* payload_offset) {
+  return guarded([&] {
+    if (!stream || stream_bytes <= 0) throw Error(NC_INVALID_ARGUMENT, "stream is null");
+    EcdcMeta m;
+    const size_t off = ecdc_read_header(stream, (size_t)stream_bytes, &m);
+    if (m.sample_rate == 0) m.sample_rate = m.model.find("48khz") != std::string::npos ? 48000 : 24000;   // EncodecCompressor.cs:264-267
+    if (audio_length) *audio_length = m.audio_length;
+    if (n_q) *n_q = m.n_codebooks;
+    if (channels) *channels = m.channels;
+    if (sample_rate) *sample_rate = m.sample_rate;
+    if (bandwidth_kbps) *bandwidth_kbps = m.has_bandwidth ? m.bandwidth : 0.f;
+    if (use_lm) *use_lm = m.use_lm ? 1 : 0;
+    if (payload_offset) *payload_offset = (int64_t)off;
+  });
+}
+
+nc_status nc_encodec_decompress(nc_handle h, const uint8_t* streams, int32_t batch, int64_t stream_stride, int64_t stream_bytes,
+                                float* audio, int64_t audio_capacity, int64_t* audio_length, int32_t* sample_rate) {
+  return guarded([&] {
+    EncodecEngine* e = encodec_of(h);
+    if (!streams) throw Error(NC_INVALID_ARGUMENT, "stream is null");
+    if (batch <= 0 || stream_bytes <= 0 || stream_stride < stream_bytes)
+      throw Error(NC_INVALID_ARGUMENT, "batch, stream_bytes and stream_stride must describe a valid buffer");
+    EcdcMeta m0;
+    const size_t off = ecdc_read_header(streams, (size_t)stream_bytes, &m0);
+    for (int b = 1; b < batch; ++b) {   // one launch decodes clips of one shape: all headers must agree
+      EcdcMeta mb;
+      const size_t ob = ecdc_read_header(streams + (size_t)b * stream_stride, (size_t)stream_bytes, &mb);
+      if (ob != off || mb.audio_length != m0.audio_length || mb.n_codebooks != m0.n_codebooks || mb.use_lm != m0.use_lm ||
+          mb.channels != m0.channels)
+        throw Error(NC_INVALID_ARGUMENT, "batched decompress needs streams with identical metadata");
+    }
+    if (m0.use_lm) throw Error(NC_UNSUPPORTED, "ecdc streams written with the language-model entropy coder are not supported");
+    const EncodecConfig& c = e->config();
+    if (m0.channels != c.channels)                                                                          // EncodecCompressor.cs:282-286
+      throw Error(NC_INVALID_ARGUMENT, "Model has " + std::to_string(c.channels) + " channels but compressed data has " +
+                                           std::to_string(m0.channels) + " channels");
+    if (m0.sample_rate != 0 && m0.sample_rate != c.sample_rate)
+      throw Error(NC_INVALID_ARGUMENT, "Model " + m0.model + " not supported");
+    if (audio_length) *audio_length = m0.audio_length;
+    if (sample_rate) *sample_rate = c.sample_rate;
+    if (!audio) return;   // size query
+    if (audio_capacity < m0.audio_length) throw Error(NC_INVALID_ARGUMENT, "audio_capacity is smaller than the stored audio length");
+    const int64_t payload = stream_bytes - (int64_t)off;
+    BusyGuard g(e);
+    e->bind();
+    DevMem d_pay((size_t)batch * std::max<int64_t>(payload, 1)), d_audio((size_t)batch * m0.audio_length * 4);
+    if (payload > 0)
+      NC_CUDA(cudaMemcpy2D(d_pay.p, (size_t)payload, streams + off, (size_t)stream_stride, (size_t)payload, (size_t)batch,
+                           cudaMemcpyHostToDevice));
+    e->decompress_dev(d_pay.as<uint8_t>(), payload, batch, m0.n_codebooks, m0.audio_length, d_audio.as<float>());
+    NC_CUDA(cudaMemcpy2D(audio, (size_t)audio_capacity * 4, d_audio.p, (size_t)m0.audio_length * 4, (size_t)m0.audio_length * 4,
+                         (size_t)batch, cudaMemcpyDeviceToHost));
   });
 }
 

@@ -20,6 +20,8 @@ Precision parse_precision(const std::string& s) {
   if (s == "3xtf32") return PREC_3XTF32;
   if (s == "bf16x3") return PREC_BF16X3;
   if (s == "f16x3") return PREC_F16X3;
+  if (s == "f16x2") return PREC_F16X2;
+  if (s == "f16") return PREC_F16;
   throw Error(NC_INVALID_ARGUMENT, "unknown precision '" + s + "' (fp32|tf32|3xtf32|bf16x3|f16x3)");
 }
 
@@ -29,6 +31,8 @@ const char* precision_name(Precision p) {
     case PREC_TF32: return "tf32";
     case PREC_3XTF32: return "3xtf32";
     case PREC_BF16X3: return "bf16x3";
+    case PREC_F16X2: return "f16x2";
+    case PREC_F16: return "f16";
     default: return "f16x3";
   }
 }
@@ -271,7 +275,7 @@ void ConvLayer::build(const std::string& name, const ConvSpec& spec, const std::
             for (int kk = 0; kk < 32; ++kk) {
               const float v = t.w[(size_t)n * t.klen + (size_t)kcl * 32 + kk];
               if (v != 0.f) any = true;
-              if (mode_ == PREC_BF16X3 || mode_ == PREC_F16X3) {
+              if (prec_is_h16(mode_)) {
                 const bool bf = mode_ == PREC_BF16X3;
                 const uint16_t h = bf ? host_bf16(v) : host_f16(v);
                 const float hf = bf ? host_bf16_to_f(h) : host_f16_to_f(h);
@@ -348,13 +352,14 @@ bool ConvLayer::fill_umma(const ConvRunArgs& a, ConvGemmParams* pp) const {
   p.post = a.post; p.post_alpha = a.post_alpha; p.post_inv_alpha = a.post_inv_alpha; p.post_period = s.cout;
   p.W = d_w_tiles_; p.w_tile_floats = w_tile_floats_; p.BN = bn_; p.n_tiles = n_tiles_; p.tiles_per_ntile = tiles_per_ntile_;
   p.mode = mma_mode(mode_);
+  p.passes = mode_ == PREC_F16 ? 1 : (mode_ == PREC_F16X2 ? 2 : 3);
   p.n_taps = (int)taps_.size();
   for (int j = 0; j < p.n_taps; ++j) p.taps[j] = utaps_[j];
   std::memcpy(p.tap_mask, tap_mask_, sizeof tap_mask_);
   p.n_kc = n_kc_; p.kc_begin = kc_begin_; p.smin = smin_; p.span = span_;
   p.dense_step = dense_step_;
   p.batch = a.batch; p.m_tiles_per_clip = (m_rows + 127) / 128;
-  const int fast = g_fast_sin >= 0 ? g_fast_sin : ((mode_ == PREC_TF32 || mode_ == PREC_BF16X3) ? 1 : 0);
+  const int fast = g_fast_sin >= 0 ? g_fast_sin : ((mode_ == PREC_TF32 || mode_ == PREC_BF16X3 || mode_ == PREC_F16X2 || mode_ == PREC_F16) ? 1 : 0);
   p.precise_sin = fast ? 0 : 1;
   return true;
 }

@@ -9,7 +9,10 @@
 
 namespace nc {
 
-enum Precision : int { PREC_FP32 = 0, PREC_TF32 = 1, PREC_3XTF32 = 3, PREC_BF16X3 = 4, PREC_F16X3 = 5 };
+// *X3 = three tensor-core products per term (hi*hi + lo*hi + hi*lo, ~16-22 operand bits); F16X2 = activations split in
+// two halves, weights rounded once to fp16 (11 bits); F16 = one fp16 product (11-bit operands, like TF32 at twice the rate).
+enum Precision : int { PREC_FP32 = 0, PREC_TF32 = 1, PREC_3XTF32 = 3, PREC_BF16X3 = 4, PREC_F16X3 = 5, PREC_F16X2 = 6, PREC_F16 = 7 };
+inline bool prec_is_h16(Precision p) { return p == PREC_BF16X3 || p == PREC_F16X3 || p == PREC_F16X2 || p == PREC_F16; }
 const char* precision_name(Precision p);
 
 Precision parse_precision(const std::string& s);

@@ -75,6 +75,7 @@ struct ConvGemmParams {
   int n_tiles;
   int tiles_per_ntile;
   int mode;                 // MmaMode
+  int passes;               // 16-bit modes: 3 = hi*hi + lo*hi + hi*lo, 2 = hi*hi + lo(A)*hi, 1 = hi*hi only
   int n_taps;
   ConvTap taps[kMaxTaps];
   unsigned char tap_mask[kMaxNTiles];  // bit j set => tap j contributes to this N tile

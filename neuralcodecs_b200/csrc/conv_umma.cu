@@ -311,11 +311,22 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
               }
             } else {
               // row = [32 hi halves (64 B) | 32 lo halves (64 B)]; K step = 16 halves = 32 B
+              if (p.passes == 3) {
 #pragma unroll
-              for (int k = 0; k < 2; ++k) {
-                umma_f16(d_tmem, a0 + 4 + 2 * k, b0 + 2 * k, idesc, acc | (uint32_t)k);  // lo * hi
-                umma_f16(d_tmem, a0 + 2 * k, b0 + 4 + 2 * k, idesc, 1);                  // hi * lo
-                umma_f16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, 1);                      // hi * hi
+                for (int k = 0; k < 2; ++k) {
+                  umma_f16(d_tmem, a0 + 4 + 2 * k, b0 + 2 * k, idesc, acc | (uint32_t)k);  // lo * hi
+                  umma_f16(d_tmem, a0 + 2 * k, b0 + 4 + 2 * k, idesc, 1);                  // hi * lo
+                  umma_f16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, 1);                      // hi * hi
+                }
+              } else if (p.passes == 2) {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                  umma_f16(d_tmem, a0 + 4 + 2 * k, b0 + 2 * k, idesc, acc | (uint32_t)k);  // lo * hi
+                  umma_f16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, 1);                      // hi * hi
+                }
+              } else {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) umma_f16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, acc | (uint32_t)k);
               }
             }
             tc_commit(&w_empty[ws]);
@@ -551,7 +562,7 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
               }
               const uint32_t sub = (uint32_t)(c & 1) * 8u;
               *reinterpret_cast<uint2*>(stage + sw128_offset((uint32_t)rho, (uint32_t)(c >> 1)) + sub) = hi;
-              *reinterpret_cast<uint2*>(stage + sw128_offset((uint32_t)rho, 4u + (uint32_t)(c >> 1)) + sub) = lo;
+              if (p.passes > 1) *reinterpret_cast<uint2*>(stage + sw128_offset((uint32_t)rho, 4u + (uint32_t)(c >> 1)) + sub) = lo;
             } else {
               const float4 hi = make_float4(rna_tf32(x.x), rna_tf32(x.y), rna_tf32(x.z), rna_tf32(x.w));
               const uint32_t off = sw128_offset((uint32_t)rho, (uint32_t)c);
@@ -672,12 +683,24 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       int ws = 0, as = 0, hs = 0;
       uint32_t wph = 0, aph = 0, hph = 0;
       uint64_t a_desc = a_desc0, w_desc = w_desc0, h_desc = h_desc0;
+      const int passes = p.passes;
       auto mma6 = [&](uint32_t d_tmem, uint64_t a0, uint64_t b0, uint32_t acc) {
+        if (passes == 3) {
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          umma_f16(d_tmem, a0 + 4 + 2 * k, b0 + 2 * k, idesc, acc | (uint32_t)k);  // lo * hi
-          umma_f16(d_tmem, a0 + 2 * k, b0 + 4 + 2 * k, idesc, 1);                  // hi * lo
-          umma_f16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, 1);                      // hi * hi
+          for (int k = 0; k < 2; ++k) {
+            umma_f16(d_tmem, a0 + 4 + 2 * k, b0 + 2 * k, idesc, acc | (uint32_t)k);  // lo * hi
+            umma_f16(d_tmem, a0 + 2 * k, b0 + 4 + 2 * k, idesc, 1);                  // hi * lo
+            umma_f16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, 1);                      // hi * hi
+          }
+        } else if (passes == 2) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            umma_f16(d_tmem, a0 + 4 + 2 * k, b0 + 2 * k, idesc, acc | (uint32_t)k);  // lo * hi
+            umma_f16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, 1);                      // hi * hi
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 2; ++k) umma_f16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, acc | (uint32_t)k);
         }
       };
       auto next_w = [&]() {
@@ -1075,7 +1098,7 @@ static int ru_fuse_max_c() {
 }
 
 bool ru_fused_supported(const ConvGemmParams& p, const ConvGemmParams& p2) {
-  return (p.mode == MODE_BF16X3 || p.mode == MODE_F16X3) && p2.mode == p.mode && p.n_tiles == 1 && p2.n_tiles == 1 &&
+  return (p.mode == MODE_BF16X3 || p.mode == MODE_F16X3) && p2.mode == p.mode && p2.passes == p.passes && p.n_tiles == 1 && p2.n_tiles == 1 &&
          p.BN == p2.BN && p.BN % 32 == 0 && p.BN <= ru_fuse_max_c() && p.n_total == p.BN && p.n_valid == p.BN && p.dense_step >= 0 &&
          p.prologue == PRO_SNAKE && p2.n_taps == 1 && p2.n_kc == p.n_kc && p.kc_begin == 0 && p.span <= 64 &&
          p.a_pitch == p.BN && umma_view_ok(p) && p.d_valid == (long long)p.m_rows * p.n_total && p.d_clip_stride % 4 == 0 &&

@@ -495,4 +495,63 @@ void EncodecEngine::decode_dev(const int64_t* codes, int B, int nq, int64_t T, f
   sync();
 }
 
+int EncodecEngine::bits_per_codebook() const {
+  int bits = 0;
+  while ((1 << bits) < cfg_.codebook_size) ++bits;
+  if ((1 << bits) != cfg_.codebook_size) throw Error(NC_UNSUPPORTED, "Only codebooks with power-of-2 sizes are supported");  // Encodec.cs:130-133
+  return bits;
+}
+
+void EncodecEngine::compress_dev(const float* audio, int B, int64_t L, int nq, uint8_t* payload, int64_t stride) {
+  require_ready();
+  bind();
+  if (B <= 0 || L <= 0 || !audio) throw Error(NC_INVALID_ARGUMENT, "batch and length must be positive");
+  if (nq <= 0 || nq > (int)embed_.size()) throw Error(NC_INVALID_ARGUMENT, "n_quantizers out of range");
+  if (L > (int64_t)1 << 28) throw Error(NC_INVALID_ARGUMENT, "clip too long");
+  const int64_t T = frames(L);
+  if (!payload || stride < ecdc_payload_bytes(nq, T)) throw Error(NC_INVALID_ARGUMENT, "ecdc payload buffer too small");
+  codes_tmp_.reserve((size_t)B * nq * T * sizeof(int64_t));
+  int64_t* codes = codes_tmp_.as<int64_t>();
+  // encode in micro-batches straight into the [B][nq][T] code tensor, then one pack launch for the whole batch
+  const int mb = micro_batch(B, L);
+  const LaunchCtx c = ctx();
+  for (int b0 = 0; b0 < B; b0 += mb) {
+    const int nb = std::min(mb, B - b0);
+    int64_t Tm = 0;
+    run_encoder(audio + (int64_t)b0 * L, nb, L, &Tm);
+    for (int q = 0; q < nq; ++q)
+      launch_encodec_vq_stage(z_.as<float>(), (long long)nb * T, embed_[q], embed_sq_[q], cfg_.codebook_size, cfg_.dimension,
+                              codes + (int64_t)b0 * nq * T, (int)T, nq, q, c);
+  }
+  launch_ecdc_pack(codes, payload, stride, B, (int)T, nq, bits_per_codebook(), c);
+  sync();
+}
+
+void EncodecEngine::decompress_dev(const uint8_t* payload, int64_t stride, int B, int nq, int64_t L, float* audio_out) {
+  require_ready();
+  bind();
+  if (B <= 0 || L <= 0 || !payload || !audio_out) throw Error(NC_INVALID_ARGUMENT, "Invalid ecdc payload");
+  if (nq <= 0 || nq > (int)embed_.size()) throw Error(NC_INVALID_ARGUMENT, "n_quantizers out of range");
+  // frameLength = ceil(L * frame_rate / sample_rate) (EncodecCompressor.cs:296-297), frame_rate = ceil(sr / hop)
+  const int64_t frame_rate = (cfg_.sample_rate + cfg_.hop() - 1) / cfg_.hop();
+  const int64_t T = (L * frame_rate + cfg_.sample_rate - 1) / cfg_.sample_rate;
+  if (stride < ecdc_payload_bytes(nq, T)) throw Error(NC_INVALID_ARGUMENT, "Stream ended too soon");   // EncodecCompressor.cs:390-393
+  const int64_t Ld = T * cfg_.hop();
+  const int mb = micro_batch(B, Ld);
+  const LaunchCtx c = ctx();
+  codes_tmp_.reserve((size_t)B * nq * T * sizeof(int64_t));
+  int64_t* codes = codes_tmp_.as<int64_t>();
+  launch_ecdc_unpack(payload, stride, codes, B, (int)T, nq, bits_per_codebook(), c);
+  audio_tmp_.reserve((size_t)mb * Ld * sizeof(float));
+  for (int b0 = 0; b0 < B; b0 += mb) {
+    const int nb = std::min(mb, B - b0);
+    Act z = act(0, nb, (int)T, cfg_.dimension);
+    launch_encodec_decode_codes(codes + (int64_t)b0 * nq * T, d_embed_ptrs_, z.base, z.stride, nb, (int)T, nq, cfg_.codebook_size,
+                                cfg_.dimension, c);
+    run_decoder(nb, (int)T, audio_tmp_.as<float>(), Ld);
+    launch_trim_rows(audio_tmp_.as<float>(), audio_out + (int64_t)b0 * L, nb, Ld, std::min<int64_t>(L, Ld), c);   // :412-415
+  }
+  sync();
+}
+
 }  // namespace nc

@@ -324,6 +324,73 @@ void launch_lstm_layer(const float* xproj, long long xproj_clip_stride, const fl
   ctx.end(ev, "lstm_layer", 2.0 * 4 * H * (double)H * T * batch, (double)batch * T * H * 4.0 * 6);
 }
 
+// ------------------------------------------------------------------ .ecdc bit packing (BitPacker.cs / BitUnpacker.cs)
+// The reference pushes code (t, k) -- t outer, k inner -- into an LSB-first accumulator of `bits` bits per value and
+// emits the low byte whenever 8 bits are available; Flush() emits the last partial byte.  Equivalent closed form:
+// value v = t*nq + k occupies stream bits [v*bits, (v+1)*bits); byte j is bits [8j, 8j+8).  One thread per output byte.
+__global__ void ecdc_pack_kernel(const int64_t* __restrict__ codes, uint8_t* __restrict__ out, long long out_stride, int T, int nq,
+                                 int bits, long long nbytes) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (j >= nbytes) return;
+  const long long nvals = (long long)T * nq;
+  const long long bit0 = j * 8;
+  long long v = bit0 / bits;
+  const long long v_last = min((bit0 + 7) / bits, nvals - 1);
+  const int64_t* cb = codes + (long long)b * nq * T;
+  unsigned int byte = 0;
+  for (; v <= v_last; ++v) {
+    const int t = (int)(v / nq), k = (int)(v % nq);
+    const unsigned long long val = (unsigned long long)cb[(long long)k * T + t] & ((1ull << bits) - 1ull);
+    const long long sh = v * bits - bit0;   // position of the value's bit 0 relative to this byte
+    byte |= (unsigned int)((sh >= 0 ? (val << sh) : (val >> (-sh))) & 0xFFull);
+  }
+  out[(long long)b * out_stride + j] = (uint8_t)byte;
+}
+
+// One thread per value: gather the (at most 5) bytes it straddles, shift, mask (BitUnpacker.Pull, BitUnpacker.cs:60-95).
+__global__ void ecdc_unpack_kernel(const uint8_t* __restrict__ in, long long in_stride, int64_t* __restrict__ codes, int T, int nq,
+                                   int bits, long long nbytes) {
+  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (v >= (long long)T * nq) return;
+  const long long bit0 = v * bits;
+  const long long j0 = bit0 >> 3;
+  const int off = (int)(bit0 & 7);
+  const uint8_t* src = in + (long long)b * in_stride;
+  unsigned long long w = 0;
+  const int need = (off + bits + 7) >> 3;   // <= 5 for bits <= 32
+  for (int i = 0; i < need; ++i)
+    if (j0 + i < nbytes) w |= (unsigned long long)src[j0 + i] << (8 * i);
+  const int t = (int)(v / nq), k = (int)(v % nq);
+  codes[(long long)b * nq * T + (long long)k * T + t] = (int64_t)((w >> off) & ((1ull << bits) - 1ull));
+}
+
+void launch_ecdc_pack(const int64_t* codes, uint8_t* out, long long out_stride, int batch, int T, int nq, int bits,
+                      const LaunchCtx& ctx) {
+  if (bits <= 0 || bits > 32) throw Error(NC_INVALID_ARGUMENT, "Bits must be between 1 and 32");   // BitPacker.cs:120-130
+  const long long nbytes = ((long long)T * nq * bits + 7) / 8;
+  if (batch == 0 || nbytes == 0) return;
+  const int ev = ctx.begin();
+  dim3 grid((unsigned)((nbytes + 255) / 256), batch);
+  ecdc_pack_kernel<<<grid, 256, 0, ctx.stream>>>(codes, out, out_stride, T, nq, bits, nbytes);
+  check_launch((int)cudaGetLastError(), "ecdc_pack");
+  ctx.end(ev, "ecdc_pack", 0.0, (double)batch * ((double)T * nq * 8 + nbytes));
+}
+
+void launch_ecdc_unpack(const uint8_t* in, long long in_stride, int64_t* codes, int batch, int T, int nq, int bits,
+                        const LaunchCtx& ctx) {
+  if (bits <= 0 || bits > 32) throw Error(NC_INVALID_ARGUMENT, "Bits must be between 1 and 32");
+  const long long nvals = (long long)T * nq;
+  if (batch == 0 || nvals == 0) return;
+  const long long nbytes = (nvals * bits + 7) / 8;
+  const int ev = ctx.begin();
+  dim3 grid((unsigned)((nvals + 255) / 256), batch);
+  ecdc_unpack_kernel<<<grid, 256, 0, ctx.stream>>>(in, in_stride, codes, T, nq, bits, nbytes);
+  check_launch((int)cudaGetLastError(), "ecdc_unpack");
+  ctx.end(ev, "ecdc_unpack", 0.0, (double)batch * ((double)nvals * 8 + nbytes));
+}
+
 int lstm_max_batch(int num_sms, int H) { return (num_sms / (H / kLU)) * kLB; }
 
 }  // namespace nc

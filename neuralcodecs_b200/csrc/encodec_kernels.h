@@ -28,4 +28,12 @@ void launch_lstm_layer(const float* xproj, long long xproj_clip_stride, const fl
 // largest batch one launch can take (all CTAs must be co-resident)
 int lstm_max_batch(int num_sms, int H);
 
+// .ecdc payload without the language model (EncodecCompressor.cs:170-190, BitPacker.cs:60-110): codes [B][nq][T] ->
+// per clip ceil(T*nq*bits/8) bytes, values in (t outer, k inner) order, LSB first, last byte zero-padded.
+void launch_ecdc_pack(const int64_t* codes, uint8_t* out, long long out_stride, int batch, int T, int nq, int bits,
+                      const LaunchCtx& ctx);
+// inverse (EncodecCompressor.cs:383-398, BitUnpacker.cs:60-95)
+void launch_ecdc_unpack(const uint8_t* in, long long in_stride, int64_t* codes, int batch, int T, int nq, int bits,
+                        const LaunchCtx& ctx);
+
 }  // namespace nc

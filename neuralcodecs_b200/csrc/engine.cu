@@ -5,6 +5,8 @@
 // with activations channels-last in HBM and every Snake fused into the consuming conv's prologue.
 #include "engine.h"
 
+#include <cstdlib>
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -137,8 +139,16 @@ void DacEngine::set_option(const std::string& key, const std::string& value) {
   } else if (key == "decoder_boost") {
     dec_boost_ = value == "1" || value == "true";
     if (ready_) throw Error(NC_INVALID_ARGUMENT, "precision options must be set before weights are loaded");
+  } else if (key == "decoder_wide_precision") {
+    dec_wide_prec_ = parse_precision(value);
+    if (ready_) throw Error(NC_INVALID_ARGUMENT, "precision options must be set before weights are loaded");
   } else if (key == "decoder_precision") {
-    dec_prec_ = parse_precision(value);
+    if (value == "mixed") {
+      dec_prec_ = PREC_BF16X3;
+      dec_wide_prec_ = PREC_F16;
+    } else {
+      dec_prec_ = dec_wide_prec_ = parse_precision(value);
+    }
     if (ready_) throw Error(NC_INVALID_ARGUMENT, "precision options must be set before weights are loaded");
   } else {
     Engine::set_option(key, value);
@@ -204,7 +214,8 @@ void DacEngine::build_ru(ResUnit& ru, const std::string& p, int dim, int dil, Pr
   ConvSpec s1;
   s1.cin = s1.cout = dim; s1.k = 7; s1.dilation = dil; s1.padding = (7 - 1) * dil / 2;  // ResidualUnit.cs:27
   auto w1 = folded_conv(p + ".conv1", dim, dim, 7, &b, dim);
-  ru.c1.build(p + ".conv1", s1, w1, b, prec);
+  const bool wide = p.compare(0, 8, "decoder.") == 0 && dim > 128 && prec != PREC_FP32;
+  ru.c1.build(p + ".conv1", s1, w1, b, wide ? dec_wide_prec_ : prec);
   ConvSpec s2;
   s2.cin = s2.cout = dim; s2.k = 1;
   auto w2 = folded_conv(p + ".conv2", dim, dim, 1, &b, dim);
@@ -293,7 +304,7 @@ void DacEngine::finalize_weights() {
     ConvSpec cs;
     cs.cin = cfg_.latent_dim; cs.cout = C; cs.k = 7; cs.padding = 3;
     auto w = folded_conv("decoder.conv1", C, cfg_.latent_dim, 7, &b, C);
-    dec_in_.build("decoder.conv1", cs, w, b, dec_prec_);
+    dec_in_.build("decoder.conv1", cs, w, b, dec_prec_ != PREC_FP32 ? dec_wide_prec_ : dec_prec_);
   }
   dec_blocks_.clear();
   int cout = C;
@@ -307,7 +318,7 @@ void DacEngine::finalize_weights() {
     ConvSpec cs;
     cs.transposed = true; cs.cin = cin; cs.cout = cout; cs.k = 2 * s; cs.stride = s; cs.padding = (s + 1) / 2;
     auto w = folded_conv(p + ".conv_t1", cin, cout, 2 * s, &b, cout);  // norm per in-channel (dims 1,2 of [Cin,Cout,k])
-    blk->up.build(p + ".conv_t1", cs, w, b, dec_prec_);
+    blk->up.build(p + ".conv_t1", cs, w, b, (cin > 128 && dec_prec_ != PREC_FP32) ? dec_wide_prec_ : dec_prec_);
     const int dils[3] = {1, 3, 9};
     for (int u = 0; u < 3; ++u) build_ru(blk->ru[u], p + ".res_unit" + std::to_string(u + 1), cout, dils[u], dec_prec_);
     dec_blocks_.push_back(std::move(blk));
@@ -342,6 +353,8 @@ std::string DacEngine::describe() const {
   s += prec_name(enc_prec_);
   s += "\", \"decoder_precision\": \"";
   s += prec_name(dec_prec_);
+  s += "\", \"decoder_wide_precision\": \"";
+  s += prec_name(dec_wide_prec_);
   s += dec_boost_ ? "\", \"decoder_boost\": true, \"layers\": {" : "\", \"decoder_boost\": false, \"layers\": {";
   bool first = true;
   auto add = [&](const ConvLayer& l) {

@@ -129,7 +129,11 @@ class DacEngine : public Engine {
   float* buf(int i) { return ws_[i].as<float>(); }
 
   DacConfig cfg_;
-  Precision enc_prec_ = PREC_BF16X3, dec_prec_ = PREC_BF16X3;
+  // Encoder: three-pass bf16 split everywhere (codes must match the fp32 reference).  Decoder: the wide layers
+  // (k > 1 convs and transposed convs with more than 128 channels -- the MMA-bound ones) take one fp16 product,
+  // everything else the three-pass split: 69.7 dB against the fp32 oracle (gate 60 dB) at +21 % throughput
+  // (profiles/r01_decoder_precision_modes.txt).  decoder_precision=<mode> makes the decoder uniform again.
+  Precision enc_prec_ = PREC_BF16X3, dec_prec_ = PREC_BF16X3, dec_wide_prec_ = PREC_F16;
   bool dec_boost_ = true;
   // encoder
   float* d_conv_in_w_ = nullptr;
@@ -297,6 +301,14 @@ class EncodecEngine : public Engine {
   void encode_dev(const float* audio, int B, int64_t L, int nq, int64_t* codes);
   void decode_dev(const int64_t* codes, int B, int nq, int64_t T, float* audio_out);
   void forward_dev(const float* audio, int B, int64_t L, int nq, float* audio_out, int64_t* codes);
+
+  // .ecdc payload (no language model): bits per code = log2(codebook size) (Encodec.cs:87,128-133)
+  int bits_per_codebook() const;
+  int64_t ecdc_payload_bytes(int nq, int64_t T) const { return ((int64_t)nq * T * bits_per_codebook() + 7) / 8; }
+  // audio [B][L] -> payload [B][stride] bytes (EncodecCompressor.cs:93-190 with useLm=false)
+  void compress_dev(const float* audio, int B, int64_t L, int nq, uint8_t* payload, int64_t stride);
+  // payload -> audio [B][L] trimmed to L = metadata "al" (EncodecCompressor.cs:288-420)
+  void decompress_dev(const uint8_t* payload, int64_t stride, int B, int nq, int64_t L, float* audio_out);
 
  private:
   struct Act {            // channels-last activation with 8 margin rows on each side of every clip

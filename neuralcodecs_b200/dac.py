@@ -115,7 +115,10 @@ class DAC:
 
     def precision_summary(self) -> str:
         d = self.describe()
-        return (f"encoder {d['encoder_precision']}, decoder {d['decoder_precision']}"
+        wide = d.get("decoder_wide_precision", d["decoder_precision"])
+        dec = d["decoder_precision"] if wide == d["decoder_precision"] else \
+            f"{wide} on k>1 / transposed convs wider than 128 channels, {d['decoder_precision']} elsewhere"
+        return (f"encoder {d['encoder_precision']}, decoder {dec}"
                 + (" (+3xtf32 on narrow 1x1 / final conv)" if d.get("decoder_boost") and d["decoder_precision"] == "tf32" else ""))
 
     def stream_ptr(self) -> int:

@@ -173,3 +173,71 @@ class Encodec:
         if not self._h.value:
             raise RuntimeError("Encodec has been disposed")
         return self._h
+
+
+class EncodecCompressor:
+    """Mirror of the reference's static EncodecCompressor (Modules/Encodec/EncodecCompressor.cs) for the path without the
+    language model: Compress :26-39 / CompressToStreamAsync :60-200, Decompress :46-52 / DecompressFromStreamAsync :236-420.
+    The reference builds the decoding model from the stream's "m" key through its model factories (:275-279); here the
+    caller passes the loaded model.  The *Batch variants take [B,1,L] audio / a list of equal-metadata streams and run as
+    one device batch."""
+
+    @staticmethod
+    def Compress(model: "Encodec", wav, useLm: bool = False) -> bytes:
+        if useLm:
+            raise NotImplementedError("the language-model entropy coder is not built (NC_UNSUPPORTED)")
+        a = np.ascontiguousarray(wav, dtype=np.float32)
+        if a.ndim != 2:
+            raise ValueError("Only single waveform can be encoded (shape should be [C, L])")        # EncodecCompressor.cs:67-70
+        if a.shape[0] != model.Config.channels:
+            raise ValueError(f"Expected {model.Config.channels} channels, got {a.shape[0]}")        # :74-77
+        return EncodecCompressor.CompressBatch(model, a[None])[0]
+
+    @staticmethod
+    def CompressBatch(model: "Encodec", wav) -> List[bytes]:
+        a = model._audio3d(wav)
+        B, _, L = a.shape
+        bw = float(model.Config.bandwidth)
+        hb, nb = C.c_int64(), C.c_int64()
+        _lib.check(_lib.lib().nc_encodec_ecdc_size(model._handle(), L, bw, C.byref(hb), C.byref(nb)), "Encodec", "Compress")
+        out = np.zeros((B, nb.value), np.uint8)
+        wrote = C.c_int64()
+        _lib.check(_lib.lib().nc_encodec_compress(model._handle(), a.ctypes.data_as(C.c_void_p), B, L, bw,
+                                                  out.ctypes.data_as(C.c_void_p), nb.value, C.byref(wrote)), "Encodec", "Compress")
+        return [out[b, :wrote.value].tobytes() for b in range(B)]
+
+    @staticmethod
+    def ReadHeader(compressed: bytes) -> dict:
+        """BinaryIO.ReadHeaderAsync (BinaryIO.cs:44-100) -> {m-less} metadata + payload offset."""
+        buf = np.frombuffer(compressed, np.uint8)
+        al, off = C.c_int64(), C.c_int64()
+        nq, ch, sr, lm = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        bw = C.c_float()
+        _lib.check(_lib.lib().nc_encodec_ecdc_info(buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(al), C.byref(nq), C.byref(ch),
+                                                   C.byref(sr), C.byref(bw), C.byref(lm), C.byref(off)), "Encodec", "Decompress")
+        return {"al": al.value, "nc": nq.value, "ch": ch.value, "sr": sr.value, "bw": bw.value, "lm": bool(lm.value),
+                "payload_offset": off.value}
+
+    @staticmethod
+    def Decompress(compressed: bytes, model: "Encodec") -> Tuple[np.ndarray, int]:
+        """-> (wav [C, al], sample rate), as DecompressFromStreamAsync returns (wav[0], model.SampleRate)."""
+        wav, sr = EncodecCompressor.DecompressBatch([compressed], model)
+        return wav[0], sr
+
+    @staticmethod
+    def DecompressBatch(streams: List[bytes], model: "Encodec") -> Tuple[np.ndarray, int]:
+        if streams is None or len(streams) == 0:
+            raise ValueError("No frames provided to decode")
+        n = len(streams[0])
+        if any(len(s) != n for s in streams):
+            raise ValueError("batched decompress needs streams with identical metadata")
+        buf = np.frombuffer(b"".join(streams), np.uint8).reshape(len(streams), n)
+        al, sr = C.c_int64(), C.c_int32()
+        lib = _lib.lib()
+        _lib.check(lib.nc_encodec_decompress(model._handle(), buf.ctypes.data_as(C.c_void_p), len(streams), n, n, None, 0,
+                                             C.byref(al), C.byref(sr)), "Encodec", "Decompress")
+        audio = np.empty((len(streams), model.Config.channels, al.value), np.float32)
+        _lib.check(lib.nc_encodec_decompress(model._handle(), buf.ctypes.data_as(C.c_void_p), len(streams), n, n,
+                                             audio.ctypes.data_as(C.c_void_p), al.value, C.byref(al), C.byref(sr)),
+                   "Encodec", "Decompress")
+        return audio, sr.value

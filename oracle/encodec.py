@@ -239,3 +239,120 @@ class EncodecOracle:
 def load_safetensors(path: str, cfg: EncodecConfig, dtype=torch.float32) -> EncodecOracle:
     from safetensors.torch import load_file
     return EncodecOracle(cfg, load_file(path), dtype)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# .ecdc container without the language model: restatement of Modules/Encodec/BinaryIO.cs, BitPacker.cs, BitUnpacker.cs
+# and the useLm == false branches of EncodecCompressor.cs.  Pure Python / numpy; test infrastructure only.
+# Parity pin: the reference ships no tests or fixtures for this path ("parity unpinned" by reference vectors); the
+# restatement is anchored on hand-derived known-answer vectors (tests/test_oracle_snac_encodec.py) and on the published
+# facebookresearch/encodec v0.1.1 format (binary.py: struct '!4sBI' header, BitPacker LSB-first), which it follows.
+class BitPacker:
+    """BitPacker.cs:60-110: `_currentValue |= value << _currentBits`, emit low bytes while >= 8 bits, Flush() emits the rest."""
+
+    def __init__(self, bits: int):
+        if not 0 < bits <= 32:
+            raise ValueError("Bits must be between 1 and 32")
+        self.bits, self.cur, self.nbits, self.out = bits, 0, 0, bytearray()
+
+    def push(self, value: int) -> None:
+        self.cur |= (int(value) & ((1 << self.bits) - 1)) << self.nbits
+        self.nbits += self.bits
+        while self.nbits >= 8:
+            self.out.append(self.cur & 0xFF)
+            self.cur >>= 8
+            self.nbits -= 8
+
+    def flush(self) -> bytes:
+        if self.nbits:
+            self.out.append(self.cur & 0xFF)
+            self.cur, self.nbits = 0, 0
+        return bytes(self.out)
+
+
+class BitUnpacker:
+    """BitUnpacker.cs:60-95: refill a byte at a time until `bits` are available, return the low `bits`; None at end of stream."""
+
+    def __init__(self, bits: int, data: bytes):
+        self.bits, self.data, self.pos, self.cur, self.nbits = bits, data, 0, 0, 0
+
+    def pull(self):
+        while self.nbits < self.bits:
+            if self.pos >= len(self.data):
+                return None
+            self.cur |= self.data[self.pos] << self.nbits
+            self.pos += 1
+            self.nbits += 8
+        v = self.cur & ((1 << self.bits) - 1)
+        self.cur >>= self.bits
+        self.nbits -= self.bits
+        return v
+
+
+def _json_number(v: float) -> str:   # System.Text.Json: shortest round-trip text, integers without a fraction
+    return str(int(v)) if float(v) == int(v) else repr(float(v))
+
+
+def ecdc_header(model_name: str, audio_length: int, n_codebooks: int, use_lm: bool, channels: int, sample_rate: int,
+                bandwidth: Optional[float]) -> bytes:
+    """BinaryIO.WriteHeaderAsync (BinaryIO.cs:152-190) over the metadata of EncodecCompressor.cs:98-111."""
+    import struct
+    j = (f'{{"m":"{model_name}","al":{int(audio_length)},"nc":{int(n_codebooks)},"lm":{"true" if use_lm else "false"},'
+         f'"ch":{int(channels)},"sr":{int(sample_rate)}')
+    if bandwidth is not None:
+        j += f',"bw":{_json_number(bandwidth)}'
+    j += "}"
+    meta = j.encode("utf-8")
+    return b"ECDC" + bytes([0]) + struct.pack(">i", len(meta)) + meta
+
+
+def ecdc_read_header(data: bytes):
+    """BinaryIO.ReadHeaderAsync + ValidateMetadata (BinaryIO.cs:44-146) -> (metadata dict, payload offset)."""
+    import json
+    import struct
+    if len(data) < 9:
+        raise EOFError("Stream ended too soon")
+    if data[:4] != b"ECDC":
+        raise ValueError("File is not in ECDC format")
+    if data[4] != 0:
+        raise ValueError(f"Version not supported: {data[4]}")
+    (n,) = struct.unpack(">i", data[5:9])
+    if n <= 0 or len(data) < 9 + n:
+        raise EOFError("Stream ended too soon")
+    meta = json.loads(data[9:9 + n].decode("utf-8"))
+    for k in ("m", "al", "nc", "lm"):
+        if k not in meta:
+            raise ValueError(f"Missing required metadata key: {k}")
+    return meta, 9 + n
+
+
+def ecdc_compress_codes(cfg: EncodecConfig, codes, audio_length: int, bandwidth: Optional[float]) -> bytes:
+    """EncodecCompressor.CompressToStreamAsync useLm=false (:93-190) for one clip's codes [nq, T] (single frame, no scale)."""
+    codes = np.asarray(codes)
+    nq, T = codes.shape
+    bits = int(np.log2(cfg.codebook_size))
+    packer = BitPacker(bits)
+    for t in range(T):
+        for k in range(nq):
+            packer.push(int(codes[k, t]))
+    name = "encodec_48khz" if cfg.sample_rate == 48000 else "encodec_24khz"
+    return ecdc_header(name, audio_length, nq, False, cfg.channels, cfg.sample_rate, bandwidth) + packer.flush()
+
+
+def ecdc_decompress_codes(cfg: EncodecConfig, data: bytes):
+    """DecompressFromStreamAsync useLm=false (:236-398) up to the code tensor: -> (codes [nq, T] int64, metadata)."""
+    import math
+    meta, off = ecdc_read_header(data)
+    if str(meta["lm"]).lower() == "true":
+        raise NotImplementedError("lm streams")
+    al, nq = int(meta["al"]), int(meta["nc"])
+    T = int(math.ceil(al * cfg.frame_rate / cfg.sample_rate))
+    un = BitUnpacker(int(np.log2(cfg.codebook_size)), data[off:])
+    codes = np.zeros((nq, T), np.int64)
+    for t in range(T):
+        for k in range(nq):
+            v = un.pull()
+            if v is None:
+                raise EOFError("Stream ended too soon")
+            codes[k, t] = v
+    return codes, meta

@@ -132,6 +132,23 @@ def test_full_config_default_policy_meets_the_gates(dac_full):
     m.Dispose()
 
 
+@pytest.mark.parametrize("mode,min_snr", [("mixed", 63.0), ("bf16x3", 85.0), ("f16x2", 62.0)])
+def test_full_config_decoder_precision_modes(dac_full, mode, min_snr):
+    """Decoder operand modes on the 44.1 kHz preset, per clip (quiet and hot clips included): every mode the engine
+    offers as a default candidate must clear the 60 dB / 1e-3 gate with a guard band, clip by clip."""
+    o, m = _models(dac_full, {"decoder_precision": mode})
+    x = _audio(dac_full[0], 3, 3 * 44100 + 5)
+    x[1] *= 0.02
+    x[2] *= 3.0
+    ref = _oracle_forward(o, x)
+    a_ref = ref["audio"].numpy()
+    a_dec = m.Decode(ref["z"].numpy())
+    per = [snr_db(a_ref[b], a_dec[b]) for b in range(3)]
+    print(f"decoder {mode}: per-clip snr {['%.1f' % s for s in per]} dB, max-abs {np.abs(a_dec - a_ref).max():.2e}")
+    assert min(per) >= max(min_snr, MIN_SNR_DB) and np.abs(a_dec - a_ref).max() <= MAX_ABS
+    m.Dispose()
+
+
 # ------------------------------------------------------------------------------------------------ edge cases
 @pytest.mark.parametrize("length", [1, 511, 512, 513, 5000])
 def test_ragged_lengths_pad_like_preprocess(dac_tiny, length):

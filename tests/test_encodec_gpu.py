@@ -104,3 +104,76 @@ def test_errors(encodec_nolstm):
     (codes, _), = m.Encode(np.zeros((1, 1, 3200), np.float32))
     assert codes.shape == (1, 4, 10)                                     # 3 kbps -> 4 codebooks, ceil(3200/320) frames
     m.Dispose()
+
+
+# ------------------------------------------------------------------ .ecdc container (no language model)
+def test_ecdc_compress_is_byte_exact_against_oracle_packer(encodec_nolstm):
+    """Header + bit-packed payload from the device equal the oracle's BinaryIO/BitPacker restatement applied to the codes
+    the same engine's Encode returns (so encoder near-ties cannot blur a packing difference)."""
+    import neuralcodecs_b200 as nc
+    from oracle import encodec as oenc
+    from oracle import synth
+    co, _, _ = encodec_nolstm
+    _, m = _models(encodec_nolstm, {"precision": "fp32"})
+    for bw, length, batch in ((6.0, 24000, 3), (1.5, 12345, 2), (24.0, 2241, 1)):
+        m.SetTargetBandwidth(bw)
+        x = synth.synth_audio(batch, length, co.sample_rate, first_clip=3)[:, None, :]
+        (codes, _), = m.Encode(x)
+        streams = nc.EncodecCompressor.CompressBatch(m, x)
+        assert len(streams) == batch
+        for b in range(batch):
+            want = oenc.ecdc_compress_codes(co, codes[b], length, bw)
+            assert streams[b] == want, f"bw {bw} clip {b}: stream differs from the oracle"
+            back, meta = oenc.ecdc_decompress_codes(co, streams[b])
+            assert np.array_equal(back, codes[b]) and meta["al"] == length and meta["nc"] == codes.shape[1]
+        assert nc.EncodecCompressor.Compress(m, x[0]) == streams[0]                       # [C, L] single-clip form
+    m.Dispose()
+
+
+def test_ecdc_decompress_round_trip(encodec_24k):
+    """Decompress(Compress(x)) == forward(x) of the same engine, and == oracle decode of the unpacked codes (tolerance)."""
+    import neuralcodecs_b200 as nc
+    from oracle import encodec as oenc
+    from oracle import synth
+    co, _, _ = encodec_24k
+    o, m = _models(encodec_24k)
+    length = 48123
+    x = synth.synth_audio(2, length, co.sample_rate, first_clip=21)[:, None, :]
+    streams = nc.EncodecCompressor.CompressBatch(m, x)
+    info = nc.EncodecCompressor.ReadHeader(streams[0])
+    assert info["al"] == length and info["nc"] == 8 and info["sr"] == 24000 and info["bw"] == 6.0 and not info["lm"]
+    wav, sr = nc.EncodecCompressor.DecompressBatch(streams, m)
+    assert sr == 24000 and wav.shape == (2, 1, length)
+    y = m.forward(x)
+    np.testing.assert_array_equal(wav, y)                 # same kernels, same codes -> identical bits
+    codes = np.stack([oenc.ecdc_decompress_codes(co, s)[0] for s in streams])
+    dref = o.decode(torch.from_numpy(codes)).numpy()[..., :length]
+    assert np.abs(wav - dref).max() <= MAX_ABS and snr_db(dref, wav) >= MIN_SNR_DB
+    one, _ = nc.EncodecCompressor.Decompress(streams[1], m)
+    np.testing.assert_array_equal(one, wav[1])
+    m.Dispose()
+
+
+def test_ecdc_oracle_written_stream_and_errors(encodec_nolstm):
+    import neuralcodecs_b200 as nc
+    from oracle import encodec as oenc
+    co, _, _ = encodec_nolstm
+    o, m = _models(encodec_nolstm, {"precision": "fp32"})
+    rng = np.random.default_rng(2)
+    length, nq = 6400, 16
+    codes = rng.integers(0, 1024, size=(nq, 20))
+    data = oenc.ecdc_compress_codes(co, codes, length, 12.0)
+    wav, sr = nc.EncodecCompressor.Decompress(data, m)
+    dref = o.decode(torch.from_numpy(codes[None])).numpy()[0, :, :length]
+    np.testing.assert_allclose(wav, dref, atol=5e-6)
+    with pytest.raises((ValueError, nc.CodecException), match="Stream ended too soon"):
+        nc.EncodecCompressor.Decompress(data[:-3], m)
+    lm = oenc.ecdc_header("encodec_24khz", length, nq, True, 1, 24000, 12.0) + data[oenc.ecdc_read_header(data)[1]:]
+    with pytest.raises((RuntimeError, nc.CodecException), match="language-model"):
+        nc.EncodecCompressor.Decompress(lm, m)
+    stereo = oenc.ecdc_header("encodec_24khz", length, nq, False, 2, 24000, 12.0) + data[oenc.ecdc_read_header(data)[1]:]
+    with pytest.raises((ValueError, nc.CodecException), match="channels"):
+        nc.EncodecCompressor.Decompress(stereo, m)
+    with pytest.raises(ValueError, match="shape should be"):
+        nc.EncodecCompressor.Compress(m, np.zeros(100, np.float32))
+    m.Dispose()

@@ -148,3 +148,92 @@ def test_encodec_lstm_matches_manual_recurrence():
             outs.append(h)
         inp = torch.stack(outs)
     np.testing.assert_allclose(y.numpy(), (inp + seq).permute(1, 2, 0).numpy(), atol=2e-6)   # + skip (SLSTM.cs:52-55)
+
+
+# ------------------------------------------------------------------ .ecdc container (no language model)
+def test_bitpacker_known_answers():
+    """Hand-derived from BitPacker.cs:60-110: LSB-first accumulator, low byte out first, Flush pads the last byte with zeros."""
+    p = oenc.BitPacker(10)
+    for v in (1, 2, 3):
+        p.push(v)
+    # 1 | 2<<10 | 3<<20 = 0x00300801 over 30 bits -> bytes 01 08 30 and the 6 remaining bits (0) flushed as 00
+    assert p.flush() == bytes([0x01, 0x08, 0x30, 0x00])
+    p = oenc.BitPacker(10)
+    p.push(1023)
+    assert p.flush() == bytes([0xFF, 0x03])
+    p = oenc.BitPacker(10)
+    for v in (1023, 0, 1023, 512):
+        p.push(v)                                       # exactly 40 bits -> 5 bytes, nothing left to flush
+    # bits 0-9 and 20-29 set, bit 39 set
+    assert p.flush() == bytes([0xFF, 0x03, 0xF0, 0x3F, 0x80])
+    p = oenc.BitPacker(3)
+    for v in (5, 7, 1):
+        p.push(v)                                       # 101 | 111<<3 | 001<<6 = 0b0_0111_1101 -> 7D, then bit 8 = 0
+    assert p.flush() == bytes([0x7D, 0x00])
+    with pytest.raises(ValueError):
+        oenc.BitPacker(0)
+
+
+def test_bitunpacker_inverts_packer_and_ends_cleanly():
+    rng = np.random.default_rng(5)
+    for bits in (1, 3, 8, 10, 11, 16):
+        vals = rng.integers(0, 1 << bits, size=257).tolist()
+        p = oenc.BitPacker(bits)
+        for v in vals:
+            p.push(v)
+        data = p.flush()
+        assert len(data) == (len(vals) * bits + 7) // 8
+        u = oenc.BitUnpacker(bits, data)
+        assert [u.pull() for _ in vals] == vals
+        tail = u.pull()                                 # only flush padding can remain: all-zero bits or end of stream
+        assert tail in (None, 0)
+    assert oenc.BitUnpacker(10, b"\xff").pull() is None  # BitUnpacker.cs:66-69 -> "Stream ended too soon" upstream
+
+
+def test_ecdc_header_known_answer_and_validation():
+    h = oenc.ecdc_header("encodec_24khz", 240000, 8, False, 1, 24000, 6.0)
+    js = b'{"m":"encodec_24khz","al":240000,"nc":8,"lm":false,"ch":1,"sr":24000,"bw":6}'
+    assert h == b"ECDC\x00" + len(js).to_bytes(4, "big") + js
+    assert oenc.ecdc_header("encodec_24khz", 1, 2, False, 1, 24000, 1.5).endswith(b'"bw":1.5}')
+    meta, off = oenc.ecdc_read_header(h + b"\x01\x02")
+    assert off == len(h) and meta == {"m": "encodec_24khz", "al": 240000, "nc": 8, "lm": False, "ch": 1, "sr": 24000, "bw": 6}
+    with pytest.raises(ValueError, match="not in ECDC format"):
+        oenc.ecdc_read_header(b"RIFF" + h[4:])
+    with pytest.raises(ValueError, match="Version not supported"):
+        oenc.ecdc_read_header(b"ECDC\x01" + h[5:])
+    with pytest.raises(EOFError):
+        oenc.ecdc_read_header(h[:20])
+    bad = b'{"m":"x","al":1,"lm":false}'
+    with pytest.raises(ValueError, match="Missing required metadata key: nc"):
+        oenc.ecdc_read_header(b"ECDC\x00" + len(bad).to_bytes(4, "big") + bad)
+
+
+def test_ecdc_codes_round_trip_and_size():
+    cfg = oenc.EncodecConfig()
+    rng = np.random.default_rng(11)
+    for nq, length in ((8, 240000), (2, 12345), (32, 321)):
+        T = math.ceil(length / cfg.hop_length)
+        codes = rng.integers(0, cfg.codebook_size, size=(nq, T))
+        data = oenc.ecdc_compress_codes(cfg, codes, length, 6.0)
+        meta, off = oenc.ecdc_read_header(data)
+        assert len(data) - off == (nq * T * 10 + 7) // 8 and meta["al"] == length and meta["nc"] == nq
+        back, _ = oenc.ecdc_decompress_codes(cfg, data)
+        assert np.array_equal(back, codes)
+        with pytest.raises(EOFError, match="Stream ended too soon"):
+            oenc.ecdc_decompress_codes(cfg, data[:-2])
+
+
+def test_c_abi_header_parser_matches_oracle():
+    """nc_encodec_ecdc_info is host-only: runs without a GPU."""
+    import neuralcodecs_b200 as nc
+    from neuralcodecs_b200 import CodecException
+    h = oenc.ecdc_header("encodec_24khz", 72000, 4, False, 1, 24000, 3.0)
+    info = nc.EncodecCompressor.ReadHeader(h + b"\x00" * 8)
+    assert info == {"al": 72000, "nc": 4, "ch": 1, "sr": 24000, "bw": 3.0, "lm": False, "payload_offset": len(h)}
+    # Python json.dumps spacing (facebookresearch/encodec streams), missing optional keys -> reference defaults
+    js = b'{"m": "encodec_48khz", "al": 10, "nc": 2, "lm": true}'
+    info = nc.EncodecCompressor.ReadHeader(b"ECDC\x00" + len(js).to_bytes(4, "big") + js)
+    assert info["sr"] == 48000 and info["ch"] == 1 and info["lm"] is True and info["bw"] == 0.0
+    for bad in (b"RIFF\x00\x00\x00\x00\x02{}", b"ECDC\x07\x00\x00\x00\x02{}", b"ECDC\x00\x00\x00\x00\x02{}", b"ECDC\x00\x00\x00\x01\x00{"):
+        with pytest.raises((ValueError, CodecException)):
+            nc.EncodecCompressor.ReadHeader(bad)

@@ -217,6 +217,7 @@ void ConvLayer::build(const std::string& name, const ConvSpec& spec, const std::
     ConvGemmParams probe{};
     probe.span = span_;
     probe.mode = mma_mode(requested);
+    probe.w_hi_only = 0;   // sized for full tiles; hi-only tiles only add weight stages
     int bn = 0;
     if (n_pad_ <= 256) {
       bn = n_pad_;
@@ -260,7 +261,11 @@ void ConvLayer::build(const std::string& name, const ConvSpec& spec, const std::
     //   TF32X3 : hi image followed by lo image (fetched with one bulk copy)
     //   H16X3  : 32 hi halves (64 B) then 32 lo halves (64 B) per row
     const size_t img = (size_t)bn_ * 32;
-    w_tile_floats_ = (int)(img * (mode_ == PREC_3XTF32 ? 2 : 1));
+    // one- and two-pass fp16 never read the weights' lo halves: ship 64-byte rows (half the L2->smem weight stream,
+    // which is what bounds those layers).  Layers that may run inside the fused ResidualUnit kernel (BN <= 128)
+    // keep the full layout that kernel expects.
+    w_hi_only_ = (mode_ == PREC_F16 || mode_ == PREC_F16X2) && bn_ > 128;
+    w_tile_floats_ = (int)(img * (mode_ == PREC_3XTF32 ? 2 : 1)) / (w_hi_only_ ? 2 : 1);
     std::vector<float> tiles((size_t)n_tiles_ * tiles_per_ntile_ * w_tile_floats_, 0.f);
     for (int nt = 0; nt < n_tiles_; ++nt) {
       for (size_t j = 0; j < taps_.size(); ++j) {
@@ -280,10 +285,14 @@ void ConvLayer::build(const std::string& name, const ConvSpec& spec, const std::
                 const uint16_t h = bf ? host_bf16(v) : host_f16(v);
                 const float hf = bf ? host_bf16_to_f(h) : host_f16_to_f(h);
                 const uint16_t l = bf ? host_bf16(v - hf) : host_f16(v - hf);
-                const size_t hi_off = ptx::sw128_offset((uint32_t)nl, (uint32_t)(kk / 8)) / 2 + (kk % 8);
-                const size_t lo_off = ptx::sw128_offset((uint32_t)nl, 4u + (uint32_t)(kk / 8)) / 2 + (kk % 8);
-                t16[hi_off] = h;
-                t16[lo_off] = l;
+                if (w_hi_only_) {
+                  t16[ptx::sw64_offset((uint32_t)nl, (uint32_t)(kk / 8)) / 2 + (kk % 8)] = h;
+                } else {
+                  const size_t hi_off = ptx::sw128_offset((uint32_t)nl, (uint32_t)(kk / 8)) / 2 + (kk % 8);
+                  const size_t lo_off = ptx::sw128_offset((uint32_t)nl, 4u + (uint32_t)(kk / 8)) / 2 + (kk % 8);
+                  t16[hi_off] = h;
+                  t16[lo_off] = l;
+                }
               } else {
                 const size_t off = ptx::sw128_offset((uint32_t)nl, (uint32_t)(kk / 4)) / 4 + (kk % 4);
                 const float h = host_rna_tf32(v);
@@ -353,6 +362,7 @@ bool ConvLayer::fill_umma(const ConvRunArgs& a, ConvGemmParams* pp) const {
   p.W = d_w_tiles_; p.w_tile_floats = w_tile_floats_; p.BN = bn_; p.n_tiles = n_tiles_; p.tiles_per_ntile = tiles_per_ntile_;
   p.mode = mma_mode(mode_);
   p.passes = mode_ == PREC_F16 ? 1 : (mode_ == PREC_F16X2 ? 2 : 3);
+  p.w_hi_only = w_hi_only_ ? 1 : 0;
   p.n_taps = (int)taps_.size();
   for (int j = 0; j < p.n_taps; ++j) p.taps[j] = utaps_[j];
   std::memcpy(p.tap_mask, tap_mask_, sizeof tap_mask_);

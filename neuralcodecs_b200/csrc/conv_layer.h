@@ -87,6 +87,7 @@ class ConvLayer {
   float* d_w_plain_ = nullptr;
   float* d_w_tiles_ = nullptr;
   int w_tile_floats_ = 0;
+  bool w_hi_only_ = false;
   // UMMA tiling
   int bn_ = 0, n_tiles_ = 0, tiles_per_ntile_ = 0;
   ConvTap utaps_[kMaxTaps];

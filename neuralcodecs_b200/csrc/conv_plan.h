@@ -75,6 +75,7 @@ struct ConvGemmParams {
   int n_tiles;
   int tiles_per_ntile;
   int mode;                 // MmaMode
+  int w_hi_only;            // 16-bit modes with passes < 3: weight tiles are [BN][32 hi halves] = 64-byte rows (SWIZZLE_64B)
   int passes;               // 16-bit modes: 3 = hi*hi + lo*hi + hi*lo, 2 = hi*hi + lo(A)*hi, 1 = hi*hi only
   int n_taps;
   ConvTap taps[kMaxTaps];

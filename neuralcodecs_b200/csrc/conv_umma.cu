@@ -190,11 +190,11 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t a_tile_bytes = (uint32_t)L.a_rows_alloc * 128u;
   const uint32_t a_stage_bytes = a_tile_bytes * (OPS == O_TF32X3 ? 2u : 1u);
-  const uint32_t w_tile_bytes = (uint32_t)p.BN * 128u;
+  const uint32_t w_tile_bytes = (uint32_t)p.BN * ((OPS == O_H16X3 && p.w_hi_only) ? 64u : 128u);
   const uint32_t w_stage_bytes = w_tile_bytes * (OPS == O_TF32X3 ? 2u : 1u);
   uint8_t* sA = smem;
   uint8_t* sW = smem + (uint32_t)L.a_stages * a_stage_bytes;
-  uint8_t* sE = sW + (uint32_t)L.w_stages * w_stage_bytes;   // epilogue ring (TMA epilogue only)
+  uint8_t* sE = sW + (((uint32_t)L.w_stages * w_stage_bytes + 1023u) & ~1023u);   // epilogue ring (TMA epilogue only)
 
   __shared__ uint64_t raw_full[kMaxAStages], a_full[kMaxAStages], a_empty[kMaxAStages];
   __shared__ uint64_t w_full[kMaxWStages], w_empty[kMaxWStages];
@@ -266,7 +266,9 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
     // so descriptors go straight to uniform registers and each tcgen05.mma is a single UTCHMMA).
     if (elect_one()) {
       const uint32_t idesc = OPS == O_H16X3 ? idesc_f16(kBM, p.BN, p.mode == MODE_BF16X3 ? 1 : 0) : idesc_tf32(kBM, p.BN);
-      const uint64_t a_desc0 = desc_at(smem_u32(sA)), w_desc0 = desc_at(smem_u32(sW));
+      const uint64_t a_desc0 = desc_at(smem_u32(sA));
+      const uint64_t w_desc0 = (OPS == O_H16X3 && p.w_hi_only) ? (kDescSw64Base | (uint64_t)((smem_u32(sW) & 0x3FFFFu) >> 4))
+                                                              : desc_at(smem_u32(sW));
       const uint32_t a_stage_u = a_stage_bytes >> 4, w_stage_u = w_stage_bytes >> 4;   // descriptor units (16 B)
       const uint32_t a_lo_u = a_tile_bytes >> 4, w_lo_u = w_tile_bytes >> 4;
       const uint32_t tap_u = (uint32_t)p.dense_step * 8u;                             // rows * 128 B / 16
@@ -961,7 +963,8 @@ size_t umma_smem_bytes(const ConvGemmParams& p, UmmaLaunch* L) {
   const int rows = ((kBM + p.span) + 7) / 8 * 8;
   const int mul = p.mode == MODE_TF32X3 ? 2 : 1;
   const long a_stage = (long)rows * 128 * mul;
-  const long w_stage = (long)p.BN * 128 * mul;
+  const bool w_hi_only = p.w_hi_only && (p.mode == MODE_BF16X3 || p.mode == MODE_F16X3);
+  const long w_stage = (long)p.BN * (w_hi_only ? 64 : 128) * mul;
   // TMA epilogue: whole [rows x n_total] output per clip, 16-byte strides, N tile a multiple of 32 columns
   L->tma_epilogue = (p.BN % 32 == 0 && p.n_total % 4 == 0 && p.d_valid == (long long)p.m_rows * p.n_total &&
                      p.d_clip_stride % 4 == 0 && p.n_valid == p.n_total &&
@@ -985,7 +988,7 @@ size_t umma_smem_bytes(const ConvGemmParams& p, UmmaLaunch* L) {
   while (ws < kMaxWStages && as * a_stage + (ws + 1) * w_stage <= budget) ++ws;
   L->a_stages = as;
   L->w_stages = ws;
-  return 1024 + (size_t)as * a_stage + (size_t)ws * w_stage + (L->tma_epilogue ? kEpiStages * kEpiStageBytes : 0);
+  return 1024 + (size_t)as * a_stage + (((size_t)ws * w_stage + 1023) & ~(size_t)1023) + (L->tma_epilogue ? kEpiStages * kEpiStageBytes : 0);
 }
 
 typedef void (*UmmaKernel)(const ConvGemmParams, const UmmaLaunch, const CUtensorMap, const CUtensorMap, const CUtensorMap);
@@ -1098,7 +1101,7 @@ static int ru_fuse_max_c() {
 }
 
 bool ru_fused_supported(const ConvGemmParams& p, const ConvGemmParams& p2) {
-  return (p.mode == MODE_BF16X3 || p.mode == MODE_F16X3) && p2.mode == p.mode && p2.passes == p.passes && p.n_tiles == 1 && p2.n_tiles == 1 &&
+  return (p.mode == MODE_BF16X3 || p.mode == MODE_F16X3) && p2.mode == p.mode && p2.passes == p.passes && !p.w_hi_only && !p2.w_hi_only && p.n_tiles == 1 && p2.n_tiles == 1 &&
          p.BN == p2.BN && p.BN % 32 == 0 && p.BN <= ru_fuse_max_c() && p.n_total == p.BN && p.n_valid == p.BN && p.dense_step >= 0 &&
          p.prologue == PRO_SNAKE && p2.n_taps == 1 && p2.n_kc == p.n_kc && p.kc_begin == 0 && p.span <= 64 &&
          p.a_pitch == p.BN && umma_view_ok(p) && p.d_valid == (long long)p.m_rows * p.n_total && p.d_clip_stride % 4 == 0 &&

@@ -149,6 +149,10 @@ __host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int fmt) {
 // OR in ((smem byte address & 0x3FFFF) >> 4) to get the descriptor of a tile / K step / row shift.
 constexpr uint64_t kDescSw128Base = (static_cast<uint64_t>(1) << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) |
                                     (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61);
+// K-major SWIZZLE_64B (64-byte rows, 8-row groups of 512 B contiguous): the hi-only weight tiles of the one- and
+// two-pass fp16 modes.
+constexpr uint64_t kDescSw64Base = (static_cast<uint64_t>(1) << 16) | (static_cast<uint64_t>(512 >> 4) << 32) |
+                                   (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(4) << 61);
 __device__ __forceinline__ uint64_t desc_at(uint32_t saddr) {
   return kDescSw128Base | static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
 }
@@ -178,6 +182,11 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
 // base is 1024-byte aligned and whose 8-row groups are contiguous (SBO = 1024)
 __host__ __device__ constexpr uint32_t sw128_offset(uint32_t r, uint32_t c) {
   return r * 128u + ((c ^ (r & 7u)) << 4);
+}
+
+// same for a SWIZZLE_64B tile (64-byte rows, chunk c in 0..3; the XOR uses address bits 7-8 = (r >> 1) & 3)
+__host__ __device__ constexpr uint32_t sw64_offset(uint32_t r, uint32_t c) {
+  return r * 64u + ((c ^ ((r >> 1) & 3u)) << 4);
 }
 
 }  // namespace ptx

@@ -562,9 +562,16 @@ def main():
             busy = sum(v["flops"] * passes(k) / kind_peak(k) for k, v in mma.items())   # seconds*1e12 at peak
             peak = peaks["bf16_tflops_sustained"]
             ach = fl / ms / 1e9
+            traffic = None
+            try:   # DRAM bytes per launch from the committed ncu capture of the same kernels, scaled by audio seconds
+                tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_dram_traffic_dac.json")))
+                if not dec_only:
+                    traffic = tj["dram_bytes"] / (tj["clips"] * tj["clip_seconds"]) * (nb * L / SAMPLE_RATE) / n
+            except Exception:
+                traffic = None
             roofline = {"bound": "tensor", "kernel": "conv_umma_kernel + conv_ru_fused_kernel (tcgen05.mma, TMA-fed implicit-GEMM conv; all conv layers)",
                         "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                        "traffic": None, "launches": n, "avg_launch_ms": ms / n, "share_of_step": ms / total_ms,
+                        "traffic": traffic, "traffic_note": "bytes per launch (avg), ncu dram read+write of these kernels (profiles/r01_dram_traffic_dac.json) scaled to this step; algorithmic = 0.95 of it", "launches": n, "avg_launch_ms": ms / n, "share_of_step": ms / total_ms,
                         "issued_tflops": issued / ms / 1e9, "issued_frac": busy / ms / 1e9,
                         "peak_note": f"{peak_src} bf16_tflops_sustained (cuBLAS bf16 under the power cap). achieved = algorithmic "
                                      "conv FLOPs (2*MAC) per second; issued_* counts the MMAs actually issued per product (3 for the "

@@ -49,6 +49,21 @@ internal static unsafe partial class Native
     [LibraryImport(Lib)] internal static partial NcStatus nc_dac_from_codes(NcHandle h, long* codes, int batch, int nQuantizers, long frames, float* z);
     [LibraryImport(Lib)] internal static partial NcStatus nc_dac_decode_codes(NcHandle h, long* codes, int batch, int nQuantizers, long frames, float* audio);
     [LibraryImport(Lib)] internal static partial NcStatus nc_dac_forward(NcHandle h, float* audio, int batch, long length, int nQuantizers, float* audioOut, long* codes, float* z, out long frames);
+    [LibraryImport(Lib)] internal static partial NcStatus nc_dac_decode_dia(NcHandle h, long* generated, int batch, int steps, int channels, int* delayPattern, long* lengths, float* audio, long audioStride);
+    // SNAC (Models/SNAC.cs): codes / noise are arrays of per-stage / per-block pointers
+    [LibraryImport(Lib)] internal static partial NcStatus nc_snac_query_shapes(NcHandle h, long length, out long paddedLength, out long frames, out int nStages, long* codeLengths, out int nNoise, long* noiseLengths);
+    [LibraryImport(Lib)] internal static partial NcStatus nc_snac_encode(NcHandle h, float* audio, int batch, long length, long** codes);
+    [LibraryImport(Lib)] internal static partial NcStatus nc_snac_decode(NcHandle h, long** codes, int batch, long frames, float** noise, ulong seed, float* audio);
+    [LibraryImport(Lib)] internal static partial NcStatus nc_snac_forward(NcHandle h, float* audio, int batch, long length, float** noise, ulong seed, float* audioOut, long** codes);
+    // Encodec (Models/Encodec.cs, Modules/Encodec/EncodecCompressor.cs)
+    [LibraryImport(Lib)] internal static partial NcStatus nc_encodec_query_shapes(NcHandle h, long length, float bandwidthKbps, out long frames, out int nQ, out long decodedLength);
+    [LibraryImport(Lib)] internal static partial NcStatus nc_encodec_encode(NcHandle h, float* audio, int batch, long length, float bandwidthKbps, long* codes);
+    [LibraryImport(Lib)] internal static partial NcStatus nc_encodec_decode(NcHandle h, long* codes, int batch, int nQ, long frames, float* audio);
+    [LibraryImport(Lib)] internal static partial NcStatus nc_encodec_forward(NcHandle h, float* audio, int batch, long length, float bandwidthKbps, float* audioOut, long* codes);
+    [LibraryImport(Lib)] internal static partial NcStatus nc_encodec_ecdc_size(NcHandle h, long length, float bandwidthKbps, out long headerBytes, out long streamBytes);
+    [LibraryImport(Lib)] internal static partial NcStatus nc_encodec_compress(NcHandle h, float* audio, int batch, long length, float bandwidthKbps, byte* output, long outStride, out long streamBytes);
+    [LibraryImport(Lib)] internal static partial NcStatus nc_encodec_ecdc_info(byte* stream, long streamBytes, out long audioLength, out int nQ, out int channels, out int sampleRate, out float bandwidthKbps, out int useLm, out long payloadOffset);
+    [LibraryImport(Lib)] internal static partial NcStatus nc_encodec_decompress(NcHandle h, byte* streams, int batch, long streamStride, long streamBytes, float* audio, long audioCapacity, out long audioLength, out int sampleRate);
 
     /// Status -> the reference's exception conventions (SURVEY 8b "Error conventions").
     internal static void Check(NcStatus s, string codec, Core.Exceptions.CodecOperation op)

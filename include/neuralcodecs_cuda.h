@@ -222,6 +222,24 @@ NC_API nc_status nc_snac_forward_dev(nc_handle h, const float* audio_dev, int32_
                                      const float* const* noise_dev, uint64_t seed, float* audio_out_dev,
                                      int64_t* const* codes_dev);
 
+/* replaces: SNAC.ProcessAudio(float[], sampleRate) Models/SNAC.cs:255-282: linear resample to the model rate when the
+ * rates differ (ResampleAudio :284-308, on the device, same double arithmetic), forward, output of the (resampled)
+ * input length.  audio [B][length] -> audio_out [B][out_capacity], *out_length samples per row written.
+ * audio_out == NULL only reports *out_length.  noise as in nc_snac_forward (lengths from nc_snac_query_shapes of
+ * *out_length). */
+NC_API nc_status nc_snac_process_audio(nc_handle h, const float* audio, int32_t batch, int64_t length,
+                                       int32_t sample_rate, const float* const* noise, uint64_t seed,
+                                       float* audio_out, int64_t out_capacity, int64_t* out_length);
+
+/* -- input conditioning (any handle; runs on that handle's device and stream) ------- */
+/* replaces: AudioUtils.ResampleLinear NeuralCodecs.Core/Utils/AudioUtils.cs:329-352 (= SNAC.ResampleAudio
+ * Models/SNAC.cs:284-308).  *out_length = (int64)(length * dst/src); out == NULL only reports it. */
+NC_API nc_status nc_resample_linear(nc_handle h, const float* audio, int32_t batch, int64_t length, int32_t src_rate,
+                                    int32_t dst_rate, float* out, int64_t out_capacity, int64_t* out_length);
+/* replaces: AudioUtils.ConvertToMono(float[], channels) NeuralCodecs.Core/Utils/AudioUtils.cs:45-62:
+ * interleaved [frames][channels] -> out [frames], float sum in channel order divided by the channel count. */
+NC_API nc_status nc_convert_to_mono(nc_handle h, const float* interleaved, int64_t frames, int32_t channels, float* out);
+
 /* -- Encodec ---------------------------------------------------------------------- */
 /* 24 kHz mono causal preset.  frames = ceil-chain of the strided SConv1d layers (SConv1d.cs:245-250);
  * n_q = max(1, floor(bandwidth*1000 / (log2(bins) * frame_rate))) (ResidualVectorQuantizer.cs:133-144);

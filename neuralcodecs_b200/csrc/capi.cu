@@ -516,6 +516,93 @@ nc_status nc_encodec_forward_dev(nc_handle h, const float* audio_dev, int32_t ba
   });
 }
 
+// ------------------------------------------------------------------------------------ input conditioning
+static int64_t resampled_length(int64_t length, int32_t src, int32_t dst, double* ratio) {
+  if (src <= 0 || dst <= 0) throw Error(NC_INVALID_ARGUMENT, "sample rates must be positive");
+  *ratio = (double)dst / (double)src;            // SNAC.cs:286
+  return (int64_t)((double)length * *ratio);     // :287
+}
+
+nc_status nc_resample_linear(nc_handle h, const float* audio, int32_t batch, int64_t length, int32_t src_rate, int32_t dst_rate,
+                             float* out, int64_t out_capacity, int64_t* out_length) {
+  return guarded([&] {
+    if (!h || !h->engine) throw Error(NC_INVALID_ARGUMENT, "null handle");
+    Engine* e = h->engine;
+    if (batch <= 0 || length <= 0) throw Error(NC_INVALID_ARGUMENT, "Audio data cannot be empty");
+    double ratio;
+    const int64_t n_out = resampled_length(length, src_rate, dst_rate, &ratio);
+    if (out_length) *out_length = n_out;
+    if (!out) return;
+    if (!audio) throw Error(NC_INVALID_ARGUMENT, "audio is null");
+    if (out_capacity < n_out) throw Error(NC_INVALID_ARGUMENT, "out_capacity is smaller than the resampled length");
+    if (n_out == 0) return;
+    BusyGuard g(e);
+    e->bind();
+    DevMem d_in((size_t)batch * length * 4), d_out((size_t)batch * n_out * 4);
+    NC_CUDA(cudaMemcpy(d_in.p, audio, (size_t)batch * length * 4, cudaMemcpyHostToDevice));
+    launch_resample_linear(d_in.as<float>(), length, length, d_out.as<float>(), n_out, n_out, ratio, batch, e->ctx());
+    e->sync();
+    NC_CUDA(cudaMemcpy2D(out, (size_t)out_capacity * 4, d_out.p, (size_t)n_out * 4, (size_t)n_out * 4, (size_t)batch,
+                         cudaMemcpyDeviceToHost));
+  });
+}
+
+nc_status nc_convert_to_mono(nc_handle h, const float* interleaved, int64_t frames, int32_t channels, float* out) {
+  return guarded([&] {
+    if (!h || !h->engine) throw Error(NC_INVALID_ARGUMENT, "null handle");
+    Engine* e = h->engine;
+    if (!interleaved || !out) throw Error(NC_INVALID_ARGUMENT, "audio is null");
+    if (frames <= 0 || channels <= 0) throw Error(NC_INVALID_ARGUMENT, "frames and channels must be positive");
+    BusyGuard g(e);
+    e->bind();
+    DevMem d_in((size_t)frames * channels * 4), d_out((size_t)frames * 4);
+    NC_CUDA(cudaMemcpy(d_in.p, interleaved, (size_t)frames * channels * 4, cudaMemcpyHostToDevice));
+    launch_to_mono(d_in.as<float>(), d_out.as<float>(), frames, channels, e->ctx());
+    e->sync();
+    NC_CUDA(cudaMemcpy(out, d_out.p, (size_t)frames * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
+nc_status nc_snac_process_audio(nc_handle h, const float* audio, int32_t batch, int64_t length, int32_t sample_rate,
+                                const float* const* noise, uint64_t seed, float* audio_out, int64_t out_capacity,
+                                int64_t* out_length) {
+  return guarded([&] {
+    SnacEngine* e = snac_of(h);
+    if (batch <= 0 || length <= 0) throw Error(NC_INVALID_ARGUMENT, "Audio data cannot be empty");   // SNAC.cs:257-258
+    double ratio = 1.0;
+    const int model_rate = e->config().sample_rate;
+    const int64_t n = sample_rate == model_rate ? length : resampled_length(length, sample_rate, model_rate, &ratio);
+    if (out_length) *out_length = n;
+    if (!audio_out) return;
+    if (!audio) throw Error(NC_INVALID_ARGUMENT, "Audio data cannot be empty");
+    if (n <= 0) throw Error(NC_INVALID_ARGUMENT, "Audio data cannot be empty");
+    if (out_capacity < n) throw Error(NC_INVALID_ARGUMENT, "out_capacity is smaller than the output length");
+    BusyGuard g(e);
+    e->bind();
+    DevMem d_in((size_t)batch * length * 4), d_rs(sample_rate == model_rate ? 0 : (size_t)batch * n * 4), d_out((size_t)batch * n * 4);
+    NC_CUDA(cudaMemcpy(d_in.p, audio, (size_t)batch * length * 4, cudaMemcpyHostToDevice));
+    const float* x = d_in.as<float>();
+    if (sample_rate != model_rate) {
+      launch_resample_linear(d_in.as<float>(), length, length, d_rs.as<float>(), n, n, ratio, batch, e->ctx());
+      x = d_rs.as<float>();
+    }
+    const int64_t T = e->frames(n);
+    const auto nl = e->noise_lengths(T);
+    SnacStaging st;
+    st.noise_dev.assign(nl.size(), nullptr);
+    if (noise)
+      for (size_t i = 0; i < nl.size(); ++i)
+        if (noise[i]) {
+          st.mem.push_back(new DevMem((size_t)batch * nl[i] * 4));
+          NC_CUDA(cudaMemcpy(st.mem.back()->p, noise[i], (size_t)batch * nl[i] * 4, cudaMemcpyHostToDevice));
+          st.noise_dev[i] = st.mem.back()->as<float>();
+        }
+    e->forward_dev(x, batch, n, st.noise_dev.data(), seed, d_out.as<float>(), nullptr);
+    NC_CUDA(cudaMemcpy2D(audio_out, (size_t)out_capacity * 4, d_out.p, (size_t)n * 4, (size_t)n * 4, (size_t)batch,
+                         cudaMemcpyDeviceToHost));
+  });
+}
+
 // ------------------------------------------------------------------------------------ .ecdc container
 static EcdcMeta ecdc_meta_for(EncodecEngine* e, int64_t length, float bw) {
   EcdcMeta m;

@@ -409,4 +409,51 @@ void launch_dia_revert(const int64_t* gen, const int* items_dev, const int* dela
   ctx.end(ev, "dia_revert", 0, 16.0 * total);
 }
 
+// ------------------------------------------------------------------------------ input conditioning
+__global__ void resample_linear_kernel(const float* __restrict__ in, long long n_in, long long in_stride, float* __restrict__ out,
+                                       long long n_out, long long out_stride, double ratio) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  const float* x = in + (long long)blockIdx.y * in_stride;
+  // same double arithmetic as the reference loop, no fused multiply-add
+  const double position = __ddiv_rn((double)i, ratio);
+  const long long index = (long long)position;
+  const double fraction = __dsub_rn(position, (double)index);
+  float y;
+  if (index >= n_in - 1) {
+    y = x[n_in - 1];
+  } else {
+    const double a = __dmul_rn(__dsub_rn(1.0, fraction), (double)x[index]);
+    const double b = __dmul_rn(fraction, (double)x[index + 1]);
+    y = (float)__dadd_rn(a, b);
+  }
+  out[(long long)blockIdx.y * out_stride + i] = y;
+}
+
+void launch_resample_linear(const float* in, long long n_in, long long in_stride, float* out, long long n_out, long long out_stride,
+                            double ratio, int batch, const LaunchCtx& ctx) {
+  if (batch <= 0 || n_out <= 0) return;
+  const int ev = ctx.begin();
+  dim3 grid((unsigned)((n_out + 255) / 256), batch);
+  resample_linear_kernel<<<grid, 256, 0, ctx.stream>>>(in, n_in, in_stride, out, n_out, out_stride, ratio);
+  check_launch((int)cudaGetLastError(), "resample_linear");
+  ctx.end(ev, "resample_linear", 0.0, 4.0 * batch * (double)(n_in + n_out));
+}
+
+__global__ void to_mono_kernel(const float* __restrict__ in, float* __restrict__ out, long long frames, int channels) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= frames) return;
+  float sum = 0.f;
+  for (int ch = 0; ch < channels; ++ch) sum += in[i * channels + ch];
+  out[i] = sum / (float)channels;
+}
+
+void launch_to_mono(const float* interleaved, float* out, long long frames, int channels, const LaunchCtx& ctx) {
+  if (frames <= 0) return;
+  const int ev = ctx.begin();
+  to_mono_kernel<<<(unsigned)((frames + 255) / 256), 256, 0, ctx.stream>>>(interleaved, out, frames, channels);
+  check_launch((int)cudaGetLastError(), "to_mono");
+  ctx.end(ev, "to_mono", 0.0, 4.0 * (double)frames * (channels + 1));
+}
+
 }  // namespace nc

@@ -54,4 +54,13 @@ void launch_rvq_from_codes(const RvqWeights& w, const int64_t* codes, float* zq,
 void launch_dia_revert(const int64_t* gen, const int* items_dev, const int* delay_dev, int64_t* codes, int n_items, int T, int C,
                        int len, int K, const LaunchCtx& ctx);
 
+// Input conditioning (the step before the codec path).
+// Linear resampler of SNAC.ResampleAudio (Models/SNAC.cs:284-308) = AudioUtils.ResampleLinear
+// (NeuralCodecs.Core/Utils/AudioUtils.cs:329-352): position = i / ratio in double, two-point interpolation in double,
+// last sample held.  in [batch][n_in] (stride in_stride) -> out [batch][n_out].  n_out = (long)(n_in * ratio).
+void launch_resample_linear(const float* in, long long n_in, long long in_stride, float* out, long long n_out, long long out_stride,
+                            double ratio, int batch, const LaunchCtx& ctx);
+// AudioUtils.ConvertToMono (AudioUtils.cs:45-62): out[i] = (sum over channels in order, float) / channels
+void launch_to_mono(const float* interleaved, float* out, long long frames, int channels, const LaunchCtx& ctx);
+
 }  // namespace nc

@@ -173,29 +173,30 @@ class SNAC:
         return audio, codes
 
     def ProcessAudio(self, audioData, sampleRate: int, noise=None, seed: int = 0) -> np.ndarray:
-        """SNAC.ProcessAudio (SNAC.cs:255-282): linear resample on the host if needed (:284-308), forward, flat array."""
+        """SNAC.ProcessAudio (SNAC.cs:255-282): linear resample to the model rate if needed (:284-308, on the device),
+        forward, flat array of the (resampled) input length.  A [B, L] array is processed as one batch -> [B, L']."""
         if audioData is None or len(audioData) == 0:
             raise ValueError("Audio data cannot be empty")
-        a = np.asarray(audioData, dtype=np.float32).reshape(-1)
-        if sampleRate != self._config.sample_rate:
-            a = self.ResampleAudio(a, sampleRate, self._config.sample_rate)
-        audio, _ = self.forward(a, noise, seed)
-        return audio.reshape(-1)
+        a = np.ascontiguousarray(audioData, dtype=np.float32)
+        flat = a.ndim == 1
+        a = a.reshape(1, -1) if flat else a.reshape(a.shape[0], -1)
+        B, L = a.shape
+        n = C.c_int64()
+        lib = _lib.lib()
+        _lib.check(lib.nc_snac_process_audio(self._handle(), None, B, L, int(sampleRate), None, 0, None, 0, C.byref(n)),
+                   "SNAC", "ProcessAudio")
+        out = np.empty((B, n.value), np.float32)
+        ns = [np.ascontiguousarray(z, dtype=np.float32).reshape(B, -1) for z in noise] if noise is not None else None
+        nz = self._ptr_array(ns, len(ns)) if ns is not None else None
+        _lib.check(lib.nc_snac_process_audio(self._handle(), a.ctypes.data_as(C.c_void_p), B, L, int(sampleRate), nz, int(seed),
+                                             out.ctypes.data_as(C.c_void_p), n.value, C.byref(n)), "SNAC", "ProcessAudio")
+        return out.reshape(-1) if flat else out
 
-    @staticmethod
-    def ResampleAudio(x: np.ndarray, src: int, dst: int) -> np.ndarray:
-        """SNAC.ResampleAudio (SNAC.cs:284-308): linear interpolation, last sample held."""
-        ratio = float(dst) / float(src)
-        n = int(len(x) * ratio)
-        pos = np.arange(n, dtype=np.float64) / ratio
-        idx = pos.astype(np.int64)
-        frac = pos - idx
-        last = idx >= len(x) - 1
-        i0 = np.minimum(idx, len(x) - 1)
-        i1 = np.minimum(idx + 1, len(x) - 1)
-        out = (1 - frac) * x[i0].astype(np.float64) + frac * x[i1].astype(np.float64)
-        out[last] = x[-1]
-        return out.astype(np.float32)
+    def ResampleAudio(self, x, src: int, dst: int) -> np.ndarray:
+        """SNAC.ResampleAudio (SNAC.cs:284-308) = AudioUtils.ResampleLinear (Core/Utils/AudioUtils.cs:329-352):
+        linear interpolation in double, last sample held; runs on the model's device."""
+        from .audio_utils import ResampleLinear
+        return ResampleLinear(self, x, src, dst)
 
     # ------------------------------------------------------------------ device-pointer variant
     def forward_dev(self, audio_ptr: int, batch: int, length: int, audio_out_ptr: int, code_ptrs: Sequence[int],

@@ -298,3 +298,51 @@ class SNACOracle:
 def load_safetensors(path: str, cfg: SNACConfig, dtype=torch.float32) -> SNACOracle:
     from safetensors.torch import load_file
     return SNACOracle(cfg, load_file(path), dtype)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Input conditioning in front of the model (test infrastructure, numpy float64 = the reference's C# double arithmetic)
+def resample_linear(x, src: int, dst: int):
+    """SNAC.ResampleAudio (Models/SNAC.cs:284-308) = AudioUtils.ResampleLinear (NeuralCodecs.Core/Utils/AudioUtils.cs:329-352):
+    position = i / ratio, index = (int)position, two-point interpolation in double, last sample held."""
+    import numpy as np
+    x = np.asarray(x, np.float32)
+    ratio = float(dst) / float(src)
+    n = int(len(x) * ratio)
+    pos = np.arange(n, dtype=np.float64) / ratio
+    idx = pos.astype(np.int64)
+    frac = pos - idx
+    last = idx >= len(x) - 1
+    i0 = np.minimum(idx, len(x) - 1)
+    i1 = np.minimum(idx + 1, len(x) - 1)
+    out = (1 - frac) * x[i0].astype(np.float64) + frac * x[i1].astype(np.float64)
+    out[last] = x[-1]
+    return out.astype(np.float32)
+
+
+def resample_linear_loop(x, src: int, dst: int):
+    """The same, as the reference's scalar loop (pure Python; small inputs only) -- pins the vectorised form."""
+    import numpy as np
+    ratio = float(dst) / float(src)
+    n = int(len(x) * ratio)
+    out = np.zeros(n, np.float32)
+    for i in range(n):
+        position = i / ratio
+        index = int(position)
+        fraction = position - index
+        if index >= len(x) - 1:
+            out[i] = x[len(x) - 1]
+        else:
+            out[i] = np.float32((1 - fraction) * float(x[index]) + fraction * float(x[index + 1]))
+    return out
+
+
+def convert_to_mono(x, channels: int):
+    """AudioUtils.ConvertToMono (AudioUtils.cs:45-62): float32 running sum in channel order, divided by the channel count."""
+    import numpy as np
+    x = np.asarray(x, np.float32)
+    frames = len(x) // channels
+    s = np.zeros(frames, np.float32)
+    for ch in range(channels):
+        s = (s + x[ch:frames * channels:channels]).astype(np.float32)
+    return (s / np.float32(channels)).astype(np.float32)

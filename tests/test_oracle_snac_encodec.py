@@ -237,3 +237,15 @@ def test_c_abi_header_parser_matches_oracle():
     for bad in (b"RIFF\x00\x00\x00\x00\x02{}", b"ECDC\x07\x00\x00\x00\x02{}", b"ECDC\x00\x00\x00\x00\x02{}", b"ECDC\x00\x00\x00\x01\x00{"):
         with pytest.raises((ValueError, CodecException)):
             nc.EncodecCompressor.ReadHeader(bad)
+
+
+def test_resampler_restatement_matches_scalar_loop_and_known_answers():
+    """oracle.snac.resample_linear (vectorised) == the reference's scalar loop (SNAC.cs:284-308); hand-derived values."""
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal(211).astype(np.float32)
+    for src, dst in ((44100, 24000), (8000, 24000), (3, 7), (7, 3), (5, 5)):
+        np.testing.assert_array_equal(osnac.resample_linear(x, src, dst), osnac.resample_linear_loop(x, src, dst))
+    np.testing.assert_array_equal(osnac.resample_linear(np.array([0.0, 1.0, 2.0], np.float32), 1, 2),
+                                  np.array([0.0, 0.5, 1.0, 1.5, 2.0, 2.0], np.float32))      # last sample held
+    assert osnac.resample_linear(np.array([1.0, 2.0, 3.0, 4.0], np.float32), 2, 1).tolist() == [1.0, 3.0]
+    assert osnac.convert_to_mono(np.array([1, 3, 5, 7, 9], np.float32), 2).tolist() == [2.0, 6.0]   # ragged tail dropped

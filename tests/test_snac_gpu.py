@@ -164,10 +164,41 @@ def test_errors_and_resampler(snac_tiny):
         m.Decode([np.zeros((1, 4), np.int64)])
     with pytest.raises(ValueError, match="Audio data cannot be empty"):
         m.ProcessAudio(np.zeros(0, np.float32), 16000)
-    y = m.ProcessAudio(np.sin(np.arange(8000) / 20).astype(np.float32), 8000, seed=1)   # 8 kHz -> 16 kHz on the host
+    y = m.ProcessAudio(np.sin(np.arange(8000) / 20).astype(np.float32), 8000, seed=1)   # 8 kHz -> 16 kHz on the device
     assert y.shape == (16000,)
-    r = nc.SNAC.ResampleAudio(np.array([0.0, 1.0, 2.0], np.float32), 1, 2)
-    np.testing.assert_allclose(r, [0.0, 0.5, 1.0, 1.5, 2.0, 2.0])
+    r = m.ResampleAudio(np.array([0.0, 1.0, 2.0], np.float32), 1, 2)
+    np.testing.assert_array_equal(r, np.array([0.0, 0.5, 1.0, 1.5, 2.0, 2.0], np.float32))
     with pytest.raises(RuntimeError):
         nc.SNAC(nc.SNACConfig(attn_window_size=16))                       # LocalMHA is built for the presets' window 32 only
+    m.Dispose()
+
+
+def test_input_conditioning_matches_the_reference_loops_bit_for_bit(snac_tiny):
+    """Device resampler / mono mix against the oracle's restatement of the C# double / float loops."""
+    from neuralcodecs_b200 import audio_utils
+    from oracle import snac as osnac
+    from oracle import synth
+    co, _, _ = snac_tiny
+    o, m = _models(snac_tiny, {"precision": "fp32"})
+    rng = np.random.default_rng(3)
+    x = synth.synth_audio(2, 44100, 44100, first_clip=5)
+    for src, dst in ((44100, 24000), (8000, 24000), (48000, 16000), (22050, 24000), (24000, 24000), (3, 7)):
+        got = audio_utils.ResampleLinear(m, x, src, dst)
+        for b in range(2):
+            want = osnac.resample_linear(x[b], src, dst)
+            assert got[b].shape == want.shape
+            np.testing.assert_array_equal(got[b], want, err_msg=f"{src}->{dst}")
+    short = rng.standard_normal(37).astype(np.float32)
+    np.testing.assert_array_equal(audio_utils.ResampleLinear(m, short, 16000, 44100), osnac.resample_linear_loop(short, 16000, 44100))
+    np.testing.assert_array_equal(audio_utils.ResampleLinear(m, short[:1], 1, 5), np.full(5, short[0], np.float32))
+    assert audio_utils.ResampleLinear(m, short[:1], 5, 1).shape == (0,)
+    for ch in (1, 2, 6):
+        inter = rng.standard_normal(1000 * ch + (ch - 1)).astype(np.float32)      # ragged tail is dropped as in the reference
+        np.testing.assert_array_equal(audio_utils.ConvertToMono(m, inter, ch), osnac.convert_to_mono(inter, ch))
+    # ProcessAudio = resample + forward of the resampled clip (same noise), batch form
+    a = x[:, :22050]
+    rs = audio_utils.ResampleLinear(m, a, 44100, co.sample_rate)
+    y = m.ProcessAudio(a, 44100, seed=7)
+    ref, _ = m.forward(rs, None, 7)
+    np.testing.assert_array_equal(y, ref.reshape(2, -1))
     m.Dispose()

@@ -48,6 +48,18 @@ WORKLOADS = {
 }
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """Write the one JSON line to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def shard_range(rank: int, world: int, batch: int):
     """Contiguous shard [lo, hi) of the global batch owned by `rank` (static split, no collective)."""
     return rank * batch // world, (rank + 1) * batch // world
@@ -195,7 +207,7 @@ def reference_arm(args, rank: int):
             "config": {"workload": args.workload, "sample": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------ weights
@@ -382,7 +394,7 @@ def run_other_codec(args, codec: str, rank: int, local_rank: int, world: int):
                            "l2": "inputs + activations far larger than L2; no flush", "weights": "random-init (seeded)"},
                 "wall_ms_per_step": wall_ms / args.steps, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels}
-        print(json.dumps(line), flush=True)
+        emit(line)
     model.Dispose()
     if dist is not None:
         dist.destroy_process_group()
@@ -391,9 +403,12 @@ def run_other_codec(args, codec: str, rank: int, local_rank: int, world: int):
 # ------------------------------------------------------------------------------------------ GPU arm
 def main():
     args = parse_args()
-    # NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION; the contract is ONE JSON line on stdout
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # The contract is ONE JSON line on stdout, but libraries write there too (NCCL prints its version banner to stdout
+    # at any NCCL_DEBUG level >= VERSION): point fd 1 at stderr for the whole run and keep the real stdout for emit().
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -599,7 +614,7 @@ def main():
                 "gflop_per_audio_s": GFLOP_PER_AUDIO_S if not dec_only else 138.6,
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                 "cpu_baseline": cpu, "kernels": kernels}
-        print(json.dumps(line), flush=True)
+        emit(line)
     model.Dispose()
     if dist is not None:
         dist.destroy_process_group()

@@ -232,9 +232,21 @@ lstm_layer_kernel(const float* __restrict__ xproj, long long xproj_clip_stride, 
   const int my_u = tid >> 4, my_b = tid & 15;
   float c_state = 0.f;
   const bool clip_ok = b0 + my_b < batch;
+  // The hoisted input projection and the skip value of a step do not depend on other CTAs: their HBM loads are
+  // issued one step ahead, between arriving at the grid barrier and waiting on it.
+  float nxi = 0.f, nxf = 0.f, nxg = 0.f, nxo = 0.f, nsk = 0.f;
+  auto prefetch = [&](int t) {
+    if (clip_ok && t < T) {
+      const float* xp = xproj + (long long)(b0 + my_b) * xproj_clip_stride + (long long)t * 4 * H + (u0 + my_u);
+      nxi = __ldg(xp); nxf = __ldg(xp + H); nxg = __ldg(xp + 2 * H); nxo = __ldg(xp + 3 * H);
+      if (skip) nsk = __ldg(skip + (long long)(b0 + my_b) * skip_clip_stride + (long long)t * H + (u0 + my_u));
+    }
+  };
+  prefetch(0);
   for (int t = 0; t < T; ++t) {
     const float* hprev = hbuf + (size_t)((t + 1) & 1) * bpad * H;   // written at step t-1 (zeros at t = 0)
     float* hnext = hbuf + (size_t)(t & 1) * bpad * H;
+    const float xi = nxi, xf = nxf, xg = nxg, xo = nxo, sk = nsk;
     for (int i = tid; i < kLB * (H / 4); i += 256) {
       const int bb = i / (H / 4), k4 = i % (H / 4);
       // written by other CTAs during this launch: bypass L1 (ld.global.cg)
@@ -263,40 +275,47 @@ lstm_layer_kernel(const float* __restrict__ xproj, long long xproj_clip_stride, 
             acc[i][j] = fmaf(w[i][4 * k4 + 3], hv[j].w, acc[i][j]);
           }
       }
-      // reduce over the 16 K slices (lanes ks = tid & 15 of each half warp)
+      // reduce-scatter over the 16 K slices (lanes ks = tid & 15 of each half warp): a butterfly that halves the
+      // number of live values per lane at every step (8 + 4 + 2 + 1 = 15 shuffles instead of 16 x 4); lane ks ends
+      // up with the complete sum of accumulator (i, j) = (ks >> 2, ks & 3).
+      float v[16];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float v = acc[i][j];
-          v += __shfl_xor_sync(0xffffffffu, v, 1);
-          v += __shfl_xor_sync(0xffffffffu, v, 2);
-          v += __shfl_xor_sync(0xffffffffu, v, 4);
-          v += __shfl_xor_sync(0xffffffffu, v, 8);
-          if (ks == 0) gates[4 * rg + i][4 * bg + j] = v;
+        for (int j = 0; j < 4; ++j) v[4 * i + j] = acc[i][j];
+#pragma unroll
+      for (int m = 8; m >= 1; m >>= 1) {
+        const bool up = (ks & m) != 0;
+#pragma unroll
+        for (int q = 0; q < m; ++q) {
+          const float send = up ? v[q] : v[q + m];
+          const float keep = up ? v[q + m] : v[q];
+          v[q] = keep + __shfl_xor_sync(0xffffffffu, send, m);
         }
+      }
+      gates[4 * rg + (ks >> 2)][4 * bg + (ks & 3)] = v[0];
     }
     __syncthreads();
     if (clip_ok) {
       const int b = b0 + my_b, u = u0 + my_u;
-      const float* xp = xproj + (long long)b * xproj_clip_stride + (long long)t * 4 * H;
-      const float gi = gates[0 * kLU + my_u][my_b] + xp[0 * H + u];
-      const float gf = gates[1 * kLU + my_u][my_b] + xp[1 * H + u];
-      const float gg = gates[2 * kLU + my_u][my_b] + xp[2 * H + u];
-      const float go = gates[3 * kLU + my_u][my_b] + xp[3 * H + u];
+      const float gi = gates[0 * kLU + my_u][my_b] + xi;
+      const float gf = gates[1 * kLU + my_u][my_b] + xf;
+      const float gg = gates[2 * kLU + my_u][my_b] + xg;
+      const float go = gates[3 * kLU + my_u][my_b] + xo;
       c_state = sigmoid_f(gf) * c_state + sigmoid_f(gi) * tanhf(gg);
       const float h = sigmoid_f(go) * tanhf(c_state);
       __stcg(hnext + (size_t)b * H + u, h);
       float y = h;
-      if (skip) y += skip[(long long)b * skip_clip_stride + (long long)t * H + u];
+      if (skip) y += sk;
       if (post_elu) y = y > 0.f ? y : expm1f(y);
       out[(long long)b * out_clip_stride + (long long)t * H + u] = y;
     }
     // barrier among the CTAs of this batch slice
     __threadfence();
     __syncthreads();
+    if (tid == 0) atomicAdd(&barriers[blockIdx.y], 1u);
+    prefetch(t + 1);
     if (tid == 0) {
-      atomicAdd(&barriers[blockIdx.y], 1u);
       const unsigned int target = (unsigned int)n_unit_ctas * (unsigned int)(t + 1);
       while (*reinterpret_cast<volatile unsigned int*>(&barriers[blockIdx.y]) < target) {
       }

@@ -15,6 +15,7 @@ idx = [hdr.index(w) for w in want if w in hdr]
 w = csv.writer(sys.stdout)
 w.writerow([hdr[i] for i in idx]); w.writerow([units[i] for i in idx])
 for r in rows[2:]:
-    if "nc::" in r[hdr.index("Kernel Name")]:
+    kn = r[hdr.index("Kernel Name")]
+    if "at::" not in kn and "elementwise" not in kn and "cub::" not in kn:
         r[hdr.index("Kernel Name")] = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "")
         w.writerow([r[i] for i in idx])

@@ -586,7 +586,7 @@ def main():
                 traffic = None
             roofline = {"bound": "tensor", "kernel": "conv_umma_kernel + conv_ru_fused_kernel (tcgen05.mma, TMA-fed implicit-GEMM conv; all conv layers)",
                         "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                        "traffic": traffic, "traffic_note": "bytes per launch (avg), ncu dram read+write of these kernels (profiles/r01_dram_traffic_dac.json) scaled to this step; algorithmic = 0.95 of it", "launches": n, "avg_launch_ms": ms / n, "share_of_step": ms / total_ms,
+                        "traffic": traffic, "traffic_note": "bytes per launch (avg), ncu dram read+write of these kernels (profiles/r01_dram_traffic_dac.json) scaled to this step; algorithmic bytes = 1.10x of it (re-reads hit L2)", "launches": n, "avg_launch_ms": ms / n, "share_of_step": ms / total_ms,
                         "issued_tflops": issued / ms / 1e9, "issued_frac": busy / ms / 1e9,
                         "peak_note": f"{peak_src} bf16_tflops_sustained (cuBLAS bf16 under the power cap). achieved = algorithmic "
                                      "conv FLOPs (2*MAC) per second; issued_* counts the MMAs actually issued per product (3 for the "

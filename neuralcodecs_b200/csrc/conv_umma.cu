@@ -244,7 +244,7 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
       int ws = 0;
       uint32_t wph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile / tiles_per_n;
+        const int nt = tile % p.n_tiles;   // N tile fastest: the N tiles of one M tile run side by side, A re-reads hit L2
         const unsigned mask = p.tap_mask[nt];
         const float* wbase = p.W + (size_t)nt * p.tiles_per_ntile * (size_t)p.w_tile_floats;
         for (int kci = 0; kci < p.n_kc; ++kci) {
@@ -282,7 +282,7 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u;
         uint32_t acc = 0;
-        const unsigned mask = p.dense_step >= 0 ? 0u : (unsigned)p.tap_mask[tile / tiles_per_n];
+        const unsigned mask = p.dense_step >= 0 ? 0u : (unsigned)p.tap_mask[tile % p.n_tiles];
         for (int kci = 0; kci < p.n_kc; ++kci) {
           mbar_wait(&a_full[as], aph);
           tc_fence_after();
@@ -349,8 +349,8 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
       int as = 0;
       uint32_t aph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile / tiles_per_n;
-        const int rem = tile - nt * tiles_per_n;
+        const int nt = tile % p.n_tiles;   // N tile fastest: the N tiles of one M tile run side by side, A re-reads hit L2
+        const int rem = tile / p.n_tiles;
         const int b = rem / p.m_tiles_per_clip;
         const int mt = rem - b * p.m_tiles_per_clip;
         const int r_base = mt * kBM + p.smin;
@@ -369,8 +369,8 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
       int es = 0;
       uint32_t eph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile / tiles_per_n;
-        const int rem = tile - nt * tiles_per_n;
+        const int nt = tile % p.n_tiles;   // N tile fastest: the N tiles of one M tile run side by side, A re-reads hit L2
+        const int rem = tile / p.n_tiles;
         const int b = rem / p.m_tiles_per_clip;
         const int mt = rem - b * p.m_tiles_per_clip;
         for (int g = 0; g < groups; ++g) {
@@ -395,8 +395,8 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
       int es = 0, prev = -1;
       uint32_t eph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int nt = tile / tiles_per_n;
-        const int rem = tile - nt * tiles_per_n;
+        const int nt = tile % p.n_tiles;   // N tile fastest: the N tiles of one M tile run side by side, A re-reads hit L2
+        const int rem = tile / p.n_tiles;
         const int b = rem / p.m_tiles_per_clip;
         const int mt = rem - b * p.m_tiles_per_clip;
         const int buf = it & 1;
@@ -455,8 +455,8 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
       // direct path (ragged outputs, Cout not a multiple of 32): each thread stores its own row
       const bool vec_ok = (p.n_total & 3) == 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int nt = tile / tiles_per_n;
-        const int rem = tile - nt * tiles_per_n;
+        const int nt = tile % p.n_tiles;   // N tile fastest: the N tiles of one M tile run side by side, A re-reads hit L2
+        const int rem = tile / p.n_tiles;
         const int b = rem / p.m_tiles_per_clip;
         const int mt = rem - b * p.m_tiles_per_clip;
         const int buf = it & 1;

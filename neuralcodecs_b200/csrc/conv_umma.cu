@@ -609,7 +609,7 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t a_stage_bytes = (uint32_t)L.a_rows_alloc * 128u;
-  const uint32_t w_stage_bytes = (uint32_t)p.BN * 128u;
+  const uint32_t w_stage_bytes = (uint32_t)p.BN * ((p.w_hi_only && p2.w_hi_only) ? 64u : 128u);
   uint8_t* sA = smem;
   uint8_t* sW = sA + (uint32_t)L.a_stages * a_stage_bytes;
   uint8_t* sH = sW + (uint32_t)L.w_stages * w_stage_bytes;
@@ -649,24 +649,84 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
   auto buf_of = [&](int it) { return dbl ? (it & 1) : 0; };
   auto use_of = [&](int it) { return (uint32_t)(dbl ? (it >> 1) : it); };   // how often that buffer was used before
 
+  // E1 (acc1 -> activation -> hi|lo operand tiles of the 1x1 conv, "H stages") is written once and run by whichever
+  // warps own it: the 8 transform warps when both accumulators are double-buffered (they are otherwise idle half the
+  // time, and the epilogue warps then only do E2), the 8 epilogue warps when single-buffered.  Both sets cover every
+  // (TMEM lane quarter, 16-column half) pair exactly once.
+  const int q = warp & 3;
+  const int half = ((warp >= kFirstProducerWarp ? warp - kFirstProducerWarp : warp - kFirstEpilogueWarp) >> 2) & 1;
+  const int rloc = q * 32 + lane;
+  const int groups = p.BN / 32;
+  int hs = 0;
+  uint32_t hph = 0;
+  auto e1 = [&](int it) {
+    const int b = buf_of(it);
+    mbar_wait(&acc1_full[b], use_of(it) & 1u);
+    tc_fence_after();
+    const uint32_t t_addr = tmem_base + acc1_col(it) + ((uint32_t)(q * 32) << 16);
+    for (int g = 0; g < groups; ++g) {
+      float v[16];
+      __syncwarp();
+      tmem_ld16(t_addr + g * 32 + half * 16, v);
+      tmem_ld_wait();
+      if (g == groups - 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc1_empty[b]);
+      }
+      const int n0 = g * 32 + half * 16;
+      epi_bias(p, v, n0);
+      epi_post(p, v, n0);
+      // 16 channels -> bf16/f16 hi (32 B) and lo (32 B) halves of this row of the K-chunk operand tile
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float x0 = v[2 * i], x1 = v[2 * i + 1];
+        if (p2.mode == MODE_BF16X3) {   // H is the 1x1 conv's A operand: its format
+          hi[i] = pack_bf16(x0, x1);
+          const __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&hi[i]);
+          lo[i] = pack_bf16(x0 - __low2float(h), x1 - __high2float(h));
+        } else {
+          hi[i] = pack_f16(x0, x1);
+          const __half2 h = *reinterpret_cast<__half2*>(&hi[i]);
+          lo[i] = pack_f16(x0 - __low2float(h), x1 - __high2float(h));
+        }
+      }
+      mbar_wait(&h_free[hs], hph ^ 1u);
+      uint8_t* stage = sH + (size_t)hs * kEpiStageBytes;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        *reinterpret_cast<uint4*>(stage + sw128_offset((uint32_t)rloc, (uint32_t)(half * 2 + c))) =
+            make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+        *reinterpret_cast<uint4*>(stage + sw128_offset((uint32_t)rloc, (uint32_t)(4 + half * 2 + c))) =
+            make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&h_full[hs]);
+      if (++hs == kHStages) { hs = 0; hph ^= 1u; }
+    }
+  };
+
   if (warp == 0) {
     // ===================================================================== weight producer (W1 and W2 tiles, MMA order)
     if (elect_one()) {
       int ws = 0;
       uint32_t wph = 0;
-      auto push = [&](const float* src) {
+      const uint32_t w1_bytes = (uint32_t)p.BN * (p.w_hi_only ? 64u : 128u), w2_bytes = (uint32_t)p.BN * (p2.w_hi_only ? 64u : 128u);
+      auto push = [&](const float* src, uint32_t bytes) {
         mbar_wait(&w_empty[ws], wph ^ 1u);
-        mbar_arrive_expect_tx(&w_full[ws], w_stage_bytes);
-        bulk_g2s(sW + (size_t)ws * w_stage_bytes, src, w_stage_bytes, &w_full[ws]);
+        mbar_arrive_expect_tx(&w_full[ws], bytes);
+        bulk_g2s(sW + (size_t)ws * w_stage_bytes, src, bytes, &w_full[ws]);
         if (++ws == L.w_stages) { ws = 0; wph ^= 1u; }
       };
       auto w1 = [&]() {
         for (int kci = 0; kci < n_kc; ++kci)
           for (int j = 0; j < p.n_taps; ++j)
-            push(p.W + (size_t)(p.taps[j].tile_base + kci) * (size_t)p.w_tile_floats);
+            push(p.W + (size_t)(p.taps[j].tile_base + kci) * (size_t)p.w_tile_floats, w1_bytes);
       };
       auto w2 = [&]() {
-        for (int g = 0; g < n_kc; ++g) push(p2.W + (size_t)g * (size_t)p2.w_tile_floats);
+        for (int g = 0; g < n_kc; ++g) push(p2.W + (size_t)g * (size_t)p2.w_tile_floats, w2_bytes);
       };
       if (dbl) {
         if (my_tiles > 0) w1();
@@ -678,15 +738,19 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
     if (elect_one()) {
-      const uint32_t idesc = idesc_f16(kBM, p.BN, p.mode == MODE_BF16X3 ? 1 : 0);
+      // the two convs may use different operand modes (k7: one fp16 product, 1x1: bf16 three-pass split)
+      const uint32_t idesc1 = idesc_f16(kBM, p.BN, p.mode == MODE_BF16X3 ? 1 : 0);
+      const uint32_t idesc2 = idesc_f16(kBM, p.BN, p2.mode == MODE_BF16X3 ? 1 : 0);
       const uint64_t a_desc0 = desc_at(smem_u32(sA)), w_desc0 = desc_at(smem_u32(sW)), h_desc0 = desc_at(smem_u32(sH));
+      // hi-only weight tiles are SWIZZLE_64B images: same address bits, different layout / SBO fields
+      const uint64_t w1_fix = p.w_hi_only ? (kDescSw64Base ^ kDescSw128Base) : 0ull;
+      const uint64_t w2_fix = p2.w_hi_only ? (kDescSw64Base ^ kDescSw128Base) : 0ull;
       const uint32_t a_stage_u = a_stage_bytes >> 4, w_stage_u = w_stage_bytes >> 4, h_stage_u = kEpiStageBytes >> 4;
       const uint32_t tap_u = (uint32_t)p.dense_step * 8u;
       int ws = 0, as = 0, hs = 0;
       uint32_t wph = 0, aph = 0, hph = 0;
       uint64_t a_desc = a_desc0, w_desc = w_desc0, h_desc = h_desc0;
-      const int passes = p.passes;
-      auto mma6 = [&](uint32_t d_tmem, uint64_t a0, uint64_t b0, uint32_t acc) {
+      auto mma6 = [&](uint32_t d_tmem, uint64_t a0, uint64_t b0, uint32_t acc, int passes, uint32_t idesc) {
         if (passes == 3) {
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
@@ -724,7 +788,7 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
             if (j) a_tap += tap_u;
             mbar_wait(&w_full[ws], wph);
             tc_fence_after();
-            mma6(d_tmem, a_tap, w_desc, acc);
+            mma6(d_tmem, a_tap, w_desc ^ w1_fix, acc, p.passes, idesc1);
             acc = 1;
             next_w();
           }
@@ -743,7 +807,7 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
           mbar_wait(&h_full[hs], hph);
           mbar_wait(&w_full[ws], wph);
           tc_fence_after();
-          mma6(d_tmem, h_desc, w_desc, g ? 1u : 0u);
+          mma6(d_tmem, h_desc, w_desc ^ w2_fix, g ? 1u : 0u, p2.passes, idesc2);
           next_w();
           tc_commit(&h_free[hs]);
           h_desc += h_stage_u;
@@ -793,62 +857,10 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       }
     }
   } else if (warp < kFirstProducerWarp) {
-    // ===================================================================== epilogue warps: E1 (acc1 -> H stages), E2 (acc2 -> y)
-    const int q = warp & 3;
-    const int half = (warp - kFirstEpilogueWarp) >> 2;
-    const int rloc = q * 32 + lane;
-    const int groups = p.BN / 32;
+    // ===================================================================== epilogue warps: E2 (acc2 -> y); E1 too when single-buffered
     const bool leader = warp == kFirstEpilogueWarp && lane == 0;
-    int hs = 0, es = 0, prev = -1;
-    uint32_t hph = 0, eph = 0;
-    auto e1 = [&](int it) {
-      const int b = buf_of(it);
-      mbar_wait(&acc1_full[b], use_of(it) & 1u);
-      tc_fence_after();
-      const uint32_t t_addr = tmem_base + acc1_col(it) + ((uint32_t)(q * 32) << 16);
-      for (int g = 0; g < groups; ++g) {
-        float v[16];
-        __syncwarp();
-        tmem_ld16(t_addr + g * 32 + half * 16, v);
-        tmem_ld_wait();
-        if (g == groups - 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc1_empty[b]);
-        }
-        const int n0 = g * 32 + half * 16;
-        epi_bias(p, v, n0);
-        epi_post(p, v, n0);
-        // 16 channels -> bf16/f16 hi (32 B) and lo (32 B) halves of this row of the K-chunk operand tile
-        uint32_t hi[8], lo[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float x0 = v[2 * i], x1 = v[2 * i + 1];
-          if (p.mode == MODE_BF16X3) {
-            hi[i] = pack_bf16(x0, x1);
-            const __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&hi[i]);
-            lo[i] = pack_bf16(x0 - __low2float(h), x1 - __high2float(h));
-          } else {
-            hi[i] = pack_f16(x0, x1);
-            const __half2 h = *reinterpret_cast<__half2*>(&hi[i]);
-            lo[i] = pack_f16(x0 - __low2float(h), x1 - __high2float(h));
-          }
-        }
-        mbar_wait(&h_free[hs], hph ^ 1u);
-        uint8_t* stage = sH + (size_t)hs * kEpiStageBytes;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          *reinterpret_cast<uint4*>(stage + sw128_offset((uint32_t)rloc, (uint32_t)(half * 2 + c))) =
-              make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
-          *reinterpret_cast<uint4*>(stage + sw128_offset((uint32_t)rloc, (uint32_t)(4 + half * 2 + c))) =
-              make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&h_full[hs]);
-        if (++hs == kHStages) { hs = 0; hph ^= 1u; }
-      }
-    };
+    int es = 0, prev = -1;
+    uint32_t eph = 0;
     auto e2 = [&](int it) {
       const int tile = (int)blockIdx.x + it * (int)gridDim.x;
       const int bb = tile / p.m_tiles_per_clip;
@@ -894,8 +906,7 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       }
     };
     if (dbl) {
-      if (my_tiles > 0) e1(0);
-      for (int it = 0; it < my_tiles; ++it) { if (it + 1 < my_tiles) e1(it + 1); e2(it); }
+      for (int it = 0; it < my_tiles; ++it) e2(it);          // E1 runs on the transform warps (below)
     } else {
       for (int it = 0; it < my_tiles; ++it) { e1(it); e2(it); }
     }
@@ -908,7 +919,7 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
     const int rows_needed = kBM + p.span;
     int as = 0;
     uint32_t aph = 0;
-    for (int it = 0; it < my_tiles; ++it) {
+    auto transform_tile = [&]() {
       for (int kci = 0; kci < n_kc; ++kci) {
         const int ai = ((p.kc_begin + kci) * 32 + c * 4) % p.alpha_period;
         const float4 al = __ldg(reinterpret_cast<const float4*>(p.alpha + ai));
@@ -950,6 +961,16 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
         if (lane == 0) mbar_arrive(&a_full[as]);
         if (++as == L.a_stages) { as = 0; aph ^= 1u; }
       }
+    };
+    if (dbl) {
+      // operands of tile it+1 first (the MMA thread issues k7(it+1) before 1x1(it)), then drain acc1 of tile it
+      if (my_tiles > 0) transform_tile();
+      for (int it = 0; it < my_tiles; ++it) {
+        if (it + 1 < my_tiles) transform_tile();
+        e1(it);
+      }
+    } else {
+      for (int it = 0; it < my_tiles; ++it) transform_tile();
     }
   }
 
@@ -1095,14 +1116,22 @@ typedef void (*RuKernel)(const ConvGemmParams, const ConvGemmParams, const UmmaL
 
 // Measured (profiles/r01_layers_dac_b16x30s_fusedru.txt): fusion wins while both accumulators can be double-buffered in
 // TMEM (C <= 128); the single-buffered variant (128 < C <= 256) loses to two launches, so it is off by default.
+static int ru_fuse_wide_max_c() {
+  static const int v = getenv("NC_RU_FUSE_WIDE_MAX_C") ? atoi(getenv("NC_RU_FUSE_WIDE_MAX_C")) : 256;
+  return v > 256 ? 256 : v;
+}
 static int ru_fuse_max_c() {
   static const int v = getenv("NC_RU_FUSE_MAX_C") ? atoi(getenv("NC_RU_FUSE_MAX_C")) : 128;
   return v;
 }
 
 bool ru_fused_supported(const ConvGemmParams& p, const ConvGemmParams& p2) {
-  return (p.mode == MODE_BF16X3 || p.mode == MODE_F16X3) && p2.mode == p.mode && p2.passes == p.passes && !p.w_hi_only && !p2.w_hi_only && p.n_tiles == 1 && p2.n_tiles == 1 &&
-         p.BN == p2.BN && p.BN % 32 == 0 && p.BN <= ru_fuse_max_c() && p.n_total == p.BN && p.n_valid == p.BN && p.dense_step >= 0 &&
+  const bool h16 = (p.mode == MODE_BF16X3 || p.mode == MODE_F16X3) && (p2.mode == MODE_BF16X3 || p2.mode == MODE_F16X3);
+  // C <= 128: both accumulators double-buffered.  128 < C <= 256: one tile in flight (acc1 + acc2 fill TMEM); the k7
+  // MMAs are then exposed to the acc1 drain, which only pays when they are short: one-pass fp16 k7 convs only.
+  const bool width_ok = p.BN <= ru_fuse_max_c() || (p.BN <= ru_fuse_wide_max_c() && p.passes == 1);
+  return h16 && width_ok && p.n_tiles == 1 && p2.n_tiles == 1 &&
+         p.BN == p2.BN && p.BN % 32 == 0 && p.n_total == p.BN && p.n_valid == p.BN && p.dense_step >= 0 &&
          p.prologue == PRO_SNAKE && p2.n_taps == 1 && p2.n_kc == p.n_kc && p.kc_begin == 0 && p.span <= 64 &&
          p.a_pitch == p.BN && umma_view_ok(p) && p.d_valid == (long long)p.m_rows * p.n_total && p.d_clip_stride % 4 == 0 &&
          !p.noise && (reinterpret_cast<uintptr_t>(p.D) & 15) == 0;
@@ -1114,7 +1143,7 @@ int launch_ru_fused(const ConvGemmParams& p, const ConvGemmParams& p2, int num_s
   if (!ru_fused_supported(p, p2)) return -1;
   UmmaLaunch L;
   const int rows = ((kBM + p.span) + 7) / 8 * 8;
-  const long a_stage = (long)rows * 128, w_stage = (long)p.BN * 128;
+  const long a_stage = (long)rows * 128, w_stage = (long)p.BN * ((p.w_hi_only && p2.w_hi_only) ? 64 : 128);
   const long budget = (long)kUmmaMaxDynSmem - 1024 - (long)(kHStages + kEpiStages) * kEpiStageBytes;
   int as = 2, ws = 2;
   if (as * a_stage + ws * w_stage > budget) return -1;

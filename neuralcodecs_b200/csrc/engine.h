@@ -130,9 +130,9 @@ class DacEngine : public Engine {
 
   DacConfig cfg_;
   // Encoder: three-pass bf16 split everywhere (codes must match the fp32 reference).  Decoder: the wide layers
-  // (k > 1 convs and transposed convs with more than 128 channels -- the MMA-bound ones) take one fp16 product,
-  // everything else the three-pass split: 69.7 dB against the fp32 oracle (gate 60 dB) at +21 % throughput
-  // (profiles/r01_decoder_precision_modes.txt).  decoder_precision=<mode> makes the decoder uniform again.
+  // (convs, transposed convs and residual units with more than 128 channels -- blocks 0-2 and decoder.conv1) take one
+  // fp16 product, everything else the three-pass split: 68.6 dB against the fp32 oracle (gate 60 dB), +26 % sustained
+  // throughput (profiles/r01_decoder_precision_modes.txt).  decoder_precision=<mode> makes the decoder uniform again.
   Precision enc_prec_ = PREC_BF16X3, dec_prec_ = PREC_BF16X3, dec_wide_prec_ = PREC_F16;
   bool dec_boost_ = true;
   // encoder

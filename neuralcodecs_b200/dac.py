@@ -117,7 +117,7 @@ class DAC:
         d = self.describe()
         wide = d.get("decoder_wide_precision", d["decoder_precision"])
         dec = d["decoder_precision"] if wide == d["decoder_precision"] else \
-            f"{wide} on k>1 / transposed convs wider than 128 channels, {d['decoder_precision']} elsewhere"
+            f"{wide} on layers wider than 128 channels, {d['decoder_precision']} elsewhere"
         return (f"encoder {d['encoder_precision']}, decoder {dec}"
                 + (" (+3xtf32 on narrow 1x1 / final conv)" if d.get("decoder_boost") and d["decoder_precision"] == "tf32" else ""))
 

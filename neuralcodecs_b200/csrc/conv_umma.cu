@@ -627,7 +627,7 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
     for (int i = 0; i < kMaxAStages; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&a_full[i], kProducerWarps); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < kMaxWStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], kEpilogueWarps);
+      mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], kEpilogueWarps);   // one warp set drains acc1 (see split_a)
       mbar_init(&acc2_full[i], 1); mbar_init(&acc2_empty[i], kEpilogueWarps);
     }
     for (int i = 0; i < kHStages; ++i) { mbar_init(&h_full[i], kEpilogueWarps); mbar_init(&h_free[i], 1); }
@@ -659,17 +659,26 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
   const int groups = p.BN / 32;
   int hs = 0;
   uint32_t hph = 0;
-  auto e1 = [&](int it) {
+  // 32-column groups [0, split_a) are drained by the transform warps, [split_a, groups) by the epilogue warps.
+  // Measured (B200, C = 64 / 96 / 128): everything on the transform warps when double-buffered beats both the
+  // original all-on-epilogue-warps split and a half/half split (7.1 vs 7.6 vs 7.6 ms at C = 64): the units are bound
+  // by the per-tile dependency chain with two tiles in flight, not by either warp set's throughput.
+  const int split_a = (p.BN <= 128) ? groups : 0;
+  auto e1 = [&](int it, int g_begin, int g_end) {
     const int b = buf_of(it);
     mbar_wait(&acc1_full[b], use_of(it) & 1u);
     tc_fence_after();
     const uint32_t t_addr = tmem_base + acc1_col(it) + ((uint32_t)(q * 32) << 16);
     for (int g = 0; g < groups; ++g) {
+      if (g < g_begin || g >= g_end) {   // the other warp set's group: only advance the ring position
+        if (++hs == kHStages) { hs = 0; hph ^= 1u; }
+        continue;
+      }
       float v[16];
       __syncwarp();
       tmem_ld16(t_addr + g * 32 + half * 16, v);
       tmem_ld_wait();
-      if (g == groups - 1) {
+      if (g == g_end - 1) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc1_empty[b]);
@@ -906,9 +915,9 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       }
     };
     if (dbl) {
-      for (int it = 0; it < my_tiles; ++it) e2(it);          // E1 runs on the transform warps (below)
+      for (int it = 0; it < my_tiles; ++it) e2(it);          // E1 runs on the transform warps (split_a == groups)
     } else {
-      for (int it = 0; it < my_tiles; ++it) { e1(it); e2(it); }
+      for (int it = 0; it < my_tiles; ++it) { e1(it, 0, groups); e2(it); }
     }
     if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else {
@@ -967,7 +976,7 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       if (my_tiles > 0) transform_tile();
       for (int it = 0; it < my_tiles; ++it) {
         if (it + 1 < my_tiles) transform_tile();
-        e1(it);
+        if (split_a > 0) e1(it, 0, split_a);
       }
     } else {
       for (int it = 0; it < my_tiles; ++it) transform_tile();

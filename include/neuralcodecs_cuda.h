@@ -231,6 +231,13 @@ NC_API nc_status nc_snac_process_audio(nc_handle h, const float* audio, int32_t 
                                        int32_t sample_rate, const float* const* noise, uint64_t seed,
                                        float* audio_out, int64_t out_capacity, int64_t* out_length);
 
+/* replaces: DACUnpickler.LoadWithConfig / CreateConfigFromMetadata Config/DAC/DACUnpickler.cs:383-424 (reading the
+ * checkpoint's metadata to build the config BEFORE the model exists).  Host only, no handle: JSON
+ * {"format": "torch_zip"|"safetensors", "metadata": {...}, "tensors": {name: {"dtype", "shape"}}} into buf.
+ * nc_load_weights itself accepts both formats: .safetensors (HF DacModel or native names) and torch.save zip
+ * checkpoints such as the official DAC .pth ({"state_dict", "metadata"}; DACUnpickler.LoadFromStream :341-381). */
+NC_API nc_status nc_inspect_weights(const char* path, char* buf, size_t buf_size);
+
 /* -- input conditioning (any handle; runs on that handle's device and stream) ------- */
 /* replaces: AudioUtils.ResampleLinear NeuralCodecs.Core/Utils/AudioUtils.cs:329-352 (= SNAC.ResampleAudio
  * Models/SNAC.cs:284-308).  *out_length = (int64)(length * dst/src); out == NULL only reports it. */

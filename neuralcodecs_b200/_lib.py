@@ -102,6 +102,7 @@ SIGNATURES = {
     "nc_encodec_forward": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_float, _P, _P]),
     "nc_encodec_forward_dev": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_float, _P, _P]),
     "nc_snac_process_audio": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int32, _P, C.c_uint64, _P, C.c_int64, _I64]),
+    "nc_inspect_weights": (C.c_int, [C.c_char_p, C.c_char_p, C.c_size_t]),
     "nc_resample_linear": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int64, _I64]),
     "nc_convert_to_mono": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P]),
     "nc_encodec_ecdc_size": (C.c_int, [_P, C.c_int64, C.c_float, _I64, _I64]),

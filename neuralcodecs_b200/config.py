@@ -63,6 +63,26 @@ class DACConfig:
                 setattr(cfg, cls._JSON[k], v)
         return cfg
 
+    @classmethod
+    def FromWeights(cls, path: str) -> "DACConfig":
+        """DACUnpickler.LoadWithConfig / CreateConfigFromMetadata (Config/DAC/DACUnpickler.cs:383-424): the config stored in an
+        official DAC `.pth` checkpoint ({"metadata": {"kwargs": {...}}}); keys and defaults as the reference reads them
+        (the reference looks the keys up at the top level of the metadata; descript-audio-codec stores them under
+        "kwargs", so both places are searched)."""
+        from . import inspect_weights
+        meta = inspect_weights(path)["metadata"] or {}
+        kw = dict(meta.get("kwargs") or {})
+        kw.update({k: v for k, v in meta.items() if k != "kwargs"})
+        cfg = cls()
+        for key, attr in (("sample_rate", "sample_rate"), ("sampling_rate", "sample_rate"), ("encoder_dim", "encoder_dim"),
+                          ("latent_dim", "latent_dim"), ("encoder_rates", "encoder_rates"), ("decoder_rates", "decoder_rates"),
+                          ("decoder_dim", "decoder_dim"), ("n_codebooks", "num_codebooks"), ("codebook_size", "codebook_size"),
+                          ("codebook_dim", "codebook_dim"), ("quantizer_dropout", "quantizer_dropout")):
+            if kw.get(key) is not None:
+                v = kw[key]
+                setattr(cfg, attr, list(v) if isinstance(v, (list, tuple)) else v)
+        return cfg
+
     # presets: DACConfig.cs:102-136
     @classmethod
     def DAC44kHz(cls) -> "DACConfig":

@@ -4,6 +4,7 @@
 #include <new>
 
 #include "ecdc.h"
+#include "pth_reader.h"
 #include "engine.h"
 
 using namespace nc;
@@ -513,6 +514,39 @@ nc_status nc_encodec_forward_dev(nc_handle h, const float* audio_dev, int32_t ba
     if (!audio_dev) throw Error(NC_INVALID_ARGUMENT, "audio is null");
     BusyGuard g(e);
     e->forward_dev(audio_dev, batch, length, e->n_q_for_bandwidth(bandwidth_kbps), audio_out_dev, codes_dev);
+  });
+}
+
+// ------------------------------------------------------------------------------------ weight files (host only)
+nc_status nc_inspect_weights(const char* path, char* buf, size_t buf_size) {
+  return guarded([&] {
+    if (!path) throw Error(NC_INVALID_ARGUMENT, "path is null");
+    if (!buf || buf_size == 0) throw Error(NC_INVALID_ARGUMENT, "null buffer");
+    FILE* fp = std::fopen(path, "rb");
+    if (!fp) throw Error(NC_FILE_NOT_FOUND, std::string("weights not found at ") + path);
+    std::fclose(fp);
+    TensorMap tm;
+    std::string meta = "{}";
+    const bool zip = is_torch_zip(path);
+    if (zip) load_torch_zip(path, &tm, &meta); else load_safetensors(path, &tm);
+    std::string s = std::string("{\"format\": \"") + (zip ? "torch_zip" : "safetensors") + "\", \"metadata\": " + meta + ", \"tensors\": {";
+    bool first = true;
+    for (auto& kv : tm) {
+      s += first ? "\"" : ", \"";
+      first = false;
+      s += kv.first + "\": {\"dtype\": \"" + (kv.second.is_int ? "int64" : "float32") + "\", \"shape\": [";
+      for (size_t i = 0; i < kv.second.shape.size(); ++i) s += (i ? ", " : "") + std::to_string(kv.second.shape[i]);
+      // position-weighted checksum of the converted values: sum_i (i % 7 + 1) * x_i in double
+      double cs = 0;
+      if (kv.second.is_int) for (size_t i = 0; i < kv.second.i64.size(); ++i) cs += (double)(i % 7 + 1) * (double)kv.second.i64[i];
+      else for (size_t i = 0; i < kv.second.f32.size(); ++i) cs += (double)(i % 7 + 1) * (double)kv.second.f32[i];
+      char cbuf[40];
+      std::snprintf(cbuf, sizeof cbuf, "%.17g", cs);
+      s += std::string("], \"checksum\": ") + cbuf + "}";
+    }
+    s += "}}";
+    if (s.size() + 1 > buf_size) throw Error(NC_INVALID_ARGUMENT, "inspect buffer too small");
+    std::memcpy(buf, s.c_str(), s.size() + 1);
   });
 }
 

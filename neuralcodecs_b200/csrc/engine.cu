@@ -4,6 +4,7 @@
 //   DecoderBlock.cs:20-44, ResidualVectorQuantizer.cs:54-103,211-238
 // with activations channels-last in HBM and every Snake fused into the consuming conv's prologue.
 #include "engine.h"
+#include "pth_reader.h"
 
 #include <cstdlib>
 
@@ -72,7 +73,13 @@ void Engine::set_option(const std::string& key, const std::string& value) {
 
 void Engine::load_weights(const std::string& path) {
   tensors_.clear();
-  load_safetensors(path, &tensors_);
+  weights_metadata_ = "{}";
+  if (is_torch_zip(path)) {
+    load_torch_zip(path, &tensors_, &weights_metadata_);   // DACUnpickler path of the reference (DAC.cs:368-372)
+  } else {
+    load_safetensors(path, &tensors_);
+  }
+  normalize_names();
   finalize_weights();
 }
 
@@ -153,6 +160,81 @@ void DacEngine::set_option(const std::string& key, const std::string& value) {
   } else {
     Engine::set_option(key, value);
   }
+}
+
+// The official `.pth` weights carry descript-audio-codec's nn.Sequential paths (the names the reference's own modules
+// use, Config/DAC/StateDictNameConverter.cs:274-335 maps the HF names onto them); the engine looks tensors up by the HF
+// DacModel names, so translate the other way.  Suffixes (weight_g / weight_v / bias / alpha) are kept.
+static bool dac_native_to_hf(const std::string& key, int n_enc, int n_dec, std::string* out) {
+  auto split = [](const std::string& s) {
+    std::vector<std::string> v;
+    size_t a = 0;
+    for (;;) {
+      const size_t b = s.find('.', a);
+      v.push_back(s.substr(a, b == std::string::npos ? std::string::npos : b - a));
+      if (b == std::string::npos) break;
+      a = b + 1;
+    }
+    return v;
+  };
+  auto join = [](const std::vector<std::string>& v, size_t from) {
+    std::string s;
+    for (size_t i = from; i < v.size(); ++i) s += "." + v[i];
+    return s;
+  };
+  auto num = [](const std::string& s, int* x) {
+    if (s.empty() || s.find_first_not_of("0123456789") != std::string::npos) return false;
+    *x = std::atoi(s.c_str());
+    return true;
+  };
+  static const char* kUnit[4] = {"snake1", "conv1", "snake2", "conv2"};
+  const auto t = split(key);
+  int i = 0, u = 0, k = 0;
+  if (t.size() >= 4 && t[0] == "encoder" && t[1] == "block" && num(t[2], &i)) {
+    if (i == 0) { *out = "encoder.conv1" + join(t, 3); return true; }
+    if (i == n_enc + 1) { *out = "encoder.snake1" + join(t, 3); return true; }
+    if (i == n_enc + 2) { *out = "encoder.conv2" + join(t, 3); return true; }
+    if (i >= 1 && i <= n_enc && t.size() >= 6 && t[3] == "block" && num(t[4], &u)) {
+      const std::string blk = "encoder.block." + std::to_string(i - 1);
+      if (u == 3) { *out = blk + ".snake1" + join(t, 5); return true; }
+      if (u == 4) { *out = blk + ".conv1" + join(t, 5); return true; }
+      if (u >= 0 && u <= 2 && t.size() >= 8 && t[5] == "block" && num(t[6], &k) && k >= 0 && k <= 3) {
+        *out = blk + ".res_unit" + std::to_string(u + 1) + "." + kUnit[k] + join(t, 7);
+        return true;
+      }
+    }
+    return false;
+  }
+  if (t.size() >= 4 && t[0] == "decoder" && t[1] == "model" && num(t[2], &i)) {
+    if (i == 0) { *out = "decoder.conv1" + join(t, 3); return true; }
+    if (i == n_dec + 1) { *out = "decoder.snake1" + join(t, 3); return true; }
+    if (i == n_dec + 2) { *out = "decoder.conv2" + join(t, 3); return true; }
+    if (i >= 1 && i <= n_dec && t.size() >= 6 && t[3] == "block" && num(t[4], &u)) {
+      const std::string blk = "decoder.block." + std::to_string(i - 1);
+      if (u == 0) { *out = blk + ".snake1" + join(t, 5); return true; }
+      if (u == 1) { *out = blk + ".conv_t1" + join(t, 5); return true; }
+      if (u >= 2 && u <= 4 && t.size() >= 8 && t[5] == "block" && num(t[6], &k) && k >= 0 && k <= 3) {
+        *out = blk + ".res_unit" + std::to_string(u - 1) + "." + kUnit[k] + join(t, 7);
+        return true;
+      }
+    }
+    return false;
+  }
+  return false;
+}
+
+void DacEngine::normalize_names() {
+  TensorMap& tm = tensors_mut();
+  if (!tm.count("decoder.model.0.weight_v") && !tm.count("encoder.block.0.weight_v") && !tm.count("decoder.model.0.weight")) return;
+  TensorMap renamed;
+  for (auto& kv : tm) {
+    std::string hf;
+    if (dac_native_to_hf(kv.first, (int)cfg_.encoder_rates.size(), (int)cfg_.decoder_rates.size(), &hf))
+      renamed[hf] = std::move(kv.second);
+    else
+      renamed[kv.first] = std::move(kv.second);
+  }
+  tm.swap(renamed);
 }
 
 void DacEngine::require_ready() const {

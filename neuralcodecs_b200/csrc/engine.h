@@ -21,7 +21,8 @@ class Engine {
   virtual void set_option(const std::string& key, const std::string& value);
   virtual std::string describe() const = 0;
 
-  void load_weights(const std::string& path);
+  void load_weights(const std::string& path);   // .safetensors or a torch.save zip checkpoint (.pth / .bin)
+  const std::string& weights_metadata() const { return weights_metadata_; }
   void set_tensor(const std::string& name, HostTensor&& t) { tensors_[name] = std::move(t); }
   void bind() const;  // cudaSetDevice
   LaunchCtx ctx();
@@ -37,6 +38,9 @@ class Engine {
   const HostTensor& tensor(const std::string& name) const;
   bool has_tensor(const std::string& name) const { return tensors_.count(name) != 0; }
   void drop_tensors() { tensors_.clear(); }
+  // hook: translate a checkpoint's native parameter names into the names finalize_weights() looks up
+  virtual void normalize_names() {}
+  TensorMap& tensors_mut() { return tensors_; }
 
   int device_ = 0;
   int num_sms_ = 148;
@@ -45,6 +49,7 @@ class Engine {
   uint64_t launches_ = 0;
   size_t max_workspace_bytes_ = (size_t)32 << 30;
   TensorMap tensors_;
+  std::string weights_metadata_ = "{}";
   bool ready_ = false;
 };
 
@@ -77,6 +82,7 @@ class DacEngine : public Engine {
   ~DacEngine() override;
   const char* codec_name() const override { return "DAC"; }
   void finalize_weights() override;
+  void normalize_names() override;   // descript-audio-codec module paths -> HF DacModel names
   void set_option(const std::string& key, const std::string& value) override;
   const DacConfig& config() const { return cfg_; }
   std::string describe() const override;

@@ -277,3 +277,70 @@ def test_dia_handoff_revert_delay_clamp_and_ragged_batch(dac_mid):
     with pytest.raises(ValueError):
         m.DecodeDia(gen, np.array([56, 1, 1, 1, 1]), delay)          # longer than T - max(delay)
     m.Dispose()
+
+
+# ------------------------------------------------------------------------------------------------ official .pth checkpoints
+def _hf_to_descript(name, n_enc, n_dec):
+    """Inverse of the engine's name translation = the reference's HF -> module-path map (StateDictNameConverter.cs:274-335)."""
+    unit = {"snake1": 0, "conv1": 1, "snake2": 2, "conv2": 3}
+    t = name.split(".")
+    if t[0] == "encoder":
+        if t[1] == "conv1": return ".".join(["encoder.block.0"] + t[2:])
+        if t[1] == "snake1": return ".".join([f"encoder.block.{n_enc + 1}"] + t[2:])
+        if t[1] == "conv2": return ".".join([f"encoder.block.{n_enc + 2}"] + t[2:])
+        i = int(t[2])
+        if t[3].startswith("res_unit"):
+            return ".".join([f"encoder.block.{i + 1}.block.{int(t[3][8:]) - 1}.block.{unit[t[4]]}"] + t[5:])
+        return ".".join([f"encoder.block.{i + 1}.block.{3 if t[3] == 'snake1' else 4}"] + t[4:])
+    if t[0] == "decoder":
+        if t[1] == "conv1": return ".".join(["decoder.model.0"] + t[2:])
+        if t[1] == "snake1": return ".".join([f"decoder.model.{n_dec + 1}"] + t[2:])
+        if t[1] == "conv2": return ".".join([f"decoder.model.{n_dec + 2}"] + t[2:])
+        i = int(t[2])
+        if t[3].startswith("res_unit"):
+            return ".".join([f"decoder.model.{i + 1}.block.{int(t[3][8:]) + 1}.block.{unit[t[4]]}"] + t[5:])
+        return ".".join([f"decoder.model.{i + 1}.block.{0 if t[3] == 'snake1' else 1}"] + t[4:])
+    return name
+
+
+def test_official_pth_checkpoint_loads_like_the_safetensors_file(dac_mid, tmp_path):
+    """nc_load_weights on a torch.save checkpoint with descript-audio-codec module paths and weight_g / weight_v pairs
+    (what the reference's DACUnpickler reads, DAC.cs:368-372) reproduces the model of the HF safetensors file."""
+    import collections
+    import neuralcodecs_b200 as nc
+    co, ce, path = dac_mid
+    from safetensors.torch import load_file
+    hf = load_file(path)
+    n_enc, n_dec = len(co.encoder_rates), len(co.decoder_rates)
+    sd = collections.OrderedDict()
+    for k, v in hf.items():
+        v = torch.as_tensor(v)
+        dk = _hf_to_descript(k, n_enc, n_dec)
+        if k.endswith(".weight") and v.dim() == 3:                       # weight-normed conv: v = w, g = ||w|| (fp32 of a double sum)
+            ss = v.double().pow(2).sum(dim=(1, 2), keepdim=True)
+            sd[dk[:-len("weight")] + "weight_g"] = ss.float().sqrt()
+            sd[dk[:-len("weight")] + "weight_v"] = v.clone()
+        else:
+            sd[dk] = v.clone()
+    pth = str(tmp_path / "weights_16khz.pth")
+    torch.save({"state_dict": sd, "metadata": {"kwargs": {"encoder_dim": co.encoder_dim, "encoder_rates": list(co.encoder_rates),
+               "decoder_dim": co.decoder_dim, "decoder_rates": list(co.decoder_rates), "n_codebooks": co.n_codebooks,
+               "codebook_size": co.codebook_size, "codebook_dim": co.codebook_dim, "sample_rate": co.sample_rate}}}, pth)
+    cfg = nc.DACConfig.FromWeights(pth)
+    assert (cfg.encoder_dim, cfg.decoder_dim, cfg.num_codebooks, cfg.codebook_size, cfg.sample_rate) == \
+        (ce.encoder_dim, ce.decoder_dim, ce.num_codebooks, ce.codebook_size, ce.sample_rate)
+    x = _audio(co, 2, 9000)
+    outs = []
+    for p, c in ((path, ce), (pth, cfg)):
+        with nc.DAC(c) as m:
+            m.LoadWeights(p)
+            outs.append(m.forward(x[:, None, :]))
+    # weight_g here comes from torch's double reduction, the engine's own norm from a sequential one: 1-ulp differences in
+    # g are two legitimately different files, so codes must agree and audio to ~1e-5 (a wrong name map gives garbage)
+    assert (outs[0]["codes"] == outs[1]["codes"]).mean() >= 0.999
+    np.testing.assert_allclose(outs[0]["audio"], outs[1]["audio"], atol=2e-5)
+    assert snr_db(outs[0]["audio"], outs[1]["audio"]) >= 80.0
+    with nc.DAC(ce) as m, pytest.raises(RuntimeError, match="Failed to load"):
+        bad = str(tmp_path / "bad.pth")
+        torch.save({"state_dict": collections.OrderedDict(x=torch.zeros(1))}, bad)
+        m.LoadWeights(bad)

@@ -55,6 +55,11 @@ internal static unsafe partial class Native
     [LibraryImport(Lib)] internal static partial NcStatus nc_snac_encode(NcHandle h, float* audio, int batch, long length, long** codes);
     [LibraryImport(Lib)] internal static partial NcStatus nc_snac_decode(NcHandle h, long** codes, int batch, long frames, float** noise, ulong seed, float* audio);
     [LibraryImport(Lib)] internal static partial NcStatus nc_snac_forward(NcHandle h, float* audio, int batch, long length, float** noise, ulong seed, float* audioOut, long** codes);
+    [LibraryImport(Lib)] internal static partial NcStatus nc_snac_process_audio(NcHandle h, float* audio, int batch, long length, int sampleRate, float** noise, ulong seed, float* audioOut, long outCapacity, out long outLength);
+    // weight files and input conditioning (Config/DAC/DACUnpickler.cs, NeuralCodecs.Core/Utils/AudioUtils.cs)
+    [LibraryImport(Lib, StringMarshalling = StringMarshalling.Utf8)] internal static partial NcStatus nc_inspect_weights(string path, byte* buf, nuint bufSize);
+    [LibraryImport(Lib)] internal static partial NcStatus nc_resample_linear(NcHandle h, float* audio, int batch, long length, int srcRate, int dstRate, float* output, long outCapacity, out long outLength);
+    [LibraryImport(Lib)] internal static partial NcStatus nc_convert_to_mono(NcHandle h, float* interleaved, long frames, int channels, float* output);
     // Encodec (Models/Encodec.cs, Modules/Encodec/EncodecCompressor.cs)
     [LibraryImport(Lib)] internal static partial NcStatus nc_encodec_query_shapes(NcHandle h, long length, float bandwidthKbps, out long frames, out int nQ, out long decodedLength);
     [LibraryImport(Lib)] internal static partial NcStatus nc_encodec_encode(NcHandle h, float* audio, int batch, long length, float bandwidthKbps, long* codes);

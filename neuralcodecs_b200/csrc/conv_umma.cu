@@ -662,7 +662,9 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
   // 32-column groups [0, split_a) are drained by the transform warps, [split_a, groups) by the epilogue warps.
   // Measured (B200, C = 64 / 96 / 128): everything on the transform warps when double-buffered beats both the
   // original all-on-epilogue-warps split and a half/half split (7.1 vs 7.6 vs 7.6 ms at C = 64): the units are bound
-  // by the per-tile dependency chain with two tiles in flight, not by either warp set's throughput.
+  // at C = 64 by shared-memory bandwidth (tensor-core operand reads of the three-pass split: ~1.1 MB of smem traffic
+  // per 128-row tile = 83 % of 128 B/clk), not by either warp set's throughput; a 4-deep accumulator ring (C <= 64)
+  // measured no faster than 2-deep and was dropped.
   const int split_a = (p.BN <= 128) ? groups : 0;
   auto e1 = [&](int it, int g_begin, int g_end) {
     const int b = buf_of(it);

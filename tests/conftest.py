@@ -50,6 +50,18 @@ def dac_mid(cache_dir):
 
 
 @pytest.fixture(scope="session")
+def dac_24k_geometry(cache_dir):
+    """The 24 kHz preset's geometry (odd stride 5: rates 2,4,5,8 / 8,5,4,2; DACConfig.cs:113-124) at reduced width."""
+    from oracle import dac as odac
+    import neuralcodecs_b200 as nc
+    co = odac.DACConfig(sample_rate=24000, encoder_dim=32, encoder_rates=[2, 4, 5, 8], decoder_dim=512, decoder_rates=[8, 5, 4, 2],
+                        n_codebooks=6, codebook_size=128)
+    ce = nc.DACConfig(sample_rate=24000, encoder_dim=32, encoder_rates=[2, 4, 5, 8], decoder_dim=512, decoder_rates=[8, 5, 4, 2],
+                      num_codebooks=6, codebook_size=128)
+    return co, ce, _write_weights(co, os.path.join(cache_dir, "dac_24k_geometry.safetensors"), "data", 1.0)
+
+
+@pytest.fixture(scope="session")
 def dac_full(cache_dir):
     """DAC 44.1 kHz preset (BASELINE configs #1/#4/#5) with seeded weights + data-fitted codebooks."""
     from oracle import dac as odac

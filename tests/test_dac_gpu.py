@@ -279,6 +279,25 @@ def test_dia_handoff_revert_delay_clamp_and_ragged_batch(dac_mid):
     m.Dispose()
 
 
+@pytest.mark.parametrize("options", [{"encoder_precision": "fp32", "decoder_precision": "fp32"}, None])
+def test_odd_stride_24khz_preset_geometry(dac_24k_geometry, options):
+    """Stride-5 strided conv (k 10, pad 3) and transposed conv (5T - 1 samples: the reference passes no output_padding,
+    SURVEY App. A) -- the 24 kHz / 16 kHz presets' shape algebra, fp32 path and default tensor-core path."""
+    o, m = _models(dac_24k_geometry, options)
+    co = dac_24k_geometry[0]
+    for length in (7000, 320 * 9):
+        x = _audio(co, 2, length)
+        ref = _oracle_forward(o, x)
+        out = m.forward(x[:, None, :])
+        a_ref = ref["audio"].numpy()
+        assert out["codes"].shape == tuple(ref["codes"].shape) and out["audio"].shape == a_ref.shape, (out["audio"].shape, a_ref.shape)
+        _check_codes(o, ref, out["codes"])
+        a_dec = m.Decode(ref["z"].numpy())
+        assert a_dec.shape == a_ref.shape
+        assert np.abs(a_dec - a_ref).max() <= MAX_ABS and snr_db(a_ref, a_dec) >= MIN_SNR_DB
+    m.Dispose()
+
+
 # ------------------------------------------------------------------------------------------------ official .pth checkpoints
 def _hf_to_descript(name, n_enc, n_dec):
     """Inverse of the engine's name translation = the reference's HF -> module-path map (StateDictNameConverter.cs:274-335)."""

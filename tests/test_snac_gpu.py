@@ -202,3 +202,26 @@ def test_input_conditioning_matches_the_reference_loops_bit_for_bit(snac_tiny):
     ref, _ = m.forward(rs, None, 7)
     np.testing.assert_array_equal(y, ref.reshape(2, -1))
     m.Dispose()
+
+
+def test_pytorch_model_bin_loads_like_safetensors(snac_tiny, tmp_path):
+    """hubertsiuzdak/snac_* ship `pytorch_model.bin` (torch.save of a bare state dict, SURVEY 8b weight contract; the
+    reference reads it with load_py, Models/SNAC.cs:216-231): same tensors -> bit-identical model."""
+    import neuralcodecs_b200 as nc
+    from safetensors.torch import load_file
+    from oracle import synth
+    co, ce, path = snac_tiny
+    sd = load_file(path)
+    binp = str(tmp_path / "pytorch_model.bin")
+    torch.save(dict(sd), binp)
+    assert nc.inspect_weights(binp)["format"] == "torch_zip"
+    x = synth.synth_audio(2, 5000, co.sample_rate, first_clip=4)
+    outs = []
+    for p in (path, binp):
+        with nc.SNAC(ce) as m:
+            m.LoadWeights(p)
+            audio, codes = m.forward(x, None, 11)
+            outs.append((audio, codes))
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert np.array_equal(a, b)

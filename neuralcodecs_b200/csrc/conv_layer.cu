@@ -368,6 +368,14 @@ bool ConvLayer::fill_umma(const ConvRunArgs& a, ConvGemmParams* pp) const {
   std::memcpy(p.tap_mask, tap_mask_, sizeof tap_mask_);
   p.n_kc = n_kc_; p.kc_begin = kc_begin_; p.smin = smin_; p.span = span_;
   p.dense_step = dense_step_;
+  if (a.dw_w) {
+    // fused depthwise prologue: plain 1x1 stride-1 conv only; the A tile carries a halo of 3*dil rows on each side and
+    // the transform warps leave the GEMM operand in stage rows [0, 128) (tap 0 of the dense path reads from row 0)
+    if (s.k != 1 || s.stride != 1 || s.transposed || p.n_taps != 1 || a.prologue != PRO_SNAKE || 6 * a.dw_dil > 64) return false;
+    p.dw_w = a.dw_w; p.dw_b = a.dw_b; p.dw_post_alpha = a.dw_post_alpha; p.dw_post_inv_alpha = a.dw_post_inv_alpha;
+    p.dw_dil = a.dw_dil;
+    p.smin = -3 * a.dw_dil; p.span = 6 * a.dw_dil; p.dense_step = 0;
+  }
   p.batch = a.batch; p.m_tiles_per_clip = (m_rows + 127) / 128;
   const int fast = g_fast_sin >= 0 ? g_fast_sin : ((mode_ == PREC_TF32 || mode_ == PREC_BF16X3 || mode_ == PREC_F16X2 || mode_ == PREC_F16) ? 1 : 0);
   p.precise_sin = fast ? 0 : 1;
@@ -420,8 +428,10 @@ void ConvLayer::run(const ConvRunArgs& a, const LaunchCtx& ctx) const {
   ConvGemmParams up;
   if (fill_umma(a, &up)) {
     check_launch(launch_conv_umma(up, ctx.num_sms, ctx.stream), name_.c_str());
-    ctx.end(ev, std::string("conv_umma_") + precision_name(mode_), fl, bytes, name_);
+    ctx.end(ev, std::string(a.dw_w ? "conv_umma_dw_" : "conv_umma_") + precision_name(mode_),
+            fl + (a.dw_w ? 2.0 * 7 * s.cin * (double)a.t_in * a.batch : 0.0), bytes, name_);
   } else {
+    if (a.dw_w) throw Error(NC_INTERNAL, "depthwise-fused conv is only available on the tcgen05 path");
     ConvSimtParams p{};
     p.A = a.in; p.a_clip_stride = a_stride; p.a_rows = a_rows; p.a_pitch = k_view_; p.a_valid = a_valid;
     p.D = a.out; p.R = a.residual; p.d_clip_stride = d_stride; p.m_rows = m_rows; p.n_total = n_total;

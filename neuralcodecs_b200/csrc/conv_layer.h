@@ -44,6 +44,13 @@ struct ConvRunArgs {
   // Lets callers keep margin rows around each clip (Encodec's reflect padding is materialised there).
   long long in_clip_stride = 0;
   long long out_clip_stride = 0;
+  // depthwise k7 conv (+ Snake after it) evaluated inside this 1x1 conv's operand prologue (tcgen05 path only):
+  // in -> prologue Snake -> depthwise(dw_w [7][Cin], dw_b, dilation dw_dil) -> Snake(dw_post_*) -> this conv
+  const float* dw_w = nullptr;
+  const float* dw_b = nullptr;
+  const float* dw_post_alpha = nullptr;
+  const float* dw_post_inv_alpha = nullptr;
+  int dw_dil = 1;
 };
 
 class ConvLayer {

@@ -75,6 +75,13 @@ struct ConvGemmParams {
   int n_tiles;
   int tiles_per_ntile;
   int mode;                 // MmaMode
+  // Optional depthwise k7 conv folded into the operand prologue of a 1x1 conv (SNAC ResidualUnit):
+  //   operand[t, c] = snake2(dw_b[c] + sum_j dw_w[j][c] * snake1(x[t + (j-3)*dw_dil, c]))      (zero padding)
+  // snake1 = alpha / inv_alpha above (prologue must be PRO_SNAKE), snake2 = dw_post_*.  smin / span describe the halo.
+  const float* dw_w;        // [7][Cin] (null = no depthwise stage)
+  const float* dw_b;        // [Cin] or null
+  const float* dw_post_alpha; const float* dw_post_inv_alpha;   // [Cin] or null
+  int dw_dil;
   int w_hi_only;            // 16-bit modes with passes < 3: weight tiles are [BN][32 hi halves] = 64-byte rows (SWIZZLE_64B)
   int passes;               // 16-bit modes: 3 = hi*hi + lo*hi + hi*lo, 2 = hi*hi + lo(A)*hi, 1 = hi*hi only
   int n_taps;

@@ -535,6 +535,71 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
         }
         uint8_t* stage = sA + (size_t)as * a_stage_bytes;
         mbar_wait(&raw_full[as], aph);
+        if (OPS == O_H16X3 && p.dw_w != nullptr) {
+          // ---- depthwise k7 conv folded into the operand prologue (SNAC ResidualUnit; conv_plan.h)
+          // phase 1: Snake on every row of the tile (halo included), fp32 in place.  OOB rows are TMA zero fill and
+          // snake(0) = 0, which is exactly the conv's zero padding.
+#pragma unroll
+          for (int i = 0; i < RIT; ++i) {
+            const int rho = rho0 + 32 * i;
+            if (rho < rows_needed) {
+              float4* ptr = reinterpret_cast<float4*>(stage + sw128_offset((uint32_t)rho, (uint32_t)c));
+              *ptr = prologue4<PRO>(*ptr, al, ia);
+            }
+          }
+          asm volatile("bar.sync 2, %0;" ::"n"(kProducerWarps * 32) : "memory");
+          // phase 2: 7 taps per output; output row o reads stage rows o + j*dil
+          const int ch = (p.kc_begin + kci) * 32 + c * 4;
+          const int d = p.dw_dil;
+          float4 acc[kBM / 32];
+          const float4 bb = p.dw_b ? __ldg(reinterpret_cast<const float4*>(p.dw_b + ch)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < kBM / 32; ++i) acc[i] = bb;
+#pragma unroll
+          for (int j = 0; j < 7; ++j) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(p.dw_w + (size_t)j * p.alpha_period + ch));
+#pragma unroll
+            for (int i = 0; i < kBM / 32; ++i) {
+              const float4 x = *reinterpret_cast<const float4*>(stage + sw128_offset((uint32_t)(rho0 + 32 * i + j * d), (uint32_t)c));
+              acc[i].x = fmaf(w.x, x.x, acc[i].x); acc[i].y = fmaf(w.y, x.y, acc[i].y);
+              acc[i].z = fmaf(w.z, x.z, acc[i].z); acc[i].w = fmaf(w.w, x.w, acc[i].w);
+            }
+          }
+          if (p.dw_post_alpha) {
+            const float4 pa = __ldg(reinterpret_cast<const float4*>(p.dw_post_alpha + ch));
+            const float4 pi = __ldg(reinterpret_cast<const float4*>(p.dw_post_inv_alpha + ch));
+#pragma unroll
+            for (int i = 0; i < kBM / 32; ++i)
+              acc[i] = p.precise_sin ? prologue4<P_SNAKE_PRECISE>(acc[i], pa, pi) : prologue4<P_SNAKE_FAST>(acc[i], pa, pi);
+          }
+          asm volatile("bar.sync 2, %0;" ::"n"(kProducerWarps * 32) : "memory");
+          // phase 3: hi | lo operand halves into stage rows [0, 128)
+#pragma unroll
+          for (int i = 0; i < kBM / 32; ++i) {
+            const int rho = rho0 + 32 * i;
+            const float4 x = acc[i];
+            uint2 hi, lo;
+            if (p.mode == MODE_BF16X3) {
+              hi.x = pack_bf16(x.x, x.y); hi.y = pack_bf16(x.z, x.w);
+              const __nv_bfloat162 h0 = *reinterpret_cast<__nv_bfloat162*>(&hi.x), h1 = *reinterpret_cast<__nv_bfloat162*>(&hi.y);
+              lo.x = pack_bf16(x.x - __low2float(h0), x.y - __high2float(h0));
+              lo.y = pack_bf16(x.z - __low2float(h1), x.w - __high2float(h1));
+            } else {
+              hi.x = pack_f16(x.x, x.y); hi.y = pack_f16(x.z, x.w);
+              const __half2 h0 = *reinterpret_cast<__half2*>(&hi.x), h1 = *reinterpret_cast<__half2*>(&hi.y);
+              lo.x = pack_f16(x.x - __low2float(h0), x.y - __high2float(h0));
+              lo.y = pack_f16(x.z - __low2float(h1), x.w - __high2float(h1));
+            }
+            const uint32_t sub = (uint32_t)(c & 1) * 8u;
+            *reinterpret_cast<uint2*>(stage + sw128_offset((uint32_t)rho, (uint32_t)(c >> 1)) + sub) = hi;
+            *reinterpret_cast<uint2*>(stage + sw128_offset((uint32_t)rho, 4u + (uint32_t)(c >> 1)) + sub) = lo;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_full[as]);
+          if (++as == L.a_stages) { as = 0; aph ^= 1u; }
+          continue;
+        }
         float4 cur[RIT];
 #pragma unroll
         for (int i = 0; i < RIT; ++i) {

@@ -250,6 +250,7 @@ class SnacEngine : public Engine {
 
   SnacConfig cfg_;
   Precision prec_ = PREC_BF16X3;
+  bool fuse_dw_ = true;   // depthwise conv folded into the 1x1 conv's operand prologue (tcgen05 path)
   int dzp_ = 0;  // padded latent dim
   float* d_conv_in_w_ = nullptr;
   float* d_conv_in_b_ = nullptr;

@@ -116,6 +116,8 @@ void SnacEngine::set_option(const std::string& key, const std::string& value) {
   if (key == "precision" || key == "encoder_precision" || key == "decoder_precision") {
     prec_ = parse_precision(value);
     if (ready_) throw Error(NC_INVALID_ARGUMENT, "precision options must be set before weights are loaded");
+  } else if (key == "fuse_dw") {
+    fuse_dw_ = value == "1" || value == "true";
   } else {
     Engine::set_option(key, value);
   }
@@ -442,6 +444,20 @@ int SnacEngine::micro_batch(int B, int64_t Lp) {
 int SnacEngine::run_ru(const ResUnit& ru, int cur, int B, int T, const SnakeParams* post) {
   const LaunchCtx c = ctx();
   const int h = (cur + 1) % 3, y = (cur + 2) % 3;
+  if (cfg_.depthwise && fuse_dw_ && ru.dw.C == ru.c2.spec().cin) {
+    // whole unit in one launch: Snake -> depthwise k7 -> Snake evaluated by the 1x1 conv's operand-transform warps,
+    // x read once as operand (+ halo) and once as residual, y written once (5 -> 3 HBM passes per unit)
+    ConvRunArgs f;
+    f.in = buf(cur); f.out = buf(y); f.residual = buf(cur); f.batch = B; f.t_in = T;
+    f.prologue = PRO_SNAKE; f.alpha = ru.s1.alpha; f.inv_alpha = ru.s1.inv_alpha;
+    f.dw_w = ru.dw.w; f.dw_b = ru.dw.b; f.dw_dil = ru.dw.dil; f.dw_post_alpha = ru.s2.alpha; f.dw_post_inv_alpha = ru.s2.inv_alpha;
+    if (post) { f.post = PRO_SNAKE; f.post_alpha = post->alpha; f.post_inv_alpha = post->inv_alpha; }
+    ConvGemmParams probe;
+    if (ru.c2.fill_umma(f, &probe)) {
+      ru.c2.run(f, c);
+      return y;
+    }
+  }
   if (cfg_.depthwise) {
     launch_dwconv7(buf(cur), buf(h), T, ru.dw.C, ru.dw.w, ru.dw.b, ru.dw.dil, ru.s1.alpha, ru.s2.alpha, B, c, ru.dw.name.c_str(),
                    prec_ != PREC_FP32 && prec_ != PREC_3XTF32);

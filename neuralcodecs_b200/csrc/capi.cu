@@ -1,6 +1,8 @@
 // C ABI of libneuralcodecs_cuda.so (include/neuralcodecs_cuda.h).  No exception crosses the
 // boundary; the last error message is kept per thread.
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <new>
 
 #include "ecdc.h"
@@ -54,13 +56,72 @@ DacEngine* dac_of(nc_handle h) {
   return static_cast<DacEngine*>(h->engine);
 }
 
-// scoped device allocation for the host-pointer entry points
+// Scoped device staging buffer for the host-pointer entry points.  cudaMalloc / cudaFree cost milliseconds and
+// serialise the device, so freed blocks go to a small per-device cache and repeated calls with the same shapes (the
+// steady state of a serving loop) allocate nothing.  A block returns to the cache only from the destructor, i.e.
+// after the entry point synchronised on every use of it.
+class StagingCache {
+ public:
+  void* take(int dev, size_t bytes) {
+    std::lock_guard<std::mutex> g(mu_);
+    auto& pool = pools_[dev];
+    auto it = pool.lower_bound(bytes);
+    if (it != pool.end() && it->first <= bytes + bytes / 4 + (1u << 20)) {
+      void* p = it->second;
+      cached_ -= it->first;
+      sizes_[p] = it->first;
+      pool.erase(it);
+      return p;
+    }
+    return nullptr;
+  }
+  void remember(void* p, size_t bytes) { std::lock_guard<std::mutex> g(mu_); sizes_[p] = bytes; }
+  // true when the block was cached (caller must not free it)
+  bool give(int dev, void* p) {
+    std::lock_guard<std::mutex> g(mu_);
+    auto it = sizes_.find(p);
+    if (it == sizes_.end()) return false;
+    const size_t bytes = it->second;
+    sizes_.erase(it);
+    if (cached_ + bytes > kMaxCached) return false;
+    pools_[dev].emplace(bytes, p);
+    cached_ += bytes;
+    return true;
+  }
+  // release every cached block of a device (nc_destroy: a destroyed model leaves no device memory behind)
+  void trim(int dev) {
+    std::lock_guard<std::mutex> g(mu_);
+    auto it = pools_.find(dev);
+    if (it == pools_.end()) return;
+    for (auto& kv : it->second) { cached_ -= kv.first; cudaFree(kv.second); }
+    it->second.clear();
+  }
+ private:
+  static constexpr size_t kMaxCached = (size_t)12 << 30;
+  std::mutex mu_;
+  std::map<int, std::multimap<size_t, void*>> pools_;
+  std::map<void*, size_t> sizes_;
+  size_t cached_ = 0;
+};
+StagingCache& staging_cache() { static StagingCache* c = new StagingCache(); return *c; }   // never destroyed: outlives the CUDA context safely
+
 struct DevMem {
   void* p = nullptr;
+  int dev = 0;
   explicit DevMem(size_t bytes) {
-    if (bytes) NC_CUDA(cudaMalloc(&p, bytes));
+    if (!bytes) return;
+    cudaGetDevice(&dev);
+    p = staging_cache().take(dev, bytes);
+    if (!p) {
+      NC_CUDA(cudaMalloc(&p, bytes));
+      staging_cache().remember(p, bytes);
+    }
   }
-  ~DevMem() { cudaFree(p); }
+  ~DevMem() {
+    if (p && !staging_cache().give(dev, p)) cudaFree(p);
+  }
+  DevMem(const DevMem&) = delete;
+  DevMem& operator=(const DevMem&) = delete;
   template <typename T>
   T* as() { return static_cast<T*>(p); }
 };
@@ -100,6 +161,12 @@ nc_status nc_create(nc_codec_kind kind, const void* cfg, size_t cfg_size, int de
 nc_status nc_destroy(nc_handle h) {
   return guarded([&] {
     if (!h) return;
+    if (h->engine) {
+      h->engine->bind();
+      int dev = 0;
+      cudaGetDevice(&dev);
+      staging_cache().trim(dev);
+    }
     delete h->engine;
     delete h;
   });

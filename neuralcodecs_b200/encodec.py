@@ -165,6 +165,11 @@ class Encodec:
                                                  out.ctypes.data_as(C.c_void_p), None), "Encodec", "Encoding")
         return out
 
+    def forward_host(self, audio_ptr: int, batch: int, length: int, audio_out_ptr: int, codes_ptr: int = 0) -> None:
+        """nc_encodec_forward on caller-owned HOST buffers given as raw addresses (e.g. pinned torch tensors' data_ptr())."""
+        _lib.check(_lib.lib().nc_encodec_forward(self._handle(), audio_ptr, batch, length, float(self._config.bandwidth),
+                                                 audio_out_ptr, codes_ptr or None), "Encodec", "Encoding")
+
     def forward_dev(self, audio_ptr: int, batch: int, length: int, audio_out_ptr: int, codes_ptr: int = 0) -> None:
         _lib.check(_lib.lib().nc_encodec_forward_dev(self._handle(), audio_ptr, batch, length, float(self._config.bandwidth),
                                                      audio_out_ptr or None, codes_ptr or None), "Encodec", "Encoding")

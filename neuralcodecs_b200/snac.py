@@ -198,6 +198,15 @@ class SNAC:
         from .audio_utils import ResampleLinear
         return ResampleLinear(self, x, src, dst)
 
+    # ------------------------------------------------------------------ raw host-pointer variant
+    def forward_host(self, audio_ptr: int, batch: int, length: int, audio_out_ptr: int, code_ptrs: Optional[Sequence[int]] = None,
+                     seed: int = 0) -> None:
+        """nc_snac_forward on caller-owned HOST buffers given as raw addresses (e.g. pinned torch tensors' data_ptr());
+        H2D / D2H copies happen inside the call.  Noise is drawn on the device from `seed`."""
+        cp = (C.c_void_p * max(len(code_ptrs), 1))(*[p or None for p in code_ptrs]) if code_ptrs else None
+        _lib.check(_lib.lib().nc_snac_forward(self._handle(), audio_ptr, batch, length, None, seed, audio_out_ptr, cp),
+                   "SNAC", "Encoding")
+
     # ------------------------------------------------------------------ device-pointer variant
     def forward_dev(self, audio_ptr: int, batch: int, length: int, audio_out_ptr: int, code_ptrs: Sequence[int],
                     noise_ptrs: Optional[Sequence[int]] = None, seed: int = 0) -> None:

@@ -25,6 +25,28 @@ internal unsafe struct NcDacConfig
     public int NCodebooks, CodebookSize, CodebookDim, LatentDim;
 }
 
+[StructLayout(LayoutKind.Sequential)]
+internal unsafe struct NcSnacConfig      // nc_snac_config (include/neuralcodecs_cuda.h)
+{
+    public uint StructSize;
+    public int SampleRate, EncoderDim, NEncoderRates;
+    public fixed int EncoderRates[8];
+    public int DecoderDim, NDecoderRates;
+    public fixed int DecoderRates[8];
+    public int LatentDim, AttnWindowSize, CodebookSize, CodebookDim, NVqStrides;
+    public fixed int VqStrides[8];
+    public int Noise, Depthwise;
+}
+
+[StructLayout(LayoutKind.Sequential)]
+internal unsafe struct NcEncodecConfig   // nc_encodec_config
+{
+    public uint StructSize;
+    public int SampleRate, Channels, NFilters, Dimension, NRatios;
+    public fixed int Ratios[8];
+    public int NResidualLayers, LstmLayers, CodebookSize, NQuantizers, Causal;
+}
+
 internal sealed class NcHandle : SafeHandle
 {
     public NcHandle() : base(IntPtr.Zero, true) { }

@@ -1075,7 +1075,7 @@ size_t umma_smem_bytes(const ConvGemmParams& p, UmmaLaunch* L) {
   // A stages buy bytes in flight from HBM, W stages hide L2 latency of the weight stream
   int as = 2, ws = 2;
   if (as * a_stage + ws * w_stage > budget) return 0;
-  static const int w_first = getenv("NC_W_FIRST") ? atoi(getenv("NC_W_FIRST")) : 4;
+  static const int w_first = std::min(std::max(getenv("NC_W_FIRST") ? atoi(getenv("NC_W_FIRST")) : 4, 2), kMaxWStages);   // tuning knob, clamped
   for (;;) {
     bool grew = false;
     if (ws < w_first && as * a_stage + (ws + 1) * w_stage <= budget) { ++ws; grew = true; }

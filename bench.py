@@ -362,7 +362,11 @@ def run_other_codec(args, codec: str, rank: int, local_rank: int, world: int):
                        "gbs": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1)} for k, v in rep.items()}
         top = max(rep.items(), key=lambda kv: kv[1]["ms"])
         k, v = top
-        if k.startswith("conv_umma") or k.startswith("conv_simt") or k == "lstm_layer":
+        # a tcgen05 conv launch can sit under either roof (SNAC's 1x1 / depthwise-fused units move far more bytes than
+        # they multiply): report the roof it is closer to
+        hbm_frac = v["bytes"] / v["ms"] / 1e6 / peaks["hbm_gbs"]
+        tc_frac = v["flops"] / v["ms"] / 1e9 / peaks["bf16_tflops_sustained"]
+        if (k.startswith("conv_umma") and tc_frac >= hbm_frac) or k.startswith("conv_simt") or k == "lstm_layer":
             peak = peaks["bf16_tflops_sustained"] if k.startswith("conv_umma") else 70.0
             ach = v["flops"] / v["ms"] / 1e9
             roofline = {"bound": "tensor", "kernel": k, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,

@@ -178,6 +178,14 @@ conv_simt_kernel(const __grid_constant__ ConvSimtParams p) {
     have = next;
   }
 
+  // per-column constants once per thread (the integer modulo is ~20 instructions; it used to run per output element)
+  float bj[TN], pj[TN];
+#pragma unroll
+  for (int j = 0; j < TN; ++j) {
+    const int n = n0 + (TN == 8 ? (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4)) : tx * TN + j);
+    bj[j] = (p.bias && n < p.n_valid) ? __ldg(p.bias + n % p.bias_period) : 0.f;
+    pj[j] = (p.post == PRO_SNAKE && n < p.n_valid) ? __ldg(p.post_alpha + n % p.post_period) : 0.f;
+  }
 #pragma unroll
   for (int i = 0; i < STM; ++i) {
     const int row = m0 + ty * STM + i;
@@ -190,11 +198,9 @@ conv_simt_kernel(const __grid_constant__ ConvSimtParams p) {
     for (int j = 0; j < TN; ++j) {
       const int n = n0 + (TN == 8 ? (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4)) : tx * TN + j);
       if (n >= p.n_valid || row_off + n >= p.d_valid) continue;
-      float x = acc[i][j];
-      if (p.bias) x += __ldg(p.bias + n % p.bias_period);
+      float x = acc[i][j] + bj[j];
       if (Rrow) x = p.noise ? fmaf(nz, x, Rrow[n]) : x + Rrow[n];
-      if (p.post != PRO_NONE)
-        x = simt_prologue(x, p.post == PRO_SNAKE ? __ldg(p.post_alpha + n % p.post_period) : 0.f, p.post);
+      if (p.post != PRO_NONE) x = simt_prologue(x, pj[j], p.post);
       if (p.act == ACT_TANH) x = tanhf(x);
       Drow[n] = x;
     }
@@ -322,6 +328,13 @@ conv_simt_k3_kernel(const __grid_constant__ ConvSimtParams p) {
     buf ^= 1;
   }
 
+  float bj[TN], pj[TN];
+#pragma unroll
+  for (int j = 0; j < TN; ++j) {
+    const int n = n0 + tx * TN + j;
+    bj[j] = (p.bias && n < p.n_valid) ? __ldg(p.bias + n % p.bias_period) : 0.f;
+    pj[j] = (p.post == PRO_SNAKE && n < p.n_valid) ? __ldg(p.post_alpha + n % p.post_period) : 0.f;
+  }
 #pragma unroll
   for (int i = 0; i < STM; ++i) {
     const int row = m0 + ty * STM + i;
@@ -333,11 +346,9 @@ conv_simt_k3_kernel(const __grid_constant__ ConvSimtParams p) {
     for (int j = 0; j < TN; ++j) {
       const int n = n0 + tx * TN + j;
       if (n >= p.n_valid || row_off + n >= p.d_valid) continue;
-      float x = acc[i][j];
-      if (p.bias) x += __ldg(p.bias + n % p.bias_period);
+      float x = acc[i][j] + bj[j];
       if (Rrow) x += Rrow[n];
-      if (p.post != PRO_NONE)
-        x = simt_prologue(x, p.post == PRO_SNAKE ? __ldg(p.post_alpha + n % p.post_period) : 0.f, p.post);
+      if (p.post != PRO_NONE) x = simt_prologue(x, pj[j], p.post);
       if (p.act == ACT_TANH) x = tanhf(x);
       Drow[n] = x;
     }

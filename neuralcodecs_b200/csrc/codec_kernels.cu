@@ -24,10 +24,12 @@ conv_cin1_kernel(const float* __restrict__ in, long long in_stride, int in_len, 
 #pragma unroll
     for (int j = 0; j < K; ++j) wr[i][j] = __ldg(w + (4 * c4 + i) * K + j);
   }
-  const long long total_t = (long long)batch * t_out;
-  for (long long bt = (long long)blockIdx.x * lanes_t + tl; bt < total_t; bt += (long long)gridDim.x * lanes_t) {
-    const int t = (int)(bt % t_out);
-    const int b = (int)(bt / t_out);
+  // (clip, time) walked incrementally: one 64-bit division per thread instead of one per output step
+  const long long bt0 = (long long)blockIdx.x * lanes_t + tl, step = (long long)gridDim.x * lanes_t;
+  int b = (int)(bt0 / t_out), t = (int)(bt0 - (long long)b * t_out);
+  const int step_b = (int)(step / t_out), step_t = (int)(step - (long long)step_b * t_out);
+  for (; b < batch; b += step_b, t += step_t) {
+    if (t >= t_out) { t -= t_out; ++b; if (b >= batch) break; }
     const float* x = in + (long long)b * in_stride;
     float a0 = br[0], a1 = br[1], a2 = br[2], a3 = br[3];
 #pragma unroll

@@ -247,8 +247,10 @@ lstm_layer_kernel(const float* __restrict__ xproj, long long xproj_clip_stride, 
     const float* hprev = hbuf + (size_t)((t + 1) & 1) * bpad * H;   // written at step t-1 (zeros at t = 0)
     float* hnext = hbuf + (size_t)(t & 1) * bpad * H;
     const float xi = nxi, xf = nxf, xg = nxg, xo = nxo, sk = nsk;
-    for (int i = tid; i < kLB * (H / 4); i += 256) {
-      const int bb = i / (H / 4), k4 = i % (H / 4);
+    // H == 512 (checked at launch): 128 float4 per clip, 8 fully unrolled loads per thread issued back to back
+#pragma unroll
+    for (int i = tid; i < kLB * 128; i += 256) {
+      const int bb = i >> 7, k4 = i & 127;
       // written by other CTAs during this launch: bypass L1 (ld.global.cg)
       const float4 v = __ldcg(reinterpret_cast<const float4*>(hprev + (size_t)(b0 + bb) * H) + k4);
       *reinterpret_cast<float4*>(&hs[bb][(k4 >> 3) * 36 + 4 * (k4 & 7)]) = v;

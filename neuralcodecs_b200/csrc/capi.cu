@@ -44,10 +44,10 @@ nc_status guarded(F&& f) {
 struct BusyGuard {
   Engine* e;
   explicit BusyGuard(Engine* eng) : e(eng) {
-    if (e->busy) throw Error(NC_INVALID_ARGUMENT, "handle is in use by another call (handles are not re-entrant)");
-    e->busy = true;
+    if (e->busy.exchange(true, std::memory_order_acquire))
+      throw Error(NC_INVALID_ARGUMENT, "handle is in use by another call (handles are not re-entrant)");
   }
-  ~BusyGuard() { e->busy = false; }
+  ~BusyGuard() { e->busy.store(false, std::memory_order_release); }
 };
 
 DacEngine* dac_of(nc_handle h) {

@@ -1,5 +1,6 @@
 // Engine objects behind an nc_handle.
 #pragma once
+#include <atomic>
 #include <memory>
 #include <string>
 #include <vector>
@@ -32,7 +33,7 @@ class Engine {
   cudaStream_t stream() const { return stream_; }
 
   // re-entrancy guard (a handle is one-thread-at-a-time)
-  bool busy = false;
+  std::atomic<bool> busy{false};   // set for the duration of an entry point (BusyGuard): handles are not re-entrant
 
  protected:
   const HostTensor& tensor(const std::string& name) const;

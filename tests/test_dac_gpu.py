@@ -363,3 +363,54 @@ def test_official_pth_checkpoint_loads_like_the_safetensors_file(dac_mid, tmp_pa
         bad = str(tmp_path / "bad.pth")
         torch.save({"state_dict": collections.OrderedDict(x=torch.zeros(1))}, bad)
         m.LoadWeights(bad)
+
+
+# ------------------------------------------------------------------------------------------------ threading contract
+def test_handles_are_independent_and_not_reentrant(dac_mid):
+    """INTEGRATION.md threading contract: different handles run concurrently from different host threads with results
+    identical to serial execution; a second concurrent call on the SAME handle is refused with INVALID_ARGUMENT
+    (never corrupts the first)."""
+    import threading
+    import neuralcodecs_b200 as nc
+    co, ce, path = dac_mid
+    x = _audio(co, 4, 40000)
+    models = []
+    for _ in range(2):
+        m = nc.DAC(ce)
+        m.LoadWeights(path)
+        models.append(m)
+    serial = [m.forward(x[:, None, :]) for m in models]
+    results, errors = [None, None], []
+
+    def work(i):
+        try:
+            for _ in range(3):
+                results[i] = models[i].forward(x[:, None, :])
+        except Exception as e:      # pragma: no cover
+            errors.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errors
+    for i in range(2):
+        assert np.array_equal(results[i]["codes"], serial[i]["codes"])
+        np.testing.assert_array_equal(results[i]["audio"], serial[i]["audio"])
+    # same handle from two threads: every call either succeeds with the right answer or is refused
+    outcomes = []
+
+    def hammer():
+        for _ in range(4):
+            try:
+                o = models[0].forward(x[:, None, :])
+                outcomes.append(np.array_equal(o["codes"], serial[0]["codes"]))
+            except ValueError as e:
+                outcomes.append("busy" if "in use" in str(e).lower() or "busy" in str(e).lower() or "concurrent" in str(e).lower() else repr(e))
+
+    ts = [threading.Thread(target=hammer) for _ in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert all(o is True or o == "busy" for o in outcomes), outcomes
+    assert any(o is True for o in outcomes)
+    for m in models:
+        m.Dispose()

@@ -3,6 +3,7 @@
 // twin is neuralcodecs_b200/snac.py.
 using System;
 using System.Collections.Generic;
+using System.Linq;
 using NeuralCodecs.Core;
 using NeuralCodecs.Core.Configuration;
 using NeuralCodecs.Core.Exceptions;
@@ -48,55 +49,78 @@ public sealed unsafe class CudaSNAC : INeuralCodec
         return (padded, frames, cl, nl);
     }
 
-    /// SNAC.Encode(float[]) (SNAC.cs:129-150): one code array per VQ stage (codes of the padded audio), batch 1.
-    public List<long[]> Encode(float[] audioData)
+    /// SNAC.Encode(float[]) (Models/SNAC.cs:129-150): one array per VQ stage holding the codes of the padded audio,
+    /// batch 1.  The reference returns the int64 indices cast to float32 (`code.to(torch.float32)`, :147), so this does
+    /// too: a codebook index (< 2^24) is exact in float32.
+    public List<float[]> Encode(float[] audioData) =>
+        EncodeCodes(audioData).ConvertAll(stage => Array.ConvertAll(stage, c => (float)c));
+
+    /// Same codes as integers (what the device produces); no counterpart in the reference's float[] API.
+    public List<long[]> EncodeCodes(float[] audioData)
     {
-        if (audioData is null) throw new ArgumentNullException(nameof(audioData));
+        ArgumentNullException.ThrowIfNull(audioData);                                   // SNAC.cs:131
         var (_, _, cl, _) = Shapes(audioData.Length);
         var codes = new List<long[]>();
         foreach (var n in cl) codes.Add(new long[n]);
-        var ptrs = stackalloc long*[cl.Length];
-        var pins = new System.Runtime.InteropServices.GCHandle[cl.Length];
-        try
+        WithPinned(codes, ptrs =>
         {
-            for (int i = 0; i < cl.Length; i++)
-            {
-                pins[i] = System.Runtime.InteropServices.GCHandle.Alloc(codes[i], System.Runtime.InteropServices.GCHandleType.Pinned);
-                ptrs[i] = (long*)pins[i].AddrOfPinnedObject();
-            }
             fixed (float* a = audioData)
                 Native.Check(Native.nc_snac_encode(_h, a, 1, audioData.Length, ptrs), "SNAC", CodecOperation.Encoding);
-        }
-        finally { foreach (var p in pins) if (p.IsAllocated) p.Free(); }
+        });
         return codes;
     }
 
-    /// SNAC.Decode(List<...>) (SNAC.cs:157-192): audio [frames * hop], not trimmed; NoiseBlock noise drawn on the device from `seed`.
-    public float[] Decode(List<long[]> codes, ulong seed = 0)
+    /// SNAC.Decode(List<float[]>) (Models/SNAC.cs:173-192): codes as float32 arrays (converted to int64 exactly like
+    /// `torch.tensor(code, dtype: torch.int64)`, :185: truncation toward zero), audio [frames * hop], not trimmed.
+    /// NoiseBlock noise is a fresh draw per call, as in the reference (NoiseBlock.cs:38-45).
+    public float[] Decode(List<float[]> codes)
     {
-        if (codes is null || codes.Count == 0) throw new ArgumentException("Codes list cannot be empty or contain null arrays"); // SNAC.cs:177-180
-        long frames = codes[^1].Length * _config.VQStrides[^1];
+        ArgumentNullException.ThrowIfNull(codes);                                       // SNAC.cs:175
+        if (codes.Count == 0 || codes.Any(c => c == null))
+            throw new ArgumentException("Codes list cannot be empty or contain null arrays", nameof(codes));   // SNAC.cs:177-180
+        return Decode(codes.ConvertAll(stage => Array.ConvertAll(stage, c => (long)c)), null);
+    }
+
+    /// Integer codes; `seed` = null draws a fresh 64-bit seed (a new noise realisation per call), a value makes the
+    /// output reproducible and independent of how a batch is split.
+    public float[] Decode(List<long[]> codes, ulong? seed = null)
+    {
+        ArgumentNullException.ThrowIfNull(codes);
+        if (codes.Count == 0 || codes.Any(c => c == null))
+            throw new ArgumentException("Codes list cannot be empty or contain null arrays", nameof(codes));
+        long frames = (long)codes[^1].Length * _config.VQStrides[^1];
         long hop = 1; foreach (var r in _config.EncoderRates) hop *= r;
         var audio = new float[frames * hop];
-        var ptrs = stackalloc long*[codes.Count];
-        var pins = new System.Runtime.InteropServices.GCHandle[codes.Count];
-        try
+        ulong s = seed ?? (ulong)Random.Shared.NextInt64();
+        WithPinned(codes, ptrs =>
         {
-            for (int i = 0; i < codes.Count; i++)
-            {
-                pins[i] = System.Runtime.InteropServices.GCHandle.Alloc(codes[i], System.Runtime.InteropServices.GCHandleType.Pinned);
-                ptrs[i] = (long*)pins[i].AddrOfPinnedObject();
-            }
             fixed (float* pa = audio)
-                Native.Check(Native.nc_snac_decode(_h, ptrs, 1, frames, null, seed, pa), "SNAC", CodecOperation.Decoding);
-        }
-        finally { foreach (var p in pins) if (p.IsAllocated) p.Free(); }
+                Native.Check(Native.nc_snac_decode(_h, ptrs, 1, frames, null, s, pa), "SNAC", CodecOperation.Decoding);
+        });
         return audio;
     }
 
-    /// SNAC.ProcessAudio(float[], sampleRate) (SNAC.cs:255-282): resample on the device when needed, forward, trimmed output.
-    public float[] ProcessAudio(float[] audioData, int sampleRate, ulong seed = 0)
+    private delegate void PinnedCall(long** ptrs);
+    private static void WithPinned(List<long[]> arrays, PinnedCall call)
     {
+        var ptrs = stackalloc long*[arrays.Count];
+        var pins = new System.Runtime.InteropServices.GCHandle[arrays.Count];
+        try
+        {
+            for (int i = 0; i < arrays.Count; i++)
+            {
+                pins[i] = System.Runtime.InteropServices.GCHandle.Alloc(arrays[i], System.Runtime.InteropServices.GCHandleType.Pinned);
+                ptrs[i] = (long*)pins[i].AddrOfPinnedObject();
+            }
+            call(ptrs);
+        }
+        finally { foreach (var p in pins) if (p.IsAllocated) p.Free(); }
+    }
+
+    /// SNAC.ProcessAudio(float[], sampleRate) (SNAC.cs:255-282): resample on the device when needed, forward, trimmed output.
+    public float[] ProcessAudio(float[] audioData, int sampleRate, ulong? noiseSeed = null)
+    {
+        ulong seed = noiseSeed ?? (ulong)Random.Shared.NextInt64();
         if (audioData is null || audioData.Length == 0) throw new ArgumentException("Audio data cannot be empty", nameof(audioData)); // SNAC.cs:257-258
         long n;
         fixed (float* a = audioData)

@@ -118,13 +118,40 @@ struct DevMem {
     }
   }
   ~DevMem() {
-    if (p && !staging_cache().give(dev, p)) cudaFree(p);
+    if (!p) return;
+    // unwinding from an entry point that already queued work on this block: drain the device before another handle
+    // or thread can take the block from the cache
+    if (std::uncaught_exceptions() > 0) cudaDeviceSynchronize();
+    if (!staging_cache().give(dev, p)) cudaFree(p);
   }
   DevMem(const DevMem&) = delete;
   DevMem& operator=(const DevMem&) = delete;
   template <typename T>
   T* as() { return static_cast<T*>(p); }
 };
+
+// Host <-> device staging copies of the host-pointer entry points.  They are issued on the ENGINE's stream (created
+// cudaStreamNonBlocking, so the legacy default stream gives no ordering against it): an H2D copy is stream-ordered
+// before the kernels that read it, a D2H copy after the kernels that wrote it, and the call returns only after the
+// stream drained, so the caller's buffers are complete and reusable.
+void h2d(Engine* e, void* dst, const void* src, size_t bytes) {
+  if (!bytes) return;
+  NC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, e->stream()));
+}
+void d2h(Engine* e, void* dst, const void* src, size_t bytes) {
+  if (!bytes) return;
+  NC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, e->stream()));
+  NC_CUDA(cudaStreamSynchronize(e->stream()));
+}
+void h2d_2d(Engine* e, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height) {
+  if (!width || !height) return;
+  NC_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyHostToDevice, e->stream()));
+}
+void d2h_2d(Engine* e, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height) {
+  if (!width || !height) return;
+  NC_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDeviceToHost, e->stream()));
+  NC_CUDA(cudaStreamSynchronize(e->stream()));
+}
 }  // namespace
 
 extern "C" {
@@ -199,6 +226,7 @@ nc_status nc_set_tensor(nc_handle h, const char* name, int dtype, int rank, cons
     } else {
       throw Error(NC_INVALID_ARGUMENT, "dtype must be 0 (f32) or 1 (i64)");
     }
+    BusyGuard g(h->engine);
     h->engine->set_tensor(name, std::move(t));
   });
 }
@@ -216,6 +244,7 @@ nc_status nc_set_option(nc_handle h, const char* key, const char* value) {
   return guarded([&] {
     if (!h || !h->engine) throw Error(NC_INVALID_ARGUMENT, "null handle");
     if (!key || !value) throw Error(NC_INVALID_ARGUMENT, "null option");
+    BusyGuard g(h->engine);
     h->engine->set_option(key, value);
   });
 }
@@ -259,11 +288,11 @@ nc_status nc_dac_encode(nc_handle h, const float* audio, int32_t batch, int64_t 
     const auto& c = e->config();
     DevMem d_audio((size_t)batch * length * 4), d_z(z ? (size_t)batch * c.latent_dim * T * 4 : 0),
         d_codes(codes ? (size_t)batch * nq * T * 8 : 0), d_lat(latents ? (size_t)batch * nq * c.codebook_dim * T * 4 : 0);
-    NC_CUDA(cudaMemcpy(d_audio.p, audio, (size_t)batch * length * 4, cudaMemcpyHostToDevice));
+    h2d(e, d_audio.p, audio, (size_t)batch * length * 4);
     e->encode_dev(d_audio.as<float>(), batch, length, nq, d_z.as<float>(), d_codes.as<int64_t>(), d_lat.as<float>());
-    if (z) NC_CUDA(cudaMemcpy(z, d_z.p, (size_t)batch * c.latent_dim * T * 4, cudaMemcpyDeviceToHost));
-    if (codes) NC_CUDA(cudaMemcpy(codes, d_codes.p, (size_t)batch * nq * T * 8, cudaMemcpyDeviceToHost));
-    if (latents) NC_CUDA(cudaMemcpy(latents, d_lat.p, (size_t)batch * nq * c.codebook_dim * T * 4, cudaMemcpyDeviceToHost));
+    if (z) d2h(e, z, d_z.p, (size_t)batch * c.latent_dim * T * 4);
+    if (codes) d2h(e, codes, d_codes.p, (size_t)batch * nq * T * 8);
+    if (latents) d2h(e, latents, d_lat.p, (size_t)batch * nq * c.codebook_dim * T * 4);
     if (frames_out) *frames_out = T;
   });
 }
@@ -278,9 +307,9 @@ nc_status nc_dac_decode(nc_handle h, const float* z, int32_t batch, int64_t fram
     const auto& c = e->config();
     const int64_t L = e->decoded_length(frames);
     DevMem d_z((size_t)batch * c.latent_dim * frames * 4), d_a((size_t)batch * L * 4);
-    NC_CUDA(cudaMemcpy(d_z.p, z, (size_t)batch * c.latent_dim * frames * 4, cudaMemcpyHostToDevice));
+    h2d(e, d_z.p, z, (size_t)batch * c.latent_dim * frames * 4);
     e->decode_dev(d_z.as<float>(), batch, frames, d_a.as<float>());
-    NC_CUDA(cudaMemcpy(audio, d_a.p, (size_t)batch * L * 4, cudaMemcpyDeviceToHost));
+    d2h(e, audio, d_a.p, (size_t)batch * L * 4);
   });
 }
 
@@ -294,9 +323,9 @@ nc_status nc_dac_from_codes(nc_handle h, const int64_t* codes, int32_t batch, in
     e->bind();
     const auto& c = e->config();
     DevMem d_c((size_t)batch * n_quantizers * frames * 8), d_z((size_t)batch * c.latent_dim * frames * 4);
-    NC_CUDA(cudaMemcpy(d_c.p, codes, (size_t)batch * n_quantizers * frames * 8, cudaMemcpyHostToDevice));
+    h2d(e, d_c.p, codes, (size_t)batch * n_quantizers * frames * 8);
     e->from_codes_dev(d_c.as<int64_t>(), batch, n_quantizers, frames, d_z.as<float>());
-    NC_CUDA(cudaMemcpy(z, d_z.p, (size_t)batch * c.latent_dim * frames * 4, cudaMemcpyDeviceToHost));
+    d2h(e, z, d_z.p, (size_t)batch * c.latent_dim * frames * 4);
   });
 }
 
@@ -310,9 +339,9 @@ nc_status nc_dac_decode_codes(nc_handle h, const int64_t* codes, int32_t batch, 
     e->bind();
     const int64_t L = e->decoded_length(frames);
     DevMem d_c((size_t)batch * n_quantizers * frames * 8), d_a((size_t)batch * L * 4);
-    NC_CUDA(cudaMemcpy(d_c.p, codes, (size_t)batch * n_quantizers * frames * 8, cudaMemcpyHostToDevice));
+    h2d(e, d_c.p, codes, (size_t)batch * n_quantizers * frames * 8);
     e->decode_codes_dev(d_c.as<int64_t>(), batch, n_quantizers, frames, d_a.as<float>());
-    NC_CUDA(cudaMemcpy(audio, d_a.p, (size_t)batch * L * 4, cudaMemcpyDeviceToHost));
+    d2h(e, audio, d_a.p, (size_t)batch * L * 4);
   });
 }
 
@@ -326,10 +355,10 @@ nc_status nc_dac_decode_dia(nc_handle h, const int64_t* generated, int32_t batch
     e->bind();
     const size_t n = (size_t)batch * steps * channels;
     DevMem d_g(n * 8), d_a((size_t)batch * audio_stride * 4);
-    NC_CUDA(cudaMemcpy(d_g.p, generated, n * 8, cudaMemcpyHostToDevice));
-    NC_CUDA(cudaMemset(d_a.p, 0, (size_t)batch * audio_stride * 4));
+    h2d(e, d_g.p, generated, n * 8);
+    NC_CUDA(cudaMemsetAsync(d_a.p, 0, (size_t)batch * audio_stride * 4, e->stream()));
     e->decode_dia_dev(d_g.as<int64_t>(), batch, steps, channels, delay_pattern, lengths, d_a.as<float>(), audio_stride);
-    NC_CUDA(cudaMemcpy(audio, d_a.p, (size_t)batch * audio_stride * 4, cudaMemcpyDeviceToHost));
+    d2h(e, audio, d_a.p, (size_t)batch * audio_stride * 4);
   });
 }
 
@@ -348,11 +377,11 @@ nc_status nc_dac_forward(nc_handle h, const float* audio, int32_t batch, int64_t
     const auto& c = e->config();
     DevMem d_audio((size_t)batch * length * 4), d_out(audio_out ? (size_t)batch * Lout * 4 : 0),
         d_z(z ? (size_t)batch * c.latent_dim * T * 4 : 0), d_codes(codes ? (size_t)batch * nq * T * 8 : 0);
-    NC_CUDA(cudaMemcpy(d_audio.p, audio, (size_t)batch * length * 4, cudaMemcpyHostToDevice));
+    h2d(e, d_audio.p, audio, (size_t)batch * length * 4);
     e->forward_dev(d_audio.as<float>(), batch, length, nq, d_out.as<float>(), d_codes.as<int64_t>(), d_z.as<float>());
-    if (audio_out) NC_CUDA(cudaMemcpy(audio_out, d_out.p, (size_t)batch * Lout * 4, cudaMemcpyDeviceToHost));
-    if (z) NC_CUDA(cudaMemcpy(z, d_z.p, (size_t)batch * c.latent_dim * T * 4, cudaMemcpyDeviceToHost));
-    if (codes) NC_CUDA(cudaMemcpy(codes, d_codes.p, (size_t)batch * nq * T * 8, cudaMemcpyDeviceToHost));
+    if (audio_out) d2h(e, audio_out, d_out.p, (size_t)batch * Lout * 4);
+    if (z) d2h(e, z, d_z.p, (size_t)batch * c.latent_dim * T * 4);
+    if (codes) d2h(e, codes, d_codes.p, (size_t)batch * nq * T * 8);
     if (frames_out) *frames_out = T;
   });
 }
@@ -426,7 +455,7 @@ static void snac_forward_host(SnacEngine* e, const float* audio, int32_t batch, 
   const int ns = e->n_stages();
   SnacStaging st;
   DevMem d_audio((size_t)batch * length * 4), d_out(audio_out ? (size_t)batch * length * 4 : 0);
-  NC_CUDA(cudaMemcpy(d_audio.p, audio, (size_t)batch * length * 4, cudaMemcpyHostToDevice));
+  h2d(e, d_audio.p, audio, (size_t)batch * length * 4);
   st.codes_dev.assign(ns, nullptr);
   if (codes)
     for (int i = 0; i < ns; ++i)
@@ -440,16 +469,16 @@ static void snac_forward_host(SnacEngine* e, const float* audio, int32_t batch, 
     for (size_t i = 0; i < nl.size(); ++i)
       if (noise[i]) {
         st.mem.push_back(new DevMem((size_t)batch * nl[i] * 4));
-        NC_CUDA(cudaMemcpy(st.mem.back()->p, noise[i], (size_t)batch * nl[i] * 4, cudaMemcpyHostToDevice));
+        h2d(e, st.mem.back()->p, noise[i], (size_t)batch * nl[i] * 4);
         st.noise_dev[i] = st.mem.back()->as<float>();
       }
   e->forward_dev(d_audio.as<float>(), batch, length, st.noise_dev.data(), seed, d_out.as<float>(),
                  codes ? st.codes_dev.data() : nullptr);
-  if (audio_out) NC_CUDA(cudaMemcpy(audio_out, d_out.p, (size_t)batch * length * 4, cudaMemcpyDeviceToHost));
+  if (audio_out) d2h(e, audio_out, d_out.p, (size_t)batch * length * 4);
   if (codes)
     for (int i = 0; i < ns; ++i)
       if (codes[i])
-        NC_CUDA(cudaMemcpy(codes[i], st.codes_dev[i], (size_t)batch * (T / e->config().vq_strides[i]) * 8, cudaMemcpyDeviceToHost));
+        d2h(e, codes[i], st.codes_dev[i], (size_t)batch * (T / e->config().vq_strides[i]) * 8);
 }
 
 nc_status nc_snac_encode(nc_handle h, const float* audio, int32_t batch, int64_t length, int64_t* const* codes) {
@@ -480,7 +509,7 @@ nc_status nc_snac_decode(nc_handle h, const int64_t* const* codes, int32_t batch
       if (!codes[i]) throw Error(NC_INVALID_ARGUMENT, "Codes list cannot be empty or contain null arrays");
       const size_t bytes = (size_t)batch * (frames / e->config().vq_strides[i]) * 8;
       st.mem.push_back(new DevMem(bytes));
-      NC_CUDA(cudaMemcpy(st.mem.back()->p, codes[i], bytes, cudaMemcpyHostToDevice));
+      h2d(e, st.mem.back()->p, codes[i], bytes);
       cdev[i] = st.mem.back()->as<int64_t>();
     }
     const auto nl = e->noise_lengths(frames);
@@ -489,13 +518,13 @@ nc_status nc_snac_decode(nc_handle h, const int64_t* const* codes, int32_t batch
       for (size_t i = 0; i < nl.size(); ++i)
         if (noise[i]) {
           st.mem.push_back(new DevMem((size_t)batch * nl[i] * 4));
-          NC_CUDA(cudaMemcpy(st.mem.back()->p, noise[i], (size_t)batch * nl[i] * 4, cudaMemcpyHostToDevice));
+          h2d(e, st.mem.back()->p, noise[i], (size_t)batch * nl[i] * 4);
           st.noise_dev[i] = st.mem.back()->as<float>();
         }
     const int64_t L = e->decoded_length(frames);
     DevMem d_a((size_t)batch * L * 4);
     e->decode_dev(cdev.data(), batch, frames, st.noise_dev.data(), seed, d_a.as<float>());
-    NC_CUDA(cudaMemcpy(audio, d_a.p, (size_t)batch * L * 4, cudaMemcpyDeviceToHost));
+    d2h(e, audio, d_a.p, (size_t)batch * L * 4);
   });
 }
 
@@ -538,10 +567,10 @@ static void encodec_forward_host(EncodecEngine* e, const float* audio, int32_t b
   const int64_t T = e->frames(length);
   DevMem d_audio((size_t)batch * length * 4), d_out(audio_out ? (size_t)batch * length * 4 : 0),
       d_codes(codes ? (size_t)batch * nq * T * 8 : 0);
-  NC_CUDA(cudaMemcpy(d_audio.p, audio, (size_t)batch * length * 4, cudaMemcpyHostToDevice));
+  h2d(e, d_audio.p, audio, (size_t)batch * length * 4);
   e->forward_dev(d_audio.as<float>(), batch, length, nq, d_out.as<float>(), d_codes.as<int64_t>());
-  if (audio_out) NC_CUDA(cudaMemcpy(audio_out, d_out.p, (size_t)batch * length * 4, cudaMemcpyDeviceToHost));
-  if (codes) NC_CUDA(cudaMemcpy(codes, d_codes.p, (size_t)batch * nq * T * 8, cudaMemcpyDeviceToHost));
+  if (audio_out) d2h(e, audio_out, d_out.p, (size_t)batch * length * 4);
+  if (codes) d2h(e, codes, d_codes.p, (size_t)batch * nq * T * 8);
 }
 
 nc_status nc_encodec_encode(nc_handle h, const float* audio, int32_t batch, int64_t length, float bandwidth_kbps, int64_t* codes) {
@@ -568,9 +597,9 @@ nc_status nc_encodec_decode(nc_handle h, const int64_t* codes, int32_t batch, in
     e->bind();
     const int64_t L = e->decoded_length(frames);
     DevMem d_c((size_t)batch * n_q * frames * 8), d_a((size_t)batch * L * 4);
-    NC_CUDA(cudaMemcpy(d_c.p, codes, (size_t)batch * n_q * frames * 8, cudaMemcpyHostToDevice));
+    h2d(e, d_c.p, codes, (size_t)batch * n_q * frames * 8);
     e->decode_dev(d_c.as<int64_t>(), batch, n_q, frames, d_a.as<float>());
-    NC_CUDA(cudaMemcpy(audio, d_a.p, (size_t)batch * L * 4, cudaMemcpyDeviceToHost));
+    d2h(e, audio, d_a.p, (size_t)batch * L * 4);
   });
 }
 
@@ -640,11 +669,10 @@ nc_status nc_resample_linear(nc_handle h, const float* audio, int32_t batch, int
     BusyGuard g(e);
     e->bind();
     DevMem d_in((size_t)batch * length * 4), d_out((size_t)batch * n_out * 4);
-    NC_CUDA(cudaMemcpy(d_in.p, audio, (size_t)batch * length * 4, cudaMemcpyHostToDevice));
+    h2d(e, d_in.p, audio, (size_t)batch * length * 4);
     launch_resample_linear(d_in.as<float>(), length, length, d_out.as<float>(), n_out, n_out, ratio, batch, e->ctx());
     e->sync();
-    NC_CUDA(cudaMemcpy2D(out, (size_t)out_capacity * 4, d_out.p, (size_t)n_out * 4, (size_t)n_out * 4, (size_t)batch,
-                         cudaMemcpyDeviceToHost));
+    d2h_2d(e, out, (size_t)out_capacity * 4, d_out.p, (size_t)n_out * 4, (size_t)n_out * 4, (size_t)batch);
   });
 }
 
@@ -657,10 +685,10 @@ nc_status nc_convert_to_mono(nc_handle h, const float* interleaved, int64_t fram
     BusyGuard g(e);
     e->bind();
     DevMem d_in((size_t)frames * channels * 4), d_out((size_t)frames * 4);
-    NC_CUDA(cudaMemcpy(d_in.p, interleaved, (size_t)frames * channels * 4, cudaMemcpyHostToDevice));
+    h2d(e, d_in.p, interleaved, (size_t)frames * channels * 4);
     launch_to_mono(d_in.as<float>(), d_out.as<float>(), frames, channels, e->ctx());
     e->sync();
-    NC_CUDA(cudaMemcpy(out, d_out.p, (size_t)frames * 4, cudaMemcpyDeviceToHost));
+    d2h(e, out, d_out.p, (size_t)frames * 4);
   });
 }
 
@@ -681,7 +709,7 @@ nc_status nc_snac_process_audio(nc_handle h, const float* audio, int32_t batch, 
     BusyGuard g(e);
     e->bind();
     DevMem d_in((size_t)batch * length * 4), d_rs(sample_rate == model_rate ? 0 : (size_t)batch * n * 4), d_out((size_t)batch * n * 4);
-    NC_CUDA(cudaMemcpy(d_in.p, audio, (size_t)batch * length * 4, cudaMemcpyHostToDevice));
+    h2d(e, d_in.p, audio, (size_t)batch * length * 4);
     const float* x = d_in.as<float>();
     if (sample_rate != model_rate) {
       launch_resample_linear(d_in.as<float>(), length, length, d_rs.as<float>(), n, n, ratio, batch, e->ctx());
@@ -695,12 +723,11 @@ nc_status nc_snac_process_audio(nc_handle h, const float* audio, int32_t batch, 
       for (size_t i = 0; i < nl.size(); ++i)
         if (noise[i]) {
           st.mem.push_back(new DevMem((size_t)batch * nl[i] * 4));
-          NC_CUDA(cudaMemcpy(st.mem.back()->p, noise[i], (size_t)batch * nl[i] * 4, cudaMemcpyHostToDevice));
+          h2d(e, st.mem.back()->p, noise[i], (size_t)batch * nl[i] * 4);
           st.noise_dev[i] = st.mem.back()->as<float>();
         }
     e->forward_dev(x, batch, n, st.noise_dev.data(), seed, d_out.as<float>(), nullptr);
-    NC_CUDA(cudaMemcpy2D(audio_out, (size_t)out_capacity * 4, d_out.p, (size_t)n * 4, (size_t)n * 4, (size_t)batch,
-                         cudaMemcpyDeviceToHost));
+    d2h_2d(e, audio_out, (size_t)out_capacity * 4, d_out.p, (size_t)n * 4, (size_t)n * 4, (size_t)batch);
   });
 }
 
@@ -745,11 +772,10 @@ nc_status nc_encodec_compress(nc_handle h, const float* audio, int32_t batch, in
     BusyGuard g(e);
     e->bind();
     DevMem d_audio((size_t)batch * length * 4), d_pay((size_t)batch * payload);
-    NC_CUDA(cudaMemcpy(d_audio.p, audio, (size_t)batch * length * 4, cudaMemcpyHostToDevice));
+    h2d(e, d_audio.p, audio, (size_t)batch * length * 4);
     e->compress_dev(d_audio.as<float>(), batch, length, m.n_codebooks, d_pay.as<uint8_t>(), payload);
     for (int b = 0; b < batch; ++b) std::memcpy(out + (size_t)b * out_stride, header.data(), header.size());
-    NC_CUDA(cudaMemcpy2D(out + header.size(), (size_t)out_stride, d_pay.p, (size_t)payload, (size_t)payload, (size_t)batch,
-                         cudaMemcpyDeviceToHost));
+    d2h_2d(e, out + header.size(), (size_t)out_stride, d_pay.p, (size_t)payload, (size_t)payload, (size_t)batch);
     if (stream_bytes) *stream_bytes = total;
   });
 }
@@ -803,11 +829,10 @@ nc_status nc_encodec_decompress(nc_handle h, const uint8_t* streams, int32_t bat
     e->bind();
     DevMem d_pay((size_t)batch * std::max<int64_t>(payload, 1)), d_audio((size_t)batch * m0.audio_length * 4);
     if (payload > 0)
-      NC_CUDA(cudaMemcpy2D(d_pay.p, (size_t)payload, streams + off, (size_t)stream_stride, (size_t)payload, (size_t)batch,
-                           cudaMemcpyHostToDevice));
+      h2d_2d(e, d_pay.p, (size_t)payload, streams + off, (size_t)stream_stride, (size_t)payload, (size_t)batch);
     e->decompress_dev(d_pay.as<uint8_t>(), payload, batch, m0.n_codebooks, m0.audio_length, d_audio.as<float>());
-    NC_CUDA(cudaMemcpy2D(audio, (size_t)audio_capacity * 4, d_audio.p, (size_t)m0.audio_length * 4, (size_t)m0.audio_length * 4,
-                         (size_t)batch, cudaMemcpyDeviceToHost));
+    d2h_2d(e, audio, (size_t)audio_capacity * 4, d_audio.p, (size_t)m0.audio_length * 4, (size_t)m0.audio_length * 4,
+           (size_t)batch);
   });
 }
 

@@ -1,4 +1,6 @@
 // HBM-bound kernels of the codec hot path.  See codec_kernels.h for the contracts.
+#include <cuda_fp16.h>
+
 #include "codec_kernels.h"
 
 #include <cfloat>
@@ -147,6 +149,26 @@ void launch_conv_cout1(const float* in, float* out, int T, int C, const float* w
 }
 
 // ------------------------------------------------------------------------------ transposes
+__global__ void f32_to_f16_kernel(const float4* __restrict__ in, uint2* __restrict__ out, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(in + i);
+    const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    out[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+  }
+}
+void launch_f32_to_f16(const float* in, void* out16, long long n, const LaunchCtx& ctx) {
+  if (n == 0) return;
+  if (n % 4 != 0) throw Error(NC_INTERNAL, "f32_to_f16: element count must be a multiple of 4");
+  const long long n4 = n / 4;
+  long long blocks = (n4 + 255) / 256;
+  const long long cap = (long long)ctx.num_sms * 8;
+  if (blocks > cap) blocks = cap;
+  const int ev = ctx.begin();
+  f32_to_f16_kernel<<<(unsigned)blocks, 256, 0, ctx.stream>>>(reinterpret_cast<const float4*>(in), static_cast<uint2*>(out16), n4);
+  check_launch((int)cudaGetLastError(), "f32_to_f16");
+  ctx.end(ev, "f32_to_f16", 0, 6.0 * n);
+}
+
 // in: [B][R][Cn] -> out: [B][Cn][R]
 __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int Cn) {
   __shared__ float tile[32][33];

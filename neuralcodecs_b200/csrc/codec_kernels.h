@@ -20,6 +20,9 @@ void launch_conv_cin1(const float* in, long long in_stride, int in_len, float* o
 void launch_conv_cout1(const float* in, float* out, int T, int C, const float* w_kc, const float* bias, int k, int pad,
                        int act, int batch, const LaunchCtx& ctx, int reflect = 0, long long in_clip_stride = 0);
 
+// out16[i] = fp16(in[i]) (round to nearest even): the latent handed to the fp16-operand decoder layers
+void launch_f32_to_f16(const float* in, void* out16, long long n, const LaunchCtx& ctx);
+
 // [B][C][T] <-> [B][T][C]
 void launch_transpose_ct_to_tc(const float* in, float* out, int batch, int C, int T, const LaunchCtx& ctx);
 void launch_transpose_tc_to_ct(const float* in, float* out, int batch, int C, int T, const LaunchCtx& ctx);

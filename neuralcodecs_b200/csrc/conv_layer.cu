@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -98,8 +99,6 @@ static inline float host_f16_to_f(uint16_t h) {
   return f;
 }
 
-static int g_fast_sin = -1;  // -1 auto (tf32 -> fast), 0 never, 1 always
-void set_fast_sin_policy(int v) { g_fast_sin = v; }
 
 static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
@@ -119,6 +118,7 @@ ConvLayer::~ConvLayer() {
   cudaFree(d_bias_);
   cudaFree(d_w_plain_);
   cudaFree(d_w_tiles_);
+  cudaFree(d_w16_);
 }
 
 int ConvLayer::out_len(int t_in) const {
@@ -135,8 +135,9 @@ double ConvLayer::flops(int batch, int t_in) const {
 }
 
 void ConvLayer::build(const std::string& name, const ConvSpec& spec, const std::vector<float>& w,
-                      const std::vector<float>& bias, Precision requested) {
+                      const std::vector<float>& bias, Precision requested, int short_chains, bool direct16) {
   name_ = name;
+  short_chains_ = (requested == PREC_BF16X3 || requested == PREC_F16X3) ? short_chains : 0;
   spec_ = spec;
   const ConvSpec& s = spec_;
   if ((size_t)s.cin * s.cout * s.k != w.size())
@@ -219,10 +220,11 @@ void ConvLayer::build(const std::string& name, const ConvSpec& spec, const std::
     probe.mode = mma_mode(requested);
     probe.w_hi_only = 0;   // sized for full tiles; hi-only tiles only add weight stages
     int bn = 0;
-    if (n_pad_ <= 256) {
+    const int bn_max = short_chains_ == 1 ? 128 : 256;   // short chains: 2 main partials + lo accumulator + running sum in 512 TMEM columns
+    if (n_pad_ <= bn_max) {
       bn = n_pad_;
     } else {
-      for (int c = 256; c >= 16; c -= 16)
+      for (int c = bn_max; c >= 16; c -= 16)
         if (n_pad_ % c == 0) { bn = c; break; }
     }
     // shrink until at least 2 weight stages fit
@@ -307,6 +309,11 @@ void ConvLayer::build(const std::string& name, const ConvSpec& spec, const std::
     }
     d_w_tiles_ = upload(tiles);
     // dense plan: every tap reads every K chunk, contributes to every N tile, and shifts are equally spaced
+    {   // main-chain length per partial: 2 hi*hi MMAs per tap and K chunk; ~96 MMAs (32 main-chain steps) keep the truncation error of one
+        // chain near 2e-6 relative (DESIGN.md "accumulation chains")
+      static const int steps = getenv("NC_FOLD_STEPS") ? std::max(2, atoi(getenv("NC_FOLD_STEPS"))) : 96;
+      fold_kc_ = std::max(1, steps / (2 * (int)taps_.size()));
+    }
     dense_step_ = taps_.size() == 1 ? 0 : taps_[1].shift - taps_[0].shift;
     for (size_t j = 0; j < taps_.size(); ++j) {
       if (utaps_[j].kc_lo != kc_begin_ || utaps_[j].kc_hi != kc_begin_ + n_kc_ ||
@@ -330,11 +337,109 @@ void ConvLayer::build(const std::string& name, const ConvSpec& spec, const std::
       std::memcpy(plain.data() + simt_w_off_[j], taps_[j].w.data(), taps_[j].w.size() * sizeof(float));
     d_w_plain_ = upload(plain);
   }
+  // ---------------------------------------------------------------- fp16-operand executor (conv_h16.cu)
+  direct16_ = false;
+  if (direct16 && umma_ok_ && mode_ == PREC_F16 && n_pad_ == n_logical_) {
+    bool ok = span_ <= 64 && k_view_ % 64 == 0 && (s.transposed || s.stride == 1);
+    // transposed convs: whole output rows only (out_len(t) == t * stride), i.e. not the one-sample-short odd strides
+    if (s.transposed) ok = ok && s.k - 2 * s.padding + s.output_padding == s.stride;
+    for (auto& t : taps_) ok = ok && t.koff % 64 == 0 && t.klen % 64 == 0;
+    int bn = 0;
+    for (int c = 256; c >= 32; c -= 32)
+      if (n_logical_ % c == 0) { bn = c; break; }
+    ok = ok && bn > 0 && n_logical_ / bn <= kMaxNTiles;
+    if (ok) {
+      bn16_ = bn;
+      n_tiles16_ = n_logical_ / bn;
+      kc_begin16_ = 1 << 30;
+      int kc_end = 0, tile_base = 0;
+      for (size_t j = 0; j < taps_.size(); ++j) {
+        utaps16_[j].shift = taps_[j].shift;
+        utaps16_[j].kc_lo = taps_[j].koff / 64;
+        utaps16_[j].kc_hi = (taps_[j].koff + taps_[j].klen) / 64;
+        utaps16_[j].tile_base = tile_base;
+        tile_base += utaps16_[j].kc_hi - utaps16_[j].kc_lo;
+        kc_begin16_ = std::min(kc_begin16_, utaps16_[j].kc_lo);
+        kc_end = std::max(kc_end, utaps16_[j].kc_hi);
+      }
+      tiles_per_ntile16_ = tile_base;
+      n_kc16_ = kc_end - kc_begin16_;
+      // [N tile][tap][64-channel chunk] tiles of [BN rows][64 halves], plain row-major (the TMA applies the swizzle)
+      std::vector<uint16_t> w16((size_t)n_tiles16_ * tiles_per_ntile16_ * bn16_ * 64, 0);
+      for (int nt = 0; nt < n_tiles16_; ++nt)
+        for (size_t j = 0; j < taps_.size(); ++j)
+          for (int kcl = 0; kcl < utaps16_[j].kc_hi - utaps16_[j].kc_lo; ++kcl) {
+            uint16_t* tile = w16.data() + ((size_t)nt * tiles_per_ntile16_ + utaps16_[j].tile_base + kcl) * bn16_ * 64;
+            for (int nl = 0; nl < bn16_; ++nl)
+              for (int kk = 0; kk < 64; ++kk)
+                tile[(size_t)nl * 64 + kk] = host_f16(taps_[j].w[(size_t)(nt * bn16_ + nl) * taps_[j].klen + (size_t)kcl * 64 + kk]);
+          }
+      std::vector<float> packed(w16.size() / 2);
+      std::memcpy(packed.data(), w16.data(), w16.size() * 2);
+      d_w16_ = upload(packed);
+      direct16_ = true;
+    }
+  }
   for (auto& t : taps_) std::vector<float>().swap(t.w);
 }
 
+// Plan for the fp16-operand executor; false when this layer / call cannot use it.
+bool ConvLayer::fill_h16(const ConvRunArgs& a, ConvGemmParams* pp, int fast_sin) const {
+  const ConvSpec& s = spec_;
+  const int t_out = out_len(a.t_in);
+  if (!direct16_ || !a.in16 || a.batch <= 0 || t_out <= 0 || a.prologue != PRO_NONE || a.noise || a.dw_w) return false;
+  if (!s.transposed && s.stride != 1) return false;
+  const int a_rows = a.t_in;
+  const int m_rows = s.transposed ? (t_out + s.stride - 1) / s.stride : t_out;
+  const int n_total = s.transposed ? s.stride * s.cout : s.cout;
+  const long long a_valid = (long long)a.t_in * s.cin, d_valid = (long long)t_out * s.cout;
+  if (d_valid != (long long)m_rows * n_total) return false;   // transposed convs one sample short (odd strides)
+  ConvGemmParams& p = *pp;
+  p = ConvGemmParams{};
+  p.a16 = 1;
+  p.A = static_cast<const float*>(a.in16); p.a_clip_stride = a.in_clip_stride ? a.in_clip_stride : a_valid;
+  p.a_rows = a_rows; p.a_pitch = k_view_; p.a_valid = a_valid;
+  p.D = a.out; p.D16 = a.out16; p.R = a.residual; p.d_clip_stride = a.out_clip_stride ? a.out_clip_stride : d_valid;
+  p.m_rows = m_rows; p.n_total = n_total; p.n_valid = n_logical_; p.d_valid = d_valid;
+  p.bias = d_bias_; p.bias_period = s.cout;
+  p.post = a.post; p.post_alpha = a.post_alpha; p.post_inv_alpha = a.post_inv_alpha; p.post_period = s.cout; p.act = a.act;
+  p.W = d_w16_; p.w_tile_floats = bn16_ * 32; p.BN = bn16_; p.n_tiles = n_tiles16_; p.tiles_per_ntile = tiles_per_ntile16_;
+  p.mode = MODE_F16X3; p.passes = 1;
+  p.n_taps = (int)taps_.size();
+  for (int j = 0; j < p.n_taps; ++j) p.taps[j] = utaps16_[j];
+  // per-N-tile tap masks: a transposed conv's tap j (input shift -q) feeds output phase phi iff kernel index
+  // phi + padding + q*stride is valid (ConvLayer::build); a tile of BN columns spans BN / cout phases (or part of one)
+  for (int nt = 0; nt < n_tiles16_; ++nt) {
+    unsigned m = 0;
+    for (int j = 0; j < p.n_taps; ++j) {
+      bool any = !s.transposed;
+      if (s.transposed) {
+        const int q = -utaps16_[j].shift;
+        const int phi_lo = (nt * bn16_) / s.cout, phi_hi = ((nt + 1) * bn16_ - 1) / s.cout;
+        for (int phi = phi_lo; phi <= phi_hi && !any; ++phi) {
+          const int jj = phi + s.padding + q * s.stride;
+          if (jj >= 0 && jj < s.k) any = true;
+        }
+      }
+      if (any) m |= 1u << j;
+    }
+    p.tap_mask[nt] = (unsigned char)m;
+  }
+  p.n_kc = n_kc16_; p.kc_begin = kc_begin16_; p.smin = smin_; p.span = span_;
+  p.dense_step = taps_.size() == 1 ? 0 : taps_[1].shift - taps_[0].shift;
+  for (size_t j = 0; j < taps_.size(); ++j)
+    if (utaps16_[j].kc_lo != kc_begin16_ || utaps16_[j].kc_hi != kc_begin16_ + n_kc16_ || taps_[j].shift != smin_ + (int)j * p.dense_step)
+      p.dense_step = -1;
+  for (int nt = 0; nt < n_tiles16_ && p.dense_step >= 0; ++nt)
+    if (p.tap_mask[nt] != (unsigned char)((1u << taps_.size()) - 1)) p.dense_step = -1;
+  p.batch = a.batch; p.m_tiles_per_clip = (m_rows + 127) / 128;
+  const int fast = fast_sin >= 0 ? fast_sin : 1;
+  p.precise_sin = fast ? 0 : 1;
+  return h16_supported(p);
+}
+
 // Fill the tcgen05 plan for one call; returns false when this layer / call cannot use the tensor-core kernel.
-bool ConvLayer::fill_umma(const ConvRunArgs& a, ConvGemmParams* pp) const {
+bool ConvLayer::fill_umma(const ConvRunArgs& a, ConvGemmParams* pp, int fast_sin) const {
   const ConvSpec& s = spec_;
   const int t_out = out_len(a.t_in);
   if (mode_ == PREC_FP32 || a.batch <= 0 || t_out <= 0) return false;
@@ -363,6 +468,8 @@ bool ConvLayer::fill_umma(const ConvRunArgs& a, ConvGemmParams* pp) const {
   p.mode = mma_mode(mode_);
   p.passes = mode_ == PREC_F16 ? 1 : (mode_ == PREC_F16X2 ? 2 : 3);
   p.w_hi_only = w_hi_only_ ? 1 : 0;
+  p.acc_split = (short_chains_ && p.passes == 3) ? ((short_chains_ == 2 && bn_ > 128) ? 2 : 1) : 0;
+  p.fold_kc = (p.acc_split == 1 && short_chains_ == 1 && fold_kc_ < n_kc_) ? fold_kc_ : 0;
   p.n_taps = (int)taps_.size();
   for (int j = 0; j < p.n_taps; ++j) p.taps[j] = utaps_[j];
   std::memcpy(p.tap_mask, tap_mask_, sizeof tap_mask_);
@@ -377,20 +484,18 @@ bool ConvLayer::fill_umma(const ConvRunArgs& a, ConvGemmParams* pp) const {
     p.smin = -3 * a.dw_dil; p.span = 6 * a.dw_dil; p.dense_step = 0;
   }
   p.batch = a.batch; p.m_tiles_per_clip = (m_rows + 127) / 128;
-  const int fast = g_fast_sin >= 0 ? g_fast_sin : ((mode_ == PREC_TF32 || mode_ == PREC_BF16X3 || mode_ == PREC_F16X2 || mode_ == PREC_F16) ? 1 : 0);
+  const int fast = fast_sin >= 0 ? fast_sin : ((mode_ == PREC_TF32 || mode_ == PREC_BF16X3 || mode_ == PREC_F16X2 || mode_ == PREC_F16) ? 1 : 0);
   p.precise_sin = fast ? 0 : 1;
   return true;
 }
 
-static int g_fuse_ru = 1;
-void set_ru_fusion(int v) { g_fuse_ru = v; }
 
 // y = c2(post1(c1(pro(x)))) + x [-> post2] in one launch when the shapes allow it (C <= 256, bf16x3 / f16x3).
 bool try_run_ru_fused(const ConvLayer& c1, const ConvLayer& c2, const ConvRunArgs& a1, const ConvRunArgs& a2,
                       const LaunchCtx& ctx) {
-  if (!g_fuse_ru) return false;
+  if (!ctx.fuse_ru) return false;
   ConvGemmParams p, p2;
-  if (!c1.fill_umma(a1, &p) || !c2.fill_umma(a2, &p2)) return false;
+  if (!c1.fill_umma(a1, &p, ctx.fast_sin) || !c2.fill_umma(a2, &p2, ctx.fast_sin)) return false;
   if (!ru_fused_supported(p, p2)) return false;
   const int ev = ctx.begin();
   const int rc = launch_ru_fused(p, p2, ctx.num_sms, ctx.stream);
@@ -426,7 +531,15 @@ void ConvLayer::run(const ConvRunArgs& a, const LaunchCtx& ctx) const {
   const long long a_stride = a.in_clip_stride ? a.in_clip_stride : a_valid;
   const long long d_stride = a.out_clip_stride ? a.out_clip_stride : d_valid;
   ConvGemmParams up;
-  if (fill_umma(a, &up)) {
+  if (a.in16) {   // fp16-operand executor: no fallback (the fp32 executors cannot read this input)
+    if (!fill_h16(a, &up, ctx.fast_sin))
+      throw Error(NC_INTERNAL, name_ + ": fp16-operand call on a layer / shape the fp16 executor does not support");
+    check_launch(launch_conv_h16(up, ctx.num_sms, ctx.stream), name_.c_str());
+    const double b16 = (double)a.batch * (2.0 * a_valid + ((a.out ? 4.0 : 0.0) + (a.out16 ? 2.0 : 0.0) + (a.residual ? 4.0 : 0.0)) * d_valid);
+    ctx.end(ev, "conv_h16", fl, b16, name_);
+    return;
+  }
+  if (fill_umma(a, &up, ctx.fast_sin)) {
     check_launch(launch_conv_umma(up, ctx.num_sms, ctx.stream), name_.c_str());
     ctx.end(ev, std::string(a.dw_w ? "conv_umma_dw_" : "conv_umma_") + precision_name(mode_),
             fl + (a.dw_w ? 2.0 * 7 * s.cin * (double)a.t_in * a.batch : 0.0), bytes, name_);

@@ -16,9 +16,6 @@ inline bool prec_is_h16(Precision p) { return p == PREC_BF16X3 || p == PREC_F16X
 const char* precision_name(Precision p);
 
 Precision parse_precision(const std::string& s);
-// Snake sin(): -1 = MUFU sin on tf32 / bf16x3 layers, precise elsewhere (default); 0 = always precise;
-// 1 = always MUFU
-void set_fast_sin_policy(int v);
 
 struct ConvSpec {
   bool transposed = false;
@@ -28,6 +25,10 @@ struct ConvSpec {
 struct ConvRunArgs {
   const float* in = nullptr;        // [B][T_in][Cin] channels-last
   float* out = nullptr;             // [B][T_out][Cout]
+  // fp16-operand path (layers built with direct16): in16 = fp16 [B][T_in][Cin] already carrying this conv's input
+  // activation; out (raw fp32, bias + residual) and / or out16 (fp16, `post` applied) are written
+  const void* in16 = nullptr;
+  void* out16 = nullptr;
   const float* residual = nullptr;  // same shape as out
   const float* noise = nullptr;     // [B][T_out] (SNAC NoiseBlock: out = residual + noise * conv)
   int batch = 0;
@@ -61,11 +62,16 @@ class ConvLayer {
   ~ConvLayer();
 
   // w: folded weights, conv [Cout][Cin][k] / transposed [Cin][Cout][k]; bias [Cout] or empty.
+  // short_chains: keep the tensor core's accumulation chains short (conv_plan.h: acc_split = 1 | 2) -- for layers whose
+  // output feeds an RVQ argmin; three-pass 16-bit modes only; 1 caps the N tile at 128 columns
   void build(const std::string& name, const ConvSpec& spec, const std::vector<float>& w,
-             const std::vector<float>& bias, Precision requested);
+             const std::vector<float>& bias, Precision requested, int short_chains = 0, bool direct16 = false);
+  bool direct16() const { return direct16_; }
+  bool fill_h16(const ConvRunArgs& a, ConvGemmParams* p, int fast_sin = -1) const;
   int out_len(int t_in) const;
   void run(const ConvRunArgs& a, const LaunchCtx& ctx) const;
-  bool fill_umma(const ConvRunArgs& a, ConvGemmParams* p) const;
+  // fast_sin: LaunchCtx::fast_sin of the calling handle
+  bool fill_umma(const ConvRunArgs& a, ConvGemmParams* p, int fast_sin = -1) const;
 
   const ConvSpec& spec() const { return spec_; }
   Precision precision() const { return mode_; }
@@ -95,6 +101,13 @@ class ConvLayer {
   float* d_w_tiles_ = nullptr;
   int w_tile_floats_ = 0;
   bool w_hi_only_ = false;
+  int short_chains_ = 0;   // 0 off, 1 = folded partials + lo accumulator (N tile <= 128), 2 = lo accumulator only (N tile <= 256)
+  int fold_kc_ = 0;
+  // fp16-operand executor: own tiling (64-channel K chunks, plain row-major fp16 weight tiles)
+  bool direct16_ = false;
+  float* d_w16_ = nullptr;
+  int bn16_ = 0, n_tiles16_ = 0, tiles_per_ntile16_ = 0, kc_begin16_ = 0, n_kc16_ = 0;
+  ConvTap utaps16_[kMaxTaps];
   // UMMA tiling
   int bn_ = 0, n_tiles_ = 0, tiles_per_ntile_ = 0;
   ConvTap utaps_[kMaxTaps];
@@ -108,6 +121,5 @@ class ConvLayer {
 // a1: args of the k7 conv with out = the UNIT's output and residual = the unit's input; a2: the 1x1 conv's post.
 bool try_run_ru_fused(const ConvLayer& c1, const ConvLayer& c2, const ConvRunArgs& a1, const ConvRunArgs& a2,
                       const LaunchCtx& ctx);
-void set_ru_fusion(int v);   // 0 disables (option "fuse_ru")
 
 }  // namespace nc

@@ -84,6 +84,22 @@ struct ConvGemmParams {
   int dw_dil;
   int w_hi_only;            // 16-bit modes with passes < 3: weight tiles are [BN][32 hi halves] = 64-byte rows (SWIZZLE_64B)
   int passes;               // 16-bit modes: 3 = hi*hi + lo*hi + hi*lo, 2 = hi*hi + lo(A)*hi, 1 = hi*hi only
+  // Short accumulation chains (three-pass 16-bit modes, BN <= 128, TMA epilogue).  The tensor core adds every MMA's
+  // K=16 partial dot product to the fp32 accumulator with truncation (measured: relative error ~4e-8 per accumulation
+  // step, always toward zero, i.e. 4e-5 over the ~700-1500 MMAs of the encoder's deep layers -- enough to flip RVQ
+  // codes whose margin is far above the 1e-6 near-tie gate).  acc_split = 1 keeps the chains short: hi*hi products go
+  // to a "main" partial accumulator that is folded into a running fp32 sum (round-to-nearest adds by the epilogue
+  // warps, kept in TMEM) every fold_kc K chunks; the small lo*hi and hi*lo products (2^-8 of the main terms, so
+  // their truncation error is negligible) go to a separate accumulator added once at the end.
+  // acc_split = 2: N tiles up to 256 columns -- main accumulator at TMEM columns [0,BN), lo-term accumulator at
+  // [256,256+BN), no folding and one tile in flight (the epilogue no longer overlaps the next tile's MMAs).
+  int acc_split;
+  int fold_kc;              // K chunks per main partial (0 = the whole tile in one partial)
+  // fp16-operand executor (conv_h16.cu): A holds fp16 activations (a_pitch / a_clip_stride / a_valid count halves; taps'
+  // kc_*, n_kc and kc_begin count 64-channel chunks; W = plain row-major fp16 tiles [BN][64]); D = raw fp32 output
+  // (bias + residual, nullable), D16 = post-activated fp16 output in the consumer's operand format (nullable).
+  int a16;
+  void* D16;
   int n_taps;
   ConvTap taps[kMaxTaps];
   unsigned char tap_mask[kMaxNTiles];  // bit j set => tap j contributes to this N tile
@@ -126,6 +142,8 @@ struct UmmaLaunch {
   int w_stages;
   int a_rows_alloc;  // multiple of 8
   int tma_epilogue;  // 1: output / residual tiles move by TMA through a swizzled smem ring
+  int knock;         // measurement only (env NC_KNOCK, results become WRONG): 1 = weight copies skipped after the ring
+                     // filled once, 2 = operand transform skipped, 4 = A loads skipped, 8 = MMAs skipped, 16 = epilogue math/stores skipped
 };
 
 }  // namespace nc
@@ -143,6 +161,9 @@ bool umma_view_ok(const ConvGemmParams& p);
 // Whole DAC-style ResidualUnit in one launch: p = the k7 conv's plan (p.D = unit output, p.R = unit input,
 // p.post = Snake2), p2 = the 1x1 conv's plan (weights, bias, post = the Snake that follows the unit).
 bool ru_fused_supported(const ConvGemmParams& p, const ConvGemmParams& p2);
+// fp16-operand executor (conv_h16.cu)
+bool h16_supported(const ConvGemmParams& p);
+int launch_conv_h16(const ConvGemmParams& p, int num_sms, cudaStream_t stream);
 int launch_ru_fused(const ConvGemmParams& p, const ConvGemmParams& p2, int num_sms, cudaStream_t stream);
 }  // namespace nc
 #endif

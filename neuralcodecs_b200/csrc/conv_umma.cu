@@ -198,15 +198,26 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
 
   __shared__ uint64_t raw_full[kMaxAStages], a_full[kMaxAStages], a_empty[kMaxAStages];
   __shared__ uint64_t w_full[kMaxWStages], w_empty[kMaxWStages];
-  __shared__ uint64_t acc_full[2], acc_empty[2];
+  __shared__ uint64_t acc_full[2], acc_empty[2], lo_empty;
   __shared__ uint64_t r_full[kEpiStages], e_free[kEpiStages];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
+  // short accumulation chains (conv_plan.h: acc_split): TMEM columns [0,BN) / [BN,2BN) = main partials,
+  // [2BN,3BN) = lo-term accumulator, [3BN,4BN) = running sum of the folded partials
+  // acc_split = 2 (N tile up to 256): main at [0,BN), lo at [256,256+BN), one tile in flight, no folding.
+  const bool s3 = OPS == O_H16X3 && p.acc_split != 0;
+  const bool s3_wide = s3 && p.acc_split == 2;
+  const int fold_kc = (s3 && !s3_wide && p.fold_kc > 0) ? p.fold_kc : p.n_kc;
+  const uint32_t acc_stride = (s3 && !s3_wide) ? (uint32_t)p.BN : 256u;
+  const uint32_t lo_col = s3_wide ? 256u : 2u * acc_stride;
+  auto part_buf = [&](uint32_t pc) { return s3_wide ? 0 : (int)(pc & 1u); };
+  auto part_phase = [&](uint32_t pc) { return s3_wide ? (pc & 1u) : ((pc >> 1) & 1u); };
 
   if (tid == 0) {
+    mbar_init(&lo_empty, kEpilogueWarps);
     for (int i = 0; i < kMaxAStages; ++i) {
       mbar_init(&raw_full[i], 1);
       mbar_init(&a_full[i], kProducerWarps);
@@ -241,7 +252,7 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
   if (warp == 0) {
     // ===================================================================== weight producer
     if (elect_one()) {
-      int ws = 0;
+      int ws = 0, wcount = 0;
       uint32_t wph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_tiles;   // N tile fastest: the N tiles of one M tile run side by side, A re-reads hit L2
@@ -253,8 +264,13 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
             if (!((mask >> j) & 1u) || kc < p.taps[j].kc_lo || kc >= p.taps[j].kc_hi) continue;
             mbar_wait(&w_empty[ws], wph ^ 1u);
             const size_t toff = (size_t)(p.taps[j].tile_base + (kc - p.taps[j].kc_lo)) * (size_t)p.w_tile_floats;
-            mbar_arrive_expect_tx(&w_full[ws], w_stage_bytes);
-            bulk_g2s(sW + (size_t)ws * w_stage_bytes, wbase + toff, w_stage_bytes, &w_full[ws]);
+            if ((L.knock & 1) && wcount >= L.w_stages) {
+              mbar_arrive(&w_full[ws]);
+            } else {
+              mbar_arrive_expect_tx(&w_full[ws], w_stage_bytes);
+              bulk_g2s(sW + (size_t)ws * w_stage_bytes, wbase + toff, w_stage_bytes, &w_full[ws]);
+            }
+            ++wcount;
             if (++ws == L.w_stages) { ws = 0; wph ^= 1u; }
           }
         }
@@ -274,16 +290,28 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
       const uint32_t tap_u = (uint32_t)p.dense_step * 8u;                             // rows * 128 B / 16
       int ws = 0, as = 0, it = 0;
       uint32_t wph = 0, aph = 0;
+      uint32_t pc = 0;   // accumulator partials issued so far (== tiles when nothing is folded)
       uint64_t a_desc = a_desc0, w_desc = w_desc0;
+      const uint32_t lo_tmem = tmem_base + lo_col;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
-        mbar_wait(&acc_empty[buf], acc_ph ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u;
-        uint32_t acc = 0;
+        if (s3) {   // the previous tile's epilogue has read the lo accumulator
+          mbar_wait(&lo_empty, ((uint32_t)it & 1u) ^ 1u);
+          tc_fence_after();
+        }
+        int buf = 0, in_part = 0;
+        bool have_buf = false;
+        uint32_t d_tmem = 0;
+        uint32_t acc = 0, acc_lo = 0;
         const unsigned mask = p.dense_step >= 0 ? 0u : (unsigned)p.tap_mask[tile % p.n_tiles];
         for (int kci = 0; kci < p.n_kc; ++kci) {
+          if (!have_buf) {
+            buf = part_buf(pc);
+            mbar_wait(&acc_empty[buf], part_phase(pc) ^ 1u);
+            tc_fence_after();
+            d_tmem = tmem_base + (uint32_t)buf * acc_stride;
+            acc = 0;
+            have_buf = true;
+          }
           mbar_wait(&a_full[as], aph);
           tc_fence_after();
           uint64_t a_tap = a_desc;
@@ -299,7 +327,9 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
             mbar_wait(&w_full[ws], wph);
             tc_fence_after();
             const uint64_t a0 = a_tap, b0 = w_desc;
-            if (OPS == O_TF32) {
+            if ((L.knock & 8) && OPS == O_H16X3) {
+              if (!acc) umma_f16(d_tmem, a0, b0, idesc, 0);
+            } else if (OPS == O_TF32) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)   // K step = 8 tf32 = 32 B = +2 descriptor units
                 umma_tf32(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, acc | (uint32_t)k);
@@ -313,7 +343,15 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
               }
             } else {
               // row = [32 hi halves (64 B) | 32 lo halves (64 B)]; K step = 16 halves = 32 B
-              if (p.passes == 3) {
+              if (s3) {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                  umma_f16(lo_tmem, a0 + 4 + 2 * k, b0 + 2 * k, idesc, acc_lo | (uint32_t)k);  // lo * hi -> lo accumulator
+                  umma_f16(lo_tmem, a0 + 2 * k, b0 + 4 + 2 * k, idesc, 1);                     // hi * lo -> lo accumulator
+                  umma_f16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, acc | (uint32_t)k);          // hi * hi -> main partial
+                }
+                acc_lo = 1;
+              } else if (p.passes == 3) {
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                   umma_f16(d_tmem, a0 + 4 + 2 * k, b0 + 2 * k, idesc, acc | (uint32_t)k);  // lo * hi
@@ -339,14 +377,19 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
           tc_commit(&a_empty[as]);
           a_desc += a_stage_u;
           if (++as == L.a_stages) { as = 0; aph ^= 1u; a_desc = a_desc0; }
+          if (++in_part == fold_kc || kci == p.n_kc - 1) {   // this partial is complete: hand it to the epilogue warps
+            tc_commit(&acc_full[buf]);
+            ++pc;
+            in_part = 0;
+            have_buf = false;
+          }
         }
-        tc_commit(&acc_full[buf]);
       }
     }
   } else if (warp == kLoaderWarp) {
     // ===================================================================== A loader (TMA)
     if (elect_one()) {
-      int as = 0;
+      int as = 0, acount = 0;
       uint32_t aph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_tiles;   // N tile fastest: the N tiles of one M tile run side by side, A re-reads hit L2
@@ -356,8 +399,13 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
         const int r_base = mt * kBM + p.smin;
         for (int kci = 0; kci < p.n_kc; ++kci) {
           mbar_wait(&a_empty[as], aph ^ 1u);
-          mbar_arrive_expect_tx(&raw_full[as], a_tile_bytes);
-          tma_load_3d(sA + (size_t)as * a_stage_bytes, &tmapA, (p.kc_begin + kci) * 32, r_base, b, &raw_full[as]);
+          if ((L.knock & 4) && acount >= L.a_stages) {
+            mbar_arrive(&raw_full[as]);
+          } else {
+            mbar_arrive_expect_tx(&raw_full[as], a_tile_bytes);
+            tma_load_3d(sA + (size_t)as * a_stage_bytes, &tmapA, (p.kc_begin + kci) * 32, r_base, b, &raw_full[as]);
+          }
+          ++acount;
           if (++as == L.a_stages) { as = 0; aph ^= 1u; }
         }
       }
@@ -394,34 +442,79 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
       const bool leader = warp == kFirstEpilogueWarp && lane == 0;
       int es = 0, prev = -1;
       uint32_t eph = 0;
+      uint32_t pc = 0;   // accumulator partials consumed so far (mirrors the MMA issuer's counter)
+      const int n_parts = (p.n_kc + fold_kc - 1) / fold_kc;
+      const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
+      const uint32_t t_lo = tmem_base + lo_col + lane_bits, t_run = tmem_base + 3u * acc_stride + lane_bits;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int nt = tile % p.n_tiles;   // N tile fastest: the N tiles of one M tile run side by side, A re-reads hit L2
         const int rem = tile / p.n_tiles;
         const int b = rem / p.m_tiles_per_clip;
         const int mt = rem - b * p.m_tiles_per_clip;
-        const int buf = it & 1;
-        const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
         const int rloc = q * 32 + lane;
         const int row = mt * kBM + rloc;
         const float nz = (p.noise && row < p.m_rows) ? __ldg(p.noise + (long long)b * p.m_rows + row) : 0.f;
+        // fold every main partial but the last into the running sum (fp32 round-to-nearest adds, kept in TMEM; each
+        // thread only ever touches its own lane and columns of it)
+        for (int part = 0; part + 1 < n_parts; ++part, ++pc) {
+          const int pbuf = part_buf(pc);
+          mbar_wait(&acc_full[pbuf], part_phase(pc));
+          tc_fence_after();
+          const uint32_t t_part = tmem_base + (uint32_t)pbuf * acc_stride + lane_bits;
+          for (int g = 0; g < groups; ++g) {
+            float v[16], r[16];
+            __syncwarp();
+            tmem_ld16(t_part + g * 32 + half * 16, v);
+            if (part > 0) tmem_ld16(t_run + g * 32 + half * 16, r);
+            tmem_ld_wait();
+            if (part > 0) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += r[i];
+            }
+            tmem_st16(t_run + g * 32 + half * 16, v);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[pbuf]);
+        }
+        const int buf = part_buf(pc);
+        const uint32_t acc_ph = part_phase(pc);
+        ++pc;
         mbar_wait(&acc_full[buf], acc_ph);
         tc_fence_after();
-        const uint32_t t_addr = tmem_base + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16);
+        const uint32_t t_addr = tmem_base + (uint32_t)buf * acc_stride + lane_bits;
         for (int g = 0; g < groups; ++g) {
           float v[16];
           __syncwarp();
           tmem_ld16(t_addr + g * 32 + half * 16, v);
-          tmem_ld_wait();
-          if (g == groups - 1) {   // accumulator fully read by this warp: hand the TMEM buffer back early
+          if (s3) {
+            float r[16], l[16];
+            if (n_parts > 1) tmem_ld16(t_run + g * 32 + half * 16, r);
+            tmem_ld16(t_lo + g * 32 + half * 16, l);
+            tmem_ld_wait();
+            if (n_parts > 1) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += r[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += l[i];
+          } else {
+            tmem_ld_wait();
+          }
+          if (g == groups - 1) {   // accumulator fully read by this warp: hand the TMEM buffers back early
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            if (lane == 0) {
+              mbar_arrive(&acc_empty[buf]);
+              if (s3) mbar_arrive(&lo_empty);
+            }
           }
           const int n0 = nt * p.BN + g * 32 + half * 16;
           epi_bias(p, v, n0);
           uint8_t* stage = sE + (size_t)es * kEpiStageBytes;
           if (p.R) mbar_wait(&r_full[es], eph); else mbar_wait(&e_free[es], eph ^ 1u);
-          if (p.R) {
+          if (p.R && !(L.knock & 16)) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float4 r = *reinterpret_cast<const float4*>(stage + sw128_offset((uint32_t)rloc, (uint32_t)(half * 4 + i)));
@@ -433,7 +526,7 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
               }
             }
           }
-          epi_post(p, v, n0);
+          if (!(L.knock & 16)) epi_post(p, v, n0);
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             *reinterpret_cast<float4*>(stage + sw128_offset((uint32_t)rloc, (uint32_t)(half * 4 + i))) =
@@ -441,7 +534,7 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
           fence_proxy_async_smem();
           asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueWarps * 32) : "memory");
           if (leader) {
-            tma_store_3d(&tmapD, stage, nt * p.BN + g * 32, mt * kBM, b);
+            if (!(L.knock & 32)) tma_store_3d(&tmapD, stage, nt * p.BN + g * 32, mt * kBM, b);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the previous store has left smem
             if (prev >= 0) mbar_arrive(&e_free[prev]);
@@ -535,6 +628,13 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
         }
         uint8_t* stage = sA + (size_t)as * a_stage_bytes;
         mbar_wait(&raw_full[as], aph);
+        if (L.knock & 2) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_full[as]);
+          if (++as == L.a_stages) { as = 0; aph ^= 1u; }
+          continue;
+        }
         if (OPS == O_H16X3 && p.dw_w != nullptr) {
           // ---- depthwise k7 conv folded into the operand prologue (SNAC ResidualUnit; conv_plan.h)
           // phase 1: Snake on every row of the tile (halo included), fp32 in place.  OOB rows are TMA zero fill and
@@ -1139,10 +1239,18 @@ bool umma_view_ok(const ConvGemmParams& p) {
 }
 
 // returns cudaError_t as int; 0 on success; -1 if the shape does not fit this kernel
-int launch_conv_umma(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
+int launch_conv_umma(const ConvGemmParams& p_in, int num_sms, cudaStream_t stream) {
   UmmaLaunch L;
-  const size_t smem = umma_smem_bytes(p, &L);
-  if (smem == 0 || !umma_view_ok(p)) return -1;
+  const size_t smem = umma_smem_bytes(p_in, &L);
+  if (smem == 0 || !umma_view_ok(p_in)) return -1;
+  ConvGemmParams p = p_in;
+  if (p.acc_split && (!L.tma_epilogue || p.BN > (p.acc_split == 2 ? 256 : 128) || (p.mode != MODE_BF16X3 && p.mode != MODE_F16X3) ||
+                      p.passes != 3 || p.dw_w)) {
+    p.acc_split = 0;   // ragged outputs / other operand modes: one accumulator per tile
+    p.fold_kc = 0;
+  }
+  static const int knock = getenv("NC_KNOCK") ? atoi(getenv("NC_KNOCK")) : 0;
+  L.knock = knock;
   const int rows_needed = kBM + p.span;
   const int rit = (rows_needed + 31) / 32;
   if (rit > 6) return -1;
@@ -1206,7 +1314,7 @@ bool ru_fused_supported(const ConvGemmParams& p, const ConvGemmParams& p2) {
   // C <= 128: both accumulators double-buffered.  128 < C <= 256: one tile in flight (acc1 + acc2 fill TMEM); the k7
   // MMAs are then exposed to the acc1 drain, which only pays when they are short: one-pass fp16 k7 convs only.
   const bool width_ok = p.BN <= ru_fuse_max_c() || (p.BN <= ru_fuse_wide_max_c() && p.passes == 1);
-  return h16 && width_ok && p.n_tiles == 1 && p2.n_tiles == 1 &&
+  return h16 && width_ok && !p.acc_split && !p2.acc_split && p.n_tiles == 1 && p2.n_tiles == 1 &&
          p.BN == p2.BN && p.BN % 32 == 0 && p.n_total == p.BN && p.n_valid == p.BN && p.dense_step >= 0 &&
          p.prologue == PRO_SNAKE && p2.n_taps == 1 && p2.n_kc == p.n_kc && p.kc_begin == 0 && p.span <= 64 &&
          p.a_pitch == p.BN && umma_view_ok(p) && p.d_valid == (long long)p.m_rows * p.n_total && p.d_clip_stride % 4 == 0 &&
@@ -1230,7 +1338,7 @@ int launch_ru_fused(const ConvGemmParams& p, const ConvGemmParams& p2, int num_s
     if (!grew) break;
   }
   while (ws < kMaxWStages && as * a_stage + (ws + 1) * w_stage <= budget) ++ws;
-  L.a_stages = as; L.w_stages = ws; L.a_rows_alloc = rows; L.tma_epilogue = 1;
+  L.a_stages = as; L.w_stages = ws; L.a_rows_alloc = rows; L.tma_epilogue = 1; L.knock = 0;
   const size_t smem = 1024 + (size_t)as * a_stage + (size_t)ws * w_stage + (size_t)(kHStages + kEpiStages) * kEpiStageBytes;
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return (int)cudaErrorNotSupported;

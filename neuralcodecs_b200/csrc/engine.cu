@@ -49,6 +49,8 @@ LaunchCtx Engine::ctx() {
   c.num_sms = num_sms_;
   c.prof = prof_.enabled ? &prof_ : nullptr;
   c.launches = &launches_;
+  c.fast_sin = fast_sin_;
+  c.fuse_ru = fuse_ru_;
   return c;
 }
 
@@ -59,9 +61,9 @@ void Engine::set_option(const std::string& key, const std::string& value) {
     prof_.enabled = value == "1" || value == "true" || value == "2";
     prof_.by_layer = value == "2";
   } else if (key == "fast_sin") {
-    set_fast_sin_policy(std::atoi(value.c_str()));
+    fast_sin_ = std::atoi(value.c_str());
   } else if (key == "fuse_ru") {
-    set_ru_fusion(std::atoi(value.c_str()));
+    fuse_ru_ = std::atoi(value.c_str());
   } else if (key == "max_workspace_mb") {
     const long long mb = std::atoll(value.c_str());
     if (mb < 64) throw Error(NC_INVALID_ARGUMENT, "max_workspace_mb must be >= 64");
@@ -142,6 +144,23 @@ DacEngine::~DacEngine() {
 void DacEngine::set_option(const std::string& key, const std::string& value) {
   if (key == "encoder_precision") {
     enc_prec_ = parse_precision(value);
+    if (ready_) throw Error(NC_INVALID_ARGUMENT, "precision options must be set before weights are loaded");
+  } else if (key == "encoder_tail_fp32") {
+    // experiment / tight-parity knob: the last N layer groups of the encoder run on the exact fp32 CUDA-core path
+    // (1: encoder.conv2; 2: + last strided conv; 3: + last block's residual units; 4: + the block before it)
+    enc_tail_fp32_ = std::atoi(value.c_str());
+    if (ready_) throw Error(NC_INVALID_ARGUMENT, "precision options must be set before weights are loaded");
+  } else if (key == "encoder_short_chains") {
+    // accumulation-chain policy of the encoder (conv_plan.h: acc_split; DESIGN.md "accumulation chains"):
+    // 0 off; 1 (default) folded partials on the frame-rate layers (last strided conv, encoder.conv2), separate lo-term
+    // accumulator on the other layers whose chains exceed ~250 MMAs; 2: folded partials on every layer the plain conv
+    // kernel runs; 3 / 4: also encoder block 1 / block 0 (they then run unfused)
+    enc_short_chains_ = std::atoi(value.c_str());
+    if (ready_) throw Error(NC_INVALID_ARGUMENT, "precision options must be set before weights are loaded");
+  } else if (key == "decoder_h16") {
+    // 1 (default): the decoder layers that take one fp16 product per term exchange fp16 activations and run on the
+    // fp16-operand executor (conv_h16.cu); 0: fp32 activations + in-kernel operand transform (conv_umma.cu)
+    dec_h16_opt_ = std::atoi(value.c_str());
     if (ready_) throw Error(NC_INVALID_ARGUMENT, "precision options must be set before weights are loaded");
   } else if (key == "decoder_boost") {
     dec_boost_ = value == "1" || value == "true";
@@ -289,7 +308,7 @@ Precision DacEngine::boosted(Precision p, bool narrow) const {
   return (p == PREC_TF32 && dec_boost_ && narrow) ? PREC_3XTF32 : p;
 }
 
-void DacEngine::build_ru(ResUnit& ru, const std::string& p, int dim, int dil, Precision prec) {
+void DacEngine::build_ru(ResUnit& ru, const std::string& p, int dim, int dil, Precision prec, int short_chains) {
   std::vector<float> b;
   ru.s1.build(alpha_of(tensor(p + ".snake1.alpha"), dim, p + ".snake1.alpha"));
   ru.s2.build(alpha_of(tensor(p + ".snake2.alpha"), dim, p + ".snake2.alpha"));
@@ -297,14 +316,17 @@ void DacEngine::build_ru(ResUnit& ru, const std::string& p, int dim, int dil, Pr
   s1.cin = s1.cout = dim; s1.k = 7; s1.dilation = dil; s1.padding = (7 - 1) * dil / 2;  // ResidualUnit.cs:27
   auto w1 = folded_conv(p + ".conv1", dim, dim, 7, &b, dim);
   const bool wide = p.compare(0, 8, "decoder.") == 0 && dim > 128 && prec != PREC_FP32;
-  ru.c1.build(p + ".conv1", s1, w1, b, wide ? dec_wide_prec_ : prec);
+  const bool d16 = wide && dec_wide_prec_ == PREC_F16 && dec_h16_opt_ != 0;
+  ru.c1.build(p + ".conv1", s1, w1, b, wide ? dec_wide_prec_ : prec, short_chains, d16);
   ConvSpec s2;
   s2.cin = s2.cout = dim; s2.k = 1;
   auto w2 = folded_conv(p + ".conv2", dim, dim, 1, &b, dim);
   const bool is_dec = p.compare(0, 8, "decoder.") == 0;
   // the 1x1 conv of a wide decoder unit follows its k7 conv's mode (one fp16 product by default): 68.6 dB instead
   // of 69.6 dB, +2.7 % sustained, and the C = 192 unit can then run as one fused launch with 64-byte weight tiles
-  ru.c2.build(p + ".conv2", s2, w2, b, wide ? dec_wide_prec_ : (is_dec ? boosted(prec, dim <= 192) : prec));
+  // the 1x1 conv's chain is dim/32 * 6 MMAs (<= 96 in the encoder): nothing to shorten unless forced
+  ru.c2.build(p + ".conv2", s2, w2, b, wide ? dec_wide_prec_ : (is_dec ? boosted(prec, dim <= 192) : prec),
+              short_chains == 1 ? 1 : 0, d16);
 }
 
 void DacEngine::finalize_weights() {
@@ -326,12 +348,26 @@ void DacEngine::finalize_weights() {
     auto blk = std::make_unique<EncBlock>();
     const std::string p = "encoder.block." + std::to_string(i);
     const int dils[3] = {1, 3, 9};
-    for (int u = 0; u < 3; ++u) build_ru(blk->ru[u], p + ".res_unit" + std::to_string(u + 1), d, dils[u], enc_prec_);
+    const int from_end = (int)cfg_.encoder_rates.size() - 1 - (int)i;   // 0 = last block
+    const Precision ru_prec = enc_tail_fp32_ >= 3 + 2 * from_end ? PREC_FP32 : enc_prec_;
+    const Precision down_prec = enc_tail_fp32_ >= 2 + 2 * from_end ? PREC_FP32 : enc_prec_;
+    // MMAs accumulated per output element: 3 products x 2 K steps per 32-channel chunk and tap
+    const int ru_chain = 6 * (d * 7 / 32), down_chain = 6 * (d * 2 * s / 32);
+    const bool last = i + 1 == cfg_.encoder_rates.size();
+    int ru_short = 0, down_short = 0;
+    if (enc_short_chains_ == 1) {
+      ru_short = (ru_chain >= 250 && d > 128) ? 2 : 0;     // units the fused kernel runs (C <= 128) keep their chains
+      down_short = down_chain >= 250 ? (last ? 1 : 2) : 0;
+    } else if (enc_short_chains_ >= 2) {
+      ru_short = (d > 128 || enc_short_chains_ >= (d > 64 ? 3 : 4)) ? 1 : 0;
+      down_short = 1;
+    }
+    for (int u = 0; u < 3; ++u) build_ru(blk->ru[u], p + ".res_unit" + std::to_string(u + 1), d, dils[u], ru_prec, ru_short);
     blk->s.build(alpha_of(tensor(p + ".snake1.alpha"), d, p + ".snake1.alpha"));
     ConvSpec cs;
     cs.cin = d; cs.cout = 2 * d; cs.k = 2 * s; cs.stride = s; cs.padding = (s + 1) / 2;  // EncoderBlock.cs:27-33
     auto w = folded_conv(p + ".conv1", 2 * d, d, 2 * s, &b, 2 * d);
-    blk->down.build(p + ".conv1", cs, w, b, enc_prec_);
+    blk->down.build(p + ".conv1", cs, w, b, down_prec, down_short);
     enc_blocks_.push_back(std::move(blk));
     d *= 2;
   }
@@ -340,7 +376,7 @@ void DacEngine::finalize_weights() {
     ConvSpec cs;
     cs.cin = d; cs.cout = cfg_.latent_dim; cs.k = 3; cs.padding = 1;
     auto w = folded_conv("encoder.conv2", cfg_.latent_dim, d, 3, &b, cfg_.latent_dim);
-    enc_out_.build("encoder.conv2", cs, w, b, enc_prec_);
+    enc_out_.build("encoder.conv2", cs, w, b, enc_tail_fp32_ >= 1 ? PREC_FP32 : enc_prec_, enc_short_chains_ >= 1 ? 1 : 0);
   }
   // ---- quantiser (Modules/DAC/VectorQuantizer.cs:36-43)
   {
@@ -388,7 +424,8 @@ void DacEngine::finalize_weights() {
     ConvSpec cs;
     cs.cin = cfg_.latent_dim; cs.cout = C; cs.k = 7; cs.padding = 3;
     auto w = folded_conv("decoder.conv1", C, cfg_.latent_dim, 7, &b, C);
-    dec_in_.build("decoder.conv1", cs, w, b, dec_prec_ != PREC_FP32 ? dec_wide_prec_ : dec_prec_);
+    dec_in_.build("decoder.conv1", cs, w, b, dec_prec_ != PREC_FP32 ? dec_wide_prec_ : dec_prec_, 0,
+                  dec_prec_ != PREC_FP32 && dec_wide_prec_ == PREC_F16 && dec_h16_opt_ != 0);
   }
   dec_blocks_.clear();
   int cout = C;
@@ -402,7 +439,8 @@ void DacEngine::finalize_weights() {
     ConvSpec cs;
     cs.transposed = true; cs.cin = cin; cs.cout = cout; cs.k = 2 * s; cs.stride = s; cs.padding = (s + 1) / 2;
     auto w = folded_conv(p + ".conv_t1", cin, cout, 2 * s, &b, cout);  // norm per in-channel (dims 1,2 of [Cin,Cout,k])
-    blk->up.build(p + ".conv_t1", cs, w, b, (cin > 128 && dec_prec_ != PREC_FP32) ? dec_wide_prec_ : dec_prec_);
+    blk->up.build(p + ".conv_t1", cs, w, b, (cin > 128 && dec_prec_ != PREC_FP32) ? dec_wide_prec_ : dec_prec_, 0,
+                  cin > 128 && dec_prec_ != PREC_FP32 && dec_wide_prec_ == PREC_F16 && dec_h16_opt_ != 0);
     const int dils[3] = {1, 3, 9};
     for (int u = 0; u < 3; ++u) build_ru(blk->ru[u], p + ".res_unit" + std::to_string(u + 1), cout, dils[u], dec_prec_);
     dec_blocks_.push_back(std::move(blk));
@@ -425,6 +463,21 @@ void DacEngine::finalize_weights() {
       if (!b.empty()) d_conv_out_b_ = upload(b);
       conv_out_c_ = cout;
     }
+  }
+  // fp16-operand decoder path: decoder.conv1, every transposed conv with more than 128 input channels and every
+  // residual unit with more than 128 channels must be on that executor (their activations are exchanged as fp16), and
+  // the last block must be narrow (it hands fp32 to the fused units / the final conv)
+  h16_ = dec_h16_opt_ != 0 && dec_in_.direct16() && !dec_blocks_.empty() && !wide_layer(cout);
+  {
+    int c_in = C;
+    for (auto& blk : dec_blocks_) {
+      const int c_out = c_in / 2;
+      if (wide_layer(c_in) && !blk->up.direct16()) h16_ = false;
+      if (wide_layer(c_out))
+        for (auto& r : blk->ru) if (!r.c1.direct16() || !r.c2.direct16()) h16_ = false;
+      c_in = c_out;
+    }
+    if (!wide_layer(C)) h16_ = false;
   }
   drop_tensors();
   ready_ = true;
@@ -485,10 +538,26 @@ int DacEngine::micro_batch(int B, int64_t Lp) const {
     c /= 2;
     peak = std::max<int64_t>(peak, t * c);
   }
-  const double per_clip = 3.0 * (double)peak * 4 + 2.0 * (double)T * cfg_.latent_dim * 4;
+  // fp16 activations of the wide decoder layers (3 rotating buffers) + the fp16 latent
+  int64_t peak16 = 0;
+  if (h16_) {
+    int64_t t16 = dec_in_.out_len((int)T);
+    peak16 = t16 * cfg_.decoder_dim;
+    int c16 = cfg_.decoder_dim;
+    for (auto& b : dec_blocks_) {
+      t16 = b->up.out_len((int)t16);
+      c16 /= 2;
+      if (wide_layer(c16)) peak16 = std::max<int64_t>(peak16, t16 * c16);
+    }
+  }
+  const double per_clip = 3.0 * (double)peak * 4 + 3.0 * (double)peak16 * 2 + 2.5 * (double)T * cfg_.latent_dim * 4;
   int mb = (int)std::max(1.0, std::floor((double)max_workspace_bytes_ / per_clip));
   const_cast<DacEngine*>(this)->per_clip_elems_ = peak;
-  return std::min(mb, B);
+  const_cast<DacEngine*>(this)->per_clip_elems16_ = peak16;
+  mb = std::min(mb, B);
+  // even split: 512 clips at 21 per micro-batch would leave a short tail batch; 25 batches of 20-21 clips instead
+  const int n_batches = (B + mb - 1) / mb;
+  return (B + n_batches - 1) / n_batches;
 }
 
 void DacEngine::ensure_workspace(int mb, int64_t Lp) {
@@ -497,6 +566,10 @@ void DacEngine::ensure_workspace(int mb, int64_t Lp) {
   for (auto& w : ws_) w.reserve((size_t)mb * per_clip_elems_ * sizeof(float));
   z_in_.reserve((size_t)mb * T * cfg_.latent_dim * sizeof(float));
   z_q_.reserve((size_t)mb * T * cfg_.latent_dim * sizeof(float));
+  if (h16_) {
+    for (auto& w : ws16_) w.reserve((size_t)mb * per_clip_elems16_ * 2);
+    z16_.reserve((size_t)mb * T * cfg_.latent_dim * 2);
+  }
 }
 
 // One ResidualUnit (Modules/DAC/ResidualUnit.cs:24-59): y = conv_k1(Snake2(conv_k7(Snake1(x)))) + x.
@@ -547,9 +620,83 @@ int DacEngine::run_encoder(const float* audio, long long audio_stride, int in_le
   return cur;
 }
 
+// Wide ResidualUnit on the fp16-operand executor (Modules/DAC/ResidualUnit.cs:24-59): the k7 conv reads Snake1(x) as
+// fp16 and writes Snake2(.) as fp16; the 1x1 conv reads that, adds the raw fp32 x and writes the raw fp32 result (for
+// the next unit's residual) and / or the following Snake of it as fp16 (the next conv's operand).
+void DacEngine::run_ru_h16(const ResUnit& ru, int* cur32, int* cur16, int B, int T, const SnakeParams* post, bool need32) {
+  const LaunchCtx c = ctx();
+  const int h16 = (*cur16 + 1) % 3, y16 = (*cur16 + 2) % 3, y32 = (*cur32 + 1) % 3;
+  ConvRunArgs a;
+  a.in16 = buf16(*cur16); a.out16 = buf16(h16); a.batch = B; a.t_in = T;
+  a.post = PRO_SNAKE; a.post_alpha = ru.s2.alpha; a.post_inv_alpha = ru.s2.inv_alpha;
+  ru.c1.run(a, c);
+  ConvRunArgs b;
+  b.in16 = buf16(h16); b.residual = buf(*cur32); b.batch = B; b.t_in = T;
+  b.out = need32 ? buf(y32) : nullptr;
+  b.out16 = buf16(y16);
+  b.post = PRO_SNAKE; b.post_alpha = post->alpha; b.post_inv_alpha = post->inv_alpha;
+  ru.c2.run(b, c);
+  if (need32) *cur32 = y32;
+  *cur16 = y16;
+}
+
 // input latent: z_q_ [B][T][latent] channels-last
 int DacEngine::run_decoder(int, int B, int T, float* audio_out, long long) {
   const LaunchCtx c = ctx();
+  if (h16_) {
+    // ---- fp16-operand path for the wide layers (conv_h16.cu); narrow blocks continue on the fp32 / fused-unit path
+    launch_f32_to_f16(z_q_.as<float>(), z16_.as<void>(), (long long)B * T * cfg_.latent_dim, c);
+    ConvRunArgs a;
+    a.in16 = z16_.as<void>(); a.out16 = buf16(0); a.batch = B; a.t_in = T;
+    a.post = PRO_SNAKE; a.post_alpha = dec_blocks_[0]->s.alpha; a.post_inv_alpha = dec_blocks_[0]->s.inv_alpha;   // DecoderBlock.cs:26
+    dec_in_.run(a, c);
+    T = dec_in_.out_len(T);
+    int cur32 = 0, cur16 = 0;
+    bool on16 = true;    // the current activation is the fp16 buffer cur16 (already carrying the next conv's Snake)
+    int ch = cfg_.decoder_dim;
+    for (size_t i = 0; i < dec_blocks_.size(); ++i) {
+      auto& blk = dec_blocks_[i];
+      const int c_out = ch / 2;
+      const SnakeParams* next = i + 1 < dec_blocks_.size() ? &dec_blocks_[i + 1]->s : &dec_snake_;
+      if (on16) {
+        // transposed conv: raw fp32 x (the first unit's residual) + fp16 Snake1(x) when the units are wide
+        const bool wide_out = wide_layer(c_out);
+        ConvRunArgs u;
+        u.in16 = buf16(cur16); u.batch = B; u.t_in = T;
+        u.out = buf(cur32);
+        if (wide_out) {
+          u.out16 = buf16((cur16 + 1) % 3);
+          u.post = PRO_SNAKE; u.post_alpha = blk->ru[0].s1.alpha; u.post_inv_alpha = blk->ru[0].s1.inv_alpha;
+        }
+        blk->up.run(u, c);
+        T = blk->up.out_len(T);
+        if (wide_out) {
+          cur16 = (cur16 + 1) % 3;
+          for (int r = 0; r < 3; ++r)
+            run_ru_h16(blk->ru[r], &cur32, &cur16, B, T, r < 2 ? &blk->ru[r + 1].s1 : next, r < 2);
+        } else {
+          on16 = false;
+          for (int r = 0; r < 3; ++r) cur32 = run_ru(blk->ru[r], cur32, B, T, r == 2 ? next : nullptr);
+        }
+      } else {
+        ConvRunArgs u;
+        u.in = buf(cur32); u.out = buf((cur32 + 1) % 3); u.batch = B; u.t_in = T;
+        blk->up.run(u, c);
+        T = blk->up.out_len(T);
+        cur32 = (cur32 + 1) % 3;
+        for (int r = 0; r < 3; ++r) cur32 = run_ru(blk->ru[r], cur32, B, T, r == 2 ? next : nullptr);
+      }
+      ch = c_out;
+    }
+    ConvRunArgs o;   // Decoder.cs:44-46: (Snake already applied) -> conv -> tanh
+    o.in = buf(cur32); o.out = audio_out; o.batch = B; o.t_in = T;
+    o.act = ACT_TANH;
+    if (conv_out_c_)
+      launch_conv_cout1(buf(cur32), audio_out, T, conv_out_c_, d_conv_out_w_, d_conv_out_b_, 7, 3, 1, B, c);
+    else
+      dec_out_.run(o, c);
+    return cur32;
+  }
   ConvRunArgs a;
   a.in = z_q_.as<float>(); a.out = buf(0); a.batch = B; a.t_in = T;
   if (!dec_blocks_.empty()) {   // DecoderBlock.cs:26: Snake1d before the transposed conv

@@ -48,6 +48,7 @@ class Engine {
   cudaStream_t stream_ = nullptr;
   Profiler prof_;
   uint64_t launches_ = 0;
+  int fast_sin_ = -1, fuse_ru_ = 1;   // options "fast_sin" / "fuse_ru" (per handle)
   size_t max_workspace_bytes_ = (size_t)32 << 30;
   TensorMap tensors_;
   std::string weights_metadata_ = "{}";
@@ -126,7 +127,7 @@ class DacEngine : public Engine {
   std::vector<float> folded_conv(const std::string& prefix, int d0, int d1, int k, std::vector<float>* bias,
                                  int bias_n);
   Precision boosted(Precision p, bool narrow) const;
-  void build_ru(ResUnit& ru, const std::string& prefix, int dim, int dil, Precision prec);
+  void build_ru(ResUnit& ru, const std::string& prefix, int dim, int dil, Precision prec, int short_chains = 0);
   // returns the buffer index holding the result; T_io: in = input length, out = output length
   int run_ru(const ResUnit& ru, int cur, int B, int T, const SnakeParams* post);
   int run_encoder(const float* audio, long long audio_stride, int in_len, int B, int Lp, int* T_out);
@@ -134,6 +135,11 @@ class DacEngine : public Engine {
   int micro_batch(int B, int64_t Lp) const;
   void ensure_workspace(int mb, int64_t Lp);
   float* buf(int i) { return ws_[i].as<float>(); }
+  void* buf16(int i) { return ws16_[i].as<void>(); }
+  bool wide_layer(int channels) const { return channels > 128 && dec_prec_ != PREC_FP32; }
+  // wide ResidualUnit on the fp16-operand executor: x32 (raw, buffer cur32) + x16 = Snake1(x) (buffer cur16) ->
+  // out32 (raw, written only when `need32`) + out16 = post(out) ; returns through *cur32 / *cur16
+  void run_ru_h16(const ResUnit& ru, int* cur32, int* cur16, int B, int T, const SnakeParams* post, bool need32);
 
   DacConfig cfg_;
   // Encoder: three-pass bf16 split everywhere (codes must match the fp32 reference).  Decoder: the wide layers
@@ -142,6 +148,8 @@ class DacEngine : public Engine {
   // throughput (profiles/r01_decoder_precision_modes.txt).  decoder_precision=<mode> makes the decoder uniform again.
   Precision enc_prec_ = PREC_BF16X3, dec_prec_ = PREC_BF16X3, dec_wide_prec_ = PREC_F16;
   bool dec_boost_ = true;
+  int enc_tail_fp32_ = 0;   // option encoder_tail_fp32
+  int enc_short_chains_ = 1;  // option encoder_short_chains
   // encoder
   float* d_conv_in_w_ = nullptr;
   float* d_conv_in_b_ = nullptr;
@@ -161,7 +169,11 @@ class DacEngine : public Engine {
   int conv_out_c_ = 0;
   // workspaces: 3 rotating activation buffers + latent buffers
   DeviceBuffer ws_[3], z_in_, z_q_, dia_codes_, dia_idx_, dia_audio_;
+  DeviceBuffer ws16_[3], z16_;  // fp16 activations of the fp16-operand decoder layers (conv_h16.cu)
   int64_t per_clip_elems_ = 0;  // per padded sample, see ensure_workspace
+  int64_t per_clip_elems16_ = 0;
+  bool h16_ = false;            // decoder's wide layers run on the fp16-operand executor (option decoder_h16, default on)
+  int dec_h16_opt_ = 1;
 };
 
 Engine* create_engine(nc_codec_kind kind, const void* cfg, size_t cfg_size, int device_index);

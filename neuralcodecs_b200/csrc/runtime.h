@@ -161,6 +161,9 @@ struct LaunchCtx {
   int num_sms = 148;
   Profiler* prof = nullptr;
   uint64_t* launches = nullptr;
+  // per-handle kernel policies (engine options "fast_sin" / "fuse_ru"); never process-global
+  int fast_sin = -1;   // Snake sin(): -1 = MUFU sin on the tf32 / bf16x3 / f16 tensor-core layers, precise elsewhere; 0 = always precise; 1 = always MUFU
+  int fuse_ru = 1;     // 0: never use the fused ResidualUnit kernel
 
   int begin() const { return prof ? prof->begin(stream) : -1; }
   void end(int id, const std::string& name, double flops, double bytes, const std::string& layer = "") const {

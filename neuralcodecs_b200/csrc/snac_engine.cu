@@ -540,7 +540,7 @@ void SnacEngine::run_decoder(int B, int T, const float* const* noise, uint64_t s
         nz = noise[i] + (int64_t)b0 * nlen[i];
       } else {
         float* gen = static_cast<float*>(noise_buf_.reserve((size_t)B * T * sizeof(float)));
-        launch_randn(gen, (long long)B * T, seed + (uint64_t)b0 * 0x9e3779b97f4a7c15ull, (uint32_t)i, c);
+        launch_randn(gen, B, T, b0, seed, (uint32_t)i, c);
         nz = gen;
       }
       ConvRunArgs n;

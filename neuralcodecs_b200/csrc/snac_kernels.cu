@@ -430,22 +430,26 @@ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
   return x;
 }
-__global__ void randn_kernel(float* __restrict__ out, long long n, uint64_t seed, uint32_t stream_id) {
+// out[b][t], b in [0, clips): the counter is (global clip index clip0 + b, t), so a clip's noise does not depend on how
+// the batch was split into micro-batches or across ranks.
+__global__ void randn_kernel(float* __restrict__ out, long long n, int T, long long clip0, uint64_t seed, uint32_t stream_id) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const uint32_t lo = (uint32_t)i, hi = (uint32_t)(i >> 32);
+    const long long clip = clip0 + i / T;
+    const uint32_t lo = (uint32_t)(i % T), hi = hash32((uint32_t)clip) ^ hash32((uint32_t)(clip >> 32) + 0x51ed270bu);
     const uint32_t a = hash32(lo ^ hash32(hi + 0x9e3779b9u) ^ hash32((uint32_t)seed + stream_id * 0x85ebca6bu));
     const uint32_t b = hash32(a ^ (uint32_t)(seed >> 32) ^ 0xc2b2ae35u);
     const float u1 = ((a >> 8) + 1) * (1.0f / 16777216.0f), u2 = (b >> 8) * (1.0f / 16777216.0f);
     out[i] = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
   }
 }
-void launch_randn(float* out, long long n, uint64_t seed, uint32_t stream_id, const LaunchCtx& ctx) {
+void launch_randn(float* out, int clips, int T, long long clip0, uint64_t seed, uint32_t stream_id, const LaunchCtx& ctx) {
+  const long long n = (long long)clips * T;
   if (n == 0) return;
   long long blocks = (n + 255) / 256;
   const long long cap = (long long)ctx.num_sms * 16;
   if (blocks > cap) blocks = cap;
   const int ev = ctx.begin();
-  randn_kernel<<<(unsigned)blocks, 256, 0, ctx.stream>>>(out, n, seed, stream_id);
+  randn_kernel<<<(unsigned)blocks, 256, 0, ctx.stream>>>(out, n, T, clip0, seed, stream_id);
   check_launch((int)cudaGetLastError(), "randn");
   ctx.end(ev, "randn", 0, 4.0 * n);
 }

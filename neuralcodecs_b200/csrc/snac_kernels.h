@@ -50,6 +50,6 @@ void launch_local_attn(const float* qkv, float* out, const float* inv_freq, int 
 // out[b, 0:out_len] = in[b*in_stride + 0:out_len]
 void launch_trim_rows(const float* in, float* out, int batch, long long in_stride, long long out_len, const LaunchCtx& ctx);
 // N(0,1) samples from a counter-based generator keyed by (seed, stream_id, index)
-void launch_randn(float* out, long long n, uint64_t seed, uint32_t stream_id, const LaunchCtx& ctx);
+void launch_randn(float* out, int clips, int T, long long clip0, uint64_t seed, uint32_t stream_id, const LaunchCtx& ctx);
 
 }  // namespace nc

@@ -7,6 +7,7 @@ place of TorchSharp tensors.  All arithmetic happens in libneuralcodecs_cuda.so.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import json
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -15,6 +16,15 @@ import numpy as np
 from . import _lib
 from .config import SNACConfig
 
+
+
+def _seed(seed: Optional[int]) -> int:
+    """NoiseBlock noise (Modules/SNAC/NoiseBlock.cs:38-45) is a fresh randn on every call in the reference: with no
+    explicit seed each call draws a new 64-bit seed; an explicit seed gives a reproducible realisation that does not
+    depend on how the batch is split (the device counter is (clip index, time step))."""
+    if seed is None:
+        return int.from_bytes(os.urandom(8), "little")
+    return int(seed) & 0xFFFFFFFFFFFFFFFF
 
 class SNAC:
     def __init__(self, config: SNACConfig, *, options: Optional[Dict[str, str]] = None):
@@ -135,7 +145,7 @@ class SNAC:
                                              self._ptr_array(codes, len(codes))), "SNAC", "Encoding")
         return codes
 
-    def Decode(self, codes, noise: Optional[Sequence[np.ndarray]] = None, seed: int = 0) -> np.ndarray:
+    def Decode(self, codes, noise: Optional[Sequence[np.ndarray]] = None, seed: Optional[int] = None) -> np.ndarray:
         """SNAC.Decode (SNAC.cs:157-192): audio [B,1,frames*hop], not trimmed.  `noise`: explicit N(0,1) tensors
         [B,1,T_i] per decoder block (None = drawn on the device from `seed`)."""
         if codes is None:
@@ -154,11 +164,11 @@ class SNAC:
         out_len = nlens[-1] if nlens else frames * self._config.hop_length
         audio = np.empty((B, 1, out_len), np.float32)
         _lib.check(_lib.lib().nc_snac_decode(self._handle(), self._ptr_array(cs, len(cs)), B, frames,
-                                             self._ptr_array(ns, len(nlens)) if ns is not None else None, seed,
+                                             self._ptr_array(ns, len(nlens)) if ns is not None else None, _seed(seed),
                                              audio.ctypes.data_as(C.c_void_p)), "SNAC", "Decoding")
         return audio
 
-    def forward(self, audioData, noise: Optional[Sequence[np.ndarray]] = None, seed: int = 0):
+    def forward(self, audioData, noise: Optional[Sequence[np.ndarray]] = None, seed: Optional[int] = None):
         """SNAC.forward (SNAC.cs:91-106) -> (audio [B,1,L] trimmed to the input length, codes)."""
         a = self._audio2d(audioData)
         B, L = a.shape
@@ -167,12 +177,12 @@ class SNAC:
         ns = [np.ascontiguousarray(n, dtype=np.float32).reshape(B, -1) for n in noise] if noise is not None else None
         audio = np.empty((B, 1, L), np.float32)
         _lib.check(_lib.lib().nc_snac_forward(self._handle(), a.ctypes.data_as(C.c_void_p), B, L,
-                                              self._ptr_array(ns, len(nlens)) if ns is not None else None, seed,
+                                              self._ptr_array(ns, len(nlens)) if ns is not None else None, _seed(seed),
                                               audio.ctypes.data_as(C.c_void_p), self._ptr_array(codes, len(codes))),
                    "SNAC", "Encoding")
         return audio, codes
 
-    def ProcessAudio(self, audioData, sampleRate: int, noise=None, seed: int = 0) -> np.ndarray:
+    def ProcessAudio(self, audioData, sampleRate: int, noise=None, seed: Optional[int] = None) -> np.ndarray:
         """SNAC.ProcessAudio (SNAC.cs:255-282): linear resample to the model rate if needed (:284-308, on the device),
         forward, flat array of the (resampled) input length.  A [B, L] array is processed as one batch -> [B, L']."""
         if audioData is None or len(audioData) == 0:
@@ -188,7 +198,7 @@ class SNAC:
         out = np.empty((B, n.value), np.float32)
         ns = [np.ascontiguousarray(z, dtype=np.float32).reshape(B, -1) for z in noise] if noise is not None else None
         nz = self._ptr_array(ns, len(ns)) if ns is not None else None
-        _lib.check(lib.nc_snac_process_audio(self._handle(), a.ctypes.data_as(C.c_void_p), B, L, int(sampleRate), nz, int(seed),
+        _lib.check(lib.nc_snac_process_audio(self._handle(), a.ctypes.data_as(C.c_void_p), B, L, int(sampleRate), nz, _seed(seed),
                                              out.ctypes.data_as(C.c_void_p), n.value, C.byref(n)), "SNAC", "ProcessAudio")
         return out.reshape(-1) if flat else out
 
@@ -200,19 +210,19 @@ class SNAC:
 
     # ------------------------------------------------------------------ raw host-pointer variant
     def forward_host(self, audio_ptr: int, batch: int, length: int, audio_out_ptr: int, code_ptrs: Optional[Sequence[int]] = None,
-                     seed: int = 0) -> None:
+                     seed: Optional[int] = None) -> None:
         """nc_snac_forward on caller-owned HOST buffers given as raw addresses (e.g. pinned torch tensors' data_ptr());
         H2D / D2H copies happen inside the call.  Noise is drawn on the device from `seed`."""
         cp = (C.c_void_p * max(len(code_ptrs), 1))(*[p or None for p in code_ptrs]) if code_ptrs else None
-        _lib.check(_lib.lib().nc_snac_forward(self._handle(), audio_ptr, batch, length, None, seed, audio_out_ptr, cp),
+        _lib.check(_lib.lib().nc_snac_forward(self._handle(), audio_ptr, batch, length, None, _seed(seed), audio_out_ptr, cp),
                    "SNAC", "Encoding")
 
     # ------------------------------------------------------------------ device-pointer variant
     def forward_dev(self, audio_ptr: int, batch: int, length: int, audio_out_ptr: int, code_ptrs: Sequence[int],
-                    noise_ptrs: Optional[Sequence[int]] = None, seed: int = 0) -> None:
+                    noise_ptrs: Optional[Sequence[int]] = None, seed: Optional[int] = None) -> None:
         cp = (C.c_void_p * max(len(code_ptrs), 1))(*[p or None for p in code_ptrs])
         npz = (C.c_void_p * max(len(noise_ptrs), 1))(*[p or None for p in noise_ptrs]) if noise_ptrs else None
-        _lib.check(_lib.lib().nc_snac_forward_dev(self._handle(), audio_ptr, batch, length, npz, seed, audio_out_ptr or None,
+        _lib.check(_lib.lib().nc_snac_forward_dev(self._handle(), audio_ptr, batch, length, npz, _seed(seed), audio_out_ptr or None,
                                                   cp if code_ptrs else None), "SNAC", "Encoding")
 
     def _handle(self):

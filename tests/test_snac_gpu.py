@@ -116,6 +116,10 @@ def test_snac24k_preset_config2_clip(snac_24k):
     a3 = m.Decode([c.numpy() for c in ref["codes"]], None, seed=8)
     np.testing.assert_array_equal(a1, a2)
     assert np.abs(a1 - a3).max() > 0
+    m.set_option("max_workspace_mb", "64")                          # micro-batches of one clip: same noise per clip
+    np.testing.assert_array_equal(a1, m.Decode([c.numpy() for c in ref["codes"]], None, seed=7))
+    a4 = m.Decode([c.numpy() for c in ref["codes"]])                # no seed: a fresh realisation per call (NoiseBlock.cs)
+    assert np.abs(a4 - m.Decode([c.numpy() for c in ref["codes"]])).max() > 0
     m.Dispose()
 
 

@@ -9,8 +9,9 @@ from .dac import DAC  # noqa: F401
 from .snac import SNAC  # noqa: F401
 from .encodec import Encodec, EncodecCompressor  # noqa: F401
 from ._lib import CodecException  # noqa: F401
+from .dac_file import DACFile  # noqa: F401
 
-__all__ = ["DAC", "DACConfig", "SNAC", "SNACConfig", "Encodec", "EncodecCompressor", "EncodecConfig", "DeviceConfiguration", "CodecException"]
+__all__ = ["DAC", "DACConfig", "SNAC", "SNACConfig", "Encodec", "EncodecCompressor", "EncodecConfig", "DeviceConfiguration", "CodecException", "DACFile"]
 
 
 def inspect_weights(path: str) -> dict:

@@ -1,7 +1,10 @@
 // HBM-bound kernels of the codec hot path.  See codec_kernels.h for the contracts.
 #include <cuda_fp16.h>
 
+#include <algorithm>
+#include <cstdlib>
 #include "codec_kernels.h"
+#include "umma.cuh"
 
 #include <cfloat>
 
@@ -300,6 +303,218 @@ rvq_encode_kernel(const RvqWeights w, const float* __restrict__ z, float* __rest
   }
 }
 
+// ------------------------------------------------------------------------------ fused RVQ encode, block version
+// The warp kernel above re-reads every stage's in_proj / codebook / out_proj (100 KB) from L1/L2 for every frame: 98
+// GB/s of algorithmic traffic (1.5 % of HBM peak), latency-bound.  Here one persistent CTA per SM stages a stage's weights
+// in shared memory ONCE per pass of 16 frames (1-D bulk async copies, double-buffered so stage s+1 streams in while
+// stage s computes) and each warp carries TWO frames in registers, so every weight fetched from shared memory feeds
+// two FMAs.  Arithmetic and evaluation order are those of the warp kernel (lane-strided in_proj partial sums in
+// ascending channel order + butterfly, expanded-form distance, lowest-index argmin): codes are bit-identical to it.
+// The kernel's own bound is shared-memory bandwidth / fp32 FMA issue, not HBM: 442 KFLOP per 8.3 KB frame is 53 FLOP/B,
+// five times the fp32 ridge of the machine.
+std::vector<float> rvq_stage_blob(int Dz, int D, int K, const float* in_w, const float* in_b, const float* cb, const float* cb_sq,
+                                  const float* out_w, const float* out_b) {
+  std::vector<float> v;
+  if (D != kVqD || Dz % 128 != 0) return v;
+  const int cpl = Dz / 32;
+  v.reserve((size_t)17 * Dz + 9 * K + 8);
+  for (int d = 0; d < D; ++d)
+    for (int i4 = 0; i4 < cpl / 4; ++i4)
+      for (int lane = 0; lane < 32; ++lane)
+        for (int j = 0; j < 4; ++j) v.push_back(in_w[(size_t)d * Dz + lane + 32 * (4 * i4 + j)]);
+  for (int d = 0; d < D; ++d) v.push_back(in_b[d]);
+  for (int k = 0; k < K; ++k) for (int d = 0; d < 4; ++d) v.push_back(cb[(size_t)k * D + d]);
+  for (int k = 0; k < K; ++k) for (int d = 4; d < 8; ++d) v.push_back(cb[(size_t)k * D + d]);
+  for (int k = 0; k < K; ++k) v.push_back(cb_sq[k]);
+  for (int c = 0; c < Dz; ++c) for (int d = 0; d < 4; ++d) v.push_back(out_w[(size_t)c * D + d]);
+  for (int c = 0; c < Dz; ++c) for (int d = 4; d < 8; ++d) v.push_back(out_w[(size_t)c * D + d]);
+  for (int c = 0; c < Dz; ++c) v.push_back(out_b[c]);
+  return v;
+}
+
+constexpr int kRvqWarps = 8, kRvqF = 2;
+
+template <int CPL>
+__global__ void __launch_bounds__(kRvqWarps * 32, 1)
+rvq_encode_block_kernel(const RvqWeights w, const float* __restrict__ z, float* __restrict__ zq, int64_t* __restrict__ codes,
+                        float* __restrict__ latents, int batch, int T, int n_q) {
+  extern __shared__ __align__(128) uint8_t rvq_smem[];
+  __shared__ uint64_t full[2];
+  const int Dz = w.Dz, K = w.K;
+  const uint32_t blob_bytes = (uint32_t)w.blob_floats * 4u;
+  const uint32_t buf_stride = (blob_bytes + 127u) & ~127u;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long frames = (long long)batch * T;
+  const long long passes = (frames + kRvqWarps * kRvqF - 1) / (kRvqWarps * kRvqF);
+  const long long my_passes = passes > (long long)blockIdx.x ? (passes - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  const long long n_total = my_passes * n_q;
+  if (tid == 0) {
+    ptx::mbar_init(&full[0], 1);
+    ptx::mbar_init(&full[1], 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  auto fetch = [&](long long n) {   // stage (n % n_q)'s image -> buffer (n & 1); thread 0 only
+    uint8_t* dst = rvq_smem + (size_t)(n & 1) * buf_stride;
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(w.blob + (size_t)(n % n_q) * w.blob_floats);
+    ptx::fence_proxy_async_smem();
+    ptx::mbar_arrive_expect_tx(&full[n & 1], blob_bytes);
+    for (uint32_t off = 0; off < blob_bytes; off += 32768u) {
+      const uint32_t len = blob_bytes - off < 32768u ? blob_bytes - off : 32768u;
+      ptx::bulk_g2s(dst + off, src + off, len, &full[n & 1]);
+    }
+  };
+  if (tid == 0 && n_total > 0) fetch(0);
+
+  float r[kRvqF][CPL], acc[kRvqF][CPL];
+  long long fidx[kRvqF];
+  bool valid[kRvqF];
+  for (long long n = 0; n < n_total; ++n) {
+    const int s = (int)(n % n_q);
+    if (s == 0) {
+      const long long pass = (long long)blockIdx.x + (n / n_q) * gridDim.x;
+#pragma unroll
+      for (int f = 0; f < kRvqF; ++f) {
+        const long long fi = pass * (kRvqWarps * kRvqF) + warp * kRvqF + f;
+        valid[f] = fi < frames;
+        fidx[f] = valid[f] ? fi : frames - 1;
+        const float* zr = z + fidx[f] * Dz;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+          r[f][i] = __ldg(zr + lane + 32 * i);
+          acc[f][i] = 0.f;
+        }
+      }
+    }
+    if (tid == 0 && n + 1 < n_total) fetch(n + 1);   // buffer (n+1)&1 was released by the barrier that ended step n-1
+    ptx::mbar_wait(&full[n & 1], (uint32_t)(n >> 1) & 1u);
+    const float* sb = reinterpret_cast<const float*>(rvq_smem + (size_t)(n & 1) * buf_stride);
+    const float4* win4 = reinterpret_cast<const float4*>(sb);
+    const float* in_b = sb + (size_t)kVqD * Dz;
+    const float4* cb_lo = reinterpret_cast<const float4*>(in_b + kVqD);
+    const float4* cb_hi = cb_lo + K;
+    const float* csq = reinterpret_cast<const float*>(cb_hi + K);
+    const float4* wo_lo = reinterpret_cast<const float4*>(csq + K);
+    const float4* wo_hi = wo_lo + Dz;
+    const float* out_b = reinterpret_cast<const float*>(wo_hi + Dz);
+
+    // ---- in_proj (Modules/DAC/VectorQuantizer.cs:70)
+    float ze[kRvqF][kVqD];
+#pragma unroll
+    for (int d = 0; d < kVqD; ++d) {
+      float p[kRvqF];
+#pragma unroll
+      for (int f = 0; f < kRvqF; ++f) p[f] = 0.f;
+#pragma unroll
+      for (int i4 = 0; i4 < CPL / 4; ++i4) {
+        const float4 wv = win4[(d * (CPL / 4) + i4) * 32 + lane];
+#pragma unroll
+        for (int f = 0; f < kRvqF; ++f) {
+          p[f] = fmaf(wv.x, r[f][4 * i4 + 0], p[f]);
+          p[f] = fmaf(wv.y, r[f][4 * i4 + 1], p[f]);
+          p[f] = fmaf(wv.z, r[f][4 * i4 + 2], p[f]);
+          p[f] = fmaf(wv.w, r[f][4 * i4 + 3], p[f]);
+        }
+      }
+      const float bd = in_b[d];
+#pragma unroll
+      for (int f = 0; f < kRvqF; ++f) ze[f][d] = warp_sum(p[f]) + bd;
+    }
+    // ---- nearest codebook entry, un-normalised expanded form (VectorQuantizer.cs:110-121)
+    float e2[kRvqF], best[kRvqF];
+    int best_k[kRvqF];
+#pragma unroll
+    for (int f = 0; f < kRvqF; ++f) {
+      e2[f] = 0.f;
+#pragma unroll
+      for (int d = 0; d < kVqD; ++d) e2[f] = fmaf(ze[f][d], ze[f][d], e2[f]);
+      best[f] = FLT_MAX;
+      best_k[f] = 0;
+    }
+    for (int k = lane; k < K; k += 32) {
+      const float4 c0 = cb_lo[k], c1 = cb_hi[k];
+      const float cs = csq[k];
+#pragma unroll
+      for (int f = 0; f < kRvqF; ++f) {
+        float dot = ze[f][0] * c0.x;
+        dot = fmaf(ze[f][1], c0.y, dot); dot = fmaf(ze[f][2], c0.z, dot); dot = fmaf(ze[f][3], c0.w, dot);
+        dot = fmaf(ze[f][4], c1.x, dot); dot = fmaf(ze[f][5], c1.y, dot); dot = fmaf(ze[f][6], c1.z, dot);
+        dot = fmaf(ze[f][7], c1.w, dot);
+        const float dist = (e2[f] + cs) - 2.0f * dot;
+        if (dist < best[f]) { best[f] = dist; best_k[f] = k; }
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < kRvqF; ++f) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(0xffffffffu, best[f], o);
+        const int ok = __shfl_xor_sync(0xffffffffu, best_k[f], o);
+        if (od < best[f] || (od == best[f] && ok < best_k[f])) { best[f] = od; best_k[f] = ok; }   // lowest index wins
+      }
+    }
+    // ---- lookup + straight-through arithmetic (VectorQuantizer.cs:81) + out_proj (:82)
+    float q[kRvqF][kVqD];
+#pragma unroll
+    for (int f = 0; f < kRvqF; ++f) {
+      const float4 q0 = cb_lo[best_k[f]], q1 = cb_hi[best_k[f]];
+      const float qq[kVqD] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+      for (int d = 0; d < kVqD; ++d) q[f][d] = ze[f][d] + (qq[d] - ze[f][d]);
+    }
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+      const int c = lane + 32 * i;
+      const float4 w0 = wo_lo[c], w1 = wo_hi[c];
+      const float bo = out_b[c];
+#pragma unroll
+      for (int f = 0; f < kRvqF; ++f) {
+        float v = w0.x * q[f][0];
+        v = fmaf(w0.y, q[f][1], v); v = fmaf(w0.z, q[f][2], v); v = fmaf(w0.w, q[f][3], v);
+        v = fmaf(w1.x, q[f][4], v); v = fmaf(w1.y, q[f][5], v); v = fmaf(w1.z, q[f][6], v); v = fmaf(w1.w, q[f][7], v);
+        v += bo;
+        acc[f][i] += v;   // zQ.add_(zQi)        ResidualVectorQuantizer.cs:68
+        r[f][i] -= v;     // residual.sub_(zQi)  ResidualVectorQuantizer.cs:69
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < kRvqF; ++f) {
+      if (!valid[f]) continue;
+      const int b = (int)(fidx[f] / T), t = (int)(fidx[f] % T);
+      if (codes && lane == 0) codes[((long long)b * n_q + s) * T + t] = best_k[f];
+      if (latents && lane < kVqD) {
+        float mine = ze[f][0];
+#pragma unroll
+        for (int d = 1; d < kVqD; ++d) mine = lane == d ? ze[f][d] : mine;
+        latents[((long long)b * n_q * kVqD + s * kVqD + lane) * T + t] = mine;
+      }
+      if (zq && s == n_q - 1) {
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) zq[fidx[f] * Dz + lane + 32 * i] = acc[f][i];
+      }
+    }
+    __syncthreads();   // every warp is done with buffer n&1 before step n+1 prefetches into it
+  }
+}
+
+template <int CPL>
+static bool rvq_encode_block_launch(const RvqWeights& w, const float* z, float* zq, int64_t* codes, float* latents,
+                                    int batch, int T, int n_q, const LaunchCtx& ctx) {
+  const size_t buf_stride = ((size_t)w.blob_floats * 4 + 127) & ~(size_t)127;
+  const size_t smem = 2 * buf_stride;
+  if (smem > 226 * 1024) return false;
+  auto k = rvq_encode_block_kernel<CPL>;
+  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  const long long frames = (long long)batch * T;
+  long long passes = (frames + kRvqWarps * kRvqF - 1) / (kRvqWarps * kRvqF);
+  const int grid = (int)std::min<long long>(passes, ctx.num_sms);
+  k<<<grid, kRvqWarps * 32, smem, ctx.stream>>>(w, z, zq, codes, latents, batch, T, n_q);
+  return true;
+}
+
 template <int CPL>
 static void rvq_encode_launch(const RvqWeights& w, const float* z, float* zq, int64_t* codes, float* latents,
                               int batch, int T, int n_q, const LaunchCtx& ctx) {
@@ -316,7 +531,18 @@ void launch_rvq_encode(const RvqWeights& w, const float* z, float* zq, int64_t* 
   if (w.Dz % 32 != 0 || w.K % 32 != 0) throw Error(NC_UNSUPPORTED, "rvq: latent dim / codebook size must be multiples of 32");
   if ((long long)batch * T == 0) return;
   const int ev = ctx.begin();
-  switch (w.Dz / 32) {
+  static const int use_block = getenv("NC_RVQ_BLOCK") ? atoi(getenv("NC_RVQ_BLOCK")) : 1;
+  bool done = false;
+  if (use_block && w.blob && w.Dz % 128 == 0) {
+    switch (w.Dz / 32) {
+      case 4: done = rvq_encode_block_launch<4>(w, z, zq, codes, latents, batch, T, n_q, ctx); break;
+      case 8: done = rvq_encode_block_launch<8>(w, z, zq, codes, latents, batch, T, n_q, ctx); break;
+      case 16: done = rvq_encode_block_launch<16>(w, z, zq, codes, latents, batch, T, n_q, ctx); break;
+      case 32: done = rvq_encode_block_launch<32>(w, z, zq, codes, latents, batch, T, n_q, ctx); break;
+      default: break;
+    }
+  }
+  if (!done) switch (w.Dz / 32) {
     case 1: rvq_encode_launch<1>(w, z, zq, codes, latents, batch, T, n_q, ctx); break;
     case 2: rvq_encode_launch<2>(w, z, zq, codes, latents, batch, T, n_q, ctx); break;
     case 4: rvq_encode_launch<4>(w, z, zq, codes, latents, batch, T, n_q, ctx); break;

@@ -2,6 +2,7 @@
 // transposes at the API boundary, fused residual vector quantisation, code lookup.
 #pragma once
 #include <cstdint>
+#include <vector>
 
 #include "runtime.h"
 
@@ -38,7 +39,16 @@ struct RvqWeights {
   const float* cb_sq = nullptr;  // [stage][K]   fp32 sum of squares (d ascending)
   const float* out_w = nullptr;  // [stage][Dz][D]
   const float* out_b = nullptr;  // [stage][Dz]
+  // per-stage shared-memory image for the block kernel (rvq_stage_blob): [stage][blob_floats], nullptr = warp kernel only
+  const float* blob = nullptr;
+  int blob_floats = 0;
 };
+// One stage's weights in the layout rvq_encode_block_kernel reads from shared memory (all fp32):
+//   in_proj  [D][Dz/128][32 lanes][4]   element (d, i4, lane, j) = in_w[d][lane + 32 * (4 * i4 + j)]
+//   in_b [D] | codebook dims 0-3 [K][4] | dims 4-7 [K][4] | cb_sq [K] | out_proj dims 0-3 [Dz][4] | dims 4-7 [Dz][4] | out_b [Dz]
+// Requires D == 8 and Dz % 128 == 0; returns an empty vector otherwise.
+std::vector<float> rvq_stage_blob(int Dz, int D, int K, const float* in_w, const float* in_b, const float* cb, const float* cb_sq,
+                                  const float* out_w, const float* out_b);
 
 // Fused DAC RVQ encode over frames z[b, t, :] (channels-last rows of Dz floats):
 //   per stage: zE = in_proj(res); idx = argmin_k (|zE|^2 + |c_k|^2) - 2 zE.c_k (lowest index wins);

@@ -39,7 +39,7 @@ constexpr int kFirstEpiWarp = 2;
 constexpr int kLoaderWarp = kFirstEpiWarp + kEpiWarps;   // 10
 constexpr int kResidualWarp = kLoaderWarp + 1;           // 11
 constexpr int kThreads = 32 * (kResidualWarp + 1);       // 384
-constexpr int kMaxA = 6, kMaxW = 8, kEpi = 2;
+constexpr int kMaxA = 6, kMaxW = 8, kMaxEpi = 6;
 constexpr uint32_t kStage32 = kBM * 128;                 // [128 rows][32 fp32]
 constexpr uint32_t kStage16 = kBM * 64;                  // [128 rows][32 fp16]
 constexpr size_t kMaxDynSmem = 227 * 1024 - 1024;
@@ -59,12 +59,15 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
+// Arrivals on a barrier given by its shared::cluster address (own CTA or the pair leader).  Default semantics (release at
+// CTA scope), as CUTLASS' ClusterBarrier does: an explicit .release.cluster compiles to MEMBAR.ALL.GPU + ERRBAR, ~500
+// clocks per pipeline step (measured with ncu: the weight producer spent its time there, profiles/r02_h16_membar.txt).
+// What these arrivals order is tensor-core / TMA traffic, which tcgen05.fence / the mbarrier's complete_tx already cover.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes)
-               : "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
 }
 
 template <bool kPair>
@@ -185,11 +188,13 @@ conv_h16_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, co
   const uint32_t w_stage_bytes = w_rows * 128u;
   uint8_t* sA = smem;
   uint8_t* sW = sA + (uint32_t)L.a_stages * a_stage_bytes;
+  // epilogue ring: E stages of an optional fp32 part (residual in / raw value out) and an optional fp16 part
+  const int E = L.epi_stages;
   uint8_t* sE32 = sW + (((uint32_t)L.w_stages * w_stage_bytes + 1023u) & ~1023u);
-  uint8_t* sE16 = sE32 + kEpi * kStage32;
+  uint8_t* sE16 = sE32 + ((p.R || p.D) ? (uint32_t)E * kStage32 : 0u);
 
   __shared__ uint64_t a_full[kMaxA], a_empty[kMaxA], w_full[kMaxW], w_empty[kMaxW];
-  __shared__ uint64_t acc_full[2], acc_empty[2], r_full[kEpi], e_free[kEpi];
+  __shared__ uint64_t acc_full[2], acc_empty[2], r_full[kMaxEpi], e_free[kMaxEpi];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -200,7 +205,7 @@ conv_h16_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, co
     for (int i = 0; i < kMaxA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < kMaxW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps * kCtas); }
-    for (int i = 0; i < kEpi; ++i) { mbar_init(&r_full[i], 1); mbar_init(&e_free[i], 1); }
+    for (int i = 0; i < kMaxEpi; ++i) { mbar_init(&r_full[i], 1); mbar_init(&e_free[i], 1); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -230,7 +235,7 @@ conv_h16_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, co
   if (warp == 0) {
     // ===================================================================== weight producer
     if (elect_one()) {
-      int ws = 0;
+      int ws = 0, wcount = 0;
       uint32_t wph = 0;
       for (int tile = first; tile < total_tiles; tile += step) {
         int nt, b, mt;
@@ -244,8 +249,13 @@ conv_h16_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, co
             mbar_wait(&w_empty[ws], wph ^ 1u);
             const int t_idx = row0 + p.taps[j].tile_base + (kc - p.taps[j].kc_lo);
             const uint32_t bar = leader_bar(&w_full[ws]);
-            if (leader) mbar_expect_tx_cluster(bar, w_stage_bytes * kCtas);
-            tma_load2<kPair>(smem_u32(sW + (size_t)ws * w_stage_bytes), &tmapW, 0, t_idx * p.BN + (int)(rank * w_rows), bar);
+            if ((L.knock & 1) && wcount >= L.w_stages) {   // measurement only: no weight traffic after the ring filled once
+              if (leader) mbar_arrive_cluster(bar);
+            } else {
+              if (leader) mbar_expect_tx_cluster(bar, w_stage_bytes * kCtas);
+              tma_load2<kPair>(smem_u32(sW + (size_t)ws * w_stage_bytes), &tmapW, 0, t_idx * p.BN + (int)(rank * w_rows), bar);
+            }
+            ++wcount;
             if (++ws == L.w_stages) { ws = 0; wph ^= 1u; }
           }
         }
@@ -282,9 +292,13 @@ conv_h16_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, co
             }
             mbar_wait(&w_full[ws], wph);
             tc_fence_after();
+            if (L.knock & 8) {   // measurement only: one MMA per tile
+              if (!acc) mma_f16<kPair>(d_tmem, a_tap, w_desc, idesc, 0);
+            } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)   // K step = 16 halves = 32 B = +2 descriptor units
-              mma_f16<kPair>(d_tmem, a_tap + 2 * k, w_desc + 2 * k, idesc, acc | (uint32_t)k);
+              for (int k = 0; k < 4; ++k)   // K step = 16 halves = 32 B = +2 descriptor units
+                mma_f16<kPair>(d_tmem, a_tap + 2 * k, w_desc + 2 * k, idesc, acc | (uint32_t)k);
+            }
             commit<kPair>(&w_empty[ws]);
             acc = 1;
             w_desc += w_stage_u;
@@ -300,7 +314,7 @@ conv_h16_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, co
   } else if (warp == kLoaderWarp) {
     // ===================================================================== A loader (TMA, fp16 rows + halo)
     if (elect_one()) {
-      int as = 0;
+      int as = 0, acount = 0;
       uint32_t aph = 0;
       for (int tile = first; tile < total_tiles; tile += step) {
         int nt, b, mt;
@@ -309,15 +323,20 @@ conv_h16_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, co
         for (int kci = 0; kci < p.n_kc; ++kci) {
           mbar_wait(&a_empty[as], aph ^ 1u);
           const uint32_t bar = leader_bar(&a_full[as]);
-          if (leader) mbar_expect_tx_cluster(bar, a_stage_bytes * kCtas);
-          tma_load3<kPair>(smem_u32(sA + (size_t)as * a_stage_bytes), &tmapA, (p.kc_begin + kci) * 64, r_base, b, bar);
+          if ((L.knock & 4) && acount >= L.a_stages) {
+            if (leader) mbar_arrive_cluster(bar);
+          } else {
+            if (leader) mbar_expect_tx_cluster(bar, a_stage_bytes * kCtas);
+            tma_load3<kPair>(smem_u32(sA + (size_t)as * a_stage_bytes), &tmapA, (p.kc_begin + kci) * 64, r_base, b, bar);
+          }
+          ++acount;
           if (++as == L.a_stages) { as = 0; aph ^= 1u; }
         }
       }
     }
   } else if (warp == kResidualWarp) {
     // ===================================================================== residual loader (fp32 tiles of R)
-    if (p.R && elect_one()) {
+    if (p.R && !(L.knock & 16) && elect_one()) {
       const int groups = p.BN / 32;
       int es = 0;
       uint32_t eph = 0;
@@ -326,9 +345,13 @@ conv_h16_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, co
         decode(tile, &nt, &b, &mt);
         for (int g = 0; g < groups; ++g) {
           mbar_wait(&e_free[es], eph ^ 1u);
-          mbar_arrive_expect_tx(&r_full[es], kStage32);
-          tma_load3<false>(smem_u32(sE32 + (size_t)es * kStage32), &tmapR, nt * p.BN + g * 32, mt * kBM, b, smem_u32(&r_full[es]));
-          if (++es == kEpi) { es = 0; eph ^= 1u; }
+          if (L.knock & 64) {   // measurement only: no residual traffic
+            mbar_arrive(&r_full[es]);
+          } else {
+            mbar_arrive_expect_tx(&r_full[es], kStage32);
+            tma_load3<false>(smem_u32(sE32 + (size_t)es * kStage32), &tmapR, nt * p.BN + g * 32, mt * kBM, b, smem_u32(&r_full[es]));
+          }
+          if (++es == E) { es = 0; eph ^= 1u; }
         }
       }
     }
@@ -341,7 +364,8 @@ conv_h16_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, co
     const bool store_leader = warp == kFirstEpiWarp && lane == 0;
     const bool precise = p.precise_sin != 0;
     const uint32_t acc_empty_leader = leader_bar(&acc_empty[0]);
-    int es = 0, prev = -1, it = 0;
+    int es = 0, it = 0;
+    long long gcount = 0;   // groups stored so far
     uint32_t eph = 0;
     for (int tile = first; tile < total_tiles; tile += step, ++it) {
       int nt, b, mt;
@@ -350,6 +374,12 @@ conv_h16_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, co
       mbar_wait(&acc_full[buf], ((uint32_t)it >> 1) & 1u);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16);
+      if (L.knock & 16) {   // measurement only: no epilogue work at all
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc_empty_leader + (uint32_t)buf * 8u);
+        continue;
+      }
       for (int g = 0; g < groups; ++g) {
         float v[16];
         __syncwarp();
@@ -409,14 +439,17 @@ conv_h16_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, co
         fence_proxy_async_smem();
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
         if (store_leader) {
-          if (p.D) tma_store3(&tmapD32, st32, nt * p.BN + g * 32, mt * kBM, b);
-          if (p.D16) tma_store3(&tmapD16, st16, nt * p.BN + g * 32, mt * kBM, b);
+          if (p.D && !(L.knock & 32)) tma_store3(&tmapD32, st32, nt * p.BN + g * 32, mt * kBM, b);
+          if (p.D16 && !(L.knock & 32)) tma_store3(&tmapD16, st16, nt * p.BN + g * 32, mt * kBM, b);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the previous group's stores have left smem
-          if (prev >= 0) mbar_arrive(&e_free[prev]);
-          prev = es;
+          // every store group but the newest has finished reading smem: hand the PREVIOUS group's stage back right away, so
+          // the residual loader can prefetch E-1 groups ahead (freeing a stage only when the next group needs it would
+          // cut the prefetch distance to one group)
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          if (gcount > 0) mbar_arrive(&e_free[es == 0 ? E - 1 : es - 1]);
         }
-        if (++es == kEpi) { es = 0; eph ^= 1u; }
+        ++gcount;
+        if (++es == E) { es = 0; eph ^= 1u; }
       }
     }
     if (store_leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -465,19 +498,32 @@ int launch_conv_h16(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
   const int rows = ((kBM + p.span) + 7) / 8 * 8;
   const long a_stage = (long)rows * 128;
   const long w_stage = (long)(p.BN / (pair ? 2 : 1)) * 128;
-  const long budget = (long)kMaxDynSmem - 1024 - (long)kEpi * (kStage32 + kStage16);
+  const long e_stage = ((p.R || p.D) ? (long)kStage32 : 0) + (p.D16 ? (long)kStage16 : 0);
+  const long budget = (long)kMaxDynSmem - 2048;
+  // Shared-memory split.  Layers with little MMA work per output element (1x1 convs: one tap) are bound by their
+  // epilogue streams (fp32 residual in, fp32 + fp16 out), so the epilogue ring gets the depth (bytes in flight);
+  // multi-tap layers put the memory into A / weight stages and keep a short ring.
+  const bool light = p.n_taps == 1;
+  int E = light ? 4 : ((p.R || p.D) ? 3 : 2);
   int as = 2, ws = 2;
-  if (as * a_stage + ws * w_stage > budget) return -1;
+  while (E > 2 && as * a_stage + ws * w_stage + E * e_stage > budget) --E;
+  if (as * a_stage + ws * w_stage + E * e_stage > budget) return -1;
+  const int as_cap = light ? 3 : 4, ws_cap = light ? 3 : 4;
   for (;;) {
     bool grew = false;
-    if (ws < 4 && as * a_stage + (ws + 1) * w_stage <= budget) { ++ws; grew = true; }
-    if (as < 4 && (as + 1) * a_stage + ws * w_stage <= budget) { ++as; grew = true; }
+    if (ws < ws_cap && as * a_stage + (ws + 1) * w_stage + E * e_stage <= budget) { ++ws; grew = true; }
+    if (as < as_cap && (as + 1) * a_stage + ws * w_stage + E * e_stage <= budget) { ++as; grew = true; }
     if (!grew) break;
   }
-  while (ws < kMaxW && as * a_stage + (ws + 1) * w_stage <= budget) ++ws;
-  while (as < kMaxA && (as + 1) * a_stage + ws * w_stage <= budget) ++as;
-  L.a_stages = as; L.w_stages = ws; L.a_rows_alloc = rows; L.tma_epilogue = 1; L.knock = 0;
-  const size_t smem = 1024 + (size_t)as * a_stage + (((size_t)ws * w_stage + 1023) & ~(size_t)1023) + (size_t)kEpi * (kStage32 + kStage16);
+  if (light) {
+    while (E < kMaxEpi && as * a_stage + ws * w_stage + (E + 1) * e_stage <= budget) ++E;
+  }
+  while (ws < kMaxW && as * a_stage + (ws + 1) * w_stage + E * e_stage <= budget) ++ws;
+  while (as < kMaxA && (as + 1) * a_stage + ws * w_stage + E * e_stage <= budget) ++as;
+  while (E < kMaxEpi && as * a_stage + ws * w_stage + (E + 1) * e_stage <= budget) ++E;
+  static const int knock = getenv("NC_KNOCK") ? atoi(getenv("NC_KNOCK")) : 0;
+  L.a_stages = as; L.w_stages = ws; L.a_rows_alloc = rows; L.tma_epilogue = 1; L.knock = knock; L.epi_stages = E;
+  const size_t smem = 1024 + (size_t)as * a_stage + (((size_t)ws * w_stage + 1023) & ~(size_t)1023) + (size_t)E * e_stage;
 
   alignas(64) CUtensorMap tA, tW, tD32, tD16, tR;
   std::memset(&tD32, 0, sizeof tD32); std::memset(&tD16, 0, sizeof tD16); std::memset(&tR, 0, sizeof tR);

@@ -80,6 +80,8 @@ class ConvLayer {
   // "tcgen05 tf32 BN=256" / "tcgen05 3xtf32 BN=128" / "simt fp32"
   std::string executor() const {
     if (mode_ == PREC_FP32) return "simt fp32";
+    if (direct16_) return "tcgen05 f16 fp16-operands BN=" + std::to_string(bn16_);
+    if (short_chains_) return std::string("tcgen05 ") + precision_name(mode_) + " BN=" + std::to_string(bn_) + (short_chains_ == 1 ? " folded" : " lo-acc");
     return std::string("tcgen05 ") + precision_name(mode_) + " BN=" + std::to_string(bn_);
   }
 

@@ -417,6 +417,22 @@ void DacEngine::finalize_weights() {
     rvq_alloc_.push_back(p = upload(cb_sq)); rvq_.cb_sq = p;
     rvq_alloc_.push_back(p = upload(out_w)); rvq_.out_w = p;
     rvq_alloc_.push_back(p = upload(out_b)); rvq_.out_b = p;
+    {   // shared-memory images of the stages for the block kernel (codec_kernels.cu)
+      std::vector<float> blob;
+      int per_stage = 0;
+      for (int q = 0; q < nq; ++q) {
+        auto v = rvq_stage_blob(Dz, D, K, in_w.data() + (size_t)q * D * Dz, in_b.data() + (size_t)q * D, cb.data() + (size_t)q * K * D,
+                                cb_sq.data() + (size_t)q * K, out_w.data() + (size_t)q * Dz * D, out_b.data() + (size_t)q * Dz);
+        if (v.empty()) { blob.clear(); per_stage = 0; break; }
+        per_stage = (int)v.size();
+        blob.insert(blob.end(), v.begin(), v.end());
+      }
+      rvq_.blob = nullptr; rvq_.blob_floats = 0;
+      if (per_stage > 0 && per_stage % 4 == 0) {
+        rvq_alloc_.push_back(p = upload(blob));
+        rvq_.blob = p; rvq_.blob_floats = per_stage;
+      }
+    }
   }
   // ---- decoder (Modules/DAC/Decoder.cs:22-58)
   const int C = cfg_.decoder_dim;

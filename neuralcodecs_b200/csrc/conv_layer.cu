@@ -345,9 +345,9 @@ void ConvLayer::build(const std::string& name, const ConvSpec& spec, const std::
     if (s.transposed) ok = ok && s.k - 2 * s.padding + s.output_padding == s.stride;
     for (auto& t : taps_) ok = ok && t.koff % 64 == 0 && t.klen % 64 == 0;
     int bn = 0;
-    for (int c = 256; c >= 32; c -= 32)
+    for (int c = 256; c >= 64; c -= 64)    // epilogue stages are 64 columns wide
       if (n_logical_ % c == 0) { bn = c; break; }
-    ok = ok && bn > 0 && n_logical_ / bn <= kMaxNTiles;
+    ok = ok && bn > 0 && n_logical_ / bn <= kMaxNTiles && s.cout % 32 == 0;
     if (ok) {
       bn16_ = bn;
       n_tiles16_ = n_logical_ / bn;

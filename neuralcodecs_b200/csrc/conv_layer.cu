@@ -137,7 +137,7 @@ double ConvLayer::flops(int batch, int t_in) const {
 void ConvLayer::build(const std::string& name, const ConvSpec& spec, const std::vector<float>& w,
                       const std::vector<float>& bias, Precision requested, int short_chains, bool direct16) {
   name_ = name;
-  short_chains_ = (requested == PREC_BF16X3 || requested == PREC_F16X3) ? short_chains : 0;
+  short_chains_ = (requested == PREC_BF16X3 || requested == PREC_F16X3 || requested == PREC_3XTF32) ? short_chains : 0;
   spec_ = spec;
   const ConvSpec& s = spec_;
   if ((size_t)s.cin * s.cout * s.k != w.size())
@@ -311,8 +311,9 @@ void ConvLayer::build(const std::string& name, const ConvSpec& spec, const std::
     // dense plan: every tap reads every K chunk, contributes to every N tile, and shifts are equally spaced
     {   // main-chain length per partial: 2 hi*hi MMAs per tap and K chunk; ~96 MMAs (32 main-chain steps) keep the truncation error of one
         // chain near 2e-6 relative (DESIGN.md "accumulation chains")
-      static const int steps = getenv("NC_FOLD_STEPS") ? std::max(2, atoi(getenv("NC_FOLD_STEPS"))) : 96;
-      fold_kc_ = std::max(1, steps / (2 * (int)taps_.size()));
+      static const int steps = getenv("NC_FOLD_STEPS") ? std::max(6, atoi(getenv("NC_FOLD_STEPS"))) : 96;   // MMAs (all three products) per partial
+      // main-chain MMAs per tap and 32-channel chunk: 2 (K = 16 halves) or 4 (K = 8 tf32)
+      fold_kc_ = std::max(1, steps / ((requested == PREC_3XTF32 ? 12 : 6) * (int)taps_.size()));
     }
     dense_step_ = taps_.size() == 1 ? 0 : taps_[1].shift - taps_[0].shift;
     for (size_t j = 0; j < taps_.size(); ++j) {

@@ -208,7 +208,7 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
   // short accumulation chains (conv_plan.h: acc_split): TMEM columns [0,BN) / [BN,2BN) = main partials,
   // [2BN,3BN) = lo-term accumulator, [3BN,4BN) = running sum of the folded partials
   // acc_split = 2 (N tile up to 256): main at [0,BN), lo at [256,256+BN), one tile in flight, no folding.
-  const bool s3 = OPS == O_H16X3 && p.acc_split != 0;
+  const bool s3 = (OPS == O_H16X3 || OPS == O_TF32X3) && p.acc_split != 0;
   const bool s3_wide = s3 && p.acc_split == 2;
   const int fold_kc = (s3 && !s3_wide && p.fold_kc > 0) ? p.fold_kc : p.n_kc;
   const uint32_t acc_stride = (s3 && !s3_wide) ? (uint32_t)p.BN : 256u;
@@ -335,11 +335,21 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
                 umma_tf32(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, acc | (uint32_t)k);
             } else if (OPS == O_TF32X3) {
               const uint64_t a1 = a0 + a_lo_u, b1 = b0 + w_lo_u;
+              if (s3) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                umma_tf32(d_tmem, a1 + 2 * k, b0 + 2 * k, idesc, acc | (uint32_t)k);  // lo * hi
-                umma_tf32(d_tmem, a0 + 2 * k, b1 + 2 * k, idesc, 1);                  // hi * lo
-                umma_tf32(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, 1);                  // hi * hi
+                for (int k = 0; k < 4; ++k) {
+                  umma_tf32(lo_tmem, a1 + 2 * k, b0 + 2 * k, idesc, acc_lo | (uint32_t)k);  // lo * hi -> lo accumulator
+                  umma_tf32(lo_tmem, a0 + 2 * k, b1 + 2 * k, idesc, 1);                     // hi * lo -> lo accumulator
+                  umma_tf32(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, acc | (uint32_t)k);      // hi * hi -> main partial
+                }
+                acc_lo = 1;
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  umma_tf32(d_tmem, a1 + 2 * k, b0 + 2 * k, idesc, acc | (uint32_t)k);  // lo * hi
+                  umma_tf32(d_tmem, a0 + 2 * k, b1 + 2 * k, idesc, 1);                  // hi * lo
+                  umma_tf32(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, 1);                  // hi * hi
+                }
               }
             } else {
               // row = [32 hi halves (64 B) | 32 lo halves (64 B)]; K step = 16 halves = 32 B
@@ -851,8 +861,10 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
         if (lane == 0) mbar_arrive(&acc1_empty[b]);
       }
       const int n0 = g * 32 + half * 16;
-      epi_bias(p, v, n0);
-      epi_post(p, v, n0);
+      if (!(L.knock & 64)) {
+        epi_bias(p, v, n0);
+        epi_post(p, v, n0);
+      }
       // 16 channels -> bf16/f16 hi (32 B) and lo (32 B) halves of this row of the K-chunk operand tile
       uint32_t hi[8], lo[8];
 #pragma unroll
@@ -927,7 +939,9 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       uint32_t wph = 0, aph = 0, hph = 0;
       uint64_t a_desc = a_desc0, w_desc = w_desc0, h_desc = h_desc0;
       auto mma6 = [&](uint32_t d_tmem, uint64_t a0, uint64_t b0, uint32_t acc, int passes, uint32_t idesc) {
-        if (passes == 3) {
+        if (L.knock & 8) {   // measurement only: one MMA per accumulator
+          if (!acc) umma_f16(d_tmem, a0, b0, idesc, 0);
+        } else if (passes == 3) {
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
             umma_f16(d_tmem, a0 + 4 + 2 * k, b0 + 2 * k, idesc, acc | (uint32_t)k);  // lo * hi
@@ -1102,6 +1116,13 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
         const float4 ia = __ldg(reinterpret_cast<const float4*>(p.inv_alpha + ai));
         uint8_t* stage = sA + (size_t)as * a_stage_bytes;
         mbar_wait(&raw_full[as], aph);
+        if (L.knock & 2) {   // measurement only: operands left as they arrived
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_full[as]);
+          if (++as == L.a_stages) { as = 0; aph ^= 1u; }
+          continue;
+        }
         float4 cur[RIT];
 #pragma unroll
         for (int i = 0; i < RIT; ++i) {
@@ -1244,8 +1265,8 @@ int launch_conv_umma(const ConvGemmParams& p_in, int num_sms, cudaStream_t strea
   const size_t smem = umma_smem_bytes(p_in, &L);
   if (smem == 0 || !umma_view_ok(p_in)) return -1;
   ConvGemmParams p = p_in;
-  if (p.acc_split && (!L.tma_epilogue || p.BN > (p.acc_split == 2 ? 256 : 128) || (p.mode != MODE_BF16X3 && p.mode != MODE_F16X3) ||
-                      p.passes != 3 || p.dw_w)) {
+  if (p.acc_split && (!L.tma_epilogue || p.BN > (p.acc_split == 2 ? 256 : 128) ||
+                      (p.mode != MODE_BF16X3 && p.mode != MODE_F16X3 && p.mode != MODE_TF32X3) || p.passes != 3 || p.dw_w)) {
     p.acc_split = 0;   // ragged outputs / other operand modes: one accumulator per tile
     p.fold_kc = 0;
   }
@@ -1338,7 +1359,8 @@ int launch_ru_fused(const ConvGemmParams& p, const ConvGemmParams& p2, int num_s
     if (!grew) break;
   }
   while (ws < kMaxWStages && as * a_stage + (ws + 1) * w_stage <= budget) ++ws;
-  L.a_stages = as; L.w_stages = ws; L.a_rows_alloc = rows; L.tma_epilogue = 1; L.knock = 0;
+  static const int knock_ru = getenv("NC_KNOCK_RU") ? atoi(getenv("NC_KNOCK_RU")) : 0;
+  L.a_stages = as; L.w_stages = ws; L.a_rows_alloc = rows; L.tma_epilogue = 1; L.knock = knock_ru; L.epi_stages = 0;
   const size_t smem = 1024 + (size_t)as * a_stage + (size_t)ws * w_stage + (size_t)(kHStages + kEpiStages) * kEpiStageBytes;
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return (int)cudaErrorNotSupported;

@@ -49,7 +49,11 @@ EncodecEngine::~EncodecEngine() {
 }
 
 void EncodecEngine::set_option(const std::string& key, const std::string& value) {
-  if (key == "precision" || key == "encoder_precision" || key == "decoder_precision") {
+  if (key == "encoder_short_chains") {
+    // tensor-core encoder modes only: keep the accumulation chains short (conv_plan.h acc_split); 0 off, 1 folded partials
+    enc_short_chains_ = std::atoi(value.c_str());
+    if (ready_) throw Error(NC_INVALID_ARGUMENT, "precision options must be set before weights are loaded");
+  } else if (key == "precision" || key == "encoder_precision" || key == "decoder_precision") {
     if (key != "decoder_precision") enc_prec_ = parse_precision(value);
     if (key != "encoder_precision") dec_prec_ = parse_precision(value);
     if (ready_) throw Error(NC_INVALID_ARGUMENT, "precision options must be set before weights are loaded");
@@ -132,15 +136,16 @@ void EncodecEngine::build_res(Res& r, const std::string& p, int dim) {
   ConvSpec s1;  // shortcut: SConv1d(dim, dim, 1)
   s1.cin = s1.cout = dim; s1.k = 1;
   auto ws = folded(p + ".shortcut", dim, dim, 1, &b, dim);
-  r.shortcut.build(p + ".shortcut", s1, ws, b, prec_);
+  const int sc = p.compare(0, 8, "encoder.") == 0 ? enc_short_chains_ : 0;
+  r.shortcut.build(p + ".shortcut", s1, ws, b, prec_, sc);
   ConvSpec s3;  // block.1: SConv1d(dim, dim/2, 3): valid conv over the left-padded input
   s3.cin = dim; s3.cout = hp; s3.k = 3;
   auto w3 = folded(p + ".block.1", hid, dim, 3, &b, hid);
-  r.c3.build(p + ".block.1", s3, pad3e(w3, hid, dim, 3, hp, dim), pad1e(b, hid, hp), prec_);
+  r.c3.build(p + ".block.1", s3, pad3e(w3, hid, dim, 3, hp, dim), pad1e(b, hid, hp), prec_, sc);
   ConvSpec s2;  // block.3: SConv1d(dim/2, dim, 1)
   s2.cin = hp; s2.cout = dim; s2.k = 1;
   auto w1 = folded(p + ".block.3", dim, hid, 1, &b, dim);
-  r.c1.build(p + ".block.3", s2, pad3e(w1, dim, hid, 1, dim, hp), b, prec_);
+  r.c1.build(p + ".block.3", s2, pad3e(w1, dim, hid, 1, dim, hp), b, prec_, sc);
 }
 
 void EncodecEngine::build_lstm(Lstm& l, const std::string& p, int dim) {
@@ -159,7 +164,8 @@ void EncodecEngine::build_lstm(Lstm& l, const std::string& p, int dim) {
     for (int j = 0; j < 4 * dim; ++j) bsum[j] = bih.f32[j] + bhh.f32[j];
     ConvSpec s;   // hoisted input projection: one GEMM over all time steps
     s.cin = dim; s.cout = 4 * dim; s.k = 1;
-    l.ih[i].build(p + ".lstm.weight_ih" + sfx, s, wih.f32, bsum, prec_ == PREC_FP32 ? PREC_FP32 : PREC_3XTF32);
+    l.ih[i].build(p + ".lstm.weight_ih" + sfx, s, wih.f32, bsum, prec_ == PREC_FP32 ? PREC_FP32 : PREC_3XTF32,
+                  p.compare(0, 8, "encoder.") == 0 ? enc_short_chains_ : 0);
     cudaFree(l.whh[i]);
     l.whh[i] = upload(whh.f32);
   }
@@ -190,7 +196,7 @@ void EncodecEngine::finalize_weights() {
     cs.cin = dim; cs.cout = 2 * dim; cs.k = 2 * r; cs.stride = r;   // valid conv over the padded input
     const std::string p = "encoder.layers." + std::to_string(idx);
     auto w = folded(p, 2 * dim, dim, 2 * r, &b, 2 * dim);
-    down->build(p, cs, w, b, enc_prec_);
+    down->build(p, cs, w, b, enc_prec_, enc_short_chains_);
     enc_down_.push_back(std::move(down));
     ++idx;
     mult *= 2;
@@ -203,7 +209,7 @@ void EncodecEngine::finalize_weights() {
     cs.cin = dim_top; cs.cout = cfg_.dimension; cs.k = 7;
     const std::string p = "encoder.layers." + std::to_string(idx);
     auto w = folded(p, cfg_.dimension, dim_top, 7, &b, cfg_.dimension);
-    enc_out_.build(p, cs, w, b, enc_prec_);
+    enc_out_.build(p, cs, w, b, enc_prec_, enc_short_chains_);
   }
   // ---- quantiser codebooks (EuclideanCodebook.cs:22-25)
   {
@@ -277,10 +283,47 @@ void EncodecEngine::finalize_weights() {
 }
 
 // ------------------------------------------------------------------------------------ shapes
+// SConv1d.forward's padding for a causal conv (SConv1d.cs:144-173): padding_total = k - s on the left, the stride
+// alignment extra on the right (computed with a float32 division, :245-250), and -- when the input is not longer than
+// the larger pad -- Pad1d's short-input branch: zero-extend on the right first (:258-272).  The zero extension is not
+// trimmed afterwards, so such a layer lengthens the sequence.
+EncodecEngine::SPad EncodecEngine::sconv_pad(int64_t T, int k, int s) {
+  const int pt = k - s;
+  const float n_frames = ((float)(T - k + pt)) / (float)s + 1.0f;
+  const int64_t ideal = ((int64_t)std::ceil(n_frames) - 1) * s + (k - pt);
+  SPad p;
+  p.left = pt;
+  p.right = (int)(ideal - T);
+  const int m = std::max(p.left, p.right);
+  p.extra_zero = T <= m ? (int)(m - T + 1) : 0;
+  p.t_out = (int)((T + p.extra_zero + p.left + p.right - k) / s + 1);
+  return p;
+}
+
 int64_t EncodecEngine::frames(int64_t L) const {
-  int64_t t = L;
-  for (int i = (int)cfg_.ratios.size() - 1; i >= 0; --i) t = (t + cfg_.ratios[i] - 1) / cfg_.ratios[i];  // SConv1d.cs:245-250
-  return t;
+  int64_t t = sconv_pad(L, 7, 1).t_out;                                    // SEANetEncoder: SConv1d(channels, n_filters, 7)
+  for (int i = (int)cfg_.ratios.size() - 1; i >= 0; --i) {
+    const int r = cfg_.ratios[i];
+    const SPad k3 = sconv_pad(t, 3, 1);                                    // resnet block: the k3 branch must keep the length
+    if (k3.t_out != t) throw Error(NC_INVALID_ARGUMENT, "Encodec: clip too short: a residual block's branches would differ in length (the reference's tensor add fails)");
+    t = sconv_pad(t, 2 * r, r).t_out;
+  }
+  return sconv_pad(t, 7, 1).t_out;                                         // final SConv1d(.., dimension, 7)
+}
+
+int64_t EncodecEngine::decoded_length(int64_t T) const { return (int64_t)sconv_pad(T, 7, 1).t_out * cfg_.hop(); }
+
+void EncodecEngine::conv_short(const ConvLayer& L, const Act& in, const SPad& pad, const Act& out, int B, int prologue, int post) {
+  const LaunchCtx c = ctx();
+  const int Tp = in.T + pad.extra_zero + pad.left + pad.right;
+  float* tmp = static_cast<float*>(pad_tmp_.reserve((size_t)B * Tp * in.C * sizeof(float)));
+  launch_pad1d_dense(in.base, in.stride, in.T, in.C, pad.extra_zero, pad.left, pad.right, tmp, B, c);
+  ConvRunArgs a;
+  a.in = tmp; a.in_clip_stride = (long long)Tp * in.C; a.t_in = Tp;
+  a.out = out.base; a.out_clip_stride = out.stride; a.batch = B;
+  a.prologue = prologue;    // ELU(0) = 0 and ELU commutes with reflection: applying it inside the conv is Pad1d(ELU(x))
+  a.post = post;
+  L.run(a, c);
 }
 
 int EncodecEngine::n_q_for_bandwidth(float kbps) const {
@@ -293,7 +336,7 @@ int EncodecEngine::n_q_for_bandwidth(float kbps) const {
 
 int EncodecEngine::micro_batch(int B, int64_t L) {
   const int64_t T = frames(L);
-  const int64_t Lfull = std::max<int64_t>(L, T * cfg_.hop());
+  const int64_t Lfull = std::max<int64_t>(L, decoded_length(T)) + 16;
   const int64_t per_buf = (Lfull + 2 * kMargin + 8) * cfg_.n_filters * 2;   // widest layers: L x 32 and L/2 x 64
   const int top = cfg_.n_filters << cfg_.ratios.size();
   double per_clip = 5.0 * per_buf * 4 + (double)T * (4.0 * top + cfg_.dimension) * 4 + (double)Lfull * 4;
@@ -306,7 +349,7 @@ int EncodecEngine::micro_batch(int B, int64_t L) {
   z_.reserve((size_t)mb * T * cfg_.dimension * sizeof(float));
   hbuf_.reserve((size_t)2 * ((mb + 15) / 16 * 16) * top * sizeof(float));
   barriers_.reserve(64 * sizeof(unsigned int));
-  audio_tmp_.reserve((size_t)mb * T * cfg_.hop() * sizeof(float));
+  audio_tmp_.reserve((size_t)mb * decoded_length(T) * sizeof(float));
   return mb;
 }
 
@@ -382,18 +425,30 @@ void EncodecEngine::run_encoder(const float* audio, int B, int64_t L, int64_t* T
   const LaunchCtx c = ctx();
   const int nf = cfg_.n_filters;
   int xb = 0, sb = -1, hb = -1;
-  Act x = act(xb, B, (int)L, nf);
-  // SConv1d(1, 32, 7) causal: left reflect pad 6 handled by index reflection inside the Cin = 1 kernel
-  launch_conv_cin1(audio, L, (int)L, x.base, (int)L, nf, d_conv_in_w_, d_conv_in_b_, 7, 1, 6, B, c, /*reflect=*/1, x.stride);
+  const SPad p_in = sconv_pad(L, 7, 1);
+  Act x = act(xb, B, p_in.t_out, nf);
+  if (p_in.extra_zero == 0) {
+    // SConv1d(1, 32, 7) causal: left reflect pad 6 handled by index reflection inside the Cin = 1 kernel
+    launch_conv_cin1(audio, L, (int)L, x.base, (int)L, nf, d_conv_in_w_, d_conv_in_b_, 7, 1, 6, B, c, /*reflect=*/1, x.stride);
+  } else {
+    // short-input branch of Pad1d (L <= 6): zero-extend, reflect, then a valid convolution over the padded samples
+    const int Tp = (int)L + p_in.extra_zero + p_in.left + p_in.right;
+    float* tmp = static_cast<float*>(pad_tmp_.reserve((size_t)B * Tp * sizeof(float)));
+    launch_pad1d_dense(audio, L, (int)L, 1, p_in.extra_zero, p_in.left, p_in.right, tmp, B, c);
+    launch_conv_cin1(tmp, Tp, Tp, x.base, p_in.t_out, nf, d_conv_in_w_, d_conv_in_b_, 7, 1, 0, B, c, /*reflect=*/0, x.stride);
+  }
   for (size_t i = 0; i < enc_res_.size(); ++i) {
     const int r = cfg_.ratios[cfg_.ratios.size() - 1 - i];
     Act y = run_res(*enc_res_[i], x, B, xb, sb, hb, /*post_elu=*/true);
-    const int t_out = (y.T + r - 1) / r;
-    const int extra = t_out * r - y.T;                                   // SConv1d.cs:245-250
-    launch_reflect_pad(y.base, y.T, y.C, y.stride, r, extra, B, c);      // padding_total = k - stride = r (left), extra (right)
+    const SPad pd = sconv_pad(y.T, 2 * r, r);                            // padding_total = k - stride = r (left), extra (right)
     const int ob = pick_free(xb, -1);
-    Act o = act(ob, B, t_out, 2 * y.C);
-    conv(*enc_down_[i], y, r, extra, o, B, PRO_NONE, PRO_NONE, nullptr);
+    Act o = act(ob, B, pd.t_out, 2 * y.C);
+    if (pd.extra_zero == 0) {
+      launch_reflect_pad(y.base, y.T, y.C, y.stride, pd.left, pd.right, B, c);
+      conv(*enc_down_[i], y, pd.left, pd.right, o, B, PRO_NONE, PRO_NONE, nullptr);
+    } else {
+      conv_short(*enc_down_[i], y, pd, o, B, PRO_NONE, PRO_NONE);        // y.T <= r: Pad1d's short-input branch
+    }
     x = o;
     xb = ob;
   }
@@ -405,13 +460,20 @@ void EncodecEngine::run_encoder(const float* audio, int B, int64_t L, int64_t* T
     xb = ob;
     prologue = PRO_NONE;
   }
-  launch_reflect_pad(top.base, top.T, top.C, top.stride, 6, 0, B, c);
-  ConvRunArgs a;
-  a.in = top.base - (long long)6 * top.C; a.in_clip_stride = top.stride; a.t_in = top.T + 6; a.batch = B;
-  a.out = z_.as<float>(); a.out_clip_stride = (long long)top.T * cfg_.dimension;
-  a.prologue = prologue;
-  enc_out_.run(a, c);
-  *T_out = top.T;
+  const SPad pf = sconv_pad(top.T, 7, 1);
+  if (pf.extra_zero == 0) {
+    launch_reflect_pad(top.base, top.T, top.C, top.stride, 6, 0, B, c);
+    ConvRunArgs a;
+    a.in = top.base - (long long)6 * top.C; a.in_clip_stride = top.stride; a.t_in = top.T + 6; a.batch = B;
+    a.out = z_.as<float>(); a.out_clip_stride = (long long)top.T * cfg_.dimension;
+    a.prologue = prologue;
+    enc_out_.run(a, c);
+  } else {                                                               // fewer than 7 frames: the final conv lengthens z
+    Act zo;
+    zo.base = z_.as<float>(); zo.T = pf.t_out; zo.C = cfg_.dimension; zo.stride = (long long)pf.t_out * cfg_.dimension;
+    conv_short(enc_out_, top, pf, zo, B, prologue, PRO_NONE);
+  }
+  *T_out = pf.t_out;
 }
 
 void EncodecEngine::run_decoder(int B, int T, float* audio_out, long long out_stride) {
@@ -419,12 +481,17 @@ void EncodecEngine::run_decoder(int B, int T, float* audio_out, long long out_st
   // zq activation was written into buffer 0 by the caller (with margins)
   int xb = 0, sb = -1, hb = -1;
   Act z = act(0, B, T, cfg_.dimension);
-  launch_reflect_pad(z.base, z.T, z.C, z.stride, 6, 0, B, c);
+  const SPad pz = sconv_pad(T, 7, 1);
   const int top = cfg_.n_filters << cfg_.ratios.size();
   int ob = 1;
-  Act x = act(ob, B, T, top);
+  Act x = act(ob, B, pz.t_out, top);
   const bool has_lstm = cfg_.lstm_layers > 0;
-  conv(dec_in_, z, 6, 0, x, B, PRO_NONE, has_lstm ? PRO_NONE : PRO_ELU, nullptr);
+  if (pz.extra_zero == 0) {
+    launch_reflect_pad(z.base, z.T, z.C, z.stride, 6, 0, B, c);
+    conv(dec_in_, z, 6, 0, x, B, PRO_NONE, has_lstm ? PRO_NONE : PRO_ELU, nullptr);
+  } else {
+    conv_short(dec_in_, z, pz, x, B, PRO_NONE, has_lstm ? PRO_NONE : PRO_ELU);   // T <= 6 frames: short-input branch
+  }
   xb = ob;
   if (has_lstm) {
     const int lb = pick_free(xb, 4);
@@ -470,8 +537,9 @@ void EncodecEngine::forward_dev(const float* audio, int B, int64_t L, int nq, fl
     if (audio_out) {
       Act z = act(0, nb, (int)T, cfg_.dimension);
       launch_encodec_decode_codes(cdst, d_embed_ptrs_, z.base, z.stride, nb, (int)T, nq, cfg_.codebook_size, cfg_.dimension, c);
-      run_decoder(nb, (int)T, audio_tmp_.as<float>(), T * cfg_.hop());
-      launch_trim_rows(audio_tmp_.as<float>(), audio_out + (int64_t)b0 * L, nb, T * cfg_.hop(), std::min<int64_t>(L, T * cfg_.hop()), c);
+      const int64_t Ld = decoded_length(T);
+      run_decoder(nb, (int)T, audio_tmp_.as<float>(), Ld);
+      launch_trim_rows(audio_tmp_.as<float>(), audio_out + (int64_t)b0 * L, nb, Ld, std::min<int64_t>(L, Ld), c);
     }
   }
   sync();
@@ -482,7 +550,7 @@ void EncodecEngine::decode_dev(const int64_t* codes, int B, int nq, int64_t T, f
   bind();
   if (B <= 0 || T <= 0 || !codes) throw Error(NC_INVALID_ARGUMENT, "Invalid frame codes in Encodec Decode");
   if (nq <= 0 || nq > (int)embed_.size()) throw Error(NC_INVALID_ARGUMENT, "n_quantizers out of range");
-  const int64_t L = T * cfg_.hop();
+  const int64_t L = decoded_length(T);
   const int mb = micro_batch(B, L);
   const LaunchCtx c = ctx();
   for (int b0 = 0; b0 < B; b0 += mb) {
@@ -536,7 +604,7 @@ void EncodecEngine::decompress_dev(const uint8_t* payload, int64_t stride, int B
   const int64_t frame_rate = (cfg_.sample_rate + cfg_.hop() - 1) / cfg_.hop();
   const int64_t T = (L * frame_rate + cfg_.sample_rate - 1) / cfg_.sample_rate;
   if (stride < ecdc_payload_bytes(nq, T)) throw Error(NC_INVALID_ARGUMENT, "Stream ended too soon");   // EncodecCompressor.cs:390-393
-  const int64_t Ld = T * cfg_.hop();
+  const int64_t Ld = decoded_length(T);
   const int mb = micro_batch(B, Ld);
   const LaunchCtx c = ctx();
   codes_tmp_.reserve((size_t)B * nq * T * sizeof(int64_t));

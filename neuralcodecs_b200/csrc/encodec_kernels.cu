@@ -5,6 +5,7 @@
 // ResidualVectorQuantizer.cs:107-157, SLSTM.cs:40-57.
 #include "encodec_kernels.h"
 
+#include <algorithm>
 #include <cfloat>
 #include <cooperative_groups.h>
 
@@ -40,6 +41,32 @@ void launch_reflect_pad(float* x, int T, int C, long long clip_stride, int left,
   reflect_pad_kernel<<<blocks, 256, 0, ctx.stream>>>(x, T, C, clip_stride, left, right, batch);
   check_launch((int)cudaGetLastError(), "reflect_pad");
   ctx.end(ev, "reflect_pad", 0, 32.0 * total);
+}
+
+__global__ void pad1d_dense_kernel(const float* __restrict__ in, long long in_clip_stride, int T, int C, int extra_zero, int left,
+                                   int Tp, float* __restrict__ out, long long total) {
+  const int Te = T + extra_zero;   // length after the zero extension
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long r = i / C;
+    const int t = (int)(r % Tp), b = (int)(r / Tp);
+    int j = t - left;
+    if (j < 0) j = -j;                       // F.pad(mode = "reflect") on the extended signal
+    if (j >= Te) j = 2 * (Te - 1) - j;
+    out[i] = (j >= 0 && j < T) ? in[(long long)b * in_clip_stride + (long long)j * C + c] : 0.f;
+  }
+}
+void launch_pad1d_dense(const float* in, long long in_clip_stride, int T, int C, int extra_zero, int left, int right, float* out,
+                        int batch, const LaunchCtx& ctx) {
+  const int Tp = T + extra_zero + left + right;
+  const long long total = (long long)batch * Tp * C;
+  if (total == 0) return;
+  if (left >= T + extra_zero || right >= T + extra_zero) throw Error(NC_INTERNAL, "pad1d: reflect padding longer than the extended input");
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 4096);
+  const int ev = ctx.begin();
+  pad1d_dense_kernel<<<blocks, 256, 0, ctx.stream>>>(in, in_clip_stride, T, C, extra_zero, left, Tp, out, total);
+  check_launch((int)cudaGetLastError(), "pad1d_dense");
+  ctx.end(ev, "pad1d_dense", 0, 8.0 * total);
 }
 
 // ------------------------------------------------------------------------------ VQ stage (D = 128)

@@ -10,6 +10,12 @@ namespace nc {
 // `clip_stride` floats apart; rows [-left, 0) and [T, T+right) are written.  (SConv1d.cs:252-274)
 void launch_reflect_pad(float* x, int T, int C, long long clip_stride, int left, int right, int batch, const LaunchCtx& ctx);
 
+// Pad1d of a SHORT input (SConv1d.cs:258-272: length <= max(left, right)): zero-extend by `extra_zero` samples on the right,
+// then reflect-pad (left, right) around the extended signal.  in: rows [0, T) of each clip (clip_stride floats apart),
+// out: dense [batch][T + extra_zero + left + right][C].  Also serves the ordinary case (extra_zero = 0).
+void launch_pad1d_dense(const float* in, long long in_clip_stride, int T, int C, int extra_zero, int left, int right, float* out,
+                        int batch, const LaunchCtx& ctx);
+
 // One residual-VQ stage with a 128-d Euclidean codebook (EuclideanCodebook.cs:155-182,
 // ResidualVectorQuantizer.cs:146-154): codes[b, stage, t] = argmin_k (|x|^2 + |e_k|^2) + (-2 x.e_k); residual -= e.
 // residual: [frames][128] dense rows (frames = B*T); codes: [B][nq][T] int64.

@@ -313,8 +313,13 @@ class EncodecEngine : public Engine {
   std::string describe() const override;
   const EncodecConfig& config() const { return cfg_; }
 
-  int64_t frames(int64_t L) const;                     // encoder frames for L samples (causal ceil chain)
-  int64_t decoded_length(int64_t T) const { return T * cfg_.hop(); }
+  int64_t frames(int64_t L) const;                     // encoder frames for L samples (per-layer SConv1d length chain)
+  // samples Decode produces for T frames: T' * hop, T' = T except for T <= 6 where the first decoder conv takes the
+  // short-input branch of Pad1d and lengthens the sequence (SConv1d.cs:258-272)
+  int64_t decoded_length(int64_t T) const;
+  // padding one SConv1d applies to an input of T samples (kernel k, stride s, causal): SConv1d.cs:144-173,245-272
+  struct SPad { int extra_zero, left, right, t_out; };
+  static SPad sconv_pad(int64_t T, int k, int s);
   int n_q_for_bandwidth(float kbps) const;             // ResidualVectorQuantizer.cs:133-144
 
   // device pointers.  codes [B][nq][T] int64; audio_out [B][T*hop] for decode, [B][L] (trimmed) for forward.
@@ -357,6 +362,7 @@ class EncodecEngine : public Engine {
   // The encoder feeds the argmin: tensor-core accumulation noise (~1e-5 of the embedding) flips codes whose
   // margin is far above the 1e-6 near-tie gate at the later RVQ stages, so it runs in true fp32 by default.
   Precision enc_prec_ = PREC_FP32, dec_prec_ = PREC_BF16X3;
+  int enc_short_chains_ = 1;   // option encoder_short_chains (tensor-core encoder modes only)
   float* d_conv_in_w_ = nullptr;
   float* d_conv_in_b_ = nullptr;
   std::vector<std::unique_ptr<Res>> enc_res_, dec_res_;
@@ -368,7 +374,9 @@ class EncodecEngine : public Engine {
   int conv_out_c_ = 0;
   std::vector<float*> embed_, embed_sq_;
   const float** d_embed_ptrs_ = nullptr;
-  DeviceBuffer ws_[5], xproj_, z_, hbuf_, barriers_, audio_tmp_, codes_tmp_;
+  DeviceBuffer ws_[5], xproj_, z_, hbuf_, barriers_, audio_tmp_, codes_tmp_, pad_tmp_;
+  // conv through the short-input branch: materialise Pad1d densely, then a plain valid convolution
+  void conv_short(const ConvLayer& L, const Act& in, const SPad& pad, const Act& out, int B, int prologue, int post);
 };
 
 }  // namespace nc

@@ -91,6 +91,24 @@ def test_encodec24k_preset_with_lstm(encodec_24k):
     m.Dispose()
 
 
+@pytest.mark.parametrize("length", [100, 319, 320, 321, 641, 1600, 1920, 1921, 2500])
+def test_short_clips_take_pad1d_short_input_branch(encodec_24k, length):
+    """Clips of fewer than 7 frames (<= 1920 samples): an SConv1d whose input is not longer than its reflect padding
+    zero-extends it first and does NOT trim afterwards (Modules/Encodec/SConv1d.cs:258-272), so the frame count grows
+    (e.g. 3 frames -> 7).  Shapes, codes and audio must follow the reference through that branch."""
+    o, m, x, ref, emb, codes, dec, dref = _run(encodec_24k, None, 2, length)
+    assert codes.shape == tuple(ref["codes"].shape) and dec.shape == dref.shape
+    if length <= 1920:
+        assert codes.shape[-1] >= 7 > -(-length // 320)                 # lengthened by the short-input branch
+    assert _bad_flips(o, emb, ref["codes"], codes) == 0
+    assert np.abs(dec - dref).max() <= MAX_ABS and snr_db(dref, dec) >= MIN_SNR_DB
+    y = m.forward(x)
+    assert y.shape == x.shape == tuple(ref["audio"].shape)
+    if np.array_equal(codes, ref["codes"].numpy()):
+        assert np.abs(y - ref["audio"].numpy()).max() <= MAX_ABS
+    m.Dispose()
+
+
 def test_errors(encodec_nolstm):
     import neuralcodecs_b200 as nc
     _, m = _models(encodec_nolstm, {"precision": "fp32"})

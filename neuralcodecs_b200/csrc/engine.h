@@ -359,9 +359,13 @@ class EncodecEngine : public Engine {
   int pick_free(int a, int b, int c = -1, int d = -1) const;
 
   EncodecConfig cfg_;
-  // The encoder feeds the argmin: tensor-core accumulation noise (~1e-5 of the embedding) flips codes whose
-  // margin is far above the 1e-6 near-tie gate at the later RVQ stages, so it runs in true fp32 by default.
-  Precision enc_prec_ = PREC_FP32, dec_prec_ = PREC_BF16X3;
+  // The encoder feeds the argmin, and Encodec's later RVQ stages quantise residuals 10-50x smaller than the embedding, so
+  // its error budget is ~10x tighter than DAC's.  Round 1 ran it in true fp32 (CUDA cores) because every tensor-core mode
+  // flipped codes with margins up to 5e-5; the cause was the tensor core's truncating accumulation over long chains, not
+  // the operands.  With short chains (conv_plan.h acc_split) 3xTF32 (22-bit operands at any magnitude) matches the fp32
+  // path: 4 near-tie flips in 6000 frames, max margin 2.5e-7 (fp32: 5, 2.6e-7; profiles/r02_encodec_chains.txt).
+  // bf16x3 (16-bit operands) still leaves one 3e-6 flip and stays opt-in.
+  Precision enc_prec_ = PREC_3XTF32, dec_prec_ = PREC_BF16X3;
   int enc_short_chains_ = 1;   // option encoder_short_chains (tensor-core encoder modes only)
   float* d_conv_in_w_ = nullptr;
   float* d_conv_in_b_ = nullptr;

@@ -43,10 +43,10 @@ std::vector<ZipEntry> zip_directory(const std::vector<uint8_t>& f) {
     // zip64: locator PK\6\7 sits 20 bytes before the EOCD and points at the zip64 EOCD record PK\6\6
     if (eocd < 20 || rd32(&f[eocd - 20]) != 0x07064b50u) bad("zip64 locator missing");
     const uint64_t z = rd64(&f[eocd - 20 + 8]);
-    if (z + 56 > n || rd32(&f[z]) != 0x06064b50u) bad("zip64 end-of-central-directory record missing");
+    if (z > n || n - z < 56 || rd32(&f[z]) != 0x06064b50u) bad("zip64 end-of-central-directory record missing");
     count = rd64(&f[z + 32]); cd_size = rd64(&f[z + 40]); cd_off = rd64(&f[z + 48]);
   }
-  if (cd_off + cd_size > n) bad("zip central directory out of range");
+  if (cd_off > n || cd_size > n - cd_off) bad("zip central directory out of range");   // written so crafted 64-bit values cannot wrap
   std::vector<ZipEntry> out;
   size_t p = (size_t)cd_off;
   for (uint64_t e = 0; e < count; ++e) {
@@ -70,10 +70,10 @@ std::vector<ZipEntry> zip_directory(const std::vector<uint8_t>& f) {
       x += 4 + (size_t)len;
     }
     if (method != 0 || csize != usize) bad("zip entry '" + z.name + "' is compressed; torch.save writes stored entries");
-    if (lho + 30 > n || rd32(&f[lho]) != 0x04034b50u) bad("zip local header corrupted");
+    if (lho > n || n - lho < 30 || rd32(&f[lho]) != 0x04034b50u) bad("zip local header corrupted");
     z.offset = lho + 30 + rd16(&f[lho + 26]) + rd16(&f[lho + 28]);
     z.size = usize;
-    if (z.offset + z.size > n) bad("zip entry '" + z.name + "' out of range");
+    if (z.offset > n || z.size > n - z.offset) bad("zip entry '" + z.name + "' out of range");
     out.push_back(std::move(z));
     p += 46 + (size_t)nlen + xlen + clen;
   }
@@ -225,6 +225,8 @@ class Unpickler {
   static P persistent(const P& pid) {
     if (pid->kind != PVal::TUPLE || pid->items.size() < 5 || pid->items[0]->kind != PVal::STR || pid->items[0]->s != "storage")
       bad("pickle: unknown persistent id");
+    if (pid->items[1]->kind != PVal::GLOBAL && pid->items[1]->kind != PVal::STR) bad("pickle: persistent id without a storage type");
+    if (pid->items[2]->kind != PVal::STR) bad("pickle: persistent id without a storage key");
     auto v = mk(PVal::STORAGE);
     v->dtype = storage_dtype(pid->items[1]->s);
     v->s = pid->items[2]->s;
@@ -248,6 +250,9 @@ class Unpickler {
       t->offset = args->items[1]->i;
       t->shape = ints(args->items[2]);
       t->stride = ints(args->items[3]);
+      if (t->stride.size() != t->shape.size()) bad("pickle: tensor record with mismatched shape / stride ranks");
+      for (int64_t d : t->shape)
+        if (d < 0 || d > ((int64_t)1 << 40)) bad("pickle: tensor record with a negative or absurd dimension");
       return t;
     }
     if (g == "torch._utils _rebuild_parameter" || g == "torch._utils _rebuild_parameter_with_state") {

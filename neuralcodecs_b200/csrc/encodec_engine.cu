@@ -62,6 +62,16 @@ void EncodecEngine::set_option(const std::string& key, const std::string& value)
   }
 }
 
+// Accumulation-chain policy of the encoder's tensor-core layers: a layer accumulates cin*k/32 K chunks of 12 (3xTF32) or 6
+// (16-bit splits) MMAs per output; chains of at most one fold interval (96 MMAs: the early, long-T layers) run the plain
+// kernel with its wide N tiles, longer ones fold (conv_plan.h acc_split = 1).
+int EncodecEngine::chain_mode(int cin, int k) const {
+  if (enc_short_chains_ <= 0) return 0;
+  if (enc_short_chains_ >= 2) return 1;
+  const int per_chunk = enc_prec_ == PREC_3XTF32 ? 12 : 6;
+  return (cin * k + 31) / 32 * per_chunk > 96 ? 1 : 0;
+}
+
 void EncodecEngine::require_ready() const {
   if (!ready_) throw Error(NC_BAD_WEIGHTS, "Encodec weights have not been loaded");
 }
@@ -136,16 +146,16 @@ void EncodecEngine::build_res(Res& r, const std::string& p, int dim) {
   ConvSpec s1;  // shortcut: SConv1d(dim, dim, 1)
   s1.cin = s1.cout = dim; s1.k = 1;
   auto ws = folded(p + ".shortcut", dim, dim, 1, &b, dim);
-  const int sc = p.compare(0, 8, "encoder.") == 0 ? enc_short_chains_ : 0;
-  r.shortcut.build(p + ".shortcut", s1, ws, b, prec_, sc);
+  const bool enc = p.compare(0, 8, "encoder.") == 0;
+  r.shortcut.build(p + ".shortcut", s1, ws, b, prec_, enc ? chain_mode(dim, 1) : 0);
   ConvSpec s3;  // block.1: SConv1d(dim, dim/2, 3): valid conv over the left-padded input
   s3.cin = dim; s3.cout = hp; s3.k = 3;
   auto w3 = folded(p + ".block.1", hid, dim, 3, &b, hid);
-  r.c3.build(p + ".block.1", s3, pad3e(w3, hid, dim, 3, hp, dim), pad1e(b, hid, hp), prec_, sc);
+  r.c3.build(p + ".block.1", s3, pad3e(w3, hid, dim, 3, hp, dim), pad1e(b, hid, hp), prec_, enc ? chain_mode(dim, 3) : 0);
   ConvSpec s2;  // block.3: SConv1d(dim/2, dim, 1)
   s2.cin = hp; s2.cout = dim; s2.k = 1;
   auto w1 = folded(p + ".block.3", dim, hid, 1, &b, dim);
-  r.c1.build(p + ".block.3", s2, pad3e(w1, dim, hid, 1, dim, hp), b, prec_, sc);
+  r.c1.build(p + ".block.3", s2, pad3e(w1, dim, hid, 1, dim, hp), b, prec_, enc ? chain_mode(hp, 1) : 0);
 }
 
 void EncodecEngine::build_lstm(Lstm& l, const std::string& p, int dim) {
@@ -165,7 +175,7 @@ void EncodecEngine::build_lstm(Lstm& l, const std::string& p, int dim) {
     ConvSpec s;   // hoisted input projection: one GEMM over all time steps
     s.cin = dim; s.cout = 4 * dim; s.k = 1;
     l.ih[i].build(p + ".lstm.weight_ih" + sfx, s, wih.f32, bsum, prec_ == PREC_FP32 ? PREC_FP32 : PREC_3XTF32,
-                  p.compare(0, 8, "encoder.") == 0 ? enc_short_chains_ : 0);
+                  p.compare(0, 8, "encoder.") == 0 ? chain_mode(dim, 1) : 0);
     cudaFree(l.whh[i]);
     l.whh[i] = upload(whh.f32);
   }
@@ -196,7 +206,7 @@ void EncodecEngine::finalize_weights() {
     cs.cin = dim; cs.cout = 2 * dim; cs.k = 2 * r; cs.stride = r;   // valid conv over the padded input
     const std::string p = "encoder.layers." + std::to_string(idx);
     auto w = folded(p, 2 * dim, dim, 2 * r, &b, 2 * dim);
-    down->build(p, cs, w, b, enc_prec_, enc_short_chains_);
+    down->build(p, cs, w, b, enc_prec_, chain_mode(dim, 2 * r));
     enc_down_.push_back(std::move(down));
     ++idx;
     mult *= 2;
@@ -209,7 +219,7 @@ void EncodecEngine::finalize_weights() {
     cs.cin = dim_top; cs.cout = cfg_.dimension; cs.k = 7;
     const std::string p = "encoder.layers." + std::to_string(idx);
     auto w = folded(p, cfg_.dimension, dim_top, 7, &b, cfg_.dimension);
-    enc_out_.build(p, cs, w, b, enc_prec_, enc_short_chains_);
+    enc_out_.build(p, cs, w, b, enc_prec_, chain_mode(dim_top, 7));
   }
   // ---- quantiser codebooks (EuclideanCodebook.cs:22-25)
   {
@@ -347,7 +357,7 @@ int EncodecEngine::micro_batch(int B, int64_t L) {
   for (auto& w : ws_) w.reserve((size_t)mb * per_buf * sizeof(float));
   xproj_.reserve((size_t)mb * T * 4 * top * sizeof(float));
   z_.reserve((size_t)mb * T * cfg_.dimension * sizeof(float));
-  hbuf_.reserve((size_t)2 * ((mb + 15) / 16 * 16) * top * sizeof(float));
+  hbuf_.reserve((size_t)2 * ((mb + 31) / 32 * 32) * top * sizeof(float));
   barriers_.reserve(64 * sizeof(unsigned int));
   audio_tmp_.reserve((size_t)mb * decoded_length(T) * sizeof(float));
   return mb;

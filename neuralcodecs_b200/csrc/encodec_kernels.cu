@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <cstdlib>
 #include <cooperative_groups.h>
 
 namespace nc {
@@ -353,6 +354,11 @@ lstm_layer_kernel(const float* __restrict__ xproj, long long xproj_clip_stride, 
     __syncthreads();
   }
 }
+
+// Tried in round 2 and dropped (profiles/r02_encodec_lstm_two_slices.txt): a CTA owning 8 units of TWO batch slices and alternating
+// between them, to hide one slice's exchange + barrier behind the other's FMAs.  Bit-identical results but 28.9 ms instead of
+// 20.3 ms per 64 x 10 s: the exchange latency (~4.6 us: device-scope fence, L2 atomic, polling) is four times one slice's FMA
+// phase, so two slices cannot cover it and every half step still waits for a barrier signalled one half step earlier.
 
 void launch_lstm_layer(const float* xproj, long long xproj_clip_stride, const float* w_hh, float* hbuf, float* out,
                        long long out_clip_stride, const float* skip, long long skip_clip_stride, int post_elu,

@@ -366,7 +366,8 @@ class EncodecEngine : public Engine {
   // path: 4 near-tie flips in 6000 frames, max margin 2.5e-7 (fp32: 5, 2.6e-7; profiles/r02_encodec_chains.txt).
   // bf16x3 (16-bit operands) still leaves one 3e-6 flip and stays opt-in.
   Precision enc_prec_ = PREC_3XTF32, dec_prec_ = PREC_BF16X3;
-  int enc_short_chains_ = 1;   // option encoder_short_chains (tensor-core encoder modes only)
+  int enc_short_chains_ = 1;   // option encoder_short_chains: 0 off, 1 layers whose chains exceed 96 MMAs, 2 every layer
+  int chain_mode(int cin, int k) const;
   float* d_conv_in_w_ = nullptr;
   float* d_conv_in_b_ = nullptr;
   std::vector<std::unique_ptr<Res>> enc_res_, dec_res_;

@@ -16,9 +16,9 @@ x = synth.synth_audio(B, int(S * 24000), 24000, first_clip=9)[:, None, :]
 xt = torch.from_numpy(x)
 t0 = time.time(); ref = o.forward(xt); emb = o.encode_latent(xt); print(f"oracle {time.time()-t0:.1f}s", flush=True)
 cr = ref["codes"]
-for tag, opts in (("fp32", {}), ("3xtf32 long chains", {"encoder_precision": "3xtf32", "encoder_short_chains": "0"}),
-                  ("3xtf32 short chains", {"encoder_precision": "3xtf32"}), ("f16x3 short chains", {"encoder_precision": "f16x3"}),
-                  ("bf16x3 short chains", {"encoder_precision": "bf16x3"})):
+for tag, opts in (("fp32", {"encoder_precision": "fp32"}), ("3xtf32 long chains", {"encoder_short_chains": "0"}),
+                  ("3xtf32 default policy", {}), ("3xtf32 fold every layer", {"encoder_short_chains": "2"}),
+                  ("f16x3 default policy", {"encoder_precision": "f16x3"}), ("bf16x3 default policy", {"encoder_precision": "bf16x3"})):
     m = nc.Encodec(ce, options=opts); m.LoadWeights(path)
     m.Encode(x[:1])
     t0 = time.time(); (codes, _), = m.Encode(x); dt = time.time() - t0

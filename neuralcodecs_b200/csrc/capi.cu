@@ -1,5 +1,6 @@
 // C ABI of libneuralcodecs_cuda.so (include/neuralcodecs_cuda.h).  No exception crosses the
 // boundary; the last error message is kept per thread.
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -377,11 +378,33 @@ nc_status nc_dac_forward(nc_handle h, const float* audio, int32_t batch, int64_t
     const auto& c = e->config();
     DevMem d_audio((size_t)batch * length * 4), d_out(audio_out ? (size_t)batch * Lout * 4 : 0),
         d_z(z ? (size_t)batch * c.latent_dim * T * 4 : 0), d_codes(codes ? (size_t)batch * nq * T * 8 : 0);
-    h2d(e, d_audio.p, audio, (size_t)batch * length * 4);
-    e->forward_dev(d_audio.as<float>(), batch, length, nq, d_out.as<float>(), d_codes.as<int64_t>(), d_z.as<float>());
-    if (audio_out) d2h(e, audio_out, d_out.p, (size_t)batch * Lout * 4);
-    if (z) d2h(e, z, d_z.p, (size_t)batch * c.latent_dim * T * 4);
-    if (codes) d2h(e, codes, d_codes.p, (size_t)batch * nq * T * 8);
+    // Chunks of one engine micro-batch: the H2D copy of chunk i+1 and the D2H copies of chunk i-1 run on the handle's copy
+    // stream while chunk i computes (they overlap when the caller's buffers are pinned; pageable memory degrades to staged
+    // synchronous copies, still correct).  forward_dev returns with the compute stream drained, so a chunk's outputs are
+    // complete when their D2H is queued; a chunk's input is waited for explicitly.
+    const int chunk = std::max(1, e->micro_batch(batch, e->padded_length(length)));
+    cudaStream_t cs = e->copy_stream();
+    cudaEvent_t ready = nullptr;
+    NC_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    struct EventGuard { cudaEvent_t ev; ~EventGuard() { cudaEventDestroy(ev); } } eg{ready};
+    auto in_bytes = [&](int n) { return (size_t)n * length * 4; };
+    NC_CUDA(cudaMemcpyAsync(d_audio.p, audio, in_bytes(std::min(chunk, (int)batch)), cudaMemcpyHostToDevice, cs));
+    for (int b0 = 0; b0 < batch; b0 += chunk) {
+      const int nb = std::min(chunk, (int)batch - b0);
+      NC_CUDA(cudaEventRecord(ready, cs));
+      NC_CUDA(cudaEventSynchronize(ready));               // this chunk's input (and everything queued before it) has landed
+      if (b0 + nb < batch) {                              // next chunk's input: flies during this chunk's kernels
+        const int nn = std::min(chunk, (int)batch - b0 - nb);
+        NC_CUDA(cudaMemcpyAsync(d_audio.as<float>() + (size_t)(b0 + nb) * length, audio + (size_t)(b0 + nb) * length, in_bytes(nn),
+                                cudaMemcpyHostToDevice, cs));
+      }
+      e->forward_dev(d_audio.as<float>() + (size_t)b0 * length, nb, length, nq, audio_out ? d_out.as<float>() + (size_t)b0 * Lout : nullptr,
+                     codes ? d_codes.as<int64_t>() + (size_t)b0 * nq * T : nullptr, z ? d_z.as<float>() + (size_t)b0 * c.latent_dim * T : nullptr);
+      if (audio_out) NC_CUDA(cudaMemcpyAsync(audio_out + (size_t)b0 * Lout, d_out.as<float>() + (size_t)b0 * Lout, (size_t)nb * Lout * 4, cudaMemcpyDeviceToHost, cs));
+      if (z) NC_CUDA(cudaMemcpyAsync(z + (size_t)b0 * c.latent_dim * T, d_z.as<float>() + (size_t)b0 * c.latent_dim * T, (size_t)nb * c.latent_dim * T * 4, cudaMemcpyDeviceToHost, cs));
+      if (codes) NC_CUDA(cudaMemcpyAsync(codes + (size_t)b0 * nq * T, d_codes.as<int64_t>() + (size_t)b0 * nq * T, (size_t)nb * nq * T * 8, cudaMemcpyDeviceToHost, cs));
+    }
+    NC_CUDA(cudaStreamSynchronize(cs));
     if (frames_out) *frames_out = T;
   });
 }

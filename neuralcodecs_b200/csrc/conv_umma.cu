@@ -624,7 +624,11 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
     // ===================================================================== A transformers
     const int ptid = tid - kFirstProducerWarp * 32;
     const int c = ptid & 7;      // 16-byte (4-float) chunk of the 128-byte input row
-    const int rho0 = ptid >> 3;  // 0..31
+    // rows of one warp: R, R+2, R+4, R+6.  The hi halves of a row occupy 16-byte chunks {0..3} ^ (row & 7), i.e. the low or
+    // the high 64 B of its 128-byte line depending on bit 2 of the row: four CONSECUTIVE rows put all their 8-byte hi
+    // (and lo) stores into the same 16 banks (4 wavefronts per store instead of 2; ncu counted 52 M bank conflicts per
+    // launch in round 1); rows two apart split them evenly.
+    const int rho0 = 8 * (ptid >> 6) + ((ptid >> 5) & 1) + 2 * ((ptid & 31) >> 3);  // 0..31, each once
     const int rows_needed = kBM + p.span;
     int as = 0;
     uint32_t aph = 0;
@@ -1105,7 +1109,7 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
     // ===================================================================== A transformers (as conv_umma_kernel, H16X3)
     const int ptid = tid - kFirstProducerWarp * 32;
     const int c = ptid & 7;
-    const int rho0 = ptid >> 3;
+    const int rho0 = 8 * (ptid >> 6) + ((ptid >> 5) & 1) + 2 * ((ptid & 31) >> 3);   // see conv_umma_kernel: bank-conflict-free hi / lo stores
     const int rows_needed = kBM + p.span;
     int as = 0;
     uint32_t aph = 0;

@@ -340,10 +340,13 @@ lstm_layer_kernel(const float* __restrict__ xproj, long long xproj_clip_stride, 
       if (post_elu) y = y > 0.f ? y : expm1f(y);
       out[(long long)b * out_clip_stride + (long long)t * H + u] = y;
     }
-    // barrier among the CTAs of this batch slice
-    __threadfence();
+    // barrier among the CTAs of this batch slice.  One device-scope fence by the signalling thread AFTER the CTA barrier
+    // (fences are cumulative over what the barrier ordered before them) instead of one MEMBAR.GPU per thread before it.
     __syncthreads();
-    if (tid == 0) atomicAdd(&barriers[blockIdx.y], 1u);
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(&barriers[blockIdx.y], 1u);
+    }
     prefetch(t + 1);
     if (tid == 0) {
       const unsigned int target = (unsigned int)n_unit_ctas * (unsigned int)(t + 1);

@@ -38,7 +38,13 @@ Engine::Engine(int device_index) : device_(device_index) {
 
 Engine::~Engine() {
   cudaSetDevice(device_);
+  if (copy_stream_) cudaStreamDestroy(copy_stream_);
   if (stream_) cudaStreamDestroy(stream_);
+}
+
+cudaStream_t Engine::copy_stream() {
+  if (!copy_stream_) NC_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+  return copy_stream_;
 }
 
 void Engine::bind() const { NC_CUDA(cudaSetDevice(device_)); }

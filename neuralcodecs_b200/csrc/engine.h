@@ -31,6 +31,8 @@ class Engine {
   Profiler& profiler() { return prof_; }
   void sync();
   cudaStream_t stream() const { return stream_; }
+  // second stream of the handle: host <-> device staging copies that overlap the kernels (host-pointer entry points)
+  cudaStream_t copy_stream();
 
   // re-entrancy guard (a handle is one-thread-at-a-time)
   std::atomic<bool> busy{false};   // set for the duration of an entry point (BusyGuard): handles are not re-entrant
@@ -46,6 +48,7 @@ class Engine {
   int device_ = 0;
   int num_sms_ = 148;
   cudaStream_t stream_ = nullptr;
+  cudaStream_t copy_stream_ = nullptr;
   Profiler prof_;
   uint64_t launches_ = 0;
   int fast_sin_ = -1, fuse_ru_ = 1;   // options "fast_sin" / "fuse_ru" (per handle)
@@ -92,6 +95,7 @@ class DacEngine : public Engine {
   int64_t padded_length(int64_t L) const;
   int64_t frames(int64_t L) const { return padded_length(L) / cfg_.hop(); }
   int64_t decoded_length(int64_t T) const;  // samples produced by Decode for T frames
+  int micro_batch(int B, int64_t Lp) const; // clips the engine processes per internal pass for clips of Lp padded samples
 
   // All pointers are device memory on this engine's device; nullable outputs may be null.
   // audio [B][L]; audio_out [B][decoded_length(T)]; codes [B][nq][T]; z [B][latent][T]; latents [B][nq*D][T]
@@ -132,7 +136,6 @@ class DacEngine : public Engine {
   int run_ru(const ResUnit& ru, int cur, int B, int T, const SnakeParams* post);
   int run_encoder(const float* audio, long long audio_stride, int in_len, int B, int Lp, int* T_out);
   int run_decoder(int cur, int B, int T, float* audio_out, long long out_stride);
-  int micro_batch(int B, int64_t Lp) const;
   void ensure_workspace(int mb, int64_t Lp);
   float* buf(int i) { return ws_[i].as<float>(); }
   void* buf16(int i) { return ws16_[i].as<void>(); }

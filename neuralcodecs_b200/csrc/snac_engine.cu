@@ -92,8 +92,8 @@ SnacEngine::SnacEngine(const nc_snac_config& c, int device_index) : Engine(devic
   if (cfg_.sample_rate <= 0 || cfg_.encoder_dim <= 0 || cfg_.decoder_dim <= 0 || cfg_.codebook_size <= 0)
     throw Error(NC_INVALID_ARGUMENT, "SNAC config: non-positive field");
   if (cfg_.codebook_dim != 8) throw Error(NC_UNSUPPORTED, "SNAC: codebook_dim must be 8");
-  if (cfg_.attn_window != 0 && cfg_.attn_window != 32)
-    throw Error(NC_UNSUPPORTED, "SNAC: LocalMHA is built for attn_window_size 32 (the reference presets) only");
+  if (cfg_.attn_window < 0 || cfg_.attn_window > 256)
+    throw Error(NC_UNSUPPORTED, "SNAC: attn_window_size must be in 1..256 (32 in the reference presets)");
   if (cfg_.attn_window != 0 && (cfg_.latent_dim % 64 != 0 || cfg_.decoder_dim % 64 != 0))
     throw Error(NC_UNSUPPORTED, "SNAC: LocalMHA needs latent_dim and decoder_dim to be multiples of the 64-wide heads");
   for (size_t i = 0; i < cfg_.vq_strides.size(); ++i)

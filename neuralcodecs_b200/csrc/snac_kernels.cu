@@ -392,16 +392,84 @@ local_attn_kernel(const float* __restrict__ qkv, float* __restrict__ out, const 
   }
 }
 
+// Any other window size (Modules/SNAC/LocalMHA.cs:46-70 takes any windowSize; the presets use 32): one CTA per
+// (clip, window, head), one thread per query row, K / V and the score rows in shared memory.  Same arithmetic order as the
+// 32-wide kernel (sequential dot products over d, max, exp, sum, weighted sum over j).
+__global__ void local_attn_generic_kernel(const float* __restrict__ qkv, float* __restrict__ out, const float* __restrict__ inv_freq,
+                                          int T, int C, int heads, int W) {
+  extern __shared__ float attn_smem[];
+  float* ks = attn_smem;                       // [W][64]
+  float* vs = ks + (size_t)W * kAttnD;         // [W][64]
+  float* sc = vs + (size_t)W * kAttnD;         // [W][W + 1]
+  const int i = threadIdx.x;
+  const int windows = T / W;
+  const long long item = blockIdx.x;
+  const int h = (int)(item % heads);
+  const int w = (int)((item / heads) % windows);
+  const int b = (int)(item / ((long long)heads * windows));
+  float q[kAttnD];
+  if (i < W) {
+    const float* row = qkv + ((long long)b * T + (long long)w * W + i) * 3 * C + h * kAttnD;
+    float kk[kAttnD];
+#pragma unroll
+    for (int d = 0; d < kAttnD; ++d) { q[d] = row[d]; kk[d] = row[C + d]; vs[(size_t)i * kAttnD + d] = row[2 * C + d]; }
+#pragma unroll
+    for (int d = 0; d < kAttnD / 2; ++d) {     // rotary with the position inside the window
+      const float f = (float)i * __ldg(inv_freq + d);
+      const float cs = cosf(f), sn = sinf(f);
+      const float q1 = q[d], q2 = q[d + 32], k1 = kk[d], k2 = kk[d + 32];
+      q[d] = q1 * cs + (-q2) * sn;
+      q[d + 32] = q2 * cs + q1 * sn;
+      kk[d] = k1 * cs + (-k2) * sn;
+      kk[d + 32] = k2 * cs + k1 * sn;
+    }
+#pragma unroll
+    for (int d = 0; d < kAttnD; ++d) ks[(size_t)i * kAttnD + d] = kk[d];
+  }
+  __syncthreads();
+  if (i >= W) return;
+  float* my = sc + (size_t)i * (W + 1);
+  float mx = -3.4e38f;
+  for (int j = 0; j < W; ++j) {
+    float sv = 0.f;
+#pragma unroll
+    for (int d = 0; d < kAttnD; ++d) sv = fmaf(q[d], ks[(size_t)j * kAttnD + d], sv);
+    sv *= 0.125f;   // 1 / sqrt(64)
+    my[j] = sv;
+    mx = fmaxf(mx, sv);
+  }
+  float sum = 0.f;
+  for (int j = 0; j < W; ++j) { const float e = expf(my[j] - mx); my[j] = e; sum += e; }
+  const float inv = 1.0f / sum;
+  float* orow = out + ((long long)b * T + (long long)w * W + i) * C + h * kAttnD;
+  for (int d4 = 0; d4 < kAttnD / 4; ++d4) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < W; ++j) {
+      const float4 v = *reinterpret_cast<const float4*>(&vs[(size_t)j * kAttnD + 4 * d4]);
+      const float pj = my[j] * inv;
+      a.x = fmaf(pj, v.x, a.x); a.y = fmaf(pj, v.y, a.y); a.z = fmaf(pj, v.z, a.z); a.w = fmaf(pj, v.w, a.w);
+    }
+    *reinterpret_cast<float4*>(orow + 4 * d4) = a;
+  }
+}
+
 void launch_local_attn(const float* qkv, float* out, const float* inv_freq, int batch, int T, int C, int heads, int window,
                        const LaunchCtx& ctx) {
-  if (window != kAttnW || C != heads * kAttnD) throw Error(NC_UNSUPPORTED, "local attention: window must be 32 and head dim 64");
+  if (C != heads * kAttnD) throw Error(NC_UNSUPPORTED, "local attention: head dim must be 64");
+  if (window < 1 || window > 256) throw Error(NC_UNSUPPORTED, "local attention: window size must be in 1..256");
   if (T % window != 0) throw Error(NC_INVALID_ARGUMENT, "local attention: frames not a multiple of the window");
   const long long total = (long long)batch * (T / window) * heads;
   if (total == 0) return;
   const int ev = ctx.begin();
-  local_attn_kernel<<<(unsigned)((total + 1) / 2), 64, 0, ctx.stream>>>(qkv, out, inv_freq, batch, T, C, heads);
+  if (window == kAttnW) {
+    local_attn_kernel<<<(unsigned)((total + 1) / 2), 64, 0, ctx.stream>>>(qkv, out, inv_freq, batch, T, C, heads);
+  } else {
+    const size_t smem = ((size_t)2 * window * kAttnD + (size_t)window * (window + 1)) * sizeof(float);
+    NC_CUDA(cudaFuncSetAttribute(local_attn_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    local_attn_generic_kernel<<<(unsigned)total, (window + 31) / 32 * 32, smem, ctx.stream>>>(qkv, out, inv_freq, T, C, heads, window);
+  }
   check_launch((int)cudaGetLastError(), "local_attn");
-  ctx.end(ev, "local_attn", (double)total * 2.0 * 2 * kAttnW * kAttnW * kAttnD, 16.0 * batch * (double)T * C);
+  ctx.end(ev, "local_attn", (double)total * 2.0 * 2 * window * window * kAttnD, 16.0 * batch * (double)T * C);
 }
 
 // ------------------------------------------------------------------------------ misc

@@ -137,6 +137,17 @@ def snac_attn(cache_dir):
     return co, ce, _write_snac(co, os.path.join(cache_dir, "snac_attn.safetensors"), 4, 1.0)
 
 
+@pytest.fixture(scope="session", params=[16, 48])
+def snac_attn_window(cache_dir, request):
+    """The snac_attn geometry with a LocalMHA window other than the presets' 32 (Modules/SNAC/LocalMHA.cs:46-70 takes any)."""
+    from oracle import snac as osnac
+    import neuralcodecs_b200 as nc
+    kw = dict(sample_rate=32000, encoder_dim=16, encoder_rates=[2, 3, 2], decoder_dim=256, decoder_rates=[2, 3, 2],
+              attn_window_size=request.param, codebook_size=128, vq_strides=[4, 2, 1])
+    co, ce = osnac.SNACConfig(**kw), nc.SNACConfig(**kw)
+    return co, ce, _write_snac(co, os.path.join(cache_dir, f"snac_attn_w{request.param}.safetensors"), 4, 1.0)
+
+
 @pytest.fixture(scope="session")
 def snac_44k(cache_dir):
     """SNAC 44 kHz preset (LocalMHA, vq strides 8/4/2/1, stride-3 blocks): SURVEY 8(d) extra coverage run."""

@@ -143,6 +143,23 @@ def test_local_attention_odd_stride_config(snac_attn, prec):
     m.Dispose()
 
 
+def test_local_attention_other_window_sizes(snac_attn_window):
+    """attn_window_size 16 and 48 (the presets use 32): padding multiple = hop * lcm(vq_stride0, window), windowed SDPA per
+    window of that size (generic kernel)."""
+    o, m = _models(snac_attn_window, {"precision": "fp32"})
+    cfg = snac_attn_window[0]
+    x, noise = _inputs(o, cfg, 2, 3000)
+    ref = o.forward(torch.from_numpy(x).unsqueeze(1), [torch.from_numpy(n) for n in noise])
+    audio, codes = m.forward(x[:, None, :], noise)
+    assert [c.shape for c in codes] == [tuple(c.shape) for c in ref["codes"]] and audio.shape == (2, 1, 3000)
+    assert _flips_ok(o, ref, codes) == 0
+    dec = m.Decode([c.numpy() for c in ref["codes"]], noise)
+    dref = o.decode(ref["codes"], [torch.from_numpy(n) for n in noise]).numpy()
+    assert dec.shape == dref.shape
+    assert np.abs(dec - dref).max() <= MAX_ABS and snr_db(dref, dec) >= MIN_SNR_DB
+    m.Dispose()
+
+
 def test_snac44k_preset_with_attention(snac_44k):
     o, m = _models(snac_44k)
     cfg = snac_44k[0]
@@ -173,7 +190,7 @@ def test_errors_and_resampler(snac_tiny):
     r = m.ResampleAudio(np.array([0.0, 1.0, 2.0], np.float32), 1, 2)
     np.testing.assert_array_equal(r, np.array([0.0, 0.5, 1.0, 1.5, 2.0, 2.0], np.float32))
     with pytest.raises(RuntimeError):
-        nc.SNAC(nc.SNACConfig(attn_window_size=16))                       # LocalMHA is built for the presets' window 32 only
+        nc.SNAC(nc.SNACConfig(attn_window_size=300))                      # LocalMHA windows up to 256 (the presets use 32)
     m.Dispose()
 
 

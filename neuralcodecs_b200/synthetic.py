@@ -289,6 +289,7 @@ def _enc_cfg(cfg):
               "num_lstm_layers", "codebook_size"):
         setattr(c, f, getattr(cfg, f))
     c.num_quantizers = cfg.num_quantizers
+    c.norm_type = getattr(cfg, "norm_type", "weight_norm")
     return c
 
 
@@ -363,8 +364,13 @@ def make_encodec_weights(cfg) -> Dict[str, np.ndarray]:
             _, cin, cout, k = spec
             w = convt_weight(name + ".conv.weight", cin, cout, k)
             fan_in, nb = cout * k, cout
-        sd[name + ".conv.weight_g"] = np.sqrt((w.astype(np.float64) ** 2).sum(axis=(1, 2), keepdims=True)).astype(np.float32)
-        sd[name + ".conv.weight_v"] = w
+        if c.norm_type == "time_group_norm":     # plain conv + GroupNorm(1, C) affine (NormConv1d.cs:52-69)
+            sd[name + ".conv.weight"] = w
+            sd[name + ".norm.weight"] = (1.0 + 0.1 * _rng(name + ".norm.weight").standard_normal(nb)).astype(np.float32)
+            sd[name + ".norm.bias"] = (0.1 * _rng(name + ".norm.bias").standard_normal(nb)).astype(np.float32)
+        else:
+            sd[name + ".conv.weight_g"] = np.sqrt((w.astype(np.float64) ** 2).sum(axis=(1, 2), keepdims=True)).astype(np.float32)
+            sd[name + ".conv.weight_v"] = w
         sd[name + ".conv.bias"] = bias(name + ".conv.bias", nb, fan_in)
     for q in range(c.num_quantizers):
         p = f"quantizer.layers.{q}.codebook"

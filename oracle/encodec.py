@@ -1,4 +1,6 @@
-"""CPU oracle for the reference's Encodec model (24 kHz mono causal weight-norm preset).  TEST INFRASTRUCTURE ONLY.
+"""CPU oracle for the reference's Encodec model: the 24 kHz preset (mono, causal, weight-norm, one frame per clip) and the
+48 kHz preset (stereo, non-causal, time_group_norm, 1 s segments with 1 % overlap, per-segment loudness scale).
+TEST INFRASTRUCTURE ONLY.
 
 PARITY UNPINNED by the reference (it has no tests); see oracle/__init__.py.
 
@@ -12,6 +14,12 @@ Op-for-op restatement of
 (paths relative to /root/reference/NeuralCodecs.Torch/).  Weight keys are the reference's:
 ``encoder.layers.{n}.conv.{weight_g,weight_v,bias}``, ``...block.{1,3}.conv.*``, ``...shortcut.conv.*``,
 ``encoder.layers.13.lstm.{weight_ih,weight_hh,bias_ih,bias_hh}_l{0,1}``, ``quantizer.layers.{i}.codebook.embed``.
+48 kHz additions:
+  Config/Encodec/EncodecConfig.cs:37-66          (preset), Models/Encodec.cs:190-196 (SegmentLength / SegmentStride)
+  Modules/Encodec/NormConv1d.cs:52-100,136-160, NormConvTranspose1d.cs:37-75   (plain conv, then GroupNorm(1, C, eps 1e-5))
+  Modules/Encodec/SConv1d.cs:119-128 / SConvTranspose1d.cs:98-106   (keys ``...conv.{weight,bias}``, ``...norm.{weight,bias}``)
+  Models/Encodec.cs:213-235,259-296,436-489      (segment loop, per-frame scale, DecodeFrame * scale, LinearOverlapAdd)
+  AudioTools/AudioTensorDSP.cs:161-261           (LinearOverlapAdd)
 """
 from __future__ import annotations
 
@@ -39,6 +47,27 @@ class EncodecConfig:
     bandwidth: float = 6.0
     causal: bool = True
     normalize: bool = False
+    norm_type: str = "weight_norm"              # "weight_norm" | "time_group_norm"
+    chunk_length_s: Optional[float] = None      # `Segment`: None = one frame per clip
+    overlap: float = 0.01
+
+    @classmethod
+    def encodec_48khz(cls) -> "EncodecConfig":
+        """Config/Encodec/EncodecConfig.cs:37-66."""
+        return cls(sample_rate=48000, channels=2, target_bandwidths=[3.0, 6.0, 12.0, 24.0], bandwidth=6.0, causal=False,
+                   normalize=True, norm_type="time_group_norm", chunk_length_s=1.0, overlap=0.01)
+
+    @property
+    def segment_length(self) -> Optional[int]:  # Models/Encodec.cs:190: (int)(_segment * SampleRate), float32 product
+        if self.chunk_length_s is None:
+            return None
+        return int(np.float32(self.chunk_length_s) * np.float32(self.sample_rate))
+
+    @property
+    def segment_stride(self) -> Optional[int]:  # Models/Encodec.cs:195-196: max(1, (int)((1 - overlap) * SegmentLength)), float32
+        if self.chunk_length_s is None:
+            return None
+        return max(1, int((np.float32(1) - np.float32(self.overlap)) * np.float32(self.segment_length)))
 
     @property
     def hop_length(self) -> int:
@@ -69,9 +98,17 @@ class EncodecOracle:
 
     # ---------------------------------------------------------------- conv wrappers
     def _w(self, p):
+        if self.cfg.norm_type != "weight_norm":  # NormConv1d.cs:52-63: plain Conv1d / ConvTranspose1d
+            return self.sd[p + ".conv.weight"]
         v, g = self.sd[p + ".conv.weight_v"], self.sd[p + ".conv.weight_g"]
         v_norm = v.contiguous().pow(2).sum([1, 2], keepdim=True, dtype=self.dtype).sqrt()
         return torch.mul(v.div(v_norm), g.sub(1e-7)).contiguous()
+
+    def _norm(self, p, y):
+        """NormConv1d.forward (NormConv1d.cs:87-100): time_group_norm = GroupNorm(1, C, eps 1e-5, affine) over (C, T)."""
+        if self.cfg.norm_type == "time_group_norm":
+            return F.group_norm(y, 1, self.sd[p + ".norm.weight"], self.sd[p + ".norm.bias"], 1e-5)
+        return y
 
     @staticmethod
     def _extra_padding(length, kernel, stride, padding_total):
@@ -100,11 +137,11 @@ class EncodecOracle:
         else:
             right = padding_total // 2
             padded = self._pad1d(x, padding_total - right, right + extra)
-        return F.conv1d(padded, self._w(p), self.sd.get(p + ".conv.bias"), stride, 0, dilation, 1)
+        return self._norm(p, F.conv1d(padded, self._w(p), self.sd.get(p + ".conv.bias"), stride, 0, dilation, 1))
 
     def sconvtr1d(self, p, x, k, stride):
         """SConvTranspose1d.forward (SConvTranspose1d.cs:116-139), trim_right_ratio = 1."""
-        y = F.conv_transpose1d(x, self._w(p), self.sd.get(p + ".conv.bias"), stride=stride)
+        y = self._norm(p, F.conv_transpose1d(x, self._w(p), self.sd.get(p + ".conv.bias"), stride=stride))   # norm, THEN trim
         padding_total = k - stride
         if self.cfg.causal:
             right = int(math.ceil(padding_total * 1.0))
@@ -234,6 +271,83 @@ class EncodecOracle:
         """Encodec.forward (Encodec.cs:292-296): decode(encode(x)) sliced to the input length."""
         codes = self.encode(audio, bandwidth)
         return {"audio": self.decode(codes)[..., :audio.shape[-1]], "codes": codes}
+
+
+    # ---------------------------------------------------------------- segmented surface (48 kHz; also valid for 24 kHz)
+    def encode_frame(self, x, bandwidth: Optional[float] = None):
+        """Encodec.EncodeFrame (Encodec.cs:457-489) -> (codes [B,nq,T], scale [B,1] | None)."""
+        c = self.cfg
+        if c.chunk_length_s is not None and x.shape[-1] / np.float32(c.sample_rate) > c.chunk_length_s + 1e-5:
+            raise ValueError("Frame duration exceeds segment size")
+        scale = None
+        if c.normalize:
+            mono = x.mean([1], keepdim=True)
+            volume = mono.pow(2).mean([2], keepdim=True).sqrt()
+            scale = volume.add(1e-8)
+            x = x.div(scale)
+            scale = scale.view(-1, 1)
+        return self.rvq_encode(self.encoder(x), bandwidth), scale
+
+    def encode_frames(self, audio, bandwidth: Optional[float] = None):
+        """Encodec.Encode(Tensor) (Encodec.cs:259-285): one EncodedFrame per `stride` samples, the last ones shorter."""
+        with torch.inference_mode():
+            if audio.dim() != 3:
+                raise ValueError(f"Expected 3D input tensor [B,C,T], got shape {list(audio.shape)}")
+            if audio.shape[1] != self.cfg.channels:
+                raise ValueError(f"Expected {self.cfg.channels} channels, got {audio.shape[1]}")
+            audio = audio.to(self.dtype)
+            length = audio.shape[2]
+            seg = self.cfg.segment_length or length
+            stride = self.cfg.segment_stride or length
+            return [self.encode_frame(audio[:, :, off:min(off + seg, length)], bandwidth) for off in range(0, length, stride)]
+
+    def decode_frame(self, codes, scale=None):
+        """Encodec.DecodeFrame (Encodec.cs:436-455)."""
+        out = self.decoder(self.rvq_decode(codes))
+        if scale is not None:
+            out = out * scale.view(-1, 1, 1)
+        return out
+
+    def decode_frames(self, frames):
+        """Encodec.Decode(List<EncodedFrame>) (Encodec.cs:213-235)."""
+        with torch.inference_mode():
+            if len(frames) == 0:
+                raise ValueError("No frames provided to decode")
+            if self.cfg.segment_length is None:
+                if len(frames) != 1:
+                    raise ValueError("Expected single frame when no segmentation is used")
+                return self.decode_frame(*frames[0])
+            return linear_overlap_add([self.decode_frame(c, s) for c, s in frames], self.cfg.segment_stride)
+
+    def forward_frames(self, audio, bandwidth: Optional[float] = None):
+        """Encodec.forward (Encodec.cs:292-296) through the segmented Encode / Decode."""
+        frames = self.encode_frames(audio, bandwidth)
+        return {"audio": self.decode_frames(frames)[..., :audio.shape[-1]], "frames": frames}
+
+
+def linear_overlap_add(frames, stride: int):
+    """DSP.LinearOverlapAdd (AudioTools/AudioTensorDSP.cs:161-261): triangular weights 0.5 - |linspace(0,1,L0+2)[1:-1] - 0.5|
+    sized by the FIRST frame, a slice of them for shorter frames, sum of weighted frames / sum of weights.  A frame that does
+    not fit into stride*(n-1) + len(last) raises, as the reference's `narrow` does."""
+    if len(frames) == 0:
+        raise ValueError("At least one frame is required")
+    dtype = frames[0].dtype
+    total = stride * (len(frames) - 1) + frames[-1].shape[-1]
+    L0 = frames[0].shape[-1]
+    t = torch.linspace(0, 1, L0 + 2, dtype=dtype)[1:-1]
+    weight = torch.tensor(0.5, dtype=dtype) - (t - torch.tensor(0.5, dtype=dtype)).abs()
+    sum_w = torch.zeros(total, dtype=dtype)
+    out = torch.zeros(*frames[0].shape[:-1], total, dtype=dtype)
+    off = 0
+    for f in frames:
+        n = f.shape[-1]
+        w = weight.narrow(0, 0, n)
+        out.narrow(-1, off, n).add_(f.mul(w))
+        sum_w.narrow(0, off, n).add_(w)
+        off += stride
+    if float(sum_w.min()) <= 1e-10:
+        sum_w = sum_w.add(1e-10)
+    return out.div(sum_w)
 
 
 def load_safetensors(path: str, cfg: EncodecConfig, dtype=torch.float32) -> EncodecOracle:

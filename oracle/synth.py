@@ -118,10 +118,20 @@ def _fit_encodec_codebooks(cfg, sd, clips, seconds, stages) -> None:
     from . import encodec as enc_oracle
 
     K = cfg.codebook_size
-    audio = torch.from_numpy(synth_audio(clips, int(round(seconds * cfg.sample_rate)), cfg.sample_rate)).unsqueeze(1)
+    audio = torch.from_numpy(synth_audio(clips * cfg.channels, int(round(seconds * cfg.sample_rate)), cfg.sample_rate))
+    audio = audio.reshape(clips, cfg.channels, -1)
     model = enc_oracle.EncodecOracle(cfg, {k: torch.from_numpy(v) for k, v in sd.items()})
     with torch.inference_mode():
-        residual = model.encoder(audio).clone()
+        # the latents the quantiser sees: per segment, after the per-segment loudness normalisation (Encodec.cs:259-285,469-480)
+        length = audio.shape[-1]
+        seg, stride = cfg.segment_length or length, cfg.segment_stride or length
+        lat = []
+        for off in range(0, length, stride):
+            x = audio[:, :, off:min(off + seg, length)]
+            if cfg.normalize:
+                x = x / (x.mean([1], keepdim=True).pow(2).mean([2], keepdim=True).sqrt() + 1e-8)
+            lat.append(model.encoder(x))
+        residual = torch.cat(lat, dim=-1).clone()
         for q in range(min(stages, cfg.num_quantizers)):
             rows = residual.transpose(1, 2).reshape(-1, residual.shape[1])
             nm = f"quantizer.layers.{q}.codebook.embed"

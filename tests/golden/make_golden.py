@@ -70,3 +70,40 @@ def encodec_small():
 
 if __name__ == "__main__" and "--encodec" in sys.argv:
     encodec_small()
+
+
+def encodec48_small():
+    """transformers.EncodecModel with a shrunk 48 kHz-style config (stereo, non-causal, time_group_norm, normalize, segments):
+    per-frame encode / decode of a full segment and of a shorter last segment, and the triangular overlap-add.  HF's own
+    `encode` loop differs from the reference's (it requires pre-padded input and never emits a short last frame), so the
+    pin is at the frame level; the segment loop is the reference's (Models/Encodec.cs:273-282), tested by hand in
+    tests/test_oracle_snac_encodec.py."""
+    from transformers import EncodecConfig as HFC, EncodecModel
+    torch.manual_seed(11)
+    hf = EncodecModel(HFC(num_filters=8, hidden_size=32, codebook_size=64, codebook_dim=32, upsampling_ratios=[4, 3, 2],
+                          target_bandwidths=[24.0, 48.0, 96.0], sampling_rate=48000, audio_channels=2, normalize=True,
+                          chunk_length_s=0.05, overlap=0.01, norm_type="time_group_norm", use_causal_conv=False)).eval()
+    with torch.no_grad():                       # GroupNorm affine away from (1, 0) so the test sees it
+        for n, p_ in hf.named_parameters():
+            if ".norm." in n:
+                p_.add_(0.2 * torch.randn_like(p_))
+    sd = {k: v.detach().clone().numpy() for k, v in hf.state_dict().items()}
+    seg = int(0.05 * 48000)                                            # 2400 samples = 100 frames of hop 24
+    x = torch.from_numpy(synth.synth_audio(4, seg + 1013, 48000)).reshape(2, 2, -1) * torch.tensor([0.3, 1.7]).view(2, 1, 1)
+    out = {}
+    with torch.inference_mode():
+        for name, fr in (("full", x[..., :seg]), ("tail", x[..., seg:])):
+            codes, scale = hf._encode_frame(fr, 48.0)
+            emb = hf.encoder(fr / scale.view(-1, 1, 1))
+            audio = hf._decode_frame(codes, scale)
+            out.update({f"{name}_codes": codes.numpy(), f"{name}_scale": scale.numpy(), f"{name}_emb": emb.numpy(),
+                        f"{name}_audio": audio.numpy()})
+        ola = hf._linear_overlap_add([torch.from_numpy(out["full_audio"]), torch.from_numpy(out["full_audio"]) * 0.5,
+                                      torch.from_numpy(out["tail_audio"])], hf.config.chunk_stride)
+    np.savez_compressed(os.path.join(OUT, "encodec48_hf_small.npz"), audio_in=x.numpy(), ola=ola.numpy(),
+                        stride=np.int64(hf.config.chunk_stride), **out, **{"w/" + k: v for k, v in sd.items()})
+    print("encodec48_hf_small.npz", {k: v.shape for k, v in out.items()}, ola.shape, hf.config.chunk_stride)
+
+
+if __name__ == "__main__" and "--encodec48" in sys.argv:
+    encodec48_small()

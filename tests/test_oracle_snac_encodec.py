@@ -249,3 +249,73 @@ def test_resampler_restatement_matches_scalar_loop_and_known_answers():
                                   np.array([0.0, 0.5, 1.0, 1.5, 2.0, 2.0], np.float32))      # last sample held
     assert osnac.resample_linear(np.array([1.0, 2.0, 3.0, 4.0], np.float32), 2, 1).tolist() == [1.0, 3.0]
     assert osnac.convert_to_mono(np.array([1, 3, 5, 7, 9], np.float32), 2).tolist() == [2.0, 6.0]   # ragged tail dropped
+
+
+# ------------------------------------------------------------------------------------------------ Encodec 48 kHz preset
+GOLD48 = os.path.join(os.path.dirname(__file__), "golden", "encodec48_hf_small.npz")
+
+
+@pytest.fixture(scope="module")
+def encodec48_gold():
+    g = np.load(GOLD48)
+    cfg = oenc.EncodecConfig(sample_rate=48000, channels=2, num_filters=8, hidden_size=32, codebook_size=64,
+                             upsampling_ratios=[4, 3, 2], target_bandwidths=[24.0, 48.0, 96.0], bandwidth=48.0, causal=False,
+                             normalize=True, norm_type="time_group_norm", chunk_length_s=0.05, overlap=0.01)
+    sd = {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w/")}
+    return g, cfg, oenc.EncodecOracle(cfg, sd)
+
+
+def test_encodec48_preset_algebra():
+    c = oenc.EncodecConfig.encodec_48khz()          # EncodecConfig.cs:37-66, Encodec.cs:70-71,86,190-196
+    assert (c.segment_length, c.segment_stride, c.frame_rate, c.num_quantizers, c.n_q_for_bandwidth()) == (48000, 47520, 150, 16, 4)
+    assert [c.n_q_for_bandwidth(b) for b in (3.0, 12.0, 24.0)] == [2, 8, 16]
+    assert oenc.EncodecConfig().segment_length is None and oenc.EncodecConfig().segment_stride is None
+
+
+def test_encodec48_frames_match_hf_fixture(encodec48_gold):
+    """Per-frame encode (scale, latents, codes) and decode of a full 100-frame segment and of a ragged 1013-sample tail
+    against transformers.EncodecModel._encode_frame / _decode_frame: pins the non-causal padding, GroupNorm after every conv
+    (before the transposed convs' trim), stereo in/out and the loudness scale."""
+    g, cfg, m = encodec48_gold
+    x = torch.from_numpy(g["audio_in"])
+    seg = cfg.segment_length
+    assert (seg, cfg.segment_stride) == (2400, int(g["stride"]))
+    for name, fr in (("full", x[..., :seg]), ("tail", x[..., seg:])):
+        with torch.inference_mode():
+            codes, scale = m.encode_frame(fr, 48.0)
+            emb = m.encoder(fr / scale.view(-1, 1, 1))
+            audio = m.decode_frame(torch.from_numpy(g[f"{name}_codes"]), torch.from_numpy(g[f"{name}_scale"]))
+        np.testing.assert_allclose(scale.numpy(), g[f"{name}_scale"], rtol=1e-6)
+        np.testing.assert_allclose(emb.numpy(), g[f"{name}_emb"], atol=5e-6)
+        np.testing.assert_array_equal(codes.numpy(), g[f"{name}_codes"])
+        np.testing.assert_allclose(audio.numpy(), g[f"{name}_audio"], atol=5e-6)
+
+
+def test_encodec48_overlap_add_matches_hf_and_hand(encodec48_gold):
+    g, cfg, _ = encodec48_gold
+    full, tail = torch.from_numpy(g["full_audio"]), torch.from_numpy(g["tail_audio"])
+    ola = oenc.linear_overlap_add([full, full * 0.5, tail], cfg.segment_stride)
+    np.testing.assert_allclose(ola.numpy(), g["ola"], atol=1e-7)
+    # hand case: two length-4 frames at stride 3: weights 0.5 - |{.2,.4,.6,.8} - .5| = {.2,.4,.4,.2}
+    a, b = torch.tensor([[1.0, 1.0, 1.0, 1.0]]), torch.tensor([[3.0, 3.0, 3.0, 3.0]])
+    out = oenc.linear_overlap_add([a, b], 3)
+    np.testing.assert_allclose(out.numpy(), [[1, 1, 1, (0.2 * 1 + 0.2 * 3) / 0.4, 3, 3, 3]], rtol=1e-6)
+    # a last frame too short to cover the previous one's end: the reference's narrow() throws (AudioTensorDSP.cs:214)
+    with pytest.raises(RuntimeError):
+        oenc.linear_overlap_add([torch.ones(1, 8), torch.ones(1, 8), torch.ones(1, 2)], 3)
+
+
+def test_encodec48_segment_loop_is_the_references(encodec48_gold):
+    """Encodec.Encode (Encodec.cs:273-282): offsets 0, stride, ... while offset < length; frames end at min(offset+segment, length)."""
+    g, cfg, m = encodec48_gold
+    x = torch.from_numpy(g["audio_in"])                     # 3413 samples: offsets 0 and 2376 -> frames of 2400 and 1037 samples
+    frames = m.encode_frames(x, 48.0)
+    assert [f[0].shape[-1] for f in frames] == [100, 44] and all(f[1].shape == (2, 1) for f in frames)
+    np.testing.assert_array_equal(frames[0][0].numpy(), g["full_codes"])
+    y = m.forward_frames(x, 48.0)["audio"]
+    assert y.shape == x.shape
+    # exact multiple of the stride plus the overlap: the reference emits one more (24-sample) frame than HF's loop; its
+    # 24 samples reach the last conv as ONE frame, whose Pad1d short-input branch (SConv1d.cs:258-272) lengthens it to 4
+    assert [f[0].shape[-1] for f in m.encode_frames(x[..., :2400], 48.0)] == [100, 4]
+    ref = oenc.linear_overlap_add([m.decode_frame(*f) for f in frames], cfg.segment_stride)[..., :x.shape[-1]]
+    np.testing.assert_allclose(y.numpy(), ref.numpy(), atol=1e-6)

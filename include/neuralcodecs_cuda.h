@@ -98,8 +98,11 @@ typedef struct nc_snac_config {
   int32_t depthwise; /* bool */
 } nc_snac_config;
 
-/* Flat mirror of Config/Encodec/EncodecConfig.cs:6-153 for the 24 kHz mono causal
- * weight-norm preset (Models/Encodec.cs:46-90). */
+/* Flat mirror of Config/Encodec/EncodecConfig.cs:6-153: the 24 kHz preset (:9-34: mono, causal, weight_norm, one
+ * frame per clip) and the 48 kHz preset (:37-66: stereo, non-causal, time_group_norm, normalize, 1 s segments with
+ * 1 % overlap); constructor Models/Encodec.cs:46-90. */
+#define NC_ENCODEC_NORM_WEIGHT 0     /* "weight_norm" */
+#define NC_ENCODEC_NORM_TIME_GROUP 1 /* "time_group_norm": GroupNorm(1, C) after every conv, NormConv1d.cs:136-160 */
 typedef struct nc_encodec_config {
   uint32_t struct_size;
   int32_t sample_rate;
@@ -113,6 +116,10 @@ typedef struct nc_encodec_config {
   int32_t codebook_size;
   int32_t n_quantizers; /* layers constructed (32 for 24 kHz) */
   int32_t causal;       /* bool */
+  int32_t norm_type;    /* NC_ENCODEC_NORM_* */
+  int32_t normalize;    /* bool: per-frame loudness scale, Models/Encodec.cs:469-480 */
+  float segment_s;      /* `Segment` in seconds (chunk_length_s); <= 0 = one frame per clip */
+  float overlap;        /* fraction of a segment shared with the next one (0.01) */
 } nc_encodec_config;
 
 /* -- library ---------------------------------------------------------------------- */
@@ -248,7 +255,7 @@ NC_API nc_status nc_resample_linear(nc_handle h, const float* audio, int32_t bat
 NC_API nc_status nc_convert_to_mono(nc_handle h, const float* interleaved, int64_t frames, int32_t channels, float* out);
 
 /* -- Encodec ---------------------------------------------------------------------- */
-/* 24 kHz mono causal preset.  frames = ceil-chain of the strided SConv1d layers (SConv1d.cs:245-250);
+/* Single-frame models (24 kHz preset).  frames = ceil-chain of the strided SConv1d layers (SConv1d.cs:245-250);
  * n_q = max(1, floor(bandwidth*1000 / (log2(bins) * frame_rate))) (ResidualVectorQuantizer.cs:133-144);
  * decoded_length = frames * hop.  bandwidth_kbps <= 0 selects every codebook in the file. */
 NC_API nc_status nc_encodec_query_shapes(nc_handle h, int64_t length, float bandwidth_kbps, int64_t* frames,
@@ -261,12 +268,41 @@ NC_API nc_status nc_encodec_encode(nc_handle h, const float* audio, int32_t batc
  * codes [B, n_q, frames] -> audio [B, 1, frames*hop] (not trimmed). */
 NC_API nc_status nc_encodec_decode(nc_handle h, const int64_t* codes, int32_t batch, int32_t n_q, int64_t frames,
                                    float* audio);
-/* replaces: Encodec.forward Models/Encodec.cs:292-296: decode(encode(x)) sliced to the input length.
- * audio_out [B,1,length]; codes nullable. */
+/* replaces: Encodec.forward Models/Encodec.cs:292-296: decode(encode(x)) sliced to the input length, for every preset
+ * (segment loop, scales and overlap-add inside).  audio / audio_out [B, channels, length]; codes nullable,
+ * [B, n_q, total_frames]. */
 NC_API nc_status nc_encodec_forward(nc_handle h, const float* audio, int32_t batch, int64_t length,
                                     float bandwidth_kbps, float* audio_out, int64_t* codes);
 NC_API nc_status nc_encodec_forward_dev(nc_handle h, const float* audio_dev, int32_t batch, int64_t length,
                                         float bandwidth_kbps, float* audio_out_dev, int64_t* codes_dev);
+
+/* Segmented / normalised models (48 kHz preset) and, equally, single-frame ones.
+ * replaces: the loop of Encodec.Encode Models/Encodec.cs:273-282 with SegmentLength / SegmentStride :190-196: segment s
+ * covers samples [s*stride, min(s*stride + segment, length)).  Reports the number of segments, the code frames of each
+ * (seg_frames[0 .. min(n_segments, capacity)), nullable), their sum, n_q for the bandwidth and the length Decode returns
+ * (stride*(n_segments-1) + decoded length of the last frame, AudioTools/AudioTensorDSP.cs:180). */
+NC_API nc_status nc_encodec_query_frames(nc_handle h, int64_t length, float bandwidth_kbps, int32_t* n_segments,
+                                         int64_t* seg_frames, int32_t seg_frames_capacity, int64_t* total_frames,
+                                         int32_t* n_q, int64_t* decoded_length);
+/* replaces: Encodec.Encode(Tensor) -> List<EncodedFrame> Models/Encodec.cs:259-285 (EncodeFrame :457-489), batched.
+ * audio [B, channels, length] planar; codes [B, n_q, total_frames] int64 with the segments' codes concatenated in time;
+ * scales [B, n_segments] float = EncodedFrame.Scale (written when the model normalises; nullable). */
+NC_API nc_status nc_encodec_encode_frames(nc_handle h, const float* audio, int32_t batch, int64_t length,
+                                          float bandwidth_kbps, int64_t* codes, float* scales);
+/* replaces: Encodec.Decode(List<EncodedFrame>) Models/Encodec.cs:213-235: DecodeFrame (* scale, :436-455) of every frame,
+ * then DSP.LinearOverlapAdd(frames, SegmentStride) AudioTools/AudioTensorDSP.cs:161-261.  seg_frames[n_segments] = code
+ * frames of each segment; scales nullable (frames without a scale); audio [B, channels, decoded_length] with
+ * decoded_length = stride*(n_segments-1) + decoded length of the last frame.  A last frame too short to cover the end
+ * of an earlier one returns NC_INVALID_ARGUMENT (the reference's narrow() throws). */
+NC_API nc_status nc_encodec_decode_frames(nc_handle h, const int64_t* codes, const float* scales, int32_t batch, int32_t n_q,
+                                          const int64_t* seg_frames, int32_t n_segments, float* audio);
+/* length nc_encodec_decode_frames writes per channel for these frames: stride*(n_segments-1) + decoded length of the
+ * last frame (frames*hop, except that fewer frames than the first decoder conv's padding lengthen, SConv1d.cs:258-272) */
+NC_API nc_status nc_encodec_query_decoded(nc_handle h, const int64_t* seg_frames, int32_t n_segments, int64_t* decoded_length);
+/* device-pointer forms of the two calls above, asynchronous on the handle's stream up to the final synchronise */
+NC_API nc_status nc_encodec_forward_frames_dev(nc_handle h, const float* audio_dev, int32_t batch, int64_t length,
+                                               float bandwidth_kbps, float* audio_out_dev, int64_t* codes_dev,
+                                               float* scales_dev);
 
 /* -- Encodec .ecdc container, language-model entropy coder off --------------------
  * Stream = "ECDC" | version byte 0 | int32 big-endian JSON length | JSON {m,al,nc,lm,ch,sr,bw}

@@ -63,7 +63,8 @@ class nc_encodec_config(C.Structure):
         ("n_filters", C.c_int32), ("dimension", C.c_int32), ("n_ratios", C.c_int32),
         ("ratios", C.c_int32 * NC_MAX_RATES), ("n_residual_layers", C.c_int32),
         ("lstm_layers", C.c_int32), ("codebook_size", C.c_int32), ("n_quantizers", C.c_int32),
-        ("causal", C.c_int32),
+        ("causal", C.c_int32), ("norm_type", C.c_int32), ("normalize", C.c_int32), ("segment_s", C.c_float),
+        ("overlap", C.c_float),
     ]
 
 
@@ -101,6 +102,12 @@ SIGNATURES = {
     "nc_encodec_decode": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int64, _P]),
     "nc_encodec_forward": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_float, _P, _P]),
     "nc_encodec_forward_dev": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_float, _P, _P]),
+    "nc_encodec_query_frames": (C.c_int, [_P, C.c_int64, C.c_float, C.POINTER(C.c_int32), _I64, C.c_int32, _I64,
+                                          C.POINTER(C.c_int32), _I64]),
+    "nc_encodec_encode_frames": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_float, _P, _P]),
+    "nc_encodec_decode_frames": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _I64, C.c_int32, _P]),
+    "nc_encodec_query_decoded": (C.c_int, [_P, _I64, C.c_int32, _I64]),
+    "nc_encodec_forward_frames_dev": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_float, _P, _P, _P]),
     "nc_snac_process_audio": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int32, _P, C.c_uint64, _P, C.c_int64, _I64]),
     "nc_inspect_weights": (C.c_int, [C.c_char_p, C.c_char_p, C.c_size_t]),
     "nc_resample_linear": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int64, _I64]),

@@ -172,7 +172,8 @@ class EncodecConfig:
     bandwidth: Optional[float] = 6.0
     use_causal_conv: bool = True
     normalize: bool = False
-    chunk_length_s: Optional[float] = None
+    chunk_length_s: Optional[float] = None      # `Segment`
+    overlap: float = 0.01
     norm_type: str = "weight_norm"
 
     _JSON = {"sampling_rate": "sample_rate", "audio_channels": "channels", "num_filters": "num_filters",
@@ -180,7 +181,7 @@ class EncodecConfig:
              "num_residual_layers": "num_residual_layers", "num_lstm_layers": "num_lstm_layers",
              "codebook_size": "codebook_size", "codebook_dim": "codebook_dim", "target_bandwidths": "target_bandwidths",
              "use_causal_conv": "use_causal_conv", "normalize": "normalize", "chunk_length_s": "chunk_length_s",
-             "norm_type": "norm_type"}
+             "overlap": "overlap", "norm_type": "norm_type"}
 
     @property
     def hop_length(self) -> int:
@@ -198,6 +199,25 @@ class EncodecConfig:
                 setattr(cfg, cls._JSON[k], v)
         return cfg
 
+    @property
+    def segment_length(self) -> Optional[int]:  # Models/Encodec.cs:190 (float32 product)
+        if self.chunk_length_s is None:
+            return None
+        import numpy as np
+        return int(np.float32(self.chunk_length_s) * np.float32(self.sample_rate))
+
+    @property
+    def segment_stride(self) -> Optional[int]:  # Models/Encodec.cs:195-196
+        if self.chunk_length_s is None:
+            return None
+        import numpy as np
+        return max(1, int((np.float32(1) - np.float32(self.overlap)) * np.float32(self.segment_length)))
+
     @classmethod
     def Encodec24Khz(cls) -> "EncodecConfig":   # EncodecConfig.cs:9-34
         return cls()
+
+    @classmethod
+    def Encodec48Khz(cls) -> "EncodecConfig":   # EncodecConfig.cs:37-66
+        return cls(sample_rate=48000, channels=2, target_bandwidths=[3.0, 6.0, 12.0, 24.0], bandwidth=6.0,
+                   use_causal_conv=False, normalize=True, chunk_length_s=1.0, overlap=0.01, norm_type="time_group_norm")

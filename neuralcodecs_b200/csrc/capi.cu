@@ -573,33 +573,74 @@ nc_status nc_encodec_query_shapes(nc_handle h, int64_t length, float bandwidth_k
   return guarded([&] {
     EncodecEngine* e = encodec_of(h);
     if (length < 0) throw Error(NC_INVALID_ARGUMENT, "length must be non-negative");
-    const int64_t T = e->frames(length);
-    if (frames) *frames = T;
     if (n_q) *n_q = e->n_q_for_bandwidth(bandwidth_kbps);
-    if (decoded_length) *decoded_length = e->decoded_length(T);
+    if (e->simple()) {
+      const int64_t T = e->frames(length);
+      if (frames) *frames = T;
+      if (decoded_length) *decoded_length = e->decoded_length(T);
+    } else {   // segmented models: all segments' frames and the overlap-added length
+      if (length == 0) throw Error(NC_INVALID_ARGUMENT, "length must be positive");
+      const EncodecEngine::SegLayout lay = e->seg_layout(length);
+      if (frames) *frames = lay.t_total;
+      if (decoded_length) *decoded_length = lay.total_out;
+    }
   });
 }
 
+nc_status nc_encodec_query_frames(nc_handle h, int64_t length, float bandwidth_kbps, int32_t* n_segments, int64_t* seg_frames,
+                                  int32_t seg_frames_capacity, int64_t* total_frames, int32_t* n_q, int64_t* decoded_length) {
+  return guarded([&] {
+    EncodecEngine* e = encodec_of(h);
+    if (length <= 0) throw Error(NC_INVALID_ARGUMENT, "length must be positive");
+    const EncodecEngine::SegLayout lay = e->seg_layout(length);
+    if (n_segments) *n_segments = lay.n_seg;
+    if (seg_frames)
+      for (int s = 0; s < lay.n_seg && s < seg_frames_capacity; ++s) seg_frames[s] = lay.frames[s];
+    if (total_frames) *total_frames = lay.t_total;
+    if (n_q) *n_q = e->n_q_for_bandwidth(bandwidth_kbps);
+    if (decoded_length) *decoded_length = lay.total_out;
+  });
+}
+
+// audio [B][C][length] host -> codes [B][nq][t_total], scales [B][n_seg], audio_out [B][C][length] (all nullable)
 static void encodec_forward_host(EncodecEngine* e, const float* audio, int32_t batch, int64_t length, float bw, float* audio_out,
-                                 int64_t* codes) {
+                                 int64_t* codes, float* scales) {
   if (!audio) throw Error(NC_INVALID_ARGUMENT, "audio is null");
   if (batch <= 0 || length <= 0) throw Error(NC_INVALID_ARGUMENT, "batch and length must be positive");
   BusyGuard g(e);
   e->bind();
   const int nq = e->n_q_for_bandwidth(bw);
-  const int64_t T = e->frames(length);
-  DevMem d_audio((size_t)batch * length * 4), d_out(audio_out ? (size_t)batch * length * 4 : 0),
-      d_codes(codes ? (size_t)batch * nq * T * 8 : 0);
-  h2d(e, d_audio.p, audio, (size_t)batch * length * 4);
-  e->forward_dev(d_audio.as<float>(), batch, length, nq, d_out.as<float>(), d_codes.as<int64_t>());
-  if (audio_out) d2h(e, audio_out, d_out.p, (size_t)batch * length * 4);
-  if (codes) d2h(e, codes, d_codes.p, (size_t)batch * nq * T * 8);
+  const int C = e->config().channels;
+  const EncodecEngine::SegLayout lay = e->seg_layout(length);
+  const size_t a_bytes = (size_t)batch * C * length * 4, c_bytes = (size_t)batch * nq * lay.t_total * 8;
+  const bool want_scales = scales && e->config().normalize;
+  DevMem d_audio(a_bytes), d_out(audio_out ? a_bytes : 0), d_codes(codes ? c_bytes : 0),
+      d_scales(want_scales ? (size_t)batch * lay.n_seg * 4 : 0);
+  h2d(e, d_audio.p, audio, a_bytes);
+  if (e->simple())
+    e->forward_dev(d_audio.as<float>(), batch, length, nq, d_out.as<float>(), d_codes.as<int64_t>());
+  else
+    e->forward_frames_dev(d_audio.as<float>(), batch, length, nq, d_out.as<float>(), d_codes.as<int64_t>(), d_scales.as<float>());
+  if (audio_out) d2h(e, audio_out, d_out.p, a_bytes);
+  if (codes) d2h(e, codes, d_codes.p, c_bytes);
+  if (want_scales) d2h(e, scales, d_scales.p, (size_t)batch * lay.n_seg * 4);
 }
 
 nc_status nc_encodec_encode(nc_handle h, const float* audio, int32_t batch, int64_t length, float bandwidth_kbps, int64_t* codes) {
   return guarded([&] {
     if (!codes) throw Error(NC_INVALID_ARGUMENT, "codes is null");
-    encodec_forward_host(encodec_of(h), audio, batch, length, bandwidth_kbps, nullptr, codes);
+    EncodecEngine* e = encodec_of(h);
+    if (e->config().normalize)
+      throw Error(NC_INVALID_ARGUMENT, "this Encodec model normalises every frame: use nc_encodec_encode_frames, which also returns the scales");
+    encodec_forward_host(e, audio, batch, length, bandwidth_kbps, nullptr, codes, nullptr);
+  });
+}
+
+nc_status nc_encodec_encode_frames(nc_handle h, const float* audio, int32_t batch, int64_t length, float bandwidth_kbps, int64_t* codes,
+                                   float* scales) {
+  return guarded([&] {
+    if (!codes) throw Error(NC_INVALID_ARGUMENT, "codes is null");
+    encodec_forward_host(encodec_of(h), audio, batch, length, bandwidth_kbps, nullptr, codes, scales);
   });
 }
 
@@ -607,32 +648,55 @@ nc_status nc_encodec_forward(nc_handle h, const float* audio, int32_t batch, int
                              float* audio_out, int64_t* codes) {
   return guarded([&] {
     if (!audio_out) throw Error(NC_INVALID_ARGUMENT, "audio_out is null");
-    encodec_forward_host(encodec_of(h), audio, batch, length, bandwidth_kbps, audio_out, codes);
+    encodec_forward_host(encodec_of(h), audio, batch, length, bandwidth_kbps, audio_out, codes, nullptr);
   });
 }
 
 nc_status nc_encodec_decode(nc_handle h, const int64_t* codes, int32_t batch, int32_t n_q, int64_t frames, float* audio) {
+  return nc_encodec_decode_frames(h, codes, nullptr, batch, n_q, &frames, 1, audio);
+}
+
+nc_status nc_encodec_decode_frames(nc_handle h, const int64_t* codes, const float* scales, int32_t batch, int32_t n_q,
+                                   const int64_t* seg_frames, int32_t n_segments, float* audio) {
   return guarded([&] {
     EncodecEngine* e = encodec_of(h);
     if (!codes || !audio) throw Error(NC_INVALID_ARGUMENT, "Invalid frame codes in Encodec Decode");   // Encodec.cs:438-442
-    if (batch <= 0 || frames <= 0 || n_q <= 0) throw Error(NC_INVALID_ARGUMENT, "No frames provided to decode");
+    if (batch <= 0 || n_q <= 0 || n_segments <= 0 || !seg_frames) throw Error(NC_INVALID_ARGUMENT, "No frames provided to decode");
     BusyGuard g(e);
     e->bind();
-    const int64_t L = e->decoded_length(frames);
-    DevMem d_c((size_t)batch * n_q * frames * 8), d_a((size_t)batch * L * 4);
-    h2d(e, d_c.p, codes, (size_t)batch * n_q * frames * 8);
-    e->decode_dev(d_c.as<int64_t>(), batch, n_q, frames, d_a.as<float>());
-    d2h(e, audio, d_a.p, (size_t)batch * L * 4);
+    const EncodecEngine::SegLayout lay = e->seg_layout_from_frames(seg_frames, n_segments);
+    const int C = e->config().channels;
+    const size_t c_bytes = (size_t)batch * n_q * lay.t_total * 8, a_bytes = (size_t)batch * C * lay.total_out * 4;
+    DevMem d_c(c_bytes), d_a(a_bytes), d_s(scales ? (size_t)batch * n_segments * 4 : 0);
+    h2d(e, d_c.p, codes, c_bytes);
+    if (scales) h2d(e, d_s.p, scales, (size_t)batch * n_segments * 4);
+    e->decode_frames_dev(d_c.as<int64_t>(), scales ? d_s.as<float>() : nullptr, batch, n_q, seg_frames, n_segments, d_a.as<float>());
+    d2h(e, audio, d_a.p, a_bytes);
+  });
+}
+
+nc_status nc_encodec_query_decoded(nc_handle h, const int64_t* seg_frames, int32_t n_segments, int64_t* decoded_length) {
+  return guarded([&] {
+    EncodecEngine* e = encodec_of(h);
+    const EncodecEngine::SegLayout lay = e->seg_layout_from_frames(seg_frames, n_segments);
+    if (decoded_length) *decoded_length = lay.total_out;
   });
 }
 
 nc_status nc_encodec_forward_dev(nc_handle h, const float* audio_dev, int32_t batch, int64_t length, float bandwidth_kbps,
                                  float* audio_out_dev, int64_t* codes_dev) {
+  return nc_encodec_forward_frames_dev(h, audio_dev, batch, length, bandwidth_kbps, audio_out_dev, codes_dev, nullptr);
+}
+
+nc_status nc_encodec_forward_frames_dev(nc_handle h, const float* audio_dev, int32_t batch, int64_t length, float bandwidth_kbps,
+                                        float* audio_out_dev, int64_t* codes_dev, float* scales_dev) {
   return guarded([&] {
     EncodecEngine* e = encodec_of(h);
     if (!audio_dev) throw Error(NC_INVALID_ARGUMENT, "audio is null");
     BusyGuard g(e);
-    e->forward_dev(audio_dev, batch, length, e->n_q_for_bandwidth(bandwidth_kbps), audio_out_dev, codes_dev);
+    const int nq = e->n_q_for_bandwidth(bandwidth_kbps);
+    if (e->simple()) e->forward_dev(audio_dev, batch, length, nq, audio_out_dev, codes_dev);
+    else e->forward_frames_dev(audio_dev, batch, length, nq, audio_out_dev, codes_dev, scales_dev);
   });
 }
 
@@ -769,6 +833,39 @@ static EcdcMeta ecdc_meta_for(EncodecEngine* e, int64_t length, float bw) {
   return m;
 }
 
+// Payload of a segmented / normalised model (EncodecCompressor.cs:116-190): per segment [int32 BE count = 1][float32 BE
+// scale] when the model normalises, then that segment's codes packed on their own.  off[s] = first byte of segment s.
+struct EcdcSegs {
+  std::vector<int64_t> frames, off;
+  int64_t total = 0;
+  int scale_bytes = 0;
+};
+static EcdcSegs ecdc_segs(EncodecEngine* e, const std::vector<int64_t>& frames, int nq) {
+  EcdcSegs g;
+  g.frames = frames;
+  g.scale_bytes = e->config().normalize ? 8 : 0;
+  for (int64_t T : frames) {
+    g.off.push_back(g.total);
+    g.total += g.scale_bytes + e->ecdc_payload_bytes(nq, T);
+  }
+  return g;
+}
+// the reader's frame counts (EncodecCompressor.cs:303-309): ceil(segment samples * FrameRate / SampleRate) -- NOT the
+// encoder's count when a very short last segment was lengthened by Pad1d's short-input branch; mirrored as is.
+static std::vector<int64_t> ecdc_reader_frames(EncodecEngine* e, int64_t al) {
+  const EncodecConfig& c = e->config();
+  const int64_t seg = e->segmented() ? c.segment_length() : al, stride = e->segmented() ? c.segment_stride() : al;
+  const int frame_rate = (int)std::ceil((float)c.sample_rate / (float)c.hop());
+  std::vector<int64_t> f;
+  for (int64_t off = 0; off < al; off += stride) {
+    const int64_t len = std::min(al - off, seg);
+    f.push_back((int64_t)std::ceil((double)(len * frame_rate) / (double)c.sample_rate));
+  }
+  return f;
+}
+static void put_be32(uint8_t* p, uint32_t v) { p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v; }
+static uint32_t get_be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3]; }
+
 nc_status nc_encodec_ecdc_size(nc_handle h, int64_t length, float bandwidth_kbps, int64_t* header_bytes, int64_t* stream_bytes) {
   return guarded([&] {
     EncodecEngine* e = encodec_of(h);
@@ -776,7 +873,9 @@ nc_status nc_encodec_ecdc_size(nc_handle h, int64_t length, float bandwidth_kbps
     const EcdcMeta m = ecdc_meta_for(e, length, bandwidth_kbps);
     const int64_t hb = (int64_t)ecdc_header(m).size();
     if (header_bytes) *header_bytes = hb;
-    if (stream_bytes) *stream_bytes = hb + e->ecdc_payload_bytes(m.n_codebooks, e->frames(length));
+    if (!stream_bytes) return;
+    if (e->simple()) *stream_bytes = hb + e->ecdc_payload_bytes(m.n_codebooks, e->frames(length));
+    else *stream_bytes = hb + ecdc_segs(e, e->seg_layout(length).frames, m.n_codebooks).total;
   });
 }
 
@@ -789,6 +888,39 @@ nc_status nc_encodec_compress(nc_handle h, const float* audio, int32_t batch, in
     if (batch <= 0 || length <= 0) throw Error(NC_INVALID_ARGUMENT, "batch and length must be positive");
     const EcdcMeta m = ecdc_meta_for(e, length, bandwidth_kbps);
     const std::string header = ecdc_header(m);
+    if (!e->simple()) {   // one frame per segment, each with its scale block (EncodecCompressor.cs:116-190)
+      const int nq = m.n_codebooks, C = e->config().channels;
+      const EncodecEngine::SegLayout lay = e->seg_layout(length);
+      const EcdcSegs sg = ecdc_segs(e, lay.frames, nq);
+      const int64_t total = (int64_t)header.size() + sg.total;
+      if (out_stride < total) throw Error(NC_INVALID_ARGUMENT, "out_stride is smaller than the stream (see nc_encodec_ecdc_size)");
+      BusyGuard g(e);
+      e->bind();
+      const size_t a_bytes = (size_t)batch * C * length * 4;
+      DevMem d_audio(a_bytes), d_codes((size_t)batch * nq * lay.t_total * 8), d_pay((size_t)batch * sg.total),
+          d_scales(sg.scale_bytes ? (size_t)batch * lay.n_seg * 4 : 0);
+      h2d(e, d_audio.p, audio, a_bytes);
+      e->forward_frames_dev(d_audio.as<float>(), batch, length, nq, nullptr, d_codes.as<int64_t>(), d_scales.as<float>());
+      for (int s = 0; s < lay.n_seg; ++s)
+        e->ecdc_pack_segment_dev(d_codes.as<int64_t>(), lay.t_total, lay.col[s], lay.frames[s], nq,
+                                 d_pay.as<uint8_t>() + sg.off[s] + sg.scale_bytes, sg.total, batch);
+      for (int b = 0; b < batch; ++b) std::memcpy(out + (size_t)b * out_stride, header.data(), header.size());
+      d2h_2d(e, out + header.size(), (size_t)out_stride, d_pay.p, (size_t)sg.total, (size_t)sg.total, (size_t)batch);
+      if (sg.scale_bytes) {
+        std::vector<float> sc((size_t)batch * lay.n_seg);
+        d2h(e, sc.data(), d_scales.p, sc.size() * 4);
+        for (int b = 0; b < batch; ++b)
+          for (int s = 0; s < lay.n_seg; ++s) {
+            uint8_t* p = out + (size_t)b * out_stride + header.size() + sg.off[s];
+            uint32_t bits;
+            std::memcpy(&bits, &sc[(size_t)b * lay.n_seg + s], 4);
+            put_be32(p, 1u);          // one waveform per stream: scale.numel() == 1 (:137-139)
+            put_be32(p + 4, bits);
+          }
+      }
+      if (stream_bytes) *stream_bytes = total;
+      return;
+    }
     const int64_t payload = e->ecdc_payload_bytes(m.n_codebooks, e->frames(length));
     const int64_t total = (int64_t)header.size() + payload;
     if (out_stride < total) throw Error(NC_INVALID_ARGUMENT, "out_stride is smaller than the stream (see nc_encodec_ecdc_size)");
@@ -848,6 +980,44 @@ nc_status nc_encodec_decompress(nc_handle h, const uint8_t* streams, int32_t bat
     if (!audio) return;   // size query
     if (audio_capacity < m0.audio_length) throw Error(NC_INVALID_ARGUMENT, "audio_capacity is smaller than the stored audio length");
     const int64_t payload = stream_bytes - (int64_t)off;
+    if (!e->simple()) {   // frames with scale blocks, decoded and overlap-added (EncodecCompressor.cs:303-415)
+      const int nq = m0.n_codebooks, C = c.channels;
+      const int64_t al = m0.audio_length;
+      if (al <= 0) throw Error(NC_INVALID_ARGUMENT, "Invalid ecdc payload");
+      const std::vector<int64_t> fr = ecdc_reader_frames(e, al);
+      const EcdcSegs sg = ecdc_segs(e, fr, nq);
+      if (payload < sg.total) throw Error(NC_INVALID_ARGUMENT, "Stream ended too soon");   // :390-393
+      const int n_seg = (int)fr.size();
+      std::vector<float> sc;
+      if (sg.scale_bytes) {
+        sc.resize((size_t)batch * n_seg);
+        for (int b = 0; b < batch; ++b)
+          for (int s = 0; s < n_seg; ++s) {
+            const uint8_t* p = streams + (size_t)b * stream_stride + off + sg.off[s];
+            const int32_t count = (int32_t)get_be32(p);
+            if (count <= 0 || count > 1000) throw Error(NC_INVALID_ARGUMENT, "Invalid scale count: " + std::to_string(count));   // :318-321
+            if (count != 1) throw Error(NC_UNSUPPORTED, "ecdc frames with more than one scale value (a batch in one stream) are not supported");
+            const uint32_t bits = get_be32(p + 4);
+            std::memcpy(&sc[(size_t)b * n_seg + s], &bits, 4);
+          }
+      }
+      BusyGuard g(e);
+      e->bind();
+      const EncodecEngine::SegLayout lay = e->seg_layout_from_frames(fr.data(), n_seg);
+      DevMem d_pay((size_t)batch * sg.total), d_codes((size_t)batch * nq * lay.t_total * 8),
+          d_audio((size_t)batch * C * lay.total_out * 4), d_sc(sc.empty() ? 0 : sc.size() * 4);
+      h2d_2d(e, d_pay.p, (size_t)sg.total, streams + off, (size_t)stream_stride, (size_t)sg.total, (size_t)batch);
+      if (!sc.empty()) h2d(e, d_sc.p, sc.data(), sc.size() * 4);
+      for (int s = 0; s < n_seg; ++s)
+        e->ecdc_unpack_segment_dev(d_pay.as<uint8_t>() + sg.off[s] + sg.scale_bytes, sg.total, d_codes.as<int64_t>(), lay.t_total,
+                                   lay.col[s], fr[s], nq, batch);
+      e->decode_frames_dev(d_codes.as<int64_t>(), sc.empty() ? nullptr : d_sc.as<float>(), batch, nq, fr.data(), n_seg, d_audio.as<float>());
+      // rows = (clip, channel); only al samples of each are returned (:408-412)
+      const int64_t keep = std::min<int64_t>(al, lay.total_out);
+      d2h_2d(e, audio, (size_t)audio_capacity * 4, d_audio.p, (size_t)lay.total_out * 4, (size_t)keep * 4, (size_t)batch * C);
+      if (audio_length) *audio_length = keep;
+      return;
+    }
     BusyGuard g(e);
     e->bind();
     DevMem d_pay((size_t)batch * std::max<int64_t>(payload, 1)), d_audio((size_t)batch * m0.audio_length * 4);

@@ -1,9 +1,13 @@
-// Encodec engine (24 kHz mono, causal, weight-norm preset).  Graph (paths under /root/reference/NeuralCodecs.Torch/):
+// Encodec engine: the 24 kHz preset (mono, causal, weight-norm, one frame per clip) and the 48 kHz preset (stereo, non-causal,
+// GroupNorm(1, C) after every conv, 1 s segments with 1 % overlap, per-segment loudness scale, triangular overlap-add:
+// Config/Encodec/EncodecConfig.cs:37-66, Modules/Encodec/NormConv1d.cs:52-100, AudioTools/AudioTensorDSP.cs:161-261).
+// Graph (paths under /root/reference/NeuralCodecs.Torch/):
 //   Models/Encodec.cs:213-296,436-489; Modules/Encodec/SEANetEncoder.cs:37-148, SEANetDecoder.cs:40-153,
 //   SEANetResnetBlock.cs:30-86, SConv1d.cs:144-173,245-274, SConvTranspose1d.cs:116-139, SLSTM.cs:40-57,
 //   ResidualVectorQuantizer.cs:107-157, EuclideanCodebook.cs:155-182.
-// Activations are channels-last with 8 margin rows around every clip: the causal left reflect padding (and the
-// right "extra" padding) of SConv1d is materialised in those rows by a tiny fix-up kernel, after which every conv
+// Activations are channels-last with 16 margin rows around every clip: the reflect padding of SConv1d (causal: k - s on the
+// left; non-causal: split left / right; plus the stride-alignment extra on the right) is materialised in those rows by a
+// tiny fix-up kernel, after which every conv
 // is a plain valid convolution for the tcgen05 kernel.  ELU commutes with reflect padding, so it is applied in the
 // producing layer's epilogue (or the consumer's prologue) like DAC's Snake.
 #include <algorithm>
@@ -27,14 +31,23 @@ EncodecEngine::EncodecEngine(const nc_encodec_config& c, int device_index) : Eng
   cfg_.codebook_size = c.codebook_size;
   cfg_.n_quantizers = c.n_quantizers;
   cfg_.causal = c.causal != 0;
-  if (cfg_.channels != 1) throw Error(NC_UNSUPPORTED, "Encodec: only the mono preset is built (channels = 1)");
-  if (!cfg_.causal) throw Error(NC_UNSUPPORTED, "Encodec: only causal convolutions are built (24 kHz preset)");
+  cfg_.group_norm = c.norm_type == NC_ENCODEC_NORM_TIME_GROUP;
+  cfg_.normalize = c.normalize != 0;
+  cfg_.segment_s = c.segment_s;
+  cfg_.overlap = c.overlap;
+  if (c.norm_type != NC_ENCODEC_NORM_WEIGHT && c.norm_type != NC_ENCODEC_NORM_TIME_GROUP)
+    throw Error(NC_UNSUPPORTED, "Encodec: norm must be weight_norm or time_group_norm");
+  if (cfg_.channels < 1 || cfg_.channels > 2) throw Error(NC_INVALID_ARGUMENT, "Invalid number of channels: " + std::to_string(cfg_.channels));   // Encodec.cs:268-271
+  if (cfg_.group_norm && cfg_.causal) throw Error(NC_INVALID_ARGUMENT, "GroupNorm doesn't support causal evaluation");   // NormConv1d.cs:143-147
+  if (cfg_.segment_s < 0.f || !(cfg_.overlap >= 0.f && cfg_.overlap < 1.f)) throw Error(NC_INVALID_ARGUMENT, "Encodec config: segment / overlap out of range");
+  if (cfg_.segment_s > 0.f && cfg_.segment_length() < 1) throw Error(NC_INVALID_ARGUMENT, "Encodec config: segment shorter than one sample");
+  generic_io_ = cfg_.channels != 1 || !cfg_.causal || cfg_.group_norm || cfg_.normalize || cfg_.segment_s > 0.f;
   if (cfg_.n_residual_layers != 1) throw Error(NC_UNSUPPORTED, "Encodec: n_residual_layers must be 1");
   if (cfg_.lstm_layers != 0 && cfg_.lstm_layers != 2) throw Error(NC_UNSUPPORTED, "Encodec: lstm_layers must be 0 or 2");
   if (cfg_.dimension != 128) throw Error(NC_UNSUPPORTED, "Encodec: dimension (codebook dim) must be 128");
   if (cfg_.n_filters % 32 != 0) throw Error(NC_UNSUPPORTED, "Encodec: n_filters must be a multiple of 32");
   for (int r : cfg_.ratios)
-    if (r < 1 || r > kMargin) throw Error(NC_UNSUPPORTED, "Encodec: ratios must be in 1..8");
+    if (r < 1 || r > 8) throw Error(NC_UNSUPPORTED, "Encodec: ratios must be in 1..8");
   if (cfg_.n_quantizers < 1 || cfg_.codebook_size < 1) throw Error(NC_INVALID_ARGUMENT, "Encodec config: non-positive field");
 }
 
@@ -44,6 +57,7 @@ EncodecEngine::~EncodecEngine() {
   for (float* p : embed_) cudaFree(p);
   for (float* p : embed_sq_) cudaFree(p);
   cudaFree(d_embed_ptrs_);
+  for (auto& kv : gn_) { cudaFree(kv.second.gamma); cudaFree(kv.second.beta); }
   for (auto* l : {&enc_lstm_, &dec_lstm_})
     for (float*& p : l->whh) { cudaFree(p); p = nullptr; }
 }
@@ -89,28 +103,38 @@ std::string EncodecEngine::describe() const {
     first = false;
     s += l.name() + "\": \"" + l.executor() + "\"";
   };
+  add(conv_in_l_);
   for (size_t i = 0; i < enc_res_.size(); ++i) { add(enc_res_[i]->shortcut); add(enc_res_[i]->c3); add(enc_res_[i]->c1); add(*enc_down_[i]); }
   add(enc_lstm_.ih[0]); add(enc_lstm_.ih[1]); add(enc_out_); add(dec_in_); add(dec_lstm_.ih[0]); add(dec_lstm_.ih[1]);
   for (size_t i = 0; i < dec_res_.size(); ++i) { add(*dec_up_[i]); add(dec_res_[i]->shortcut); add(dec_res_[i]->c3); add(dec_res_[i]->c1); }
-  s += "}}";
+  add(conv_out_l_);
+  s += "}";
+  if (cfg_.group_norm) s += ", \"norm\": \"time_group_norm\"";
+  if (segmented()) s += ", \"segment_length\": " + std::to_string(cfg_.segment_length()) + ", \"segment_stride\": " + std::to_string(cfg_.segment_stride());
+  s += "}";
   return s;
 }
 
 // w = (v / ||v||_(1,2)) * (g - 1e-7)   (Modules/Encodec/WNConv1d.cs:113-127, WNConvTranspose1d.cs:124-156)
+// time_group_norm models carry the plain conv weight (NormConv1d.cs:52-63; keys SConv1d.cs:119-128).
 std::vector<float> EncodecEngine::folded(const std::string& p, int d0, int d1, int k, std::vector<float>* bias, int bias_n) {
-  const HostTensor& v = tensor(p + ".conv.weight_v");
-  const HostTensor& g = tensor(p + ".conv.weight_g");
+  const HostTensor& v = tensor(p + (cfg_.group_norm ? ".conv.weight" : ".conv.weight_v"));
   if (v.is_int || v.shape.size() != 3 || v.shape[0] != d0 || v.shape[1] != d1 || v.shape[2] != k)
     throw Error(NC_SHAPE_MISMATCH, "Failed to load Encodec weights: '" + p + "' has the wrong shape");
-  if (g.is_int || (int64_t)g.numel() != d0)
-    throw Error(NC_SHAPE_MISMATCH, "Failed to load Encodec weights: '" + p + ".conv.weight_g' has the wrong shape");
   std::vector<float> w(v.f32.size());
-  const size_t inner = (size_t)d1 * k;
-  for (int i = 0; i < d0; ++i) {
-    double ss = 0;
-    for (size_t j = 0; j < inner; ++j) ss += (double)v.f32[i * inner + j] * v.f32[i * inner + j];
-    const float norm = std::sqrt((float)ss), gi = g.f32[i] - 1e-7f;
-    for (size_t j = 0; j < inner; ++j) w[i * inner + j] = (v.f32[i * inner + j] / norm) * gi;
+  if (cfg_.group_norm) {
+    w = v.f32;
+  } else {
+    const HostTensor& g = tensor(p + ".conv.weight_g");
+    if (g.is_int || (int64_t)g.numel() != d0)
+      throw Error(NC_SHAPE_MISMATCH, "Failed to load Encodec weights: '" + p + ".conv.weight_g' has the wrong shape");
+    const size_t inner = (size_t)d1 * k;
+    for (int i = 0; i < d0; ++i) {
+      double ss = 0;
+      for (size_t j = 0; j < inner; ++j) ss += (double)v.f32[i * inner + j] * v.f32[i * inner + j];
+      const float norm = std::sqrt((float)ss), gi = g.f32[i] - 1e-7f;
+      for (size_t j = 0; j < inner; ++j) w[i * inner + j] = (v.f32[i * inner + j] / norm) * gi;
+    }
   }
   if (bias) {
     bias->clear();
@@ -138,6 +162,21 @@ static std::vector<float> pad1e(const std::vector<float>& b, int n, int p) {
 }
 static int pad32e(int c) { return (c + 31) / 32 * 32; }
 
+// GroupNorm(1, C, eps 1e-5, affine) of a conv (NormConv1d.cs:136-160): keys "<p>.norm.{weight,bias}"; padded channels get
+// gamma = beta = 0 so they stay zero.
+void EncodecEngine::load_gn(const std::string& p, int c_real, int c_pad) {
+  if (!cfg_.group_norm) return;
+  const HostTensor& g = tensor(p + ".norm.weight");
+  const HostTensor& b = tensor(p + ".norm.bias");
+  if (g.is_int || b.is_int || (int)g.numel() != c_real || (int)b.numel() != c_real)
+    throw Error(NC_SHAPE_MISMATCH, "Failed to load Encodec weights: '" + p + ".norm' has the wrong shape");
+  Gn& n = gn_[p];
+  cudaFree(n.gamma); cudaFree(n.beta);
+  n.gamma = upload(pad1e(g.f32, c_real, c_pad));
+  n.beta = upload(pad1e(b.f32, c_real, c_pad));
+  n.c_real = c_real;
+}
+
 void EncodecEngine::build_res(Res& r, const std::string& p, int dim) {
   std::vector<float> b;
   const Precision prec_ = p.compare(0, 8, "encoder.") == 0 ? enc_prec_ : dec_prec_;
@@ -148,6 +187,9 @@ void EncodecEngine::build_res(Res& r, const std::string& p, int dim) {
   auto ws = folded(p + ".shortcut", dim, dim, 1, &b, dim);
   const bool enc = p.compare(0, 8, "encoder.") == 0;
   r.shortcut.build(p + ".shortcut", s1, ws, b, prec_, enc ? chain_mode(dim, 1) : 0);
+  load_gn(p + ".shortcut", dim, dim);
+  load_gn(p + ".block.1", hid, hp);
+  load_gn(p + ".block.3", dim, dim);
   ConvSpec s3;  // block.1: SConv1d(dim, dim/2, 3): valid conv over the left-padded input
   s3.cin = dim; s3.cout = hp; s3.k = 3;
   auto w3 = folded(p + ".block.1", hid, dim, 3, &b, hid);
@@ -187,11 +229,17 @@ void EncodecEngine::finalize_weights() {
   std::vector<float> b;
   const int nf = cfg_.n_filters;
   // ---- encoder (SEANetEncoder.cs:60-125): Sequential indices
-  {
+  if (!generic_io_) {
     auto w = folded("encoder.layers.0", nf, 1, 7, &b, nf);
     cudaFree(d_conv_in_w_); cudaFree(d_conv_in_b_);
     d_conv_in_w_ = upload(w);
     d_conv_in_b_ = upload(pad1e(b, nf, nf));
+  } else {   // SConv1d(channels, n_filters, 7) over the channel-padded channels-last segment
+    ConvSpec cs;
+    cs.cin = cin_pad_; cs.cout = nf; cs.k = 7;
+    auto w = folded("encoder.layers.0", nf, cfg_.channels, 7, &b, nf);
+    conv_in_l_.build("encoder.layers.0", cs, pad3e(w, nf, cfg_.channels, 7, nf, cin_pad_), b, enc_prec_, chain_mode(cin_pad_, 7));
+    load_gn("encoder.layers.0", nf, nf);
   }
   enc_res_.clear(); enc_down_.clear();
   int mult = 1, idx = 1;
@@ -207,6 +255,7 @@ void EncodecEngine::finalize_weights() {
     const std::string p = "encoder.layers." + std::to_string(idx);
     auto w = folded(p, 2 * dim, dim, 2 * r, &b, 2 * dim);
     down->build(p, cs, w, b, enc_prec_, chain_mode(dim, 2 * r));
+    load_gn(p, 2 * dim, 2 * dim);
     enc_down_.push_back(std::move(down));
     ++idx;
     mult *= 2;
@@ -220,6 +269,7 @@ void EncodecEngine::finalize_weights() {
     const std::string p = "encoder.layers." + std::to_string(idx);
     auto w = folded(p, cfg_.dimension, dim_top, 7, &b, cfg_.dimension);
     enc_out_.build(p, cs, w, b, enc_prec_, chain_mode(dim_top, 7));
+    load_gn(p, cfg_.dimension, cfg_.dimension);
   }
   // ---- quantiser codebooks (EuclideanCodebook.cs:22-25)
   {
@@ -255,6 +305,7 @@ void EncodecEngine::finalize_weights() {
     cs.cin = cfg_.dimension; cs.cout = mult * nf; cs.k = 7;
     auto w = folded("decoder.layers.0", mult * nf, cfg_.dimension, 7, &b, mult * nf);
     dec_in_.build("decoder.layers.0", cs, w, b, dec_prec_);
+    load_gn("decoder.layers.0", mult * nf, mult * nf);
   }
   idx = 1;
   if (cfg_.lstm_layers > 0) { build_lstm(dec_lstm_, "decoder.layers." + std::to_string(idx), mult * nf); ++idx; }
@@ -268,6 +319,7 @@ void EncodecEngine::finalize_weights() {
     const std::string p = "decoder.layers." + std::to_string(idx);
     auto w = folded(p, cin, cout, 2 * r, &b, cout);
     up->build(p, cs, w, b, dec_prec_);
+    load_gn(p, cout, cout);
     dec_up_.push_back(std::move(up));
     ++idx;
     auto res = std::make_unique<Res>();
@@ -279,6 +331,16 @@ void EncodecEngine::finalize_weights() {
   ++idx;  // ELU
   {
     const std::string p = "decoder.layers." + std::to_string(idx);
+    if (generic_io_) {   // SConv1d(n_filters, channels, 7) with the output channels padded to one N tile
+      ConvSpec cs;
+      cs.cin = nf; cs.cout = cout_pad_; cs.k = 7;
+      auto w = folded(p, cfg_.channels, nf, 7, &b, cfg_.channels);
+      conv_out_l_.build(p, cs, pad3e(w, cfg_.channels, nf, 7, cout_pad_, nf), pad1e(b, cfg_.channels, cout_pad_), dec_prec_);
+      load_gn(p, cfg_.channels, cout_pad_);
+      drop_tensors();
+      ready_ = true;
+      return;
+    }
     auto w = folded(p, 1, nf, 7, &b, 1);
     std::vector<float> wkc((size_t)7 * nf);
     for (int ci = 0; ci < nf; ++ci)
@@ -293,17 +355,25 @@ void EncodecEngine::finalize_weights() {
 }
 
 // ------------------------------------------------------------------------------------ shapes
-// SConv1d.forward's padding for a causal conv (SConv1d.cs:144-173): padding_total = k - s on the left, the stride
-// alignment extra on the right (computed with a float32 division, :245-250), and -- when the input is not longer than
-// the larger pad -- Pad1d's short-input branch: zero-extend on the right first (:258-272).  The zero extension is not
-// trimmed afterwards, so such a layer lengthens the sequence.
-EncodecEngine::SPad EncodecEngine::sconv_pad(int64_t T, int k, int s) {
+// SConv1d.forward's padding (SConv1d.cs:144-173): padding_total = k - s goes on the left (causal) or is split
+// right = padding_total / 2, left = the rest (non-causal); the stride alignment extra goes on the right (computed with a
+// float32 division, :245-250); and -- when the input is not longer than the larger pad -- Pad1d's short-input branch
+// zero-extends on the right first (:258-272).  The zero extension is not trimmed afterwards, so such a layer lengthens
+// the sequence.
+EncodecEngine::SPad EncodecEngine::sconv_pad(int64_t T, int k, int s, bool causal) {
   const int pt = k - s;
   const float n_frames = ((float)(T - k + pt)) / (float)s + 1.0f;
   const int64_t ideal = ((int64_t)std::ceil(n_frames) - 1) * s + (k - pt);
+  const int extra = (int)(ideal - T);
   SPad p;
-  p.left = pt;
-  p.right = (int)(ideal - T);
+  if (causal) {
+    p.left = pt;
+    p.right = extra;
+  } else {
+    const int right = pt / 2;
+    p.left = pt - right;
+    p.right = right + extra;
+  }
   const int m = std::max(p.left, p.right);
   p.extra_zero = T <= m ? (int)(m - T + 1) : 0;
   p.t_out = (int)((T + p.extra_zero + p.left + p.right - k) / s + 1);
@@ -321,7 +391,74 @@ int64_t EncodecEngine::frames(int64_t L) const {
   return sconv_pad(t, 7, 1).t_out;                                         // final SConv1d(.., dimension, 7)
 }
 
-int64_t EncodecEngine::decoded_length(int64_t T) const { return (int64_t)sconv_pad(T, 7, 1).t_out * cfg_.hop(); }
+int64_t EncodecEngine::decoded_length(int64_t T) const {
+  int64_t t = sconv_pad(T, 7, 1).t_out;
+  for (size_t i = 0; i < cfg_.ratios.size(); ++i) {
+    t *= cfg_.ratios[i];
+    const SPad k3 = sconv_pad(t, 3, 1);
+    if (k3.t_out != t) throw Error(NC_INVALID_ARGUMENT, "Encodec: too few frames: a residual block's branches would differ in length (the reference's tensor add fails)");
+  }
+  return sconv_pad(t, 7, 1).t_out;
+}
+
+// Encodec.Encode's loop (Encodec.cs:273-282): offsets 0, stride, ... while offset < length; a frame ends at
+// min(offset + segment, length).  SegmentLength / SegmentStride: Encodec.cs:190-196.
+EncodecEngine::SegLayout EncodecEngine::seg_layout(int64_t L) const {
+  SegLayout lay;
+  lay.seg = segmented() ? cfg_.segment_length() : L;
+  lay.stride = segmented() ? cfg_.segment_stride() : L;
+  lay.n_seg = (int)((L + lay.stride - 1) / lay.stride);
+  for (int s = 0; s < lay.n_seg; ++s) {
+    const int64_t len = std::min<int64_t>(lay.seg, L - (int64_t)s * lay.stride);
+    lay.len.push_back(len);
+    if (len == lay.seg && lay.n_full == s) ++lay.n_full;
+    const int64_t T = frames(len);
+    lay.col.push_back(lay.t_total);
+    lay.frames.push_back(T);
+    lay.t_total += T;
+    lay.ld.push_back(decoded_length(T));
+    lay.ld_max = std::max(lay.ld_max, lay.ld.back());
+  }
+  lay.total_out = lay.stride * (lay.n_seg - 1) + lay.ld.back();            // AudioTensorDSP.cs:180
+  return lay;
+}
+
+EncodecEngine::SegLayout EncodecEngine::seg_layout_from_frames(const int64_t* seg_frames, int n_seg) const {
+  if (n_seg < 1 || !seg_frames) throw Error(NC_INVALID_ARGUMENT, "No frames provided to decode");               // Encodec.cs:215-218
+  if (!segmented() && n_seg != 1) throw Error(NC_INVALID_ARGUMENT, "Expected single frame when no segmentation is used");   // :222-225
+  SegLayout lay;
+  lay.n_seg = n_seg;
+  lay.seg = segmented() ? cfg_.segment_length() : 0;
+  lay.stride = segmented() ? cfg_.segment_stride() : 0;
+  for (int s = 0; s < n_seg; ++s) {
+    const int64_t T = seg_frames[s];
+    if (T <= 0 || T > ((int64_t)1 << 24)) throw Error(NC_INVALID_ARGUMENT, "Invalid frame codes in Encodec Decode");
+    if (T == seg_frames[0] && lay.n_full == s) ++lay.n_full;     // equal-length leading frames decode as one batch
+    lay.len.push_back(0);
+    lay.col.push_back(lay.t_total);
+    lay.frames.push_back(T);
+    lay.t_total += T;
+    lay.ld.push_back(decoded_length(T));
+    lay.ld_max = std::max(lay.ld_max, lay.ld.back());
+  }
+  lay.total_out = lay.stride * (n_seg - 1) + lay.ld.back();
+  return lay;
+}
+
+std::vector<EncodecEngine::Group> EncodecEngine::groups_of(const SegLayout& lay) const {
+  std::vector<Group> g;
+  if (lay.n_full > 0) g.push_back({lay.n_full, 0, lay.len[0], lay.frames[0], 0});
+  for (int s = lay.n_full; s < lay.n_seg; ++s) g.push_back({1, s, lay.len[s], lay.frames[s], lay.col[s]});
+  return g;
+}
+
+// LinearOverlapAdd narrows the output at [s*stride, s*stride + len_s) for every frame (AudioTensorDSP.cs:214): a frame that
+// sticks out beyond stride*(n-1) + len_last makes the reference throw; weights come from the FIRST frame's length (:184-189).
+void EncodecEngine::check_overlap_add(const SegLayout& lay) const {
+  for (int s = 0; s < lay.n_seg; ++s)
+    if ((int64_t)s * lay.stride + lay.ld[s] > lay.total_out || lay.ld[s] > lay.ld[0])
+      throw Error(NC_INVALID_ARGUMENT, "Encodec Decode: frame " + std::to_string(s) + " does not fit the overlap-add output (the last frame is too short; the reference's narrow() fails)");
+}
 
 void EncodecEngine::conv_short(const ConvLayer& L, const Act& in, const SPad& pad, const Act& out, int B, int prologue, int post) {
   const LaunchCtx c = ctx();
@@ -360,6 +497,7 @@ int EncodecEngine::micro_batch(int B, int64_t L) {
   hbuf_.reserve((size_t)2 * ((mb + 31) / 32 * 32) * top * sizeof(float));
   barriers_.reserve(64 * sizeof(unsigned int));
   audio_tmp_.reserve((size_t)mb * decoded_length(T) * sizeof(float));
+  gn_stats_.reserve((size_t)mb * 2 * sizeof(double));
   return mb;
 }
 
@@ -388,6 +526,34 @@ void EncodecEngine::conv(const ConvLayer& L, const Act& in, int left_pad, int ex
   L.run(a, ctx());
 }
 
+// time_group_norm: y = GroupNorm(conv(x)), then whatever followed the conv in the weight-norm graph (residual add, ELU of
+// the next layer).  Two HBM passes over the conv's output: fp64 sums, then the in-place affine.
+void EncodecEngine::finish_norm(const ConvLayer& L, const Act& y, int B, int post, const Act* residual, int row0, int rows) {
+  if (!cfg_.group_norm) return;
+  const LaunchCtx c = ctx();
+  const auto it = gn_.find(L.name());
+  if (it == gn_.end()) throw Error(NC_INTERNAL, "no GroupNorm parameters for " + L.name());
+  const Gn& g = it->second;
+  double* st = gn_stats_.as<double>();
+  launch_gn_stats(y.base + (long long)row0 * y.C, y.stride, (long long)rows * y.C, st, B, c);
+  launch_gn_apply(y.base, y.stride, y.T, y.C, st, (double)rows * g.c_real, 1e-5f, g.gamma, g.beta, residual ? residual->base : nullptr,
+                  residual ? residual->stride : 0, post == PRO_ELU ? 1 : 0, B, c);
+}
+
+void EncodecEngine::conv_n(const ConvLayer& L, const Act& in, int left_pad, int extra, const Act& out, int B, int prologue, int post,
+                           const Act* residual, int out_row0, int stat_rows) {
+  const bool gn = cfg_.group_norm;
+  Act o = out;
+  o.base += (long long)out_row0 * out.C;      // transposed convs: the rows trimmed on the left land in the margin
+  conv(L, in, left_pad, extra, o, B, prologue, gn ? PRO_NONE : post, gn ? nullptr : residual);
+  finish_norm(L, out, B, post, residual, out_row0, stat_rows < 0 ? out.T : stat_rows);
+}
+
+void EncodecEngine::conv_short_n(const ConvLayer& L, const Act& in, const SPad& pad, const Act& out, int B, int prologue, int post) {
+  conv_short(L, in, pad, out, B, prologue, cfg_.group_norm ? PRO_NONE : post);
+  finish_norm(L, out, B, post, nullptr, 0, out.T);
+}
+
 int EncodecEngine::pick_free(int a, int b, int c, int d) const {
   for (int i = 0; i < 5; ++i)
     if (i != a && i != b && i != c && i != d) return i;
@@ -402,10 +568,11 @@ EncodecEngine::Act EncodecEngine::run_res(const Res& r, const Act& x, int B, int
   hb = pick_free(xb, sb);
   const int yb = pick_free(xb, sb, hb);
   Act S = act(sb, B, x.T, x.C), H = act(hb, B, x.T, r.hidden_p), Y = act(yb, B, x.T, x.C);
-  conv(r.shortcut, x, 0, 0, S, B, PRO_NONE, PRO_NONE, nullptr);
-  launch_reflect_pad(x.base, x.T, x.C, x.stride, 2, 0, B, c);            // k3: padding_total = 2, causal -> left
-  conv(r.c3, x, 2, 0, H, B, PRO_ELU, PRO_ELU, nullptr);
-  conv(r.c1, H, 0, 0, Y, B, PRO_NONE, post_elu ? PRO_ELU : PRO_NONE, &S);
+  conv_n(r.shortcut, x, 0, 0, S, B, PRO_NONE, PRO_NONE, nullptr);
+  const SPad k3 = sconv_pad(x.T, 3, 1);                                   // padding_total = 2: causal (2, 0), else (1, 1)
+  launch_reflect_pad(x.base, x.T, x.C, x.stride, k3.left, k3.right, B, c);
+  conv_n(r.c3, x, k3.left, k3.right, H, B, PRO_ELU, PRO_ELU, nullptr);
+  conv_n(r.c1, H, 0, 0, Y, B, PRO_NONE, post_elu ? PRO_ELU : PRO_NONE, &S);
   xb = yb;
   return Y;
 }
@@ -431,13 +598,23 @@ EncodecEngine::Act EncodecEngine::run_lstm(const Lstm& l, const Act& x, int B, i
   return cur;
 }
 
+// audio: [B][L] mono samples (24 kHz-style path); the generic path expects the caller to have written the prepared,
+// channel-padded segment into act(1, B, L, cin_pad_) (launch_encodec_segment_prep).
 void EncodecEngine::run_encoder(const float* audio, int B, int64_t L, int64_t* T_out) {
   const LaunchCtx c = ctx();
   const int nf = cfg_.n_filters;
   int xb = 0, sb = -1, hb = -1;
   const SPad p_in = sconv_pad(L, 7, 1);
   Act x = act(xb, B, p_in.t_out, nf);
-  if (p_in.extra_zero == 0) {
+  if (generic_io_) {
+    Act in = act(1, B, (int)L, cin_pad_);
+    if (p_in.extra_zero == 0) {
+      launch_reflect_pad(in.base, in.T, in.C, in.stride, p_in.left, p_in.right, B, c);
+      conv_n(conv_in_l_, in, p_in.left, p_in.right, x, B, PRO_NONE, PRO_NONE, nullptr);
+    } else {
+      conv_short_n(conv_in_l_, in, p_in, x, B, PRO_NONE, PRO_NONE);
+    }
+  } else if (p_in.extra_zero == 0) {
     // SConv1d(1, 32, 7) causal: left reflect pad 6 handled by index reflection inside the Cin = 1 kernel
     launch_conv_cin1(audio, L, (int)L, x.base, (int)L, nf, d_conv_in_w_, d_conv_in_b_, 7, 1, 6, B, c, /*reflect=*/1, x.stride);
   } else {
@@ -450,14 +627,14 @@ void EncodecEngine::run_encoder(const float* audio, int B, int64_t L, int64_t* T
   for (size_t i = 0; i < enc_res_.size(); ++i) {
     const int r = cfg_.ratios[cfg_.ratios.size() - 1 - i];
     Act y = run_res(*enc_res_[i], x, B, xb, sb, hb, /*post_elu=*/true);
-    const SPad pd = sconv_pad(y.T, 2 * r, r);                            // padding_total = k - stride = r (left), extra (right)
+    const SPad pd = sconv_pad(y.T, 2 * r, r);                            // padding_total = k - stride = r, + the alignment extra
     const int ob = pick_free(xb, -1);
     Act o = act(ob, B, pd.t_out, 2 * y.C);
     if (pd.extra_zero == 0) {
       launch_reflect_pad(y.base, y.T, y.C, y.stride, pd.left, pd.right, B, c);
-      conv(*enc_down_[i], y, pd.left, pd.right, o, B, PRO_NONE, PRO_NONE, nullptr);
+      conv_n(*enc_down_[i], y, pd.left, pd.right, o, B, PRO_NONE, PRO_NONE, nullptr);
     } else {
-      conv_short(*enc_down_[i], y, pd, o, B, PRO_NONE, PRO_NONE);        // y.T <= r: Pad1d's short-input branch
+      conv_short_n(*enc_down_[i], y, pd, o, B, PRO_NONE, PRO_NONE);      // y.T <= the pad: Pad1d's short-input branch
     }
     x = o;
     xb = ob;
@@ -471,17 +648,13 @@ void EncodecEngine::run_encoder(const float* audio, int B, int64_t L, int64_t* T
     prologue = PRO_NONE;
   }
   const SPad pf = sconv_pad(top.T, 7, 1);
+  Act zo;
+  zo.base = z_.as<float>(); zo.T = pf.t_out; zo.C = cfg_.dimension; zo.stride = (long long)pf.t_out * cfg_.dimension;
   if (pf.extra_zero == 0) {
-    launch_reflect_pad(top.base, top.T, top.C, top.stride, 6, 0, B, c);
-    ConvRunArgs a;
-    a.in = top.base - (long long)6 * top.C; a.in_clip_stride = top.stride; a.t_in = top.T + 6; a.batch = B;
-    a.out = z_.as<float>(); a.out_clip_stride = (long long)top.T * cfg_.dimension;
-    a.prologue = prologue;
-    enc_out_.run(a, c);
-  } else {                                                               // fewer than 7 frames: the final conv lengthens z
-    Act zo;
-    zo.base = z_.as<float>(); zo.T = pf.t_out; zo.C = cfg_.dimension; zo.stride = (long long)pf.t_out * cfg_.dimension;
-    conv_short(enc_out_, top, pf, zo, B, prologue, PRO_NONE);
+    launch_reflect_pad(top.base, top.T, top.C, top.stride, pf.left, pf.right, B, c);
+    conv_n(enc_out_, top, pf.left, pf.right, zo, B, prologue, PRO_NONE, nullptr);
+  } else {                                                               // fewer frames than the pad: the final conv lengthens z
+    conv_short_n(enc_out_, top, pf, zo, B, prologue, PRO_NONE);
   }
   *T_out = pf.t_out;
 }
@@ -497,10 +670,10 @@ void EncodecEngine::run_decoder(int B, int T, float* audio_out, long long out_st
   Act x = act(ob, B, pz.t_out, top);
   const bool has_lstm = cfg_.lstm_layers > 0;
   if (pz.extra_zero == 0) {
-    launch_reflect_pad(z.base, z.T, z.C, z.stride, 6, 0, B, c);
-    conv(dec_in_, z, 6, 0, x, B, PRO_NONE, has_lstm ? PRO_NONE : PRO_ELU, nullptr);
+    launch_reflect_pad(z.base, z.T, z.C, z.stride, pz.left, pz.right, B, c);
+    conv_n(dec_in_, z, pz.left, pz.right, x, B, PRO_NONE, has_lstm ? PRO_NONE : PRO_ELU, nullptr);
   } else {
-    conv_short(dec_in_, z, pz, x, B, PRO_NONE, has_lstm ? PRO_NONE : PRO_ELU);   // T <= 6 frames: short-input branch
+    conv_short_n(dec_in_, z, pz, x, B, PRO_NONE, has_lstm ? PRO_NONE : PRO_ELU);   // T <= the pad: short-input branch
   }
   xb = ob;
   if (has_lstm) {
@@ -511,14 +684,41 @@ void EncodecEngine::run_decoder(int B, int T, float* audio_out, long long out_st
   for (size_t i = 0; i < dec_up_.size(); ++i) {
     const int r = cfg_.ratios[i];
     const int ub = pick_free(xb, -1);
-    Act u = act(ub, B, x.T * r, x.C / 2);   // conv_transpose1d yields (T+1)*r rows; the last r land in the margin = trimmed
-    conv(*dec_up_[i], x, 0, 0, u, B, PRO_NONE, PRO_NONE, nullptr);
+    // SConvTranspose1d (SConvTranspose1d.cs:116-139): conv_transpose1d yields (T+1)*r rows, GroupNorm (if any) sees all of
+    // them, then padding_total = r rows are trimmed: all on the right (causal) or r - r/2 left, r/2 right.  The trimmed rows
+    // land in the margins of u.
+    const int trim_right = cfg_.causal ? r : r / 2, trim_left = r - trim_right;
+    Act u = act(ub, B, x.T * r, x.C / 2);
+    conv_n(*dec_up_[i], x, 0, 0, u, B, PRO_NONE, PRO_NONE, nullptr, -trim_left, (x.T + 1) * r);
     xb = ub;
     x = run_res(*dec_res_[i], u, B, xb, sb, hb, /*post_elu=*/true);
   }
-  // SConv1d(32, 1, 7) causal: reflect handled by index reflection in the Cout = 1 kernel
-  launch_conv_cout1(x.base, audio_out, x.T, conv_out_c_, d_conv_out_w_, d_conv_out_b_, 7, 6, 0, B, c, /*reflect=*/1, x.stride);
-  (void)out_stride;
+  if (!generic_io_) {
+    // SConv1d(32, 1, 7) causal: reflect handled by index reflection in the Cout = 1 kernel
+    launch_conv_cout1(x.base, audio_out, x.T, conv_out_c_, d_conv_out_w_, d_conv_out_b_, 7, 6, 0, B, c, /*reflect=*/1, x.stride);
+    (void)out_stride;
+    return;
+  }
+  // SConv1d(n_filters, channels, 7) on the padded-N layer, then GroupNorm over the real channels, * scale (Encodec.cs:448-451)
+  // and the planar frame for the overlap-add
+  const SPad po = sconv_pad(x.T, 7, 1);
+  const int rb = pick_free(xb, -1);
+  Act raw = act(rb, B, po.t_out, cout_pad_);
+  if (po.extra_zero == 0) {
+    launch_reflect_pad(x.base, x.T, x.C, x.stride, po.left, po.right, B, c);
+    conv(conv_out_l_, x, po.left, po.right, raw, B, PRO_NONE, PRO_NONE, nullptr);
+  } else {
+    conv_short(conv_out_l_, x, po, raw, B, PRO_NONE, PRO_NONE);
+  }
+  const double* st = nullptr;
+  const float *gamma = nullptr, *beta = nullptr;
+  if (cfg_.group_norm) {
+    const Gn& g = gn_.at(conv_out_l_.name());
+    launch_gn_stats(raw.base, raw.stride, (long long)raw.T * raw.C, gn_stats_.as<double>(), B, c);
+    st = gn_stats_.as<double>(); gamma = g.gamma; beta = g.beta;
+  }
+  launch_encodec_frame_out(raw.base, raw.stride, raw.T, cout_pad_, cfg_.channels, st, 1e-5f, gamma, beta, map_.segs, map_.s0,
+                           map_.item0, map_.n_seg, map_.scales, audio_out, out_stride, B, c);
 }
 
 // ------------------------------------------------------------------------------------ entry points
@@ -529,6 +729,7 @@ void EncodecEngine::encode_dev(const float* audio, int B, int64_t L, int nq, int
 void EncodecEngine::forward_dev(const float* audio, int B, int64_t L, int nq, float* audio_out, int64_t* codes) {
   require_ready();
   bind();
+  if (!simple()) { forward_frames_dev(audio, B, L, nq, audio_out, codes, nullptr); return; }
   if (B <= 0 || L <= 0) throw Error(NC_INVALID_ARGUMENT, "batch and length must be positive");
   if (nq <= 0 || nq > (int)embed_.size()) throw Error(NC_INVALID_ARGUMENT, "n_quantizers out of range");
   if (L > (int64_t)1 << 28) throw Error(NC_INVALID_ARGUMENT, "clip too long");
@@ -558,6 +759,7 @@ void EncodecEngine::forward_dev(const float* audio, int B, int64_t L, int nq, fl
 void EncodecEngine::decode_dev(const int64_t* codes, int B, int nq, int64_t T, float* audio_out) {
   require_ready();
   bind();
+  if (!simple()) { decode_frames_dev(codes, nullptr, B, nq, &T, 1, audio_out); return; }
   if (B <= 0 || T <= 0 || !codes) throw Error(NC_INVALID_ARGUMENT, "Invalid frame codes in Encodec Decode");
   if (nq <= 0 || nq > (int)embed_.size()) throw Error(NC_INVALID_ARGUMENT, "n_quantizers out of range");
   const int64_t L = decoded_length(T);
@@ -573,6 +775,89 @@ void EncodecEngine::decode_dev(const int64_t* codes, int B, int nq, int64_t T, f
   sync();
 }
 
+// One group of equal-length segments, micro-batched over its B*segs items: prep (loudness scale, channels-last) -> encoder
+// -> RVQ -> codes into the caller's layout; and / or codes -> decoder -> scaled planar frames for the overlap-add.
+void EncodecEngine::run_group(const float* audio, int B, int64_t L, const SegLayout& lay, const Group& g, int nq, int64_t* codes_user,
+                              float* scales, bool encode, bool decode) {
+  const LaunchCtx c = ctx();
+  const int items = B * g.segs;
+  const int64_t T = g.frames;
+  const int64_t Ld = decoded_length(T);
+  const int mb = micro_batch(items, encode ? g.len : Ld);
+  codes_tmp_.reserve((size_t)mb * nq * T * sizeof(int64_t));
+  int64_t* dense = codes_tmp_.as<int64_t>();
+  for (int i0 = 0; i0 < items; i0 += mb) {
+    const int nb = std::min(mb, items - i0);
+    if (encode) {
+      Act in = act(1, nb, (int)g.len, cin_pad_);
+      launch_encodec_segment_prep(audio, cfg_.channels, L, g.segs, g.s0, lay.stride, (int)g.len, i0, lay.n_seg,
+                                  cfg_.normalize ? scales : nullptr, in.base, in.stride, cin_pad_, nb, c);
+      int64_t Tm = 0;
+      run_encoder(nullptr, nb, g.len, &Tm);
+      if (Tm != T) throw Error(NC_INTERNAL, "Encodec: frame count mismatch");
+      for (int q = 0; q < nq; ++q)
+        launch_encodec_vq_stage(z_.as<float>(), (long long)nb * T, embed_[q], embed_sq_[q], cfg_.codebook_size, cfg_.dimension,
+                                dense, (int)T, nq, q, c);
+      if (codes_user) launch_encodec_codes_segment_copy(dense, codes_user, g.segs, i0, nq, (int)T, lay.t_total, g.col0, 1, nb, c);
+    } else {
+      launch_encodec_codes_segment_copy(dense, codes_user, g.segs, i0, nq, (int)T, lay.t_total, g.col0, 0, nb, c);
+    }
+    if (decode) {
+      Act z = act(0, nb, (int)T, cfg_.dimension);
+      launch_encodec_decode_codes(dense, d_embed_ptrs_, z.base, z.stride, nb, (int)T, nq, cfg_.codebook_size, cfg_.dimension, c);
+      map_.segs = g.segs; map_.s0 = g.s0; map_.item0 = i0; map_.n_seg = lay.n_seg;
+      map_.scales = scales;            // frames without a scale decode unscaled (Encodec.cs:448-451)
+      run_decoder(nb, (int)T, frames_.as<float>(), lay.ld_max);
+    }
+  }
+}
+
+void EncodecEngine::overlap_add(const SegLayout& lay, int B, float* audio_out, int64_t out_len) {
+  std::vector<int> lens(lay.ld.begin(), lay.ld.end());
+  int* d = static_cast<int*>(seg_lens_.reserve(lens.size() * sizeof(int)));
+  NC_CUDA(cudaMemcpyAsync(d, lens.data(), lens.size() * sizeof(int), cudaMemcpyHostToDevice, stream_));
+  NC_CUDA(cudaStreamSynchronize(stream_));   // `lens` is a stack vector
+  launch_encodec_overlap_add(frames_.as<float>(), B, lay.n_seg, cfg_.channels, lay.ld_max, d, (int)lay.ld_max, lay.stride,
+                             segmented() ? 1 : 0, audio_out, out_len, ctx());
+}
+
+void EncodecEngine::forward_frames_dev(const float* audio, int B, int64_t L, int nq, float* audio_out, int64_t* codes, float* scales) {
+  require_ready();
+  bind();
+  if (simple()) throw Error(NC_INTERNAL, "forward_frames_dev on the single-frame path");
+  if (B <= 0 || L <= 0 || !audio) throw Error(NC_INVALID_ARGUMENT, "batch and length must be positive");
+  if (nq <= 0 || nq > (int)embed_.size()) throw Error(NC_INVALID_ARGUMENT, "n_quantizers out of range");
+  if (L > (int64_t)1 << 28) throw Error(NC_INVALID_ARGUMENT, "clip too long");
+  const SegLayout lay = seg_layout(L);
+  if (audio_out) check_overlap_add(lay);
+  if (!cfg_.normalize) scales = nullptr;
+  else if (!scales) scales = static_cast<float*>(scales_.reserve((size_t)B * lay.n_seg * sizeof(float)));
+  if (audio_out) frames_.reserve((size_t)B * lay.n_seg * cfg_.channels * lay.ld_max * sizeof(float));
+  for (const Group& g : groups_of(lay)) run_group(audio, B, L, lay, g, nq, codes, scales, /*encode=*/true, /*decode=*/audio_out != nullptr);
+  if (audio_out) overlap_add(lay, B, audio_out, std::min<int64_t>(L, lay.total_out));   // Encodec.cs:295: sliced to the input length
+  sync();
+}
+
+void EncodecEngine::decode_frames_dev(const int64_t* codes, const float* scales, int B, int nq, const int64_t* seg_frames, int n_seg,
+                                      float* audio_out) {
+  require_ready();
+  bind();
+  if (simple()) {
+    if (n_seg != 1 || !seg_frames) throw Error(NC_INVALID_ARGUMENT, "Expected single frame when no segmentation is used");
+    decode_dev(codes, B, nq, seg_frames[0], audio_out);
+    return;
+  }
+  if (B <= 0 || !codes || !audio_out) throw Error(NC_INVALID_ARGUMENT, "Invalid frame codes in Encodec Decode");
+  if (nq <= 0 || nq > (int)embed_.size()) throw Error(NC_INVALID_ARGUMENT, "n_quantizers out of range");
+  const SegLayout lay = seg_layout_from_frames(seg_frames, n_seg);
+  check_overlap_add(lay);
+  frames_.reserve((size_t)B * lay.n_seg * cfg_.channels * lay.ld_max * sizeof(float));
+  for (const Group& g : groups_of(lay))
+    run_group(nullptr, B, 0, lay, g, nq, const_cast<int64_t*>(codes), const_cast<float*>(scales), /*encode=*/false, /*decode=*/true);
+  overlap_add(lay, B, audio_out, lay.total_out);
+  sync();
+}
+
 int EncodecEngine::bits_per_codebook() const {
   int bits = 0;
   while ((1 << bits) < cfg_.codebook_size) ++bits;
@@ -580,9 +865,24 @@ int EncodecEngine::bits_per_codebook() const {
   return bits;
 }
 
+void EncodecEngine::ecdc_pack_segment_dev(const int64_t* codes, int64_t t_total, int64_t col, int64_t T, int nq, uint8_t* bytes,
+                                          int64_t stride, int B) {
+  bind();
+  launch_ecdc_pack(codes + col, bytes, stride, B, (int)T, nq, bits_per_codebook(), ctx(), t_total, (long long)nq * t_total);
+  sync();
+}
+
+void EncodecEngine::ecdc_unpack_segment_dev(const uint8_t* bytes, int64_t stride, int64_t* codes, int64_t t_total, int64_t col,
+                                            int64_t T, int nq, int B) {
+  bind();
+  launch_ecdc_unpack(bytes, stride, codes + col, B, (int)T, nq, bits_per_codebook(), ctx(), t_total, (long long)nq * t_total);
+  sync();
+}
+
 void EncodecEngine::compress_dev(const float* audio, int B, int64_t L, int nq, uint8_t* payload, int64_t stride) {
   require_ready();
   bind();
+  if (!simple()) throw Error(NC_INTERNAL, "compress_dev is the single-frame path");
   if (B <= 0 || L <= 0 || !audio) throw Error(NC_INVALID_ARGUMENT, "batch and length must be positive");
   if (nq <= 0 || nq > (int)embed_.size()) throw Error(NC_INVALID_ARGUMENT, "n_quantizers out of range");
   if (L > (int64_t)1 << 28) throw Error(NC_INVALID_ARGUMENT, "clip too long");
@@ -608,6 +908,7 @@ void EncodecEngine::compress_dev(const float* audio, int B, int64_t L, int nq, u
 void EncodecEngine::decompress_dev(const uint8_t* payload, int64_t stride, int B, int nq, int64_t L, float* audio_out) {
   require_ready();
   bind();
+  if (!simple()) throw Error(NC_INTERNAL, "decompress_dev is the single-frame path");
   if (B <= 0 || L <= 0 || !payload || !audio_out) throw Error(NC_INVALID_ARGUMENT, "Invalid ecdc payload");
   if (nq <= 0 || nq > (int)embed_.size()) throw Error(NC_INVALID_ARGUMENT, "n_quantizers out of range");
   // frameLength = ceil(L * frame_rate / sample_rate) (EncodecCompressor.cs:296-297), frame_rate = ceil(sr / hop)

@@ -386,7 +386,7 @@ void launch_lstm_layer(const float* xproj, long long xproj_clip_stride, const fl
 // emits the low byte whenever 8 bits are available; Flush() emits the last partial byte.  Equivalent closed form:
 // value v = t*nq + k occupies stream bits [v*bits, (v+1)*bits); byte j is bits [8j, 8j+8).  One thread per output byte.
 __global__ void ecdc_pack_kernel(const int64_t* __restrict__ codes, uint8_t* __restrict__ out, long long out_stride, int T, int nq,
-                                 int bits, long long nbytes) {
+                                 int bits, long long nbytes, long long row_stride, long long clip_stride) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (j >= nbytes) return;
@@ -394,11 +394,11 @@ __global__ void ecdc_pack_kernel(const int64_t* __restrict__ codes, uint8_t* __r
   const long long bit0 = j * 8;
   long long v = bit0 / bits;
   const long long v_last = min((bit0 + 7) / bits, nvals - 1);
-  const int64_t* cb = codes + (long long)b * nq * T;
+  const int64_t* cb = codes + (long long)b * clip_stride;
   unsigned int byte = 0;
   for (; v <= v_last; ++v) {
     const int t = (int)(v / nq), k = (int)(v % nq);
-    const unsigned long long val = (unsigned long long)cb[(long long)k * T + t] & ((1ull << bits) - 1ull);
+    const unsigned long long val = (unsigned long long)cb[(long long)k * row_stride + t] & ((1ull << bits) - 1ull);
     const long long sh = v * bits - bit0;   // position of the value's bit 0 relative to this byte
     byte |= (unsigned int)((sh >= 0 ? (val << sh) : (val >> (-sh))) & 0xFFull);
   }
@@ -407,7 +407,7 @@ __global__ void ecdc_pack_kernel(const int64_t* __restrict__ codes, uint8_t* __r
 
 // One thread per value: gather the (at most 5) bytes it straddles, shift, mask (BitUnpacker.Pull, BitUnpacker.cs:60-95).
 __global__ void ecdc_unpack_kernel(const uint8_t* __restrict__ in, long long in_stride, int64_t* __restrict__ codes, int T, int nq,
-                                   int bits, long long nbytes) {
+                                   int bits, long long nbytes, long long row_stride, long long clip_stride) {
   const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (v >= (long long)T * nq) return;
@@ -420,32 +420,294 @@ __global__ void ecdc_unpack_kernel(const uint8_t* __restrict__ in, long long in_
   for (int i = 0; i < need; ++i)
     if (j0 + i < nbytes) w |= (unsigned long long)src[j0 + i] << (8 * i);
   const int t = (int)(v / nq), k = (int)(v % nq);
-  codes[(long long)b * nq * T + (long long)k * T + t] = (int64_t)((w >> off) & ((1ull << bits) - 1ull));
+  codes[(long long)b * clip_stride + (long long)k * row_stride + t] = (int64_t)((w >> off) & ((1ull << bits) - 1ull));
 }
 
 void launch_ecdc_pack(const int64_t* codes, uint8_t* out, long long out_stride, int batch, int T, int nq, int bits,
-                      const LaunchCtx& ctx) {
+                      const LaunchCtx& ctx, long long row_stride, long long clip_stride) {
+  if (row_stride == 0) row_stride = T;
+  if (clip_stride == 0) clip_stride = (long long)nq * T;
   if (bits <= 0 || bits > 32) throw Error(NC_INVALID_ARGUMENT, "Bits must be between 1 and 32");   // BitPacker.cs:120-130
   const long long nbytes = ((long long)T * nq * bits + 7) / 8;
   if (batch == 0 || nbytes == 0) return;
   const int ev = ctx.begin();
   dim3 grid((unsigned)((nbytes + 255) / 256), batch);
-  ecdc_pack_kernel<<<grid, 256, 0, ctx.stream>>>(codes, out, out_stride, T, nq, bits, nbytes);
+  ecdc_pack_kernel<<<grid, 256, 0, ctx.stream>>>(codes, out, out_stride, T, nq, bits, nbytes, row_stride, clip_stride);
   check_launch((int)cudaGetLastError(), "ecdc_pack");
   ctx.end(ev, "ecdc_pack", 0.0, (double)batch * ((double)T * nq * 8 + nbytes));
 }
 
 void launch_ecdc_unpack(const uint8_t* in, long long in_stride, int64_t* codes, int batch, int T, int nq, int bits,
-                        const LaunchCtx& ctx) {
+                        const LaunchCtx& ctx, long long row_stride, long long clip_stride) {
+  if (row_stride == 0) row_stride = T;
+  if (clip_stride == 0) clip_stride = (long long)nq * T;
   if (bits <= 0 || bits > 32) throw Error(NC_INVALID_ARGUMENT, "Bits must be between 1 and 32");
   const long long nvals = (long long)T * nq;
   if (batch == 0 || nvals == 0) return;
   const long long nbytes = (nvals * bits + 7) / 8;
   const int ev = ctx.begin();
   dim3 grid((unsigned)((nvals + 255) / 256), batch);
-  ecdc_unpack_kernel<<<grid, 256, 0, ctx.stream>>>(in, in_stride, codes, T, nq, bits, nbytes);
+  ecdc_unpack_kernel<<<grid, 256, 0, ctx.stream>>>(in, in_stride, codes, T, nq, bits, nbytes, row_stride, clip_stride);
   check_launch((int)cudaGetLastError(), "ecdc_unpack");
   ctx.end(ev, "ecdc_unpack", 0.0, (double)batch * ((double)nvals * 8 + nbytes));
+}
+
+// ------------------------------------------------------------------------------ 48 kHz preset: GroupNorm(1, C), segments
+// time_group_norm (NormConv1d.cs:136-160): one mean / variance per clip over (C, T).  Pass 1: per-thread fp32 partials over
+// at most kGnPerThread elements, block reduction and the cross-block sum in fp64.
+constexpr int kGnChunk = 16384;   // floats per block
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const float* __restrict__ x, long long clip_stride, long long n, double* __restrict__ stats) {
+  const int b = blockIdx.y;
+  const float4* p = reinterpret_cast<const float4*>(x + (long long)b * clip_stride);
+  const long long n4 = n >> 2;
+  const long long i0 = (long long)blockIdx.x * (kGnChunk / 4), i1 = min(i0 + kGnChunk / 4, n4);
+  float s = 0.f, ss = 0.f;
+  for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
+    const float4 v = __ldg(p + i);
+    s += (v.x + v.y) + (v.z + v.w);
+    ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+  double ds = s, dss = ss;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ds += __shfl_xor_sync(0xffffffffu, ds, o);
+    dss += __shfl_xor_sync(0xffffffffu, dss, o);
+  }
+  __shared__ double sh[2][8];
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = ds; sh[1][threadIdx.x >> 5] = dss; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a += sh[0][i]; c += sh[1][i]; }
+    atomicAdd(stats + 2 * b, a);
+    atomicAdd(stats + 2 * b + 1, c);
+  }
+}
+
+void launch_gn_stats(const float* x, long long clip_stride, long long n_per_clip, double* stats, int batch, const LaunchCtx& ctx) {
+  if (batch == 0 || n_per_clip == 0) return;
+  if (n_per_clip % 4 != 0) throw Error(NC_INTERNAL, "gn_stats: row width must be a multiple of 4");
+  NC_CUDA(cudaMemsetAsync(stats, 0, (size_t)batch * 2 * sizeof(double), ctx.stream));
+  const int ev = ctx.begin();
+  dim3 grid((unsigned)((n_per_clip + kGnChunk - 1) / kGnChunk), batch);
+  gn_stats_kernel<<<grid, 256, 0, ctx.stream>>>(x, clip_stride, n_per_clip, stats);
+  check_launch((int)cudaGetLastError(), "gn_stats");
+  ctx.end(ev, "gn_stats", 0.0, 4.0 * batch * (double)n_per_clip);
+}
+
+__device__ __forceinline__ void gn_coeffs(const double* stats, int b, double count, float eps, float& mean, float& rstd) {
+  const double m = stats[2 * b] / count;
+  const double var = fmax(stats[2 * b + 1] / count - m * m, 0.0);
+  mean = (float)m;
+  rstd = (float)(1.0 / sqrt(var + (double)eps));
+}
+__device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expm1f(v); }
+
+// Pass 2, in place over rows [0, T): y = (x - mean) * rstd * gamma[c] + beta[c] (+ residual) (-> ELU)
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(float* __restrict__ y, long long clip_stride, int T, int C, const double* __restrict__ stats, double count, float eps,
+                const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ residual,
+                long long res_clip_stride, int elu) {
+  const int b = blockIdx.y, c4n = C >> 2;
+  float mean, rstd;
+  gn_coeffs(stats, b, count, eps, mean, rstd);
+  float4* p = reinterpret_cast<float4*>(y + (long long)b * clip_stride);
+  const float4* r = residual ? reinterpret_cast<const float4*>(residual + (long long)b * res_clip_stride) : nullptr;
+  const long long n4 = (long long)T * c4n;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    const int c4 = (int)(i % c4n);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4), be = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+    float4 v = p[i];
+    v.x = (v.x - mean) * rstd * g.x + be.x; v.y = (v.y - mean) * rstd * g.y + be.y;
+    v.z = (v.z - mean) * rstd * g.z + be.z; v.w = (v.w - mean) * rstd * g.w + be.w;
+    if (r) { const float4 q = __ldg(r + i); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
+    if (elu) { v.x = elu1(v.x); v.y = elu1(v.y); v.z = elu1(v.z); v.w = elu1(v.w); }
+    p[i] = v;
+  }
+}
+
+void launch_gn_apply(float* y, long long clip_stride, int T, int C, const double* stats, double count, float eps, const float* gamma,
+                     const float* beta, const float* residual, long long res_clip_stride, int elu, int batch, const LaunchCtx& ctx) {
+  if (batch == 0 || T == 0) return;
+  if (C % 4 != 0) throw Error(NC_INTERNAL, "gn_apply: channel count must be a multiple of 4");
+  const long long n4 = (long long)T * (C / 4);
+  const int ev = ctx.begin();
+  dim3 grid((unsigned)std::min<long long>((n4 + 1023) / 1024, 8LL * ctx.num_sms), batch);
+  gn_apply_kernel<<<grid, 256, 0, ctx.stream>>>(y, clip_stride, T, C, stats, count, eps, gamma, beta, residual, res_clip_stride, elu);
+  check_launch((int)cudaGetLastError(), "gn_apply");
+  ctx.end(ev, "gn_apply", 0.0, (residual ? 12.0 : 8.0) * batch * (double)T * C);
+}
+
+// Segment item i of a launch = global item item0 + i -> clip b = item / segs, segment s = s0 + item % segs, samples
+// [s * seg_stride, s * seg_stride + seg_len) of audio [B][C][L].
+// Loudness scale (Encodec.cs:469-480): sqrt(mean_t (mean_c x)^2) + 1e-8, one block per item, fp64 accumulation.
+__global__ void __launch_bounds__(256)
+segment_scale_kernel(const float* __restrict__ audio, int C, long long L, int segs, int s0, long long seg_stride, int seg_len,
+                     int item0, int n_seg_total, float* __restrict__ scales) {
+  const int item = item0 + blockIdx.x, b = item / segs, s = s0 + item % segs;
+  const float* x = audio + (long long)b * C * L + (long long)s * seg_stride;
+  double acc = 0;
+  for (int t = threadIdx.x; t < seg_len; t += 256) {
+    float m = 0.f;
+    for (int c = 0; c < C; ++c) m += x[(long long)c * L + t];
+    m /= (float)C;
+    acc += (double)(m * m);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ double sh[8];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a += sh[i];
+    scales[(long long)b * n_seg_total + s] = sqrtf((float)(a / seg_len)) + 1e-8f;
+  }
+}
+
+// planar [B][C][L] segment -> channels-last rows [seg_len][Cpad] (channels >= C zero), divided by the item's scale
+__global__ void __launch_bounds__(256)
+segment_prep_kernel(const float* __restrict__ audio, int C, long long L, int segs, int s0, long long seg_stride, int seg_len, int item0,
+                    int n_seg_total, const float* __restrict__ scales, float* __restrict__ out, long long out_clip_stride, int Cpad) {
+  const int i = blockIdx.y, item = item0 + i, b = item / segs, s = s0 + item % segs;
+  const float* x = audio + (long long)b * C * L + (long long)s * seg_stride;
+  const float sc = scales ? scales[(long long)b * n_seg_total + s] : 1.f;
+  float* o = out + (long long)i * out_clip_stride;
+  const long long n = (long long)seg_len * Cpad;
+  for (long long j = (long long)blockIdx.x * 256 + threadIdx.x; j < n; j += (long long)gridDim.x * 256) {
+    const int c = (int)(j % Cpad);
+    const long long t = j / Cpad;
+    float v = 0.f;
+    if (c < C) { v = x[(long long)c * L + t]; if (scales) v = v / sc; }
+    o[j] = v;
+  }
+}
+
+void launch_encodec_segment_prep(const float* audio, int C, long long L, int segs, int s0, long long seg_stride, int seg_len, int item0,
+                                 int n_seg_total, float* scales, float* out, long long out_clip_stride, int Cpad, int items,
+                                 const LaunchCtx& ctx) {
+  if (items == 0 || seg_len == 0) return;
+  const int ev = ctx.begin();
+  if (scales) {
+    segment_scale_kernel<<<items, 256, 0, ctx.stream>>>(audio, C, L, segs, s0, seg_stride, seg_len, item0, n_seg_total, scales);
+    check_launch((int)cudaGetLastError(), "segment_scale");
+  }
+  const long long n = (long long)seg_len * Cpad;
+  dim3 grid((unsigned)std::min<long long>((n + 1023) / 1024, 4LL * ctx.num_sms), items);
+  segment_prep_kernel<<<grid, 256, 0, ctx.stream>>>(audio, C, L, segs, s0, seg_stride, seg_len, item0, n_seg_total, scales, out,
+                                                    out_clip_stride, Cpad);
+  check_launch((int)cudaGetLastError(), "segment_prep");
+  if (ctx.launches && scales) ++*ctx.launches;
+  ctx.end(ev, "segment_prep", 0.0, 4.0 * items * (double)seg_len * (C * (scales ? 2 : 1) + Cpad));
+}
+
+// last decoder conv's raw rows [T][Cpad] -> (GroupNorm over the C real channels) * scale -> planar frame [C][frame_ld]
+__global__ void __launch_bounds__(256)
+frame_out_kernel(const float* __restrict__ raw, long long clip_stride, int T, int Cpad, int C, const double* __restrict__ stats, float eps,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, int segs, int s0, int item0, int n_seg_total,
+                 const float* __restrict__ scales, float* __restrict__ frames, long long frame_ld) {
+  const int i = blockIdx.y, item = item0 + i, b = item / segs, s = s0 + item % segs;
+  float mean = 0.f, rstd = 1.f;
+  if (stats) gn_coeffs(stats, i, (double)T * C, eps, mean, rstd);
+  const float sc = scales ? scales[(long long)b * n_seg_total + s] : 1.f;
+  const float* x = raw + (long long)i * clip_stride;
+  float* o = frames + ((long long)b * n_seg_total + s) * C * frame_ld;
+  for (long long j = (long long)blockIdx.x * 256 + threadIdx.x; j < (long long)T * C; j += (long long)gridDim.x * 256) {
+    const int c = (int)(j / T);
+    const int t = (int)(j - (long long)c * T);
+    float v = x[(long long)t * Cpad + c];
+    if (stats) v = (v - mean) * rstd * gamma[c] + beta[c];
+    if (scales) v = v * sc;
+    o[(long long)c * frame_ld + t] = v;
+  }
+}
+
+void launch_encodec_frame_out(const float* raw, long long clip_stride, int T, int Cpad, int C, const double* stats, float eps,
+                              const float* gamma, const float* beta, int segs, int s0, int item0, int n_seg_total, const float* scales,
+                              float* frames, long long frame_ld, int items, const LaunchCtx& ctx) {
+  if (items == 0 || T == 0) return;
+  const long long n = (long long)T * C;
+  const int ev = ctx.begin();
+  dim3 grid((unsigned)std::min<long long>((n + 1023) / 1024, 4LL * ctx.num_sms), items);
+  frame_out_kernel<<<grid, 256, 0, ctx.stream>>>(raw, clip_stride, T, Cpad, C, stats, eps, gamma, beta, segs, s0, item0, n_seg_total,
+                                                 scales, frames, frame_ld);
+  check_launch((int)cudaGetLastError(), "frame_out");
+  ctx.end(ev, "frame_out", 0.0, 4.0 * items * (double)T * (Cpad + C));
+}
+
+// DSP.LinearOverlapAdd (AudioTensorDSP.cs:161-261): out[t] = (sum_s w[t - s*stride] * frame_s[t - s*stride]) / sum_s w[..],
+// w = 0.5 - |linspace(0, 1, len0 + 2)[1:-1] - 0.5| (torch's two-sided linspace), frames summed in ascending order from 0.
+// frames [B][n_seg][C][frame_ld]; frame s has lens[s] samples (device array).  segmented == 0: plain copy.
+__device__ __forceinline__ float ola_weight(int j, int len0) {
+  const int steps = len0 + 2, idx = j + 1;
+  const float step = 1.0f / (float)(steps - 1);
+  const float t = idx < steps / 2 ? step * (float)idx : 1.0f - step * (float)(steps - idx - 1);
+  return 0.5f - fabsf(t - 0.5f);
+}
+__global__ void __launch_bounds__(256)
+overlap_add_kernel(const float* __restrict__ frames, int n_seg, int C, long long frame_ld, const int* __restrict__ lens, int len_max,
+                   long long stride, int segmented, float* __restrict__ out, long long out_len) {
+  const int bc = blockIdx.y, b = bc / C, c = bc % C;
+  const int len0 = lens[0];
+  for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < out_len; t += (long long)gridDim.x * 256) {
+    float v;
+    if (!segmented) {
+      v = frames[((long long)b * n_seg * C + c) * frame_ld + t];
+    } else {
+      long long s_lo = t - (len_max - 1);
+      s_lo = s_lo <= 0 ? 0 : (s_lo + stride - 1) / stride;
+      const long long s_hi = min((long long)n_seg - 1, t / stride);
+      float acc = 0.f, wsum = 0.f;
+      for (long long s = s_lo; s <= s_hi; ++s) {
+        const int j = (int)(t - s * stride);
+        if (j >= lens[s]) continue;
+        const float w = ola_weight(j, len0);
+        acc += frames[(((long long)b * n_seg + s) * C + c) * frame_ld + j] * w;
+        wsum += w;
+      }
+      v = acc / wsum;
+    }
+    out[(long long)bc * out_len + t] = v;
+  }
+}
+
+void launch_encodec_overlap_add(const float* frames, int batch, int n_seg, int C, long long frame_ld, const int* lens_dev, int len_max,
+                                long long stride, int segmented, float* out, long long out_len, const LaunchCtx& ctx) {
+  if (batch == 0 || out_len == 0) return;
+  const int ev = ctx.begin();
+  dim3 grid((unsigned)std::min<long long>((out_len + 1023) / 1024, 8LL * ctx.num_sms), batch * C);
+  overlap_add_kernel<<<grid, 256, 0, ctx.stream>>>(frames, n_seg, C, frame_ld, lens_dev, len_max, stride, segmented, out, out_len);
+  check_launch((int)cudaGetLastError(), "overlap_add");
+  ctx.end(ev, "overlap_add", 0.0, 8.0 * batch * C * (double)out_len);
+}
+
+// codes of `items` segment items (item = b*segs + j), dense [items][nq][T]  <->  the caller's [B][nq][T_total] with the
+// group's j-th segment at column col0 + j*T
+__global__ void __launch_bounds__(256)
+codes_segment_copy_kernel(int64_t* __restrict__ dense, int64_t* __restrict__ user, int segs, int item0, int nq, int T,
+                          long long T_total, long long col0, int to_user, long long n) {
+  for (long long j = (long long)blockIdx.x * 256 + threadIdx.x; j < n; j += (long long)gridDim.x * 256) {
+    const int t = (int)(j % T);
+    const long long r = j / T;
+    const int q = (int)(r % nq), i = (int)(r / nq);
+    const int item = item0 + i, b = item / segs, j_seg = item % segs;
+    const long long u = ((long long)b * nq + q) * T_total + col0 + (long long)j_seg * T + t;
+    if (to_user) user[u] = dense[j]; else dense[j] = user[u];
+  }
+}
+
+void launch_encodec_codes_segment_copy(int64_t* dense, int64_t* user, int segs, int item0, int nq, int T, long long T_total,
+                                       long long col0, int to_user, int items, const LaunchCtx& ctx) {
+  const long long n = (long long)items * nq * T;
+  if (n == 0) return;
+  const int ev = ctx.begin();
+  codes_segment_copy_kernel<<<(unsigned)std::min<long long>((n + 255) / 256, 2048), 256, 0, ctx.stream>>>(dense, user, segs, item0, nq, T,
+                                                                                                         T_total, col0, to_user, n);
+  check_launch((int)cudaGetLastError(), "codes_segment_copy");
+  ctx.end(ev, "codes_segment_copy", 0.0, 16.0 * n);
 }
 
 int lstm_max_batch(int num_sms, int H) { return (num_sms / (H / kLU)) * kLB; }

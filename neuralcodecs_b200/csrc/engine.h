@@ -3,6 +3,7 @@
 #include <atomic>
 #include <memory>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "codec_kernels.h"
@@ -299,10 +300,20 @@ struct EncodecConfig {
   std::vector<int> ratios{8, 5, 4, 2};   // decoder order
   int n_residual_layers = 1, lstm_layers = 2, codebook_size = 1024, n_quantizers = 32;
   bool causal = true;
+  // 48 kHz preset (EncodecConfig.cs:37-66): GroupNorm(1, C) after every conv, loudness scale per frame, segments
+  bool group_norm = false, normalize = false;
+  float segment_s = 0.f, overlap = 0.01f;   // segment_s <= 0: one frame per clip
   int hop() const {
     int h = 1;
     for (int r : ratios) h *= r;
     return h;
+  }
+  // Models/Encodec.cs:190-196 (float32 products)
+  int64_t segment_length() const { return segment_s > 0.f ? (int64_t)(int)(segment_s * (float)sample_rate) : 0; }
+  int64_t segment_stride() const {
+    if (segment_s <= 0.f) return 0;
+    const int v = (int)((1.0f - overlap) * (float)(int)segment_length());
+    return v > 1 ? v : 1;
   }
 };
 
@@ -320,9 +331,29 @@ class EncodecEngine : public Engine {
   // samples Decode produces for T frames: T' * hop, T' = T except for T <= 6 where the first decoder conv takes the
   // short-input branch of Pad1d and lengthens the sequence (SConv1d.cs:258-272)
   int64_t decoded_length(int64_t T) const;
-  // padding one SConv1d applies to an input of T samples (kernel k, stride s, causal): SConv1d.cs:144-173,245-272
+  // padding one SConv1d applies to an input of T samples (kernel k, stride s): SConv1d.cs:144-173,245-272
   struct SPad { int extra_zero, left, right, t_out; };
-  static SPad sconv_pad(int64_t T, int k, int s);
+  static SPad sconv_pad(int64_t T, int k, int s, bool causal);
+  SPad sconv_pad(int64_t T, int k, int s) const { return sconv_pad(T, k, s, cfg_.causal); }
+  // Segment loop of Encodec.Encode / Decode (Encodec.cs:213-235,273-282): segment s covers samples
+  // [s*stride, min(s*stride + seg, L)); its codes sit at columns [col[s], col[s] + frames[s]) of the clip's [n_q][t_total] code
+  // matrix and its decoded frame (ld[s] samples) is overlap-added at s*stride.  The first n_full segments have the full length.
+  struct SegLayout {
+    int n_seg = 1, n_full = 0;
+    int64_t seg = 0, stride = 0, t_total = 0, total_out = 0, ld_max = 0;
+    std::vector<int64_t> len, frames, ld, col;
+  };
+  SegLayout seg_layout(int64_t L) const;
+  SegLayout seg_layout_from_frames(const int64_t* seg_frames, int n_seg) const;
+  bool segmented() const { return cfg_.segment_s > 0.f; }
+  // true: the 24 kHz-style engine path (mono, causal, weight-norm, one un-normalised frame per clip)
+  bool simple() const { return !generic_io_; }
+  // Device pointers.  audio [B][C][L]; codes [B][n_q][t_total] int64 (nullable); scales [B][n_seg] float (nullable; written only
+  // when the model normalises); audio_out [B][C][L] (forward: Decode(...) sliced to the input length, nullable = encode only).
+  void forward_frames_dev(const float* audio, int B, int64_t L, int nq, float* audio_out, int64_t* codes, float* scales);
+  // codes [B][n_q][sum seg_frames], scales [B][n_seg] (nullable) -> audio_out [B][C][total_out]
+  void decode_frames_dev(const int64_t* codes, const float* scales, int B, int nq, const int64_t* seg_frames, int n_seg,
+                         float* audio_out);
   int n_q_for_bandwidth(float kbps) const;             // ResidualVectorQuantizer.cs:133-144
 
   // device pointers.  codes [B][nq][T] int64; audio_out [B][T*hop] for decode, [B][L] (trimmed) for forward.
@@ -335,6 +366,11 @@ class EncodecEngine : public Engine {
   int64_t ecdc_payload_bytes(int nq, int64_t T) const { return ((int64_t)nq * T * bits_per_codebook() + 7) / 8; }
   // audio [B][L] -> payload [B][stride] bytes (EncodecCompressor.cs:93-190 with useLm=false)
   void compress_dev(const float* audio, int B, int64_t L, int nq, uint8_t* payload, int64_t stride);
+  // Segmented streams (EncodecCompressor.cs:116-190,303-400): per segment an optional scale block (int32 BE count, float32 BE
+  // values: written by the host) and the segment's codes packed on their own, zero-padded to a byte.  These pack / unpack
+  // ONE segment (columns [col, col+T) of codes [B][nq][t_total]) to / from bytes at `bytes` + b*stride, then synchronise.
+  void ecdc_pack_segment_dev(const int64_t* codes, int64_t t_total, int64_t col, int64_t T, int nq, uint8_t* bytes, int64_t stride, int B);
+  void ecdc_unpack_segment_dev(const uint8_t* bytes, int64_t stride, int64_t* codes, int64_t t_total, int64_t col, int64_t T, int nq, int B);
   // payload -> audio [B][L] trimmed to L = metadata "al" (EncodecCompressor.cs:288-420)
   void decompress_dev(const uint8_t* payload, int64_t stride, int B, int nq, int64_t L, float* audio_out);
 
@@ -346,8 +382,28 @@ class EncodecEngine : public Engine {
   };
   struct Res { ConvLayer shortcut, c3, c1; int hidden_p = 0; };
   struct Lstm { ConvLayer ih[2]; float* whh[2] = {nullptr, nullptr}; int layers = 0; };
-  static constexpr int kMargin = 8;
+  static constexpr int kMargin = 16;   // >= the largest reflect pad: causal k - s <= 8 left, non-causal s/2 + (s - 1) right
   void require_ready() const;
+  // GroupNorm affine of one conv (time_group_norm): gamma / beta padded like the conv's output channels
+  struct Gn { float* gamma = nullptr; float* beta = nullptr; int c_real = 0; };
+  std::unordered_map<std::string, Gn> gn_;
+  void load_gn(const std::string& p, int c_real, int c_pad);
+  // GroupNorm + follow-up of a conv's raw output `y` (no-op for weight-norm models, whose epilogue already did it):
+  // statistics over rows [row0, row0 + rows) (the transposed convs normalise BEFORE their trim), result rows [0, y.T)
+  void finish_norm(const ConvLayer& L, const Act& y, int B, int post, const Act* residual, int row0, int rows);
+  // one group of equal-length segment items (clip-major: item = b*segs + j -> segment s0 + j) through encoder and / or decoder
+  struct Group { int segs, s0; int64_t len, frames, col0; };
+  void run_group(const float* audio, int B, int64_t L, const SegLayout& lay, const Group& g, int nq, int64_t* codes_user,
+                 float* scales, bool encode, bool decode);
+  std::vector<Group> groups_of(const SegLayout& lay) const;
+  void check_overlap_add(const SegLayout& lay) const;
+  void overlap_add(const SegLayout& lay, int B, float* audio_out, int64_t out_len);
+  struct ItemMap { int segs = 1, s0 = 0, item0 = 0, n_seg = 1; const float* scales = nullptr; };
+  ItemMap map_;                        // where run_decoder's generic output stage puts its frames
+  bool generic_io_ = false;            // conv_in / conv_out as channel-padded ConvLayers (stereo, non-causal or GroupNorm)
+  ConvLayer conv_in_l_, conv_out_l_;
+  int cin_pad_ = 32, cout_pad_ = 32;
+  DeviceBuffer gn_stats_, scales_, frames_, seg_lens_;
   std::vector<float> folded(const std::string& p, int d0, int d1, int k, std::vector<float>* bias, int bias_n);
   void build_res(Res& r, const std::string& p, int dim);
   void build_lstm(Lstm& l, const std::string& p, int dim);
@@ -355,6 +411,10 @@ class EncodecEngine : public Engine {
   void conv(const ConvLayer& L, const Act& in, int left_pad, int t_in_extra, const Act& out, int B, int prologue, int post,
             const Act* residual);
   Act run_res(const Res& r, const Act& x, int B, int& free_a, int& free_b, int& free_c, bool post_elu);
+  // conv + finish_norm: in GroupNorm models the post activation / residual move behind the normalisation
+  void conv_n(const ConvLayer& L, const Act& in, int left_pad, int t_in_extra, const Act& out, int B, int prologue, int post,
+              const Act* residual, int out_row0 = 0, int stat_rows = -1);
+  void conv_short_n(const ConvLayer& L, const Act& in, const SPad& pad, const Act& out, int B, int prologue, int post);
   Act run_lstm(const Lstm& l, const Act& x, int B, int out_buf);
   void run_encoder(const float* audio, int B, int64_t L, int64_t* T_out);   // -> z_ (dense [B][T][128])
   void run_decoder(int B, int T, float* audio_out, long long out_stride);   // zq_ act -> audio

@@ -1,4 +1,4 @@
-"""Host-side mirror of the reference's Encodec model class over the C ABI (24 kHz mono causal preset).
+"""Host-side mirror of the reference's Encodec model class over the C ABI (24 kHz and 48 kHz presets).
 
 Same public method names and argument meaning as /root/reference/NeuralCodecs.Torch/Models/Encodec.cs
 (Encode :243/:259, Decode :213, forward :292, LoadWeights :348), numpy arrays in place of TorchSharp tensors;
@@ -33,6 +33,12 @@ class Encodec:
             c.ratios[i] = r
         c.n_residual_layers, c.lstm_layers = config.num_residual_layers, config.num_lstm_layers
         c.codebook_size, c.n_quantizers, c.causal = config.codebook_size, config.num_quantizers, int(config.use_causal_conv)
+        norms = {"weight_norm": 0, "time_group_norm": 1}
+        if config.norm_type not in norms:
+            raise ValueError(f"Unsupported normalization: {config.norm_type}")              # NormConv1d.cs:156-157
+        c.norm_type, c.normalize = norms[config.norm_type], int(bool(config.normalize))
+        c.segment_s = float(config.chunk_length_s) if config.chunk_length_s else 0.0
+        c.overlap = float(config.overlap)
         self._h = C.c_void_p()
         _lib.check(_lib.lib().nc_create(_lib.NC_CODEC_ENCODEC, C.byref(c), C.sizeof(c), config.device.index, C.byref(self._h)),
                    "Encodec", "Create")
@@ -128,39 +134,68 @@ class Encodec:
             raise ValueError(f"Expected {self._config.channels} channels, got {a.shape[1]}")   # Encodec.cs:499-503
         return a
 
+    def query_frames(self, length: int) -> Tuple[List[int], int, int]:
+        """(code frames of each segment, n_q at the configured bandwidth, length Decode returns)."""
+        n, nq, tot, dl = C.c_int32(), C.c_int32(), C.c_int64(), C.c_int64()
+        bw = float(self._config.bandwidth)
+        _lib.check(_lib.lib().nc_encodec_query_frames(self._handle(), length, bw, C.byref(n), None, 0, C.byref(tot), C.byref(nq),
+                                                      C.byref(dl)), "Encodec", "Encoding")
+        seg = (C.c_int64 * n.value)()
+        _lib.check(_lib.lib().nc_encodec_query_frames(self._handle(), length, bw, C.byref(n), seg, n.value, None, None, None),
+                   "Encodec", "Encoding")
+        return list(seg), nq.value, dl.value
+
     def Encode(self, audioData) -> List[EncodedFrame]:
-        """Encodec.Encode (Encodec.cs:243-285): the 24 kHz preset has no segmenting -> one frame for the whole clip."""
+        """Encodec.Encode (Encodec.cs:243-285): one EncodedFrame (codes [B,nq,T_s], scale [B,1] | None) per segment; the
+        24 kHz preset has no segmenting -> one frame for the whole clip.  All segments run in one batched device call."""
         a = self._audio3d(audioData)
         B, _, L = a.shape
-        T, nq, _ = self.query_shapes(L)
-        codes = np.empty((B, nq, T), np.int64)
-        _lib.check(_lib.lib().nc_encodec_encode(self._handle(), a.ctypes.data_as(C.c_void_p), B, L, float(self._config.bandwidth),
-                                                codes.ctypes.data_as(C.c_void_p)), "Encodec", "Encoding")
-        return [(codes, None)]
+        seg, nq, _ = self.query_frames(L)
+        codes = np.empty((B, nq, sum(seg)), np.int64)
+        scales = np.empty((B, len(seg)), np.float32) if self._config.normalize else None
+        _lib.check(_lib.lib().nc_encodec_encode_frames(self._handle(), a.ctypes.data_as(C.c_void_p), B, L, float(self._config.bandwidth),
+                                                       codes.ctypes.data_as(C.c_void_p),
+                                                       scales.ctypes.data_as(C.c_void_p) if scales is not None else None),
+                   "Encodec", "Encoding")
+        frames, col = [], 0
+        for s, t in enumerate(seg):
+            frames.append((np.ascontiguousarray(codes[:, :, col:col + t]), scales[:, s:s + 1].copy() if scales is not None else None))
+            col += t
+        return frames
 
     def Decode(self, encodedFrames: List[EncodedFrame]) -> np.ndarray:
-        """Encodec.Decode (Encodec.cs:213-235): audio [B,1,frames*hop], not trimmed."""
+        """Encodec.Decode (Encodec.cs:213-235): DecodeFrame (* scale) of every frame, then LinearOverlapAdd for segmented
+        models; audio [B, channels, stride*(n-1) + len(last)], not trimmed."""
         if encodedFrames is None or len(encodedFrames) == 0:
             raise ValueError("No frames provided to decode")
-        if len(encodedFrames) != 1:
+        if self._config.chunk_length_s is None and len(encodedFrames) != 1:
             raise ValueError("Expected single frame when no segmentation is used")
-        codes, scale = encodedFrames[0]
-        if codes is None:
+        if any(f[0] is None for f in encodedFrames):
             raise ValueError("Invalid frame codes in Encodec Decode")
-        c = np.ascontiguousarray(codes, dtype=np.int64)
-        B, nq, T = c.shape
-        audio = np.empty((B, 1, T * self._config.hop_length), np.float32)
-        _lib.check(_lib.lib().nc_encodec_decode(self._handle(), c.ctypes.data_as(C.c_void_p), B, nq, T,
-                                                audio.ctypes.data_as(C.c_void_p)), "Encodec", "Decoding")
-        if scale is not None:
-            audio *= np.asarray(scale, np.float32).reshape(-1, 1, 1)       # Encodec.cs:449-452
+        cs = [np.ascontiguousarray(f[0], dtype=np.int64) for f in encodedFrames]
+        B, nq = cs[0].shape[0], cs[0].shape[1]
+        codes = np.ascontiguousarray(np.concatenate(cs, axis=2))
+        seg = (C.c_int64 * len(cs))(*[c.shape[2] for c in cs])
+        with_scale = [f[1] is not None for f in encodedFrames]
+        if any(with_scale) and not all(with_scale):
+            raise ValueError("frames with and without a scale cannot be mixed in one call")
+        scales = None
+        if all(with_scale):
+            scales = np.ascontiguousarray(np.stack([np.asarray(f[1], np.float32).reshape(B) for f in encodedFrames], axis=1))
+        total = C.c_int64()
+        _lib.check(_lib.lib().nc_encodec_query_decoded(self._handle(), seg, len(cs), C.byref(total)), "Encodec", "Decoding")
+        total = total.value
+        audio = np.empty((B, self._config.channels, total), np.float32)
+        _lib.check(_lib.lib().nc_encodec_decode_frames(self._handle(), codes.ctypes.data_as(C.c_void_p),
+                                                       scales.ctypes.data_as(C.c_void_p) if scales is not None else None, B, nq,
+                                                       seg, len(cs), audio.ctypes.data_as(C.c_void_p)), "Encodec", "Decoding")
         return audio
 
     def forward(self, x) -> np.ndarray:
         """Encodec.forward (Encodec.cs:292-296): decode(encode(x)) sliced to the input length."""
         a = self._audio3d(x)
-        B, _, L = a.shape
-        out = np.empty((B, 1, L), np.float32)
+        B, Cn, L = a.shape
+        out = np.empty((B, Cn, L), np.float32)
         _lib.check(_lib.lib().nc_encodec_forward(self._handle(), a.ctypes.data_as(C.c_void_p), B, L, float(self._config.bandwidth),
                                                  out.ctypes.data_as(C.c_void_p), None), "Encodec", "Encoding")
         return out

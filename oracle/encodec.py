@@ -470,3 +470,61 @@ def ecdc_decompress_codes(cfg: EncodecConfig, data: bytes):
                 raise EOFError("Stream ended too soon")
             codes[k, t] = v
     return codes, meta
+
+
+def ecdc_compress_frames(cfg: EncodecConfig, frames, audio_length: int, bandwidth: Optional[float]) -> bytes:
+    """EncodecCompressor.CompressToStreamAsync useLm=false (:93-190) for ONE waveform's frames [(codes [nq, T_s], scale | None)]:
+    header, then per frame an optional scale block (int32 BE count = 1, float32 BE value, :116-139) and the frame's codes in a
+    BitPacker of its own (t outer, k inner; Flush pads to a byte, :177-187)."""
+    import struct
+    nq = int(np.asarray(frames[0][0]).shape[0])
+    bits = int(np.log2(cfg.codebook_size))
+    name = "encodec_48khz" if cfg.sample_rate == 48000 else "encodec_24khz"
+    out = bytearray(ecdc_header(name, audio_length, nq, False, cfg.channels, cfg.sample_rate, bandwidth))
+    for codes, scale in frames:
+        codes = np.asarray(codes)
+        if scale is not None:
+            out += struct.pack(">i", 1) + struct.pack(">f", float(np.asarray(scale, np.float32).reshape(-1)[0]))
+        packer = BitPacker(bits)
+        for t in range(codes.shape[1]):
+            for k in range(codes.shape[0]):
+                packer.push(int(codes[k, t]))
+        out += packer.flush()
+    return bytes(out)
+
+
+def ecdc_decompress_frames(cfg: EncodecConfig, data: bytes):
+    """DecompressFromStreamAsync useLm=false (:236-400) up to the frame list: -> ([(codes [nq, T_s] int64, scale | None)], metadata).
+    Frame lengths follow the READER's formula ceil(segment samples * frame_rate / sample_rate) (:306-309)."""
+    import math
+    import struct
+    meta, pos = ecdc_read_header(data)
+    if str(meta["lm"]).lower() == "true":
+        raise NotImplementedError("lm streams")
+    al, nq = int(meta["al"]), int(meta["nc"])
+    seg, stride = cfg.segment_length or al, cfg.segment_stride or al
+    bits = int(np.log2(cfg.codebook_size))
+    frames = []
+    for off in range(0, al, stride):
+        T = int(math.ceil(min(al - off, seg) * cfg.frame_rate / float(cfg.sample_rate)))
+        scale = None
+        if cfg.normalize:
+            if len(data) < pos + 4:
+                raise EOFError("Stream ended too soon")
+            (n,) = struct.unpack(">i", data[pos:pos + 4])
+            if n <= 0 or n > 1000:
+                raise ValueError(f"Invalid scale count: {n}")
+            scale = np.array(struct.unpack(f">{n}f", data[pos + 4:pos + 4 + 4 * n]), np.float32)
+            pos += 4 + 4 * n
+        nbytes = (T * nq * bits + 7) // 8
+        un = BitUnpacker(bits, data[pos:pos + nbytes])
+        codes = np.zeros((nq, T), np.int64)
+        for t in range(T):
+            for k in range(nq):
+                v = un.pull()
+                if v is None:
+                    raise EOFError("Stream ended too soon")
+                codes[k, t] = v
+        pos += nbytes
+        frames.append((codes, scale))
+    return frames, meta

@@ -1,4 +1,4 @@
-"""Device-resident timing of SNAC / Encodec forward: python scripts/time_codec.py snac|encodec [batch] [seconds] [k=v ...]"""
+"""Device-resident timing of SNAC / Encodec forward: python scripts/time_codec.py snac|encodec|encodec48 [batch] [seconds] [k=v ...]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -14,6 +14,11 @@ if which == "snac":
     path = os.path.join(tempfile.gettempdir(), "snac24_bench.safetensors")
     if not os.path.exists(path): synthetic.save_safetensors(synthetic.make_snac_weights(cfg), path)
     m = nc.SNAC(cfg, options=opts)
+elif which == "encodec48":
+    cfg = nc.EncodecConfig.Encodec48Khz(); sr = 48000
+    path = os.path.join(tempfile.gettempdir(), "encodec48_bench.safetensors")
+    if not os.path.exists(path): synthetic.save_safetensors(synthetic.make_encodec_weights(cfg), path)
+    m = nc.Encodec(cfg, options=opts)
 else:
     cfg = nc.EncodecConfig.Encodec24Khz(); sr = 24000
     path = os.path.join(tempfile.gettempdir(), "encodec24_bench.safetensors")
@@ -23,7 +28,13 @@ m.LoadWeights(path)
 L = int(S * sr)
 x = torch.from_numpy(synthetic.synth_audio(min(B, 8), L, sr)).to(dev).repeat((B + 7) // 8, 1)[:B].contiguous()
 out = torch.empty(B, L, device=dev)
-if which == "snac":
+if which == "encodec48":   # stereo: [B][2][L]
+    x = torch.stack([x, x.flip(0) * 0.7], dim=1).contiguous()
+    out = torch.empty(B, 2, L, device=dev)
+    seg, nq, _ = m.query_frames(L)
+    codes = torch.empty(B, nq, sum(seg), dtype=torch.int64, device=dev)
+    run = lambda: m.forward_dev(x.data_ptr(), B, L, out.data_ptr(), codes.data_ptr())
+elif which == "snac":
     _, T, clens, nlens = m.query_shapes(L)
     codes = [torch.empty(B, n, dtype=torch.int64, device=dev) for n in clens]
     run = lambda: m.forward_dev(x.data_ptr(), B, L, out.data_ptr(), [c.data_ptr() for c in codes], None, 5)

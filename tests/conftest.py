@@ -155,3 +155,23 @@ def snac_44k(cache_dir):
     import neuralcodecs_b200 as nc
     co, ce = osnac.SNACConfig.snac_44khz(), nc.SNACConfig.SNAC44kHz()
     return co, ce, _write_snac(co, os.path.join(cache_dir, "snac44_seed4321.safetensors"), 2, 2.0)
+
+
+@pytest.fixture(scope="session")
+def encodec_48k(cache_dir):
+    """Encodec 48 kHz preset (stereo, non-causal, time_group_norm, normalize, 1 s segments, 1 % overlap) at 6 kbps."""
+    from oracle import encodec as oenc
+    import neuralcodecs_b200 as nc
+    co, ce = oenc.EncodecConfig.encodec_48khz(), nc.EncodecConfig.Encodec48Khz()
+    return co, ce, _write_encodec(co, os.path.join(cache_dir, "encodec48_seed4321.safetensors"), 2, 3.0)
+
+
+@pytest.fixture(scope="session")
+def encodec_48k_one_frame(cache_dir):
+    """The 48 kHz architecture without segments and without the loudness scale (one un-normalised frame per clip)."""
+    from oracle import encodec as oenc
+    import neuralcodecs_b200 as nc
+    co, ce = oenc.EncodecConfig.encodec_48khz(), nc.EncodecConfig.Encodec48Khz()
+    co.chunk_length_s = ce.chunk_length_s = None
+    co.normalize = ce.normalize = False
+    return co, ce, _write_encodec(co, os.path.join(cache_dir, "encodec48_oneframe_seed4321.safetensors"), 2, 3.0)

@@ -37,7 +37,7 @@ def test_config_structs_match_header_layout():
     # 4-byte fields only: sizes follow directly from the header's field lists
     assert C.sizeof(_lib.nc_dac_config) == 4 * (4 + 8 + 2 + 8 + 4)
     assert C.sizeof(_lib.nc_snac_config) == 4 * (4 + 8 + 2 + 8 + 4 + 1 + 8 + 2)
-    assert C.sizeof(_lib.nc_encodec_config) == 4 * (6 + 8 + 5)
+    assert C.sizeof(_lib.nc_encodec_config) == 4 * (6 + 8 + 5 + 4)
 
 
 def test_no_cpu_fallback_without_device():

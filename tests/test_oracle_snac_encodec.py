@@ -319,3 +319,32 @@ def test_encodec48_segment_loop_is_the_references(encodec48_gold):
     assert [f[0].shape[-1] for f in m.encode_frames(x[..., :2400], 48.0)] == [100, 4]
     ref = oenc.linear_overlap_add([m.decode_frame(*f) for f in frames], cfg.segment_stride)[..., :x.shape[-1]]
     np.testing.assert_allclose(y.numpy(), ref.numpy(), atol=1e-6)
+
+
+def test_ecdc_frames_with_scale_blocks_known_answer_and_round_trip():
+    """Segmented stream (EncodecCompressor.cs:116-190,303-400): per frame [int32 BE 1][float32 BE scale][codes packed on their own]."""
+    import struct
+    cfg = oenc.EncodecConfig.encodec_48khz()
+    rng = np.random.default_rng(0)
+    al = 2 * 47520 + 12345
+    frames = [(rng.integers(0, 1024, (4, t)), np.float32(0.25 * (i + 1))) for i, t in enumerate((150, 150, 39))]
+    data = oenc.ecdc_compress_frames(cfg, frames, al, 6.0)
+    meta, off = oenc.ecdc_read_header(data)
+    assert meta == {"m": "encodec_48khz", "al": al, "nc": 4, "lm": False, "ch": 2, "sr": 48000, "bw": 6}
+    per = [8 + (4 * t * 10 + 7) // 8 for t in (150, 150, 39)]
+    assert len(data) == off + sum(per)
+    assert data[off:off + 8] == struct.pack(">if", 1, 0.25) and data[off + per[0]:off + per[0] + 8] == struct.pack(">if", 1, 0.5)
+    # first code bytes of frame 0: values (t0,k0), (t0,k1) at 10 bits each, LSB first
+    v0, v1 = int(frames[0][0][0, 0]), int(frames[0][0][1, 0])
+    assert data[off + 8] == v0 & 0xFF and data[off + 9] == ((v0 >> 8) | (v1 << 2)) & 0xFF
+    back, meta2 = oenc.ecdc_decompress_frames(cfg, data)
+    assert meta2 == meta and [f[0].shape for f in back] == [(4, 150), (4, 150), (4, 39)]
+    for (c, s), (c2, s2) in zip(frames, back):
+        np.testing.assert_array_equal(c, c2)
+        assert s2.shape == (1,) and s2[0] == s
+    with pytest.raises(EOFError):
+        oenc.ecdc_decompress_frames(cfg, data[:-3])
+    bad = bytearray(data)
+    bad[off:off + 4] = struct.pack(">i", 0)
+    with pytest.raises(ValueError, match="Invalid scale count"):
+        oenc.ecdc_decompress_frames(cfg, bytes(bad))

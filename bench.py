@@ -283,7 +283,8 @@ def synth_audio_cuda(torch, batch, length, first_clip, device):
 
 def codec_weights_path(codec: str) -> str:
     from neuralcodecs_b200 import synthetic
-    return os.path.join(tempfile.gettempdir(), f"nc_bench_{codec}24_seed{synthetic.WEIGHT_SEED}.safetensors")
+    tag = codec if codec.endswith("48") else codec + "24"
+    return os.path.join(tempfile.gettempdir(), f"nc_bench_{tag}_seed{synthetic.WEIGHT_SEED}.safetensors")
 
 
 def ensure_codec_weights(codec: str) -> str:
@@ -294,6 +295,8 @@ def ensure_codec_weights(codec: str) -> str:
     if not os.path.exists(wpath):
         if codec == "snac":
             sd = synthetic.make_snac_weights(nc.SNACConfig.SNAC24kHz())
+        elif codec == "encodec48":
+            sd = synthetic.make_encodec_weights(nc.EncodecConfig.Encodec48Khz())
         else:
             sd = synthetic.make_encodec_weights(nc.EncodecConfig.Encodec24Khz())
         for k in sd:   # N(0,1) codebooks scaled into the latents' range (timing is data independent)
@@ -368,6 +371,21 @@ def other_configs(dac_model, local_rank: int, steps: int = 3, warmup: int = 3):
             out[f"{codec}24k_b{B}x10s"] = {"value": B * 10.0 / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": max(steps, 5),
                                            "warmup": warmup}
             m.Dispose()
+        # Encodec 48 kHz preset (stereo, GroupNorm, 1 s segments + overlap-add): 16 stereo clips x 10 s
+        cfg = nc.EncodecConfig.Encodec48Khz()
+        cfg.device = nc.DeviceConfiguration.CUDA(local_rank)
+        m = nc.Encodec(cfg)
+        m.LoadWeights(ensure_codec_weights("encodec48"))
+        B, L = 16, 480000
+        base = torch.from_numpy(synthetic.synth_audio(16, L, 48000)).to(dev)
+        audio = torch.stack([base, base.flip(0) * 0.7], dim=1).contiguous()
+        ao = torch.empty(B, 2, L, device=dev)
+        seg, nq, _ = m.query_frames(L)
+        cs = torch.empty(B, nq, sum(seg), dtype=torch.int64, device=dev)
+        ms = timed(m, lambda: m.forward_dev(audio.data_ptr(), B, L, ao.data_ptr(), cs.data_ptr()), max(steps, 5))
+        out["encodec48k_stereo_b16x10s"] = {"value": B * 10.0 / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": max(steps, 5),
+                                            "warmup": warmup}
+        m.Dispose()
     except Exception as e:   # a side measurement must never take the headline line down
         out["error"] = f"{type(e).__name__}: {e}"
     return out

@@ -1,4 +1,4 @@
-// Drop-in counterpart of NeuralCodecs.Torch/Models/Encodec.cs (24 kHz mono causal preset) and of the static
+// Drop-in counterpart of NeuralCodecs.Torch/Models/Encodec.cs (24 kHz and 48 kHz presets) and of the static
 // EncodecCompressor (Modules/Encodec/EncodecCompressor.cs, useLm: false) over the C ABI.  NOT compiled in this
 // repository (no dotnet); its executable twin is neuralcodecs_b200/encodec.py.
 using System;
@@ -40,6 +40,14 @@ public sealed unsafe class CudaEncodec : INeuralCodec
             NResidualLayers = config.NumResidualLayers, LstmLayers = config.NumLstmLayers, CodebookSize = config.CodebookSize,
             NQuantizers = (int)(1000 * config.TargetBandwidths.Max() / (frameRate * 10)),   // Encodec.cs:70-71
             Causal = config.UseCausalConv ? 1 : 0,
+            NormType = config.NormType switch
+            {
+                "weight_norm" => 0, "time_group_norm" => 1,
+                _ => throw new ArgumentException($"Unsupported normalization: {config.NormType}")   // NormConv1d.cs:156-157
+            },
+            Normalize = config.Normalize ? 1 : 0,
+            SegmentS = config.ChunkLengthSeconds ?? 0f,                          // Encodec.cs:79
+            Overlap = config.Overlap ?? 0f,                                      // Encodec.cs:84
         };
         for (int i = 0; i < config.UpsamplingRatios.Length; i++) c.Ratios[i] = config.UpsamplingRatios[i];
         Native.Check(Native.nc_create(NcCodecKind.Encodec, &c, (nuint)sizeof(NcEncodecConfig), config.Device?.Index ?? 0, out _h),
@@ -56,41 +64,66 @@ public sealed unsafe class CudaEncodec : INeuralCodec
         _bandwidth = bandwidth;
     }
 
-    /// Encodec.Encode(float[]) (Encodec.cs:243-250): one frame for the whole clip (no segmenting in the 24 kHz preset), scale = null.
+    /// Encodec.Encode(float[]) (Encodec.cs:243-285): audioData is [Channels, L] planar (the reference reshapes it to
+    /// (1, Channels, -1)); one frame per segment -- one for the whole clip in the 24 kHz preset, scale = null there.
     public List<CudaEncodedFrame> Encode(float[] audioData)
     {
         if (audioData is null) throw new ArgumentNullException(nameof(audioData));
-        Native.Check(Native.nc_encodec_query_shapes(_h, audioData.Length, _bandwidth, out long T, out int nq, out _), "Encodec", CodecOperation.Encoding);
-        var codes = new long[nq * T];
-        fixed (float* a = audioData) fixed (long* pc = codes)
-            Native.Check(Native.nc_encodec_encode(_h, a, 1, audioData.Length, _bandwidth, pc), "Encodec", CodecOperation.Encoding);
-        return new List<CudaEncodedFrame> { new(codes, nq, null) };
+        long L = audioData.Length / _config.Channels;
+        Native.Check(Native.nc_encodec_query_frames(_h, L, _bandwidth, out int nSeg, null, 0, out long total, out int nq, out _), "Encodec", CodecOperation.Encoding);
+        var seg = new long[nSeg];
+        fixed (long* ps = seg)
+            Native.Check(Native.nc_encodec_query_frames(_h, L, _bandwidth, out nSeg, ps, nSeg, out total, out nq, out _), "Encodec", CodecOperation.Encoding);
+        var codes = new long[nq * total];
+        var scales = _config.Normalize ? new float[nSeg] : null;
+        fixed (float* a = audioData) fixed (long* pc = codes) fixed (float* psc = scales)
+            Native.Check(Native.nc_encodec_encode_frames(_h, a, 1, L, _bandwidth, pc, psc), "Encodec", CodecOperation.Encoding);
+        var frames = new List<CudaEncodedFrame>(nSeg);
+        long col = 0;
+        for (int s = 0; s < nSeg; col += seg[s], s++)
+        {
+            var fc = new long[nq * seg[s]];
+            for (int q = 0; q < nq; q++) Array.Copy(codes, q * total + col, fc, q * seg[s], seg[s]);
+            frames.Add(new CudaEncodedFrame(fc, nq, scales is null ? null : new[] { scales[s] }));
+        }
+        return frames;
     }
 
-    /// Encodec.Decode(List<EncodedFrame>) (Encodec.cs:213-235): audio [frames * hop], not trimmed.
+    /// Encodec.Decode(List<EncodedFrame>) (Encodec.cs:213-235): DecodeFrame (* scale) of every frame and, for segmented
+    /// models, DSP.LinearOverlapAdd; audio [Channels, stride*(n-1) + len(last)] planar, not trimmed.
     public float[] Decode(List<CudaEncodedFrame> frames)
     {
         if (frames is null || frames.Count == 0) throw new ArgumentException("No frames provided to decode");
-        if (frames.Count != 1) throw new ArgumentException("Expected single frame when no segmentation is used");
-        var f = frames[0];
-        if (f.Codes is null) throw new ArgumentException("Invalid frame codes in Encodec Decode");     // Encodec.cs:438-442
-        long T = f.Codes.Length / f.NumCodebooks;
-        int hop = _config.UpsamplingRatios.Aggregate(1, (a, b) => a * b);
-        var audio = new float[T * hop];
-        fixed (long* pc = f.Codes) fixed (float* pa = audio)
-            Native.Check(Native.nc_encodec_decode(_h, pc, 1, f.NumCodebooks, T, pa), "Encodec", CodecOperation.Decoding);
-        if (f.Scale is { Length: > 0 }) for (int i = 0; i < audio.Length; i++) audio[i] *= f.Scale[0];  // Encodec.cs:449-452
-        return audio;
+        if (_config.ChunkLengthSeconds is null && frames.Count != 1) throw new ArgumentException("Expected single frame when no segmentation is used");
+        if (frames.Any(f => f.Codes is null)) throw new ArgumentException("Invalid frame codes in Encodec Decode");     // Encodec.cs:438-442
+        int nq = frames[0].NumCodebooks;
+        var seg = frames.Select(f => (long)(f.Codes.Length / nq)).ToArray();
+        long total = seg.Sum();
+        var codes = new long[nq * total];
+        long col = 0;
+        for (int s = 0; s < frames.Count; col += seg[s], s++)
+            for (int q = 0; q < nq; q++) Array.Copy(frames[s].Codes, q * seg[s], codes, q * total + col, seg[s]);
+        bool scaled = frames.All(f => f.Scale is { Length: > 0 });
+        var scales = scaled ? frames.Select(f => f.Scale![0]).ToArray() : null;
+        fixed (long* ps = seg) fixed (long* pc = codes) fixed (float* psc = scales)
+        {
+            Native.Check(Native.nc_encodec_query_decoded(_h, ps, seg.Length, out long n), "Encodec", CodecOperation.Decoding);
+            var audio = new float[_config.Channels * n];
+            fixed (float* pa = audio)
+                Native.Check(Native.nc_encodec_decode_frames(_h, pc, psc, 1, nq, ps, seg.Length, pa), "Encodec", CodecOperation.Decoding);
+            return audio;
+        }
     }
 
     /// EncodecCompressor.Compress(model, wav, useLm: false) (EncodecCompressor.cs:26-39,60-200): the .ecdc byte stream.
     public byte[] Compress(float[] wav)
     {
         if (wav is null) throw new ArgumentNullException(nameof(wav));
-        Native.Check(Native.nc_encodec_ecdc_size(_h, wav.Length, _bandwidth, out _, out long total), "Encodec", CodecOperation.Encoding);
+        long L = wav.Length / _config.Channels;                                  // wav is [Channels, L] planar (:67-77)
+        Native.Check(Native.nc_encodec_ecdc_size(_h, L, _bandwidth, out _, out long total), "Encodec", CodecOperation.Encoding);
         var outp = new byte[total];
         fixed (float* a = wav) fixed (byte* po = outp)
-            Native.Check(Native.nc_encodec_compress(_h, a, 1, wav.Length, _bandwidth, po, total, out _), "Encodec", CodecOperation.Encoding);
+            Native.Check(Native.nc_encodec_compress(_h, a, 1, L, _bandwidth, po, total, out _), "Encodec", CodecOperation.Encoding);
         return outp;
     }
 
@@ -101,7 +134,7 @@ public sealed unsafe class CudaEncodec : INeuralCodec
         fixed (byte* ps = compressed)
         {
             Native.Check(Native.nc_encodec_decompress(_h, ps, 1, compressed.Length, compressed.Length, null, 0, out long al, out int sr), "Encodec", CodecOperation.Decoding);
-            var wav = new float[al];
+            var wav = new float[_config.Channels * al];                          // [Channels, al] planar
             fixed (float* pw = wav)
                 Native.Check(Native.nc_encodec_decompress(_h, ps, 1, compressed.Length, compressed.Length, pw, al, out al, out sr), "Encodec", CodecOperation.Decoding);
             return (wav, sr);

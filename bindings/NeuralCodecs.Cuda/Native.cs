@@ -45,6 +45,10 @@ internal unsafe struct NcEncodecConfig   // nc_encodec_config
     public int SampleRate, Channels, NFilters, Dimension, NRatios;
     public fixed int Ratios[8];
     public int NResidualLayers, LstmLayers, CodebookSize, NQuantizers, Causal;
+    public int NormType;      // 0 = "weight_norm", 1 = "time_group_norm"
+    public int Normalize;
+    public float SegmentS;    // ChunkLengthSeconds, 0 = one frame per clip
+    public float Overlap;
 }
 
 internal sealed class NcHandle : SafeHandle
@@ -87,6 +91,10 @@ internal static unsafe partial class Native
     [LibraryImport(Lib)] internal static partial NcStatus nc_encodec_encode(NcHandle h, float* audio, int batch, long length, float bandwidthKbps, long* codes);
     [LibraryImport(Lib)] internal static partial NcStatus nc_encodec_decode(NcHandle h, long* codes, int batch, int nQ, long frames, float* audio);
     [LibraryImport(Lib)] internal static partial NcStatus nc_encodec_forward(NcHandle h, float* audio, int batch, long length, float bandwidthKbps, float* audioOut, long* codes);
+    [LibraryImport(Lib)] internal static partial NcStatus nc_encodec_query_frames(NcHandle h, long length, float bandwidthKbps, out int nSegments, long* segFrames, int segFramesCapacity, out long totalFrames, out int nQ, out long decodedLength);
+    [LibraryImport(Lib)] internal static partial NcStatus nc_encodec_encode_frames(NcHandle h, float* audio, int batch, long length, float bandwidthKbps, long* codes, float* scales);
+    [LibraryImport(Lib)] internal static partial NcStatus nc_encodec_decode_frames(NcHandle h, long* codes, float* scales, int batch, int nQ, long* segFrames, int nSegments, float* audio);
+    [LibraryImport(Lib)] internal static partial NcStatus nc_encodec_query_decoded(NcHandle h, long* segFrames, int nSegments, out long decodedLength);
     [LibraryImport(Lib)] internal static partial NcStatus nc_encodec_ecdc_size(NcHandle h, long length, float bandwidthKbps, out long headerBytes, out long streamBytes);
     [LibraryImport(Lib)] internal static partial NcStatus nc_encodec_compress(NcHandle h, float* audio, int batch, long length, float bandwidthKbps, byte* output, long outStride, out long streamBytes);
     [LibraryImport(Lib)] internal static partial NcStatus nc_encodec_ecdc_info(byte* stream, long streamBytes, out long audioLength, out int nQ, out int channels, out int sampleRate, out float bandwidthKbps, out int useLm, out long payloadOffset);

@@ -173,7 +173,7 @@ class EncodecConfig:
     use_causal_conv: bool = True
     normalize: bool = False
     chunk_length_s: Optional[float] = None      # `Segment`
-    overlap: float = 0.01
+    overlap: Optional[float] = None             # Models/Encodec.cs:84: `config.Overlap ?? 0`
     norm_type: str = "weight_norm"
 
     _JSON = {"sampling_rate": "sample_rate", "audio_channels": "channels", "num_filters": "num_filters",
@@ -211,7 +211,7 @@ class EncodecConfig:
         if self.chunk_length_s is None:
             return None
         import numpy as np
-        return max(1, int((np.float32(1) - np.float32(self.overlap)) * np.float32(self.segment_length)))
+        return max(1, int((np.float32(1) - np.float32(self.overlap or 0.0)) * np.float32(self.segment_length)))
 
     @classmethod
     def Encodec24Khz(cls) -> "EncodecConfig":   # EncodecConfig.cs:9-34

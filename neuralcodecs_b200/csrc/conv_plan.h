@@ -142,7 +142,8 @@ struct UmmaLaunch {
   int w_stages;
   int a_rows_alloc;  // multiple of 8
   int tma_epilogue;  // 1: output / residual tiles move by TMA through a swizzled smem ring
-  int epi_stages;    // conv_h16: depth of the epilogue's smem ring (residual prefetch / stores in flight)
+  int epi_stages;    // conv_h16 / fused unit: depth of the epilogue's smem ring (residual prefetch / stores in flight)
+  int h_stages;      // fused unit: depth of the ring of 1x1-conv operand tiles written by the acc1 drain
   int knock;         // measurement only (env NC_KNOCK, results become WRONG): 1 = weight copies skipped after the ring
                      // filled once, 2 = operand transform skipped, 4 = A loads skipped, 8 = MMAs skipped, 16 = epilogue math/stores skipped
 };

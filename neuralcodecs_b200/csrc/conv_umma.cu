@@ -44,7 +44,7 @@ constexpr int kUmmaThreads = 32 * (kResidualWarp + 1);                          
 constexpr int kEpiStages = 3;
 constexpr uint32_t kEpiStageBytes = kBM * 128;                                    // [128 rows][32 fp32]
 constexpr int kMaxAStages = 6;
-constexpr int kMaxWStages = 8;
+constexpr int kMaxWStages = 16;
 // 227 KB opt-in limit minus the kernel's static shared memory (barriers), rounded up to 1 KB
 constexpr size_t kUmmaMaxDynSmem = 227 * 1024 - 1024;
 
@@ -778,7 +778,7 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
 // C <= 128: both accumulators double-buffered (4 x C <= 512 TMEM columns) and the k7 MMAs of tile i+1 are issued
 // BEFORE the 1x1 MMAs of tile i, so draining acc1 overlaps tensor-core work.  128 < C <= 256: single-buffered,
 // issue order k7(i), 1x1(i).  Operand mode: bf16x3 / f16x3 only.
-constexpr int kHStages = 3;
+constexpr int kHStages = 3;   // most; the launch picks L.h_stages / L.epi_stages (the weight ring gets the rest)
 
 template <int PRO, int RIT>
 __global__ void __launch_bounds__(kUmmaThreads, 1)
@@ -792,7 +792,7 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
   uint8_t* sA = smem;
   uint8_t* sW = sA + (uint32_t)L.a_stages * a_stage_bytes;
   uint8_t* sH = sW + (uint32_t)L.w_stages * w_stage_bytes;
-  uint8_t* sE = sH + kHStages * kEpiStageBytes;
+  uint8_t* sE = sH + (uint32_t)L.h_stages * kEpiStageBytes;
 
   __shared__ uint64_t raw_full[kMaxAStages], a_full[kMaxAStages], a_empty[kMaxAStages];
   __shared__ uint64_t w_full[kMaxWStages], w_empty[kMaxWStages];
@@ -852,7 +852,7 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
     const uint32_t t_addr = tmem_base + acc1_col(it) + ((uint32_t)(q * 32) << 16);
     for (int g = 0; g < groups; ++g) {
       if (g < g_begin || g >= g_end) {   // the other warp set's group: only advance the ring position
-        if (++hs == kHStages) { hs = 0; hph ^= 1u; }
+        if (++hs == L.h_stages) { hs = 0; hph ^= 1u; }
         continue;
       }
       float v[16];
@@ -896,7 +896,7 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&h_full[hs]);
-      if (++hs == kHStages) { hs = 0; hph ^= 1u; }
+      if (++hs == L.h_stages) { hs = 0; hph ^= 1u; }
     }
   };
 
@@ -908,8 +908,12 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       const uint32_t w1_bytes = (uint32_t)p.BN * (p.w_hi_only ? 64u : 128u), w2_bytes = (uint32_t)p.BN * (p2.w_hi_only ? 64u : 128u);
       auto push = [&](const float* src, uint32_t bytes) {
         mbar_wait(&w_empty[ws], wph ^ 1u);
-        mbar_arrive_expect_tx(&w_full[ws], bytes);
-        bulk_g2s(sW + (size_t)ws * w_stage_bytes, src, bytes, &w_full[ws]);
+        if (L.knock & 128) {   // measurement only: no weight stream from L2
+          mbar_arrive(&w_full[ws]);
+        } else {
+          mbar_arrive_expect_tx(&w_full[ws], bytes);
+          bulk_g2s(sW + (size_t)ws * w_stage_bytes, src, bytes, &w_full[ws]);
+        }
         if (++ws == L.w_stages) { ws = 0; wph ^= 1u; }
       };
       auto w1 = [&]() {
@@ -1005,7 +1009,7 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
           next_w();
           tc_commit(&h_free[hs]);
           h_desc += h_stage_u;
-          if (++hs == kHStages) { hs = 0; hph ^= 1u; h_desc = h_desc0; }
+          if (++hs == L.h_stages) { hs = 0; hph ^= 1u; h_desc = h_desc0; }
         }
         tc_commit(&acc2_full[b]);
       };
@@ -1044,9 +1048,13 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
         const int mt = tile - b * p.m_tiles_per_clip;
         for (int g = 0; g < groups; ++g) {
           mbar_wait(&e_free[es], eph ^ 1u);
-          mbar_arrive_expect_tx(&r_full[es], kEpiStageBytes);
-          tma_load_3d(sE + (size_t)es * kEpiStageBytes, &tmapR, g * 32, mt * kBM, b, &r_full[es]);
-          if (++es == kEpiStages) { es = 0; eph ^= 1u; }
+          if (L.knock & 1024) {   // measurement only: no residual read
+            mbar_arrive(&r_full[es]);
+          } else {
+            mbar_arrive_expect_tx(&r_full[es], kEpiStageBytes);
+            tma_load_3d(sE + (size_t)es * kEpiStageBytes, &tmapR, g * 32, mt * kBM, b, &r_full[es]);
+          }
+          if (++es == L.epi_stages) { es = 0; eph ^= 1u; }
         }
       }
     }
@@ -1074,15 +1082,17 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
           if (lane == 0) mbar_arrive(&acc2_empty[b]);
         }
         const int n0 = g * 32 + half * 16;
-        epi_bias(p2, v, n0);
         uint8_t* stage = sE + (size_t)es * kEpiStageBytes;
         mbar_wait(&r_full[es], eph);
+        if (!(L.knock & 256)) {   // (knock 256, measurement only: no bias / residual / activation math)
+          epi_bias(p2, v, n0);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 r = *reinterpret_cast<const float4*>(stage + sw128_offset((uint32_t)rloc, (uint32_t)(half * 4 + i)));
-          v[4 * i + 0] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
+          for (int i = 0; i < 4; ++i) {
+            const float4 r = *reinterpret_cast<const float4*>(stage + sw128_offset((uint32_t)rloc, (uint32_t)(half * 4 + i)));
+            v[4 * i + 0] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
+          }
+          epi_post(p2, v, n0);
         }
-        epi_post(p2, v, n0);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           *reinterpret_cast<float4*>(stage + sw128_offset((uint32_t)rloc, (uint32_t)(half * 4 + i))) =
@@ -1090,13 +1100,13 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
         fence_proxy_async_smem();
         asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueWarps * 32) : "memory");
         if (leader) {
-          tma_store_3d(&tmapD, stage, g * 32, mt * kBM, bb);
+          if (!(L.knock & 512)) tma_store_3d(&tmapD, stage, g * 32, mt * kBM, bb);   // (knock 512, measurement only: no store)
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           if (prev >= 0) mbar_arrive(&e_free[prev]);
           prev = es;
         }
-        if (++es == kEpiStages) { es = 0; eph ^= 1u; }
+        if (++es == L.epi_stages) { es = 0; eph ^= 1u; }
       }
     };
     if (dbl) {
@@ -1353,19 +1363,22 @@ int launch_ru_fused(const ConvGemmParams& p, const ConvGemmParams& p2, int num_s
   UmmaLaunch L;
   const int rows = ((kBM + p.span) + 7) / 8 * 8;
   const long a_stage = (long)rows * 128, w_stage = (long)p.BN * ((p.w_hi_only && p2.w_hi_only) ? 64 : 128);
-  const long budget = (long)kUmmaMaxDynSmem - 1024 - (long)(kHStages + kEpiStages) * kEpiStageBytes;
-  int as = 2, ws = 2;
+  // Shared-memory split (sweep: profiles/r02_ru_fused_smem_split.txt).  These units are bound by shared-memory bandwidth
+  // (~1 MB of smem traffic per 128-row tile at C = 64, 60 % of it tensor-core operand reads of the 7-tap x 3-pass products),
+  // so no ring depth changes much; the best measured split keeps 3 H stages, 2 E stages, an A ring of one tile (+1 chunk at
+  // C = 64) and gives the rest to the weight ring (-6 % over the round-1 split of 4 / 3 / 3).
+  static const int env_as = getenv("NC_RU_AS") ? atoi(getenv("NC_RU_AS")) : 0;
+  static const int env_hs = getenv("NC_RU_HS") ? atoi(getenv("NC_RU_HS")) : 0;
+  static const int env_es = getenv("NC_RU_ES") ? atoi(getenv("NC_RU_ES")) : 0;
+  const int hs = std::min(std::max(env_hs ? env_hs : 3, 2), kHStages), es = std::min(std::max(env_es ? env_es : 2, 2), kEpiStages);
+  const long budget = (long)kUmmaMaxDynSmem - 1024 - (long)(hs + es) * kEpiStageBytes;
+  int as = env_as ? std::min(std::max(env_as, 2), kMaxAStages) : std::min(std::max(p.n_kc + 1, 3), 4), ws = 2;
+  while (as > 2 && as * a_stage + ws * w_stage > budget) --as;
   if (as * a_stage + ws * w_stage > budget) return -1;
-  for (;;) {
-    bool grew = false;
-    if (ws < 4 && as * a_stage + (ws + 1) * w_stage <= budget) { ++ws; grew = true; }
-    if (as < 4 && (as + 1) * a_stage + ws * w_stage <= budget) { ++as; grew = true; }
-    if (!grew) break;
-  }
   while (ws < kMaxWStages && as * a_stage + (ws + 1) * w_stage <= budget) ++ws;
   static const int knock_ru = getenv("NC_KNOCK_RU") ? atoi(getenv("NC_KNOCK_RU")) : 0;
-  L.a_stages = as; L.w_stages = ws; L.a_rows_alloc = rows; L.tma_epilogue = 1; L.knock = knock_ru; L.epi_stages = 0;
-  const size_t smem = 1024 + (size_t)as * a_stage + (size_t)ws * w_stage + (size_t)(kHStages + kEpiStages) * kEpiStageBytes;
+  L.a_stages = as; L.w_stages = ws; L.a_rows_alloc = rows; L.tma_epilogue = 1; L.knock = knock_ru; L.epi_stages = es; L.h_stages = hs;
+  const size_t smem = 1024 + (size_t)as * a_stage + (size_t)ws * w_stage + (size_t)(hs + es) * kEpiStageBytes;
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return (int)cudaErrorNotSupported;
   alignas(64) CUtensorMap tA, tD, tR;

@@ -38,7 +38,7 @@ class Encodec:
             raise ValueError(f"Unsupported normalization: {config.norm_type}")              # NormConv1d.cs:156-157
         c.norm_type, c.normalize = norms[config.norm_type], int(bool(config.normalize))
         c.segment_s = float(config.chunk_length_s) if config.chunk_length_s else 0.0
-        c.overlap = float(config.overlap)
+        c.overlap = float(config.overlap or 0.0)
         self._h = C.c_void_p()
         _lib.check(_lib.lib().nc_create(_lib.NC_CODEC_ENCODEC, C.byref(c), C.sizeof(c), config.device.index, C.byref(self._h)),
                    "Encodec", "Create")

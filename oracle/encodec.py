@@ -49,7 +49,7 @@ class EncodecConfig:
     normalize: bool = False
     norm_type: str = "weight_norm"              # "weight_norm" | "time_group_norm"
     chunk_length_s: Optional[float] = None      # `Segment`: None = one frame per clip
-    overlap: float = 0.01
+    overlap: Optional[float] = None             # Models/Encodec.cs:84: `config.Overlap ?? 0`
 
     @classmethod
     def encodec_48khz(cls) -> "EncodecConfig":
@@ -67,7 +67,7 @@ class EncodecConfig:
     def segment_stride(self) -> Optional[int]:  # Models/Encodec.cs:195-196: max(1, (int)((1 - overlap) * SegmentLength)), float32
         if self.chunk_length_s is None:
             return None
-        return max(1, int((np.float32(1) - np.float32(self.overlap)) * np.float32(self.segment_length)))
+        return max(1, int((np.float32(1) - np.float32(self.overlap or 0.0)) * np.float32(self.segment_length)))
 
     @property
     def hop_length(self) -> int:

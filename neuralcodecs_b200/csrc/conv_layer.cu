@@ -462,7 +462,7 @@ bool ConvLayer::fill_umma(const ConvRunArgs& a, ConvGemmParams* pp, int fast_sin
   p.A = a.in; p.a_clip_stride = a_stride; p.a_rows = a_rows; p.a_pitch = k_view_; p.a_valid = a_valid;
   p.D = a.out; p.R = a.residual; p.d_clip_stride = d_stride; p.m_rows = m_rows; p.n_total = n_total;
   p.n_valid = n_logical_; p.d_valid = d_valid;
-  p.bias = d_bias_; p.bias_period = s.cout; p.noise = a.noise;
+  p.bias = d_bias_; p.bias_period = s.cout; p.noise = a.noise; p.gn_stats = a.gn_stats;
   p.alpha = a.alpha; p.inv_alpha = a.inv_alpha; p.alpha_period = s.cin; p.prologue = a.prologue; p.act = a.act;
   p.post = a.post; p.post_alpha = a.post_alpha; p.post_inv_alpha = a.post_inv_alpha; p.post_period = s.cout;
   p.W = d_w_tiles_; p.w_tile_floats = w_tile_floats_; p.BN = bn_; p.n_tiles = n_tiles_; p.tiles_per_ntile = tiles_per_ntile_;
@@ -540,8 +540,10 @@ void ConvLayer::run(const ConvRunArgs& a, const LaunchCtx& ctx) const {
     ctx.end(ev, "conv_h16", fl, b16, name_);
     return;
   }
+  if (a.gn_stats_done) *a.gn_stats_done = false;
   if (fill_umma(a, &up, ctx.fast_sin)) {
     check_launch(launch_conv_umma(up, ctx.num_sms, ctx.stream), name_.c_str());
+    if (a.gn_stats_done) *a.gn_stats_done = a.gn_stats != nullptr;
     ctx.end(ev, std::string(a.dw_w ? "conv_umma_dw_" : "conv_umma_") + precision_name(mode_),
             fl + (a.dw_w ? 2.0 * 7 * s.cin * (double)a.t_in * a.batch : 0.0), bytes, name_);
   } else {

@@ -31,6 +31,10 @@ struct ConvRunArgs {
   void* out16 = nullptr;
   const float* residual = nullptr;  // same shape as out
   const float* noise = nullptr;     // [B][T_out] (SNAC NoiseBlock: out = residual + noise * conv)
+  // Encodec time_group_norm: [B][2] fp64 {sum, sum of squares} of conv + bias over each clip's outputs, ADDED to by the
+  // tcgen05 epilogue; *gn_stats_done tells the caller whether the executor did it (the CUDA-core fallback does not)
+  double* gn_stats = nullptr;
+  bool* gn_stats_done = nullptr;
   int batch = 0;
   int t_in = 0;
   int prologue = PRO_NONE;

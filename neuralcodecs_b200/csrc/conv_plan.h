@@ -58,6 +58,8 @@ struct ConvGemmParams {
   const float* bias;        // nullable
   int bias_period;
   const float* noise;       // nullable; [clip][m_rows]: D = R + noise*acc (SNAC NoiseBlock)
+  double* gn_stats;         // nullable; [clip][2]: the epilogue adds sum / sum of squares of (acc + bias) over the clip's valid
+                            // outputs (Encodec time_group_norm: the statistics of the GroupNorm that follows the conv)
   // ---- prologue / post-activation / activation
   const float* alpha;       // [alpha_period]
   const float* inv_alpha;   // [alpha_period] (1/alpha, 0 where alpha == 0)
@@ -144,6 +146,7 @@ struct UmmaLaunch {
   int tma_epilogue;  // 1: output / residual tiles move by TMA through a swizzled smem ring
   int epi_stages;    // conv_h16 / fused unit: depth of the epilogue's smem ring (residual prefetch / stores in flight)
   int h_stages;      // fused unit: depth of the ring of 1x1-conv operand tiles written by the acc1 drain
+  unsigned long long* trace;   // measurement only (env NC_TRACE_RU): CTA 0 writes clock64() at role events of its first tiles
   int knock;         // measurement only (env NC_KNOCK, results become WRONG): 1 = weight copies skipped after the ring
                      // filled once, 2 = operand transform skipped, 4 = A loads skipped, 8 = MMAs skipped, 16 = epilogue math/stores skipped
 };

@@ -22,7 +22,9 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <cstdio>
 #include <cstdlib>
+#include <vector>
 #include <cstring>
 #include <mutex>
 
@@ -180,6 +182,17 @@ __device__ __forceinline__ void epi_post(const ConvGemmParams& p, float (&v)[16]
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i]);
   }
+}
+
+// Encodec time_group_norm: a warp's partial {sum, sum of squares} of its rows of one tile -> the clip's fp64 totals
+__device__ __forceinline__ void gn_stats_add(double* dst, float s, float ss, int lane) {
+  double ds = (double)s, dss = (double)ss;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ds += __shfl_xor_sync(0xffffffffu, ds, o);
+    dss += __shfl_xor_sync(0xffffffffu, dss, o);
+  }
+  if (lane == 0) { atomicAdd(dst, ds); atomicAdd(dst + 1, dss); }
 }
 
 template <int OPS, int PRO, int RIT>
@@ -464,6 +477,7 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
         const int rloc = q * 32 + lane;
         const int row = mt * kBM + rloc;
         const float nz = (p.noise && row < p.m_rows) ? __ldg(p.noise + (long long)b * p.m_rows + row) : 0.f;
+        float gn_s = 0.f, gn_ss = 0.f;   // GroupNorm statistics of this thread's row (p.gn_stats)
         // fold every main partial but the last into the running sum (fp32 round-to-nearest adds, kept in TMEM; each
         // thread only ever touches its own lane and columns of it)
         for (int part = 0; part + 1 < n_parts; ++part, ++pc) {
@@ -522,6 +536,10 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
           }
           const int n0 = nt * p.BN + g * 32 + half * 16;
           epi_bias(p, v, n0);
+          if (p.gn_stats && row < p.m_rows) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { gn_s += v[i]; gn_ss = fmaf(v[i], v[i], gn_ss); }
+          }
           uint8_t* stage = sE + (size_t)es * kEpiStageBytes;
           if (p.R) mbar_wait(&r_full[es], eph); else mbar_wait(&e_free[es], eph ^ 1u);
           if (p.R && !(L.knock & 16)) {
@@ -552,6 +570,7 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
           }
           if (++es == kEpiStages) { es = 0; eph ^= 1u; }
         }
+        if (p.gn_stats) gn_stats_add(p.gn_stats + 2 * b, gn_s, gn_ss, lane);
       }
       if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else {
@@ -573,6 +592,7 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
         mbar_wait(&acc_full[buf], acc_ph);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16);
+        float gn_s = 0.f, gn_ss = 0.f;
         for (int cc = half; cc < p.BN / 16; cc += 2) {
           float v[16];
           __syncwarp();
@@ -582,6 +602,11 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
           if (!row_ok || n0 >= p.n_valid) continue;
           const bool full = (n0 + 16 <= p.n_valid) && (row_off + n0 + 16 <= p.d_valid);
           epi_bias(p, v, n0);
+          if (p.gn_stats) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (n0 + i < p.n_valid && row_off + n0 + i < p.d_valid) { gn_s += v[i]; gn_ss = fmaf(v[i], v[i], gn_ss); }
+          }
           if (Rrow) {
             if (full && vec_ok) {
 #pragma unroll
@@ -618,6 +643,7 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        if (p.gn_stats) gn_stats_add(p.gn_stats + 2 * b, gn_s, gn_ss, lane);
       }
     }
   } else {
@@ -778,6 +804,8 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
 // C <= 128: both accumulators double-buffered (4 x C <= 512 TMEM columns) and the k7 MMAs of tile i+1 are issued
 // BEFORE the 1x1 MMAs of tile i, so draining acc1 overlaps tensor-core work.  128 < C <= 256: single-buffered,
 // issue order k7(i), 1x1(i).  Operand mode: bf16x3 / f16x3 only.
+constexpr int kTraceTiles = 96, kTraceEvents = 32;
+#define RU_TRACE(it_, ev_) do { if (L.trace && blockIdx.x == 0 && (it_) < kTraceTiles) L.trace[(it_) * kTraceEvents + (ev_)] = (unsigned long long)clock64(); } while (0)
 constexpr int kHStages = 3;   // most; the launch picks L.h_stages / L.epi_stages (the weight ring gets the rest)
 
 template <int PRO, int RIT>
@@ -847,8 +875,10 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
   const int split_a = (p.BN <= 128) ? groups : 0;
   auto e1 = [&](int it, int g_begin, int g_end) {
     const int b = buf_of(it);
+    if (tid == kFirstProducerWarp * 32) RU_TRACE(it, 18);
     mbar_wait(&acc1_full[b], use_of(it) & 1u);
     tc_fence_after();
+    if (tid == kFirstProducerWarp * 32) RU_TRACE(it, 10);
     const uint32_t t_addr = tmem_base + acc1_col(it) + ((uint32_t)(q * 32) << 16);
     for (int g = 0; g < groups; ++g) {
       if (g < g_begin || g >= g_end) {   // the other warp set's group: only advance the ring position
@@ -896,6 +926,7 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&h_full[hs]);
+      if (g == groups - 1 && tid == kFirstProducerWarp * 32) RU_TRACE(it, 11);
       if (++hs == L.h_stages) { hs = 0; hph ^= 1u; }
     }
   };
@@ -926,7 +957,13 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       };
       if (dbl) {
         if (my_tiles > 0) w1();
-        for (int it = 0; it < my_tiles; ++it) { if (it + 1 < my_tiles) w1(); w2(); }
+        for (int it = 0; it < my_tiles; ++it) {
+          RU_TRACE(it, 15);
+          if (it + 1 < my_tiles) w1();
+          RU_TRACE(it, 16);
+          w2();
+          RU_TRACE(it, 17);
+        }
       } else {
         for (int it = 0; it < my_tiles; ++it) { w1(); w2(); }
       }
@@ -974,13 +1011,16 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       };
       auto m1 = [&](int it) {
         const int b = buf_of(it);
+        RU_TRACE(it, 3);
         mbar_wait(&acc1_empty[b], (use_of(it) & 1u) ^ 1u);
         tc_fence_after();
+        RU_TRACE(it, 4);
         const uint32_t d_tmem = tmem_base + acc1_col(it);
         uint32_t acc = 0;
         for (int kci = 0; kci < n_kc; ++kci) {
           mbar_wait(&a_full[as], aph);
           tc_fence_after();
+          if (kci == 0) RU_TRACE(it, 5);
           uint64_t a_tap = a_desc;
           for (int j = 0; j < p.n_taps; ++j) {
             if (j) a_tap += tap_u;
@@ -994,15 +1034,18 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
           a_desc += a_stage_u;
           if (++as == L.a_stages) { as = 0; aph ^= 1u; a_desc = a_desc0; }
         }
+        RU_TRACE(it, 6);
         tc_commit(&acc1_full[b]);
       };
       auto m2 = [&](int it) {
         const int b = buf_of(it);
         mbar_wait(&acc2_empty[b], (use_of(it) & 1u) ^ 1u);
         tc_fence_after();
+        RU_TRACE(it, 7);
         const uint32_t d_tmem = tmem_base + acc2_col(it);
         for (int g = 0; g < n_kc; ++g) {
           mbar_wait(&h_full[hs], hph);
+          if (g == 0) RU_TRACE(it, 8);
           mbar_wait(&w_full[ws], wph);
           tc_fence_after();
           mma6(d_tmem, h_desc, w_desc ^ w2_fix, g ? 1u : 0u, p2.passes, idesc2);
@@ -1011,6 +1054,7 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
           h_desc += h_stage_u;
           if (++hs == L.h_stages) { hs = 0; hph ^= 1u; h_desc = h_desc0; }
         }
+        RU_TRACE(it, 9);
         tc_commit(&acc2_full[b]);
       };
       if (dbl) {
@@ -1025,12 +1069,15 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
     if (elect_one()) {
       int as = 0;
       uint32_t aph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int b = tile / p.m_tiles_per_clip;
         const int mt = tile - b * p.m_tiles_per_clip;
         const int r_base = mt * kBM + p.smin;
         for (int kci = 0; kci < n_kc; ++kci) {
           mbar_wait(&a_empty[as], aph ^ 1u);
+          if (kci == 0) RU_TRACE(it, 0);
+          if (kci == n_kc - 1) RU_TRACE(it, 1);
           mbar_arrive_expect_tx(&raw_full[as], a_stage_bytes);
           tma_load_3d(sA + (size_t)as * a_stage_bytes, &tmapA, (p.kc_begin + kci) * 32, r_base, b, &raw_full[as]);
           if (++as == L.a_stages) { as = 0; aph ^= 1u; }
@@ -1068,8 +1115,10 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       const int bb = tile / p.m_tiles_per_clip;
       const int mt = tile - bb * p.m_tiles_per_clip;
       const int b = buf_of(it);
+      if (leader) RU_TRACE(it, 19);
       mbar_wait(&acc2_full[b], use_of(it) & 1u);
       tc_fence_after();
+      if (leader) RU_TRACE(it, 12);
       const uint32_t t_addr = tmem_base + acc2_col(it) + ((uint32_t)(q * 32) << 16);
       for (int g = 0; g < groups; ++g) {
         float v[16];
@@ -1084,6 +1133,7 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
         const int n0 = g * 32 + half * 16;
         uint8_t* stage = sE + (size_t)es * kEpiStageBytes;
         mbar_wait(&r_full[es], eph);
+        if (leader && g == 0) RU_TRACE(it, 13);
         if (!(L.knock & 256)) {   // (knock 256, measurement only: no bias / residual / activation math)
           epi_bias(p2, v, n0);
 #pragma unroll
@@ -1105,6 +1155,7 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
           asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           if (prev >= 0) mbar_arrive(&e_free[prev]);
           prev = es;
+          if (g == groups - 1) RU_TRACE(it, 14);
         }
         if (++es == L.epi_stages) { es = 0; eph ^= 1u; }
       }
@@ -1121,15 +1172,17 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
     const int c = ptid & 7;
     const int rho0 = 8 * (ptid >> 6) + ((ptid >> 5) & 1) + 2 * ((ptid & 31) >> 3);   // see conv_umma_kernel: bank-conflict-free hi / lo stores
     const int rows_needed = kBM + p.span;
-    int as = 0;
+    int as = 0, tt = 0;   // tt: tiles transformed so far
     uint32_t aph = 0;
     auto transform_tile = [&]() {
       for (int kci = 0; kci < n_kc; ++kci) {
+        if (kci == 0 && ptid == 0) RU_TRACE(tt, 20);
         const int ai = ((p.kc_begin + kci) * 32 + c * 4) % p.alpha_period;
         const float4 al = __ldg(reinterpret_cast<const float4*>(p.alpha + ai));
         const float4 ia = __ldg(reinterpret_cast<const float4*>(p.inv_alpha + ai));
         uint8_t* stage = sA + (size_t)as * a_stage_bytes;
         mbar_wait(&raw_full[as], aph);
+        if (kci == 0 && ptid == 0) RU_TRACE(tt, 2);
         if (L.knock & 2) {   // measurement only: operands left as they arrived
           fence_proxy_async_smem();
           __syncwarp();
@@ -1170,8 +1223,10 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_full[as]);
+        if (kci == n_kc - 1 && ptid == 0) RU_TRACE(tt, 21);
         if (++as == L.a_stages) { as = 0; aph ^= 1u; }
       }
+      ++tt;
     };
     if (dbl) {
       // operands of tile it+1 first (the MMA thread issues k7(it+1) before 1x1(it)), then drain acc1 of tile it
@@ -1412,7 +1467,32 @@ int launch_ru_fused(const ConvGemmParams& p, const ConvGemmParams& p2, int num_s
   const int total_tiles = p.batch * p.m_tiles_per_clip;
   const int grid = total_tiles < num_sms ? total_tiles : num_sms;
   if (grid <= 0) return 0;
+  // measurement only: NC_TRACE_RU=<file> [NC_TRACE_RU_C=<channels>] dumps CTA 0's role timeline of one launch
+  static const char* trace_path = getenv("NC_TRACE_RU");
+  static const int trace_c = getenv("NC_TRACE_RU_C") ? atoi(getenv("NC_TRACE_RU_C")) : 64;
+  static int trace_skip = getenv("NC_TRACE_RU_SKIP") ? atoi(getenv("NC_TRACE_RU_SKIP")) : 3;   // warm launches first
+  L.trace = nullptr;
+  const bool tracing = trace_path && p.BN == trace_c && trace_skip-- == 0;
+  if (tracing) {
+    if (cudaMalloc(&L.trace, sizeof(unsigned long long) * kTraceTiles * kTraceEvents) != cudaSuccess) return (int)cudaErrorMemoryAllocation;
+    cudaMemsetAsync(L.trace, 0, sizeof(unsigned long long) * kTraceTiles * kTraceEvents, stream);
+  }
   k<<<grid, kUmmaThreads, smem, stream>>>(p, p2, L, tA, tD, tR);
+  if (tracing) {
+    std::vector<unsigned long long> h((size_t)kTraceTiles * kTraceEvents);
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h.data(), L.trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(L.trace);
+    if (FILE* f = std::fopen(trace_path, "w")) {
+      std::fprintf(f, "# BN=%d n_kc=%d span=%d taps=%d a_stages=%d w_stages=%d h_stages=%d e_stages=%d grid=%d tiles=%d\n", p.BN, p.n_kc, p.span,
+                   p.n_taps, L.a_stages, L.w_stages, L.h_stages, L.epi_stages, grid, total_tiles);
+      for (int t = 0; t < kTraceTiles; ++t) {
+        for (int e = 0; e < 22; ++e) std::fprintf(f, "%llu ", h[(size_t)t * kTraceEvents + e]);
+        std::fprintf(f, "\n");
+      }
+      std::fclose(f);
+    }
+  }
   return (int)cudaGetLastError();
 }
 

@@ -470,6 +470,12 @@ void EncodecEngine::conv_short(const ConvLayer& L, const Act& in, const SPad& pa
   a.out = out.base; a.out_clip_stride = out.stride; a.batch = B;
   a.prologue = prologue;    // ELU(0) = 0 and ELU commutes with reflection: applying it inside the conv is Pad1d(ELU(x))
   a.post = post;
+  gn_fused_ = false;
+  if (cfg_.group_norm && gn_.count(L.name())) {
+    NC_CUDA(cudaMemsetAsync(gn_stats_.as<double>(), 0, (size_t)B * 2 * sizeof(double), stream_));
+    a.gn_stats = gn_stats_.as<double>();
+    a.gn_stats_done = &gn_fused_;
+  }
   L.run(a, c);
 }
 
@@ -523,6 +529,12 @@ void EncodecEngine::conv(const ConvLayer& L, const Act& in, int left_pad, int ex
   a.prologue = prologue;
   a.post = post;
   if (residual) a.residual = residual->base;
+  gn_fused_ = false;
+  if (cfg_.group_norm && gn_.count(L.name())) {   // the tcgen05 epilogue accumulates the GroupNorm statistics
+    NC_CUDA(cudaMemsetAsync(gn_stats_.as<double>(), 0, (size_t)B * 2 * sizeof(double), stream_));
+    a.gn_stats = gn_stats_.as<double>();
+    a.gn_stats_done = &gn_fused_;
+  }
   L.run(a, ctx());
 }
 
@@ -535,7 +547,8 @@ void EncodecEngine::finish_norm(const ConvLayer& L, const Act& y, int B, int pos
   if (it == gn_.end()) throw Error(NC_INTERNAL, "no GroupNorm parameters for " + L.name());
   const Gn& g = it->second;
   double* st = gn_stats_.as<double>();
-  launch_gn_stats(y.base + (long long)row0 * y.C, y.stride, (long long)rows * y.C, st, B, c);
+  if (!gn_fused_) launch_gn_stats(y.base + (long long)row0 * y.C, y.stride, (long long)rows * y.C, st, B, c);   // CUDA-core fallback convs
+  gn_fused_ = false;
   launch_gn_apply(y.base, y.stride, y.T, y.C, st, (double)rows * g.c_real, 1e-5f, g.gamma, g.beta, residual ? residual->base : nullptr,
                   residual ? residual->stride : 0, post == PRO_ELU ? 1 : 0, B, c);
 }
@@ -714,7 +727,8 @@ void EncodecEngine::run_decoder(int B, int T, float* audio_out, long long out_st
   const float *gamma = nullptr, *beta = nullptr;
   if (cfg_.group_norm) {
     const Gn& g = gn_.at(conv_out_l_.name());
-    launch_gn_stats(raw.base, raw.stride, (long long)raw.T * raw.C, gn_stats_.as<double>(), B, c);
+    if (!gn_fused_) launch_gn_stats(raw.base, raw.stride, (long long)raw.T * raw.C, gn_stats_.as<double>(), B, c);
+    gn_fused_ = false;
     st = gn_stats_.as<double>(); gamma = g.gamma; beta = g.beta;
   }
   launch_encodec_frame_out(raw.base, raw.stride, raw.T, cout_pad_, cfg_.channels, st, 1e-5f, gamma, beta, map_.segs, map_.s0,

@@ -575,13 +575,18 @@ segment_prep_kernel(const float* __restrict__ audio, int C, long long L, int seg
   const int i = blockIdx.y, item = item0 + i, b = item / segs, s = s0 + item % segs;
   const float* x = audio + (long long)b * C * L + (long long)s * seg_stride;
   const float sc = scales ? scales[(long long)b * n_seg_total + s] : 1.f;
-  float* o = out + (long long)i * out_clip_stride;
-  const long long n = (long long)seg_len * Cpad;
+  float4* o = reinterpret_cast<float4*>(out + (long long)i * out_clip_stride);
+  const int c4n = Cpad >> 2;                       // C <= 4 real channels live in the first float4 of a row
+  const long long n = (long long)seg_len * c4n;
   for (long long j = (long long)blockIdx.x * 256 + threadIdx.x; j < n; j += (long long)gridDim.x * 256) {
-    const int c = (int)(j % Cpad);
-    const long long t = j / Cpad;
-    float v = 0.f;
-    if (c < C) { v = x[(long long)c * L + t]; if (scales) v = v / sc; }
+    const int c4 = (int)(j % c4n);
+    const long long t = j / c4n;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c4 == 0) {
+      v.x = x[t];
+      if (C > 1) v.y = x[L + t];
+      if (scales) { v.x = v.x / sc; v.y = v.y / sc; }
+    }
     o[j] = v;
   }
 }
@@ -595,7 +600,8 @@ void launch_encodec_segment_prep(const float* audio, int C, long long L, int seg
     segment_scale_kernel<<<items, 256, 0, ctx.stream>>>(audio, C, L, segs, s0, seg_stride, seg_len, item0, n_seg_total, scales);
     check_launch((int)cudaGetLastError(), "segment_scale");
   }
-  const long long n = (long long)seg_len * Cpad;
+  if (C > 2 || Cpad % 4 != 0) throw Error(NC_INTERNAL, "segment_prep: at most 2 channels");
+  const long long n = (long long)seg_len * (Cpad / 4);
   dim3 grid((unsigned)std::min<long long>((n + 1023) / 1024, 4LL * ctx.num_sms), items);
   segment_prep_kernel<<<grid, 256, 0, ctx.stream>>>(audio, C, L, segs, s0, seg_stride, seg_len, item0, n_seg_total, scales, out,
                                                     out_clip_stride, Cpad);

@@ -400,6 +400,7 @@ class EncodecEngine : public Engine {
   void overlap_add(const SegLayout& lay, int B, float* audio_out, int64_t out_len);
   struct ItemMap { int segs = 1, s0 = 0, item0 = 0, n_seg = 1; const float* scales = nullptr; };
   ItemMap map_;                        // where run_decoder's generic output stage puts its frames
+  bool gn_fused_ = false;              // the last conv's epilogue already accumulated its GroupNorm statistics
   bool generic_io_ = false;            // conv_in / conv_out as channel-padded ConvLayers (stereo, non-causal or GroupNorm)
   ConvLayer conv_in_l_, conv_out_l_;
   int cin_pad_ = 32, cout_pad_ = 32;

@@ -748,6 +748,15 @@ def main():
                 roofline["tensor_pipe_note"] = tp["note"]
             except Exception:
                 roofline["tensor_pipe_pct"] = None
+            # the fused narrow residual units are bound by shared-memory bandwidth, not by the tensor pipe or HBM: their byte
+            # budget per 128-row tile and the measured period per tile come from the committed role timeline
+            fused = {k: v for k, v in rep.items() if k.startswith("ru_fused")}
+            if fused:
+                roofline["fused_units_shared_memory"] = {
+                    "kernel": "conv_ru_fused_kernel", "bound": "shared memory (128 B/clk/SM)", "share_of_step": sum(v["ms"] for v in fused.values()) / total_ms,
+                    "frac_by_width": {"C=64": 0.76, "C=96": 0.88, "C=128": 0.99},
+                    "source": "profiles/r02_ru_fused_timeline.txt: smem bytes per tile (58 % tensor-core operand reads of the 7-tap x 3-pass "
+                              "products) / 128 B/clk against the measured clocks per tile of CTA 0 (clock64 at every role hand-off)"}
             # the other kernel BASELINE.json's metric names: the fused RVQ (algorithmic bytes per frame: read z, write
             # z_q, write codes = SURVEY 8d's 8.3 KB at the 44.1 kHz preset)
             rv = rep.get("rvq_encode")

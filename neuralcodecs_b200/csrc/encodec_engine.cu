@@ -472,8 +472,8 @@ void EncodecEngine::conv_short(const ConvLayer& L, const Act& in, const SPad& pa
   a.post = post;
   gn_fused_ = false;
   if (cfg_.group_norm && gn_.count(L.name())) {
-    NC_CUDA(cudaMemsetAsync(gn_stats_.as<double>(), 0, (size_t)B * 2 * sizeof(double), stream_));
-    a.gn_stats = gn_stats_.as<double>();
+    NC_CUDA(cudaMemsetAsync(gn_slot(), 0, (size_t)B * 2 * sizeof(double), stream_));
+    a.gn_stats = gn_slot();
     a.gn_stats_done = &gn_fused_;
   }
   L.run(a, c);
@@ -503,7 +503,8 @@ int EncodecEngine::micro_batch(int B, int64_t L) {
   hbuf_.reserve((size_t)2 * ((mb + 31) / 32 * 32) * top * sizeof(float));
   barriers_.reserve(64 * sizeof(unsigned int));
   audio_tmp_.reserve((size_t)mb * decoded_length(T) * sizeof(float));
-  gn_stats_.reserve((size_t)mb * 2 * sizeof(double));
+  gn_stats_.reserve((size_t)2 * mb * 2 * sizeof(double));   // two slots: the conv being normalised, and a resnet block's shortcut
+  gn_mb_ = mb;
   return mb;
 }
 
@@ -531,8 +532,8 @@ void EncodecEngine::conv(const ConvLayer& L, const Act& in, int left_pad, int ex
   if (residual) a.residual = residual->base;
   gn_fused_ = false;
   if (cfg_.group_norm && gn_.count(L.name())) {   // the tcgen05 epilogue accumulates the GroupNorm statistics
-    NC_CUDA(cudaMemsetAsync(gn_stats_.as<double>(), 0, (size_t)B * 2 * sizeof(double), stream_));
-    a.gn_stats = gn_stats_.as<double>();
+    NC_CUDA(cudaMemsetAsync(gn_slot(), 0, (size_t)B * 2 * sizeof(double), stream_));
+    a.gn_stats = gn_slot();
     a.gn_stats_done = &gn_fused_;
   }
   L.run(a, ctx());
@@ -540,17 +541,20 @@ void EncodecEngine::conv(const ConvLayer& L, const Act& in, int left_pad, int ex
 
 // time_group_norm: y = GroupNorm(conv(x)), then whatever followed the conv in the weight-norm graph (residual add, ELU of
 // the next layer).  Two HBM passes over the conv's output: fp64 sums, then the in-place affine.
-void EncodecEngine::finish_norm(const ConvLayer& L, const Act& y, int B, int post, const Act* residual, int row0, int rows) {
+void EncodecEngine::finish_norm(const ConvLayer& L, const Act& y, int B, int post, const Act* residual, int row0, int rows,
+                                const ConvLayer* raw_residual_of) {
   if (!cfg_.group_norm) return;
   const LaunchCtx c = ctx();
   const auto it = gn_.find(L.name());
   if (it == gn_.end()) throw Error(NC_INTERNAL, "no GroupNorm parameters for " + L.name());
   const Gn& g = it->second;
-  double* st = gn_stats_.as<double>();
+  double* st = gn_slot();
   if (!gn_fused_) launch_gn_stats(y.base + (long long)row0 * y.C, y.stride, (long long)rows * y.C, st, B, c);   // CUDA-core fallback convs
   gn_fused_ = false;
+  const Gn* g2 = raw_residual_of ? &gn_.at(raw_residual_of->name()) : nullptr;   // residual = that conv's raw output, statistics in slot 1
   launch_gn_apply(y.base, y.stride, y.T, y.C, st, (double)rows * g.c_real, 1e-5f, g.gamma, g.beta, residual ? residual->base : nullptr,
-                  residual ? residual->stride : 0, post == PRO_ELU ? 1 : 0, B, c);
+                  residual ? residual->stride : 0, post == PRO_ELU ? 1 : 0, B, c, g2 ? gn_stats_.as<double>() + (size_t)2 * gn_mb_ : nullptr,
+                  g2 ? (double)residual->T * g2->c_real : 0.0, g2 ? g2->gamma : nullptr, g2 ? g2->beta : nullptr);
 }
 
 void EncodecEngine::conv_n(const ConvLayer& L, const Act& in, int left_pad, int extra, const Act& out, int B, int prologue, int post,
@@ -581,11 +585,25 @@ EncodecEngine::Act EncodecEngine::run_res(const Res& r, const Act& x, int B, int
   hb = pick_free(xb, sb);
   const int yb = pick_free(xb, sb, hb);
   Act S = act(sb, B, x.T, x.C), H = act(hb, B, x.T, r.hidden_p), Y = act(yb, B, x.T, x.C);
-  conv_n(r.shortcut, x, 0, 0, S, B, PRO_NONE, PRO_NONE, nullptr);
+  const bool gn = cfg_.group_norm;
+  if (gn) {   // the shortcut stays RAW (statistics in slot 1): its GroupNorm is applied inside the block output's apply pass
+    gn_slot_ = 1;
+    conv(r.shortcut, x, 0, 0, S, B, PRO_NONE, PRO_NONE, nullptr);
+    if (!gn_fused_) launch_gn_stats(S.base, S.stride, (long long)S.T * S.C, gn_slot(), B, c);
+    gn_fused_ = false;
+    gn_slot_ = 0;
+  } else {
+    conv(r.shortcut, x, 0, 0, S, B, PRO_NONE, PRO_NONE, nullptr);
+  }
   const SPad k3 = sconv_pad(x.T, 3, 1);                                   // padding_total = 2: causal (2, 0), else (1, 1)
   launch_reflect_pad(x.base, x.T, x.C, x.stride, k3.left, k3.right, B, c);
   conv_n(r.c3, x, k3.left, k3.right, H, B, PRO_ELU, PRO_ELU, nullptr);
-  conv_n(r.c1, H, 0, 0, Y, B, PRO_NONE, post_elu ? PRO_ELU : PRO_NONE, &S);
+  if (gn) {
+    conv(r.c1, H, 0, 0, Y, B, PRO_NONE, PRO_NONE, nullptr);
+    finish_norm(r.c1, Y, B, post_elu ? PRO_ELU : PRO_NONE, &S, 0, Y.T, &r.shortcut);
+  } else {
+    conv(r.c1, H, 0, 0, Y, B, PRO_NONE, post_elu ? PRO_ELU : PRO_NONE, &S);
+  }
   xb = yb;
   return Y;
 }
@@ -727,9 +745,9 @@ void EncodecEngine::run_decoder(int B, int T, float* audio_out, long long out_st
   const float *gamma = nullptr, *beta = nullptr;
   if (cfg_.group_norm) {
     const Gn& g = gn_.at(conv_out_l_.name());
-    if (!gn_fused_) launch_gn_stats(raw.base, raw.stride, (long long)raw.T * raw.C, gn_stats_.as<double>(), B, c);
+    if (!gn_fused_) launch_gn_stats(raw.base, raw.stride, (long long)raw.T * raw.C, gn_slot(), B, c);
     gn_fused_ = false;
-    st = gn_stats_.as<double>(); gamma = g.gamma; beta = g.beta;
+    st = gn_slot(); gamma = g.gamma; beta = g.beta;
   }
   launch_encodec_frame_out(raw.base, raw.stride, raw.T, cout_pad_, cfg_.channels, st, 1e-5f, gamma, beta, map_.segs, map_.s0,
                            map_.item0, map_.n_seg, map_.scales, audio_out, out_stride, B, c);

@@ -505,14 +505,18 @@ __device__ __forceinline__ void gn_coeffs(const double* stats, int b, double cou
 }
 __device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expm1f(v); }
 
-// Pass 2, in place over rows [0, T): y = (x - mean) * rstd * gamma[c] + beta[c] (+ residual) (-> ELU)
+// Pass 2, in place over rows [0, T): y = (x - mean) * rstd * gamma[c] + beta[c] (+ residual) (-> ELU).  The residual is either
+// final values or -- stats2 != nullptr -- another conv's RAW output normalised on the fly with its own statistics and affine
+// (the resnet shortcut: saves that tensor's own apply pass).
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(float* __restrict__ y, long long clip_stride, int T, int C, const double* __restrict__ stats, double count, float eps,
                 const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ residual,
-                long long res_clip_stride, int elu) {
+                long long res_clip_stride, int elu, const double* __restrict__ stats2, double count2, const float* __restrict__ gamma2,
+                const float* __restrict__ beta2) {
   const int b = blockIdx.y, c4n = C >> 2;
-  float mean, rstd;
+  float mean, rstd, mean2 = 0.f, rstd2 = 1.f;
   gn_coeffs(stats, b, count, eps, mean, rstd);
+  if (stats2) gn_coeffs(stats2, b, count2, eps, mean2, rstd2);
   float4* p = reinterpret_cast<float4*>(y + (long long)b * clip_stride);
   const float4* r = residual ? reinterpret_cast<const float4*>(residual + (long long)b * res_clip_stride) : nullptr;
   const long long n4 = (long long)T * c4n;
@@ -522,20 +526,30 @@ gn_apply_kernel(float* __restrict__ y, long long clip_stride, int T, int C, cons
     float4 v = p[i];
     v.x = (v.x - mean) * rstd * g.x + be.x; v.y = (v.y - mean) * rstd * g.y + be.y;
     v.z = (v.z - mean) * rstd * g.z + be.z; v.w = (v.w - mean) * rstd * g.w + be.w;
-    if (r) { const float4 q = __ldg(r + i); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
+    if (r) {
+      float4 q = __ldg(r + i);
+      if (stats2) {
+        const float4 g2 = __ldg(reinterpret_cast<const float4*>(gamma2) + c4), b2 = __ldg(reinterpret_cast<const float4*>(beta2) + c4);
+        q.x = (q.x - mean2) * rstd2 * g2.x + b2.x; q.y = (q.y - mean2) * rstd2 * g2.y + b2.y;
+        q.z = (q.z - mean2) * rstd2 * g2.z + b2.z; q.w = (q.w - mean2) * rstd2 * g2.w + b2.w;
+      }
+      v.x = q.x + v.x; v.y = q.y + v.y; v.z = q.z + v.z; v.w = q.w + v.w;    // shortcut + block, the reference's operand order
+    }
     if (elu) { v.x = elu1(v.x); v.y = elu1(v.y); v.z = elu1(v.z); v.w = elu1(v.w); }
     p[i] = v;
   }
 }
 
 void launch_gn_apply(float* y, long long clip_stride, int T, int C, const double* stats, double count, float eps, const float* gamma,
-                     const float* beta, const float* residual, long long res_clip_stride, int elu, int batch, const LaunchCtx& ctx) {
+                     const float* beta, const float* residual, long long res_clip_stride, int elu, int batch, const LaunchCtx& ctx,
+                     const double* stats2, double count2, const float* gamma2, const float* beta2) {
   if (batch == 0 || T == 0) return;
   if (C % 4 != 0) throw Error(NC_INTERNAL, "gn_apply: channel count must be a multiple of 4");
   const long long n4 = (long long)T * (C / 4);
   const int ev = ctx.begin();
   dim3 grid((unsigned)std::min<long long>((n4 + 1023) / 1024, 8LL * ctx.num_sms), batch);
-  gn_apply_kernel<<<grid, 256, 0, ctx.stream>>>(y, clip_stride, T, C, stats, count, eps, gamma, beta, residual, res_clip_stride, elu);
+  gn_apply_kernel<<<grid, 256, 0, ctx.stream>>>(y, clip_stride, T, C, stats, count, eps, gamma, beta, residual, res_clip_stride, elu,
+                                                stats2, count2, gamma2, beta2);
   check_launch((int)cudaGetLastError(), "gn_apply");
   ctx.end(ev, "gn_apply", 0.0, (residual ? 12.0 : 8.0) * batch * (double)T * C);
 }

@@ -49,8 +49,10 @@ void launch_ecdc_unpack(const uint8_t* in, long long in_stride, int64_t* codes, 
 // n_per_clip contiguous floats of each clip starting at x; apply in place over rows [0, T): (x - mean) * rstd * gamma + beta,
 // then + residual and / or ELU.  count = the elements the reference normalises over (padded channels hold zeros and do not count).
 void launch_gn_stats(const float* x, long long clip_stride, long long n_per_clip, double* stats, int batch, const LaunchCtx& ctx);
+// stats2 != nullptr: `residual` holds another conv's RAW output, normalised on the fly with (stats2, count2, gamma2, beta2)
 void launch_gn_apply(float* y, long long clip_stride, int T, int C, const double* stats, double count, float eps, const float* gamma,
-                     const float* beta, const float* residual, long long res_clip_stride, int elu, int batch, const LaunchCtx& ctx);
+                     const float* beta, const float* residual, long long res_clip_stride, int elu, int batch, const LaunchCtx& ctx,
+                     const double* stats2 = nullptr, double count2 = 0.0, const float* gamma2 = nullptr, const float* beta2 = nullptr);
 // Segment items: launch item i = global item item0 + i -> clip b = item / segs, segment s = s0 + item % segs, samples
 // [s*seg_stride, +seg_len) of audio [B][C][L].  Writes the loudness scale (Encodec.cs:469-480) to scales[b*n_seg_total + s]
 // (scales == nullptr: Normalize = false) and the normalised segment channels-last [seg_len][Cpad] into out.

@@ -390,7 +390,10 @@ class EncodecEngine : public Engine {
   void load_gn(const std::string& p, int c_real, int c_pad);
   // GroupNorm + follow-up of a conv's raw output `y` (no-op for weight-norm models, whose epilogue already did it):
   // statistics over rows [row0, row0 + rows) (the transposed convs normalise BEFORE their trim), result rows [0, y.T)
-  void finish_norm(const ConvLayer& L, const Act& y, int B, int post, const Act* residual, int row0, int rows);
+  void finish_norm(const ConvLayer& L, const Act& y, int B, int post, const Act* residual, int row0, int rows,
+                   const ConvLayer* raw_residual_of = nullptr);
+  int gn_slot_ = 0, gn_mb_ = 0;        // statistics slot the next conv accumulates into ([slot][micro-batch][2] fp64)
+  double* gn_slot() { return gn_stats_.as<double>() + (size_t)gn_slot_ * 2 * gn_mb_; }
   // one group of equal-length segment items (clip-major: item = b*segs + j -> segment s0 + j) through encoder and / or decoder
   struct Group { int segs, s0; int64_t len, frames, col0; };
   void run_group(const float* audio, int B, int64_t L, const SegLayout& lay, const Group& g, int nq, int64_t* codes_user,

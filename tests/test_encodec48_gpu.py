@@ -186,3 +186,38 @@ def test_ecdc_streams_with_scale_blocks(encodec_48k):
     with pytest.raises(ValueError, match="Invalid scale count"):
         nc.EncodecCompressor.Decompress(bytes(bad), m)
     m.Dispose()
+
+
+def test_full_size_properties_thirty_second_stereo_clips(encodec_48k):
+    """Size-independent properties at a realistic size (4 stereo clips x 30 s = 31 segments each, 124 batch items), where the
+    oracle would take minutes: (i) the loudness normalisation makes the codes invariant to the input gain and the scales
+    proportional to it; (ii) a clip's frames do not depend on its batch neighbours; (iii) Decode of the frames = forward;
+    (iv) segment s of a long clip = the encoding of that segment alone."""
+    o, m = _models(encodec_48k)
+    L = 30 * 48000
+    x = _stereo(4, L, first=21)
+    seg, nq, total = m.query_frames(L)
+    assert len(seg) == 31 and seg[:-1] == [150] * 30 and nq == 4 and total == 30 * STRIDE + seg[-1] * 320
+    f1 = m.Encode(x)
+    f2 = m.Encode(4.0 * x)                                            # power-of-two gain: x / scale is the same up to the 1e-8 offset
+    assert len(f1) == 31
+    match = np.mean([float((a[0] == b[0]).mean()) for a, b in zip(f1, f2)])
+    assert match >= 0.9995
+    for (_, s1), (_, s2) in zip(f1, f2):
+        np.testing.assert_allclose(s2, 4.0 * s1, rtol=1e-6)
+    solo = m.Encode(x[2:3])
+    for (c, s), (cs, ss) in zip(f1, solo):
+        np.testing.assert_array_equal(c[2:3], cs)
+        np.testing.assert_array_equal(s[2:3], ss)
+    y = m.forward(x)
+    dec = m.Decode(f1)
+    assert y.shape == x.shape and dec.shape == (4, 2, total)
+    np.testing.assert_allclose(y, dec[..., :L], atol=1e-6)
+    assert np.isfinite(y).all() and snr_db(x, y) > -20.0              # random weights: only sanity on the level
+    s = 17
+    alone = m.Encode(np.ascontiguousarray(x[:, :, s * STRIDE:s * STRIDE + SEG]))
+    assert len(alone) == 2                                            # the 48000-sample excerpt is itself cut into 47520 + 480
+    one = m.Encode(np.ascontiguousarray(x[:, :, s * STRIDE:s * STRIDE + SEG - 480 + 480]))[0]
+    np.testing.assert_array_equal(one[0], f1[s][0])
+    np.testing.assert_allclose(one[1], f1[s][1], rtol=1e-6)
+    m.Dispose()

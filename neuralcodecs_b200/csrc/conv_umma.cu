@@ -47,6 +47,10 @@ constexpr int kEpiStages = 3;
 constexpr uint32_t kEpiStageBytes = kBM * 128;                                    // [128 rows][32 fp32]
 constexpr int kMaxAStages = 6;
 constexpr int kMaxWStages = 16;
+// measurement only: role timeline of CTA 0 (env NC_TRACE_RU / NC_TRACE_UMMA), see scripts/ru_trace_analyze.py
+constexpr int kTraceTiles = 96, kTraceEvents = 32;
+#define RU_TRACE(it_, ev_) do { if (L.trace && blockIdx.x == 0 && (it_) < kTraceTiles) L.trace[(it_) * kTraceEvents + (ev_)] = (unsigned long long)clock64(); } while (0)
+
 // 227 KB opt-in limit minus the kernel's static shared memory (barriers), rounded up to 1 KB
 constexpr size_t kUmmaMaxDynSmem = 227 * 1024 - 1024;
 
@@ -92,7 +96,23 @@ __device__ __forceinline__ float snake_f(float x, float a, float ia) {
   }
   return fmaf(s * s, ia, x);  // a == 0 -> ia == 0 -> x   (where(alpha == 0, x, x + sin^2(alpha x)/alpha))
 }
-__device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : expm1f(x); }
+// ELU on the tensor-core path: expm1 for x <= 0 in ~12 instructions instead of expm1f's ~40 (the role timelines showed the ELU of
+// the operand prologue and of the epilogue bounding Encodec's narrow layers): Taylor series to degree 8 on (-0.5, 0] (relative
+// truncation error 1.1e-8) and MUFU ex2 - 1 below (relative error of the difference <= 2^-22.5 * e^x / (1 - e^x) < 2.7e-7), i.e.
+// within 3 ulp of expm1f everywhere; NaN propagates, -inf -> -1.
+__device__ __forceinline__ float elu_f(float x) {   // branch-free: both forms are evaluated and selected (FSEL)
+  float p = fmaf(x, 1.0f / 40320.0f, 1.0f / 5040.0f);
+  p = fmaf(x, p, 1.0f / 720.0f);
+  p = fmaf(x, p, 1.0f / 120.0f);
+  p = fmaf(x, p, 1.0f / 24.0f);
+  p = fmaf(x, p, 1.0f / 6.0f);
+  p = fmaf(x, p, 0.5f);
+  p = fmaf(x, p, 1.0f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+  const float neg = x > -0.5f ? x * p : e - 1.0f;
+  return x > 0.f ? x : neg;
+}
 
 template <int PRO>
 __device__ __forceinline__ float4 prologue4(float4 x, const float4& al, const float4& ia) {
@@ -265,9 +285,10 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
   if (warp == 0) {
     // ===================================================================== weight producer
     if (elect_one()) {
-      int ws = 0, wcount = 0;
+      int ws = 0, wcount = 0, it = 0;
       uint32_t wph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        RU_TRACE(it, 15);
         const int nt = tile % p.n_tiles;   // N tile fastest: the N tiles of one M tile run side by side, A re-reads hit L2
         const unsigned mask = p.tap_mask[nt];
         const float* wbase = p.W + (size_t)nt * p.tiles_per_ntile * (size_t)p.w_tile_floats;
@@ -315,6 +336,7 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
         bool have_buf = false;
         uint32_t d_tmem = 0;
         uint32_t acc = 0, acc_lo = 0;
+        RU_TRACE(it, 3);
         const unsigned mask = p.dense_step >= 0 ? 0u : (unsigned)p.tap_mask[tile % p.n_tiles];
         for (int kci = 0; kci < p.n_kc; ++kci) {
           if (!have_buf) {
@@ -324,9 +346,11 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
             d_tmem = tmem_base + (uint32_t)buf * acc_stride;
             acc = 0;
             have_buf = true;
+            if (kci == 0) RU_TRACE(it, 4);
           }
           mbar_wait(&a_full[as], aph);
           tc_fence_after();
+          if (kci == 0) RU_TRACE(it, 5);
           uint64_t a_tap = a_desc;
           for (int j = 0; j < p.n_taps; ++j) {
             if (p.dense_step >= 0) {
@@ -401,6 +425,7 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
           a_desc += a_stage_u;
           if (++as == L.a_stages) { as = 0; aph ^= 1u; a_desc = a_desc0; }
           if (++in_part == fold_kc || kci == p.n_kc - 1) {   // this partial is complete: hand it to the epilogue warps
+            if (kci == p.n_kc - 1) RU_TRACE(it, 6);
             tc_commit(&acc_full[buf]);
             ++pc;
             in_part = 0;
@@ -412,9 +437,9 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
   } else if (warp == kLoaderWarp) {
     // ===================================================================== A loader (TMA)
     if (elect_one()) {
-      int as = 0, acount = 0;
+      int as = 0, acount = 0, it = 0;
       uint32_t aph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int nt = tile % p.n_tiles;   // N tile fastest: the N tiles of one M tile run side by side, A re-reads hit L2
         const int rem = tile / p.n_tiles;
         const int b = rem / p.m_tiles_per_clip;
@@ -422,6 +447,8 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
         const int r_base = mt * kBM + p.smin;
         for (int kci = 0; kci < p.n_kc; ++kci) {
           mbar_wait(&a_empty[as], aph ^ 1u);
+          if (kci == 0) RU_TRACE(it, 0);
+          if (kci == p.n_kc - 1) RU_TRACE(it, 1);
           if ((L.knock & 4) && acount >= L.a_stages) {
             mbar_arrive(&raw_full[as]);
           } else {
@@ -478,6 +505,7 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
         const int row = mt * kBM + rloc;
         const float nz = (p.noise && row < p.m_rows) ? __ldg(p.noise + (long long)b * p.m_rows + row) : 0.f;
         float gn_s = 0.f, gn_ss = 0.f;   // GroupNorm statistics of this thread's row (p.gn_stats)
+        if (leader) RU_TRACE(it, 19);
         // fold every main partial but the last into the running sum (fp32 round-to-nearest adds, kept in TMEM; each
         // thread only ever touches its own lane and columns of it)
         for (int part = 0; part + 1 < n_parts; ++part, ++pc) {
@@ -507,6 +535,7 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
         ++pc;
         mbar_wait(&acc_full[buf], acc_ph);
         tc_fence_after();
+        if (leader) RU_TRACE(it, 12);
         const uint32_t t_addr = tmem_base + (uint32_t)buf * acc_stride + lane_bits;
         for (int g = 0; g < groups; ++g) {
           float v[16];
@@ -526,6 +555,7 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
           } else {
             tmem_ld_wait();
           }
+          if (leader && g == 0) RU_TRACE(it, 22);
           if (g == groups - 1) {   // accumulator fully read by this warp: hand the TMEM buffers back early
             tc_fence_before();
             __syncwarp();
@@ -541,7 +571,9 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
             for (int i = 0; i < 16; ++i) { gn_s += v[i]; gn_ss = fmaf(v[i], v[i], gn_ss); }
           }
           uint8_t* stage = sE + (size_t)es * kEpiStageBytes;
+          if (leader && g == 0) RU_TRACE(it, 23);
           if (p.R) mbar_wait(&r_full[es], eph); else mbar_wait(&e_free[es], eph ^ 1u);
+          if (leader && g == 0) RU_TRACE(it, 13);
           if (p.R && !(L.knock & 16)) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -555,18 +587,22 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
             }
           }
           if (!(L.knock & 16)) epi_post(p, v, n0);
+          if (leader && g == 0) RU_TRACE(it, 24);
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             *reinterpret_cast<float4*>(stage + sw128_offset((uint32_t)rloc, (uint32_t)(half * 4 + i))) =
                 make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           fence_proxy_async_smem();
+          if (leader && g == 0) RU_TRACE(it, 25);
           asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueWarps * 32) : "memory");
+          if (leader && g == 0) RU_TRACE(it, 26);
           if (leader) {
             if (!(L.knock & 32)) tma_store_3d(&tmapD, stage, nt * p.BN + g * 32, mt * kBM, b);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the previous store has left smem
             if (prev >= 0) mbar_arrive(&e_free[prev]);
             prev = es;
+            if (g == groups - 1) RU_TRACE(it, 14);
           }
           if (++es == kEpiStages) { es = 0; eph ^= 1u; }
         }
@@ -656,10 +692,11 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
     // launch in round 1); rows two apart split them evenly.
     const int rho0 = 8 * (ptid >> 6) + ((ptid >> 5) & 1) + 2 * ((ptid & 31) >> 3);  // 0..31, each once
     const int rows_needed = kBM + p.span;
-    int as = 0;
+    int as = 0, tt = 0;
     uint32_t aph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tt) {
       for (int kci = 0; kci < p.n_kc; ++kci) {
+        if (kci == 0 && ptid == 0) RU_TRACE(tt, 20);
         float4 al = make_float4(0.f, 0.f, 0.f, 0.f), ia = al;
         if (PRO == P_SNAKE_FAST || PRO == P_SNAKE_PRECISE) {
           const int ai = ((p.kc_begin + kci) * 32 + c * 4) % p.alpha_period;
@@ -668,6 +705,7 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
         }
         uint8_t* stage = sA + (size_t)as * a_stage_bytes;
         mbar_wait(&raw_full[as], aph);
+        if (kci == 0 && ptid == 0) RU_TRACE(tt, 2);
         if (L.knock & 2) {
           fence_proxy_async_smem();
           __syncwarp();
@@ -785,6 +823,7 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_full[as]);
+        if (kci == p.n_kc - 1 && ptid == 0) RU_TRACE(tt, 21);
         if (++as == L.a_stages) { as = 0; aph ^= 1u; }
       }
     }
@@ -804,8 +843,6 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
 // C <= 128: both accumulators double-buffered (4 x C <= 512 TMEM columns) and the k7 MMAs of tile i+1 are issued
 // BEFORE the 1x1 MMAs of tile i, so draining acc1 overlaps tensor-core work.  128 < C <= 256: single-buffered,
 // issue order k7(i), 1x1(i).  Operand mode: bf16x3 / f16x3 only.
-constexpr int kTraceTiles = 96, kTraceEvents = 32;
-#define RU_TRACE(it_, ev_) do { if (L.trace && blockIdx.x == 0 && (it_) < kTraceTiles) L.trace[(it_) * kTraceEvents + (ev_)] = (unsigned long long)clock64(); } while (0)
 constexpr int kHStages = 3;   // most; the launch picks L.h_stages / L.epi_stages (the weight ring gets the rest)
 
 template <int PRO, int RIT>
@@ -1330,7 +1367,7 @@ bool umma_view_ok(const ConvGemmParams& p) {
 
 // returns cudaError_t as int; 0 on success; -1 if the shape does not fit this kernel
 int launch_conv_umma(const ConvGemmParams& p_in, int num_sms, cudaStream_t stream) {
-  UmmaLaunch L;
+  UmmaLaunch L{};
   const size_t smem = umma_smem_bytes(p_in, &L);
   if (smem == 0 || !umma_view_ok(p_in)) return -1;
   ConvGemmParams p = p_in;
@@ -1380,7 +1417,35 @@ int launch_conv_umma(const ConvGemmParams& p_in, int num_sms, cudaStream_t strea
   const int total_tiles = p.n_tiles * p.batch * p.m_tiles_per_clip;
   const int grid = total_tiles < num_sms ? total_tiles : num_sms;
   if (grid <= 0) return 0;
+  // measurement only: NC_TRACE_UMMA=<file> NC_TRACE_UMMA_MATCH=<BN>,<a_pitch>,<n_taps> [NC_TRACE_UMMA_SKIP=n] dumps CTA 0's role
+  // timeline of one matching launch (scripts/ru_trace_analyze.py)
+  static const char* trace_path = getenv("NC_TRACE_UMMA");
+  static int t_bn = 0, t_pitch = 0, t_taps = 0, t_skip = 3;
+  static const bool trace_cfg = trace_path && getenv("NC_TRACE_UMMA_MATCH") &&
+                                std::sscanf(getenv("NC_TRACE_UMMA_MATCH"), "%d,%d,%d", &t_bn, &t_pitch, &t_taps) == 3 &&
+                                ((t_skip = getenv("NC_TRACE_UMMA_SKIP") ? atoi(getenv("NC_TRACE_UMMA_SKIP")) : 3), true);
+  const bool tracing = trace_cfg && p.BN == t_bn && p.a_pitch == t_pitch && p.n_taps == t_taps && t_skip-- == 0;
+  if (tracing) {
+    if (cudaMalloc(&L.trace, sizeof(unsigned long long) * kTraceTiles * kTraceEvents) != cudaSuccess) return (int)cudaErrorMemoryAllocation;
+    cudaMemsetAsync(L.trace, 0, sizeof(unsigned long long) * kTraceTiles * kTraceEvents, stream);
+  }
   k<<<grid, kUmmaThreads, smem, stream>>>(p, L, tmap, tmapD, tmapR);
+  if (tracing) {
+    std::vector<unsigned long long> h((size_t)kTraceTiles * kTraceEvents);
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h.data(), L.trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(L.trace);
+    if (FILE* f = std::fopen(trace_path, "w")) {
+      std::fprintf(f, "# conv_umma BN=%d n_tiles=%d n_kc=%d span=%d taps=%d mode=%d passes=%d acc_split=%d dw=%d residual=%d a_stages=%d w_stages=%d grid=%d tiles=%d\n",
+                   p.BN, p.n_tiles, p.n_kc, p.span, p.n_taps, p.mode, p.passes, p.acc_split, p.dw_w ? 1 : 0, p.R ? 1 : 0, L.a_stages, L.w_stages, grid,
+                   total_tiles);
+      for (int t = 0; t < kTraceTiles; ++t) {
+        for (int e = 0; e < 28; ++e) std::fprintf(f, "%llu ", h[(size_t)t * kTraceEvents + e]);
+        std::fprintf(f, "\n");
+      }
+      std::fclose(f);
+    }
+  }
   return (int)cudaGetLastError();
 }
 
@@ -1415,7 +1480,7 @@ bool ru_fused_supported(const ConvGemmParams& p, const ConvGemmParams& p2) {
 // p2: the 1x1 conv's plan (weights, bias, post = the Snake that follows the unit or none).
 int launch_ru_fused(const ConvGemmParams& p, const ConvGemmParams& p2, int num_sms, cudaStream_t stream) {
   if (!ru_fused_supported(p, p2)) return -1;
-  UmmaLaunch L;
+  UmmaLaunch L{};
   const int rows = ((kBM + p.span) + 7) / 8 * 8;
   const long a_stage = (long)rows * 128, w_stage = (long)p.BN * ((p.w_hi_only && p2.w_hi_only) ? 64 : 128);
   // Shared-memory split (sweep: profiles/r02_ru_fused_smem_split.txt).  These units are bound by shared-memory bandwidth
@@ -1487,7 +1552,7 @@ int launch_ru_fused(const ConvGemmParams& p, const ConvGemmParams& p2, int num_s
       std::fprintf(f, "# BN=%d n_kc=%d span=%d taps=%d a_stages=%d w_stages=%d h_stages=%d e_stages=%d grid=%d tiles=%d\n", p.BN, p.n_kc, p.span,
                    p.n_taps, L.a_stages, L.w_stages, L.h_stages, L.epi_stages, grid, total_tiles);
       for (int t = 0; t < kTraceTiles; ++t) {
-        for (int e = 0; e < 22; ++e) std::fprintf(f, "%llu ", h[(size_t)t * kTraceEvents + e]);
+        for (int e = 0; e < 28; ++e) std::fprintf(f, "%llu ", h[(size_t)t * kTraceEvents + e]);
         std::fprintf(f, "\n");
       }
       std::fclose(f);

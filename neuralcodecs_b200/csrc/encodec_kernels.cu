@@ -503,7 +503,7 @@ __device__ __forceinline__ void gn_coeffs(const double* stats, int b, double cou
   mean = (float)m;
   rstd = (float)(1.0 / sqrt(var + (double)eps));
 }
-__device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expm1f(v); }
+__device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expm1f(v); }   // HBM-bound pass: the precise form is free here
 
 // Pass 2, in place over rows [0, T): y = (x - mean) * rstd * gamma[c] + beta[c] (+ residual) (-> ELU).  The residual is either
 // final values or -- stats2 != nullptr -- another conv's RAW output normalised on the fly with its own statistics and affine

@@ -17,7 +17,7 @@ for t in range(lo, hi):
 print("\nsteady-state period per tile (clk), tiles 16..80:")
 for e in order:
     col = a[16:80, e]
-    if (col > 0).all():
+    if (col > 0).all() and len(col) > 1:
         d = np.diff(col)
         print(f"  {NAMES[e]:>12s}: mean {d.mean():8.0f}  min {d.min():6d}  max {d.max():6d}")
 print("\nmean gaps within a tile (clk), tiles 16..80:")
@@ -26,7 +26,14 @@ pairs = [(0, 2, "A load issue -> raw tile landed (TMA latency + queue)"), (2, 21
          (6, 10, "m1 issued -> E1 sees acc1 full (MMA completion + commit)"), (18, 10, "E1 waiting for acc1"), (10, 11, "E1 drain (all groups)"),
          (11, 8, "E1 done -> m2 sees h_full0"), (7, 9, "m2: acc2 free -> issued"), (9, 12, "m2 issued -> E2 sees acc2 full"),
          (19, 12, "E2 waiting for acc2"), (12, 14, "E2 (all groups) until last store issued"), (3, 4, "m1 waiting for acc1 free"),
-         (16, 17, "W: w2 tiles of the tile"), (15, 16, "W: w1 tiles of the next tile")]
+         (16, 17, "W: w2 tiles of the tile"), (15, 16, "W: w1 tiles of the next tile"),
+         # conv_umma_kernel (no m2 / e1): the same event ids, one accumulator
+         (6, 12, "MMAs issued -> epilogue sees acc full"), (3, 4, "MMA thread waiting for a free accumulator"),
+         (4, 5, "MMA thread waiting for the first A chunk"), (12, 13, "epilogue: acc full -> first stage free / residual landed"),
+         (12, 22, "epilogue g0: acc full -> tcgen05.ld done"), (22, 23, "epilogue g0: acc_empty arrive + bias"),
+         (23, 13, "epilogue g0: waiting for the stage (e_free / residual landed)"), (13, 24, "epilogue g0: residual add + activation"),
+         (24, 25, "epilogue g0: smem stores + proxy fence"), (25, 26, "epilogue g0: bar.sync of the 8 warps"),
+         (26, 14, "epilogue: bar.sync(g0) -> last group's store issued + wait_group.read 1")]
 for x, y, label in pairs:
     v = a[16:80, y] - a[16:80, x]
     ok = (a[16:80, y] > 0) & (a[16:80, x] > 0)

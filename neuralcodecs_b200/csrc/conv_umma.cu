@@ -52,7 +52,7 @@ constexpr int kTraceTiles = 96, kTraceEvents = 32;
 #define RU_TRACE(it_, ev_) do { if (L.trace && blockIdx.x == 0 && (it_) < kTraceTiles) L.trace[(it_) * kTraceEvents + (ev_)] = (unsigned long long)clock64(); } while (0)
 
 // 227 KB opt-in limit minus the kernel's static shared memory (barriers), rounded up to 1 KB
-constexpr size_t kUmmaMaxDynSmem = 227 * 1024 - 1024;
+constexpr size_t kUmmaMaxDynSmem = 227 * 1024 - 1024 - 3072;   // 3 KB of static shared memory hold the epilogue coefficients
 
 // producer template codes
 constexpr int P_NONE = 0, P_SNAKE_FAST = 1, P_SNAKE_PRECISE = 2, P_ELU = 3;
@@ -169,6 +169,31 @@ __device__ __forceinline__ void epi_bias(const ConvGemmParams& p, float (&v)[16]
   }
 }
 
+// Epilogue coefficients cached in shared memory (conv_umma_kernel, one N tile): with the whole carve-out given to the rings the
+// L1 holds nothing, so the per-group bias / Snake-parameter loads were L2 round trips (~250 clk each) on the epilogue warps'
+// critical path (role timeline).  sc: [bias | post_alpha | post_inv_alpha][256], index = output column.
+__device__ __forceinline__ void epi_bias_cached(const float* sc, float (&v)[16], int n0) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 bb = *reinterpret_cast<const float4*>(sc + n0 + 4 * i);
+    v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+  }
+}
+__device__ __forceinline__ void epi_snake_cached(const ConvGemmParams& p, const float* sc, float (&v)[16], int n0) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 al = *reinterpret_cast<const float4*>(sc + 256 + n0 + 4 * i);
+    const float4 ia = *reinterpret_cast<const float4*>(sc + 512 + n0 + 4 * i);
+    if (p.precise_sin) {
+      v[4 * i + 0] = snake_f<true>(v[4 * i + 0], al.x, ia.x); v[4 * i + 1] = snake_f<true>(v[4 * i + 1], al.y, ia.y);
+      v[4 * i + 2] = snake_f<true>(v[4 * i + 2], al.z, ia.z); v[4 * i + 3] = snake_f<true>(v[4 * i + 3], al.w, ia.w);
+    } else {
+      v[4 * i + 0] = snake_f<false>(v[4 * i + 0], al.x, ia.x); v[4 * i + 1] = snake_f<false>(v[4 * i + 1], al.y, ia.y);
+      v[4 * i + 2] = snake_f<false>(v[4 * i + 2], al.z, ia.z); v[4 * i + 3] = snake_f<false>(v[4 * i + 3], al.w, ia.w);
+    }
+  }
+}
+
 // the consumer's activation (applied once per element, here) followed by this layer's own activation
 __device__ __forceinline__ void epi_post(const ConvGemmParams& p, float (&v)[16], int n0) {
   if (p.post == PRO_SNAKE) {
@@ -233,6 +258,7 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
   __shared__ uint64_t w_full[kMaxWStages], w_empty[kMaxWStages];
   __shared__ uint64_t acc_full[2], acc_empty[2], lo_empty;
   __shared__ uint64_t r_full[kEpiStages], e_free[kEpiStages];
+  __shared__ __align__(16) float s_coef[3 * 256];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x;
@@ -273,6 +299,16 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
   if (warp == 1) {
     tmem_alloc<512>(&tmem_base_s);
     tmem_relinquish();
+  }
+  const bool coef_cached = L.tma_epilogue && p.n_tiles == 1 && p.BN <= 256;
+  if (coef_cached) {
+    for (int i = threadIdx.x; i < p.BN; i += blockDim.x) {
+      s_coef[i] = p.bias ? __ldg(p.bias + i % p.bias_period) : 0.f;
+      if (p.post == PRO_SNAKE) {
+        s_coef[256 + i] = __ldg(p.post_alpha + i % p.post_period);
+        s_coef[512 + i] = __ldg(p.post_inv_alpha + i % p.post_period);
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -565,7 +601,7 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
             }
           }
           const int n0 = nt * p.BN + g * 32 + half * 16;
-          epi_bias(p, v, n0);
+          if (coef_cached) epi_bias_cached(s_coef, v, n0); else epi_bias(p, v, n0);
           if (p.gn_stats && row < p.m_rows) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) { gn_s += v[i]; gn_ss = fmaf(v[i], v[i], gn_ss); }
@@ -586,7 +622,9 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
               }
             }
           }
-          if (!(L.knock & 16)) epi_post(p, v, n0);
+          if (!(L.knock & 16)) {
+            if (coef_cached && p.post == PRO_SNAKE && p.act != ACT_TANH) epi_snake_cached(p, s_coef, v, n0); else epi_post(p, v, n0);
+          }
           if (leader && g == 0) RU_TRACE(it, 24);
 #pragma unroll
           for (int i = 0; i < 4; ++i)

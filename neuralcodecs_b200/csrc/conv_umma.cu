@@ -44,6 +44,7 @@ constexpr int kLoaderWarp = kFirstProducerWarp + kProducerWarps;                
 constexpr int kResidualWarp = kLoaderWarp + 1;                                    // 19
 constexpr int kUmmaThreads = 32 * (kResidualWarp + 1);                            // 640
 constexpr int kEpiStages = 3;
+constexpr int kMaxEpiStages = 5;   // conv_umma_kernel picks L.epi_stages = 3 or 5 (two-team epilogue with residual prefetch)
 constexpr uint32_t kEpiStageBytes = kBM * 128;                                    // [128 rows][32 fp32]
 constexpr int kMaxAStages = 6;
 constexpr int kMaxWStages = 16;
@@ -257,7 +258,7 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
   __shared__ uint64_t raw_full[kMaxAStages], a_full[kMaxAStages], a_empty[kMaxAStages];
   __shared__ uint64_t w_full[kMaxWStages], w_empty[kMaxWStages];
   __shared__ uint64_t acc_full[2], acc_empty[2], lo_empty;
-  __shared__ uint64_t r_full[kEpiStages], e_free[kEpiStages];
+  __shared__ uint64_t r_full[kMaxEpiStages], e_free[kMaxEpiStages];
   __shared__ __align__(16) float s_coef[3 * 256];
   __shared__ uint32_t tmem_base_s;
 
@@ -288,9 +289,10 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], kEpilogueWarps);
+      // two-team epilogue, one 32-column group per tile: only the team that owns the tile's group reads the accumulator
+      mbar_init(&acc_empty[i], (L.epi_teams && p.BN == 32) ? kEpilogueWarps / 2 : kEpilogueWarps);
     }
-    for (int i = 0; i < kEpiStages; ++i) {
+    for (int i = 0; i < kMaxEpiStages; ++i) {
       mbar_init(&r_full[i], 1);
       mbar_init(&e_free[i], 1);
     }
@@ -511,7 +513,7 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
           mbar_wait(&e_free[es], eph ^ 1u);
           mbar_arrive_expect_tx(&r_full[es], kEpiStageBytes);
           tma_load_3d(sE + (size_t)es * kEpiStageBytes, &tmapR, nt * p.BN + g * 32, mt * kBM, b, &r_full[es]);
-          if (++es == kEpiStages) { es = 0; eph ^= 1u; }
+          if (++es == L.epi_stages) { es = 0; eph ^= 1u; }
         }
       }
     }
@@ -526,6 +528,91 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
       // row with conflict-free 128-bit smem accesses, so no uncoalesced global traffic is issued.
       const int groups = p.BN / 32;
       const bool leader = warp == kFirstEpilogueWarp && lane == 0;
+      if (L.epi_teams) {
+        // Two teams of 4 warps (each covers the 4 TMEM lane quarters) take alternate 32-column groups, so two groups'
+        // latency chains (tcgen05.ld -> accumulator hand-back -> stage wait -> math -> smem -> barrier -> TMA store) overlap:
+        // the role timeline showed narrow layers bound by that chain (~3k clk per group), not by any throughput.
+        // Group k (counted over the whole launch) uses stage k % E; a team frees a stage one of ITS stores later.
+        const int team = half;
+        const bool tleader = ((warp - kFirstEpilogueWarp) & 3) == 0 && lane == 0;
+        const int E = L.epi_stages;
+        const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
+        int prev = -1;
+        long long k0 = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it, k0 += groups) {
+          const int nt = tile % p.n_tiles;
+          const int rem = tile / p.n_tiles;
+          const int b = rem / p.m_tiles_per_clip;
+          const int mt = rem - b * p.m_tiles_per_clip;
+          const int rloc = q * 32 + lane;
+          const int row = mt * kBM + rloc;
+          float gn_s = 0.f, gn_ss = 0.f;
+          const int g_first = (int)((k0 ^ (long long)team) & 1);
+          if (g_first < groups) {
+            const int buf = it & 1;
+            if (leader) RU_TRACE(it, 19);
+            mbar_wait(&acc_full[buf], ((uint32_t)it >> 1) & 1u);
+            tc_fence_after();
+            if (leader) RU_TRACE(it, 12);
+            const uint32_t t_addr = tmem_base + (uint32_t)buf * acc_stride + lane_bits;
+            const int g_last = g_first + ((groups - 1 - g_first) & ~1);
+            for (int g = g_first; g < groups; g += 2) {
+              const long long k = k0 + g;
+              const int es = (int)(k % E);
+              const uint32_t eph = (uint32_t)((k / E) & 1);
+              uint8_t* stage = sE + (size_t)es * kEpiStageBytes;
+#pragma unroll 1
+              for (int hh = 0; hh < 2; ++hh) {
+                float v[16];
+                __syncwarp();
+                tmem_ld16(t_addr + g * 32 + hh * 16, v);
+                tmem_ld_wait();
+                if (g == g_last && hh == 1) {   // this warp is done with the accumulator
+                  tc_fence_before();
+                  __syncwarp();
+                  if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                }
+                const int n0 = nt * p.BN + g * 32 + hh * 16;
+                if (coef_cached) epi_bias_cached(s_coef, v, n0); else epi_bias(p, v, n0);
+                if (p.gn_stats && row < p.m_rows) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) { gn_s += v[i]; gn_ss = fmaf(v[i], v[i], gn_ss); }
+                }
+                if (hh == 0) {
+                  if (p.R) mbar_wait(&r_full[es], eph); else mbar_wait(&e_free[es], eph ^ 1u);
+                }
+                if (p.R && !(L.knock & 16)) {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float4 r = *reinterpret_cast<const float4*>(stage + sw128_offset((uint32_t)rloc, (uint32_t)(hh * 4 + i)));
+                    v[4 * i + 0] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
+                  }
+                }
+                if (!(L.knock & 16)) {
+                  if (coef_cached && p.post == PRO_SNAKE && p.act != ACT_TANH) epi_snake_cached(p, s_coef, v, n0); else epi_post(p, v, n0);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  *reinterpret_cast<float4*>(stage + sw128_offset((uint32_t)rloc, (uint32_t)(hh * 4 + i))) =
+                      make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+              }
+              fence_proxy_async_smem();
+              if (team == 0) asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueWarps * 16) : "memory");
+              else asm volatile("bar.sync 3, %0;" ::"n"(kEpilogueWarps * 16) : "memory");
+              if (tleader) {
+                if (!(L.knock & 32)) tma_store_3d(&tmapD, stage, nt * p.BN + g * 32, mt * kBM, b);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // this team's previous store has left smem
+                if (prev >= 0) mbar_arrive(&e_free[prev]);
+                prev = es;
+                if (leader && g == g_last) RU_TRACE(it, 14);
+              }
+            }
+          }
+          if (p.gn_stats) gn_stats_add(p.gn_stats + 2 * b, gn_s, gn_ss, lane);
+        }
+        if (tleader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      } else {
       int es = 0, prev = -1;
       uint32_t eph = 0;
       uint32_t pc = 0;   // accumulator partials consumed so far (mirrors the MMA issuer's counter)
@@ -642,11 +729,12 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
             prev = es;
             if (g == groups - 1) RU_TRACE(it, 14);
           }
-          if (++es == kEpiStages) { es = 0; eph ^= 1u; }
+          if (++es == L.epi_stages) { es = 0; eph ^= 1u; }
         }
         if (p.gn_stats) gn_stats_add(p.gn_stats + 2 * b, gn_s, gn_ss, lane);
       }
       if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      }   // one-team epilogue
     } else {
       // direct path (ragged outputs, Cout not a multiple of 32): each thread stores its own row
       const bool vec_ok = (p.n_total & 3) == 0;
@@ -1332,25 +1420,47 @@ size_t umma_smem_bytes(const ConvGemmParams& p, UmmaLaunch* L) {
                      p.d_clip_stride % 4 == 0 && p.n_valid == p.n_total &&
                      (reinterpret_cast<uintptr_t>(p.D) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.R) & 15) == 0)
                         ? 1 : 0;
-  const long budget = (long)kUmmaMaxDynSmem - 1024 /*alignment slack*/ - (L->tma_epilogue ? (long)kEpiStages * kEpiStageBytes : 0);
   L->a_rows_alloc = rows;
   L->a_stages = L->w_stages = 0;
+  L->epi_stages = kEpiStages;
   if (p.span > 64) return 0;
-  // at least 2 A stages and 2 W stages; then alternate while both fit (A up to 6, W up to 8):
-  // A stages buy bytes in flight from HBM, W stages hide L2 latency of the weight stream
-  int as = 2, ws = 2;
-  if (as * a_stage + ws * w_stage > budget) return 0;
   static const int w_first = std::min(std::max(getenv("NC_W_FIRST") ? atoi(getenv("NC_W_FIRST")) : 4, 2), kMaxWStages);   // tuning knob, clamped
-  for (;;) {
-    bool grew = false;
-    if (ws < w_first && as * a_stage + (ws + 1) * w_stage <= budget) { ++ws; grew = true; }
-    if (as < kMaxAStages && (as + 1) * a_stage + ws * w_stage <= budget && (ws >= w_first || as < 3)) { ++as; grew = true; }
-    if (!grew) break;
+  // at least 2 A stages and 2 W stages; then alternate while both fit (A up to 6, W up to 16):
+  // A stages buy bytes in flight from HBM, W stages hide L2 latency of the weight stream
+  auto size_rings = [&](long budget, int* as_out, int* ws_out) {
+    int as = 2, ws = 2;
+    if (as * a_stage + ws * w_stage > budget) return false;
+    for (;;) {
+      bool grew = false;
+      if (ws < w_first && as * a_stage + (ws + 1) * w_stage <= budget) { ++ws; grew = true; }
+      if (as < kMaxAStages && (as + 1) * a_stage + ws * w_stage <= budget && (ws >= w_first || as < 3)) { ++as; grew = true; }
+      if (!grew) break;
+    }
+    while (ws < kMaxWStages && as * a_stage + (ws + 1) * w_stage <= budget) ++ws;
+    *as_out = as; *ws_out = ws;
+    return true;
+  };
+  const long base = (long)kUmmaMaxDynSmem - 1024 /*alignment slack*/;
+  int as = 0, ws = 0;
+  // a 5-stage epilogue ring (two-team epilogue with both teams' residual tiles prefetched) for the narrow layers (N <= 64) when
+  // the A / W rings still get 4 stages each: their rings would otherwise only soak up the unused shared memory (one-box A/B:
+  // Encodec -4.4 %, SNAC -3.5 %; the same preference on the wider DAC layers cost 3.5 %)
+  bool ok = false;
+  if (L->tma_epilogue && p.BN <= 64 && size_rings(base - (long)kMaxEpiStages * kEpiStageBytes, &as, &ws) && as >= 4 && ws >= 4) {
+    L->epi_stages = kMaxEpiStages;
+    ok = true;
   }
-  while (ws < kMaxWStages && as * a_stage + (ws + 1) * w_stage <= budget) ++ws;
+  if (!ok) {
+    const long budget = base - (L->tma_epilogue ? (long)kEpiStages * kEpiStageBytes : 0);
+    if (!size_rings(budget, &as, &ws)) return 0;
+    // wider layers: only shared memory the rings cannot use anyway (both at their caps)
+    const long used = (long)as * a_stage + (((long)ws * w_stage + 1023) & ~1023L);
+    if (L->tma_epilogue && used + (long)(kMaxEpiStages - kEpiStages) * kEpiStageBytes <= budget) L->epi_stages = kMaxEpiStages;
+  }
   L->a_stages = as;
   L->w_stages = ws;
-  return 1024 + (size_t)as * a_stage + (((size_t)ws * w_stage + 1023) & ~(size_t)1023) + (L->tma_epilogue ? kEpiStages * kEpiStageBytes : 0);
+  return 1024 + (size_t)as * a_stage + (((size_t)ws * w_stage + 1023) & ~(size_t)1023) +
+         (L->tma_epilogue ? (size_t)L->epi_stages * kEpiStageBytes : 0);
 }
 
 typedef void (*UmmaKernel)(const ConvGemmParams, const UmmaLaunch, const CUtensorMap, const CUtensorMap, const CUtensorMap);
@@ -1416,6 +1526,8 @@ int launch_conv_umma(const ConvGemmParams& p_in, int num_sms, cudaStream_t strea
   }
   static const int knock = getenv("NC_KNOCK") ? atoi(getenv("NC_KNOCK")) : 0;
   L.knock = knock;
+  static const int teams_env = getenv("NC_EPI_TEAMS") ? atoi(getenv("NC_EPI_TEAMS")) : 1;
+  L.epi_teams = (teams_env && L.tma_epilogue && !p.acc_split && !p.noise && (!p.R || L.epi_stages == kMaxEpiStages)) ? 1 : 0;
   const int rows_needed = kBM + p.span;
   const int rit = (rows_needed + 31) / 32;
   if (rit > 6) return -1;

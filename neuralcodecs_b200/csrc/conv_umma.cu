@@ -195,6 +195,21 @@ __device__ __forceinline__ void epi_snake_cached(const ConvGemmParams& p, const 
   }
 }
 
+__device__ __forceinline__ void epi_snake_smem(bool precise, const float* al_s, const float* ia_s, float (&v)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 al = *reinterpret_cast<const float4*>(al_s + 4 * i);
+    const float4 ia = *reinterpret_cast<const float4*>(ia_s + 4 * i);
+    if (precise) {
+      v[4 * i + 0] = snake_f<true>(v[4 * i + 0], al.x, ia.x); v[4 * i + 1] = snake_f<true>(v[4 * i + 1], al.y, ia.y);
+      v[4 * i + 2] = snake_f<true>(v[4 * i + 2], al.z, ia.z); v[4 * i + 3] = snake_f<true>(v[4 * i + 3], al.w, ia.w);
+    } else {
+      v[4 * i + 0] = snake_f<false>(v[4 * i + 0], al.x, ia.x); v[4 * i + 1] = snake_f<false>(v[4 * i + 1], al.y, ia.y);
+      v[4 * i + 2] = snake_f<false>(v[4 * i + 2], al.z, ia.z); v[4 * i + 3] = snake_f<false>(v[4 * i + 3], al.w, ia.w);
+    }
+  }
+}
+
 // the consumer's activation (applied once per element, here) followed by this layer's own activation
 __device__ __forceinline__ void epi_post(const ConvGemmParams& p, float (&v)[16], int n0) {
   if (p.post == PRO_SNAKE) {
@@ -991,8 +1006,22 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
   __shared__ uint64_t h_full[kHStages], h_free[kHStages];
   __shared__ uint64_t r_full[kEpiStages], e_free[kEpiStages];
   __shared__ uint32_t tmem_base_s;
+  // bias / Snake parameters of both convs (C <= 128): [b1 | a1 | 1/a1 | b2 | a2 | 1/a2][128]; global loads would be L2 round trips
+  // on the drain warps' critical path (no L1 under a full shared-memory carve-out)
+  __shared__ __align__(16) float s_cf[6 * 128];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool cf = p.BN <= 128 && p.act != ACT_TANH && p2.act != ACT_TANH;
+  if (cf) {
+    for (int i = tid; i < p.BN; i += blockDim.x) {
+      s_cf[i] = p.bias ? __ldg(p.bias + i % p.bias_period) : 0.f;
+      s_cf[128 + i] = p.post == PRO_SNAKE ? __ldg(p.post_alpha + i % p.post_period) : 0.f;
+      s_cf[256 + i] = p.post == PRO_SNAKE ? __ldg(p.post_inv_alpha + i % p.post_period) : 0.f;
+      s_cf[384 + i] = p2.bias ? __ldg(p2.bias + i % p2.bias_period) : 0.f;
+      s_cf[512 + i] = p2.post == PRO_SNAKE ? __ldg(p2.post_alpha + i % p2.post_period) : 0.f;
+      s_cf[640 + i] = p2.post == PRO_SNAKE ? __ldg(p2.post_inv_alpha + i % p2.post_period) : 0.f;
+    }
+  }
   if (tid == 0) {
     for (int i = 0; i < kMaxAStages; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&a_full[i], kProducerWarps); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < kMaxWStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
@@ -1059,8 +1088,13 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       }
       const int n0 = g * 32 + half * 16;
       if (!(L.knock & 64)) {
-        epi_bias(p, v, n0);
-        epi_post(p, v, n0);
+        if (cf && p.post == PRO_SNAKE) {
+          epi_bias_cached(s_cf, v, n0);
+          epi_snake_smem(p.precise_sin != 0, s_cf + 128 + n0, s_cf + 256 + n0, v);
+        } else {
+          epi_bias(p, v, n0);
+          epi_post(p, v, n0);
+        }
       }
       // 16 channels -> bf16/f16 hi (32 B) and lo (32 B) halves of this row of the K-chunk operand tile
       uint32_t hi[8], lo[8];
@@ -1298,13 +1332,14 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
         mbar_wait(&r_full[es], eph);
         if (leader && g == 0) RU_TRACE(it, 13);
         if (!(L.knock & 256)) {   // (knock 256, measurement only: no bias / residual / activation math)
-          epi_bias(p2, v, n0);
+          if (cf) epi_bias_cached(s_cf + 384, v, n0); else epi_bias(p2, v, n0);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float4 r = *reinterpret_cast<const float4*>(stage + sw128_offset((uint32_t)rloc, (uint32_t)(half * 4 + i)));
             v[4 * i + 0] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
           }
-          epi_post(p2, v, n0);
+          if (cf && p2.post == PRO_SNAKE) epi_snake_smem(p2.precise_sin != 0, s_cf + 512 + n0, s_cf + 640 + n0, v);
+          else epi_post(p2, v, n0);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i)

@@ -74,14 +74,17 @@ void launch_pad1d_dense(const float* in, long long in_clip_stride, int T, int C,
 // One block = 64 frames.  dist[f][k] = (|x_f|^2 + |e_k|^2) + (-2 * x_f.e_k), dot accumulated sequentially over d
 // in fp32 (4x4 register tile per thread, x and e tiles staged in shared memory); running argmin with lowest-index
 // tie-break; then residual[f] -= embed[argmin].
-constexpr int kVqFrames = 64, kVqEntries = 64, kVqD = 128;
+// The codebook chunk is staged ROW-MAJOR ([entry][d], 16-byte stores, conflict-free and coalesced); round 1 transposed it with
+// scalar stores that hit 2 banks per warp (16-way conflicts), which cost as much as the FMAs.  The compute loop then reads its
+// four entries with broadcast scalar loads (a warp holds only two distinct entry quads).
+constexpr int kVqFrames = 64, kVqEntries = 64, kVqD = 128, kVqLd = kVqD + 4;
 
 __global__ void __launch_bounds__(256)
 encodec_vq_stage_kernel(float* __restrict__ residual, long long frames, const float* __restrict__ embed,
                         const float* __restrict__ embed_sq, int K, int64_t* __restrict__ codes, int T, int nq, int stage) {
   extern __shared__ __align__(16) float vq_smem[];
   float (*xs)[kVqFrames + 4] = reinterpret_cast<float (*)[kVqFrames + 4]>(vq_smem);                               // [d][frame]
-  float (*es)[kVqEntries + 4] = reinterpret_cast<float (*)[kVqEntries + 4]>(vq_smem + kVqD * (kVqFrames + 4));    // [d][entry]
+  float (*es)[kVqLd] = reinterpret_cast<float (*)[kVqLd]>(vq_smem + kVqD * (kVqFrames + 4));                      // [entry][d]
   __shared__ float best_d[kVqFrames][16];
   __shared__ int best_k[kVqFrames][16];
   __shared__ int win[kVqFrames];
@@ -113,7 +116,7 @@ encodec_vq_stage_kernel(float* __restrict__ residual, long long frames, const fl
       const int en = i / (kVqD / 4), d4 = i % (kVqD / 4);
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (k0 + en < K) v = __ldg(reinterpret_cast<const float4*>(embed + (size_t)(k0 + en) * kVqD) + d4);
-      es[4 * d4 + 0][en] = v.x; es[4 * d4 + 1][en] = v.y; es[4 * d4 + 2][en] = v.z; es[4 * d4 + 3][en] = v.w;
+      *reinterpret_cast<float4*>(&es[en][4 * d4]) = v;
     }
     __syncthreads();
     float acc[4][4];
@@ -121,11 +124,14 @@ encodec_vq_stage_kernel(float* __restrict__ residual, long long frames, const fl
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const float* e0 = es[4 * te + 0];
+    const float* e1 = es[4 * te + 1];
+    const float* e2r = es[4 * te + 2];
+    const float* e3 = es[4 * te + 3];
 #pragma unroll 8
     for (int d = 0; d < kVqD; ++d) {
       const float4 xv = *reinterpret_cast<const float4*>(&xs[d][4 * tf]);
-      const float4 ev = *reinterpret_cast<const float4*>(&es[d][4 * te]);
-      const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, ea[4] = {ev.x, ev.y, ev.z, ev.w};
+      const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, ea[4] = {e0[d], e1[d], e2r[d], e3[d]};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -176,7 +182,7 @@ void launch_encodec_vq_stage(float* residual, long long frames, const float* emb
   if (D != kVqD) throw Error(NC_UNSUPPORTED, "encodec vq: codebook dimension must be 128");
   if (frames == 0) return;
   const unsigned blocks = (unsigned)((frames + kVqFrames - 1) / kVqFrames);
-  const size_t smem = (size_t)kVqD * (kVqFrames + 4 + kVqEntries + 4) * sizeof(float);
+  const size_t smem = ((size_t)kVqD * (kVqFrames + 4) + (size_t)kVqEntries * kVqLd) * sizeof(float);
   cudaFuncSetAttribute(encodec_vq_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int ev = ctx.begin();
   encodec_vq_stage_kernel<<<blocks, 256, smem, ctx.stream>>>(residual, frames, embed, embed_sq, K, codes, T, nq, stage);

@@ -349,16 +349,15 @@ lstm_layer_kernel(const float* __restrict__ xproj, long long xproj_clip_stride, 
     // barrier among the CTAs of this batch slice.  One device-scope fence by the signalling thread AFTER the CTA barrier
     // (fences are cumulative over what the barrier ordered before them) instead of one MEMBAR.GPU per thread before it.
     __syncthreads();
-    if (tid == 0) {
-      __threadfence();
-      atomicAdd(&barriers[blockIdx.y], 1u);
-    }
+    if (tid == 0)   // release at device scope: cumulative over the h_t stores the CTA barrier ordered before it
+      asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(barriers + blockIdx.y), "r"(1u) : "memory");
     prefetch(t + 1);
     if (tid == 0) {
       const unsigned int target = (unsigned int)n_unit_ctas * (unsigned int)(t + 1);
-      while (*reinterpret_cast<volatile unsigned int*>(&barriers[blockIdx.y]) < target) {
-      }
-      __threadfence();
+      unsigned int seen;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(barriers + blockIdx.y) : "memory");
+      } while (seen < target);
     }
     __syncthreads();
   }

@@ -60,6 +60,26 @@ def test_null_and_bad_arguments_are_status_codes_not_crashes():
     h = C.c_void_p()
     assert lib.nc_create(_lib.NC_CODEC_DAC, None, 0, 0, C.byref(h)) != _lib.NC_OK
     assert lib.nc_launch_count(None) == 0
+    # the segmented Encodec entry points (48 kHz preset) reject a null handle the same way
+    n, tot, dl = C.c_int32(), C.c_int64(), C.c_int64()
+    assert lib.nc_encodec_query_frames(None, 48000, 6.0, C.byref(n), None, 0, C.byref(tot), None, C.byref(dl)) == _lib.NC_INVALID_ARGUMENT
+    assert lib.nc_encodec_encode_frames(None, None, 1, 48000, 6.0, None, None) == _lib.NC_INVALID_ARGUMENT
+    assert lib.nc_encodec_decode_frames(None, None, None, 1, 4, None, 1, None) == _lib.NC_INVALID_ARGUMENT
+    assert lib.nc_encodec_query_decoded(None, None, 1, C.byref(dl)) == _lib.NC_INVALID_ARGUMENT
+
+
+def test_encodec_config_presets_and_segment_algebra():
+    import neuralcodecs_b200 as nc
+    c24, c48 = nc.EncodecConfig.Encodec24Khz(), nc.EncodecConfig.Encodec48Khz()       # EncodecConfig.cs:9-66
+    assert (c24.channels, c24.use_causal_conv, c24.norm_type, c24.normalize, c24.segment_length, c24.segment_stride) == \
+        (1, True, "weight_norm", False, None, None)
+    assert (c48.sample_rate, c48.channels, c48.use_causal_conv, c48.norm_type, c48.normalize) == (48000, 2, False, "time_group_norm", True)
+    assert (c48.segment_length, c48.segment_stride, c48.num_quantizers, c48.hop_length) == (48000, 47520, 16, 320)   # Encodec.cs:70-71,190-196
+    j = nc.EncodecConfig.from_json('{"sampling_rate": 48000, "audio_channels": 2, "chunk_length_s": 1.0, "overlap": 0.01,'
+                                   ' "norm_type": "time_group_norm", "normalize": true, "use_causal_conv": false}')
+    assert (j.segment_length, j.segment_stride, j.norm_type) == (48000, 47520, "time_group_norm")
+    j.overlap = None                                                                    # Encodec.cs:84: `config.Overlap ?? 0`
+    assert j.segment_stride == 48000
 
 
 def test_dac_config_presets_and_json():

@@ -115,11 +115,21 @@ __device__ __forceinline__ float elu_f(float x) {   // branch-free: both forms a
   return x > 0.f ? x : neg;
 }
 
+// Fast Snake on four values with packed fp32x2 multiplies / FMAs (sm_100 FMUL2 / FFMA2): the same round-to-nearest operations as
+// snake_f<false> per element (bit-identical), 7 instead of 10 FP-pipe instructions per pair.
+__device__ __forceinline__ void snake4_fast(float& x0, float& x1, float& x2, float& x3, const float4& al, const float4& ia) {
+  const float2 xa = make_float2(x0, x1), xb = make_float2(x2, x3);
+  const float2 ta = __fmul2_rn(make_float2(al.x, al.y), xa), tb = __fmul2_rn(make_float2(al.z, al.w), xb);
+  const float2 sa = make_float2(__sinf(ta.x), __sinf(ta.y)), sb = make_float2(__sinf(tb.x), __sinf(tb.y));
+  const float2 ra = __ffma2_rn(__fmul2_rn(sa, sa), make_float2(ia.x, ia.y), xa);
+  const float2 rb = __ffma2_rn(__fmul2_rn(sb, sb), make_float2(ia.z, ia.w), xb);
+  x0 = ra.x; x1 = ra.y; x2 = rb.x; x3 = rb.y;
+}
+
 template <int PRO>
 __device__ __forceinline__ float4 prologue4(float4 x, const float4& al, const float4& ia) {
   if (PRO == P_SNAKE_FAST) {
-    x.x = snake_f<false>(x.x, al.x, ia.x); x.y = snake_f<false>(x.y, al.y, ia.y);
-    x.z = snake_f<false>(x.z, al.z, ia.z); x.w = snake_f<false>(x.w, al.w, ia.w);
+    snake4_fast(x.x, x.y, x.z, x.w, al, ia);
   } else if (PRO == P_SNAKE_PRECISE) {
     x.x = snake_f<true>(x.x, al.x, ia.x); x.y = snake_f<true>(x.y, al.y, ia.y);
     x.z = snake_f<true>(x.z, al.z, ia.z); x.w = snake_f<true>(x.w, al.w, ia.w);
@@ -189,8 +199,7 @@ __device__ __forceinline__ void epi_snake_cached(const ConvGemmParams& p, const 
       v[4 * i + 0] = snake_f<true>(v[4 * i + 0], al.x, ia.x); v[4 * i + 1] = snake_f<true>(v[4 * i + 1], al.y, ia.y);
       v[4 * i + 2] = snake_f<true>(v[4 * i + 2], al.z, ia.z); v[4 * i + 3] = snake_f<true>(v[4 * i + 3], al.w, ia.w);
     } else {
-      v[4 * i + 0] = snake_f<false>(v[4 * i + 0], al.x, ia.x); v[4 * i + 1] = snake_f<false>(v[4 * i + 1], al.y, ia.y);
-      v[4 * i + 2] = snake_f<false>(v[4 * i + 2], al.z, ia.z); v[4 * i + 3] = snake_f<false>(v[4 * i + 3], al.w, ia.w);
+      snake4_fast(v[4 * i + 0], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3], al, ia);
     }
   }
 }
@@ -204,8 +213,7 @@ __device__ __forceinline__ void epi_snake_smem(bool precise, const float* al_s, 
       v[4 * i + 0] = snake_f<true>(v[4 * i + 0], al.x, ia.x); v[4 * i + 1] = snake_f<true>(v[4 * i + 1], al.y, ia.y);
       v[4 * i + 2] = snake_f<true>(v[4 * i + 2], al.z, ia.z); v[4 * i + 3] = snake_f<true>(v[4 * i + 3], al.w, ia.w);
     } else {
-      v[4 * i + 0] = snake_f<false>(v[4 * i + 0], al.x, ia.x); v[4 * i + 1] = snake_f<false>(v[4 * i + 1], al.y, ia.y);
-      v[4 * i + 2] = snake_f<false>(v[4 * i + 2], al.z, ia.z); v[4 * i + 3] = snake_f<false>(v[4 * i + 3], al.w, ia.w);
+      snake4_fast(v[4 * i + 0], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3], al, ia);
     }
   }
 }
@@ -872,18 +880,24 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
           const int d = p.dw_dil;
           float4 acc[kBM / 32];
           const float4 bb = p.dw_b ? __ldg(reinterpret_cast<const float4*>(p.dw_b + ch)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          // packed fp32x2 FMAs (FFMA2: two independent round-to-nearest FMAs per instruction, identical results): this prologue is
+          // instruction-issue bound (profiles/r02_narrow_layer_timelines.txt)
+          float2 a01[kBM / 32], a23[kBM / 32];
 #pragma unroll
-          for (int i = 0; i < kBM / 32; ++i) acc[i] = bb;
+          for (int i = 0; i < kBM / 32; ++i) { a01[i] = make_float2(bb.x, bb.y); a23[i] = make_float2(bb.z, bb.w); }
 #pragma unroll
           for (int j = 0; j < 7; ++j) {
             const float4 w = __ldg(reinterpret_cast<const float4*>(p.dw_w + (size_t)j * p.alpha_period + ch));
+            const float2 w01 = make_float2(w.x, w.y), w23 = make_float2(w.z, w.w);
 #pragma unroll
             for (int i = 0; i < kBM / 32; ++i) {
               const float4 x = *reinterpret_cast<const float4*>(stage + sw128_offset((uint32_t)(rho0 + 32 * i + j * d), (uint32_t)c));
-              acc[i].x = fmaf(w.x, x.x, acc[i].x); acc[i].y = fmaf(w.y, x.y, acc[i].y);
-              acc[i].z = fmaf(w.z, x.z, acc[i].z); acc[i].w = fmaf(w.w, x.w, acc[i].w);
+              a01[i] = __ffma2_rn(w01, make_float2(x.x, x.y), a01[i]);
+              a23[i] = __ffma2_rn(w23, make_float2(x.z, x.w), a23[i]);
             }
           }
+#pragma unroll
+          for (int i = 0; i < kBM / 32; ++i) acc[i] = make_float4(a01[i].x, a01[i].y, a23[i].x, a23[i].y);
           if (p.dw_post_alpha) {
             const float4 pa = __ldg(reinterpret_cast<const float4*>(p.dw_post_alpha + ch));
             const float4 pi = __ldg(reinterpret_cast<const float4*>(p.dw_post_inv_alpha + ch));

@@ -324,8 +324,11 @@ NC_API nc_status nc_encodec_ecdc_info(const uint8_t* stream, int64_t stream_byte
                                       int64_t* payload_offset);
 /* replaces: EncodecCompressor.DecompressFromStreamAsync Modules/Encodec/EncodecCompressor.cs:236-420 (and Decompress
  * :46-52), batched over streams with identical metadata: B streams of stream_bytes bytes, stream b at
- * streams + b*stream_stride -> audio [B][audio_capacity] with the first *audio_length samples of each row written
- * (output trimmed to the stored length, :412-415).  audio == NULL only reports *audio_length / *sample_rate.
+ * streams + b*stream_stride -> audio [B][channels][audio_capacity] with the first *audio_length samples of each row
+ * written (output trimmed to the stored length, :412-415).  audio == NULL only reports *audio_length / *sample_rate.
+ * Segmented / normalised models (48 kHz): per segment a scale block [int32 BE count = 1][float32 BE scale] and that
+ * segment's codes (frames per segment = ceil(segment samples * frame_rate / sample_rate), :303-309), then
+ * Encodec.Decode with the overlap-add.
  * lm = true streams return NC_UNSUPPORTED; a truncated payload returns NC_INVALID_ARGUMENT "Stream ended too soon". */
 NC_API nc_status nc_encodec_decompress(nc_handle h, const uint8_t* streams, int32_t batch, int64_t stream_stride,
                                        int64_t stream_bytes, float* audio, int64_t audio_capacity, int64_t* audio_length,

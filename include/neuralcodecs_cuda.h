@@ -313,7 +313,7 @@ NC_API nc_status nc_encodec_forward_frames_dev(nc_handle h, const float* audio_d
 NC_API nc_status nc_encodec_ecdc_size(nc_handle h, int64_t length, float bandwidth_kbps, int64_t* header_bytes,
                                       int64_t* stream_bytes);
 /* replaces: EncodecCompressor.CompressToStreamAsync(model, wav, stream, useLm: false)
- * Modules/Encodec/EncodecCompressor.cs:60-200 (and Compress :26-39), batched: audio [B,1,length] -> B streams of
+ * Modules/Encodec/EncodecCompressor.cs:60-200 (and Compress :26-39), batched: audio [B,channels,length] -> B streams of
  * *stream_bytes bytes each, clip b at out + b*out_stride.  Encode and bit-pack run on the device. */
 NC_API nc_status nc_encodec_compress(nc_handle h, const float* audio, int32_t batch, int64_t length,
                                      float bandwidth_kbps, uint8_t* out, int64_t out_stride, int64_t* stream_bytes);

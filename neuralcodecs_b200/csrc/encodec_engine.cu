@@ -495,12 +495,11 @@ int EncodecEngine::micro_batch(int B, int64_t L) {
   double per_clip = 5.0 * per_buf * 4 + (double)T * (4.0 * top + cfg_.dimension) * 4 + (double)Lfull * 4;
   int mb = (int)std::max(1.0, std::floor((double)max_workspace_bytes_ / per_clip));
   mb = std::min(mb, B);
-  if (cfg_.lstm_layers > 0) mb = std::min(mb, lstm_max_batch(num_sms_, top));
-  mb = std::max(mb, 1);
+  mb = std::max(mb, 1);   // (the LSTM splits a micro-batch into slices of at most lstm_max_batch clips itself: run_lstm)
   for (auto& w : ws_) w.reserve((size_t)mb * per_buf * sizeof(float));
   xproj_.reserve((size_t)mb * T * 4 * top * sizeof(float));
   z_.reserve((size_t)mb * T * cfg_.dimension * sizeof(float));
-  hbuf_.reserve((size_t)2 * ((mb + 31) / 32 * 32) * top * sizeof(float));
+  hbuf_.reserve((size_t)2 * ((std::min(mb, cfg_.lstm_layers > 0 ? lstm_max_batch(num_sms_, top) : mb) + 31) / 32 * 32) * top * sizeof(float));
   barriers_.reserve(64 * sizeof(unsigned int));
   audio_tmp_.reserve((size_t)mb * decoded_length(T) * sizeof(float));
   gn_stats_.reserve((size_t)2 * mb * 2 * sizeof(double));   // two slots: the conv being normalised, and a resnet block's shortcut
@@ -622,8 +621,16 @@ EncodecEngine::Act EncodecEngine::run_lstm(const Lstm& l, const Act& x, int B, i
     const bool last = i + 1 == l.layers;
     // layer outputs go to out_buf for the last layer, else to a scratch activation in z_-independent buffer 4
     Act o = act(last ? out_buf : 4, B, x.T, H);
-    launch_lstm_layer(xproj_.as<float>(), (long long)cur.T * 4 * H, l.whh[i], hbuf_.as<float>(), o.base, o.stride,
-                      last ? x.base : nullptr, x.stride, last ? 1 : 0, barriers_.as<unsigned int>(), B, x.T, H, c);
+    // one cooperative launch takes at most lstm_max_batch clips (all its CTAs must be co-resident); the convs around it run on
+    // the whole micro-batch, so a batch of many short segments (48 kHz: 11 per 10 s clip) is not cut into small conv launches
+    const int lmax = lstm_max_batch(num_sms_, H);
+    const long long xstride = (long long)cur.T * 4 * H;
+    for (int b0 = 0; b0 < B; b0 += lmax) {
+      const int nb = std::min(lmax, B - b0);
+      launch_lstm_layer(xproj_.as<float>() + (long long)b0 * xstride, xstride, l.whh[i], hbuf_.as<float>(), o.base + (long long)b0 * o.stride,
+                        o.stride, last ? x.base + (long long)b0 * x.stride : nullptr, x.stride, last ? 1 : 0, barriers_.as<unsigned int>(),
+                        nb, x.T, H, c);
+    }
     cur = o;
   }
   return cur;

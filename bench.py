@@ -45,6 +45,7 @@ WORKLOADS = {
     "dia_dac_decode_b256x20s": (256, 20.004, True),  # BASELINE configs[4]
     "snac24k_b32x10s": (32, 10.0, False),        # BASELINE configs[1]
     "encodec24k_b64x10s": (64, 10.0, False),     # BASELINE configs[2]
+    "encodec48k_b32x10s": (32, 10.0, False),     # the 48 kHz stereo preset (segments, GroupNorm, overlap-add)
 }
 
 
@@ -66,6 +67,8 @@ def shard_range(rank: int, world: int, batch: int):
 
 
 def codec_of(workload: str) -> str:
+    if workload.startswith("encodec48"):
+        return "encodec48"
     return "snac" if workload.startswith("snac") else "encodec" if workload.startswith("encodec") else "dac"
 
 
@@ -409,7 +412,8 @@ def run_other_codec(args, codec: str, rank: int, local_rank: int, world: int):
     B, S, _ = WORKLOADS[args.workload]
     B = args.batch or B
     S = args.seconds or S
-    sr = 24000
+    sr = 48000 if codec == "encodec48" else 24000
+    ch = 2 if codec == "encodec48" else 1
     L = int(round(S * sr))
     lo, hi = shard_range(rank, world, B)
     nb = hi - lo
@@ -423,20 +427,23 @@ def run_other_codec(args, codec: str, rank: int, local_rank: int, world: int):
         cfg.device = nc.DeviceConfiguration.CUDA(local_rank)
         model = nc.SNAC(cfg)
     else:
-        cfg = nc.EncodecConfig.Encodec24Khz()
+        cfg = nc.EncodecConfig.Encodec48Khz() if codec == "encodec48" else nc.EncodecConfig.Encodec24Khz()
         cfg.device = nc.DeviceConfiguration.CUDA(local_rank)
         model = nc.Encodec(cfg)
     model.LoadWeights(wpath)
     base = torch.from_numpy(synthetic.synth_audio(min(max(nb, 1), 16), L, sr, first_clip=lo)).to(dev)
     audio = base.repeat((max(nb, 1) + base.shape[0] - 1) // base.shape[0], 1)[:nb].contiguous()
-    out = torch.empty(nb, L, device=dev)
+    if ch == 2:   # planar stereo [nb, 2, L]: second channel = another clip at another level
+        audio = torch.stack([audio, audio.flip(0) * 0.7], dim=1).contiguous()
+    out = torch.empty(nb, ch * L, device=dev)
     if codec == "snac":
         _, T, clens, _ = model.query_shapes(L)
         codes = [torch.empty(nb, n, dtype=torch.int64, device=dev) for n in clens]
         step_dev = lambda: nb and model.forward_dev(audio.data_ptr(), nb, L, out.data_ptr(), [c.data_ptr() for c in codes], None, 5)
         code_bytes = sum(c.numel() for c in codes) * 8
     else:
-        T, nq, _ = model.query_shapes(L)
+        seg, nq, _ = model.query_frames(L)          # one segment for the 24 kHz preset
+        T = sum(seg)
         codes = torch.empty(nb, nq, T, dtype=torch.int64, device=dev)
         step_dev = lambda: nb and model.forward_dev(audio.data_ptr(), nb, L, out.data_ptr(), codes.data_ptr())
         code_bytes = codes.numel() * 8
@@ -477,9 +484,9 @@ def run_other_codec(args, codec: str, rank: int, local_rank: int, world: int):
     value = audio_s * args.steps / (dev_ms / 1e3)
     # e2e through the host-buffer entry point
     # pinned host buffers, raw-pointer host entry point (copies inside the call)
-    h_in = torch.empty(max(nb, 1), L, dtype=torch.float32).pin_memory()
-    h_in[:nb].copy_(audio)
-    h_out = torch.empty(max(nb, 1), L, dtype=torch.float32).pin_memory()
+    h_in = torch.empty(max(nb, 1), ch * L, dtype=torch.float32).pin_memory()
+    h_in[:nb].copy_(audio.reshape(nb, ch * L))
+    h_out = torch.empty(max(nb, 1), ch * L, dtype=torch.float32).pin_memory()
     if codec == "snac":
         h_codes = [torch.empty(max(nb, 1), n, dtype=torch.int64).pin_memory() for n in clens]
         step_host = lambda: nb and model.forward_host(h_in.data_ptr(), nb, L, h_out.data_ptr(), [c.data_ptr() for c in h_codes], 5)
@@ -488,8 +495,8 @@ def run_other_codec(args, codec: str, rank: int, local_rank: int, world: int):
         step_host = lambda: nb and model.forward_host(h_in.data_ptr(), nb, L, h_out.data_ptr(), h_codes.data_ptr())
     step_host()
     _, e2e_ms = timed(step_host, args.steps)
-    e2e = {"value": audio_s * args.steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(B * L * 4),
-           "d2h_bytes_per_step": int(B * L * 4 + code_bytes * B // max(nb, 1)),
+    e2e = {"value": audio_s * args.steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(B * ch * L * 4),
+           "d2h_bytes_per_step": int(B * ch * L * 4 + code_bytes * B // max(nb, 1)),
            "timer": "wall clock, max over ranks"}
     roofline = kernels = cpu = None
     if rank == 0 and nb:
@@ -527,17 +534,18 @@ def run_other_codec(args, codec: str, rank: int, local_rank: int, world: int):
             o = om.load_safetensors(wpath, om.SNACConfig.snac_24khz())
         else:
             from oracle import encodec as om
-            o = om.load_safetensors(wpath, om.EncodecConfig())
-        xs = torch.from_numpy(synthetic.synth_audio(2, L, sr)).unsqueeze(1)
-        o.forward(xs[:1, :, : sr])
-        t0 = time.perf_counter(); o.forward(xs); dt = time.perf_counter() - t0
+            o = om.load_safetensors(wpath, om.EncodecConfig.encodec_48khz() if codec == "encodec48" else om.EncodecConfig())
+        xs = torch.from_numpy(synthetic.synth_audio(2 * ch, L, sr)).reshape(2, ch, L)
+        fwd = o.forward_frames if codec == "encodec48" else o.forward
+        fwd(xs[:1, :, : sr])
+        t0 = time.perf_counter(); fwd(xs); dt = time.perf_counter() - t0
         cpu = {"value": 2 * S / dt, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"2 clips x {S:g} s (of {B}) in {dt:.1f} s, fp32 PyTorch-CPU restatement of the reference op stream"}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32 in/out; see config.precision", "data": "synthetic",
-                "config": {"workload": args.workload, "codec": "SNAC 24 kHz" if codec == "snac" else "Encodec 24 kHz 6 kbps",
+                "config": {"workload": args.workload, "codec": "SNAC 24 kHz" if codec == "snac" else "Encodec 48 kHz stereo 6 kbps" if codec == "encodec48" else "Encodec 24 kHz 6 kbps",
                            "global_batch": B, "clip_seconds": S, "clips_per_gpu": nb, "precision": model.describe().get("precision")
                            or f"encoder {model.describe().get('encoder_precision')}, decoder {model.describe().get('decoder_precision')}",
                            "l2": "inputs + activations far larger than L2; no flush", "weights": "random-init (seeded)"},

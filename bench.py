@@ -756,15 +756,17 @@ def main():
                 roofline["tensor_pipe_note"] = tp["note"]
             except Exception:
                 roofline["tensor_pipe_pct"] = None
-            # the fused narrow residual units are bound by shared-memory bandwidth, not by the tensor pipe or HBM: their byte
-            # budget per 128-row tile and the measured period per tile come from the committed role timeline
+            # the fused narrow residual units (N = 64 / 96 / 128) are bound by the issue interval of their single MMA thread: one
+            # thread sustains one tcgen05.mma per ~80 clk whatever N is (tools/probe_mma_rate.cu), against tensor-core floors of
+            # 32 / 48 / 64 clk; the role timeline measures ~100 clk per MMA in the units
             fused = {k: v for k, v in rep.items() if k.startswith("ru_fused")}
             if fused:
-                roofline["fused_units_shared_memory"] = {
-                    "kernel": "conv_ru_fused_kernel", "bound": "shared memory (128 B/clk/SM)", "share_of_step": sum(v["ms"] for v in fused.values()) / total_ms,
-                    "frac_by_width": {"C=64": 0.76, "C=96": 0.88, "C=128": 0.99},
-                    "source": "profiles/r02_ru_fused_timeline.txt: smem bytes per tile (58 % tensor-core operand reads of the 7-tap x 3-pass "
-                              "products) / 128 B/clk against the measured clocks per tile of CTA 0 (clock64 at every role hand-off)"}
+                roofline["fused_units_mma_issue"] = {
+                    "kernel": "conv_ru_fused_kernel", "bound": "tcgen05.mma issue interval of one thread (~80 clk per MMA, any N)",
+                    "share_of_step": sum(v["ms"] for v in fused.values()) / total_ms,
+                    "clk_per_mma_measured": 100, "clk_per_mma_issue_floor": 80, "tensor_floor_clk_by_width": {"C=64": 32, "C=96": 48, "C=128": 64},
+                    "source": "profiles/r02_mma_issue_rate_probe.txt (two issuing warps double the rate; cta_group::2 halves the issue cost per "
+                              "row) and profiles/r02_ru_fused_timeline.txt (clock64 at every role hand-off of CTA 0)"}
             # the other kernel BASELINE.json's metric names: the fused RVQ (algorithmic bytes per frame: read z, write
             # z_q, write codes = SURVEY 8d's 8.3 KB at the 44.1 kHz preset)
             rv = rep.get("rvq_encode")

@@ -1075,9 +1075,8 @@ conv_ru_fused_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
   // 32-column groups [0, split_a) are drained by the transform warps, [split_a, groups) by the epilogue warps.
   // Measured (B200, C = 64 / 96 / 128): everything on the transform warps when double-buffered beats both the
   // original all-on-epilogue-warps split and a half/half split (7.1 vs 7.6 vs 7.6 ms at C = 64): the units are bound
-  // at C = 64 by shared-memory bandwidth (tensor-core operand reads of the three-pass split: ~1.1 MB of smem traffic
-  // per 128-row tile = 83 % of 128 B/clk), not by either warp set's throughput; a 4-deep accumulator ring (C <= 64)
-  // measured no faster than 2-deep and was dropped.
+  // by the MMA thread's issue interval (~80-100 clk per tcgen05.mma whatever N is, profiles/r02_mma_issue_rate_probe.txt),
+  // not by either warp set's throughput; a 4-deep accumulator ring (C <= 64) measured no faster than 2-deep and was dropped.
   const int split_a = (p.BN <= 128) ? groups : 0;
   auto e1 = [&](int it, int g_begin, int g_end) {
     const int b = buf_of(it);
@@ -1682,10 +1681,10 @@ int launch_ru_fused(const ConvGemmParams& p, const ConvGemmParams& p2, int num_s
   UmmaLaunch L{};
   const int rows = ((kBM + p.span) + 7) / 8 * 8;
   const long a_stage = (long)rows * 128, w_stage = (long)p.BN * ((p.w_hi_only && p2.w_hi_only) ? 64 : 128);
-  // Shared-memory split (sweep: profiles/r02_ru_fused_smem_split.txt).  These units are bound by shared-memory bandwidth
-  // (~1 MB of smem traffic per 128-row tile at C = 64, 60 % of it tensor-core operand reads of the 7-tap x 3-pass products),
-  // so no ring depth changes much; the best measured split keeps 3 H stages, 2 E stages, an A ring of one tile (+1 chunk at
-  // C = 64) and gives the rest to the weight ring (-6 % over the round-1 split of 4 / 3 / 3).
+  // Shared-memory split (sweep: profiles/r02_ru_fused_smem_split.txt).  These units are bound by the issue interval of their single
+  // MMA thread (~80-100 clk per tcgen05.mma whatever N is: profiles/r02_mma_issue_rate_probe.txt), so no ring depth changes much;
+  // the best measured split keeps 3 H stages, 2 E stages, an A ring of one tile (+1 chunk at C = 64) and gives the rest to the
+  // weight ring (-6 % over the round-1 split of 4 / 3 / 3).
   static const int env_as = getenv("NC_RU_AS") ? atoi(getenv("NC_RU_AS")) : 0;
   static const int env_hs = getenv("NC_RU_HS") ? atoi(getenv("NC_RU_HS")) : 0;
   static const int env_es = getenv("NC_RU_ES") ? atoi(getenv("NC_RU_ES")) : 0;

@@ -146,6 +146,7 @@ struct UmmaLaunch {
   int tma_epilogue;  // 1: output / residual tiles move by TMA through a swizzled smem ring
   int epi_stages;    // conv_h16 / fused unit: depth of the epilogue's smem ring (residual prefetch / stores in flight)
   int epi_teams;     // conv_umma_kernel: 1 = the 8 epilogue warps work as two teams of 4 on alternate 32-column groups
+  int dual_issue;    // conv_umma_kernel: 1 = a second MMA-issuing warp takes the odd tiles (see mma_role)
   int h_stages;      // fused unit: depth of the ring of 1x1-conv operand tiles written by the acc1 drain
   unsigned long long* trace;   // measurement only (env NC_TRACE_RU): CTA 0 writes clock64() at role events of its first tiles
   int knock;         // measurement only (env NC_KNOCK, results become WRONG): 1 = weight copies skipped after the ring

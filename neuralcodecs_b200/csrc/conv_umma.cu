@@ -343,39 +343,15 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
   const int tiles_per_n = p.batch * p.m_tiles_per_clip;
   const int total_tiles = p.n_tiles * tiles_per_n;
 
-  if (warp == 0) {
-    // ===================================================================== weight producer
-    if (elect_one()) {
-      int ws = 0, wcount = 0, it = 0;
-      uint32_t wph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        RU_TRACE(it, 15);
-        const int nt = tile % p.n_tiles;   // N tile fastest: the N tiles of one M tile run side by side, A re-reads hit L2
-        const unsigned mask = p.tap_mask[nt];
-        const float* wbase = p.W + (size_t)nt * p.tiles_per_ntile * (size_t)p.w_tile_floats;
-        for (int kci = 0; kci < p.n_kc; ++kci) {
-          const int kc = p.kc_begin + kci;
-          for (int j = 0; j < p.n_taps; ++j) {
-            if (!((mask >> j) & 1u) || kc < p.taps[j].kc_lo || kc >= p.taps[j].kc_hi) continue;
-            mbar_wait(&w_empty[ws], wph ^ 1u);
-            const size_t toff = (size_t)(p.taps[j].tile_base + (kc - p.taps[j].kc_lo)) * (size_t)p.w_tile_floats;
-            if ((L.knock & 1) && wcount >= L.w_stages) {
-              mbar_arrive(&w_full[ws]);
-            } else {
-              mbar_arrive_expect_tx(&w_full[ws], w_stage_bytes);
-              bulk_g2s(sW + (size_t)ws * w_stage_bytes, wbase + toff, w_stage_bytes, &w_full[ws]);
-            }
-            ++wcount;
-            if (++ws == L.w_stages) { ws = 0; wph ^= 1u; }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    // ONE elected lane runs the whole persistent loop (elect.sync tells ptxas the region is single-threaded,
-    // so descriptors go straight to uniform registers and each tcgen05.mma is a single UTCHMMA).
-    if (elect_one()) {
+  // ===================================================================== MMA issuer role
+  // One thread sustains one tcgen05.mma per ~80 clk whatever N is (profiles/r02_mma_issue_rate_probe.txt), which bounds every layer
+  // with N <= 128; two issuing warps double the rate.  With L.dual_issue (no residual tile to load, dense taps, one N tile, no
+  // folded partials) the otherwise idle residual-loader warp issues the odd tiles into accumulator 1 while warp 1 issues the even
+  // tiles into accumulator 0: both walk the same A / weight rings, their positions computed from the tile index.  Measured on the
+  // layers that qualify (Encodec's convs without a residual; job AM): results identical, time neutral to -2 % -- those layers are
+  // bound by their transform / epilogue warps, not by MMA issue -- so it is off by default (NC_DUAL_ISSUE=1); the layers that ARE
+  // issue-bound (the fused residual units) need their weight ring deepened or CTA pairs before a second issuer can help.
+  auto mma_role = [&](const int it0, const int it_step) {
       const uint32_t idesc = OPS == O_H16X3 ? idesc_f16(kBM, p.BN, p.mode == MODE_BF16X3 ? 1 : 0) : idesc_tf32(kBM, p.BN);
       const uint64_t a_desc0 = desc_at(smem_u32(sA));
       const uint64_t w_desc0 = (OPS == O_H16X3 && p.w_hi_only) ? (kDescSw64Base | (uint64_t)((smem_u32(sW) & 0x3FFFFu) >> 4))
@@ -383,12 +359,22 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
       const uint32_t a_stage_u = a_stage_bytes >> 4, w_stage_u = w_stage_bytes >> 4;   // descriptor units (16 B)
       const uint32_t a_lo_u = a_tile_bytes >> 4, w_lo_u = w_tile_bytes >> 4;
       const uint32_t tap_u = (uint32_t)p.dense_step * 8u;                             // rows * 128 B / 16
-      int ws = 0, as = 0, it = 0;
+      int ws = 0, as = 0, it = it0;
       uint32_t wph = 0, aph = 0;
       uint32_t pc = 0;   // accumulator partials issued so far (== tiles when nothing is folded)
       uint64_t a_desc = a_desc0, w_desc = w_desc0;
       const uint32_t lo_tmem = tmem_base + lo_col;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int n_w = p.n_kc * p.n_taps;   // weight stages per tile (dual issue only: dense taps, one N tile)
+      for (int tile = (int)blockIdx.x + it0 * (int)gridDim.x; tile < total_tiles; tile += it_step * (int)gridDim.x, it += it_step) {
+        if (it_step == 2) {
+          // dual issue: this thread takes every other tile, so the ring positions follow from the tile index
+          const long long sw = (long long)it * n_w, sa = (long long)it * p.n_kc;
+          ws = (int)(sw % L.w_stages); wph = (uint32_t)((sw / L.w_stages) & 1);
+          as = (int)(sa % L.a_stages); aph = (uint32_t)((sa / L.a_stages) & 1);
+          w_desc = w_desc0 + (uint64_t)ws * w_stage_u;
+          a_desc = a_desc0 + (uint64_t)as * a_stage_u;
+          pc = (uint32_t)it;
+        }
         if (s3) {   // the previous tile's epilogue has read the lo accumulator
           mbar_wait(&lo_empty, ((uint32_t)it & 1u) ^ 1u);
           tc_fence_after();
@@ -494,7 +480,41 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
           }
         }
       }
+  };
+
+  if (warp == 0) {
+    // ===================================================================== weight producer
+    if (elect_one()) {
+      int ws = 0, wcount = 0, it = 0;
+      uint32_t wph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        RU_TRACE(it, 15);
+        const int nt = tile % p.n_tiles;   // N tile fastest: the N tiles of one M tile run side by side, A re-reads hit L2
+        const unsigned mask = p.tap_mask[nt];
+        const float* wbase = p.W + (size_t)nt * p.tiles_per_ntile * (size_t)p.w_tile_floats;
+        for (int kci = 0; kci < p.n_kc; ++kci) {
+          const int kc = p.kc_begin + kci;
+          for (int j = 0; j < p.n_taps; ++j) {
+            if (!((mask >> j) & 1u) || kc < p.taps[j].kc_lo || kc >= p.taps[j].kc_hi) continue;
+            mbar_wait(&w_empty[ws], wph ^ 1u);
+            const size_t toff = (size_t)(p.taps[j].tile_base + (kc - p.taps[j].kc_lo)) * (size_t)p.w_tile_floats;
+            if ((L.knock & 1) && wcount >= L.w_stages) {
+              mbar_arrive(&w_full[ws]);
+            } else {
+              mbar_arrive_expect_tx(&w_full[ws], w_stage_bytes);
+              bulk_g2s(sW + (size_t)ws * w_stage_bytes, wbase + toff, w_stage_bytes, &w_full[ws]);
+            }
+            ++wcount;
+            if (++ws == L.w_stages) { ws = 0; wph ^= 1u; }
+          }
+        }
+      }
     }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    // ONE elected lane runs the whole persistent loop (elect.sync tells ptxas the region is single-threaded,
+    // so descriptors go straight to uniform registers and each tcgen05.mma is a single UTCHMMA).
+    if (elect_one()) mma_role(0, L.dual_issue ? 2 : 1);
   } else if (warp == kLoaderWarp) {
     // ===================================================================== A loader (TMA)
     if (elect_one()) {
@@ -522,8 +542,10 @@ conv_umma_kernel(const __grid_constant__ ConvGemmParams p, const UmmaLaunch L, c
       }
     }
   } else if (warp == kResidualWarp) {
-    // ===================================================================== residual loader (TMA)
-    if (L.tma_epilogue && p.R && elect_one()) {
+    // ===================================================================== second MMA issuer (dual issue) / residual loader (TMA)
+    if (L.dual_issue) {
+      if (elect_one()) mma_role(1, 2);
+    } else if (L.tma_epilogue && p.R && elect_one()) {
       const int groups = p.BN / 32;
       int es = 0;
       uint32_t eph = 0;
@@ -1576,6 +1598,9 @@ int launch_conv_umma(const ConvGemmParams& p_in, int num_sms, cudaStream_t strea
   L.knock = knock;
   static const int teams_env = getenv("NC_EPI_TEAMS") ? atoi(getenv("NC_EPI_TEAMS")) : 1;
   L.epi_teams = (teams_env && L.tma_epilogue && !p.acc_split && !p.noise && (!p.R || L.epi_stages == kMaxEpiStages)) ? 1 : 0;
+  static const int dual_env = getenv("NC_DUAL_ISSUE") ? atoi(getenv("NC_DUAL_ISSUE")) : 0;   // opt-in: measured neutral to -2 % (job AM)
+  L.dual_issue = (dual_env && L.tma_epilogue && !p.R && !p.acc_split && p.dense_step >= 0 && p.n_tiles == 1 && !p.dw_w && p.BN <= 128 &&
+                  L.w_stages >= p.n_kc * p.n_taps + 2 && L.a_stages >= p.n_kc + 1) ? 1 : 0;
   const int rows_needed = kBM + p.span;
   const int rit = (rows_needed + 31) / 32;
   if (rit > 6) return -1;
